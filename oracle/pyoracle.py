@@ -1,0 +1,292 @@
+"""ctypes binding of the parity oracle (oracle/libsp_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+ALPH = 21
+AA = "ACDEFGHIKLMNPQRSTVWYX"
+
+
+class Matrix(C.Structure):
+    _fields_ = [
+        ("alph", C.c_int),
+        ("aa2num", C.c_ubyte * 256),
+        ("num2aa", C.c_char * 32),
+        ("sub", (C.c_short * ALPH) * ALPH),
+        ("pBack", C.c_double * ALPH),
+        ("prob", (C.c_double * ALPH) * ALPH),
+        ("lambda_", C.c_double),
+    ]
+
+
+class Hit(C.Structure):
+    _fields_ = [("id", C.c_uint32), ("score", C.c_int32), ("diag", C.c_int32)]
+
+
+class PrefilterParams(C.Structure):
+    _fields_ = [
+        ("kmerThr", C.c_int),
+        ("maxSeqs", C.c_int),
+        ("minDiagScore", C.c_int),
+        ("binSize", C.c_int),
+        ("compBias", C.c_int),
+        ("pattern", C.c_char * 33),
+    ]
+
+
+class QueryStats(C.Structure):
+    _fields_ = [("kmers", C.c_uint64), ("dbMatches", C.c_uint64), ("events", C.c_uint64)]
+
+
+class Gumbel(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "lambda_", "K", "a_I", "b_I", "alpha_I", "beta_I", "a_J", "b_J", "alpha_J", "beta_J", "sigma", "tau")]
+
+
+class AlignParams(C.Structure):
+    _fields_ = [
+        ("gapOpen", C.c_int), ("gapExtend", C.c_int),
+        ("evalThr", C.c_double),
+        ("dbResCount", C.c_uint64),
+        ("compBias", C.c_int),
+        ("byteLanes", C.c_int), ("wordLanes", C.c_int),
+        ("g", Gumbel),
+    ]
+
+
+class Aln(C.Structure):
+    _fields_ = [
+        ("ok", C.c_int), ("score", C.c_int), ("bits", C.c_int), ("eval", C.c_double),
+        ("qStart", C.c_int), ("qEnd", C.c_int), ("tStart", C.c_int), ("tEnd", C.c_int),
+        ("nIdent", C.c_int), ("alnLen", C.c_int), ("seqId", C.c_float),
+        ("cigar", C.c_char * 1024),
+    ]
+
+
+# ALP parameters of VTML40, gap open 16 / extend 2 (probed from the reference)
+GUMBEL_VTML40_16_2 = dict(
+    lambda_=0.34420393530174209, K=0.27487374979561635,
+    a_I=0.22018895496520485, b_I=0.026237512825550646,
+    alpha_I=0.18481499377626534, beta_I=1.7126891360391483,
+    a_J=0.22018895496520485, b_J=0.026237512825550646,
+    alpha_J=0.18481499377626534, beta_J=1.7126891360391483,
+    sigma=0.18283871043913499, tau=1.7838353361758408)
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libsp_oracle.so")
+    src = [os.path.join(_HERE, f) for f in ("sp_oracle.c", "sp_oracle.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "libsp_oracle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    L = C.CDLL(build())
+    u8p = C.POINTER(C.c_ubyte)
+    L.spo_matrix_parse.argtypes = [C.c_char_p, C.c_double, C.c_double, C.POINTER(Matrix)]
+    L.spo_matrix_parse.restype = C.c_int
+    L.spo_comp_bias.argtypes = [C.POINTER(Matrix), u8p, C.c_int, C.POINTER(C.c_float)]
+    L.spo_tantan_mask.argtypes = [C.POINTER(Matrix), u8p, C.c_int]
+    L.spo_tantan_mask.restype = C.c_int
+    L.spo_kmer_threshold.argtypes = [C.c_float]
+    L.spo_kmer_threshold.restype = C.c_int
+    L.spo_prefilter_create.argtypes = [u8p, C.POINTER(C.c_uint64), C.c_uint32, C.POINTER(Matrix),
+                                       C.POINTER(Matrix), C.POINTER(PrefilterParams)]
+    L.spo_prefilter_create.restype = C.c_void_p
+    L.spo_prefilter_destroy.argtypes = [C.c_void_p]
+    L.spo_prefilter_num_postings.argtypes = [C.c_void_p]
+    L.spo_prefilter_num_postings.restype = C.c_uint64
+    L.spo_prefilter_postings.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.spo_prefilter_query.argtypes = [C.c_void_p, u8p, C.c_int, C.POINTER(Hit), C.POINTER(QueryStats)]
+    L.spo_prefilter_query.restype = C.c_int
+    L.spo_prefilter_batch.argtypes = [C.c_void_p, u8p, C.POINTER(C.c_uint64), C.c_uint32,
+                                      C.POINTER(C.c_uint64), C.POINTER(Hit), C.c_int]
+    L.spo_similar_kmers.argtypes = [C.c_void_p, u8p, C.c_int, C.POINTER(C.c_uint32), C.c_int]
+    L.spo_similar_kmers.restype = C.c_int
+    L.spo_evalue.argtypes = [C.POINTER(Gumbel), C.c_double, C.c_double, C.c_double]
+    L.spo_evalue.restype = C.c_double
+    L.spo_bitscore.argtypes = [C.POINTER(Gumbel), C.c_double]
+    L.spo_bitscore.restype = C.c_double
+    L.spo_align_pair.argtypes = [C.POINTER(Matrix), C.POINTER(AlignParams), u8p, C.c_int, u8p, C.c_int,
+                                 C.POINTER(Aln)]
+    L.spo_sw_forward.argtypes = [C.POINTER(Matrix), C.POINTER(AlignParams), u8p, C.c_int, u8p, C.c_int,
+                                 C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.spo_format_row.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(Aln), C.c_int, C.c_int]
+    L.spo_format_row.restype = C.c_int
+    _LIB = L
+    return L
+
+
+def _u8(a):
+    return a.ctypes.data_as(C.POINTER(C.c_ubyte))
+
+
+def parse_matrix(text, bit_factor, score_bias):
+    m = Matrix()
+    if isinstance(text, str):
+        text = text.encode()
+    rc = lib().spo_matrix_parse(text, bit_factor, score_bias, C.byref(m))
+    if rc != 0:
+        raise ValueError("spo_matrix_parse failed: %d" % rc)
+    return m
+
+
+def matrix_sub(m):
+    return np.array([[m.sub[i][j] for j in range(ALPH)] for i in range(ALPH)], dtype=np.int16)
+
+
+def matrix_pback(m):
+    return np.array([m.pBack[i] for i in range(ALPH)], dtype=np.float64)
+
+
+def encode(seq, m=None):
+    """ASCII residues -> numeric (Sequence::mapSequence)."""
+    if m is None:
+        tab = np.full(256, 20, dtype=np.uint8)
+        for i, c in enumerate(AA):
+            tab[ord(c)] = i
+            tab[ord(c.lower())] = i
+        for c, d in (("J", "L"), ("Z", "E"), ("B", "D")):
+            tab[ord(c)] = tab[ord(c.lower())] = AA.index(d)
+    else:
+        tab = np.frombuffer(bytes(m.aa2num), dtype=np.uint8)
+    return tab[np.frombuffer(seq.encode() if isinstance(seq, str) else seq, dtype=np.uint8)].copy()
+
+
+def comp_bias(m, seq):
+    seq = np.ascontiguousarray(seq, dtype=np.uint8)
+    out = np.zeros(len(seq), dtype=np.float32)
+    lib().spo_comp_bias(C.byref(m), _u8(seq), len(seq), out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out
+
+
+def tantan_mask(m80, seq):
+    seq = np.array(seq, dtype=np.uint8, copy=True)
+    n = lib().spo_tantan_mask(C.byref(m80), _u8(seq), len(seq))
+    return seq, n
+
+
+def concat(seqs):
+    """list of uint8 arrays -> (residues, offsets[T+1] uint64)."""
+    lens = np.array([len(s) for s in seqs], dtype=np.uint64)
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    res = np.concatenate(seqs).astype(np.uint8) if len(seqs) else np.zeros(0, dtype=np.uint8)
+    return np.ascontiguousarray(res), off
+
+
+class Prefilter:
+    def __init__(self, tres, toff, m80, m40u, kmer_thr=112, max_seqs=300, min_diag=15, bin_size=2,
+                 comp_bias=1, pattern="11011101"):
+        self.tres = np.ascontiguousarray(tres, dtype=np.uint8)
+        self.toff = np.ascontiguousarray(toff, dtype=np.uint64)
+        self.m80, self.m40u = m80, m40u
+        self.p = PrefilterParams(kmer_thr, max_seqs, min_diag, bin_size, comp_bias, pattern.encode())
+        self.T = len(self.toff) - 1
+        self.h = lib().spo_prefilter_create(_u8(self.tres), self.toff.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                            self.T, C.byref(m80), C.byref(m40u), C.byref(self.p))
+        if not self.h:
+            raise ValueError("spo_prefilter_create failed")
+
+    def close(self):
+        if self.h:
+            lib().spo_prefilter_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def postings(self):
+        n = lib().spo_prefilter_num_postings(self.h)
+        k = np.zeros(n, dtype=np.uint32)
+        i = np.zeros(n, dtype=np.uint32)
+        p = np.zeros(n, dtype=np.uint16)
+        lib().spo_prefilter_postings(self.h, k.ctypes.data, i.ctypes.data, p.ctypes.data)
+        return k, i, p
+
+    def similar(self, kmer6, thr, cap=1 << 20):
+        kmer6 = np.ascontiguousarray(kmer6, dtype=np.uint8)
+        out = np.zeros(cap, dtype=np.uint32)
+        n = lib().spo_similar_kmers(self.h, _u8(kmer6), thr, out.ctypes.data_as(C.POINTER(C.c_uint32)), cap)
+        return out[:n].copy()
+
+    def query(self, q):
+        q = np.ascontiguousarray(q, dtype=np.uint8)
+        out = (Hit * max(1, self.p.maxSeqs))()
+        st = QueryStats()
+        n = lib().spo_prefilter_query(self.h, _u8(q), len(q), out, C.byref(st))
+        return [(out[i].id, out[i].score, out[i].diag) for i in range(n)], st
+
+    def batch(self, qres, qoff, threads=0):
+        qres = np.ascontiguousarray(qres, dtype=np.uint8)
+        qoff = np.ascontiguousarray(qoff, dtype=np.uint64)
+        Q = len(qoff) - 1
+        off = np.zeros(Q + 1, dtype=np.uint64)
+        hits = np.zeros(max(1, Q * self.p.maxSeqs), dtype=[("id", "<u4"), ("score", "<i4"), ("diag", "<i4")])
+        lib().spo_prefilter_batch(self.h, _u8(qres), qoff.ctypes.data_as(C.POINTER(C.c_uint64)), Q,
+                                  off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                  hits.ctypes.data_as(C.POINTER(Hit)), threads)
+        return off, hits[: int(off[-1])]
+
+
+def align_params(db_res_count, gap_open=16, gap_extend=2, eval_thr=200.0, comp_bias=1, gumbel=None,
+                 byte_lanes=32, word_lanes=16):
+    g = Gumbel(**(gumbel or GUMBEL_VTML40_16_2))
+    return AlignParams(gap_open, gap_extend, eval_thr, db_res_count, comp_bias, byte_lanes, word_lanes, g)
+
+
+def align_pair(m40, p, q, t):
+    q = np.ascontiguousarray(q, dtype=np.uint8)
+    t = np.ascontiguousarray(t, dtype=np.uint8)
+    a = Aln()
+    lib().spo_align_pair(C.byref(m40), C.byref(p), _u8(q), len(q), _u8(t), len(t), C.byref(a))
+    return a
+
+
+def sw_forward(m40, p, q, t):
+    q = np.ascontiguousarray(q, dtype=np.uint8)
+    t = np.ascontiguousarray(t, dtype=np.uint8)
+    s, qe, te, w = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    lib().spo_sw_forward(C.byref(m40), C.byref(p), _u8(q), len(q), _u8(t), len(t),
+                         C.byref(s), C.byref(qe), C.byref(te), C.byref(w))
+    return s.value, qe.value, te.value, w.value
+
+
+def format_row(tkey, a, qlen, tlen):
+    buf = C.create_string_buffer(2048)
+    n = lib().spo_format_row(buf, tkey, C.byref(a), qlen, tlen)
+    return buf.raw[:n].decode()
+
+
+def evalue(score, qlen, db_res, gumbel=None):
+    g = Gumbel(**(gumbel or GUMBEL_VTML40_16_2))
+    return lib().spo_evalue(C.byref(g), float(score), float(qlen), float(db_res))
+
+
+def bitscore(score, gumbel=None):
+    g = Gumbel(**(gumbel or GUMBEL_VTML40_16_2))
+    return lib().spo_bitscore(C.byref(g), float(score))
+
+
+def align_query(m40, p, q, targets, keys):
+    """Align q against each (target residues, key); returns rows sorted like Matcher::compareHits."""
+    res = []
+    for t, key in zip(targets, keys):
+        a = align_pair(m40, p, q, t)
+        if a.ok == 1:
+            res.append((a.eval, -a.bits, len(t), key, format_row(key, a, len(q), len(t))))
+    res.sort(key=lambda r: r[:4])
+    return [r[4] for r in res]
