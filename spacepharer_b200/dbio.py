@@ -1,0 +1,80 @@
+"""Minimal MMseqs2 on-disk DB helpers (Python side: tests, bench and the Python mirror).
+
+Format (M/commons/DBReader.h:57-99, DBWriter.cpp:216-440): `<name>` holds NUL-terminated entries,
+`<name>.index` text lines `key\\toffset\\tlength` (length includes the NUL), `<name>.dbtype` a 4-byte
+little-endian int (0 amino acids, 5 alignment results, 7 prefilter results).  Multi-threaded writers
+may leave `<name>.0 .. <name>.N-1` whose offsets live in the concatenated space.  The native reader /
+writer used by the spb200 binary is spacepharer_b200/csrc/host/db_io.cpp.
+"""
+import glob
+import os
+import struct
+
+import numpy as np
+
+DBTYPE_AMINO_ACIDS = 0
+DBTYPE_ALIGNMENT_RES = 5
+DBTYPE_PREFILTER_RES = 7
+
+
+def read_db(name):
+    """-> (keys uint32[n], offsets int64[n], lengths int64[n], data bytes); index sorted by key."""
+    if os.path.exists(name):
+        data = open(name, "rb").read()
+    else:
+        parts = sorted(glob.glob(name + ".[0-9]*"), key=lambda x: int(x.rsplit(".", 1)[1]))
+        parts = [p for p in parts if p.rsplit(".", 1)[1].isdigit()]
+        if not parts:
+            raise FileNotFoundError(name)
+        data = b"".join(open(p, "rb").read() for p in parts)
+    rows = [tuple(int(x) for x in line.split()[:3]) for line in open(name + ".index") if line.strip()]
+    rows.sort()
+    a = np.array(rows, dtype=np.int64).reshape(-1, 3)
+    return a[:, 0].astype(np.uint32), a[:, 1].copy(), a[:, 2].copy(), data
+
+
+def read_dbtype(name):
+    with open(name + ".dbtype", "rb") as f:
+        return struct.unpack("<i", f.read(4))[0]
+
+
+def read_entries(name):
+    keys, off, ln, data = read_db(name)
+    return {int(k): data[o:o + l - 1] for k, o, l in zip(keys, off, ln)}
+
+
+def read_sequence_db(name):
+    """Sequence DB -> (keys in LINEAR_ACCESS order (by offset, DBReader.cpp:339-368), list of ASCII residue bytes).
+    Entries are `residues\\n\\0`, seqLen = length - 2 (DBReader.h:191-213)."""
+    keys, off, ln, data = read_db(name)
+    order = np.argsort(off, kind="stable")
+    seqs = [data[int(off[i]):int(off[i]) + int(ln[i]) - 2] for i in order]
+    return keys[order], seqs
+
+
+def amino_acid_db_size(name):
+    """DBReader::getAminoAcidDBSize (DBReader.cpp:541-550): data bytes - 2 * entries."""
+    keys, off, ln, data = read_db(name)
+    return int(ln.sum()) - 2 * len(keys)
+
+
+def write_db(name, entries, dbtype):
+    """entries: iterable of (key, payload bytes without NUL) in write order."""
+    pos = 0
+    idx = []
+    with open(name, "wb") as f:
+        for k, payload in entries:
+            f.write(payload)
+            f.write(b"\0")
+            idx.append((int(k), pos, len(payload) + 1))
+            pos += len(payload) + 1
+    idx.sort()
+    with open(name + ".index", "w") as f:
+        for k, o, l in idx:
+            f.write("%d\t%d\t%d\n" % (k, o, l))
+    with open(name + ".dbtype", "wb") as f:
+        f.write(struct.pack("<i", dbtype))
+
+
+def write_sequence_db(name, keys, seqs):
+    write_db(name, ((k, s + b"\n") for k, s in zip(keys, seqs)), DBTYPE_AMINO_ACIDS)
