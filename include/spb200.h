@@ -1,0 +1,173 @@
+/*
+ * spb200.h -- C ABI of the B200-native SpacePHARER search hot path (prefilter + align).
+ *
+ * The reference (soedinglab/spacepharer, MMseqs2 vendored under lib/mmseqs/src = "M/") has no FFI:
+ * its seam for this path is the module CLI + on-disk DB format.  The entry points below
+ * are the batched equivalents of the reference's internal per-query seams, which a maintainer would
+ * bind from M/prefiltering/Prefiltering.cpp and M/alignment/Alignment.cpp:
+ *
+ *   spb_index_build        <->  IndexBuilder::fillDatabase            M/prefiltering/IndexBuilder.cpp:53-256
+ *                               + ExtendedSubstitutionMatrix::calcScoreMatrix  ExtendedSubstitutionMatrix.cpp:20-69
+ *   spb_prefilter          <->  QueryMatcher::matchQuery(Sequence*, identityId, isNucl) -> (hit_t*, n)
+ *                                                                     M/prefiltering/QueryMatcher.h:64, .cpp:84-186
+ *   spb_align_set_targets  <->  tdbr->getData()/Sequence::mapSequence  M/alignment/Alignment.cpp:386-392
+ *   spb_align              <->  Matcher::initQuery + Matcher::getSWResult -> result_t
+ *                                                                     M/alignment/Matcher.h:152-153, Matcher.cpp:61-187
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every input buffer (host memory; pinned
+ * memory makes the copies asynchronous); the library owns outputs until the matching spb_free_* call;
+ * every function returns 0 on success, non-zero on failure with spb_last_error() describing it (the host
+ * `main` turns that into the reference's Debug(Debug::ERROR)...EXIT(EXIT_FAILURE) behaviour).  No C++
+ * exceptions cross this boundary.  A context is bound to one CUDA device and is not thread-safe (one
+ * host thread per context, like one QueryMatcher / Matcher per OpenMP thread in the reference).
+ * There is no CPU fallback: without a CUDA device spb_ctx_create fails.
+ */
+#ifndef SPB200_H
+#define SPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPB_ALPHABET 21   /* ACDEFGHIKLMNPQRSTVWYX, X = 20 (lib/mmseqs/data/VTML40.out:13) */
+
+typedef struct spb_ctx spb_ctx;
+
+/* ---- life cycle ------------------------------------------------------------------------------- */
+int spb_ctx_create(int device, spb_ctx **out);
+void spb_ctx_destroy(spb_ctx *ctx);
+const char *spb_last_error(void);
+const char *spb_version(void);
+/* the CUDA stream all work of this context is enqueued on (cudaStream_t as void*) */
+void *spb_ctx_stream(spb_ctx *ctx);
+
+/* ---- substitution matrices ---------------------------------------------------------------------
+ * int16 scores as the reference's SubstitutionMatrix produces them (row-major [21][21]):
+ *   sub_seed     k-mer matrix      VTML80, bit factor 8, bias -0.2   M/prefiltering/Prefiltering.cpp:64
+ *   sub_ungapped ungapped matrix   VTML40, bit factor 2, bias -0.2   M/prefiltering/Prefiltering.cpp:65
+ *   sub_align    alignment matrix  VTML40, bit factor 2, bias  0     M/alignment/Alignment.cpp:159
+ * pback_* = BaseMatrix::pBack of the seed / alignment matrix (composition-bias correction). */
+int spb_set_matrices(spb_ctx *ctx, const int16_t *sub_seed, const double *pback_seed,
+                     const int16_t *sub_ungapped, const int16_t *sub_align, const double *pback_align);
+
+/* ---- target index ------------------------------------------------------------------------------
+ * residues: numeric target residues (0..20) as the index must see them, i.e. already tantan-masked when
+ * --mask 1 (host pre-step, M/prefiltering/IndexBuilder.cpp:137-149); offsets[T+1]; ids are positions in
+ * this array (DBReader LINEAR_ACCESS order).  pattern: spaced k-mer pattern with six '1' ("11011101").
+ * kmer_thr: index-side self-score threshold (M/prefiltering/Prefiltering.cpp:510-513).
+ * Builds, resident in HBM: masked residue store (SequenceLookup), k-mer -> sorted (id,pos) postings
+ * (IndexTable) and the 3-mer similarity rows (ScoreMatrix). */
+int spb_index_build(spb_ctx *ctx, const uint8_t *residues, const uint64_t *offsets, uint32_t T,
+                    const char *pattern, int kmer_thr);
+
+typedef struct spb_index_stats {
+    uint64_t n_targets, n_residues, n_postings, n_kmers_nonempty;
+    uint64_t bytes_device;      /* HBM held by the index */
+    double build_ms;            /* device time of the last build */
+} spb_index_stats;
+int spb_index_stats_get(spb_ctx *ctx, spb_index_stats *out);
+/* copy the postings out as sorted (kmer, id, pos) triples; arrays sized n_postings (test hook) */
+int spb_index_export(spb_ctx *ctx, uint32_t *kmer, uint32_t *id, uint16_t *pos);
+/* similar k-mer list of one 6-mer at threshold thr (test hook for KmerGenerator parity); returns count in *n */
+int spb_similar_kmers(spb_ctx *ctx, const uint8_t *kmer6, int thr, uint32_t *out, uint32_t cap, uint32_t *n);
+
+/* ---- prefilter --------------------------------------------------------------------------------- */
+typedef struct spb_prefilter_params {
+    int32_t kmer_thr;        /* -s 5.7 => 112 (Prefiltering::getKmerThreshold) */
+    int32_t max_seqs;        /* --max-seqs (300) */
+    int32_t min_diag_score;  /* --min-ungapped-score (15) */
+    int32_t bin_size;        /* CacheFriendlyOperations BINSIZE of the emulated host (2..2048, power of 2);
+                                M/prefiltering/QueryMatcher.cpp:383-411 -- only affects tie order under truncation */
+    int32_t comp_bias;       /* --comp-bias-corr */
+    uint32_t id_base;        /* added to local target ids for tie-order purposes (target shards) */
+} spb_prefilter_params;
+
+typedef struct spb_hit {     /* hit_t, M/prefiltering/QueryMatcher.h:35-52 */
+    uint32_t id;             /* target index (position in the array given to spb_index_build) */
+    int32_t score;           /* ungapped diagonal score */
+    int32_t diag;            /* (short) diagonal */
+} spb_hit;
+
+typedef struct spb_prefilter_result {
+    uint32_t n_queries;
+    uint64_t *offsets;       /* [n_queries+1] */
+    spb_hit *hits;           /* sorted per query by (score desc, id asc) like compareHitsByScoreAndId */
+    uint64_t n_hits;
+    /* counters (Prefiltering.cpp:934-957 prints the same statistics) */
+    uint64_t n_kmers, n_db_matches, n_events, n_slow_path;
+    double kernel_ms;        /* device time of the match kernel(s) */
+    uint64_t algo_bytes;     /* algorithmic bytes moved by the match kernel */
+} spb_prefilter_result;
+
+int spb_prefilter(spb_ctx *ctx, const uint8_t *q_residues, const uint64_t *q_offsets, uint32_t Q,
+                  const spb_prefilter_params *p, spb_prefilter_result **out);
+void spb_free_prefilter_result(spb_prefilter_result *r);
+
+/* ---- alignment --------------------------------------------------------------------------------- */
+typedef struct spb_gumbel {  /* ALP parameter set (lib/mmseqs/lib/alp/sls_alignment_evaluer.hpp) */
+    double lambda, K, a_I, b_I, alpha_I, beta_I, a_J, b_J, alpha_J, beta_J, sigma, tau;
+} spb_gumbel;
+
+typedef struct spb_align_params {
+    int32_t gap_open, gap_extend;   /* aa:16 / 2 */
+    double eval_thr;                /* -e */
+    uint64_t db_res_count;          /* DBReader::getAminoAcidDBSize of the WHOLE target DB (Alignment.cpp:269) */
+    int32_t comp_bias;
+    int32_t byte_lanes, word_lanes; /* SIMD layout of the emulated reference build: 32/16 (AVX2), 16/8 (SSE) */
+    spb_gumbel gumbel;
+} spb_align_params;
+
+typedef struct spb_aln {     /* Matcher::result_t, M/alignment/Matcher.h:24-119 */
+    uint32_t query;          /* query index in the batch */
+    uint32_t target;         /* target index */
+    int32_t score;           /* raw Smith-Waterman score */
+    int32_t bits;            /* (int)(bitScore + 0.5) */
+    double eval;
+    int32_t q_start, q_end, t_start, t_end;   /* 0-based inclusive */
+    int32_t n_ident, aln_len;
+    float seq_id;
+    uint32_t cigar_off, cigar_len;  /* slice of spb_align_result::cigar_ops (one op char per column: M/I/D) */
+} spb_aln;
+
+typedef struct spb_align_result {
+    uint32_t n_queries;
+    uint64_t *offsets;       /* [n_queries+1] accepted rows per query */
+    spb_aln *rows;           /* per query sorted like Matcher::compareHits (eval asc, bits desc, tLen asc, id asc) */
+    uint64_t n_rows;
+    char *cigar_ops;
+    uint64_t n_cigar;
+    uint64_t n_pairs, n_cells;      /* pairs aligned, forward-pass cells (sum qLen*tLen) */
+    double kernel_ms;               /* device time of the forward-pass kernel(s) */
+    double total_ms;
+} spb_align_result;
+
+/* unmasked numeric target residues (align reads the raw DB, not the masked lookup).  keys (nullable): DB key of
+ * every target, used only as the last tie-break of the row order (Matcher::compareHits sorts by dbKey). */
+int spb_align_set_targets(spb_ctx *ctx, const uint8_t *residues, const uint64_t *offsets, uint32_t T,
+                          const uint32_t *keys);
+/* pairs given CSR-style: query i is aligned against pair_targets[pair_offsets[i] .. pair_offsets[i+1]) */
+int spb_align(spb_ctx *ctx, const uint8_t *q_residues, const uint64_t *q_offsets, uint32_t Q,
+              const uint64_t *pair_offsets, const uint32_t *pair_targets,
+              const spb_align_params *p, spb_align_result **out);
+void spb_free_align_result(spb_align_result *r);
+
+/* E-value / bit score of one raw score on the device path's formula, evaluated on the host in double
+ * (EvalueComputation::computeEvalue / computeBitScore, M/alignment/EvalueComputation.h:18-40) */
+double spb_evalue(const spb_gumbel *g, double score, double q_len, double db_res_count);
+double spb_bitscore(const spb_gumbel *g, double score);
+
+/* ---- host pre-step (CPU, as in the reference) -----------------------------------------------------
+ * tantan repeat masking of the target residues before the index build (--mask 1; call site
+ * M/prefiltering/IndexBuilder.cpp:137-149, M/commons/tantan.cpp).  prob = joint probabilities P_ab [21][21] and
+ * pback[21] of the seed matrix (BaseMatrix::probMatrix / pBack).  Masks in place (residue -> X); OpenMP over
+ * targets.  Not a device fallback: the reference keeps this O(50 x residues) double-precision HMM on the host too. */
+int spb_tantan_mask(const double *prob, const double *pback, uint8_t *residues, const uint64_t *offsets, uint32_t T,
+                    int threads, uint64_t *n_masked);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,244 @@
+"""Host-side mirror of the reference's prefilter / align operators over the C ABI.
+
+`Searcher` plays the role of Prefiltering + Alignment (M/prefiltering/Prefiltering.cpp,
+M/alignment/Alignment.cpp) for one target DB on one GPU: same parameter names and meaning as the
+module flags (-s, -k, --max-seqs, --min-ungapped-score, --comp-bias-corr, -e, --gap-open,
+--gap-extend), same error behaviour (exceptions instead of EXIT), results in the reference's row
+layouts.  All arithmetic of the hot path runs in libspb200's CUDA kernels; there is no CPU path.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import capi, matrices
+from .submat import SubMat
+
+# ALP Gumbel parameter sets (M/alignment/EvalueComputation.h:56-75 table + the VTML40 16/2 set the
+# reference estimates at start-up with seed 42).  Order: lambda K a_I b_I alpha_I beta_I
+# a_J b_J alpha_J beta_J sigma tau.
+GUMBEL = {
+    ("VTML40.out", 16, 2): (0.34420393530174209, 0.27487374979561635, 0.22018895496520485, 0.026237512825550646,
+                            0.18481499377626534, 1.7126891360391483, 0.22018895496520485, 0.026237512825550646,
+                            0.18481499377626534, 1.7126891360391483, 0.18283871043913499, 1.7838353361758408),
+    ("blosum62.out", 11, 1): (0.27359865037097330642, 0.044620920658722244834, 1.5938724404943873658,
+                              -19.959867650284412122, 30.455610143099914211, -622.28684628915891608,
+                              1.5938724404943873658, -19.959867650284412122, 30.455610143099914211,
+                              -622.28684628915891608, 29.602444874818868215, -601.81087985041381216),
+}
+
+
+def kmer_threshold(sensitivity, kmer_size=6):
+    """Prefiltering::getKmerThreshold (M/prefiltering/Prefiltering.cpp:987-1021), sequence search."""
+    if kmer_size != 6:
+        raise ValueError("only k = 6 is supported")
+    base = float(np.float32(163.2))
+    return int(base - float(np.float32(sensitivity)) * 8.917)
+
+
+def gumbel_for(matrix_name, gap_open, gap_extend):
+    key = (matrix_name, int(gap_open), int(gap_extend))
+    if key not in GUMBEL:
+        raise capi.SpbError("no Gumbel parameters for %s gap open %d extend %d: obtain them from the ALP estimator "
+                            "of the reference run and pass gumbel=..." % key)
+    return GUMBEL[key]
+
+
+def _u8(a):
+    return a.ctypes.data_as(C.POINTER(C.c_ubyte))
+
+
+def _u64(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint64))
+
+
+def tantan_mask(seed, tres, toff, threads=0):
+    """Host pre-step of the index build (--mask 1): returns (masked copy of tres, number of masked residues)."""
+    import os
+    lib = capi.load()
+    tres = np.array(tres, dtype=np.uint8, copy=True)
+    toff = np.ascontiguousarray(toff, dtype=np.uint64)
+    prob = np.ascontiguousarray(seed.prob, dtype=np.float64)
+    pb = np.ascontiguousarray(seed.pback, dtype=np.float64)
+    n = C.c_uint64()
+    f64 = C.POINTER(C.c_double)
+    capi.check(lib.spb_tantan_mask(prob.ctypes.data_as(f64), pb.ctypes.data_as(f64), _u8(tres), _u64(toff),
+                                   len(toff) - 1, threads or (os.cpu_count() or 1), C.byref(n)))
+    return tres, int(n.value)
+
+
+class Searcher:
+    def __init__(self, device=0, sub_mat="VTML40.out", seed_sub_mat="VTML80.out", score_bias=0.0):
+        self.lib = capi.load()
+        self.seed = SubMat(matrices.matrix_text(seed_sub_mat), 8.0, -0.2)          # Prefiltering.cpp:64
+        self.ungapped = SubMat(matrices.matrix_text(sub_mat), 2.0, -0.2)           # Prefiltering.cpp:65
+        self.align_mat = SubMat(matrices.matrix_text(sub_mat), 2.0, score_bias)    # Alignment.cpp:159
+        self.sub_mat_name = sub_mat.split("/")[-1]
+        h = C.c_void_p()
+        capi.check(self.lib.spb_ctx_create(device, C.byref(h)))
+        self.h = h
+        s80 = np.ascontiguousarray(self.seed.sub, dtype=np.int16)
+        s40u = np.ascontiguousarray(self.ungapped.sub, dtype=np.int16)
+        s40 = np.ascontiguousarray(self.align_mat.sub, dtype=np.int16)
+        p80 = np.ascontiguousarray(self.seed.pback, dtype=np.float64)
+        p40 = np.ascontiguousarray(self.align_mat.pback, dtype=np.float64)
+        i16 = C.POINTER(C.c_int16)
+        f64 = C.POINTER(C.c_double)
+        capi.check(self.lib.spb_set_matrices(h, s80.ctypes.data_as(i16), p80.ctypes.data_as(f64),
+                                             s40u.ctypes.data_as(i16), s40.ctypes.data_as(i16),
+                                             p40.ctypes.data_as(f64)))
+        self.T = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.spb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- index -------------------------------------------------------------------------------
+    def build_index(self, tres, toff, kmer_thr=112, pattern="11011101"):
+        """tres: masked numeric residues (uint8), toff: uint64[T+1]"""
+        tres = np.ascontiguousarray(tres, dtype=np.uint8)
+        toff = np.ascontiguousarray(toff, dtype=np.uint64)
+        self.T = len(toff) - 1
+        capi.check(self.lib.spb_index_build(self.h, _u8(tres), _u64(toff), self.T, pattern.encode(), kmer_thr))
+        return self.index_stats()
+
+    def index_stats(self):
+        st = capi.IndexStats()
+        capi.check(self.lib.spb_index_stats_get(self.h, C.byref(st)))
+        return {f: getattr(st, f) for f, _ in st._fields_}
+
+    def export_index(self):
+        n = self.index_stats()["n_postings"]
+        k = np.zeros(n, dtype=np.uint32)
+        i = np.zeros(n, dtype=np.uint32)
+        p = np.zeros(n, dtype=np.uint16)
+        capi.check(self.lib.spb_index_export(self.h, k.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                             i.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                             p.ctypes.data_as(C.POINTER(C.c_uint16))))
+        return k, i, p
+
+    def similar_kmers(self, kmer6, thr, cap=1 << 20):
+        kmer6 = np.ascontiguousarray(kmer6, dtype=np.uint8)
+        out = np.zeros(cap, dtype=np.uint32)
+        n = C.c_uint32()
+        capi.check(self.lib.spb_similar_kmers(self.h, _u8(kmer6), thr, out.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                              cap, C.byref(n)))
+        return out[: min(n.value, cap)].copy()
+
+    # ---- prefilter ---------------------------------------------------------------------------
+    def prefilter(self, qres, qoff, kmer_thr=112, max_seqs=300, min_ungapped_score=15, bin_size=2, comp_bias=1,
+                  id_base=0):
+        """-> (offsets uint64[Q+1], hits structured array (id, score, diag), stats dict)"""
+        qres = np.ascontiguousarray(qres, dtype=np.uint8)
+        qoff = np.ascontiguousarray(qoff, dtype=np.uint64)
+        Q = len(qoff) - 1
+        p = capi.PrefilterParams(kmer_thr, max_seqs, min_ungapped_score, bin_size, comp_bias, id_base)
+        r = C.POINTER(capi.PrefilterResult)()
+        capi.check(self.lib.spb_prefilter(self.h, _u8(qres), _u64(qoff), Q, C.byref(p), C.byref(r)))
+        try:
+            R = r.contents
+            off = np.ctypeslib.as_array(R.offsets, shape=(Q + 1,)).copy()
+            n = int(R.n_hits)
+            dt = np.dtype([("id", "<u4"), ("score", "<i4"), ("diag", "<i4")])
+            hits = np.frombuffer(C.string_at(R.hits, n * 12), dtype=dt).copy() if n else np.zeros(0, dtype=dt)
+            stats = dict(n_kmers=int(R.n_kmers), n_db_matches=int(R.n_db_matches), n_events=int(R.n_events),
+                         n_slow_path=int(R.n_slow_path), kernel_ms=float(R.kernel_ms), algo_bytes=int(R.algo_bytes))
+        finally:
+            self.lib.spb_free_prefilter_result(r)
+        return off, hits, stats
+
+    # ---- align -------------------------------------------------------------------------------
+    def set_align_targets(self, tres, toff, keys=None):
+        tres = np.ascontiguousarray(tres, dtype=np.uint8)
+        toff = np.ascontiguousarray(toff, dtype=np.uint64)
+        kp = None
+        if keys is not None:
+            keys = np.ascontiguousarray(keys, dtype=np.uint32)
+            kp = keys.ctypes.data_as(C.POINTER(C.c_uint32))
+        self.aT = len(toff) - 1
+        self.a_toff = toff
+        self.a_keys = keys
+        capi.check(self.lib.spb_align_set_targets(self.h, _u8(tres), _u64(toff), self.aT, kp))
+
+    def align(self, qres, qoff, pair_off, pair_targets, db_res_count, evalue=200.0, gap_open=16, gap_extend=2,
+              comp_bias=1, gumbel=None, byte_lanes=32, word_lanes=16):
+        """-> (offsets uint64[Q+1], rows structured array, cigar bytes, stats)"""
+        qres = np.ascontiguousarray(qres, dtype=np.uint8)
+        qoff = np.ascontiguousarray(qoff, dtype=np.uint64)
+        pair_off = np.ascontiguousarray(pair_off, dtype=np.uint64)
+        pair_targets = np.ascontiguousarray(pair_targets, dtype=np.uint32)
+        Q = len(qoff) - 1
+        g = capi.Gumbel(*(gumbel or gumbel_for(self.sub_mat_name, gap_open, gap_extend)))
+        p = capi.AlignParams(gap_open, gap_extend, evalue, db_res_count, comp_bias, byte_lanes, word_lanes, g)
+        r = C.POINTER(capi.AlignResult)()
+        capi.check(self.lib.spb_align(self.h, _u8(qres), _u64(qoff), Q, _u64(pair_off),
+                                      pair_targets.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(p), C.byref(r)))
+        try:
+            R = r.contents
+            off = np.ctypeslib.as_array(R.offsets, shape=(Q + 1,)).copy()
+            n = int(R.n_rows)
+            dt = np.dtype([("query", "<u4"), ("target", "<u4"), ("score", "<i4"), ("bits", "<i4"), ("eval", "<f8"),
+                           ("q_start", "<i4"), ("q_end", "<i4"), ("t_start", "<i4"), ("t_end", "<i4"),
+                           ("n_ident", "<i4"), ("aln_len", "<i4"), ("seq_id", "<f4"), ("cigar_off", "<u4"),
+                           ("cigar_len", "<u4")])
+            assert dt.itemsize == C.sizeof(capi.Aln)
+            rows = np.frombuffer(C.string_at(R.rows, n * dt.itemsize), dtype=dt).copy() if n else np.zeros(0, dtype=dt)
+            cig = C.string_at(R.cigar_ops, int(R.n_cigar)) if R.n_cigar else b""
+            stats = dict(n_pairs=int(R.n_pairs), n_cells=int(R.n_cells), kernel_ms=float(R.kernel_ms),
+                         total_ms=float(R.total_ms))
+        finally:
+            self.lib.spb_free_align_result(r)
+        return off, rows, cig, stats
+
+
+def format_prefilter_rows(hits, keys=None):
+    """QueryMatcher::prefilterHitToBuffer (M/prefiltering/QueryMatcher.h:114-126): key \\t score \\t diagonal"""
+    return ["%d\t%d\t%d" % (int(keys[h["id"]]) if keys is not None else int(h["id"]), int(h["score"]), int(h["diag"]))
+            for h in hits]
+
+
+def compress_cigar(ops):
+    """Matcher::compressAlignment (M/alignment/Matcher.cpp:211-230): always emits counts."""
+    out = []
+    state, count = "M", 0
+    for ch in ops:
+        if ch != state:
+            out.append("%d%s" % (count, state))
+            state, count = ch, 1
+        else:
+            count += 1
+    out.append("%d%s" % (count, state))
+    return "".join(out)
+
+
+def format_seq_id(x):
+    """Util::fastSeqIdToBuffer (M/commons/Util.cpp:278-307) incl. the 4-character "1.00" quirk."""
+    x = np.float32(x)
+    if x == np.float32(1.0):
+        return "1.00"
+    s = "0."
+    if float(x) < 0.10:
+        s += "0"
+    if float(x) < 0.01:
+        s += "0"
+    return s + str(int(np.float32(x * np.float32(1000))))
+
+
+def format_align_rows(rows, cigar, q_lens, t_lens, keys=None):
+    """Matcher::resultToBuffer (M/alignment/Matcher.cpp:323-370)"""
+    out = []
+    for r in rows:
+        t = int(r["target"])
+        ops = cigar[int(r["cigar_off"]): int(r["cigar_off"]) + int(r["cigar_len"])].decode()
+        out.append("%d\t%d\t%s\t%.3E\t%d\t%d\t%d\t%d\t%d\t%d\t%s" % (
+            int(keys[t]) if keys is not None else t, int(r["bits"]), format_seq_id(r["seq_id"]), float(r["eval"]),
+            int(r["q_start"]), int(r["q_end"]), int(q_lens[int(r["query"])]), int(r["t_start"]), int(r["t_end"]),
+            int(t_lens[t]), compress_cigar(ops) if ops else ""))
+    return out

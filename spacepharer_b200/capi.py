@@ -1,0 +1,114 @@
+"""ctypes binding of libspb200.so (include/spb200.h).  The library is built in-tree by `make`
+(or __graft_entry__.build()); importing this module never falls back to a CPU implementation."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libspb200.so")
+ALPH = 21
+
+
+class Gumbel(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "lambda_", "K", "a_I", "b_I", "alpha_I", "beta_I", "a_J", "b_J", "alpha_J", "beta_J", "sigma", "tau")]
+
+
+class IndexStats(C.Structure):
+    _fields_ = [("n_targets", C.c_uint64), ("n_residues", C.c_uint64), ("n_postings", C.c_uint64),
+                ("n_kmers_nonempty", C.c_uint64), ("bytes_device", C.c_uint64), ("build_ms", C.c_double)]
+
+
+class PrefilterParams(C.Structure):
+    _fields_ = [("kmer_thr", C.c_int32), ("max_seqs", C.c_int32), ("min_diag_score", C.c_int32),
+                ("bin_size", C.c_int32), ("comp_bias", C.c_int32), ("id_base", C.c_uint32)]
+
+
+class Hit(C.Structure):
+    _fields_ = [("id", C.c_uint32), ("score", C.c_int32), ("diag", C.c_int32)]
+
+
+class PrefilterResult(C.Structure):
+    _fields_ = [("n_queries", C.c_uint32), ("offsets", C.POINTER(C.c_uint64)), ("hits", C.POINTER(Hit)),
+                ("n_hits", C.c_uint64), ("n_kmers", C.c_uint64), ("n_db_matches", C.c_uint64),
+                ("n_events", C.c_uint64), ("n_slow_path", C.c_uint64), ("kernel_ms", C.c_double),
+                ("algo_bytes", C.c_uint64)]
+
+
+class AlignParams(C.Structure):
+    _fields_ = [("gap_open", C.c_int32), ("gap_extend", C.c_int32), ("eval_thr", C.c_double),
+                ("db_res_count", C.c_uint64), ("comp_bias", C.c_int32), ("byte_lanes", C.c_int32),
+                ("word_lanes", C.c_int32), ("gumbel", Gumbel)]
+
+
+class Aln(C.Structure):
+    _fields_ = [("query", C.c_uint32), ("target", C.c_uint32), ("score", C.c_int32), ("bits", C.c_int32),
+                ("eval", C.c_double), ("q_start", C.c_int32), ("q_end", C.c_int32), ("t_start", C.c_int32),
+                ("t_end", C.c_int32), ("n_ident", C.c_int32), ("aln_len", C.c_int32), ("seq_id", C.c_float),
+                ("cigar_off", C.c_uint32), ("cigar_len", C.c_uint32)]
+
+
+class AlignResult(C.Structure):
+    _fields_ = [("n_queries", C.c_uint32), ("offsets", C.POINTER(C.c_uint64)), ("rows", C.POINTER(Aln)),
+                ("n_rows", C.c_uint64), ("cigar_ops", C.POINTER(C.c_char)), ("n_cigar", C.c_uint64),
+                ("n_pairs", C.c_uint64), ("n_cells", C.c_uint64), ("kernel_ms", C.c_double),
+                ("total_ms", C.c_double)]
+
+
+# every symbol include/spb200.h declares (tests check the library exports exactly these)
+SYMBOLS = [
+    "spb_ctx_create", "spb_ctx_destroy", "spb_last_error", "spb_version", "spb_ctx_stream", "spb_set_matrices",
+    "spb_index_build", "spb_index_stats_get", "spb_index_export", "spb_similar_kmers", "spb_prefilter",
+    "spb_free_prefilter_result", "spb_align_set_targets", "spb_align", "spb_free_align_result", "spb_evalue",
+    "spb_bitscore", "spb_tantan_mask",
+]
+
+_lib = None
+
+
+class SpbError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libspb200.so; raises if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SpbError("libspb200.so not built: run `make` (or __graft_entry__.build()) in the repo root")
+    L = C.CDLL(LIB_PATH)
+    vp, u8p, u64p, u32p = C.c_void_p, C.POINTER(C.c_ubyte), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
+    L.spb_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.spb_ctx_destroy.argtypes = [vp]
+    L.spb_ctx_destroy.restype = None
+    L.spb_last_error.restype = C.c_char_p
+    L.spb_version.restype = C.c_char_p
+    L.spb_ctx_stream.argtypes = [vp]
+    L.spb_ctx_stream.restype = vp
+    L.spb_set_matrices.argtypes = [vp, C.POINTER(C.c_int16), C.POINTER(C.c_double), C.POINTER(C.c_int16),
+                                   C.POINTER(C.c_int16), C.POINTER(C.c_double)]
+    L.spb_index_build.argtypes = [vp, u8p, u64p, C.c_uint32, C.c_char_p, C.c_int]
+    L.spb_index_stats_get.argtypes = [vp, C.POINTER(IndexStats)]
+    L.spb_index_export.argtypes = [vp, u32p, u32p, C.POINTER(C.c_uint16)]
+    L.spb_similar_kmers.argtypes = [vp, u8p, C.c_int, u32p, C.c_uint32, u32p]
+    L.spb_prefilter.argtypes = [vp, u8p, u64p, C.c_uint32, C.POINTER(PrefilterParams),
+                                C.POINTER(C.POINTER(PrefilterResult))]
+    L.spb_free_prefilter_result.argtypes = [C.POINTER(PrefilterResult)]
+    L.spb_free_prefilter_result.restype = None
+    L.spb_align_set_targets.argtypes = [vp, u8p, u64p, C.c_uint32, u32p]
+    L.spb_align.argtypes = [vp, u8p, u64p, C.c_uint32, u64p, u32p, C.POINTER(AlignParams),
+                            C.POINTER(C.POINTER(AlignResult))]
+    L.spb_free_align_result.argtypes = [C.POINTER(AlignResult)]
+    L.spb_free_align_result.restype = None
+    L.spb_evalue.argtypes = [C.POINTER(Gumbel), C.c_double, C.c_double, C.c_double]
+    L.spb_evalue.restype = C.c_double
+    L.spb_bitscore.argtypes = [C.POINTER(Gumbel), C.c_double]
+    L.spb_bitscore.restype = C.c_double
+    L.spb_tantan_mask.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), u8p, u64p, C.c_uint32, C.c_int, u64p]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise SpbError(load().spb_last_error().decode(errors="replace"))

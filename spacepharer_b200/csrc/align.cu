@@ -1,0 +1,635 @@
+// align.cu -- gapped alignment of (query frame, target ORF) pairs: score, end/start coordinates, CIGAR, E-value.
+//
+// Replaces Matcher::getSWResult -> SmithWaterman::ssw_init / ssw_align / banded_sw
+// (M/alignment/Matcher.cpp:61-187, StripedSmithWaterman.cpp:130-290,301-687,689-984) and
+// EvalueComputation::computeEvalue / computeBitScore (M/alignment/EvalueComputation.h:18-40).
+//
+// The reference computes a Farrar-striped SW whose E update sees H *before* the cross-stripe lazy-F correction,
+// so its result depends on the SIMD layout.  One thread per pair reproduces that exactly with two F accumulators
+// per column (no striped emulation needed):
+//     Fs : F chain restarted at every stripe start (row % segLen == 0)      -> H1 = max(0, Hdiag + s, E, Fs)
+//     Ff : the full F chain over all rows                                     -> H  = max(H1, Ff)
+//     E' = max(E - ge, H1 - go)      (never opens from a cell that was raised by a cross-stripe F)
+// with segLen = ceil(L / lanes) of the emulated build (byte kernel 32 lanes, word kernel 16 lanes for AVX2).
+// The byte kernel's saturation only matters through its overflow test (max + bias >= 255 -> word kernel).
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace spb {
+
+// ---- per-query composition bias (SmithWaterman::ssw_init, StripedSmithWaterman.cpp:689-706) ----
+__global__ void align_profile_kernel(const uint8_t *__restrict__ q, const uint64_t *__restrict__ qoff, uint32_t Q,
+                                     const Matrices *__restrict__ mat, int compBias, signed char *__restrict__ cb,
+                                     int *__restrict__ qbias) {
+    const uint32_t qi = blockIdx.x;
+    if (qi >= Q) return;
+    __shared__ int s_min;
+    if (threadIdx.x == 0) s_min = 0;
+    __syncthreads();
+    const uint64_t o = qoff[qi];
+    const int L = (int)(qoff[qi + 1] - o);
+    const uint8_t *s = q + o;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        signed char c = 0;
+        if (compBias) {
+            const int lo = max(0, i - 20), hi = min(L, i + 20);
+            const int16_t *row = mat->align + s[i] * SPB_ALPHABET;
+            int sum = 0;
+            for (int j = lo; j < hi; j++) sum += row[s[j]];
+            sum -= row[s[i]];
+            float d = (float)sum;
+            d = __double2float_rn(__ddiv_rn((double)d, -1.0 * (double)(float)(hi - lo)));
+            for (int a = 0; a < SPB_ALPHABET; a++)
+                d = __double2float_rn(__dadd_rn((double)d, __dmul_rn(mat->pback_align[a], (double)(float)row[a])));
+            double r = (d < 0.0f) ? __dsub_rn((double)d, 0.5) : __dadd_rn((double)d, 0.5);
+            c = (signed char)r;
+        }
+        cb[o + i] = c;
+        if (c < 0) atomicMin(&s_min, (int)c);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int mn = 0;
+        for (int i = 0; i < SPB_ALPHABET * SPB_ALPHABET; i++) mn = min(mn, (int)(signed char)mat->align[i]);
+        qbias[qi] = abs(mn) + abs(min(s_min, 0));
+    }
+}
+
+// ---- E-value on the device (lib/alp/sls_pvalues.cpp:366-541) ----
+__device__ __forceinline__ double dev_evalue(const spb_gumbel &g, double y, double n, double m) {
+    const double const_val = 0.3989422804014326779;  // 1/sqrt(2 pi)
+    double m_li_y = m - (g.a_I * y + g.b_I);
+    double vi_y = fmax(2.0 * g.alpha_I / g.lambda, g.alpha_I * y + g.beta_I);
+    double sqrt_vi_y = sqrt(vi_y);
+    double m_F = sqrt_vi_y == 0.0 ? 1e100 : m_li_y / sqrt_vi_y;
+    double P_m_F = 0.5 * erfc(-sqrt(0.5) * m_F);
+    double E_m_F = -const_val * exp(-0.5 * m_F * m_F);
+    double p1 = m_li_y * P_m_F - sqrt_vi_y * E_m_F;
+    double n_lj_y = n - (g.a_J * y + g.b_J);
+    double vj_y = fmax(2.0 * g.alpha_J / g.lambda, g.alpha_J * y + g.beta_J);
+    double sqrt_vj_y = sqrt(vj_y);
+    double n_F = sqrt_vj_y == 0.0 ? 1e100 : n_lj_y / sqrt_vj_y;
+    double P_n_F = 0.5 * erfc(-sqrt(0.5) * n_F);
+    double E_n_F = -const_val * exp(-0.5 * n_F * n_F);
+    double p2 = n_lj_y * P_n_F - sqrt_vj_y * E_n_F;
+    double c_y = fmax(2.0 * g.sigma / g.lambda, g.sigma * y + g.tau);
+    double area = p1 * p2 + c_y * (P_m_F * P_n_F);
+    return g.K * exp(-g.lambda * y) * area;
+}
+
+struct PairOut {      // per pair, written by the forward kernel, completed by reverse / traceback
+    int32_t score, qEnd, tEnd, word;
+    int32_t qStart, tStart;
+    int32_t status;   // 0 rejected (E-value / nothing aligned), 1 accepted, <0 error
+    int32_t bits;
+    double eval;
+    int32_t nIdent, alnLen;
+    uint32_t cigOff, cigLen;
+};
+
+// One DP pass over columns jBegin, jBegin+step, ... (exclusive jEnd) for one pair held by one thread.
+// H/E live at he[i * stride] (int16 pairs).  prof(i, a) = substitution score + composition bias of query row i.
+template <class Prof>
+__device__ __forceinline__ void sw_pass(const uint8_t *__restrict__ t, int jBegin, int jEnd, int step, int L, int segLen,
+                                        int go, int ge, int terminate, Prof prof, short2 *he, int stride,
+                                        int &bestScore, int &bestCol, int &bestRow) {
+    for (int i = 0; i < L; i++) he[i * stride] = make_short2(0, 0);
+    bestScore = 0;
+    bestCol = -1;
+    bestRow = L - 1;
+    for (int j = jBegin; j != jEnd; j += step) {
+        const int a = __ldg(t + j);
+        int hdiag = 0, Fs = 0, Ff = 0, colMax = 0, colRow = 0, seg = 0;
+        for (int i = 0; i < L; i++) {
+            if (seg == 0) Fs = 0;
+            const short2 old = he[i * stride];
+            int h1 = hdiag + prof(i, a);
+            h1 = min(h1, 32767);
+            h1 = max(max(h1, (int)old.y), max(Fs, 0));
+            const int open = max(h1 - go, 0);
+            const int e = max(max((int)old.y - ge, 0), open);
+            Fs = max(max(Fs - ge, 0), open);
+            const int h = max(h1, Ff);
+            Ff = max(max(Ff - ge, 0), open);
+            hdiag = old.x;
+            he[i * stride] = make_short2((short)h, (short)e);
+            if (h > colMax) { colMax = h; colRow = i; }
+            if (++seg == segLen) seg = 0;
+        }
+        if (colMax > bestScore) {
+            bestScore = colMax;
+            bestCol = j;
+            bestRow = colRow;
+        }
+        if (terminate > 0 && colMax == terminate) break;
+    }
+}
+
+struct FwdItem { uint32_t query, pairStart, count; };
+
+struct AlnArgs {
+    const uint8_t *q;
+    const uint64_t *qoff;
+    const signed char *qcb;
+    const int *qbias;
+    const uint8_t *tres;
+    const uint64_t *toff;
+    const Matrices *mat;
+    const FwdItem *items;
+    uint32_t nItems;
+    const uint32_t *pairT;     // target id per pair (work order)
+    PairOut *out;
+    int go, ge, byteLanes, wordLanes;
+    double evalThr, dbRes;
+    spb_gumbel g;
+    int Lpad;                  // padded max query length of the batch (smem layout)
+    unsigned long long *cells; // forward cells counter
+};
+
+// Forward pass: one warp per (query, <=32 targets) item, one lane per pair.  Per warp shared memory:
+// profile int8[21][Lpad] followed by H/E short2[Lpad][32].
+__global__ void __launch_bounds__(128) sw_forward_kernel(AlnArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t item = blockIdx.x * nw + wid;
+    if (item >= A.nItems) return;
+    const size_t perWarp = (size_t)SPB_ALPHABET * A.Lpad + (size_t)A.Lpad * 32 * sizeof(short2);
+    signed char *sprof = reinterpret_cast<signed char *>(smem + wid * perWarp);
+    short2 *she = reinterpret_cast<short2 *>(smem + wid * perWarp + (size_t)SPB_ALPHABET * A.Lpad);
+    const FwdItem it = A.items[item];
+    const uint64_t qo = A.qoff[it.query];
+    const int L = (int)(A.qoff[it.query + 1] - qo);
+    const int Lpad = A.Lpad;
+    // profile(i, a) = M[a][q_i] + cb_i  (StripedSmithWaterman.cpp:93-127)
+    for (int x = lane; x < SPB_ALPHABET * L; x += 32) {
+        const int a = x / L, i = x - a * L;
+        sprof[a * Lpad + i] = (signed char)((int)(signed char)A.mat->align[a * SPB_ALPHABET + A.q[qo + i]] + (int)A.qcb[qo + i]);
+    }
+    __syncwarp();
+    if (lane >= (int)it.count) return;
+    const uint32_t pair = it.pairStart + lane;
+    const uint32_t tid = A.pairT[pair];
+    const uint64_t to = A.toff[tid];
+    const int tLen = (int)(A.toff[tid + 1] - to);
+    const uint8_t *t = A.tres + to;
+    const int bias = A.qbias[it.query];
+    auto prof = [&](int i, int a) -> int { return (int)sprof[a * Lpad + i]; };
+    const int segB = (L + A.byteLanes - 1) / A.byteLanes, segW = (L + A.wordLanes - 1) / A.wordLanes;
+    int score, col, row, word = 0;
+    sw_pass(t, 0, tLen, 1, L, segB, A.go, A.ge, -1, prof, she + lane, 32, score, col, row);
+    if (score + bias >= 255) {          // byte kernel overflow -> word kernel (StripedSmithWaterman.cpp:156-163)
+        word = 1;
+        if (segW != segB) sw_pass(t, 0, tLen, 1, L, segW, A.go, A.ge, -1, prof, she + lane, 32, score, col, row);
+    }
+    PairOut o;
+    memset(&o, 0, sizeof(o));
+    o.score = score;
+    o.qEnd = row;
+    o.tEnd = col;
+    o.word = word;
+    o.qStart = o.tStart = -1;
+    o.status = 0;
+    if (col >= 0) {
+        o.eval = dev_evalue(A.g, (double)score, (double)L, A.dbRes);
+        o.bits = (int)((A.g.lambda * (double)score - log(A.g.K)) / log(2.0) + 0.5);
+        if (!(o.eval > A.evalThr)) o.status = 1;
+    }
+    A.out[pair] = o;
+    atomicAdd(A.cells, (unsigned long long)L * (unsigned long long)tLen);
+}
+
+// Reverse pass + banded traceback for accepted pairs: one thread per pair, scratch in global memory.
+struct TbArgs {
+    const uint8_t *q;
+    const uint64_t *qoff;
+    const signed char *qcb;
+    const uint8_t *tres;
+    const uint64_t *toff;
+    const Matrices *mat;
+    const uint32_t *acc;       // accepted pair indices
+    uint32_t nAcc;
+    const uint32_t *pairQ, *pairT;
+    PairOut *out;
+    int go, ge, byteLanes, wordLanes;
+    short2 *heScratch;         // [nAcc] slices, offsets heOff
+    const uint64_t *heOff;
+    // traceback scratch
+    const uint64_t *tbOff;     // [nAcc+1] byte offsets into tbScratch
+    unsigned char *tbScratch;
+    const uint64_t *cigOff;    // [nAcc+1] offsets into cigar
+    char *cigar;
+};
+
+__global__ void sw_reverse_kernel(TbArgs A) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= A.nAcc) return;
+    const uint32_t pair = A.acc[k];
+    PairOut o = A.out[pair];
+    const uint32_t qi = A.pairQ[pair], ti = A.pairT[pair];
+    const uint64_t qo = A.qoff[qi];
+    const uint8_t *q = A.q + qo;
+    const signed char *cb = A.qcb + qo;
+    const uint8_t *t = A.tres + A.toff[ti];
+    const int rl = o.qEnd + 1;
+    const int lanes = o.word ? A.wordLanes : A.byteLanes;
+    const int seg = (rl + lanes - 1) / lanes;
+    const int qEnd = o.qEnd;
+    const int16_t *M = A.mat->align;
+    auto prof = [&](int i, int a) -> int { return (int)(signed char)M[a * SPB_ALPHABET + q[qEnd - i]] + (int)cb[qEnd - i]; };
+    int score, col, row;
+    sw_pass(t, o.tEnd, -1, -1, rl, seg, A.go, A.ge, o.score, prof, A.heScratch + A.heOff[k], 1, score, col, row);
+    if (score != o.score || col < 0) {
+        o.status = -1;      // "Score of forward/backward SW differ" (StripedSmithWaterman.cpp:225-228)
+    } else {
+        o.tStart = col;
+        o.qStart = qEnd - row;
+    }
+    A.out[pair] = o;
+}
+
+// banded_sw (StripedSmithWaterman.cpp:781-984), transcribed literally: band doubling, direction codes 1..5, traceback
+// from the bottom-right cell, final forced 'M'.  Scratch per pair: h_b/e_b/h_c int32[W] + direction int8[D].
+__device__ __forceinline__ int band_u(int w, int i, int j) { int x = i - w; x = x > 0 ? x : 0; return j - x + 1; }
+__device__ __forceinline__ int band_d(int w, int i, int j, int p) { int x = i - w; x = x > 0 ? x : 0; x = j - x; return x * 3 + p; }
+
+__global__ void sw_traceback_kernel(TbArgs A) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= A.nAcc) return;
+    const uint32_t pair = A.acc[k];
+    PairOut o = A.out[pair];
+    if (o.status != 1) return;
+    const uint32_t qi = A.pairQ[pair], ti = A.pairT[pair];
+    const uint64_t qo = A.qoff[qi];
+    const uint8_t *qs = A.q + qo + o.qStart;
+    const signed char *cb = A.qcb + qo + o.qStart;
+    const uint8_t *db = A.tres + A.toff[ti] + o.tStart;
+    const int16_t *M = A.mat->align;
+    const int dbLen = o.tEnd - o.tStart + 1, qLen = o.qEnd - o.qStart + 1;
+    const int score = o.score, go = A.go, ge = A.ge;
+    int bw = abs(dbLen - qLen) + 1;
+    // scratch layout: [h_b | e_b | h_c] int32 each Wmax, then direction bytes
+    const uint64_t bytes = A.tbOff[k + 1] - A.tbOff[k];
+    unsigned char *base = A.tbScratch + A.tbOff[k];
+    int bwMax = bw;
+    while (bwMax < max(qLen, dbLen)) bwMax *= 2;
+    const int64_t Wmax = (int64_t)bwMax * 2 + 3 + 2;
+    int32_t *h_b = reinterpret_cast<int32_t *>(base);
+    int32_t *e_b = h_b + Wmax;
+    int32_t *h_c = e_b + Wmax;
+    int8_t *direction = reinterpret_cast<int8_t *>(h_c + Wmax);
+    const int64_t dirCap = (int64_t)bytes - 3 * Wmax * 4;
+    for (int64_t x = 0; x < 3 * Wmax; x++) h_b[x] = 0;
+    int64_t width = 0, width_d = 0;
+    int mx = 0;
+    int8_t *dl = direction;
+    bool bad = false;
+    do {
+        width = (int64_t)bw * 2 + 3;
+        width_d = (int64_t)bw * 2 + 1;
+        if (width + 1 > Wmax || width_d * qLen * 3 > dirCap) { bad = true; break; }
+        for (int j = 1; j < width - 1; j++) h_b[j] = 0;
+        for (int i = 0; i < qLen; i++) {
+            int beg = 0, end = dbLen - 1, u = 0, edge, f, j;
+            j = i - bw; beg = beg > j ? beg : j;
+            j = i + bw; end = end < j ? end : j;
+            edge = end + 1 < width - 1 ? end + 1 : (int)(width - 1);
+            f = h_b[0] = e_b[0] = h_b[edge] = e_b[edge] = h_c[0] = 0;
+            dl = direction + width_d * i * 3;
+            const int qa = qs[i];
+            const int cbi = cb[i];
+            for (j = beg; j <= end; j++) {
+                u = band_u(bw, i, j);
+                const int e = band_u(bw, i - 1, j), b = band_u(bw, i, j - 1), d = band_u(bw, i - 1, j - 1);
+                const int de = band_d(bw, i, j, 0), df = band_d(bw, i, j, 1), dh = band_d(bw, i, j, 2);
+                int t1 = i == 0 ? -go : h_b[e] - go;
+                int t2 = i == 0 ? -ge : e_b[e] - ge;
+                e_b[u] = t1 > t2 ? t1 : t2;
+                dl[de] = t1 > t2 ? 3 : 2;
+                t1 = h_c[b] - go;
+                t2 = f - ge;
+                f = t1 > t2 ? t1 : t2;
+                dl[df] = t1 > t2 ? 5 : 4;
+                const int e1 = e_b[u] > 0 ? e_b[u] : 0;
+                const int f1 = f > 0 ? f : 0;
+                t1 = e1 > f1 ? e1 : f1;
+                t2 = h_b[d] + (int)(signed char)M[qa * SPB_ALPHABET + db[j]] + cbi;
+                h_c[u] = t1 > t2 ? t1 : t2;
+                if (h_c[u] > mx) mx = h_c[u];
+                if (t1 <= t2) dl[dh] = 1;
+                else dl[dh] = e1 > f1 ? dl[de] : dl[df];
+            }
+            for (j = 1; j <= u; j++) h_b[j] = h_c[j];
+        }
+        bw *= 2;
+    } while (mx < score);
+    char *cig = A.cigar + A.cigOff[k];
+    const uint32_t cigCap = (uint32_t)(A.cigOff[k + 1] - A.cigOff[k]);
+    uint32_t n = 0;
+    if (!bad) {
+        bw /= 2;
+        int i = qLen - 1, j = dbLen - 1, st = 2;
+        while (i > 0 || j > 0) {
+            const int t1 = band_d(bw, i, j, st);
+            char op = 0;
+            switch (dl[t1]) {
+                case 1: --i; --j; st = 2; dl -= width_d * 3; op = 'M'; break;
+                case 2: --i; st = 0; dl -= width_d * 3; op = 'I'; break;
+                case 3: --i; st = 2; dl -= width_d * 3; op = 'I'; break;
+                case 4: --j; st = 1; op = 'D'; break;
+                case 5: --j; st = 2; op = 'D'; break;
+                default: bad = true; break;
+            }
+            if (bad || n + 1 >= cigCap) { bad = true; break; }
+            cig[n++] = op;
+        }
+    }
+    if (bad) {
+        // reference: "Trace back error" -> no CIGAR; alnLength from coordinates, no identities (Matcher.cpp:141-152)
+        o.cigLen = 0;
+        o.nIdent = 0;
+        o.alnLen = max(abs(o.qEnd - o.qStart), abs(o.tEnd - o.tStart)) + 1;
+    } else {
+        cig[n++] = 'M';
+        for (uint32_t a = 0, b = n - 1; a < b; a++, b--) { char tmp = cig[a]; cig[a] = cig[b]; cig[b] = tmp; }
+        int ids = 0, qi2 = 0, ti2 = 0;
+        for (uint32_t x = 0; x < n; x++) {
+            if (cig[x] == 'M') { ids += (qs[qi2] == db[ti2]); qi2++; ti2++; }
+            else if (cig[x] == 'I') qi2++;
+            else ti2++;
+        }
+        o.cigLen = n;
+        o.nIdent = ids;
+        o.alnLen = (int)n;
+    }
+    o.cigOff = (uint32_t)A.cigOff[k];
+    A.out[pair] = o;
+}
+
+}  // namespace spb
+
+using namespace spb;
+
+extern "C" int spb_align_set_targets(spb_ctx *c, const uint8_t *residues, const uint64_t *offsets, uint32_t T,
+                                     const uint32_t *keys) {
+    SPB_CHECK(c && residues && offsets, "spb_align_set_targets: NULL argument");
+    SPB_CUDA(cudaSetDevice(c->device));
+    const uint64_t N = offsets[T];
+    if (c->d_ares.ensure(N + 64) || c->d_aoff.ensure(((size_t)T + 1) * 8)) return 1;
+    SPB_CUDA(cudaMemcpyAsync(c->d_ares.p, residues, N, cudaMemcpyHostToDevice, c->stream));
+    SPB_CUDA(cudaMemcpyAsync(c->d_aoff.p, offsets, ((size_t)T + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    SPB_CUDA(cudaStreamSynchronize(c->stream));
+    c->aT = T;
+    c->a_res = N;
+    c->h_aoff.assign(offsets, offsets + T + 1);
+    c->h_akeys.resize(T);
+    for (uint32_t i = 0; i < T; i++) c->h_akeys[i] = keys ? keys[i] : i;
+    c->have_aln_targets = true;
+    return 0;
+}
+
+extern "C" void spb_free_align_result(spb_align_result *r) {
+    if (!r) return;
+    free(r->offsets);
+    free(r->rows);
+    free(r->cigar_ops);
+    free(r);
+}
+
+extern "C" int spb_align(spb_ctx *c, const uint8_t *q_residues, const uint64_t *q_offsets, uint32_t Q,
+                         const uint64_t *pair_offsets, const uint32_t *pair_targets, const spb_align_params *p,
+                         spb_align_result **out) {
+    SPB_CHECK(c && q_offsets && pair_offsets && p && out, "spb_align: NULL argument");
+    SPB_CHECK(c->have_matrices, "spb_align: call spb_set_matrices first");
+    SPB_CHECK(c->have_aln_targets, "spb_align: call spb_align_set_targets first");
+    SPB_CHECK(p->gap_open >= 0 && p->gap_open <= 255 && p->gap_extend >= 0 && p->gap_extend <= 255, "spb_align: gap costs out of range");
+    SPB_CHECK(p->byte_lanes > 0 && p->word_lanes > 0, "spb_align: lanes must be positive");
+    SPB_CUDA(cudaSetDevice(c->device));
+    *out = nullptr;
+    cudaStream_t st = c->stream;
+    const uint64_t NQ = q_offsets[Q];
+    const uint64_t NP = pair_offsets[Q];
+    SPB_CHECK(NP < 0xFFFFFFF0ull, "spb_align: more than 2^32 pairs in one call; split the batch");
+
+    spb_align_result *res = (spb_align_result *)calloc(1, sizeof(spb_align_result));
+    res->n_queries = Q;
+    res->offsets = (uint64_t *)calloc((size_t)Q + 1, sizeof(uint64_t));
+    res->rows = (spb_aln *)calloc(1, sizeof(spb_aln));
+    res->cigar_ops = (char *)calloc(1, 1);
+    res->n_pairs = NP;
+    if (NP == 0) { *out = res; return 0; }
+
+    // ---- work order: per query, targets by length descending (lanes of a warp finish together), <=32 per item
+    std::vector<uint32_t> pairQ(NP), pairT(NP);
+    std::vector<FwdItem> items;
+    uint32_t maxL = 0;
+    {
+        std::vector<uint32_t> tmp;
+        uint64_t w = 0;
+        for (uint32_t qi = 0; qi < Q; qi++) {
+            const uint64_t a = pair_offsets[qi], b = pair_offsets[qi + 1];
+            if (b == a) continue;
+            const uint32_t L = (uint32_t)(q_offsets[qi + 1] - q_offsets[qi]);
+            maxL = std::max(maxL, L);
+            tmp.assign(pair_targets + a, pair_targets + b);
+            for (uint32_t t : tmp) {
+                if (t >= c->aT) {
+                    spb::set_error("spb_align: target id %u of query %u out of range (%u targets)", t, qi, c->aT);
+                    spb_free_align_result(res);
+                    return 1;
+                }
+            }
+            std::stable_sort(tmp.begin(), tmp.end(), [&](uint32_t x, uint32_t y) {
+                return (c->h_aoff[x + 1] - c->h_aoff[x]) > (c->h_aoff[y + 1] - c->h_aoff[y]);
+            });
+            for (uint64_t k = 0; k < tmp.size(); k += 32) {
+                FwdItem it;
+                it.query = qi;
+                it.pairStart = (uint32_t)(w + k);
+                it.count = (uint32_t)std::min<uint64_t>(32, tmp.size() - k);
+                items.push_back(it);
+            }
+            for (uint32_t t : tmp) { pairQ[w] = qi; pairT[w] = t; w++; }
+        }
+    }
+    const int Lpad = (int)((maxL + 3) & ~3u);
+    const size_t perWarp = (size_t)SPB_ALPHABET * Lpad + (size_t)Lpad * 32 * sizeof(short2);
+    if (maxL == 0 || perWarp > 200 * 1024) {
+        spb::set_error("spb_align: query length %u outside the supported range of the shared-memory kernel (1..%d)", maxL,
+                       (int)(200 * 1024 / (SPB_ALPHABET + 128)));
+        spb_free_align_result(res);
+        return 1;
+    }
+    int warpsPerBlock = (int)std::min<size_t>(4, std::max<size_t>(1, (96 * 1024) / perWarp));
+    const size_t smem = perWarp * warpsPerBlock;
+
+    DevBuf d_q, d_qoff, d_cb, d_qbias, d_items, d_pairQ, d_pairT, d_out, d_cells, d_acc, d_he, d_heOff, d_tbOff, d_tb, d_cigOff, d_cig;
+    std::vector<DevBuf *> all = {&d_q, &d_qoff, &d_cb, &d_qbias, &d_items, &d_pairQ, &d_pairT, &d_out, &d_cells, &d_acc,
+                                 &d_he, &d_heOff, &d_tbOff, &d_tb, &d_cigOff, &d_cig};
+    auto fail = [&]() { for (DevBuf *b : all) b->release(); spb_free_align_result(res); return 1; };
+#define AL_CUDA(call)                                                                             \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            spb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return fail();                                                                        \
+        }                                                                                         \
+    } while (0)
+    if (d_q.ensure(NQ + 64) || d_qoff.ensure(((size_t)Q + 1) * 8) || d_cb.ensure(NQ + 64) || d_qbias.ensure((size_t)Q * 4) ||
+        d_items.ensure(items.size() * sizeof(FwdItem)) || d_pairQ.ensure(NP * 4) || d_pairT.ensure(NP * 4) ||
+        d_out.ensure(NP * sizeof(PairOut)) || d_cells.ensure(8)) return fail();
+    AL_CUDA(cudaEventRecord(c->ev2, st));
+    AL_CUDA(cudaMemcpyAsync(d_q.p, q_residues, NQ, cudaMemcpyHostToDevice, st));
+    AL_CUDA(cudaMemcpyAsync(d_qoff.p, q_offsets, ((size_t)Q + 1) * 8, cudaMemcpyHostToDevice, st));
+    AL_CUDA(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(FwdItem), cudaMemcpyHostToDevice, st));
+    AL_CUDA(cudaMemcpyAsync(d_pairQ.p, pairQ.data(), NP * 4, cudaMemcpyHostToDevice, st));
+    AL_CUDA(cudaMemcpyAsync(d_pairT.p, pairT.data(), NP * 4, cudaMemcpyHostToDevice, st));
+    AL_CUDA(cudaMemsetAsync(d_cells.p, 0, 8, st));
+    align_profile_kernel<<<Q, 64, 0, st>>>(d_q.as<uint8_t>(), d_qoff.as<uint64_t>(), Q, c->d_mat.as<Matrices>(), p->comp_bias,
+                                           d_cb.as<signed char>(), d_qbias.as<int>());
+    AL_CUDA(cudaGetLastError());
+
+    AlnArgs A;
+    memset(&A, 0, sizeof(A));
+    A.q = d_q.as<uint8_t>();
+    A.qoff = d_qoff.as<uint64_t>();
+    A.qcb = d_cb.as<signed char>();
+    A.qbias = d_qbias.as<int>();
+    A.tres = c->d_ares.as<uint8_t>();
+    A.toff = c->d_aoff.as<uint64_t>();
+    A.mat = c->d_mat.as<Matrices>();
+    A.items = d_items.as<FwdItem>();
+    A.nItems = (uint32_t)items.size();
+    A.pairT = d_pairT.as<uint32_t>();
+    A.out = d_out.as<PairOut>();
+    A.go = p->gap_open;
+    A.ge = p->gap_extend;
+    A.byteLanes = p->byte_lanes;
+    A.wordLanes = p->word_lanes;
+    A.evalThr = p->eval_thr;
+    A.dbRes = (double)p->db_res_count;
+    A.g = p->gumbel;
+    A.Lpad = Lpad;
+    A.cells = d_cells.as<unsigned long long>();
+    AL_CUDA(cudaFuncSetAttribute(sw_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AL_CUDA(cudaEventRecord(c->ev0, st));
+    sw_forward_kernel<<<(unsigned)((items.size() + warpsPerBlock - 1) / warpsPerBlock), 32 * warpsPerBlock, smem, st>>>(A);
+    AL_CUDA(cudaGetLastError());
+    AL_CUDA(cudaEventRecord(c->ev1, st));
+
+    std::vector<PairOut> h_out(NP);
+    AL_CUDA(cudaMemcpyAsync(h_out.data(), d_out.p, NP * sizeof(PairOut), cudaMemcpyDeviceToHost, st));
+    unsigned long long cells = 0;
+    AL_CUDA(cudaMemcpyAsync(&cells, d_cells.p, 8, cudaMemcpyDeviceToHost, st));
+    AL_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    AL_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    res->kernel_ms = ms;
+    res->n_cells = cells;
+
+    // ---- accepted pairs: reverse pass + traceback
+    std::vector<uint32_t> acc;
+    for (uint64_t i = 0; i < NP; i++) if (h_out[i].status == 1) acc.push_back((uint32_t)i);
+    const uint32_t nAcc = (uint32_t)acc.size();
+    if (nAcc) {
+        std::vector<uint64_t> heOff(nAcc + 1, 0), tbOff(nAcc + 1, 0), cigOff(nAcc + 1, 0);
+        for (uint32_t k = 0; k < nAcc; k++) heOff[k + 1] = heOff[k] + (uint64_t)h_out[acc[k]].qEnd + 1;
+        if (d_acc.ensure((size_t)nAcc * 4) || d_he.ensure(heOff[nAcc] * sizeof(short2) + 16) || d_heOff.ensure(((size_t)nAcc + 1) * 8)) return fail();
+        AL_CUDA(cudaMemcpyAsync(d_acc.p, acc.data(), (size_t)nAcc * 4, cudaMemcpyHostToDevice, st));
+        AL_CUDA(cudaMemcpyAsync(d_heOff.p, heOff.data(), ((size_t)nAcc + 1) * 8, cudaMemcpyHostToDevice, st));
+        TbArgs B;
+        memset(&B, 0, sizeof(B));
+        B.q = A.q; B.qoff = A.qoff; B.qcb = A.qcb; B.tres = A.tres; B.toff = A.toff; B.mat = A.mat;
+        B.acc = d_acc.as<uint32_t>();
+        B.nAcc = nAcc;
+        B.pairQ = d_pairQ.as<uint32_t>();
+        B.pairT = d_pairT.as<uint32_t>();
+        B.out = A.out;
+        B.go = A.go; B.ge = A.ge; B.byteLanes = A.byteLanes; B.wordLanes = A.wordLanes;
+        B.heScratch = d_he.as<short2>();
+        B.heOff = d_heOff.as<uint64_t>();
+        sw_reverse_kernel<<<(nAcc + 63) / 64, 64, 0, st>>>(B);
+        AL_CUDA(cudaGetLastError());
+        AL_CUDA(cudaMemcpyAsync(h_out.data(), d_out.p, NP * sizeof(PairOut), cudaMemcpyDeviceToHost, st));
+        AL_CUDA(cudaStreamSynchronize(st));
+        for (uint32_t k = 0; k < nAcc; k++) {
+            const PairOut &o = h_out[acc[k]];
+            if (o.status != 1) {
+                spb::set_error("spb_align: forward and reverse Smith-Waterman scores differ for query %u target %u", pairQ[acc[k]], pairT[acc[k]]);
+                return fail();
+            }
+            const int64_t ql = o.qEnd - o.qStart + 1, dl = o.tEnd - o.tStart + 1;
+            int64_t bw = std::llabs(dl - ql) + 1;
+            while (bw < std::max(ql, dl)) bw *= 2;
+            const int64_t Wmax = bw * 2 + 3 + 2;
+            uint64_t bytes = (uint64_t)(3 * Wmax * 4 + (bw * 2 + 1) * ql * 3 + 16);
+            bytes = (bytes + 15) & ~15ull;
+            tbOff[k + 1] = tbOff[k] + bytes;
+            cigOff[k + 1] = cigOff[k] + (uint64_t)(ql + dl + 2);
+        }
+        if (d_tbOff.ensure(((size_t)nAcc + 1) * 8) || d_tb.ensure(tbOff[nAcc] + 64) || d_cigOff.ensure(((size_t)nAcc + 1) * 8) ||
+            d_cig.ensure(cigOff[nAcc] + 64)) return fail();
+        AL_CUDA(cudaMemcpyAsync(d_tbOff.p, tbOff.data(), ((size_t)nAcc + 1) * 8, cudaMemcpyHostToDevice, st));
+        AL_CUDA(cudaMemcpyAsync(d_cigOff.p, cigOff.data(), ((size_t)nAcc + 1) * 8, cudaMemcpyHostToDevice, st));
+        B.tbOff = d_tbOff.as<uint64_t>();
+        B.tbScratch = d_tb.as<unsigned char>();
+        B.cigOff = d_cigOff.as<uint64_t>();
+        B.cigar = d_cig.as<char>();
+        sw_traceback_kernel<<<(nAcc + 63) / 64, 64, 0, st>>>(B);
+        AL_CUDA(cudaGetLastError());
+        AL_CUDA(cudaMemcpyAsync(h_out.data(), d_out.p, NP * sizeof(PairOut), cudaMemcpyDeviceToHost, st));
+        free(res->cigar_ops);
+        res->cigar_ops = (char *)malloc(cigOff[nAcc] + 1);
+        res->n_cigar = cigOff[nAcc];
+        AL_CUDA(cudaMemcpyAsync(res->cigar_ops, d_cig.p, cigOff[nAcc], cudaMemcpyDeviceToHost, st));
+        AL_CUDA(cudaStreamSynchronize(st));
+    }
+
+    // ---- rows per query, sorted like Matcher::compareHits (Matcher.h:156-167); Alignment::checkCriteria keeps eval <= thr
+    std::vector<uint64_t> cnt(Q + 1, 0);
+    for (uint32_t k = 0; k < nAcc; k++) cnt[pairQ[acc[k]] + 1]++;
+    for (uint32_t i = 0; i < Q; i++) cnt[i + 1] += cnt[i];
+    memcpy(res->offsets, cnt.data(), ((size_t)Q + 1) * 8);
+    free(res->rows);
+    res->rows = (spb_aln *)calloc(std::max<size_t>(nAcc, 1), sizeof(spb_aln));
+    res->n_rows = nAcc;
+    {
+        std::vector<uint64_t> fill(cnt.begin(), cnt.end() - 1);
+        for (uint32_t k = 0; k < nAcc; k++) {
+            const uint32_t pair = acc[k];
+            const PairOut &o = h_out[pair];
+            spb_aln &r = res->rows[fill[pairQ[pair]]++];
+            r.query = pairQ[pair];
+            r.target = pairT[pair];
+            r.score = o.score;
+            r.bits = o.bits;
+            r.eval = o.eval;
+            r.q_start = o.qStart; r.q_end = o.qEnd; r.t_start = o.tStart; r.t_end = o.tEnd;
+            r.n_ident = o.nIdent;
+            r.aln_len = o.alnLen;
+            r.seq_id = (float)o.nIdent / (float)o.alnLen;   // Util::computeSeqId, --seq-id-mode 0
+            r.cigar_off = o.cigOff;
+            r.cigar_len = o.cigLen;
+        }
+        for (uint32_t qi = 0; qi < Q; qi++) {
+            std::sort(res->rows + cnt[qi], res->rows + cnt[qi + 1], [&](const spb_aln &x, const spb_aln &y) {
+                if (x.eval != y.eval) return x.eval < y.eval;
+                if (x.bits != y.bits) return x.bits > y.bits;
+                const uint64_t lx = c->h_aoff[x.target + 1] - c->h_aoff[x.target], ly = c->h_aoff[y.target + 1] - c->h_aoff[y.target];
+                if (lx != ly) return lx < ly;
+                return c->h_akeys[x.target] < c->h_akeys[y.target];
+            });
+        }
+    }
+    AL_CUDA(cudaEventRecord(c->ev3, st));
+    AL_CUDA(cudaStreamSynchronize(st));
+    AL_CUDA(cudaEventElapsedTime(&ms, c->ev2, c->ev3));
+    res->total_ms = ms;
+#undef AL_CUDA
+    for (DevBuf *b : all) b->release();
+    *out = res;
+    return 0;
+}

@@ -1,0 +1,111 @@
+// capi.cu -- context life cycle, error plumbing, matrices, host-side E-value helpers.
+#include <math.h>
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace spb {
+static thread_local char g_err[1024] = "";
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace spb
+
+extern "C" {
+
+const char *spb_last_error(void) { return spb::g_err; }
+const char *spb_version(void) { return "spb200 0.1 (sm_100a)"; }
+
+int spb_ctx_create(int device, spb_ctx **out) {
+    SPB_CHECK(out != nullptr, "spb_ctx_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        spb::set_error("spb_ctx_create: no CUDA device available (%s); this library has no CPU fallback",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return 1;
+    }
+    SPB_CHECK(device >= 0 && device < n, "spb_ctx_create: device %d out of range (0..%d)", device, n - 1);
+    SPB_CUDA(cudaSetDevice(device));
+    spb_ctx *c = new spb_ctx();
+    c->device = device;
+    SPB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    SPB_CUDA(cudaEventCreate(&c->ev0));
+    SPB_CUDA(cudaEventCreate(&c->ev1));
+    SPB_CUDA(cudaEventCreate(&c->ev2));
+    SPB_CUDA(cudaEventCreate(&c->ev3));
+    *out = c;
+    return 0;
+}
+
+void spb_ctx_destroy(spb_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    spb::DevBuf *bufs[] = {&c->d_mat, &c->d_tres, &c->d_toff, &c->d_koff, &c->d_post, &c->d_row3, &c->d_cnt3,
+                           &c->d_ares, &c->d_aoff, &c->d_q, &c->d_qoff, &c->d_tmp0, &c->d_tmp1, &c->d_tmp2,
+                           &c->d_tmp3, &c->d_tmp4, &c->d_tmp5, &c->d_tmp6, &c->d_tmp7};
+    for (spb::DevBuf *b : bufs) b->release();
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaEventDestroy(c->ev2);
+    cudaEventDestroy(c->ev3);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void *spb_ctx_stream(spb_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int spb_set_matrices(spb_ctx *c, const int16_t *sub_seed, const double *pback_seed, const int16_t *sub_ungapped,
+                     const int16_t *sub_align, const double *pback_align) {
+    SPB_CHECK(c && sub_seed && pback_seed && sub_ungapped && sub_align && pback_align, "spb_set_matrices: NULL argument");
+    SPB_CUDA(cudaSetDevice(c->device));
+    const int n = SPB_ALPHABET * SPB_ALPHABET;
+    memcpy(c->hm.seed, sub_seed, n * sizeof(int16_t));
+    memcpy(c->hm.ungapped, sub_ungapped, n * sizeof(int16_t));
+    memcpy(c->hm.align, sub_align, n * sizeof(int16_t));
+    memcpy(c->hm.pback_seed, pback_seed, SPB_ALPHABET * sizeof(double));
+    memcpy(c->hm.pback_align, pback_align, SPB_ALPHABET * sizeof(double));
+    for (int i = 0; i < n; i++) {
+        SPB_CHECK(sub_seed[i] >= -85 && sub_seed[i] <= 85, "spb_set_matrices: seed score %d out of the supported range", sub_seed[i]);
+        SPB_CHECK(sub_ungapped[i] >= -64 && sub_ungapped[i] <= 63 && sub_align[i] >= -64 && sub_align[i] <= 63,
+                  "spb_set_matrices: alignment score out of the supported int8 range");
+    }
+    if (c->d_mat.ensure(sizeof(spb::Matrices))) return 1;
+    SPB_CUDA(cudaMemcpyAsync(c->d_mat.p, &c->hm, sizeof(spb::Matrices), cudaMemcpyHostToDevice, c->stream));
+    SPB_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_matrices = true;
+    c->have_index = false;  // 3-mer rows depend on the seed matrix
+    return 0;
+}
+
+// EvalueComputation::computeEvalue (M/alignment/EvalueComputation.h:36-40) with
+// pvalues::get_appr_tail_prob_with_cov_without_errors (lib/alp/sls_pvalues.cpp:366-541)
+double spb_evalue(const spb_gumbel *g, double y, double n, double m) {
+    const double const_val = 1.0 / sqrt(2.0 * 3.1415926535897932384626433832795);
+    double m_li_y = m - (g->a_I * y + g->b_I);
+    double vi_y = fmax(2.0 * g->alpha_I / g->lambda, g->alpha_I * y + g->beta_I);
+    double sqrt_vi_y = sqrt(vi_y);
+    double m_F = sqrt_vi_y == 0.0 ? 1e100 : m_li_y / sqrt_vi_y;
+    double P_m_F = 0.5 * erfc(-sqrt(0.5) * m_F);
+    double E_m_F = -const_val * exp(-0.5 * m_F * m_F);
+    double p1 = m_li_y * P_m_F - sqrt_vi_y * E_m_F;
+    double n_lj_y = n - (g->a_J * y + g->b_J);
+    double vj_y = fmax(2.0 * g->alpha_J / g->lambda, g->alpha_J * y + g->beta_J);
+    double sqrt_vj_y = sqrt(vj_y);
+    double n_F = sqrt_vj_y == 0.0 ? 1e100 : n_lj_y / sqrt_vj_y;
+    double P_n_F = 0.5 * erfc(-sqrt(0.5) * n_F);
+    double E_n_F = -const_val * exp(-0.5 * n_F * n_F);
+    double p2 = n_lj_y * P_n_F - sqrt_vj_y * E_n_F;
+    double c_y = fmax(2.0 * g->sigma / g->lambda, g->sigma * y + g->tau);
+    double area = p1 * p2 + c_y * (P_m_F * P_n_F);
+    return g->K * exp(-g->lambda * y) * area;
+}
+
+double spb_bitscore(const spb_gumbel *g, double score) { return (g->lambda * score - log(g->K)) / log(2.0); }
+
+}  // extern "C"

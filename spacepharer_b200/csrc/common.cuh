@@ -1,0 +1,173 @@
+// common.cuh -- shared context, error plumbing and block-level primitives of libspb200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/spb200.h"
+
+#define SPB_X 20
+#define SPB_N3 8000           // 20^3
+#define SPB_NK 64000000u      // 20^6
+#define SPB_CNT3_W 512        // score-count table width: scores -256 .. 255
+#define SPB_SCORE_OFF 256
+
+namespace spb {
+
+void set_error(const char *fmt, ...);
+
+#define SPB_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            spb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return 1;                                                                           \
+        }                                                                                       \
+    } while (0)
+
+#define SPB_CHECK(cond, ...)                \
+    do {                                    \
+        if (!(cond)) {                      \
+            spb::set_error(__VA_ARGS__);    \
+            return 1;                       \
+        }                                   \
+    } while (0)
+
+// growable device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + (bytes >> 3) + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            return 1;
+        }
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Matrices {
+    int16_t seed[SPB_ALPHABET * SPB_ALPHABET];
+    int16_t ungapped[SPB_ALPHABET * SPB_ALPHABET];
+    int16_t align[SPB_ALPHABET * SPB_ALPHABET];
+    double pback_seed[SPB_ALPHABET];
+    double pback_align[SPB_ALPHABET];
+};
+
+}  // namespace spb
+
+struct spb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    bool have_matrices = false;
+    spb::Matrices hm;             // host copy
+    spb::DevBuf d_mat;            // device copy of spb::Matrices
+
+    // ---- index (masked targets) ----
+    bool have_index = false;
+    uint32_t T = 0;
+    uint64_t n_res = 0;
+    int span = 0;
+    int pat[6] = {0, 0, 0, 0, 0, 0};
+    spb::DevBuf d_tres;           // u8[n_res + pad] masked residues
+    spb::DevBuf d_toff;           // u32[T+1]
+    spb::DevBuf d_koff;           // u32[20^6 + 1] CSR offsets
+    spb::DevBuf d_post;           // u64[n_post]: id << 16 | pos
+    uint64_t n_post = 0, n_kmers_nonempty = 0;
+    spb::DevBuf d_row3;           // u32[8000][8000]: (score + 256) << 16 | 3-mer index
+    spb::DevBuf d_cnt3;           // u16[8000][512]: #entries with score >= v
+    double build_ms = 0;
+
+    // ---- alignment targets (unmasked) ----
+    bool have_aln_targets = false;
+    uint32_t aT = 0;
+    uint64_t a_res = 0;
+    spb::DevBuf d_ares;           // u8
+    spb::DevBuf d_aoff;           // u64[aT+1]
+    std::vector<uint64_t> h_aoff; // host copy (work ordering, row order)
+    std::vector<uint32_t> h_akeys;
+
+    // ---- scratch ----
+    spb::DevBuf d_q, d_qoff, d_tmp0, d_tmp1, d_tmp2, d_tmp3, d_tmp4, d_tmp5, d_tmp6, d_tmp7;
+};
+
+namespace spb {
+
+// ---------------------------------------------------------------------------------------------
+// block-level primitives (blockDim.x threads, multiple of 32, <= 1024)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_incl_scan(int v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+// exclusive scan over the block; returns exclusive prefix, *total = block sum. wsum: int[33] in smem.
+__device__ __forceinline__ int block_excl_scan(int v, int *wsum, int *total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int inc = warp_incl_scan(v);
+    __syncthreads();
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int s = lane < nw ? wsum[lane] : 0;
+        int si = warp_incl_scan(s);
+        if (lane < nw) wsum[lane] = si - s;
+        if (lane == 31) wsum[32] = si;
+    }
+    __syncthreads();
+    int r = inc - v + wsum[wid];
+    *total = wsum[32];
+    return r;
+}
+
+// in-place bitonic sort of n_pow2 keys (ascending); caller pads with max sentinels. Works on shared or global.
+template <class K, class Less>
+__device__ __forceinline__ void block_bitonic_sort(K *a, int n_pow2, Less less) {
+    for (int k = 2; k <= n_pow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (n_pow2 >> 1); t += blockDim.x) {
+                // index of the lower element of pair t for stride j
+                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                int p = i | j;
+                bool up = ((i & k) == 0);
+                K x = a[i], y = a[p];
+                bool sw = up ? less(y, x) : less(x, y);
+                if (sw) { a[i] = y; a[p] = x; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ int next_pow2(int n) {
+    int p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+}  // namespace spb

@@ -1,0 +1,302 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle and the golden fixtures.
+Bit-exact for hit lists, scores, coordinates and CIGARs; E-values within 1e-6 relative (BASELINE.json)."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+import common as Cm
+
+pytestmark = pytest.mark.gpu
+
+EVAL_RTOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def searcher():
+    from spacepharer_b200 import api
+    s = api.Searcher(device=0)
+    yield s
+    s.close()
+
+
+def _product_mask(searcher, T):
+    from spacepharer_b200 import api
+    tres, toff = O.concat(T)
+    m, _ = api.tantan_mask(searcher.seed, tres, toff)
+    return m, toff
+
+
+def test_matrices_match_oracle(searcher):
+    m80, m40u, m40 = Cm.mats()
+    assert (searcher.seed.sub == O.matrix_sub(m80)).all()
+    assert (searcher.ungapped.sub == O.matrix_sub(m40u)).all()
+    assert (searcher.align_mat.sub == O.matrix_sub(m40)).all()
+
+
+def test_index_matches_oracle(searcher):
+    T, _ = Cm.load_fasta_set("small")
+    tres, toff = _product_mask(searcher, T)
+    m80, m40u, _ = Cm.mats()
+    st = searcher.build_index(tres, toff)
+    pf = O.Prefilter(tres, toff, m80, m40u)
+    k, i, p = pf.postings()
+    gk, gi, gp = searcher.export_index()
+    assert st["n_postings"] == len(k)
+    assert (gk == k).all() and (gi == i).all() and (gp == p).all()
+    pf.close()
+
+
+def test_similar_kmers_order(searcher):
+    """KmerGenerator parity: same list, same order (the order fixes the hit stream)"""
+    T, Q = Cm.load_fasta_set("small")
+    tres, toff = _product_mask(searcher, T)
+    m80, m40u, _ = Cm.mats()
+    searcher.build_index(tres, toff)
+    pf = O.Prefilter(tres, toff, m80, m40u)
+    rng = np.random.default_rng(3)
+    for thr in (90, 100, 112, 120, 135, 160):
+        for _ in range(6):
+            k6 = rng.integers(0, 20, 6).astype(np.uint8)
+            a = pf.similar(k6, thr)
+            b = searcher.similar_kmers(k6, thr)
+            assert len(a) == len(b) and (a == b).all(), (thr, k6)
+    pf.close()
+
+
+def _gpu_prefilter_rows(searcher, T_masked, toff, Q, tkeys=None, **kw):
+    from spacepharer_b200 import api
+    searcher.build_index(T_masked, toff)
+    qres, qoff = O.concat(Q)
+    off, hits, st = searcher.prefilter(qres, qoff, **kw)
+    return [api.format_prefilter_rows(hits[int(off[i]):int(off[i + 1])], tkeys) for i in range(len(Q))], st
+
+
+@pytest.mark.parametrize("fname,mask,maxseqs", [
+    ("pref_mask1.txt.gz", 1, 300), ("pref_mask0.txt.gz", 0, 300),
+    ("pref_mask1_max2.txt.gz", 1, 2), ("pref_mask0_max5.txt.gz", 0, 5)])
+def test_prefilter_small_golden(searcher, fname, mask, maxseqs):
+    T, Q = Cm.load_fasta_set("small")
+    tres, toff = _product_mask(searcher, T) if mask else O.concat(T)
+    rows, st = _gpu_prefilter_rows(searcher, tres, toff, Q, max_seqs=maxseqs)
+    ref = Cm.dump("small", fname)
+    bad = [(i, rows[i][:3], ref.get(i, [])[:3]) for i in range(len(Q)) if rows[i] != ref.get(i, [])]
+    assert not bad, bad[:5]
+
+
+@pytest.mark.parametrize("fname,maxseqs", [("pref_max300.txt.gz", 300), ("pref_max10.txt.gz", 10),
+                                           ("pref_max3.txt.gz", 3)])
+def test_prefilter_family_truncation_golden(searcher, fname, maxseqs):
+    T, Q = Cm.load_fasta_set("family")
+    tres, toff = _product_mask(searcher, T)
+    rows, st = _gpu_prefilter_rows(searcher, tres, toff, Q, max_seqs=maxseqs)
+    ref = Cm.dump("family", fname)
+    bad = [(i, rows[i][:3], ref.get(i, [])[:3]) for i in range(len(Q)) if rows[i] != ref.get(i, [])]
+    assert not bad, bad[:5]
+
+
+def test_prefilter_long_golden(searcher):
+    T, Q = Cm.load_fasta_set("long")
+    tres, toff = _product_mask(searcher, T)
+    rows, st = _gpu_prefilter_rows(searcher, tres, toff, Q)
+    ref = Cm.dump("long", "pref_mask1.txt.gz")
+    bad = [(i, rows[i][:3], ref.get(i, [])[:3]) for i in range(len(Q)) if rows[i] != ref.get(i, [])]
+    assert not bad, bad[:5]
+
+
+@pytest.mark.parametrize("target,fname", [("targets", "pref_0.txt.gz"), ("targets_rev", "pref_0_rev.txt.gz")])
+def test_prefilter_config1_golden(searcher, target, fname):
+    tkeys, T, qkeys, Q = Cm.load_config1(target)
+    tres, toff = _product_mask(searcher, T)
+    rows, st = _gpu_prefilter_rows(searcher, tres, toff, Q, tkeys=tkeys)
+    ref = Cm.dump("config1", fname)
+    bad = [(int(qkeys[i]), rows[i], ref.get(int(qkeys[i]), [])) for i in range(len(Q)) if rows[i] != ref.get(int(qkeys[i]), [])]
+    assert not bad, bad[:5]
+
+
+@pytest.mark.parametrize("bin_size,maxseqs", [(2, 300), (2, 4), (8, 4), (2048, 7)])
+def test_prefilter_random_vs_oracle(searcher, bin_size, maxseqs):
+    """seeded synthetic set of the benchmark's shape (scaled down), oracle finishes in seconds"""
+    from spacepharer_b200 import synth
+    tres, toff, _ = synth.make_targets(n_genomes=60, seed=5)
+    qres, qoff, _ = synth.make_query_frames(3000, tres, toff, seed=9)
+    m80, m40u, _ = Cm.mats()
+    searcher.build_index(tres, toff)
+    off, hits, st = searcher.prefilter(qres, qoff, max_seqs=maxseqs, bin_size=bin_size)
+    pf = O.Prefilter(tres, toff, m80, m40u, max_seqs=maxseqs, bin_size=bin_size)
+    ooff, ohits = pf.batch(qres, qoff)
+    pf.close()
+    assert (off == ooff).all()
+    assert (hits["id"] == ohits["id"]).all() and (hits["score"] == ohits["score"]).all() and (hits["diag"] == ohits["diag"]).all()
+    assert st["n_slow_path"] == 0
+
+
+def test_prefilter_edge_cases(searcher):
+    """empty batch, queries shorter than the k-mer span, one window only, X-only query"""
+    T, _ = Cm.load_fasta_set("small")
+    tres, toff = O.concat(T)
+    searcher.build_index(tres, toff)
+    off, hits, _ = searcher.prefilter(np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    assert len(off) == 1 and len(hits) == 0
+    Q = [T[5][:7], T[5][:8], np.full(12, 20, np.uint8), T[5][:9], T[7][10:22]]
+    qres, qoff = O.concat(Q)
+    off, hits, _ = searcher.prefilter(qres, qoff)
+    m80, m40u, _ = Cm.mats()
+    pf = O.Prefilter(tres, toff, m80, m40u)
+    ooff, ohits = pf.batch(qres, qoff)
+    pf.close()
+    assert (off == ooff).all() and (hits["id"] == ohits["id"]).all() and (hits["score"] == ohits["score"]).all()
+    assert off[1] == 0 and off[2] == off[1] and off[3] == off[2]   # no windows / single window / X never hit
+
+
+def test_prefilter_slow_path_matches(searcher):
+    """a hit list larger than the shared-memory capacity takes the global-memory variant: same result"""
+    rng = np.random.default_rng(17)
+    base = rng.integers(0, 20, 60).astype(np.uint8)
+    T = []
+    for i in range(3000):
+        t = base.copy()
+        for _ in range(3):
+            t[int(rng.integers(0, 60))] = rng.integers(0, 20)
+        T.append(np.concatenate([rng.integers(0, 20, int(rng.integers(0, 30))).astype(np.uint8), t]))
+    Q = [base[5:28].copy(), base[20:40].copy(), rng.integers(0, 20, 15).astype(np.uint8)]
+    tres, toff = O.concat(T)
+    qres, qoff = O.concat(Q)
+    searcher.build_index(tres, toff)
+    m80, m40u, _ = Cm.mats()
+    for maxseqs in (300, 50):
+        off, hits, st = searcher.prefilter(qres, qoff, max_seqs=maxseqs)
+        pf = O.Prefilter(tres, toff, m80, m40u, max_seqs=maxseqs)
+        ooff, ohits = pf.batch(qres, qoff)
+        pf.close()
+        assert st["n_slow_path"] >= 1
+        assert (off == ooff).all()
+        assert (hits["id"] == ohits["id"]).all() and (hits["score"] == ohits["score"]).all() and (hits["diag"] == ohits["diag"]).all()
+
+
+# ---------------------------------------------------------------------------------------------- align
+def _gpu_align_rows(searcher, T, Q, pairs, db_res, tkeys=None, **kw):
+    """pairs: list (per query) of target indices"""
+    from spacepharer_b200 import api
+    tres, toff = O.concat(T)
+    searcher.set_align_targets(tres, toff, tkeys)
+    qres, qoff = O.concat(Q)
+    poff = np.zeros(len(Q) + 1, dtype=np.uint64)
+    np.cumsum([len(p) for p in pairs], out=poff[1:])
+    pt = np.concatenate([np.asarray(p, dtype=np.uint32) for p in pairs]) if poff[-1] else np.zeros(0, np.uint32)
+    off, rows, cig, st = searcher.align(qres, qoff, poff, pt, db_res, **kw)
+    qlens = [len(q) for q in Q]
+    tlens = [len(t) for t in T]
+    out = [api.format_align_rows(rows[int(off[i]):int(off[i + 1])], cig, qlens, tlens, tkeys) for i in range(len(Q))]
+    return out, rows, st
+
+
+def test_align_small_golden(searcher):
+    T, Q = Cm.load_fasta_set("small")
+    pref = Cm.dump("small", "pref_mask1.txt.gz")
+    pairs = [[int(r.split("\t")[0]) for r in pref.get(i, [])] for i in range(len(Q))]
+    rows, _, _ = _gpu_align_rows(searcher, T, Q, pairs, Cm.db_res_count(T))
+    ref = Cm.dump("small", "aln_mask1.txt.gz")
+    bad = [(i, rows[i][:2], ref.get(i, [])[:2]) for i in range(len(Q)) if rows[i] != ref.get(i, [])]
+    assert not bad, bad[:4]
+
+
+def test_align_small_evalue_cut_golden(searcher):
+    T, Q = Cm.load_fasta_set("small")
+    pref = Cm.dump("small", "pref_mask1.txt.gz")
+    pairs = [[int(r.split("\t")[0]) for r in pref.get(i, [])] for i in range(len(Q))]
+    rows, _, _ = _gpu_align_rows(searcher, T, Q, pairs, Cm.db_res_count(T), evalue=1e-2)
+    ref = Cm.dump("small", "aln_mask1_e0.01.txt.gz")
+    bad = [(i, rows[i][:2], ref.get(i, [])[:2]) for i in range(len(Q)) if rows[i] != ref.get(i, [])]
+    assert not bad, bad[:4]
+
+
+def test_align_small_allpairs_golden(searcher):
+    T, Q = Cm.load_fasta_set("small")
+    pairs = [list(range(0, len(T), 3)) if i < 40 else [] for i in range(len(Q))]
+    rows, _, st = _gpu_align_rows(searcher, T, Q, pairs, Cm.db_res_count(T))
+    ref = Cm.dump("small", "aln_allpairs.txt.gz")
+    bad = [(i, rows[i][:2], ref.get(i, [])[:2]) for i in range(len(Q)) if rows[i] != ref.get(i, [])]
+    assert not bad, bad[:4]
+    assert st["n_cells"] == sum(len(Q[i]) * len(T[t]) for i in range(40) for t in pairs[i])
+
+
+def test_align_family_golden(searcher):
+    T, Q = Cm.load_fasta_set("family")
+    pref = Cm.dump("family", "pref_max300.txt.gz")
+    pairs = [[int(r.split("\t")[0]) for r in pref.get(i, [])] for i in range(len(Q))]
+    rows, _, _ = _gpu_align_rows(searcher, T, Q, pairs, Cm.db_res_count(T))
+    ref = Cm.dump("family", "aln_max300.txt.gz")
+    bad = [(i, rows[i][:2], ref.get(i, [])[:2]) for i in range(len(Q)) if rows[i] != ref.get(i, [])]
+    assert not bad, bad[:4]
+
+
+def test_align_long_striped_golden(searcher):
+    """queries of 17..150 aa: stripe-dependent E update, byte->word overflow, gapped tracebacks"""
+    T, Q = Cm.load_fasta_set("long")
+    pairs = [list(range(len(T))) for _ in Q]
+    rows, _, _ = _gpu_align_rows(searcher, T, Q, pairs, Cm.db_res_count(T), evalue=0.1)
+    ref = Cm.dump("long", "aln_allpairs_e0.1.txt.gz")
+    bad = [(i, rows[i][:2], ref.get(i, [])[:2]) for i in range(len(Q)) if rows[i] != ref.get(i, [])]
+    assert not bad, bad[:4]
+
+
+@pytest.mark.parametrize("target,pref,aln", [("targets", "pref_0.txt.gz", "prot_result.txt.gz"),
+                                             ("targets_rev", "pref_0_rev.txt.gz", "prot_result_rev.txt.gz")])
+def test_align_config1_golden(searcher, target, pref, aln):
+    tkeys, T, qkeys, Q = Cm.load_config1(target)
+    key2t = {int(k): i for i, k in enumerate(tkeys)}
+    p = Cm.dump("config1", pref)
+    pairs = [[key2t[int(r.split("\t")[0])] for r in p.get(int(qkeys[i]), [])] for i in range(len(Q))]
+    rows, _, _ = _gpu_align_rows(searcher, T, Q, pairs, Cm.db_res_count(T), tkeys=tkeys)
+    ref = Cm.dump("config1", aln)
+    bad = [(int(qkeys[i]), rows[i], ref.get(int(qkeys[i]), [])) for i in range(len(Q)) if rows[i] != ref.get(int(qkeys[i]), [])]
+    assert not bad, bad[:4]
+
+
+@pytest.mark.parametrize("go,ge", [(16, 2), (5, 1), (3, 1)])
+def test_align_random_vs_oracle(searcher, go, ge):
+    """integer fields bit-exact, E-values within 1e-6 relative; low gap costs exercise the
+    'E never opens from an F-derived cell' rule and gapped tracebacks"""
+    from spacepharer_b200 import synth
+    rng = np.random.default_rng(23)
+    tres, toff, _ = synth.make_targets(n_genomes=8, seed=6)
+    T = [tres[int(toff[i]):int(toff[i + 1])] for i in range(len(toff) - 1)]
+    Q, pairs = [], []
+    for i in range(120):
+        t = int(rng.integers(0, len(T)))
+        L = int(rng.integers(9, 33))
+        if len(T[t]) <= L + 6:
+            continue
+        s = int(rng.integers(0, len(T[t]) - L - 4))
+        q = list(T[t][s:s + L + 4])
+        for _ in range(int(rng.integers(0, 4))):
+            q[int(rng.integers(0, len(q)))] = int(rng.integers(0, 20))
+        for _ in range(int(rng.integers(0, 3))):
+            c = int(rng.integers(2, len(q) - 2))
+            if rng.random() < 0.5:
+                del q[c]
+            else:
+                q.insert(c, int(rng.integers(0, 20)))
+        Q.append(np.array(q[:L], dtype=np.uint8))
+        pairs.append([t] + [int(x) for x in rng.integers(0, len(T), 6)])
+    _, _, m40 = Cm.mats()
+    db_res = Cm.db_res_count(T)
+    rows, raw, _ = _gpu_align_rows(searcher, T, Q, pairs, db_res, gap_open=go, gap_extend=ge,
+                                   gumbel=tuple(O.GUMBEL_VTML40_16_2.values()))
+    p = O.align_params(db_res, gap_open=go, gap_extend=ge)
+    nrow = 0
+    for i, q in enumerate(Q):
+        exp = {}
+        for t in pairs[i]:
+            a = O.align_pair(m40, p, q, T[t])
+            if a.ok == 1:
+                exp[t] = a
+        got = {int(r["target"]): r for r in raw if int(r["query"]) == i}
+        assert set(got) == set(exp), (i, sorted(got), sorted(exp))
+        for t, a in exp.items():
+            r = got[t]
+            assert (int(r["score"]), int(r["bits"]), int(r["q_start"]), int(r["q_end"]), int(r["t_start"]), int(r["t_end"]),
+                    int(r["n_ident"]), int(r["aln_len"])) == (a.score, a.bits, a.qStart, a.qEnd, a.tStart, a.tEnd, a.nIdent, a.alnLen)
+            assert abs(float(r["eval"]) - a.eval) <= EVAL_RTOL * abs(a.eval)
+            nrow += 1
+    assert nrow > 100
