@@ -146,8 +146,8 @@ class Searcher:
             R = r.contents
             off = np.ctypeslib.as_array(R.offsets, shape=(Q + 1,)).copy()
             n = int(R.n_hits)
-            dt = np.dtype([("id", "<u4"), ("score", "<i4"), ("diag", "<i4")])
-            hits = np.frombuffer(C.string_at(R.hits, n * 12), dtype=dt).copy() if n else np.zeros(0, dtype=dt)
+            dt = np.dtype(capi.Hit)
+            hits = np.frombuffer(C.string_at(R.hits, n * dt.itemsize), dtype=dt).copy() if n else np.zeros(0, dtype=dt)
             stats = dict(n_kmers=int(R.n_kmers), n_db_matches=int(R.n_db_matches), n_events=int(R.n_events),
                          n_slow_path=int(R.n_slow_path), kernel_ms=float(R.kernel_ms), algo_bytes=int(R.algo_bytes))
         finally:
@@ -184,11 +184,7 @@ class Searcher:
             R = r.contents
             off = np.ctypeslib.as_array(R.offsets, shape=(Q + 1,)).copy()
             n = int(R.n_rows)
-            dt = np.dtype([("query", "<u4"), ("target", "<u4"), ("score", "<i4"), ("bits", "<i4"), ("eval", "<f8"),
-                           ("q_start", "<i4"), ("q_end", "<i4"), ("t_start", "<i4"), ("t_end", "<i4"),
-                           ("n_ident", "<i4"), ("aln_len", "<i4"), ("seq_id", "<f4"), ("cigar_off", "<u4"),
-                           ("cigar_len", "<u4")])
-            assert dt.itemsize == C.sizeof(capi.Aln)
+            dt = np.dtype(capi.Aln)
             rows = np.frombuffer(C.string_at(R.rows, n * dt.itemsize), dtype=dt).copy() if n else np.zeros(0, dtype=dt)
             cig = C.string_at(R.cigar_ops, int(R.n_cigar)) if R.n_cigar else b""
             stats = dict(n_pairs=int(R.n_pairs), n_cells=int(R.n_cells), kernel_ms=float(R.kernel_ms),
