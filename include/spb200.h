@@ -99,6 +99,7 @@ typedef struct spb_prefilter_result {
     /* counters (Prefiltering.cpp:934-957 prints the same statistics) */
     uint64_t n_kmers, n_db_matches, n_events, n_slow_path;
     double kernel_ms;        /* device time of the match kernel(s) */
+    double total_ms;         /* device time of the whole resident stage */
     uint64_t algo_bytes;     /* algorithmic bytes moved by the match kernel */
 } spb_prefilter_result;
 
@@ -158,6 +159,25 @@ void spb_free_align_result(spb_align_result *r);
  * (EvalueComputation::computeEvalue / computeBitScore, M/alignment/EvalueComputation.h:18-40) */
 double spb_evalue(const spb_gumbel *g, double score, double q_len, double db_res_count);
 double spb_bitscore(const spb_gumbel *g, double score);
+
+/* ---- resident pipeline ----------------------------------------------------------------------------
+ * The calls above are compositions of the stages below.  A caller that keeps the batch in HBM (the fused
+ * predictmatch search: prefilter -> align without the pref DB round trip of blastp.sh:33,41) uses them directly:
+ *   spb_queries_set            upload a query batch once
+ *   spb_prefilter_resident     hit lists stay on the device (spb_prefilter_fetch copies them out)
+ *   spb_pairs_from_prefilter   the resident hit lists become the alignment work list (no host round trip)
+ *   spb_pairs_set              ... or upload an explicit pair list (what `align` reads from the pref DB)
+ *   spb_align_resident         rows and CIGARs stay on the device (spb_align_fetch copies them out, sorted)
+ * spb_*_stats return the counters of the last resident run (pointer members NULL). */
+int spb_queries_set(spb_ctx *ctx, const uint8_t *q_residues, const uint64_t *q_offsets, uint32_t Q);
+int spb_prefilter_resident(spb_ctx *ctx, const spb_prefilter_params *p);
+int spb_prefilter_stats(spb_ctx *ctx, spb_prefilter_result *out);
+int spb_prefilter_fetch(spb_ctx *ctx, spb_prefilter_result **out);
+int spb_pairs_set(spb_ctx *ctx, const uint64_t *pair_offsets, const uint32_t *pair_targets);
+int spb_pairs_from_prefilter(spb_ctx *ctx);
+int spb_align_resident(spb_ctx *ctx, const spb_align_params *p);
+int spb_align_stats(spb_ctx *ctx, spb_align_result *out);
+int spb_align_fetch(spb_ctx *ctx, spb_align_result **out);
 
 /* ---- host pre-step (CPU, as in the reference) -----------------------------------------------------
  * tantan repeat masking of the target residues before the index build (--mask 1; call site

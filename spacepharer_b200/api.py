@@ -132,6 +132,95 @@ class Searcher:
                                               cap, C.byref(n)))
         return out[: min(n.value, cap)].copy()
 
+    # ---- resident stages ---------------------------------------------------------------------
+    def set_queries(self, qres, qoff):
+        qres = np.ascontiguousarray(qres, dtype=np.uint8)
+        qoff = np.ascontiguousarray(qoff, dtype=np.uint64)
+        self.Q = len(qoff) - 1
+        capi.check(self.lib.spb_queries_set(self.h, _u8(qres), _u64(qoff), self.Q))
+
+    @staticmethod
+    def _pref_stats(R):
+        return dict(n_hits=int(R.n_hits), n_kmers=int(R.n_kmers), n_db_matches=int(R.n_db_matches),
+                    n_events=int(R.n_events), n_slow_path=int(R.n_slow_path), kernel_ms=float(R.kernel_ms),
+                    total_ms=float(R.total_ms), algo_bytes=int(R.algo_bytes))
+
+    @staticmethod
+    def _aln_stats(R):
+        return dict(n_rows=int(R.n_rows), n_pairs=int(R.n_pairs), n_cells=int(R.n_cells), kernel_ms=float(R.kernel_ms),
+                    total_ms=float(R.total_ms))
+
+    def prefilter_resident(self, kmer_thr=112, max_seqs=300, min_ungapped_score=15, bin_size=2, comp_bias=1, id_base=0):
+        p = capi.PrefilterParams(kmer_thr, max_seqs, min_ungapped_score, bin_size, comp_bias, id_base)
+        capi.check(self.lib.spb_prefilter_resident(self.h, C.byref(p)))
+        R = capi.PrefilterResult()
+        capi.check(self.lib.spb_prefilter_stats(self.h, C.byref(R)))
+        return self._pref_stats(R)
+
+    def prefilter_fetch(self):
+        r = C.POINTER(capi.PrefilterResult)()
+        capi.check(self.lib.spb_prefilter_fetch(self.h, C.byref(r)))
+        try:
+            R = r.contents
+            Q = int(R.n_queries)
+            off = np.ctypeslib.as_array(R.offsets, shape=(Q + 1,)).copy()
+            n = int(R.n_hits)
+            dt = np.dtype(capi.Hit)
+            hits = np.frombuffer(C.string_at(R.hits, n * dt.itemsize), dtype=dt).copy() if n else np.zeros(0, dtype=dt)
+            stats = self._pref_stats(R)
+        finally:
+            self.lib.spb_free_prefilter_result(r)
+        return off, hits, stats
+
+    def pairs_from_prefilter(self):
+        capi.check(self.lib.spb_pairs_from_prefilter(self.h))
+
+    def set_pairs(self, pair_off, pair_targets):
+        pair_off = np.ascontiguousarray(pair_off, dtype=np.uint64)
+        pair_targets = np.ascontiguousarray(pair_targets, dtype=np.uint32)
+        capi.check(self.lib.spb_pairs_set(self.h, _u64(pair_off), pair_targets.ctypes.data_as(C.POINTER(C.c_uint32))))
+
+    def _align_params(self, db_res_count, evalue, gap_open, gap_extend, comp_bias, gumbel, byte_lanes, word_lanes):
+        g = capi.Gumbel(*(gumbel or gumbel_for(self.sub_mat_name, gap_open, gap_extend)))
+        return capi.AlignParams(gap_open, gap_extend, evalue, db_res_count, comp_bias, byte_lanes, word_lanes, g)
+
+    def align_resident(self, db_res_count, evalue=200.0, gap_open=16, gap_extend=2, comp_bias=1, gumbel=None,
+                       byte_lanes=32, word_lanes=16):
+        p = self._align_params(db_res_count, evalue, gap_open, gap_extend, comp_bias, gumbel, byte_lanes, word_lanes)
+        capi.check(self.lib.spb_align_resident(self.h, C.byref(p)))
+        R = capi.AlignResult()
+        capi.check(self.lib.spb_align_stats(self.h, C.byref(R)))
+        return self._aln_stats(R)
+
+    def align_fetch(self):
+        r = C.POINTER(capi.AlignResult)()
+        capi.check(self.lib.spb_align_fetch(self.h, C.byref(r)))
+        try:
+            R = r.contents
+            Q = int(R.n_queries)
+            off = np.ctypeslib.as_array(R.offsets, shape=(Q + 1,)).copy()
+            n = int(R.n_rows)
+            dt = np.dtype(capi.Aln)
+            rows = np.frombuffer(C.string_at(R.rows, n * dt.itemsize), dtype=dt).copy() if n else np.zeros(0, dtype=dt)
+            cig = C.string_at(R.cigar_ops, int(R.n_cigar)) if R.n_cigar else b""
+            stats = self._aln_stats(R)
+        finally:
+            self.lib.spb_free_align_result(r)
+        return off, rows, cig, stats
+
+    def search(self, qres, qoff, db_res_count, fetch_prefilter=False, **kw):
+        """Fused predictmatch search step: prefilter -> align with the hit lists kept in HBM.
+        kw: kmer_thr, max_seqs, min_ungapped_score, bin_size, comp_bias, evalue, gap_open, gap_extend, gumbel"""
+        pk = {k: kw[k] for k in ("kmer_thr", "max_seqs", "min_ungapped_score", "bin_size", "comp_bias", "id_base") if k in kw}
+        ak = {k: kw[k] for k in ("evalue", "gap_open", "gap_extend", "comp_bias", "gumbel", "byte_lanes", "word_lanes") if k in kw}
+        self.set_queries(qres, qoff)
+        pst = self.prefilter_resident(**pk)
+        pref = self.prefilter_fetch() if fetch_prefilter else None
+        self.pairs_from_prefilter()
+        ast = self.align_resident(db_res_count, **ak)
+        off, rows, cig, _ = self.align_fetch()
+        return off, rows, cig, dict(prefilter=pst, align=ast), pref
+
     # ---- prefilter ---------------------------------------------------------------------------
     def prefilter(self, qres, qoff, kmer_thr=112, max_seqs=300, min_ungapped_score=15, bin_size=2, comp_bias=1,
                   id_base=0):
@@ -148,8 +237,7 @@ class Searcher:
             n = int(R.n_hits)
             dt = np.dtype(capi.Hit)
             hits = np.frombuffer(C.string_at(R.hits, n * dt.itemsize), dtype=dt).copy() if n else np.zeros(0, dtype=dt)
-            stats = dict(n_kmers=int(R.n_kmers), n_db_matches=int(R.n_db_matches), n_events=int(R.n_events),
-                         n_slow_path=int(R.n_slow_path), kernel_ms=float(R.kernel_ms), algo_bytes=int(R.algo_bytes))
+            stats = self._pref_stats(R)
         finally:
             self.lib.spb_free_prefilter_result(r)
         return off, hits, stats
@@ -175,8 +263,7 @@ class Searcher:
         pair_off = np.ascontiguousarray(pair_off, dtype=np.uint64)
         pair_targets = np.ascontiguousarray(pair_targets, dtype=np.uint32)
         Q = len(qoff) - 1
-        g = capi.Gumbel(*(gumbel or gumbel_for(self.sub_mat_name, gap_open, gap_extend)))
-        p = capi.AlignParams(gap_open, gap_extend, evalue, db_res_count, comp_bias, byte_lanes, word_lanes, g)
+        p = self._align_params(db_res_count, evalue, gap_open, gap_extend, comp_bias, gumbel, byte_lanes, word_lanes)
         r = C.POINTER(capi.AlignResult)()
         capi.check(self.lib.spb_align(self.h, _u8(qres), _u64(qoff), Q, _u64(pair_off),
                                       pair_targets.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(p), C.byref(r)))
@@ -187,8 +274,7 @@ class Searcher:
             dt = np.dtype(capi.Aln)
             rows = np.frombuffer(C.string_at(R.rows, n * dt.itemsize), dtype=dt).copy() if n else np.zeros(0, dtype=dt)
             cig = C.string_at(R.cigar_ops, int(R.n_cigar)) if R.n_cigar else b""
-            stats = dict(n_pairs=int(R.n_pairs), n_cells=int(R.n_cells), kernel_ms=float(R.kernel_ms),
-                         total_ms=float(R.total_ms))
+            stats = self._aln_stats(R)
         finally:
             self.lib.spb_free_align_result(r)
         return off, rows, cig, stats

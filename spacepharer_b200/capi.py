@@ -31,7 +31,7 @@ class PrefilterResult(C.Structure):
     _fields_ = [("n_queries", C.c_uint32), ("offsets", C.POINTER(C.c_uint64)), ("hits", C.POINTER(Hit)),
                 ("n_hits", C.c_uint64), ("n_kmers", C.c_uint64), ("n_db_matches", C.c_uint64),
                 ("n_events", C.c_uint64), ("n_slow_path", C.c_uint64), ("kernel_ms", C.c_double),
-                ("algo_bytes", C.c_uint64)]
+                ("total_ms", C.c_double), ("algo_bytes", C.c_uint64)]
 
 
 class AlignParams(C.Structure):
@@ -59,7 +59,9 @@ SYMBOLS = [
     "spb_ctx_create", "spb_ctx_destroy", "spb_last_error", "spb_version", "spb_ctx_stream", "spb_set_matrices",
     "spb_index_build", "spb_index_stats_get", "spb_index_export", "spb_similar_kmers", "spb_prefilter",
     "spb_free_prefilter_result", "spb_align_set_targets", "spb_align", "spb_free_align_result", "spb_evalue",
-    "spb_bitscore", "spb_tantan_mask",
+    "spb_bitscore", "spb_tantan_mask", "spb_queries_set", "spb_prefilter_resident", "spb_prefilter_stats",
+    "spb_prefilter_fetch", "spb_pairs_set", "spb_pairs_from_prefilter", "spb_align_resident", "spb_align_stats",
+    "spb_align_fetch",
 ]
 
 _lib = None
@@ -104,6 +106,15 @@ def load():
     L.spb_evalue.restype = C.c_double
     L.spb_bitscore.argtypes = [C.POINTER(Gumbel), C.c_double]
     L.spb_bitscore.restype = C.c_double
+    L.spb_queries_set.argtypes = [vp, u8p, u64p, C.c_uint32]
+    L.spb_prefilter_resident.argtypes = [vp, C.POINTER(PrefilterParams)]
+    L.spb_prefilter_stats.argtypes = [vp, C.POINTER(PrefilterResult)]
+    L.spb_prefilter_fetch.argtypes = [vp, C.POINTER(C.POINTER(PrefilterResult))]
+    L.spb_pairs_set.argtypes = [vp, u64p, u32p]
+    L.spb_pairs_from_prefilter.argtypes = [vp]
+    L.spb_align_resident.argtypes = [vp, C.POINTER(AlignParams)]
+    L.spb_align_stats.argtypes = [vp, C.POINTER(AlignResult)]
+    L.spb_align_fetch.argtypes = [vp, C.POINTER(C.POINTER(AlignResult))]
     L.spb_tantan_mask.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), u8p, u64p, C.c_uint32, C.c_int, u64p]
     _lib = L
     return L

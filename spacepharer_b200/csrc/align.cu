@@ -14,6 +14,8 @@
 // The byte kernel's saturation only matters through its overflow test (max + bias >= 255 -> word kernel).
 #include <math.h>
 
+#include <cub/cub.cuh>
+
 #include <algorithm>
 #include <vector>
 
@@ -142,6 +144,8 @@ struct AlnArgs {
     const FwdItem *items;
     uint32_t nItems;
     const uint32_t *pairT;     // target id per pair (work order)
+    uint32_t *pairQ;           // out: query of every pair
+    uint8_t *accFlag;          // out: 1 if the pair passed the E-value test
     PairOut *out;
     int go, ge, byteLanes, wordLanes;
     double evalThr, dbRes;
@@ -199,6 +203,8 @@ __global__ void __launch_bounds__(128) sw_forward_kernel(AlnArgs A) {
         if (!(o.eval > A.evalThr)) o.status = 1;
     }
     A.out[pair] = o;
+    A.pairQ[pair] = it.query;
+    A.accFlag[pair] = (uint8_t)(o.status == 1);
     atomicAdd(A.cells, (unsigned long long)L * (unsigned long long)tLen);
 }
 
@@ -369,6 +375,77 @@ __global__ void sw_traceback_kernel(TbArgs A) {
     A.out[pair] = o;
 }
 
+
+// ---- work-item construction, scratch sizing and row packing (all on the device) ----
+__global__ void item_count_kernel(const uint64_t *__restrict__ pairOff, uint32_t Q, uint32_t *__restrict__ cnt) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < Q) cnt[q] = (uint32_t)((pairOff[q + 1] - pairOff[q] + 31) >> 5);
+    if (q == Q) cnt[q] = 0;
+}
+
+__global__ void item_fill_kernel(const uint64_t *__restrict__ pairOff, const uint32_t *__restrict__ itemBase, uint32_t Q,
+                                 FwdItem *__restrict__ items) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    const uint64_t a = pairOff[q], b = pairOff[q + 1];
+    uint32_t k = itemBase[q];
+    for (uint64_t s = a; s < b; s += 32, k++) {
+        FwdItem it;
+        it.query = q;
+        it.pairStart = (uint32_t)s;
+        it.count = (uint32_t)min((uint64_t)32, b - s);
+        items[k] = it;
+    }
+}
+
+__global__ void hit_ids_kernel(const spb_hit *__restrict__ hits, uint64_t n, uint32_t *__restrict__ ids) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ids[i] = hits[i].id;
+}
+
+__global__ void he_size_kernel(const PairOut *__restrict__ out, const uint32_t *__restrict__ acc, uint32_t nAcc, uint64_t *__restrict__ sz) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nAcc) sz[k] = (uint64_t)out[acc[k]].qEnd + 1;
+    if (k == nAcc) sz[k] = 0;
+}
+
+__global__ void tb_size_kernel(const PairOut *__restrict__ out, const uint32_t *__restrict__ acc, uint32_t nAcc,
+                               uint64_t *__restrict__ tbSz, uint64_t *__restrict__ cigSz, int *__restrict__ err) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == nAcc) { tbSz[k] = 0; cigSz[k] = 0; }
+    if (k >= nAcc) return;
+    const PairOut o = out[acc[k]];
+    if (o.status != 1) { atomicMax(err, (int)k + 1); tbSz[k] = 0; cigSz[k] = 0; return; }
+    const long long ql = o.qEnd - o.qStart + 1, dl = o.tEnd - o.tStart + 1;
+    long long bw = llabs(dl - ql) + 1;
+    while (bw < max(ql, dl)) bw *= 2;
+    const long long Wmax = bw * 2 + 3 + 2;
+    unsigned long long bytes = (unsigned long long)(3 * Wmax * 4 + (bw * 2 + 1) * ql * 3 + 16);
+    tbSz[k] = (bytes + 15) & ~15ull;
+    cigSz[k] = (uint64_t)(ql + dl + 2);
+}
+
+__global__ void pack_rows_kernel(const PairOut *__restrict__ out, const uint32_t *__restrict__ acc, uint32_t nAcc,
+                                 const uint32_t *__restrict__ pairQ, const uint32_t *__restrict__ pairT, spb_aln *__restrict__ rows) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nAcc) return;
+    const uint32_t pair = acc[k];
+    const PairOut o = out[pair];
+    spb_aln r;
+    r.query = pairQ[pair];
+    r.target = pairT[pair];
+    r.score = o.score;
+    r.bits = o.bits;
+    r.eval = o.eval;
+    r.q_start = o.qStart; r.q_end = o.qEnd; r.t_start = o.tStart; r.t_end = o.tEnd;
+    r.n_ident = o.nIdent;
+    r.aln_len = o.alnLen;
+    r.seq_id = (float)o.nIdent / (float)o.alnLen;   // Util::computeSeqId, --seq-id-mode 0
+    r.cigar_off = o.cigOff;
+    r.cigar_len = o.cigLen;
+    rows[k] = r;
+}
+
 }  // namespace spb
 
 using namespace spb;
@@ -388,6 +465,7 @@ extern "C" int spb_align_set_targets(spb_ctx *c, const uint8_t *residues, const 
     c->h_akeys.resize(T);
     for (uint32_t i = 0; i < T; i++) c->h_akeys[i] = keys ? keys[i] : i;
     c->have_aln_targets = true;
+    c->have_aln = false;
     return 0;
 }
 
@@ -399,112 +477,69 @@ extern "C" void spb_free_align_result(spb_align_result *r) {
     free(r);
 }
 
-extern "C" int spb_align(spb_ctx *c, const uint8_t *q_residues, const uint64_t *q_offsets, uint32_t Q,
-                         const uint64_t *pair_offsets, const uint32_t *pair_targets, const spb_align_params *p,
-                         spb_align_result **out) {
-    SPB_CHECK(c && q_offsets && pair_offsets && p && out, "spb_align: NULL argument");
+// pairs resident in c->d_pairoff (u64[Q+1]) / c->d_pairT (u32[n_pairs]); results stay in c->d_pairout / d_acc / d_cig
+static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
     SPB_CHECK(c->have_matrices, "spb_align: call spb_set_matrices first");
     SPB_CHECK(c->have_aln_targets, "spb_align: call spb_align_set_targets first");
+    SPB_CHECK(c->have_queries && c->have_pairs, "spb_align: no resident queries / pairs");
     SPB_CHECK(p->gap_open >= 0 && p->gap_open <= 255 && p->gap_extend >= 0 && p->gap_extend <= 255, "spb_align: gap costs out of range");
     SPB_CHECK(p->byte_lanes > 0 && p->word_lanes > 0, "spb_align: lanes must be positive");
-    SPB_CUDA(cudaSetDevice(c->device));
-    *out = nullptr;
     cudaStream_t st = c->stream;
-    const uint64_t NQ = q_offsets[Q];
-    const uint64_t NP = pair_offsets[Q];
-    SPB_CHECK(NP < 0xFFFFFFF0ull, "spb_align: more than 2^32 pairs in one call; split the batch");
-
-    spb_align_result *res = (spb_align_result *)calloc(1, sizeof(spb_align_result));
-    res->n_queries = Q;
-    res->offsets = (uint64_t *)calloc((size_t)Q + 1, sizeof(uint64_t));
-    res->rows = (spb_aln *)calloc(1, sizeof(spb_aln));
-    res->cigar_ops = (char *)calloc(1, 1);
-    res->n_pairs = NP;
-    if (NP == 0) { *out = res; return 0; }
-
-    // ---- work order: per query, targets by length descending (lanes of a warp finish together), <=32 per item
-    std::vector<uint32_t> pairQ(NP), pairT(NP);
-    std::vector<FwdItem> items;
-    uint32_t maxL = 0;
-    {
-        std::vector<uint32_t> tmp;
-        uint64_t w = 0;
-        for (uint32_t qi = 0; qi < Q; qi++) {
-            const uint64_t a = pair_offsets[qi], b = pair_offsets[qi + 1];
-            if (b == a) continue;
-            const uint32_t L = (uint32_t)(q_offsets[qi + 1] - q_offsets[qi]);
-            maxL = std::max(maxL, L);
-            tmp.assign(pair_targets + a, pair_targets + b);
-            for (uint32_t t : tmp) {
-                if (t >= c->aT) {
-                    spb::set_error("spb_align: target id %u of query %u out of range (%u targets)", t, qi, c->aT);
-                    spb_free_align_result(res);
-                    return 1;
-                }
-            }
-            std::stable_sort(tmp.begin(), tmp.end(), [&](uint32_t x, uint32_t y) {
-                return (c->h_aoff[x + 1] - c->h_aoff[x]) > (c->h_aoff[y + 1] - c->h_aoff[y]);
-            });
-            for (uint64_t k = 0; k < tmp.size(); k += 32) {
-                FwdItem it;
-                it.query = qi;
-                it.pairStart = (uint32_t)(w + k);
-                it.count = (uint32_t)std::min<uint64_t>(32, tmp.size() - k);
-                items.push_back(it);
-            }
-            for (uint32_t t : tmp) { pairQ[w] = qi; pairT[w] = t; w++; }
-        }
-    }
+    const uint32_t Q = c->Q;
+    const uint64_t NP = c->n_pairs;
+    c->have_aln = false;
+    memset(&c->aln_stats, 0, sizeof(c->aln_stats));
+    c->aln_stats.n_queries = Q;
+    c->aln_stats.n_pairs = NP;
+    c->n_acc = 0;
+    c->n_cigar = 0;
+    if (NP == 0) { c->have_aln = true; return 0; }
+    const uint32_t maxL = c->q_maxlen;
     const int Lpad = (int)((maxL + 3) & ~3u);
     const size_t perWarp = (size_t)SPB_ALPHABET * Lpad + (size_t)Lpad * 32 * sizeof(short2);
-    if (maxL == 0 || perWarp > 200 * 1024) {
-        spb::set_error("spb_align: query length %u outside the supported range of the shared-memory kernel (1..%d)", maxL,
-                       (int)(200 * 1024 / (SPB_ALPHABET + 128)));
-        spb_free_align_result(res);
-        return 1;
-    }
-    int warpsPerBlock = (int)std::min<size_t>(4, std::max<size_t>(1, (96 * 1024) / perWarp));
+    SPB_CHECK(maxL > 0 && perWarp <= 200 * 1024, "spb_align: query length %u outside the supported range of the shared-memory kernel (1..%d)",
+              maxL, (int)(200 * 1024 / (SPB_ALPHABET + 128)));
+    const int warpsPerBlock = (int)std::min<size_t>(4, std::max<size_t>(1, (96 * 1024) / perWarp));
     const size_t smem = perWarp * warpsPerBlock;
+    SPB_CUDA(cudaEventRecord(c->ev2, st));
 
-    DevBuf d_q, d_qoff, d_cb, d_qbias, d_items, d_pairQ, d_pairT, d_out, d_cells, d_acc, d_he, d_heOff, d_tbOff, d_tb, d_cigOff, d_cig;
-    std::vector<DevBuf *> all = {&d_q, &d_qoff, &d_cb, &d_qbias, &d_items, &d_pairQ, &d_pairT, &d_out, &d_cells, &d_acc,
-                                 &d_he, &d_heOff, &d_tbOff, &d_tb, &d_cigOff, &d_cig};
-    auto fail = [&]() { for (DevBuf *b : all) b->release(); spb_free_align_result(res); return 1; };
-#define AL_CUDA(call)                                                                             \
-    do {                                                                                          \
-        cudaError_t e__ = (call);                                                                 \
-        if (e__ != cudaSuccess) {                                                                 \
-            spb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
-            return fail();                                                                        \
-        }                                                                                         \
-    } while (0)
-    if (d_q.ensure(NQ + 64) || d_qoff.ensure(((size_t)Q + 1) * 8) || d_cb.ensure(NQ + 64) || d_qbias.ensure((size_t)Q * 4) ||
-        d_items.ensure(items.size() * sizeof(FwdItem)) || d_pairQ.ensure(NP * 4) || d_pairT.ensure(NP * 4) ||
-        d_out.ensure(NP * sizeof(PairOut)) || d_cells.ensure(8)) return fail();
-    AL_CUDA(cudaEventRecord(c->ev2, st));
-    AL_CUDA(cudaMemcpyAsync(d_q.p, q_residues, NQ, cudaMemcpyHostToDevice, st));
-    AL_CUDA(cudaMemcpyAsync(d_qoff.p, q_offsets, ((size_t)Q + 1) * 8, cudaMemcpyHostToDevice, st));
-    AL_CUDA(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(FwdItem), cudaMemcpyHostToDevice, st));
-    AL_CUDA(cudaMemcpyAsync(d_pairQ.p, pairQ.data(), NP * 4, cudaMemcpyHostToDevice, st));
-    AL_CUDA(cudaMemcpyAsync(d_pairT.p, pairT.data(), NP * 4, cudaMemcpyHostToDevice, st));
-    AL_CUDA(cudaMemsetAsync(d_cells.p, 0, 8, st));
-    align_profile_kernel<<<Q, 64, 0, st>>>(d_q.as<uint8_t>(), d_qoff.as<uint64_t>(), Q, c->d_mat.as<Matrices>(), p->comp_bias,
-                                           d_cb.as<signed char>(), d_qbias.as<int>());
-    AL_CUDA(cudaGetLastError());
+    // scratch: s_a cb i8[q_res], s_b qbias int[Q], s_c itemCnt/itemBase u32[Q+1] x2, s_d items, s_e accFlag u8[NP], s_f counters
+    if (c->s_a.ensure(c->q_res + 64) || c->s_b.ensure((size_t)Q * 4 + 4) || c->s_c.ensure(((size_t)Q + 1) * 8) ||
+        c->s_e.ensure(NP + 64) || c->s_f.ensure(128) || c->d_pairQ.ensure(NP * 4) || c->d_pairout.ensure(NP * sizeof(PairOut)) ||
+        c->d_acc.ensure(NP * 4)) return 1;
+    SPB_CUDA(cudaMemsetAsync(c->s_f.p, 0, 128, st));
+    align_profile_kernel<<<Q, 64, 0, st>>>(c->d_q.as<uint8_t>(), c->d_qoff64.as<uint64_t>(), Q, c->d_mat.as<Matrices>(), p->comp_bias,
+                                           c->s_a.as<signed char>(), c->s_b.as<int>());
+    SPB_CUDA(cudaGetLastError());
+    uint32_t *itemCnt = c->s_c.as<uint32_t>(), *itemBase = itemCnt + (Q + 1);
+    item_count_kernel<<<(Q + 1 + 255) / 256, 256, 0, st>>>(c->d_pairoff.as<uint64_t>(), Q, itemCnt);
+    SPB_CUDA(cudaGetLastError());
+    size_t tmpBytes = 0;
+    SPB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, itemCnt, itemBase, (int)(Q + 1), st));
+    if (c->s_cub.ensure(tmpBytes)) return 1;
+    SPB_CUDA(cub::DeviceScan::ExclusiveSum(c->s_cub.p, tmpBytes, itemCnt, itemBase, (int)(Q + 1), st));
+    uint32_t nItems = 0;
+    SPB_CUDA(cudaMemcpyAsync(&nItems, itemBase + Q, 4, cudaMemcpyDeviceToHost, st));
+    SPB_CUDA(cudaStreamSynchronize(st));
+    if (c->s_d.ensure((size_t)nItems * sizeof(FwdItem) + 16)) return 1;
+    item_fill_kernel<<<(Q + 255) / 256, 256, 0, st>>>(c->d_pairoff.as<uint64_t>(), itemBase, Q, c->s_d.as<FwdItem>());
+    SPB_CUDA(cudaGetLastError());
 
     AlnArgs A;
     memset(&A, 0, sizeof(A));
-    A.q = d_q.as<uint8_t>();
-    A.qoff = d_qoff.as<uint64_t>();
-    A.qcb = d_cb.as<signed char>();
-    A.qbias = d_qbias.as<int>();
+    A.q = c->d_q.as<uint8_t>();
+    A.qoff = c->d_qoff64.as<uint64_t>();
+    A.qcb = c->s_a.as<signed char>();
+    A.qbias = c->s_b.as<int>();
     A.tres = c->d_ares.as<uint8_t>();
     A.toff = c->d_aoff.as<uint64_t>();
     A.mat = c->d_mat.as<Matrices>();
-    A.items = d_items.as<FwdItem>();
-    A.nItems = (uint32_t)items.size();
-    A.pairT = d_pairT.as<uint32_t>();
-    A.out = d_out.as<PairOut>();
+    A.items = c->s_d.as<FwdItem>();
+    A.nItems = nItems;
+    A.pairT = c->d_pairT.as<uint32_t>();
+    A.pairQ = c->d_pairQ.as<uint32_t>();
+    A.accFlag = c->s_e.as<uint8_t>();
+    A.out = c->d_pairout.as<PairOut>();
     A.go = p->gap_open;
     A.ge = p->gap_extend;
     A.byteLanes = p->byte_lanes;
@@ -513,109 +548,193 @@ extern "C" int spb_align(spb_ctx *c, const uint8_t *q_residues, const uint64_t *
     A.dbRes = (double)p->db_res_count;
     A.g = p->gumbel;
     A.Lpad = Lpad;
-    A.cells = d_cells.as<unsigned long long>();
-    AL_CUDA(cudaFuncSetAttribute(sw_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AL_CUDA(cudaEventRecord(c->ev0, st));
-    sw_forward_kernel<<<(unsigned)((items.size() + warpsPerBlock - 1) / warpsPerBlock), 32 * warpsPerBlock, smem, st>>>(A);
-    AL_CUDA(cudaGetLastError());
-    AL_CUDA(cudaEventRecord(c->ev1, st));
+    A.cells = c->s_f.as<unsigned long long>();
+    SPB_CUDA(cudaFuncSetAttribute(sw_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SPB_CUDA(cudaEventRecord(c->ev0, st));
+    sw_forward_kernel<<<(nItems + warpsPerBlock - 1) / warpsPerBlock, 32 * warpsPerBlock, smem, st>>>(A);
+    SPB_CUDA(cudaGetLastError());
+    SPB_CUDA(cudaEventRecord(c->ev1, st));
 
-    std::vector<PairOut> h_out(NP);
-    AL_CUDA(cudaMemcpyAsync(h_out.data(), d_out.p, NP * sizeof(PairOut), cudaMemcpyDeviceToHost, st));
-    unsigned long long cells = 0;
-    AL_CUDA(cudaMemcpyAsync(&cells, d_cells.p, 8, cudaMemcpyDeviceToHost, st));
-    AL_CUDA(cudaStreamSynchronize(st));
+    // ---- accepted pairs
+    unsigned long long *d_ctr = c->s_f.as<unsigned long long>();   // [0] cells, [1] nAcc (as u32), [2] error
+    uint32_t *d_nAcc = reinterpret_cast<uint32_t *>(d_ctr + 1);
+    int *d_err = reinterpret_cast<int *>(d_ctr + 2);
+    cub::CountingInputIterator<uint32_t> cnt_it(0);
+    SPB_CUDA(cub::DeviceSelect::Flagged(nullptr, tmpBytes, cnt_it, c->s_e.as<uint8_t>(), c->d_acc.as<uint32_t>(), d_nAcc, (int)NP, st));
+    if (c->s_cub.ensure(tmpBytes)) return 1;
+    SPB_CUDA(cub::DeviceSelect::Flagged(c->s_cub.p, tmpBytes, cnt_it, c->s_e.as<uint8_t>(), c->d_acc.as<uint32_t>(), d_nAcc, (int)NP, st));
+    unsigned long long h_ctr[3];
+    SPB_CUDA(cudaMemcpyAsync(h_ctr, d_ctr, 24, cudaMemcpyDeviceToHost, st));
+    SPB_CUDA(cudaStreamSynchronize(st));
     float ms = 0;
-    AL_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    res->kernel_ms = ms;
-    res->n_cells = cells;
-
-    // ---- accepted pairs: reverse pass + traceback
-    std::vector<uint32_t> acc;
-    for (uint64_t i = 0; i < NP; i++) if (h_out[i].status == 1) acc.push_back((uint32_t)i);
-    const uint32_t nAcc = (uint32_t)acc.size();
+    SPB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->aln_stats.kernel_ms = ms;
+    c->aln_stats.n_cells = h_ctr[0];
+    const uint32_t nAcc = (uint32_t)(h_ctr[1] & 0xFFFFFFFFull);
     if (nAcc) {
-        std::vector<uint64_t> heOff(nAcc + 1, 0), tbOff(nAcc + 1, 0), cigOff(nAcc + 1, 0);
-        for (uint32_t k = 0; k < nAcc; k++) heOff[k + 1] = heOff[k] + (uint64_t)h_out[acc[k]].qEnd + 1;
-        if (d_acc.ensure((size_t)nAcc * 4) || d_he.ensure(heOff[nAcc] * sizeof(short2) + 16) || d_heOff.ensure(((size_t)nAcc + 1) * 8)) return fail();
-        AL_CUDA(cudaMemcpyAsync(d_acc.p, acc.data(), (size_t)nAcc * 4, cudaMemcpyHostToDevice, st));
-        AL_CUDA(cudaMemcpyAsync(d_heOff.p, heOff.data(), ((size_t)nAcc + 1) * 8, cudaMemcpyHostToDevice, st));
+        // scratch: s_g he offsets u64[nAcc+1] (+ sizes), s_h he scratch, s_i tb offsets, s_j cig offsets, s_k tb scratch
+        if (c->s_g.ensure(((size_t)nAcc + 1) * 16)) return 1;
+        uint64_t *heSz = c->s_g.as<uint64_t>(), *heOff = heSz + (nAcc + 1);
+        he_size_kernel<<<(nAcc + 1 + 255) / 256, 256, 0, st>>>(A.out, c->d_acc.as<uint32_t>(), nAcc, heSz);
+        SPB_CUDA(cudaGetLastError());
+        SPB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, heSz, heOff, (int)(nAcc + 1), st));
+        if (c->s_cub.ensure(tmpBytes)) return 1;
+        SPB_CUDA(cub::DeviceScan::ExclusiveSum(c->s_cub.p, tmpBytes, heSz, heOff, (int)(nAcc + 1), st));
+        uint64_t heTotal = 0;
+        SPB_CUDA(cudaMemcpyAsync(&heTotal, heOff + nAcc, 8, cudaMemcpyDeviceToHost, st));
+        SPB_CUDA(cudaStreamSynchronize(st));
+        if (c->s_h.ensure(heTotal * sizeof(short2) + 16)) return 1;
         TbArgs B;
         memset(&B, 0, sizeof(B));
         B.q = A.q; B.qoff = A.qoff; B.qcb = A.qcb; B.tres = A.tres; B.toff = A.toff; B.mat = A.mat;
-        B.acc = d_acc.as<uint32_t>();
+        B.acc = c->d_acc.as<uint32_t>();
         B.nAcc = nAcc;
-        B.pairQ = d_pairQ.as<uint32_t>();
-        B.pairT = d_pairT.as<uint32_t>();
+        B.pairQ = A.pairQ;
+        B.pairT = A.pairT;
         B.out = A.out;
         B.go = A.go; B.ge = A.ge; B.byteLanes = A.byteLanes; B.wordLanes = A.wordLanes;
-        B.heScratch = d_he.as<short2>();
-        B.heOff = d_heOff.as<uint64_t>();
+        B.heScratch = c->s_h.as<short2>();
+        B.heOff = heOff;
         sw_reverse_kernel<<<(nAcc + 63) / 64, 64, 0, st>>>(B);
-        AL_CUDA(cudaGetLastError());
-        AL_CUDA(cudaMemcpyAsync(h_out.data(), d_out.p, NP * sizeof(PairOut), cudaMemcpyDeviceToHost, st));
-        AL_CUDA(cudaStreamSynchronize(st));
-        for (uint32_t k = 0; k < nAcc; k++) {
-            const PairOut &o = h_out[acc[k]];
-            if (o.status != 1) {
-                spb::set_error("spb_align: forward and reverse Smith-Waterman scores differ for query %u target %u", pairQ[acc[k]], pairT[acc[k]]);
-                return fail();
-            }
-            const int64_t ql = o.qEnd - o.qStart + 1, dl = o.tEnd - o.tStart + 1;
-            int64_t bw = std::llabs(dl - ql) + 1;
-            while (bw < std::max(ql, dl)) bw *= 2;
-            const int64_t Wmax = bw * 2 + 3 + 2;
-            uint64_t bytes = (uint64_t)(3 * Wmax * 4 + (bw * 2 + 1) * ql * 3 + 16);
-            bytes = (bytes + 15) & ~15ull;
-            tbOff[k + 1] = tbOff[k] + bytes;
-            cigOff[k + 1] = cigOff[k] + (uint64_t)(ql + dl + 2);
-        }
-        if (d_tbOff.ensure(((size_t)nAcc + 1) * 8) || d_tb.ensure(tbOff[nAcc] + 64) || d_cigOff.ensure(((size_t)nAcc + 1) * 8) ||
-            d_cig.ensure(cigOff[nAcc] + 64)) return fail();
-        AL_CUDA(cudaMemcpyAsync(d_tbOff.p, tbOff.data(), ((size_t)nAcc + 1) * 8, cudaMemcpyHostToDevice, st));
-        AL_CUDA(cudaMemcpyAsync(d_cigOff.p, cigOff.data(), ((size_t)nAcc + 1) * 8, cudaMemcpyHostToDevice, st));
-        B.tbOff = d_tbOff.as<uint64_t>();
-        B.tbScratch = d_tb.as<unsigned char>();
-        B.cigOff = d_cigOff.as<uint64_t>();
-        B.cigar = d_cig.as<char>();
+        SPB_CUDA(cudaGetLastError());
+        if (c->s_i.ensure(((size_t)nAcc + 1) * 16) || c->s_j.ensure(((size_t)nAcc + 1) * 16)) return 1;
+        uint64_t *tbSz = c->s_i.as<uint64_t>(), *tbOff = tbSz + (nAcc + 1);
+        uint64_t *cigSz = c->s_j.as<uint64_t>(), *cigOff = cigSz + (nAcc + 1);
+        tb_size_kernel<<<(nAcc + 1 + 255) / 256, 256, 0, st>>>(A.out, c->d_acc.as<uint32_t>(), nAcc, tbSz, cigSz, d_err);
+        SPB_CUDA(cudaGetLastError());
+        SPB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, tbSz, tbOff, (int)(nAcc + 1), st));
+        if (c->s_cub.ensure(tmpBytes)) return 1;
+        SPB_CUDA(cub::DeviceScan::ExclusiveSum(c->s_cub.p, tmpBytes, tbSz, tbOff, (int)(nAcc + 1), st));
+        SPB_CUDA(cub::DeviceScan::ExclusiveSum(c->s_cub.p, tmpBytes, cigSz, cigOff, (int)(nAcc + 1), st));
+        uint64_t tbTotal = 0, cigTotal = 0;
+        int h_err = 0;
+        SPB_CUDA(cudaMemcpyAsync(&tbTotal, tbOff + nAcc, 8, cudaMemcpyDeviceToHost, st));
+        SPB_CUDA(cudaMemcpyAsync(&cigTotal, cigOff + nAcc, 8, cudaMemcpyDeviceToHost, st));
+        SPB_CUDA(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, st));
+        SPB_CUDA(cudaStreamSynchronize(st));
+        SPB_CHECK(h_err == 0, "spb_align: forward and reverse Smith-Waterman scores differ (accepted pair #%d)", h_err - 1);
+        if (c->s_k.ensure(tbTotal + 64) || c->d_cig.ensure(cigTotal + 64)) return 1;
+        B.tbOff = tbOff;
+        B.tbScratch = c->s_k.as<unsigned char>();
+        B.cigOff = cigOff;
+        B.cigar = c->d_cig.as<char>();
         sw_traceback_kernel<<<(nAcc + 63) / 64, 64, 0, st>>>(B);
-        AL_CUDA(cudaGetLastError());
-        AL_CUDA(cudaMemcpyAsync(h_out.data(), d_out.p, NP * sizeof(PairOut), cudaMemcpyDeviceToHost, st));
-        free(res->cigar_ops);
-        res->cigar_ops = (char *)malloc(cigOff[nAcc] + 1);
-        res->n_cigar = cigOff[nAcc];
-        AL_CUDA(cudaMemcpyAsync(res->cigar_ops, d_cig.p, cigOff[nAcc], cudaMemcpyDeviceToHost, st));
-        AL_CUDA(cudaStreamSynchronize(st));
+        SPB_CUDA(cudaGetLastError());
+        c->n_cigar = cigTotal;
     }
+    SPB_CUDA(cudaEventRecord(c->ev3, st));
+    SPB_CUDA(cudaStreamSynchronize(st));
+    SPB_CUDA(cudaEventElapsedTime(&ms, c->ev2, c->ev3));
+    c->aln_stats.total_ms = ms;
+    c->aln_stats.n_rows = nAcc;
+    c->n_acc = nAcc;
+    c->have_aln = true;
+    return 0;
+}
 
-    // ---- rows per query, sorted like Matcher::compareHits (Matcher.h:156-167); Alignment::checkCriteria keeps eval <= thr
-    std::vector<uint64_t> cnt(Q + 1, 0);
-    for (uint32_t k = 0; k < nAcc; k++) cnt[pairQ[acc[k]] + 1]++;
-    for (uint32_t i = 0; i < Q; i++) cnt[i + 1] += cnt[i];
-    memcpy(res->offsets, cnt.data(), ((size_t)Q + 1) * 8);
-    free(res->rows);
-    res->rows = (spb_aln *)calloc(std::max<size_t>(nAcc, 1), sizeof(spb_aln));
-    res->n_rows = nAcc;
-    {
-        std::vector<uint64_t> fill(cnt.begin(), cnt.end() - 1);
-        for (uint32_t k = 0; k < nAcc; k++) {
-            const uint32_t pair = acc[k];
-            const PairOut &o = h_out[pair];
-            spb_aln &r = res->rows[fill[pairQ[pair]]++];
-            r.query = pairQ[pair];
-            r.target = pairT[pair];
-            r.score = o.score;
-            r.bits = o.bits;
-            r.eval = o.eval;
-            r.q_start = o.qStart; r.q_end = o.qEnd; r.t_start = o.tStart; r.t_end = o.tEnd;
-            r.n_ident = o.nIdent;
-            r.aln_len = o.alnLen;
-            r.seq_id = (float)o.nIdent / (float)o.alnLen;   // Util::computeSeqId, --seq-id-mode 0
-            r.cigar_off = o.cigOff;
-            r.cigar_len = o.cigLen;
+extern "C" int spb_pairs_set(spb_ctx *c, const uint64_t *pair_offsets, const uint32_t *pair_targets) {
+    SPB_CHECK(c && pair_offsets, "spb_pairs_set: NULL argument");
+    SPB_CHECK(c->have_queries, "spb_pairs_set: no resident query batch (spb_queries_set)");
+    SPB_CHECK(c->have_aln_targets, "spb_pairs_set: call spb_align_set_targets first");
+    SPB_CUDA(cudaSetDevice(c->device));
+    const uint32_t Q = c->Q;
+    const uint64_t NP = pair_offsets[Q];
+    SPB_CHECK(NP < 0x7FFFFFF0ull, "spb_pairs_set: more than 2^31 pairs in one call; split the batch");
+    SPB_CHECK(NP == 0 || pair_targets, "spb_pairs_set: NULL targets");
+    // work order: per query, targets by length descending so that the lanes of a warp finish together
+    std::vector<uint32_t> pairT(NP);
+    for (uint32_t qi = 0; qi < Q; qi++) {
+        const uint64_t a = pair_offsets[qi], b = pair_offsets[qi + 1];
+        SPB_CHECK(b >= a && b <= NP, "spb_pairs_set: offsets not monotone at %u", qi);
+        for (uint64_t k = a; k < b; k++) {
+            SPB_CHECK(pair_targets[k] < c->aT, "spb_align: target id %u of query %u out of range (%u targets)", pair_targets[k], qi, c->aT);
+            pairT[k] = pair_targets[k];
         }
+        if (b - a > 1)
+            std::stable_sort(pairT.begin() + a, pairT.begin() + b, [&](uint32_t x, uint32_t y) {
+                return (c->h_aoff[x + 1] - c->h_aoff[x]) > (c->h_aoff[y + 1] - c->h_aoff[y]);
+            });
+    }
+    if (c->d_pairoff.ensure(((size_t)Q + 1) * 8) || c->d_pairT.ensure(NP * 4 + 16)) return 1;
+    SPB_CUDA(cudaMemcpyAsync(c->d_pairoff.p, pair_offsets, ((size_t)Q + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    if (NP) SPB_CUDA(cudaMemcpyAsync(c->d_pairT.p, pairT.data(), NP * 4, cudaMemcpyHostToDevice, c->stream));
+    SPB_CUDA(cudaStreamSynchronize(c->stream));
+    c->n_pairs = NP;
+    c->have_pairs = true;
+    c->have_aln = false;
+    return 0;
+}
+
+// pairs = the resident prefilter result (hit lists never leave HBM between the two stages)
+extern "C" int spb_pairs_from_prefilter(spb_ctx *c) {
+    SPB_CHECK(c, "spb_pairs_from_prefilter: NULL argument");
+    SPB_CHECK(c->have_pref, "spb_pairs_from_prefilter: no resident prefilter result");
+    SPB_CUDA(cudaSetDevice(c->device));
+    const uint32_t Q = c->Q;
+    const uint64_t NP = c->n_hits;
+    SPB_CHECK(NP < 0x7FFFFFF0ull, "spb_pairs_from_prefilter: more than 2^31 pairs; split the batch");
+    if (c->d_pairoff.ensure(((size_t)Q + 1) * 8) || c->d_pairT.ensure(NP * 4 + 16)) return 1;
+    SPB_CUDA(cudaMemcpyAsync(c->d_pairoff.p, c->d_hitoff.p, ((size_t)Q + 1) * 8, cudaMemcpyDeviceToDevice, c->stream));
+    if (NP) {
+        hit_ids_kernel<<<(unsigned)((NP + 255) / 256), 256, 0, c->stream>>>(c->d_hits.as<spb_hit>(), NP, c->d_pairT.as<uint32_t>());
+        SPB_CUDA(cudaGetLastError());
+    }
+    c->n_pairs = NP;
+    c->have_pairs = true;
+    c->have_aln = false;
+    return 0;
+}
+
+extern "C" int spb_align_resident(spb_ctx *c, const spb_align_params *p) {
+    SPB_CHECK(c && p, "spb_align_resident: NULL argument");
+    SPB_CUDA(cudaSetDevice(c->device));
+    return align_pipeline(c, p);
+}
+
+extern "C" int spb_align_stats(spb_ctx *c, spb_align_result *out) {
+    SPB_CHECK(c && out, "spb_align_stats: NULL argument");
+    SPB_CHECK(c->have_aln, "spb_align_stats: no resident alignment result");
+    *out = c->aln_stats;
+    out->offsets = nullptr;
+    out->rows = nullptr;
+    out->cigar_ops = nullptr;
+    return 0;
+}
+
+extern "C" int spb_align_fetch(spb_ctx *c, spb_align_result **out) {
+    SPB_CHECK(c && out, "spb_align_fetch: NULL argument");
+    SPB_CHECK(c->have_aln, "spb_align_fetch: no resident alignment result");
+    SPB_CUDA(cudaSetDevice(c->device));
+    *out = nullptr;
+    cudaStream_t st = c->stream;
+    const uint32_t Q = c->Q;
+    const uint32_t nAcc = (uint32_t)c->n_acc;
+    spb_align_result *res = (spb_align_result *)calloc(1, sizeof(spb_align_result));
+    *res = c->aln_stats;
+    res->offsets = (uint64_t *)calloc((size_t)Q + 1, sizeof(uint64_t));
+    res->rows = (spb_aln *)calloc(std::max<size_t>(nAcc, 1), sizeof(spb_aln));
+    res->cigar_ops = (char *)malloc(c->n_cigar + 1);
+    res->n_cigar = c->n_cigar;
+    res->n_rows = nAcc;
+    if (nAcc) {
+        if (c->s_g.ensure((size_t)nAcc * sizeof(spb_aln))) { spb_free_align_result(res); return 1; }
+        pack_rows_kernel<<<(nAcc + 255) / 256, 256, 0, st>>>(c->d_pairout.as<PairOut>(), c->d_acc.as<uint32_t>(), nAcc,
+                                                             c->d_pairQ.as<uint32_t>(), c->d_pairT.as<uint32_t>(), c->s_g.as<spb_aln>());
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(res->rows, c->s_g.p, (size_t)nAcc * sizeof(spb_aln), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && c->n_cigar) e = cudaMemcpyAsync(res->cigar_ops, c->d_cig.p, c->n_cigar, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            spb_free_align_result(res);
+            spb::set_error("spb_align_fetch: %s", cudaGetErrorString(e));
+            return 1;
+        }
+        // rows arrive grouped by query (pair order); per query sort like Matcher::compareHits (Matcher.h:156-167)
+        for (uint32_t k = 0; k < nAcc; k++) res->offsets[res->rows[k].query + 1]++;
+        for (uint32_t i = 0; i < Q; i++) res->offsets[i + 1] += res->offsets[i];
         for (uint32_t qi = 0; qi < Q; qi++) {
-            std::sort(res->rows + cnt[qi], res->rows + cnt[qi + 1], [&](const spb_aln &x, const spb_aln &y) {
+            if (res->offsets[qi + 1] - res->offsets[qi] < 2) continue;
+            std::sort(res->rows + res->offsets[qi], res->rows + res->offsets[qi + 1], [&](const spb_aln &x, const spb_aln &y) {
                 if (x.eval != y.eval) return x.eval < y.eval;
                 if (x.bits != y.bits) return x.bits > y.bits;
                 const uint64_t lx = c->h_aoff[x.target + 1] - c->h_aoff[x.target], ly = c->h_aoff[y.target + 1] - c->h_aoff[y.target];
@@ -624,12 +743,17 @@ extern "C" int spb_align(spb_ctx *c, const uint8_t *q_residues, const uint64_t *
             });
         }
     }
-    AL_CUDA(cudaEventRecord(c->ev3, st));
-    AL_CUDA(cudaStreamSynchronize(st));
-    AL_CUDA(cudaEventElapsedTime(&ms, c->ev2, c->ev3));
-    res->total_ms = ms;
-#undef AL_CUDA
-    for (DevBuf *b : all) b->release();
     *out = res;
     return 0;
+}
+
+extern "C" int spb_align(spb_ctx *c, const uint8_t *q_residues, const uint64_t *q_offsets, uint32_t Q,
+                         const uint64_t *pair_offsets, const uint32_t *pair_targets, const spb_align_params *p,
+                         spb_align_result **out) {
+    SPB_CHECK(c && q_offsets && pair_offsets && p && out, "spb_align: NULL argument");
+    *out = nullptr;
+    if (spb_queries_set(c, q_residues, q_offsets, Q)) return 1;
+    if (spb_pairs_set(c, pair_offsets, pair_targets)) return 1;
+    if (spb_align_resident(c, p)) return 1;
+    return spb_align_fetch(c, out);
 }

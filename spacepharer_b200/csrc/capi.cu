@@ -47,8 +47,10 @@ void spb_ctx_destroy(spb_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     spb::DevBuf *bufs[] = {&c->d_mat, &c->d_tres, &c->d_toff, &c->d_koff, &c->d_post, &c->d_row3, &c->d_cnt3,
-                           &c->d_ares, &c->d_aoff, &c->d_q, &c->d_qoff, &c->d_tmp0, &c->d_tmp1, &c->d_tmp2,
-                           &c->d_tmp3, &c->d_tmp4, &c->d_tmp5, &c->d_tmp6, &c->d_tmp7};
+                           &c->d_ares, &c->d_aoff, &c->d_q, &c->d_qoff, &c->d_qoff64, &c->d_hits, &c->d_hitoff,
+                           &c->d_pairoff, &c->d_pairT, &c->d_pairQ, &c->d_pairout, &c->d_acc, &c->d_cig,
+                           &c->s_a, &c->s_b, &c->s_c, &c->s_d, &c->s_e, &c->s_f, &c->s_g, &c->s_h, &c->s_i, &c->s_j,
+                           &c->s_k, &c->s_cub};
     for (spb::DevBuf *b : bufs) b->release();
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);

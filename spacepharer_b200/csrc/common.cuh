@@ -106,8 +106,36 @@ struct spb_ctx {
     std::vector<uint64_t> h_aoff; // host copy (work ordering, row order)
     std::vector<uint32_t> h_akeys;
 
-    // ---- scratch ----
-    spb::DevBuf d_q, d_qoff, d_tmp0, d_tmp1, d_tmp2, d_tmp3, d_tmp4, d_tmp5, d_tmp6, d_tmp7;
+    // ---- resident query batch ----
+    bool have_queries = false;
+    uint32_t Q = 0;
+    uint64_t q_res = 0;
+    uint32_t q_maxlen = 0;
+    spb::DevBuf d_q;              // u8[q_res]
+    spb::DevBuf d_qoff;           // u32[Q+1]
+    spb::DevBuf d_qoff64;         // u64[Q+1]
+
+    // ---- resident prefilter result (query order) ----
+    bool have_pref = false;
+    uint64_t n_hits = 0;
+    spb::DevBuf d_hits;           // spb_hit[n_hits]
+    spb::DevBuf d_hitoff;         // u64[Q+1]
+    spb_prefilter_result pref_stats;   // counters of the last run (pointers unused)
+
+    // ---- resident alignment input / result ----
+    bool have_pairs = false, have_aln = false;
+    uint64_t n_pairs = 0;
+    spb::DevBuf d_pairoff;        // u64[Q+1]
+    spb::DevBuf d_pairT;          // u32[n_pairs] (work order)
+    spb::DevBuf d_pairQ;          // u32[n_pairs]
+    spb::DevBuf d_pairout;        // PairOut[n_pairs]
+    spb::DevBuf d_acc;            // u32[n_acc] accepted pair indices
+    uint64_t n_acc = 0, n_cigar = 0;
+    spb::DevBuf d_cig;            // char[n_cigar]
+    spb_align_result aln_stats;
+
+    // ---- scratch (grow-only, reused across calls) ----
+    spb::DevBuf s_a, s_b, s_c, s_d, s_e, s_f, s_g, s_h, s_i, s_j, s_k, s_cub;
 };
 
 namespace spb {

@@ -5,9 +5,8 @@
 //  CacheFriendlyOperations.cpp:146-235,311-341; UngappedAlignment.cpp:27-51,216-233,295-403).
 //
 // The reference consumes a sequential hit stream ordered by (window, similar-k-mer rank, posting order) and runs
-// order-dependent per-target byte state machines over it.  Here every hit is tagged with (id, window, rank),
-// the CTA sorts its hits by that key in shared memory, and every reference rule becomes a comparison between
-// neighbours of the sorted list:
+// order-dependent per-target byte state machines over it.  Here every hit carries (id, window, rank); once the hits
+// of a target are sorted by (window, rank) every reference rule is a comparison between neighbours:
 //   double hit      : hit i is an event iff its 8-bit diagonal equals that of the previous hit of the same target,
 //                     or -- first hit of a target -- equals 0 (quirk B: the byte array starts zeroed)
 //   event de-dup    : an event is kept iff the previous EVENT of the same target has a different 8-bit diagonal
@@ -15,6 +14,14 @@
 //   truncation      : order key (score desc, id & (BIN-1), window, rank, id) == order of the reference's two stable
 //                     counting sorts over the bin-major event list
 // Windows w >= P-1 (the last window) never contribute (quirk A, CacheFriendlyOperations.cpp:43).
+//
+// Almost every index hit belongs to a target that is hit once and can never be an event.  The kernel therefore
+// enumerates the hit stream twice (the second time out of L1/L2): pass 1 only marks hash(id) in two shared-memory
+// bitmaps ("seen once", "seen twice"); pass 2 keeps a hit iff its target was seen twice or its 8-bit diagonal is 0.
+// Only that short list (a few dozen records instead of ~600) is sorted and scored.  Hash collisions merely keep a
+// few harmless extra hits.  The rank key is (a << 16 | b), the position in the nested 3-mer x 3-mer enumeration.
+#include <cub/cub.cuh>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -23,11 +30,22 @@ namespace spb {
 
 struct Pattern6 { int span; int pos[6]; };
 
+struct Rec {            // one index hit
+    uint64_t hi;        // id << 32 | window << 16 | position_j
+    uint64_t lo;        // rank: outer index << 16 | inner index
+};
+__device__ __forceinline__ bool rec_less(const Rec &a, const Rec &b) {
+    const uint64_t ka = a.hi >> 16, kb = b.hi >> 16;   // (id, window)
+    return ka != kb ? ka < kb : a.lo < b.lo;
+}
+__device__ __forceinline__ uint32_t rec_id(const Rec &r) { return (uint32_t)(r.hi >> 32); }
+__device__ __forceinline__ uint32_t rec_diag16(const Rec &r) { return (uint32_t)(((r.hi >> 16) & 0xFFFFu) - (r.hi & 0xFFFFu)) & 0xFFFFu; }
+
 struct PrefArgs {
     const uint8_t *q;
     const uint32_t *qoff;
     uint32_t Q;
-    const uint32_t *qlist;   // optional list of query indices (slow path), else NULL
+    const uint32_t *qlist;   // optional list of query indices (global-memory variant), else NULL
     const uint8_t *tres;
     const uint32_t *toff;
     uint32_t T;
@@ -39,18 +57,15 @@ struct PrefArgs {
     Pattern6 pat;
     int kmerThr, maxHits, minDiag, compBias, minSubUngapped;
     uint32_t binMask, idBase;
-    int rankBits, wBits;     // record layout: id | w | rank | pos(16)
-    // storage for the global-memory variant
-    uint64_t *gScratch;      // [gridDim.x][cap]
+    Rec *gScratch;           // [gridDim.x][cap] (global-memory variant)
     uint32_t cap;            // record capacity per CTA
-    // outputs
     spb_hit *arena;
-    unsigned long long *cursor;  // [0] arena cursor, [1] kmers, [2] dbMatches, [3] events, [4] gather bytes
+    unsigned long long *cursor;  // [0] arena cursor, [1] kmers, [2] dbMatches, [3] events, [4] kept hits
     uint64_t arenaCap;
     uint64_t *outStart;      // per query
     uint32_t *outCount;      // per query
-    uint32_t *status;        // per query: 0 ok, 1 exceeds this variant's capacity, 2 arena overflow, 3 record layout overflow
-    uint32_t *need;          // per query: hits needed when status == 1
+    uint32_t *status;        // per query: ST_*
+    uint32_t *need;          // per query: records needed when status == ST_CAPACITY
 };
 
 #define ST_OK 0u
@@ -58,63 +73,14 @@ struct PrefArgs {
 #define ST_ARENA 2u
 #define ST_LAYOUT 3u
 
-// Enumerate the similar k-mers of one window with one warp, in the order of KmerGenerator::calculateArrayProduct:
-// outer loop over the neighbours of the first 3-mer (row order) while score >= thr - best2, inner loop over the
-// neighbours of the second 3-mer while score >= thr - s1.  f(kmer, rank, valid) is called by all 32 lanes.
-template <class F>
-__device__ __forceinline__ uint32_t warp_similar_kmers(const uint32_t *__restrict__ row3, const uint16_t *__restrict__ cnt3,
-                                                       int x1, int x2, int thr, int *s_excl, uint32_t *s_i1, F f) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t *r1 = row3 + (size_t)x1 * SPB_N3;
-    const uint32_t *r2 = row3 + (size_t)x2 * SPB_N3;
-    const uint16_t *c1 = cnt3 + (size_t)x1 * SPB_CNT3_W;
-    const uint16_t *c2 = cnt3 + (size_t)x2 * SPB_CNT3_W;
-    const int best2 = (int)(__ldg(r2) >> 16) - SPB_SCORE_OFF;
-    int cut1 = thr - best2;
-    cut1 = max(-SPB_SCORE_OFF, min(cut1, SPB_CNT3_W - SPB_SCORE_OFF - 1));
-    const int n1 = (thr - best2 > SPB_CNT3_W - SPB_SCORE_OFF - 1) ? 0 : (int)__ldg(c1 + cut1 + SPB_SCORE_OFF);
-    uint32_t rankBase = 0;
-    for (int a0 = 0; a0 < n1; a0 += 32) {
-        const int a = a0 + lane;
-        uint32_t e1 = 0;
-        int n2 = 0;
-        if (a < n1) {
-            e1 = __ldg(r1 + a);
-            int s1 = (int)(e1 >> 16) - SPB_SCORE_OFF;
-            int cut2 = thr - s1;
-            if (cut2 <= SPB_CNT3_W - SPB_SCORE_OFF - 1) {
-                cut2 = max(cut2, -SPB_SCORE_OFF);
-                n2 = (int)__ldg(c2 + cut2 + SPB_SCORE_OFF);
-            }
-        }
-        int inc = warp_incl_scan(n2);
-        const int total = __shfl_sync(0xffffffffu, inc, 31);
-        __syncwarp();
-        s_excl[lane] = inc - n2;
-        s_i1[lane] = e1 & 0xFFFFu;
-        __syncwarp();
-        for (int p0 = 0; p0 < total; p0 += 32) {
-            const int p = p0 + lane;
-            const bool valid = p < total;
-            uint32_t kmer = 0;
-            if (valid) {
-                // largest j with s_excl[j] <= p
-                int lo = 0, hi = 31;
-#pragma unroll
-                for (int it = 0; it < 5; it++) {
-                    int mid = (lo + hi + 1) >> 1;
-                    if (s_excl[mid] <= p) lo = mid; else hi = mid - 1;
-                }
-                const int b = p - s_excl[lo];
-                kmer = s_i1[lo] + 8000u * (__ldg(r2 + b) & 0xFFFFu);
-            }
-            f(kmer, rankBase + (uint32_t)p, valid);
-        }
-        rankBase += (uint32_t)total;
-        __syncwarp();
-    }
-    return rankBase;
-}
+#define PF_THREADS 128
+#define PF_WARPS (PF_THREADS / 32)
+#define PF_MAXL 512          // longest query whose per-position arrays fit the static shared memory
+#define PF_BM_BITS 32768     // bits per "seen" bitmap
+#define PF_BM_WORDS (PF_BM_BITS / 32)
+#define PF_SMEM_CAP 1024u    // records per CTA in shared memory (16 KB)
+
+__device__ __forceinline__ uint32_t id_hash(uint32_t id) { return (id * 2654435761u) >> (32 - 15); }
 
 // UngappedAlignment::computeSingelSequenceScores + scalarDiagonalScoring (UngappedAlignment.cpp:37-51,368-382)
 __device__ __forceinline__ int ungapped_diag(const uint8_t *__restrict__ t, uint32_t tLen, const uint8_t *q, int L,
@@ -166,31 +132,23 @@ __device__ __forceinline__ int ungapped_u16(const uint8_t *__restrict__ tres, co
     return ungapped_diag(t, tLen, q, L, corr, m40u, (int)(short)diag16);
 }
 
-#define PF_THREADS 128
-#define PF_WARPS (PF_THREADS / 32)
-#define PF_MAXL_SMEM 512     // queries up to this length keep their per-position arrays in shared memory
-
-// In-place stable compaction of a[0..n) (and optionally b[0..n)) keeping elements with flag; the flag functor sees
-// (index, element, previous element or ~0 for index 0).  Returns the new length (uniform across the block).
+// In-place stable compaction of a[0..n) keeping elements with flag(i, a[i], a[i-1]); returns the new length.
 template <class Flag>
-__device__ __forceinline__ int block_compact_prev(uint64_t *a, int n, int *wsum, Flag flag) {
-    __shared__ uint64_t s_carry;
+__device__ __forceinline__ int block_compact_prev(Rec *a, int n, int *wsum, Rec *carry, Flag flag) {
     int outN = 0;
-    if (threadIdx.x == 0) s_carry = ~0ull;
-    __syncthreads();
     for (int c0 = 0; c0 < n; c0 += blockDim.x) {
         const int i = c0 + threadIdx.x;
-        uint64_t r = 0, rp = ~0ull;
+        Rec r = {0, 0}, rp = {~0ull, ~0ull};
         int keep = 0;
         if (i < n) {
             r = a[i];
-            rp = (threadIdx.x == 0) ? s_carry : a[i - 1];
+            if (i > 0) rp = (threadIdx.x == 0) ? *carry : a[i - 1];
             keep = flag(i, r, rp) ? 1 : 0;
         }
         int total;
-        int ex = block_excl_scan(keep, wsum, &total);  // contains __syncthreads before any write below
+        int ex = block_excl_scan(keep, wsum, &total);  // barriers inside: all reads above precede all writes below
         const int last = min(n, c0 + (int)blockDim.x) - 1;
-        if (i == last) s_carry = r;
+        if (i == last) *carry = r;
         if (keep) a[outN + ex] = r;
         outN += total;
         __syncthreads();
@@ -198,21 +156,75 @@ __device__ __forceinline__ int block_compact_prev(uint64_t *a, int n, int *wsum,
     return outN;
 }
 
+// One work unit = 32 consecutive neighbours `a` of the first 3-mer of window w (KmerGenerator::calculateArrayProduct,
+// KmerGenerator.cpp:186-216: outer loop over row(x1) while s1 >= thr - best2, inner loop over row(x2) while
+// s2 >= thr - s1).  f(kmer, a, b, valid) is called warp-wide for every (a, b) pair of the unit.
+template <class F>
+__device__ __forceinline__ uint32_t warp_unit_kmers(const uint32_t *__restrict__ row3, const uint16_t *__restrict__ cnt3,
+                                                    int x1, int x2, int thr, int n1, int a0, int *s_excl, uint32_t *s_i1, F f) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t *r1 = row3 + (size_t)x1 * SPB_N3;
+    const uint32_t *r2 = row3 + (size_t)x2 * SPB_N3;
+    const uint16_t *c2 = cnt3 + (size_t)x2 * SPB_CNT3_W;
+    const int a = a0 + lane;
+    uint32_t e1 = 0;
+    int n2 = 0;
+    if (a < n1) {
+        e1 = __ldg(r1 + a);
+        const int s1 = (int)(e1 >> 16) - SPB_SCORE_OFF;
+        int cut2 = thr - s1;
+        if (cut2 <= SPB_CNT3_W - SPB_SCORE_OFF - 1) {
+            cut2 = max(cut2, -SPB_SCORE_OFF);
+            n2 = (int)__ldg(c2 + cut2 + SPB_SCORE_OFF);
+        }
+    }
+    const int inc = warp_incl_scan(n2);
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    __syncwarp();
+    s_excl[lane] = inc - n2;
+    s_i1[lane] = e1 & 0xFFFFu;
+    __syncwarp();
+    for (int p0 = 0; p0 < total; p0 += 32) {
+        const int p = p0 + lane;
+        const bool valid = p < total;
+        uint32_t kmer = 0;
+        int j = 0, b = 0;
+        if (valid) {
+            int lo = 0, hi = 31;   // largest j with s_excl[j] <= p
+#pragma unroll
+            for (int it = 0; it < 5; it++) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (s_excl[mid] <= p) lo = mid; else hi = mid - 1;
+            }
+            j = lo;
+            b = p - s_excl[lo];
+            kmer = s_i1[lo] + 8000u * (__ldg(r2 + b) & 0xFFFFu);
+        }
+        f(kmer, (uint32_t)(a0 + j), (uint32_t)b, valid);
+    }
+    __syncwarp();
+    return (uint32_t)total;
+}
+
 template <bool GLOBAL>
 __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ uint8_t s_q[PF_MAXL_SMEM];
-    __shared__ float s_cb[PF_MAXL_SMEM];
-    __shared__ signed char s_corr[PF_MAXL_SMEM];
-    __shared__ short s_thr[PF_MAXL_SMEM];       // per window: similar-k-mer threshold, -1 = window contains X
+    __shared__ uint8_t s_q[PF_MAXL];
+    __shared__ float s_cb[PF_MAXL];
+    __shared__ signed char s_corr[PF_MAXL];
+    __shared__ short s_thr[PF_MAXL];            // per window: similar-k-mer threshold, -1 = skipped
+    __shared__ unsigned short s_n1[PF_MAXL];    // per window: number of outer neighbours
+    __shared__ int s_ubase[PF_MAXL + 1];        // per window: first work unit
     __shared__ signed char s_m40u[SPB_ALPHABET * SPB_ALPHABET];
+    __shared__ uint32_t s_seen1[PF_BM_WORDS], s_seen2[PF_BM_WORDS];
     __shared__ int s_wsum[33];
     __shared__ int s_excl[PF_WARPS][32];
     __shared__ uint32_t s_i1[PF_WARPS][32];
     __shared__ int s_hist[256];
-    __shared__ unsigned int s_nHits, s_flags;
+    __shared__ Rec s_carry;
+    __shared__ unsigned int s_nHits;
     __shared__ int s_minCorr, s_thrD;
-    __shared__ unsigned long long s_base, s_stat[3];
+    __shared__ unsigned long long s_base, s_stat[2];
 
     const uint32_t qi = A.qlist ? A.qlist[blockIdx.x] : blockIdx.x;
     if (qi >= A.Q) return;
@@ -220,24 +232,23 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
     const uint32_t qo = A.qoff[qi];
     const int L = (int)(A.qoff[qi + 1] - qo);
     const int P = L - A.pat.span + 1;
-    if (P < 1) {
+    if (P < 2) {   // no window, or only the (never counted) last one
         if (tid == 0) { A.outStart[qi] = 0; A.outCount[qi] = 0; A.status[qi] = ST_OK; }
         return;
     }
-    if (L > PF_MAXL_SMEM || P > (1 << A.wBits)) {
+    if (L > PF_MAXL) {
         if (tid == 0) { A.outStart[qi] = 0; A.outCount[qi] = 0; A.status[qi] = ST_LAYOUT; }
         return;
     }
-    uint64_t *rec = GLOBAL ? (A.gScratch + (size_t)blockIdx.x * A.cap) : reinterpret_cast<uint64_t *>(smem_raw);
+    Rec *rec = GLOBAL ? (A.gScratch + (size_t)blockIdx.x * A.cap) : reinterpret_cast<Rec *>(smem_raw);
     const uint32_t CAP = A.cap;
-    const int rankBits = A.rankBits, wShift = 16 + A.rankBits, idShift = 16 + A.rankBits + A.wBits;
-    const uint64_t rankMask = (1ull << rankBits) - 1, wMask = (1ull << A.wBits) - 1;
 
-    // ---------------- phase 0/1: query, composition bias, thresholds ----------------
+    // ---------------- phase 0/1: query, composition bias, thresholds, work units ----------------
     for (int i = tid; i < SPB_ALPHABET * SPB_ALPHABET; i += PF_THREADS) s_m40u[i] = (signed char)A.mat->ungapped[i];
     for (int i = tid; i < L; i += PF_THREADS) s_q[i] = A.q[qo + i];
-    if (tid == 0) { s_nHits = 0; s_flags = 0; s_minCorr = 0; s_stat[0] = s_stat[1] = s_stat[2] = 0; }
+    for (int i = tid; i < PF_BM_WORDS; i += PF_THREADS) { s_seen1[i] = 0; s_seen2[i] = 0; }
     for (int i = tid; i < 256; i += PF_THREADS) s_hist[i] = 0;
+    if (tid == 0) { s_nHits = 0; s_minCorr = 0; s_stat[0] = s_stat[1] = 0; }
     __syncthreads();
     // SubstitutionMatrix::calcLocalAaBiasCorrection (SubstitutionMatrix.cpp:85-114): float accumulator, the division
     // and every pBack*score term in double; explicit _rn intrinsics keep the compiler from fusing into FMA.
@@ -256,9 +267,9 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
         }
         s_cb[i] = d;
         // UngappedAlignment::createProfile (UngappedAlignment.cpp:322-328)
-        float t4 = __fdiv_rn(d, 4.0f);
-        double dd = (d < 0.0f) ? __dsub_rn((double)t4, 0.5) : __dadd_rn((double)t4, 0.5);
-        signed char cc = (signed char)__double2float_rn(dd);
+        const float t4 = __fdiv_rn(d, 4.0f);
+        const double dd = (d < 0.0f) ? __dsub_rn((double)t4, 0.5) : __dadd_rn((double)t4, 0.5);
+        const signed char cc = (signed char)__double2float_rn(dd);
         s_corr[i] = cc;
         if (cc < 0) atomicMin(&s_minCorr, (int)cc);
     }
@@ -272,100 +283,127 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
             b = __fadd_rn(b, s_cb[w + A.pat.pos[k]]);
         }
         // QueryMatcher::match (QueryMatcher.cpp:205-219)
-        short bias = (short)((b < 0.0f) ? __dsub_rn((double)b, 0.5) : __dadd_rn((double)b, 0.5));
-        short thr = (short)max(A.kmerThr - (int)bias, 0);
-        s_thr[w] = hasX ? (short)-1 : thr;
+        const short bias = (short)((b < 0.0f) ? __dsub_rn((double)b, 0.5) : __dadd_rn((double)b, 0.5));
+        const short thr = (short)max(A.kmerThr - (int)bias, 0);
+        int n1 = 0;
+        if (!hasX && w < P - 1) {   // quirk A: the last window is never counted
+            const int x1 = s_q[w + A.pat.pos[0]] + 20 * s_q[w + A.pat.pos[1]] + 400 * s_q[w + A.pat.pos[2]];
+            const int x2 = s_q[w + A.pat.pos[3]] + 20 * s_q[w + A.pat.pos[4]] + 400 * s_q[w + A.pat.pos[5]];
+            const int best2 = (int)(__ldg(A.row3 + (size_t)x2 * SPB_N3) >> 16) - SPB_SCORE_OFF;
+            const int cut1 = (int)thr - best2;
+            if (cut1 <= SPB_CNT3_W - SPB_SCORE_OFF - 1)
+                n1 = (int)__ldg(A.cnt3 + (size_t)x1 * SPB_CNT3_W + max(cut1, -SPB_SCORE_OFF) + SPB_SCORE_OFF);
+        }
+        s_thr[w] = thr;
+        s_n1[w] = (unsigned short)n1;
     }
     __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int w = 0; w < P; w++) { s_ubase[w] = acc; acc += ((int)s_n1[w] + 31) >> 5; }
+        s_ubase[P] = acc;
+    }
+    __syncthreads();
+    const int nUnits = s_ubase[P];
     const int ungBias = abs(A.minSubUngapped) + abs(min(s_minCorr, 0));
     const int capScore = 255 - ungBias;
 
-    // ---------------- phase 2: similar k-mers -> index postings -> tagged hits ----------------
+    // ---------------- phase 2: two passes over the hit stream ----------------
     unsigned long long nk = 0, nm = 0;
-    for (int w = wid; w < P - 1; w += PF_WARPS) {   // quirk A: the last window is never counted
-        const int thr = s_thr[w];
-        if (thr < 0) continue;
-        const int x1 = s_q[w + A.pat.pos[0]] + 20 * s_q[w + A.pat.pos[1]] + 400 * s_q[w + A.pat.pos[2]];
-        const int x2 = s_q[w + A.pat.pos[3]] + 20 * s_q[w + A.pat.pos[4]] + 400 * s_q[w + A.pat.pos[5]];
-        uint32_t nKmers = warp_similar_kmers(A.row3, A.cnt3, x1, x2, thr, s_excl[wid], s_i1[wid],
-            [&](uint32_t kmer, uint32_t rank, bool valid) {
-                uint32_t o0 = 0, len = 0;
-                if (valid) {
-                    o0 = __ldg(A.koff + kmer);
-                    len = __ldg(A.koff + kmer + 1) - o0;
-                }
-                int inc = warp_incl_scan((int)len);
-                const int tot = __shfl_sync(0xffffffffu, inc, 31);
-                if (tot == 0) return;
-                unsigned int base = 0;
-                if (lane == 31) base = atomicAdd(&s_nHits, (unsigned int)tot);
-                base = __shfl_sync(0xffffffffu, base, 31);
-                nm += len;
-                if (len) {
-                    if ((uint64_t)rank > rankMask) atomicOr(&s_flags, 1u);
-                    unsigned int dst = base + (unsigned int)(inc - (int)len);
-                    for (uint32_t z = 0; z < len; z++, dst++) {
-                        if (dst < CAP) {
-                            uint64_t pe = __ldg(A.post + o0 + z);   // id << 16 | pos
-                            rec[dst] = ((pe >> 16) << idShift) | ((uint64_t)w << wShift) |
-                                       (((uint64_t)rank & rankMask) << 16) | (pe & 0xFFFFull);
+    for (int pass = 0; pass < 2; pass++) {
+        for (int u = wid; u < nUnits; u += PF_WARPS) {
+            int lo = 0, hi = P - 1;   // window of unit u: largest w with s_ubase[w] <= u
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (s_ubase[mid] <= u) lo = mid; else hi = mid - 1;
+            }
+            const int w = lo;
+            const int a0 = (u - s_ubase[w]) << 5;
+            const int x1 = s_q[w + A.pat.pos[0]] + 20 * s_q[w + A.pat.pos[1]] + 400 * s_q[w + A.pat.pos[2]];
+            const int x2 = s_q[w + A.pat.pos[3]] + 20 * s_q[w + A.pat.pos[4]] + 400 * s_q[w + A.pat.pos[5]];
+            const uint32_t nKmers = warp_unit_kmers(A.row3, A.cnt3, x1, x2, (int)s_thr[w], (int)s_n1[w], a0, s_excl[wid], s_i1[wid],
+                [&](uint32_t kmer, uint32_t a, uint32_t b, bool valid) {
+                    uint32_t o0 = 0, len = 0;
+                    if (valid) {
+                        o0 = __ldg(A.koff + kmer);
+                        len = __ldg(A.koff + kmer + 1) - o0;
+                    }
+                    if (pass == 0) {
+                        nm += len;
+                        for (uint32_t z = 0; z < len; z++) {
+                            const uint32_t h = id_hash((uint32_t)(__ldg(A.post + o0 + z) >> 16));
+                            const uint32_t m = 1u << (h & 31);
+                            const uint32_t old = atomicOr(&s_seen1[h >> 5], m);
+                            if (old & m) atomicOr(&s_seen2[h >> 5], m);
+                        }
+                    } else {
+                        for (uint32_t z = 0; z < len; z++) {
+                            const uint64_t pe = __ldg(A.post + o0 + z);   // id << 16 | pos
+                            const uint32_t id = (uint32_t)(pe >> 16);
+                            const uint32_t h = id_hash(id);
+                            const bool twice = (s_seen2[h >> 5] >> (h & 31)) & 1u;
+                            const bool diag0 = (((uint32_t)w - (uint32_t)(pe & 0xFFFFu)) & 0xFFu) == 0u;
+                            if (twice || diag0) {
+                                const unsigned int dst = atomicAdd(&s_nHits, 1u);
+                                if (dst < CAP) {
+                                    Rec r;
+                                    r.hi = ((uint64_t)id << 32) | ((uint64_t)w << 16) | (pe & 0xFFFFull);
+                                    r.lo = ((uint64_t)a << 16) | (uint64_t)b;
+                                    rec[dst] = r;
+                                }
+                            }
                         }
                     }
-                }
-            });
-        if (lane == 0) nk += nKmers;
+                });
+            if (pass == 0 && lane == 0) nk += nKmers;
+        }
+        __syncthreads();
     }
     for (int d = 16; d > 0; d >>= 1) nm += __shfl_down_sync(0xffffffffu, nm, d);
     if (lane == 0) { atomicAdd(&s_stat[0], nk); atomicAdd(&s_stat[1], nm); }
     __syncthreads();
     int n = (int)s_nHits;
-    if (s_flags & 1u) {
-        if (tid == 0) { A.outStart[qi] = 0; A.outCount[qi] = 0; A.status[qi] = ST_LAYOUT; }
-        return;
-    }
-    if ((uint32_t)n > CAP) {
-        if (tid == 0) { A.outStart[qi] = 0; A.outCount[qi] = 0; A.status[qi] = ST_CAPACITY; A.need[qi] = (uint32_t)n; }
+    // later stages keep events A[0..EV) (Rec), final keys B[0..EV) (u64), cnt u8[EV] and ord u16/u32[EV] in the buffer
+    const uint32_t EV = CAP / 2;
+    if ((uint32_t)n > CAP || (uint32_t)next_pow2(max(A.maxHits, 2)) > EV) {
+        if (tid == 0) {
+            A.outStart[qi] = 0; A.outCount[qi] = 0; A.status[qi] = ST_CAPACITY;
+            A.need[qi] = max((uint32_t)n, 2u * (uint32_t)next_pow2(max(A.maxHits, 2)));
+        }
         return;
     }
 
-    // ---------------- phase 3: sort hits by (id, window, rank) ----------------
+    // ---------------- phase 3: sort the kept hits by (id, window, rank) ----------------
     {
         const int np2 = next_pow2(max(n, 2));
-        for (int i = n + tid; i < np2; i += PF_THREADS) rec[i] = ~0ull;
+        for (int i = n + tid; i < np2; i += PF_THREADS) { rec[i].hi = ~0ull; rec[i].lo = ~0ull; }
         __syncthreads();
-        block_bitonic_sort(rec, np2, [](uint64_t a, uint64_t b) { return a < b; });
+        block_bitonic_sort(rec, np2, [](const Rec &a, const Rec &b) { return rec_less(a, b); });
     }
 
     // ---------------- phase 4: double-hit events, then de-duplication of consecutive equal events ----------------
-    auto diag16 = [&](uint64_t r) -> uint32_t { return (uint32_t)(((r >> wShift) & wMask) - (r & 0xFFFFull)) & 0xFFFFu; };
-    int ne = block_compact_prev(rec, n, s_wsum, [&](int i, uint64_t r, uint64_t rp) {
-        const uint32_t d8 = diag16(r) & 0xFFu;
-        const bool same = (i > 0) && ((rp >> idShift) == (r >> idShift));
-        return same ? (d8 == (diag16(rp) & 0xFFu)) : (d8 == 0u);
+    int ne = block_compact_prev(rec, n, s_wsum, &s_carry, [&](int i, const Rec &r, const Rec &rp) {
+        const uint32_t d8 = rec_diag16(r) & 0xFFu;
+        const bool same = (i > 0) && (rec_id(rp) == rec_id(r));
+        return same ? (d8 == (rec_diag16(rp) & 0xFFu)) : (d8 == 0u);
     });
-    int nkept = block_compact_prev(rec, ne, s_wsum, [&](int i, uint64_t r, uint64_t rp) {
-        const bool same = (i > 0) && ((rp >> idShift) == (r >> idShift));
-        return !same || ((diag16(r) & 0xFFu) != (diag16(rp) & 0xFFu));
+    int nkept = block_compact_prev(rec, ne, s_wsum, &s_carry, [&](int i, const Rec &r, const Rec &rp) {
+        const bool same = (i > 0) && (rec_id(rp) == rec_id(r));
+        return !same || ((rec_diag16(r) & 0xFFu) != (rec_diag16(rp) & 0xFFu));
     });
-    if (tid == 0) s_stat[2] = (unsigned long long)nkept;
-
-    // later stages need: events A[0..EV), final keys B[0..EV), cnt u8[EV], ord u16[EV] inside the record buffer
-    const uint32_t EV = CAP / 4;
-    if ((uint32_t)nkept > EV || (uint32_t)next_pow2(max(A.maxHits, 2)) > EV) {
-        if (tid == 0) { A.outStart[qi] = 0; A.outCount[qi] = 0; A.status[qi] = ST_CAPACITY; A.need[qi] = max((uint32_t)n, 4u * (uint32_t)max(nkept, 2 * A.maxHits)); }
+    if ((uint32_t)nkept > EV) {
+        if (tid == 0) { A.outStart[qi] = 0; A.outCount[qi] = 0; A.status[qi] = ST_CAPACITY; A.need[qi] = 2u * (uint32_t)nkept; }
         return;
     }
-    uint64_t *evA = rec;
-    uint64_t *finB = rec + EV;
-    uint8_t *cnt = reinterpret_cast<uint8_t *>(rec + 2 * (size_t)EV);
-    uint16_t *ord16 = reinterpret_cast<uint16_t *>(rec + 2 * (size_t)EV + (EV + 7) / 8);
-    uint32_t *ord32 = reinterpret_cast<uint32_t *>(rec + 2 * (size_t)EV + (EV + 7) / 8);
-    const bool wideOrd = EV > 65536u;
+    Rec *evA = rec;
+    uint64_t *finB = reinterpret_cast<uint64_t *>(rec + EV);
+    uint8_t *cnt = reinterpret_cast<uint8_t *>(finB + EV);
+    uint32_t *ord = reinterpret_cast<uint32_t *>(cnt + ((EV + 15) & ~15u));   // 16 + 8 + 1 + 4 bytes per slot <= 32
 
     // ---------------- phase 5: ungapped diagonal scores (capped like the uint8 counter) ----------------
     for (int i = tid; i < nkept; i += PF_THREADS) {
-        const uint64_t r = evA[i];
-        int s = ungapped_u16(A.tres, A.toff, (uint32_t)(r >> idShift), s_q, L, s_corr, s_m40u, diag16(r));
+        const Rec r = evA[i];
+        const int s = ungapped_u16(A.tres, A.toff, rec_id(r), s_q, L, s_corr, s_m40u, rec_diag16(r));
         cnt[i] = (uint8_t)min(s, capScore);
     }
     __syncthreads();
@@ -375,22 +413,22 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
     for (int c0 = 0; c0 < nkept; c0 += PF_THREADS) {
         const int i = c0 + tid;
         int keep = 0;
-        uint64_t r = 0;
+        Rec r = {0, 0};
         uint8_t best = 0;
         if (i < nkept) {
             r = evA[i];
-            const uint64_t id = r >> idShift;
-            const bool head = (i == 0) || ((evA[i - 1] >> idShift) != id);
+            const uint32_t id = rec_id(r);
+            const bool head = (i == 0) || (rec_id(evA[i - 1]) != id);
             if (head) {
                 int bi = i;
                 best = cnt[i];
-                for (int j = i + 1; j < nkept && (evA[j] >> idShift) == id; j++)
+                for (int j = i + 1; j < nkept && rec_id(evA[j]) == id; j++)
                     if (cnt[j] > best) { best = cnt[j]; bi = j; }
                 if ((int)best >= A.minDiag) { keep = 1; r = evA[bi]; }
             }
         }
         int total;
-        int ex = block_excl_scan(keep, s_wsum, &total);
+        const int ex = block_excl_scan(keep, s_wsum, &total);
         if (keep) { evA[nc + ex] = r; cnt[nc + ex] = best; }
         nc += total;
         __syncthreads();
@@ -417,7 +455,7 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
         rescale = (s_thrD >= capScore);
     }
     if (rescale) {
-        // rescoreHits (QueryMatcher.cpp:486-505): all remaining candidates are saturated; rescale exact scores to 0..255
+        // rescoreHits (QueryMatcher.cpp:486-505): every remaining candidate is saturated; rescale exact scores to 0..255
         {
             int s = 0, best = 0;
             for (int k = 0; k < L; k++) {
@@ -431,18 +469,18 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
         for (int c0 = 0; c0 < nc; c0 += PF_THREADS) {
             const int i = c0 + tid;
             int keep = 0;
-            uint64_t r = 0;
+            Rec r = {0, 0};
             uint8_t nc8 = 0;
             if (i < nc && (int)cnt[i] >= capScore) {
                 r = evA[i];
-                unsigned int nsx = (unsigned int)ungapped_u16(A.tres, A.toff, (uint32_t)(r >> idShift), s_q, L, s_corr, s_m40u, diag16(r));
+                unsigned int nsx = (unsigned int)ungapped_u16(A.tres, A.toff, rec_id(r), s_q, L, s_corr, s_m40u, rec_diag16(r));
                 nsx -= (unsigned int)capScore;
-                float sc = (float)min(nsx, 65535u);
+                const float sc = (float)min(nsx, 65535u);
                 nc8 = (uint8_t)__dadd_rn((double)__fmul_rn(__fdiv_rn(sc, fltMax), 255.0f), 0.5);
                 keep = 1;
             }
             int total;
-            int ex = block_excl_scan(keep, s_wsum, &total);
+            const int ex = block_excl_scan(keep, s_wsum, &total);
             if (keep) { evA[m + ex] = r; cnt[m + ex] = nc8; }
             m += total;
             __syncthreads();
@@ -452,29 +490,21 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
     if (nc > maxHits) {
         // order of the reference's stable counting sorts: score desc, bin, (window, rank), id
         const uint32_t binMask = A.binMask, idBase = A.idBase;
-        auto less = [&](uint32_t a, uint32_t b) {
+        const int np2 = next_pow2(nc);
+        for (int i = tid; i < np2; i += PF_THREADS) ord[i] = i < nc ? (uint32_t)i : 0xFFFFFFFFu;
+        __syncthreads();
+        block_bitonic_sort(ord, np2, [&](uint32_t a, uint32_t b) {
             if (a == 0xFFFFFFFFu || b == 0xFFFFFFFFu) return a != 0xFFFFFFFFu && b == 0xFFFFFFFFu;
             const uint8_t ca = cnt[a], cb = cnt[b];
             if (ca != cb) return ca > cb;
-            const uint64_t ra = evA[a], rb = evA[b];
-            const uint32_t ba = ((uint32_t)(ra >> idShift) + idBase) & binMask, bb = ((uint32_t)(rb >> idShift) + idBase) & binMask;
+            const Rec ra = evA[a], rb = evA[b];
+            const uint32_t ba = (rec_id(ra) + idBase) & binMask, bb = (rec_id(rb) + idBase) & binMask;
             if (ba != bb) return ba < bb;
-            const uint64_t oa = (ra >> 16) & ((1ull << (idShift - 16)) - 1), ob = (rb >> 16) & ((1ull << (idShift - 16)) - 1);
-            if (oa != ob) return oa < ob;
-            return (ra >> idShift) < (rb >> idShift);
-        };
-        const int np2 = next_pow2(nc);
-        if (wideOrd) {
-            for (int i = tid; i < np2; i += PF_THREADS) ord32[i] = i < nc ? (uint32_t)i : 0xFFFFFFFFu;
-            __syncthreads();
-            block_bitonic_sort(ord32, np2, less);
-        } else {
-            for (int i = tid; i < np2; i += PF_THREADS) ord16[i] = i < nc ? (uint16_t)i : (uint16_t)0xFFFF;
-            __syncthreads();
-            block_bitonic_sort(ord16, np2, [&](uint16_t a, uint16_t b) {
-                return less(a == 0xFFFF ? 0xFFFFFFFFu : (uint32_t)a, b == 0xFFFF ? 0xFFFFFFFFu : (uint32_t)b);
-            });
-        }
+            const uint32_t wa = (uint32_t)(ra.hi >> 16) & 0xFFFFu, wb = (uint32_t)(rb.hi >> 16) & 0xFFFFu;
+            if (wa != wb) return wa < wb;
+            if (ra.lo != rb.lo) return ra.lo < rb.lo;
+            return rec_id(ra) < rec_id(rb);
+        });
         ns = maxHits;
     } else {
         ns = nc;
@@ -482,16 +512,17 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
 
     // ---------------- phase 8: exact scores, final order (score desc, id asc), output ----------------
     for (int k = tid; k < ns; k += PF_THREADS) {
-        const int i = (nc > maxHits) ? (wideOrd ? (int)ord32[k] : (int)ord16[k]) : k;
-        const uint64_t r = evA[i];
-        const uint32_t id = (uint32_t)(r >> idShift);
+        const int i = (nc > maxHits) ? (int)ord[k] : k;
+        const Rec r = evA[i];
+        const uint32_t id = rec_id(r);
         int sc = cnt[i];
         if (rescale) {
             sc = capScore + (int)((unsigned int)cnt[i] * (unsigned int)maxSelf / 255u);
         } else if (sc >= capScore) {
-            sc = ungapped_u16(A.tres, A.toff, id, s_q, L, s_corr, s_m40u, diag16(r));   // getResult, QueryMatcher.cpp:371-374
+            sc = ungapped_u16(A.tres, A.toff, id, s_q, L, s_corr, s_m40u, rec_diag16(r));   // getResult, QueryMatcher.cpp:371-374
         }
-        finB[k] = ((uint64_t)(0xFFFFFu - (uint32_t)min(sc, 0xFFFFF)) << 44) | ((uint64_t)id << 16) | diag16(r);
+        // (score desc, id asc): 16-bit inverted score | 32-bit id | 16-bit diagonal (scores < 64 * PF_MAXL fit 16 bits)
+        finB[k] = ((uint64_t)(0xFFFFu - (uint32_t)min(sc, 0xFFFF)) << 48) | ((uint64_t)id << 16) | rec_diag16(r);
     }
     {
         const int np2 = next_pow2(max(ns, 2));
@@ -500,11 +531,11 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
         block_bitonic_sort(finB, np2, [](uint64_t a, uint64_t b) { return a < b; });
     }
     if (tid == 0) {
-        unsigned long long base = atomicAdd(A.cursor, (unsigned long long)ns);
-        s_base = base;
+        s_base = atomicAdd(A.cursor, (unsigned long long)ns);
         atomicAdd(A.cursor + 1, s_stat[0]);
         atomicAdd(A.cursor + 2, s_stat[1]);
-        atomicAdd(A.cursor + 3, s_stat[2]);
+        atomicAdd(A.cursor + 3, (unsigned long long)nkept);
+        atomicAdd(A.cursor + 4, (unsigned long long)n);
     }
     __syncthreads();
     const unsigned long long base = s_base;
@@ -515,8 +546,8 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
     for (int k = tid; k < ns; k += PF_THREADS) {
         const uint64_t f = finB[k];
         spb_hit h;
-        h.id = (uint32_t)((f >> 16) & 0xFFFFFFFull);
-        h.score = (int32_t)(0xFFFFFu - (uint32_t)(f >> 44));
+        h.id = (uint32_t)(f >> 16);
+        h.score = (int32_t)(0xFFFFu - (uint32_t)(f >> 48));
         h.diag = (int32_t)(short)(uint16_t)(f & 0xFFFFull);
         A.arena[base + k] = h;
     }
@@ -526,11 +557,36 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
 // gather per-query slices of the arena into query order
 __global__ void gather_hits_kernel(const spb_hit *__restrict__ arena, const uint64_t *__restrict__ start, const uint64_t *__restrict__ outOff,
                                    uint32_t Q, spb_hit *__restrict__ out) {
-    const uint32_t qi = blockIdx.x;
+    const uint32_t qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (qi >= Q) return;
     const uint64_t s = start[qi], o = outOff[qi];
     const uint32_t n = (uint32_t)(outOff[qi + 1] - o);
-    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) out[o + k] = arena[s + k];
+    for (uint32_t k = threadIdx.x & 31; k < n; k += 32) out[o + k] = arena[s + k];
+}
+
+__global__ void count_to_u64_kernel(const uint32_t *__restrict__ cnt, uint32_t Q, uint64_t *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Q) out[i] = cnt[i];
+    if (i == Q) out[i] = 0;
+}
+
+// status scan: list of queries needing the global-memory variant, max need, error flags
+__global__ void status_scan_kernel(const uint32_t *__restrict__ status, const uint32_t *__restrict__ need, uint32_t Q,
+                                   uint32_t *__restrict__ list, unsigned int *__restrict__ ctr) {
+    // ctr: [0] nSlow, [1] maxNeed, [2] arena overflow, [3] layout error (query index + 1), [4] unprocessed
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Q) return;
+    const uint32_t s = status[i];
+    if (s == ST_CAPACITY) {
+        list[atomicAdd(&ctr[0], 1u)] = i;
+        atomicMax(&ctr[1], need[i]);
+    } else if (s == ST_ARENA) {
+        atomicOr(&ctr[2], 1u);
+    } else if (s == ST_LAYOUT) {
+        atomicMax(&ctr[3], i + 1);
+    } else if (s != ST_OK) {
+        atomicMax(&ctr[4], i + 1);
+    }
 }
 
 __global__ void similar_kmers_test_kernel(const uint32_t *row3, const uint16_t *cnt3, const uint8_t *k6, int thr, uint32_t *out,
@@ -539,23 +595,27 @@ __global__ void similar_kmers_test_kernel(const uint32_t *row3, const uint16_t *
     __shared__ uint32_t s_i1[32];
     const int x1 = k6[0] + 20 * k6[1] + 400 * k6[2];
     const int x2 = k6[3] + 20 * k6[4] + 400 * k6[5];
-    uint32_t tot = warp_similar_kmers(row3, cnt3, x1, x2, thr, s_excl, s_i1, [&](uint32_t kmer, uint32_t rank, bool valid) {
-        if (valid && rank < cap) out[rank] = kmer;
-    });
-    if (threadIdx.x == 0) *n = tot;
-}
-
-static int bits_for(uint64_t n) {
-    int b = 1;
-    while ((1ull << b) < n) b++;
-    return b;
+    const int best2 = (int)(row3[(size_t)x2 * SPB_N3] >> 16) - SPB_SCORE_OFF;
+    const int cut1 = thr - best2;
+    int n1 = 0;
+    if (cut1 <= SPB_CNT3_W - SPB_SCORE_OFF - 1) n1 = cnt3[(size_t)x1 * SPB_CNT3_W + max(cut1, -SPB_SCORE_OFF) + SPB_SCORE_OFF];
+    uint32_t base = 0;
+    for (int a0 = 0; a0 < n1; a0 += 32) {
+        uint32_t tot = warp_unit_kmers(row3, cnt3, x1, x2, thr, n1, a0, s_excl, s_i1, [&](uint32_t kmer, uint32_t a, uint32_t b, bool valid) {
+            // rank within the unit: position in (a, b) order == base + (exclusive count of a) + b
+            if (valid) {
+                const uint32_t r = base + (uint32_t)s_excl[a - a0] + b;
+                if (r < cap) out[r] = kmer;
+            }
+        });
+        base += tot;
+    }
+    if (threadIdx.x == 0) *n = base;
 }
 
 }  // namespace spb
 
 using namespace spb;
-
-#define PF_SMEM_CAP 4096u   // records per CTA in shared memory (32 KB)
 
 extern "C" int spb_similar_kmers(spb_ctx *c, const uint8_t *kmer6, int thr, uint32_t *out, uint32_t cap, uint32_t *n) {
     SPB_CHECK(c && kmer6 && out && n, "spb_similar_kmers: NULL argument");
@@ -576,54 +636,60 @@ extern "C" int spb_similar_kmers(spb_ctx *c, const uint8_t *kmer6, int thr, uint
     return 0;
 }
 
-extern "C" void spb_free_prefilter_result(spb_prefilter_result *r) {
-    if (!r) return;
-    free(r->offsets);
-    free(r->hits);
-    free(r);
+// ------------------------------------------------------------------------------------------------------
+// resident pipeline
+// ------------------------------------------------------------------------------------------------------
+extern "C" int spb_queries_set(spb_ctx *c, const uint8_t *q_residues, const uint64_t *q_offsets, uint32_t Q) {
+    SPB_CHECK(c && q_offsets, "spb_queries_set: NULL argument");
+    SPB_CUDA(cudaSetDevice(c->device));
+    const uint64_t NQ = q_offsets[Q];
+    SPB_CHECK(NQ < 0xFFFFFFF0ull, "spb_queries_set: query batch too large for 32-bit offsets; split the batch");
+    SPB_CHECK(Q == 0 || q_residues, "spb_queries_set: NULL residues");
+    std::vector<uint32_t> off32((size_t)Q + 1);
+    uint32_t maxL = 0;
+    for (uint32_t i = 0; i <= Q; i++) {
+        SPB_CHECK(q_offsets[i] <= NQ && (i == 0 || q_offsets[i] >= q_offsets[i - 1]), "spb_queries_set: offsets not monotone at %u", i);
+        off32[i] = (uint32_t)q_offsets[i];
+        if (i) maxL = std::max(maxL, (uint32_t)(q_offsets[i] - q_offsets[i - 1]));
+    }
+    if (c->d_q.ensure(NQ + 64) || c->d_qoff.ensure(((size_t)Q + 1) * 4) || c->d_qoff64.ensure(((size_t)Q + 1) * 8)) return 1;
+    if (NQ) SPB_CUDA(cudaMemcpyAsync(c->d_q.p, q_residues, NQ, cudaMemcpyHostToDevice, c->stream));
+    SPB_CUDA(cudaMemcpyAsync(c->d_qoff.p, off32.data(), off32.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    SPB_CUDA(cudaMemcpyAsync(c->d_qoff64.p, q_offsets, ((size_t)Q + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    SPB_CUDA(cudaStreamSynchronize(c->stream));
+    c->Q = Q;
+    c->q_res = NQ;
+    c->q_maxlen = maxL;
+    c->have_queries = true;
+    c->have_pref = false;
+    c->have_pairs = false;
+    c->have_aln = false;
+    return 0;
 }
 
-extern "C" int spb_prefilter(spb_ctx *c, const uint8_t *q_residues, const uint64_t *q_offsets, uint32_t Q,
-                             const spb_prefilter_params *p, spb_prefilter_result **out) {
-    SPB_CHECK(c && q_offsets && p && out, "spb_prefilter: NULL argument");
+extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p) {
+    SPB_CHECK(c && p, "spb_prefilter_resident: NULL argument");
     SPB_CHECK(c->have_index, "spb_prefilter: build the index first (spb_index_build)");
+    SPB_CHECK(c->have_queries, "spb_prefilter: no resident query batch (spb_queries_set)");
     SPB_CHECK(p->bin_size >= 2 && p->bin_size <= 2048 && (p->bin_size & (p->bin_size - 1)) == 0,
               "spb_prefilter: bin_size %d must be a power of two in 2..2048", p->bin_size);
     SPB_CHECK(p->max_seqs >= 1, "spb_prefilter: max_seqs must be >= 1");
     SPB_CHECK(p->min_diag_score >= 0 && p->min_diag_score <= 255, "spb_prefilter: min_diag_score out of range");
+    SPB_CHECK(c->q_maxlen <= PF_MAXL, "spb_prefilter: query of %u residues exceeds the supported query length %d of the spacer path",
+              c->q_maxlen, PF_MAXL);
     SPB_CUDA(cudaSetDevice(c->device));
-    *out = nullptr;
     cudaStream_t st = c->stream;
-    const uint64_t NQ = q_offsets[Q];
-    SPB_CHECK(NQ < 0xFFFFFFF0ull, "spb_prefilter: query batch too large for 32-bit offsets; split the batch");
-
-    spb_prefilter_result *res = (spb_prefilter_result *)calloc(1, sizeof(spb_prefilter_result));
-    res->n_queries = Q;
-    res->offsets = (uint64_t *)calloc((size_t)Q + 1, sizeof(uint64_t));
-    if (Q == 0) { res->hits = (spb_hit *)calloc(1, sizeof(spb_hit)); *out = res; return 0; }
-
-    // ---- upload queries
-    std::vector<uint32_t> off32((size_t)Q + 1);
-    uint32_t maxL = 0;
-    for (uint32_t i = 0; i <= Q; i++) {
-        off32[i] = (uint32_t)q_offsets[i];
-        if (i) maxL = std::max(maxL, (uint32_t)(q_offsets[i] - q_offsets[i - 1]));
+    const uint32_t Q = c->Q;
+    c->have_pref = false;
+    memset(&c->pref_stats, 0, sizeof(c->pref_stats));
+    c->pref_stats.n_queries = Q;
+    if (c->d_hitoff.ensure(((size_t)Q + 1) * 8)) return 1;
+    if (Q == 0) {
+        SPB_CUDA(cudaMemsetAsync(c->d_hitoff.p, 0, 8, st));
+        c->n_hits = 0;
+        c->have_pref = true;
+        return 0;
     }
-    int rcode = 1;
-    DevBuf d_start, d_count, d_status, d_need, d_cursor, d_arena;
-    auto fail = [&]() { d_start.release(); d_count.release(); d_status.release(); d_need.release(); d_cursor.release(); d_arena.release(); spb_free_prefilter_result(res); return rcode; };
-#define PF_CUDA(call)                                                                             \
-    do {                                                                                          \
-        cudaError_t e__ = (call);                                                                 \
-        if (e__ != cudaSuccess) {                                                                 \
-            spb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
-            return fail();                                                                        \
-        }                                                                                         \
-    } while (0)
-    if (c->d_q.ensure(NQ + 64) || c->d_qoff.ensure(((size_t)Q + 1) * 4)) return fail();
-    PF_CUDA(cudaMemcpyAsync(c->d_q.p, q_residues, NQ, cudaMemcpyHostToDevice, st));
-    PF_CUDA(cudaMemcpyAsync(c->d_qoff.p, off32.data(), off32.size() * 4, cudaMemcpyHostToDevice, st));
-
     PrefArgs A;
     memset(&A, 0, sizeof(A));
     A.q = c->d_q.as<uint8_t>();
@@ -647,151 +713,167 @@ extern "C" int spb_prefilter(spb_ctx *c, const uint8_t *q_residues, const uint64
     for (int i = 0; i < SPB_ALPHABET * SPB_ALPHABET; i++) A.minSubUngapped = std::min(A.minSubUngapped, (int)c->hm.ungapped[i]);
     A.binMask = (uint32_t)p->bin_size - 1;
     A.idBase = p->id_base;
-    const int idBits = bits_for(std::max<uint64_t>(c->T, 2));
-    const int P = (int)maxL - c->span + 1;
-    A.wBits = bits_for((uint64_t)std::max(P, 2));
-    A.rankBits = 48 - idBits - A.wBits;
-    if (A.rankBits > 23) A.rankBits = 23;   // KmerGenerator::MAX_KMER_RESULT_SIZE = 2^23
-    if (A.rankBits < 10) {
-        spb::set_error("spb_prefilter: %u targets x query length %u do not fit the 64-bit hit record; shard the targets", c->T, maxL);
-        return fail();
-    }
-    if (maxL > PF_MAXL_SMEM) {
-        spb::set_error("spb_prefilter: query of %u residues exceeds the supported query length %d of the spacer path", maxL, PF_MAXL_SMEM);
-        return fail();
-    }
 
-    if (d_start.ensure((size_t)Q * 8) || d_count.ensure((size_t)Q * 4) || d_status.ensure((size_t)Q * 4) || d_need.ensure((size_t)Q * 4) ||
-        d_cursor.ensure(64)) return fail();
+    // scratch: s_a start u64[Q], s_b count u32[Q], s_c status u32[Q], s_d need u32[Q], s_e slow list u32[Q], s_f counters, s_g arena
+    if (c->s_a.ensure((size_t)Q * 8) || c->s_b.ensure((size_t)Q * 4) || c->s_c.ensure((size_t)Q * 4) || c->s_d.ensure((size_t)Q * 4) ||
+        c->s_e.ensure((size_t)Q * 4) || c->s_f.ensure(128)) return 1;
     uint64_t arenaCap = std::min<uint64_t>((uint64_t)Q * (uint64_t)A.maxHits, std::max<uint64_t>((uint64_t)Q * 24, 1u << 20));
-    std::vector<uint32_t> h_status(Q), h_count(Q), h_need(Q);
-    std::vector<uint64_t> h_start(Q);
     float kernelMs = 0;
     uint64_t nSlow = 0;
     unsigned long long h_cursor[8];
+    unsigned int h_ctr[8];
+    SPB_CUDA(cudaEventRecord(c->ev2, st));
     for (int attempt = 0;; attempt++) {
-        if (d_arena.ensure(arenaCap * sizeof(spb_hit) + 64)) return fail();
-        A.arena = d_arena.as<spb_hit>();
+        if (c->s_g.ensure(arenaCap * sizeof(spb_hit) + 64)) return 1;
+        A.arena = c->s_g.as<spb_hit>();
         A.arenaCap = arenaCap;
-        A.cursor = d_cursor.as<unsigned long long>();
-        A.outStart = d_start.as<uint64_t>();
-        A.outCount = d_count.as<uint32_t>();
-        A.status = d_status.as<uint32_t>();
-        A.need = d_need.as<uint32_t>();
+        A.cursor = c->s_f.as<unsigned long long>();
+        A.outStart = c->s_a.as<uint64_t>();
+        A.outCount = c->s_b.as<uint32_t>();
+        A.status = c->s_c.as<uint32_t>();
+        A.need = c->s_d.as<uint32_t>();
         A.qlist = nullptr;
         A.gScratch = nullptr;
         A.cap = PF_SMEM_CAP;
-        PF_CUDA(cudaMemsetAsync(d_cursor.p, 0, 64, st));
-        PF_CUDA(cudaMemsetAsync(d_status.p, 0xFF, (size_t)Q * 4, st));
-        const size_t smem = (size_t)PF_SMEM_CAP * 8;
-        PF_CUDA(cudaFuncSetAttribute(prefilter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PF_CUDA(cudaEventRecord(c->ev0, st));
+        unsigned int *d_ctr = reinterpret_cast<unsigned int *>(c->s_f.as<unsigned long long>() + 8);
+        SPB_CUDA(cudaMemsetAsync(c->s_f.p, 0, 128, st));
+        SPB_CUDA(cudaMemsetAsync(c->s_c.p, 0xFF, (size_t)Q * 4, st));
+        const size_t smem = (size_t)PF_SMEM_CAP * sizeof(Rec);
+        SPB_CUDA(cudaEventRecord(c->ev0, st));
         prefilter_kernel<false><<<Q, PF_THREADS, smem, st>>>(A);
-        PF_CUDA(cudaGetLastError());
-        PF_CUDA(cudaEventRecord(c->ev1, st));
-        PF_CUDA(cudaMemcpyAsync(h_status.data(), d_status.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
-        PF_CUDA(cudaMemcpyAsync(h_need.data(), d_need.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
-        PF_CUDA(cudaMemcpyAsync(h_cursor, d_cursor.p, 64, cudaMemcpyDeviceToHost, st));
-        PF_CUDA(cudaStreamSynchronize(st));
+        SPB_CUDA(cudaGetLastError());
+        SPB_CUDA(cudaEventRecord(c->ev1, st));
+        status_scan_kernel<<<(Q + 255) / 256, 256, 0, st>>>(A.status, A.need, Q, c->s_e.as<uint32_t>(), d_ctr);
+        SPB_CUDA(cudaGetLastError());
+        SPB_CUDA(cudaMemcpyAsync(h_ctr, d_ctr, 32, cudaMemcpyDeviceToHost, st));
+        SPB_CUDA(cudaStreamSynchronize(st));
         float ms = 0;
-        PF_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        SPB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         kernelMs += ms;
-        // ---- slow path: queries whose hit list does not fit shared memory run again on global-memory scratch
-        std::vector<uint32_t> slow;
-        uint32_t maxNeed = 0;
-        bool arenaOverflow = false;
-        for (uint32_t i = 0; i < Q; i++) {
-            if (h_status[i] == ST_CAPACITY) { slow.push_back(i); maxNeed = std::max(maxNeed, h_need[i]); }
-            else if (h_status[i] == ST_ARENA) arenaOverflow = true;
-            else if (h_status[i] == ST_LAYOUT) {
-                spb::set_error("spb_prefilter: query %u exceeds the hit-record layout (rank bits %d, window bits %d)", i, A.rankBits, A.wBits);
-                return fail();
-            } else if (h_status[i] != ST_OK) {
-                spb::set_error("spb_prefilter: query %u was not processed (status %u)", i, h_status[i]);
-                return fail();
-            }
-        }
-        if (!slow.empty() && !arenaOverflow) {
-            nSlow = slow.size();
-            uint32_t capG = 1;
-            while (capG < std::max(maxNeed, 4096u)) capG <<= 1;
-            DevBuf d_list, d_scr;
-            for (size_t done = 0; done < slow.size() && !arenaOverflow;) {
-                // a need estimate can grow once later stages are reached: loop until every query fits
-                size_t chunk = std::min<size_t>(slow.size() - done, std::max<size_t>(1, ((size_t)2 << 30) / ((size_t)capG * 8)));
-                if (d_list.ensure(chunk * 4) || d_scr.ensure(chunk * (size_t)capG * 8)) { d_list.release(); d_scr.release(); return fail(); }
-                PF_CUDA(cudaMemcpyAsync(d_list.p, slow.data() + done, chunk * 4, cudaMemcpyHostToDevice, st));
-                A.qlist = d_list.as<uint32_t>();
-                A.gScratch = d_scr.as<uint64_t>();
+        SPB_CHECK(h_ctr[3] == 0, "spb_prefilter: query %u is longer than the supported %d residues", h_ctr[3] - 1, PF_MAXL);
+        SPB_CHECK(h_ctr[4] == 0, "spb_prefilter: query %u was not processed", h_ctr[4] - 1);
+        bool arenaOverflow = h_ctr[2] != 0;
+        // queries whose kept-hit list does not fit shared memory run again on global-memory scratch
+        uint32_t nList = h_ctr[0], maxNeed = h_ctr[1], capG = 2048;
+        nSlow = nList;
+        while (nList && !arenaOverflow) {
+            while (capG < maxNeed) capG <<= 1;
+            SPB_CHECK(capG <= (1u << 28), "spb_prefilter: hit list of a query exceeds 2^28 records");
+            const uint32_t chunkMax = (uint32_t)std::max<uint64_t>(1, ((uint64_t)4 << 30) / ((uint64_t)capG * sizeof(Rec)));
+            if (c->s_h.ensure((size_t)std::min(chunkMax, nList) * capG * sizeof(Rec))) return 1;
+            SPB_CUDA(cudaEventRecord(c->ev0, st));
+            for (uint32_t done = 0; done < nList; done += chunkMax) {
+                const uint32_t chunk = std::min(chunkMax, nList - done);
+                A.qlist = c->s_e.as<uint32_t>() + done;
+                A.gScratch = c->s_h.as<Rec>();
                 A.cap = capG;
-                PF_CUDA(cudaEventRecord(c->ev0, st));
-                prefilter_kernel<true><<<(unsigned)chunk, PF_THREADS, 0, st>>>(A);
-                PF_CUDA(cudaGetLastError());
-                PF_CUDA(cudaEventRecord(c->ev1, st));
-                PF_CUDA(cudaMemcpyAsync(h_status.data(), d_status.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
-                PF_CUDA(cudaMemcpyAsync(h_need.data(), d_need.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
-                PF_CUDA(cudaStreamSynchronize(st));
-                PF_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-                kernelMs += ms;
-                bool again = false;
-                for (size_t k = done; k < done + chunk; k++) {
-                    uint32_t s = h_status[slow[k]];
-                    if (s == ST_ARENA) arenaOverflow = true;
-                    else if (s == ST_CAPACITY) { again = true; while (capG < h_need[slow[k]]) capG <<= 1; }
-                    else if (s != ST_OK) {
-                        spb::set_error("spb_prefilter: query %u failed on the global-memory path (status %u)", slow[k], s);
-                        d_list.release(); d_scr.release();
-                        return fail();
-                    }
-                }
-                if (!again) done += chunk;
-                else if (capG > (1u << 28)) {
-                    spb::set_error("spb_prefilter: hit list of a query exceeds 2^28 records");
-                    d_list.release(); d_scr.release();
-                    return fail();
-                }
+                prefilter_kernel<true><<<chunk, PF_THREADS, 0, st>>>(A);
+                SPB_CUDA(cudaGetLastError());
             }
-            d_list.release();
-            d_scr.release();
-            PF_CUDA(cudaMemcpyAsync(h_cursor, d_cursor.p, 64, cudaMemcpyDeviceToHost, st));
-            PF_CUDA(cudaStreamSynchronize(st));
+            SPB_CUDA(cudaEventRecord(c->ev1, st));
+            // which of them still need more room (their status stays ST_CAPACITY)?
+            if (c->s_i.ensure((size_t)Q * 4)) return 1;
+            SPB_CUDA(cudaMemsetAsync(d_ctr, 0, 32, st));
+            status_scan_kernel<<<(Q + 255) / 256, 256, 0, st>>>(A.status, A.need, Q, c->s_i.as<uint32_t>(), d_ctr);
+            SPB_CUDA(cudaGetLastError());
+            SPB_CUDA(cudaMemcpyAsync(h_ctr, d_ctr, 32, cudaMemcpyDeviceToHost, st));
+            SPB_CUDA(cudaStreamSynchronize(st));
+            SPB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+            kernelMs += ms;
+            SPB_CHECK(h_ctr[3] == 0 && h_ctr[4] == 0, "spb_prefilter: a query failed on the global-memory path");
+            arenaOverflow = h_ctr[2] != 0;
+            nList = h_ctr[0];
+            if (nList) {
+                SPB_CUDA(cudaMemcpyAsync(c->s_e.p, c->s_i.p, (size_t)nList * 4, cudaMemcpyDeviceToDevice, st));
+                maxNeed = std::max(h_ctr[1], capG * 2);
+            }
         }
         if (!arenaOverflow) break;
-        if (arenaCap >= (uint64_t)Q * (uint64_t)A.maxHits || attempt > 8) {
-            spb::set_error("spb_prefilter: result arena overflow could not be resolved");
-            return fail();
-        }
+        SPB_CHECK(arenaCap < (uint64_t)Q * (uint64_t)A.maxHits && attempt < 8, "spb_prefilter: result arena overflow could not be resolved");
         arenaCap = std::min<uint64_t>((uint64_t)Q * (uint64_t)A.maxHits, arenaCap * 4);
     }
+    SPB_CUDA(cudaMemcpyAsync(h_cursor, c->s_f.p, 64, cudaMemcpyDeviceToHost, st));
 
-    // ---- compact the arena into query order
-    PF_CUDA(cudaMemcpyAsync(h_count.data(), d_count.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
-    PF_CUDA(cudaStreamSynchronize(st));
-    for (uint32_t i = 0; i < Q; i++) res->offsets[i + 1] = res->offsets[i] + h_count[i];
-    const uint64_t nHits = res->offsets[Q];
-    res->n_hits = nHits;
-    res->hits = (spb_hit *)malloc(std::max<uint64_t>(nHits, 1) * sizeof(spb_hit));
+    // ---- compact the arena into query order: offsets = exclusive scan of the counts
+    if (c->s_i.ensure(((size_t)Q + 1) * 8)) return 1;
+    count_to_u64_kernel<<<(Q + 1 + 255) / 256, 256, 0, st>>>(c->s_b.as<uint32_t>(), Q, c->s_i.as<uint64_t>());
+    SPB_CUDA(cudaGetLastError());
+    size_t tmpBytes = 0;
+    SPB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, c->s_i.as<uint64_t>(), c->d_hitoff.as<uint64_t>(), (int)(Q + 1), st));
+    if (c->s_cub.ensure(tmpBytes)) return 1;
+    SPB_CUDA(cub::DeviceScan::ExclusiveSum(c->s_cub.p, tmpBytes, c->s_i.as<uint64_t>(), c->d_hitoff.as<uint64_t>(), (int)(Q + 1), st));
+    uint64_t nHits = 0;
+    SPB_CUDA(cudaMemcpyAsync(&nHits, c->d_hitoff.as<uint64_t>() + Q, 8, cudaMemcpyDeviceToHost, st));
+    SPB_CUDA(cudaStreamSynchronize(st));
+    if (c->d_hits.ensure(std::max<uint64_t>(nHits, 1) * sizeof(spb_hit))) return 1;
     if (nHits) {
-        DevBuf d_ooff, d_out;
-        if (d_ooff.ensure(((size_t)Q + 1) * 8) || d_out.ensure(nHits * sizeof(spb_hit))) { d_ooff.release(); d_out.release(); return fail(); }
-        PF_CUDA(cudaMemcpyAsync(d_ooff.p, res->offsets, ((size_t)Q + 1) * 8, cudaMemcpyHostToDevice, st));
-        gather_hits_kernel<<<Q, 64, 0, st>>>(d_arena.as<spb_hit>(), d_start.as<uint64_t>(), d_ooff.as<uint64_t>(), Q, d_out.as<spb_hit>());
-        PF_CUDA(cudaGetLastError());
-        PF_CUDA(cudaMemcpyAsync(res->hits, d_out.p, nHits * sizeof(spb_hit), cudaMemcpyDeviceToHost, st));
-        PF_CUDA(cudaStreamSynchronize(st));
-        d_ooff.release();
-        d_out.release();
+        gather_hits_kernel<<<(Q + 3) / 4, 128, 0, st>>>(c->s_g.as<spb_hit>(), c->s_a.as<uint64_t>(), c->d_hitoff.as<uint64_t>(), Q,
+                                                        c->d_hits.as<spb_hit>());
+        SPB_CUDA(cudaGetLastError());
     }
-#undef PF_CUDA
-    res->n_kmers = h_cursor[1];
-    res->n_db_matches = h_cursor[2];
-    res->n_events = h_cursor[3];
-    res->n_slow_path = nSlow;
-    res->kernel_ms = kernelMs;
-    // algorithmic bytes: per similar k-mer one 3-mer row entry (4 B) + two CSR offsets (8 B),
-    // per index hit one posting (8 B), per query its residues, per output hit 12 B
-    res->algo_bytes = res->n_kmers * 12ull + res->n_db_matches * 8ull + NQ + nHits * 12ull;
-    d_start.release(); d_count.release(); d_status.release(); d_need.release(); d_cursor.release(); d_arena.release();
+    SPB_CUDA(cudaEventRecord(c->ev3, st));
+    SPB_CUDA(cudaStreamSynchronize(st));
+    float totalMs = 0;
+    SPB_CUDA(cudaEventElapsedTime(&totalMs, c->ev2, c->ev3));
+    c->n_hits = nHits;
+    spb_prefilter_result &R = c->pref_stats;
+    R.n_hits = nHits;
+    R.n_kmers = h_cursor[1];
+    R.n_db_matches = h_cursor[2];
+    R.n_events = h_cursor[3];
+    R.n_slow_path = nSlow;
+    R.kernel_ms = kernelMs;
+    R.total_ms = totalMs;
+    // algorithmic bytes of one pass over the hit stream: per similar k-mer one 3-mer row entry (4 B) and two
+    // CSR offsets (8 B), per index hit one posting (8 B), per query its residues, per output hit 12 B
+    R.algo_bytes = R.n_kmers * 12ull + R.n_db_matches * 8ull + c->q_res + nHits * 12ull;
+    c->have_pref = true;
+    return 0;
+}
+
+extern "C" int spb_prefilter_stats(spb_ctx *c, spb_prefilter_result *out) {
+    SPB_CHECK(c && out, "spb_prefilter_stats: NULL argument");
+    SPB_CHECK(c->have_pref, "spb_prefilter_stats: no resident prefilter result");
+    *out = c->pref_stats;
+    out->offsets = nullptr;
+    out->hits = nullptr;
+    return 0;
+}
+
+extern "C" void spb_free_prefilter_result(spb_prefilter_result *r) {
+    if (!r) return;
+    free(r->offsets);
+    free(r->hits);
+    free(r);
+}
+
+extern "C" int spb_prefilter_fetch(spb_ctx *c, spb_prefilter_result **out) {
+    SPB_CHECK(c && out, "spb_prefilter_fetch: NULL argument");
+    SPB_CHECK(c->have_pref, "spb_prefilter_fetch: no resident prefilter result");
+    SPB_CUDA(cudaSetDevice(c->device));
+    *out = nullptr;
+    const uint32_t Q = c->Q;
+    spb_prefilter_result *res = (spb_prefilter_result *)calloc(1, sizeof(spb_prefilter_result));
+    *res = c->pref_stats;
+    res->offsets = (uint64_t *)calloc((size_t)Q + 1, sizeof(uint64_t));
+    res->hits = (spb_hit *)malloc(std::max<uint64_t>(c->n_hits, 1) * sizeof(spb_hit));
+    cudaError_t e = cudaMemcpyAsync(res->offsets, c->d_hitoff.p, ((size_t)Q + 1) * 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && c->n_hits) e = cudaMemcpyAsync(res->hits, c->d_hits.p, c->n_hits * sizeof(spb_hit), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+        spb_free_prefilter_result(res);
+        spb::set_error("spb_prefilter_fetch: %s", cudaGetErrorString(e));
+        return 1;
+    }
     *out = res;
     return 0;
+}
+
+extern "C" int spb_prefilter(spb_ctx *c, const uint8_t *q_residues, const uint64_t *q_offsets, uint32_t Q,
+                             const spb_prefilter_params *p, spb_prefilter_result **out) {
+    SPB_CHECK(c && q_offsets && p && out, "spb_prefilter: NULL argument");
+    *out = nullptr;
+    if (spb_queries_set(c, q_residues, q_offsets, Q)) return 1;
+    if (spb_prefilter_resident(c, p)) return 1;
+    return spb_prefilter_fetch(c, out);
 }

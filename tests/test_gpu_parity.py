@@ -300,3 +300,27 @@ def test_align_random_vs_oracle(searcher, go, ge):
             assert abs(float(r["eval"]) - a.eval) <= EVAL_RTOL * abs(a.eval)
             nrow += 1
     assert nrow > 100
+
+
+def test_fused_search_equals_two_step(searcher):
+    """resident prefilter -> align (hit lists stay in HBM) gives the same rows as the two host-level calls"""
+    from spacepharer_b200 import api
+    T, Q = Cm.load_fasta_set("family")
+    tres, toff = _product_mask(searcher, T)
+    searcher.build_index(tres, toff)
+    ures, utoff = O.concat(T)
+    searcher.set_align_targets(ures, utoff)
+    qres, qoff = O.concat(Q)
+    db_res = Cm.db_res_count(T)
+    off, rows, cig, st, pref = searcher.search(qres, qoff, db_res, fetch_prefilter=True)
+    poff, phits, _ = searcher.prefilter(qres, qoff)
+    assert (pref[0] == poff).all() and (pref[1]["id"] == phits["id"]).all()
+    off2, rows2, cig2, _ = searcher.align(qres, qoff, poff, phits["id"], db_res)
+    qlens = [len(q) for q in Q]
+    tlens = [len(t) for t in T]
+    a = api.format_align_rows(rows, cig, qlens, tlens)
+    b = api.format_align_rows(rows2, cig2, qlens, tlens)
+    assert (off == off2).all() and a == b
+    ref = Cm.dump("family", "aln_max300.txt.gz")
+    got = {i: a[int(off[i]):int(off[i + 1])] for i in range(len(Q)) if off[i + 1] > off[i]}
+    assert got == ref
