@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- spacer-frame queries/s of the SpacePHARER search hot path (prefilter + align) on B200.
+
+Workload (BASELINE.json configs[1]): 10 000 synthetic spacers (25-45 nt, six-frame translated, ~38 k frames)
+against a synthetic GenBank_phage_2018_09-shaped ORF set (8 000 genomes, ~0.5 M ORFs, ~53 M residues),
+predictmatch parameters (VTML80 seeding, -s 5.7, k = 6 spaced 11011101, --max-seqs 300, VTML40 16/2, -e 200, -a 1).
+
+A "step" is one pass of the search (prefilter -> align) over the whole query batch against the resident index:
+  value   : device-resident pass (queries already in HBM), CUDA events on the library's stream, L2 flushed
+            between steps, max over ranks
+  e2e     : the same pass through the public API with HOST buffers (pinned): H2D of the frames, kernels,
+            D2H of the sorted result rows + CIGARs, wall clock around synchronised calls
+  roofline: the prefilter match kernel (dominant kernel), algorithmic bytes / its CUDA-event duration against the
+            measured HBM peak (MEASURED_PEAKS.json)
+  cpu_baseline / --impl reference: the CPU oracle port (oracle/, OpenMP over queries like the reference) on a
+            bounded sample of the same workload on this host's cores.
+N > 1 (torchrun): targets sharded across ranks like MMseqs2 --split (target split), queries replicated, per-query
+candidate lists exchanged over NCCL and merged to the unsplit result; `--split-mode query` runs query replicas.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "spacer-frame queries/sec (prefilter+align)"
+UNIT = "queries/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--spacers", type=int, default=10000)
+    ap.add_argument("--genomes", type=int, default=8000)
+    ap.add_argument("--split-mode", default="target", choices=["target", "query"])
+    ap.add_argument("--cpu-sample-spacers", type=int, default=0, help="spacers in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mask", action="store_true", help="skip the tantan host pre-step (--mask 0)")
+    return ap.parse_args()
+
+
+def workload(args):
+    from spacepharer_b200 import synth
+    tres, toff, _ = synth.make_targets(n_genomes=args.genomes)
+    qres, qoff, _ = synth.make_query_frames(args.spacers, tres, toff)
+    return tres, toff, qres, qoff
+
+
+def workload_name(args, Q, T, nres):
+    return ("%d synthetic spacers (25-45 nt, six-frame, %d frames) vs synthetic GenBank_phage_2018_09-shaped ORF setDB "
+            "(%d genomes, %d ORFs, %d aa); predictmatch search parameters" % (args.spacers, Q, args.genomes, T, nres))
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port)
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_run(args, tres, toff, qres, qoff, steps, warmup, sample_spacers, masked=None):
+    """Times the CPU port (oracle/) of the same path: prefilter batch + alignment of its hit lists, OpenMP over
+    queries with all host threads, on the first `sample_spacers`-worth of frames.  Index build is excluded (it is
+    excluded on the GPU side too) and reported separately."""
+    from oracle import pyoracle as O
+    from spacepharer_b200 import matrices
+    m80 = O.parse_matrix(matrices.matrix_text("VTML80.out"), 8.0, -0.2)
+    m40u = O.parse_matrix(matrices.matrix_text("VTML40.out"), 2.0, -0.2)
+    m40 = O.parse_matrix(matrices.matrix_text("VTML40.out"), 2.0, 0.0)
+    cores = os.cpu_count() or 1
+    Q = len(qoff) - 1
+    frames_per_spacer = Q / float(args.spacers)
+    nq = int(min(Q, max(1, round(sample_spacers * frames_per_spacer))))
+    t0 = time.perf_counter()
+    pf = O.Prefilter(masked if masked is not None else tres, toff, m80, m40u)
+    build_s = time.perf_counter() - t0
+    p = O.align_params(int(toff[-1]))
+    sq, so = qres[: int(qoff[nq])], qoff[: nq + 1]
+    times = []
+    rows_acc = 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        off, hits = pf.batch(sq, so, threads=cores)
+        rows = O.align_batch(m40, p, sq, so, tres, toff, off, hits["id"], threads=cores)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+            rows_acc = int((rows["ok"] == 1).sum())
+    pf.close()
+    mean = float(np.mean(times))
+    return {"value": nq / mean, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "first %d frames (%d spacers) of the workload, %d step(s); oracle index build %.1f s excluded"
+                      % (nq, sample_spacers, len(times), build_s),
+            "ms_per_step": mean * 1e3, "sample_queries": nq, "rows": rows_acc}
+
+
+def auto_sample(cores):
+    # the scalar port does roughly 350 frames/s/core; aim at ~10 s per CPU step
+    return int(max(500, min(10000, 900 * cores)))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    tres, toff, qres, qoff = workload(args)
+    cores = os.cpu_count() or 1
+    sample = args.cpu_sample_spacers or auto_sample(cores)
+    sample = min(sample, args.spacers)
+    masked = None
+    if not args.no_mask:
+        from oracle import pyoracle as O  # noqa: F401  (the port masks with its own tantan restatement)
+        masked = oracle_mask(tres, toff)
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    r = cpu_reference_run(args, tres, toff, qres, qoff, steps, warm, sample, masked)
+    Q = len(qoff) - 1
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": workload_name(args, Q, len(toff) - 1, int(toff[-1])),
+                       "note": "CPU port of the reference path (oracle/, scalar C + OpenMP); each step = the bounded sample"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def oracle_mask(tres, toff):
+    """tantan masking with the oracle's restatement (reference arm only)."""
+    import ctypes as C
+    from oracle import pyoracle as O
+    from spacepharer_b200 import matrices
+    m80 = O.parse_matrix(matrices.matrix_text("VTML80.out"), 8.0, -0.2)
+    out = np.array(tres, dtype=np.uint8, copy=True)
+    L = O.lib()
+    base = out.ctypes.data
+    for i in range(len(toff) - 1):
+        a, b = int(toff[i]), int(toff[i + 1])
+        L.spo_tantan_mask(C.byref(m80), C.cast(base + a, C.POINTER(C.c_ubyte)), b - a)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from spacepharer_b200 import api, multigpu
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.gpus != world and rank == 0:
+        print("bench.py: warning: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
+
+    tres, toff, qres, qoff = workload(args)
+    T, Q = len(toff) - 1, len(qoff) - 1
+    db_res = int(toff[-1])
+    t0 = time.perf_counter()
+    eng = multigpu.ShardedSearcher(device=local, rank=rank, world=world, split_mode=args.split_mode)
+    masked, n_masked = (tres, 0) if args.no_mask else api.tantan_mask(eng.searcher.seed, tres, toff)
+    mask_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ist = eng.load_targets(masked, tres, toff)
+    build_s = time.perf_counter() - t0
+
+    # pinned host copies of the query batch (what a caller hands to the public API)
+    q_pin = torch.from_numpy(np.ascontiguousarray(qres)).pin_memory()
+    o_pin = torch.from_numpy(np.ascontiguousarray(qoff).view(np.int64)).pin_memory()
+    q_np, o_np = q_pin.numpy(), o_pin.numpy().view(np.uint64)
+    stream = torch.cuda.ExternalStream(eng.searcher.stream_ptr(), device=torch.device("cuda", local))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg ("value") ----
+    eng.set_queries(q_np, o_np)
+    for _ in range(args.warmup):
+        eng.step_resident(db_res)
+    launches0 = eng.launches()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    pk_ms, pk_bytes, sw_ms, sw_cells = [], [], [], []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()          # L2 flush between timed iterations (256 MB > 126 MB L2), outside the events
+            ev[k][0].record(stream)
+        st = eng.step_resident(db_res)
+        ev[k][1].record(stream)
+        pk_ms.append(st["prefilter"]["kernel_ms"])
+        pk_bytes.append(st["prefilter"]["algo_bytes"])
+        sw_ms.append(st["align"]["kernel_ms"])
+        sw_cells.append(st["align"]["n_cells"])
+    barrier()
+    wall_value = time.perf_counter() - t_wall0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = eng.launches() - launches0
+    last = st
+
+    # ---- end-to-end leg through the public API with host buffers ----
+    for _ in range(min(2, args.warmup)):
+        eng.search_host(q_np, o_np, db_res)
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for k in range(args.steps):
+        res = eng.search_host(q_np, o_np, db_res)
+        d2h = res["d2h_bytes"]
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    q_total = eng.queries_per_step(Q)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        kms = float(np.mean(pk_ms))
+        achieved = float(np.mean(pk_bytes)) / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": q_total * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.split_mode == "target" else "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args, Q, T, db_res), "queries_per_step": q_total,
+                       "split_mode": args.split_mode if world > 1 else "none",
+                       "l2": "256 MB memset between timed steps (outside the per-step CUDA events); index %.2f GB > L2"
+                             % (ist["bytes_device"] / 1e9),
+                       "timing": "sum of per-step CUDA-event intervals on the library stream, max over ranks",
+                       "index": "resident (built once: %.1f ms device, %.2f s wall incl. H2D; tantan host pre-step %.2f s, %d residues masked)"
+                                % (ist["build_ms"], build_s, mask_s, n_masked)},
+            "e2e": {"value": q_total * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(q_np.nbytes + o_np.nbytes), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "prefilter_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                         "algo_bytes_per_launch": float(np.mean(pk_bytes)), "kernel_ms": kms,
+                         "share_of_step": kms / (dev_ms / args.steps)},
+            "sw": {"gcups": float(np.mean(sw_cells)) / (float(np.mean(sw_ms)) * 1e-3) / 1e9 if np.mean(sw_ms) > 0 else None,
+                   "kernel_ms": float(np.mean(sw_ms)), "cells_per_step": float(np.mean(sw_cells)),
+                   "pairs": last["align"]["n_pairs"], "rows": last["align"]["n_rows"]},
+            "clocks": clocks,
+            "wall_s_value_leg": wall_value,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            sample = min(args.spacers, args.cpu_sample_spacers or auto_sample(cores))
+            r = cpu_reference_run(args, tres, toff, qres, qoff, 1, 0, sample, masked if not args.no_mask else None)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return float(json.load(open(p))["prefilter_kernel_dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

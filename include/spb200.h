@@ -43,6 +43,8 @@ const char *spb_last_error(void);
 const char *spb_version(void);
 /* the CUDA stream all work of this context is enqueued on (cudaStream_t as void*) */
 void *spb_ctx_stream(spb_ctx *ctx);
+/* number of this library's own CUDA kernels launched on the context so far (cub library kernels not counted) */
+uint64_t spb_ctx_launches(spb_ctx *ctx);
 
 /* ---- substitution matrices ---------------------------------------------------------------------
  * int16 scores as the reference's SubstitutionMatrix produces them (row-major [21][21]):

@@ -124,6 +124,9 @@ def lib():
                                  C.POINTER(Aln)]
     L.spo_sw_forward.argtypes = [C.POINTER(Matrix), C.POINTER(AlignParams), u8p, C.c_int, u8p, C.c_int,
                                  C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.spo_align_batch.argtypes = [C.POINTER(Matrix), C.POINTER(AlignParams), u8p, C.POINTER(C.c_uint64), C.c_uint32, u8p,
+                                  C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_void_p, C.c_int]
+    L.spo_align_batch.restype = None
     L.spo_format_row.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(Aln), C.c_int, C.c_int]
     L.spo_format_row.restype = C.c_int
     _LIB = L
@@ -290,3 +293,24 @@ def align_query(m40, p, q, targets, keys):
             res.append((a.eval, -a.bits, len(t), key, format_row(key, a, len(q), len(t))))
     res.sort(key=lambda r: r[:4])
     return [r[4] for r in res]
+
+
+ALN_ROW = np.dtype([("ok", "<i4"), ("score", "<i4"), ("bits", "<i4"), ("_pad", "<i4"), ("eval", "<f8"),
+                    ("q_start", "<i4"), ("q_end", "<i4"), ("t_start", "<i4"), ("t_end", "<i4"),
+                    ("n_ident", "<i4"), ("aln_len", "<i4")])
+
+
+def align_batch(m40, p, qres, qoff, tres, toff, pair_off, pair_t, threads=0):
+    """OpenMP batch alignment of a CSR pair list -> structured rows (one per pair, ok==1 means accepted)."""
+    qres = np.ascontiguousarray(qres, dtype=np.uint8)
+    tres = np.ascontiguousarray(tres, dtype=np.uint8)
+    qoff = np.ascontiguousarray(qoff, dtype=np.uint64)
+    toff = np.ascontiguousarray(toff, dtype=np.uint64)
+    pair_off = np.ascontiguousarray(pair_off, dtype=np.uint64)
+    pair_t = np.ascontiguousarray(pair_t, dtype=np.uint32)
+    rows = np.zeros(max(1, int(pair_off[-1])), dtype=ALN_ROW)
+    u64p = C.POINTER(C.c_uint64)
+    lib().spo_align_batch(C.byref(m40), C.byref(p), _u8(qres), qoff.ctypes.data_as(u64p), len(qoff) - 1, _u8(tres),
+                          toff.ctypes.data_as(u64p), pair_off.ctypes.data_as(u64p),
+                          pair_t.ctypes.data_as(C.POINTER(C.c_uint32)), rows.ctypes.data, threads)
+    return rows[: int(pair_off[-1])]

@@ -1153,6 +1153,28 @@ void spo_align_pair(const spo_matrix *m, const spo_align_params *p, const unsign
     free(cb); free(sc);
 }
 
+/* batch driver (OpenMP over queries like Alignment.cpp:285-321, schedule(dynamic,5)); rows[k] for pair k of the CSR
+ * list pairOff[Q+1] / pairT[]; used by the parity tests at scale and by bench.py's CPU baseline leg */
+void spo_align_batch(const spo_matrix *m, const spo_align_params *p, const unsigned char *qres, const uint64_t *qoff,
+                     uint32_t Q, const unsigned char *tres, const uint64_t *toff, const uint64_t *pairOff,
+                     const uint32_t *pairT, spo_aln_row *rows, int threads) {
+    (void)threads;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 5) num_threads(threads > 0 ? threads : omp_get_max_threads())
+#endif
+    for (long i = 0; i < (long)Q; i++) {
+        spo_aln a;
+        for (uint64_t k = pairOff[i]; k < pairOff[i + 1]; k++) {
+            uint32_t t = pairT[k];
+            spo_align_pair(m, p, qres + qoff[i], (int)(qoff[i + 1] - qoff[i]), tres + toff[t], (int)(toff[t + 1] - toff[t]), &a);
+            spo_aln_row *r = rows + k;
+            r->ok = a.ok; r->score = a.score; r->bits = a.bits; r->eval = a.eval;
+            r->qStart = a.qStart; r->qEnd = a.qEnd; r->tStart = a.tStart; r->tEnd = a.tEnd;
+            r->nIdent = a.nIdent; r->alnLen = a.alnLen;
+        }
+    }
+}
+
 /* Matcher::resultToBuffer + Util::fastSeqIdToBuffer (M/alignment/Matcher.cpp:323-370, M/commons/Util.cpp:278-307) */
 int spo_format_row(char *buf, uint32_t tKey, const spo_aln *a, int qLen, int tLen) {
     char sid[16];

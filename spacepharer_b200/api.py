@@ -89,6 +89,14 @@ class Searcher:
                                              p40.ctypes.data_as(f64)))
         self.T = 0
 
+    def stream_ptr(self):
+        """cudaStream_t (as int) all work of this searcher is enqueued on"""
+        return int(self.lib.spb_ctx_stream(self.h) or 0)
+
+    def launches(self):
+        """number of libspb200 kernels launched on this context so far"""
+        return int(self.lib.spb_ctx_launches(self.h))
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.spb_ctx_destroy(self.h)

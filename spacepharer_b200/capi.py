@@ -57,7 +57,7 @@ class AlignResult(C.Structure):
 # every symbol include/spb200.h declares (tests check the library exports exactly these)
 SYMBOLS = [
     "spb_ctx_create", "spb_ctx_destroy", "spb_last_error", "spb_version", "spb_ctx_stream", "spb_set_matrices",
-    "spb_index_build", "spb_index_stats_get", "spb_index_export", "spb_similar_kmers", "spb_prefilter",
+    "spb_ctx_launches", "spb_index_build", "spb_index_stats_get", "spb_index_export", "spb_similar_kmers", "spb_prefilter",
     "spb_free_prefilter_result", "spb_align_set_targets", "spb_align", "spb_free_align_result", "spb_evalue",
     "spb_bitscore", "spb_tantan_mask", "spb_queries_set", "spb_prefilter_resident", "spb_prefilter_stats",
     "spb_prefilter_fetch", "spb_pairs_set", "spb_pairs_from_prefilter", "spb_align_resident", "spb_align_stats",
@@ -87,6 +87,8 @@ def load():
     L.spb_version.restype = C.c_char_p
     L.spb_ctx_stream.argtypes = [vp]
     L.spb_ctx_stream.restype = vp
+    L.spb_ctx_launches.argtypes = [vp]
+    L.spb_ctx_launches.restype = C.c_uint64
     L.spb_set_matrices.argtypes = [vp, C.POINTER(C.c_int16), C.POINTER(C.c_double), C.POINTER(C.c_int16),
                                    C.POINTER(C.c_int16), C.POINTER(C.c_double)]
     L.spb_index_build.argtypes = [vp, u8p, u64p, C.c_uint32, C.c_char_p, C.c_int]

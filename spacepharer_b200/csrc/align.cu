@@ -510,10 +510,10 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
     SPB_CUDA(cudaMemsetAsync(c->s_f.p, 0, 128, st));
     align_profile_kernel<<<Q, 64, 0, st>>>(c->d_q.as<uint8_t>(), c->d_qoff64.as<uint64_t>(), Q, c->d_mat.as<Matrices>(), p->comp_bias,
                                            c->s_a.as<signed char>(), c->s_b.as<int>());
-    SPB_CUDA(cudaGetLastError());
+    SPB_CUDA(cudaGetLastError()); c->n_launches++;
     uint32_t *itemCnt = c->s_c.as<uint32_t>(), *itemBase = itemCnt + (Q + 1);
     item_count_kernel<<<(Q + 1 + 255) / 256, 256, 0, st>>>(c->d_pairoff.as<uint64_t>(), Q, itemCnt);
-    SPB_CUDA(cudaGetLastError());
+    SPB_CUDA(cudaGetLastError()); c->n_launches++;
     size_t tmpBytes = 0;
     SPB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, itemCnt, itemBase, (int)(Q + 1), st));
     if (c->s_cub.ensure(tmpBytes)) return 1;
@@ -523,7 +523,7 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
     SPB_CUDA(cudaStreamSynchronize(st));
     if (c->s_d.ensure((size_t)nItems * sizeof(FwdItem) + 16)) return 1;
     item_fill_kernel<<<(Q + 255) / 256, 256, 0, st>>>(c->d_pairoff.as<uint64_t>(), itemBase, Q, c->s_d.as<FwdItem>());
-    SPB_CUDA(cudaGetLastError());
+    SPB_CUDA(cudaGetLastError()); c->n_launches++;
 
     AlnArgs A;
     memset(&A, 0, sizeof(A));
@@ -552,7 +552,7 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
     SPB_CUDA(cudaFuncSetAttribute(sw_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SPB_CUDA(cudaEventRecord(c->ev0, st));
     sw_forward_kernel<<<(nItems + warpsPerBlock - 1) / warpsPerBlock, 32 * warpsPerBlock, smem, st>>>(A);
-    SPB_CUDA(cudaGetLastError());
+    SPB_CUDA(cudaGetLastError()); c->n_launches++;
     SPB_CUDA(cudaEventRecord(c->ev1, st));
 
     // ---- accepted pairs
@@ -576,7 +576,7 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
         if (c->s_g.ensure(((size_t)nAcc + 1) * 16)) return 1;
         uint64_t *heSz = c->s_g.as<uint64_t>(), *heOff = heSz + (nAcc + 1);
         he_size_kernel<<<(nAcc + 1 + 255) / 256, 256, 0, st>>>(A.out, c->d_acc.as<uint32_t>(), nAcc, heSz);
-        SPB_CUDA(cudaGetLastError());
+        SPB_CUDA(cudaGetLastError()); c->n_launches++;
         SPB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, heSz, heOff, (int)(nAcc + 1), st));
         if (c->s_cub.ensure(tmpBytes)) return 1;
         SPB_CUDA(cub::DeviceScan::ExclusiveSum(c->s_cub.p, tmpBytes, heSz, heOff, (int)(nAcc + 1), st));
@@ -596,12 +596,12 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
         B.heScratch = c->s_h.as<short2>();
         B.heOff = heOff;
         sw_reverse_kernel<<<(nAcc + 63) / 64, 64, 0, st>>>(B);
-        SPB_CUDA(cudaGetLastError());
+        SPB_CUDA(cudaGetLastError()); c->n_launches++;
         if (c->s_i.ensure(((size_t)nAcc + 1) * 16) || c->s_j.ensure(((size_t)nAcc + 1) * 16)) return 1;
         uint64_t *tbSz = c->s_i.as<uint64_t>(), *tbOff = tbSz + (nAcc + 1);
         uint64_t *cigSz = c->s_j.as<uint64_t>(), *cigOff = cigSz + (nAcc + 1);
         tb_size_kernel<<<(nAcc + 1 + 255) / 256, 256, 0, st>>>(A.out, c->d_acc.as<uint32_t>(), nAcc, tbSz, cigSz, d_err);
-        SPB_CUDA(cudaGetLastError());
+        SPB_CUDA(cudaGetLastError()); c->n_launches++;
         SPB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, tbSz, tbOff, (int)(nAcc + 1), st));
         if (c->s_cub.ensure(tmpBytes)) return 1;
         SPB_CUDA(cub::DeviceScan::ExclusiveSum(c->s_cub.p, tmpBytes, tbSz, tbOff, (int)(nAcc + 1), st));
@@ -619,7 +619,7 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
         B.cigOff = cigOff;
         B.cigar = c->d_cig.as<char>();
         sw_traceback_kernel<<<(nAcc + 63) / 64, 64, 0, st>>>(B);
-        SPB_CUDA(cudaGetLastError());
+        SPB_CUDA(cudaGetLastError()); c->n_launches++;
         c->n_cigar = cigTotal;
     }
     SPB_CUDA(cudaEventRecord(c->ev3, st));
@@ -677,7 +677,7 @@ extern "C" int spb_pairs_from_prefilter(spb_ctx *c) {
     SPB_CUDA(cudaMemcpyAsync(c->d_pairoff.p, c->d_hitoff.p, ((size_t)Q + 1) * 8, cudaMemcpyDeviceToDevice, c->stream));
     if (NP) {
         hit_ids_kernel<<<(unsigned)((NP + 255) / 256), 256, 0, c->stream>>>(c->d_hits.as<spb_hit>(), NP, c->d_pairT.as<uint32_t>());
-        SPB_CUDA(cudaGetLastError());
+        SPB_CUDA(cudaGetLastError()); c->n_launches++;
     }
     c->n_pairs = NP;
     c->have_pairs = true;
@@ -720,7 +720,7 @@ extern "C" int spb_align_fetch(spb_ctx *c, spb_align_result **out) {
         if (c->s_g.ensure((size_t)nAcc * sizeof(spb_aln))) { spb_free_align_result(res); return 1; }
         pack_rows_kernel<<<(nAcc + 255) / 256, 256, 0, st>>>(c->d_pairout.as<PairOut>(), c->d_acc.as<uint32_t>(), nAcc,
                                                              c->d_pairQ.as<uint32_t>(), c->d_pairT.as<uint32_t>(), c->s_g.as<spb_aln>());
-        cudaError_t e = cudaGetLastError();
+        cudaError_t e = cudaGetLastError(); c->n_launches++;
         if (e == cudaSuccess) e = cudaMemcpyAsync(res->rows, c->s_g.p, (size_t)nAcc * sizeof(spb_aln), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess && c->n_cigar) e = cudaMemcpyAsync(res->cigar_ops, c->d_cig.p, c->n_cigar, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);

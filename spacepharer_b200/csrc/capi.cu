@@ -61,6 +61,7 @@ void spb_ctx_destroy(spb_ctx *c) {
 }
 
 void *spb_ctx_stream(spb_ctx *c) { return c ? (void *)c->stream : nullptr; }
+uint64_t spb_ctx_launches(spb_ctx *c) { return c ? c->n_launches : 0; }
 
 int spb_set_matrices(spb_ctx *c, const int16_t *sub_seed, const double *pback_seed, const int16_t *sub_ungapped,
                      const int16_t *sub_align, const double *pback_align) {

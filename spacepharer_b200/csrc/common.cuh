@@ -78,6 +78,7 @@ struct spb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    uint64_t n_launches = 0;      // hand-written kernels launched so far (library kernels such as cub's are not counted)
     bool have_matrices = false;
     spb::Matrices hm;             // host copy
     spb::DevBuf d_mat;            // device copy of spb::Matrices

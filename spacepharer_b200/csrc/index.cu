@@ -205,7 +205,7 @@ extern "C" int spb_index_build(spb_ctx *c, const uint8_t *residues, const uint64
     // ---- 3-mer rows
     if (c->d_row3.ensure((size_t)SPB_N3 * SPB_N3 * 4) || c->d_cnt3.ensure((size_t)SPB_N3 * SPB_CNT3_W * 2)) return 1;
     row3_kernel<<<SPB_N3, 256, 0, st>>>(c->d_mat.as<Matrices>(), c->d_row3.as<uint32_t>(), c->d_cnt3.as<uint16_t>());
-    SPB_CUDA(cudaGetLastError());
+    SPB_CUDA(cudaGetLastError()); c->n_launches++;
 
     // ---- postings
     const size_t Np = (size_t)(N > 0 ? N : 1);
@@ -233,7 +233,7 @@ extern "C" int spb_index_build(spb_ctx *c, const uint8_t *residues, const uint64
         int blocks = (int)((T + 7) / 8 < 148 * 16 ? (T + 7) / 8 : 148 * 16);
         extract_kmers_kernel<<<blocks, 256, 0, st>>>(c->d_tres.as<uint8_t>(), c->d_toff.as<uint32_t>(), T, pat, kmer_thr,
                                                      c->d_mat.as<Matrices>(), keysA.as<uint64_t>(), valsA.as<uint16_t>(), d_nValid);
-        IDX_CUDA(cudaGetLastError());
+        IDX_CUDA(cudaGetLastError()); c->n_launches++;
     }
     unsigned long long M = 0;
     IDX_CUDA(cudaMemcpyAsync(&M, d_nValid, 8, cudaMemcpyDeviceToHost, st));
@@ -253,7 +253,7 @@ extern "C" int spb_index_build(spb_ctx *c, const uint8_t *residues, const uint64
         uint32_t *excl = flags + M;
         unsigned gridM = (unsigned)((M + 255) / 256);
         flag_first_kernel<<<gridM, 256, 0, st>>>(keysB.as<uint64_t>(), M, flags);
-        IDX_CUDA(cudaGetLastError());
+        IDX_CUDA(cudaGetLastError()); c->n_launches++;
         size_t tmp2 = 0;
         IDX_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, flags, excl, (int64_t)M, st));
         if (cubTmp.ensure(tmp2)) { cleanup(); return 1; }
@@ -269,10 +269,10 @@ extern "C" int spb_index_build(spb_ctx *c, const uint8_t *residues, const uint64
         uint32_t *pk = cubTmp.as<uint32_t>();
         scatter_postings_kernel<<<gridM, 256, 0, st>>>(keysB.as<uint64_t>(), valsB.as<uint16_t>(), flags, excl, M,
                                                        c->d_post.as<uint64_t>(), pk);
-        IDX_CUDA(cudaGetLastError());
+        IDX_CUDA(cudaGetLastError()); c->n_launches++;
         unsigned gridP = (unsigned)((nPost + 1 + 255) / 256);
         fill_offsets_kernel<<<gridP, 256, 0, st>>>(pk, nPost, c->d_koff.as<uint32_t>(), d_nNonEmpty);
-        IDX_CUDA(cudaGetLastError());
+        IDX_CUDA(cudaGetLastError()); c->n_launches++;
     } else {
         if (c->d_post.ensure(64)) { cleanup(); return 1; }
         IDX_CUDA(cudaMemsetAsync(c->d_koff.p, 0, ((size_t)SPB_NK + 2) * 4, st));
@@ -314,7 +314,7 @@ extern "C" int spb_index_export(spb_ctx *c, uint32_t *kmer, uint32_t *id, uint16
     if (dk.ensure(c->n_post * 4) || di.ensure(c->n_post * 4) || dp.ensure(c->n_post * 2)) return 1;
     export_postings_kernel<<<(SPB_NK + 255) / 256, 256, 0, c->stream>>>(c->d_koff.as<uint32_t>(), c->d_post.as<uint64_t>(),
                                                                         dk.as<uint32_t>(), di.as<uint32_t>(), dp.as<uint16_t>());
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = cudaGetLastError(); c->n_launches++;
     if (e == cudaSuccess) e = cudaMemcpyAsync(kmer, dk.p, c->n_post * 4, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(id, di.p, c->n_post * 4, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(pos, dp.p, c->n_post * 2, cudaMemcpyDeviceToHost, c->stream);

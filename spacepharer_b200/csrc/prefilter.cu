@@ -741,10 +741,10 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
         const size_t smem = (size_t)PF_SMEM_CAP * sizeof(Rec);
         SPB_CUDA(cudaEventRecord(c->ev0, st));
         prefilter_kernel<false><<<Q, PF_THREADS, smem, st>>>(A);
-        SPB_CUDA(cudaGetLastError());
+        SPB_CUDA(cudaGetLastError()); c->n_launches++;
         SPB_CUDA(cudaEventRecord(c->ev1, st));
         status_scan_kernel<<<(Q + 255) / 256, 256, 0, st>>>(A.status, A.need, Q, c->s_e.as<uint32_t>(), d_ctr);
-        SPB_CUDA(cudaGetLastError());
+        SPB_CUDA(cudaGetLastError()); c->n_launches++;
         SPB_CUDA(cudaMemcpyAsync(h_ctr, d_ctr, 32, cudaMemcpyDeviceToHost, st));
         SPB_CUDA(cudaStreamSynchronize(st));
         float ms = 0;
@@ -768,14 +768,14 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
                 A.gScratch = c->s_h.as<Rec>();
                 A.cap = capG;
                 prefilter_kernel<true><<<chunk, PF_THREADS, 0, st>>>(A);
-                SPB_CUDA(cudaGetLastError());
+                SPB_CUDA(cudaGetLastError()); c->n_launches++;
             }
             SPB_CUDA(cudaEventRecord(c->ev1, st));
             // which of them still need more room (their status stays ST_CAPACITY)?
             if (c->s_i.ensure((size_t)Q * 4)) return 1;
             SPB_CUDA(cudaMemsetAsync(d_ctr, 0, 32, st));
             status_scan_kernel<<<(Q + 255) / 256, 256, 0, st>>>(A.status, A.need, Q, c->s_i.as<uint32_t>(), d_ctr);
-            SPB_CUDA(cudaGetLastError());
+            SPB_CUDA(cudaGetLastError()); c->n_launches++;
             SPB_CUDA(cudaMemcpyAsync(h_ctr, d_ctr, 32, cudaMemcpyDeviceToHost, st));
             SPB_CUDA(cudaStreamSynchronize(st));
             SPB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
@@ -797,7 +797,7 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
     // ---- compact the arena into query order: offsets = exclusive scan of the counts
     if (c->s_i.ensure(((size_t)Q + 1) * 8)) return 1;
     count_to_u64_kernel<<<(Q + 1 + 255) / 256, 256, 0, st>>>(c->s_b.as<uint32_t>(), Q, c->s_i.as<uint64_t>());
-    SPB_CUDA(cudaGetLastError());
+    SPB_CUDA(cudaGetLastError()); c->n_launches++;
     size_t tmpBytes = 0;
     SPB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, c->s_i.as<uint64_t>(), c->d_hitoff.as<uint64_t>(), (int)(Q + 1), st));
     if (c->s_cub.ensure(tmpBytes)) return 1;
@@ -809,7 +809,7 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
     if (nHits) {
         gather_hits_kernel<<<(Q + 3) / 4, 128, 0, st>>>(c->s_g.as<spb_hit>(), c->s_a.as<uint64_t>(), c->d_hitoff.as<uint64_t>(), Q,
                                                         c->d_hits.as<spb_hit>());
-        SPB_CUDA(cudaGetLastError());
+        SPB_CUDA(cudaGetLastError()); c->n_launches++;
     }
     SPB_CUDA(cudaEventRecord(c->ev3, st));
     SPB_CUDA(cudaStreamSynchronize(st));
