@@ -24,9 +24,16 @@
 namespace spb {
 
 // ---- per-query composition bias (SmithWaterman::ssw_init, StripedSmithWaterman.cpp:689-706) ----
+// Also emits, for queries short enough for the register kernel (L <= fastMaxL <= 16), the 16-row profile
+// prof16[q][a][i] = M[a][q_i] + cb_i (int8; rows >= L and the pad symbol a = 21 hold -128) and qfast[q] = 1.
+#define SWF_ROWS 16
+#define SWF_THREADS 64
+#define SWF_PROF_ROWS 22      // 21 residues + the pad symbol used beyond the end of a target
+#define SWF_PAD 21
 __global__ void align_profile_kernel(const uint8_t *__restrict__ q, const uint64_t *__restrict__ qoff, uint32_t Q,
                                      const Matrices *__restrict__ mat, int compBias, signed char *__restrict__ cb,
-                                     int *__restrict__ qbias) {
+                                     int *__restrict__ qbias, signed char *__restrict__ prof16, uint8_t *__restrict__ qfast,
+                                     int fastMaxL) {
     const uint32_t qi = blockIdx.x;
     if (qi >= Q) return;
     __shared__ int s_min;
@@ -58,6 +65,16 @@ __global__ void align_profile_kernel(const uint8_t *__restrict__ q, const uint64
         int mn = 0;
         for (int i = 0; i < SPB_ALPHABET * SPB_ALPHABET; i++) mn = min(mn, (int)(signed char)mat->align[i]);
         qbias[qi] = abs(mn) + abs(min(s_min, 0));
+        qfast[qi] = (uint8_t)(L >= 1 && L <= fastMaxL);
+    }
+    if (L >= 1 && L <= fastMaxL) {
+        signed char *pq = prof16 + (size_t)qi * SWF_PROF_ROWS * SWF_ROWS;
+        for (int x = threadIdx.x; x < SWF_PROF_ROWS * SWF_ROWS; x += blockDim.x) {
+            const int a = x / SWF_ROWS, i = x % SWF_ROWS;
+            int v = -128;
+            if (a < SPB_ALPHABET && i < L) v = (int)(signed char)mat->align[a * SPB_ALPHABET + s[i]] + (int)cb[o + i];
+            pq[x] = (signed char)v;
+        }
     }
 }
 
@@ -206,6 +223,171 @@ __global__ void __launch_bounds__(128) sw_forward_kernel(AlnArgs A) {
     A.pairQ[pair] = it.query;
     A.accFlag[pair] = (uint8_t)(o.status == 1);
     atomicAdd(A.cells, (unsigned long long)L * (unsigned long long)tLen);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Register-resident forward pass for short queries (L <= 16: every spacer frame).
+//
+// One thread owns TWO pairs, packed into the two int16 halves of every register, and keeps the whole DP column
+// (16 rows of H and E) in registers; the target is streamed column by column.  With segLen == 1 (L <= lanes of
+// both emulated SIMD kernels) the reference recurrence is exactly (StripedSmithWaterman.cpp:382-416)
+//     h1 = max(0, Hdiag + s, E)        open = max(0, h1 - go)
+//     E' = max(E - ge, open)           H = max(h1, F)            F' = max(F - ge, open)
+// i.e. 7 packed DPX/ALU instructions per 2 cells: PRMT (two int8 profile scores -> int16x2), VIADD.16x2,
+// 3 x VIADDMNMX.S16x2.RELU, 2 x VIMNMX.S16x2.  Pairs are sorted by target length (descending) so the 64 pairs of a warp
+// finish together.  The per-query profile (22 x 16 int8) is staged in shared memory as s_prof[pair][a][thread]:
+// a thread reads its own 16-byte column, so the LDS.128 of a quarter warp never conflicts.
+// Rows >= L and columns beyond a target's end score -128 and can never raise the maximum.
+// ---------------------------------------------------------------------------------------------------------
+struct FastArgs {
+    const uint32_t *sortedKey;   // tLen + 1 (0: pair not eligible), descending
+    const uint32_t *sortedPair;
+    uint32_t NP;
+    const uint32_t *pairQ, *pairT;
+    const uint64_t *qoff;
+    const int *qbias;
+    const uint4 *prof16;
+    const uint8_t *tres;
+    const uint64_t *toff;
+    PairOut *out;
+    uint8_t *accFlag;
+    int go, ge;
+    double evalThr, dbRes;
+    spb_gumbel g;
+    unsigned long long *cells;
+};
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
+__device__ __noinline__ void sw_finish_pair(const FastArgs &A, uint32_t pair, int L, int tLen, int bias, int score, int col, int row) {
+    PairOut o;
+    memset(&o, 0, sizeof(o));
+    if (score == 0) { col = -1; row = L - 1; }
+    o.score = score;
+    o.qEnd = row;
+    o.tEnd = col;
+    o.word = (score + bias >= 255) ? 1 : 0;     // byte kernel overflow -> word kernel; same recurrence when segLen == 1
+    o.qStart = o.tStart = -1;
+    o.status = 0;
+    if (col >= 0) {
+        o.eval = dev_evalue(A.g, (double)score, (double)L, A.dbRes);
+        o.bits = (int)((A.g.lambda * (double)score - log(A.g.K)) / log(2.0) + 0.5);
+        if (!(o.eval > A.evalThr)) o.status = 1;
+    }
+    A.out[pair] = o;
+    A.accFlag[pair] = (uint8_t)(o.status == 1);
+}
+
+__global__ void __launch_bounds__(SWF_THREADS) sw_fast_kernel(FastArgs A) {
+    __shared__ uint4 s_prof[2][SWF_PROF_ROWS][SWF_THREADS];
+    const int tid = threadIdx.x;
+    const uint32_t e0 = 2u * (blockIdx.x * SWF_THREADS + tid);
+    const uint32_t keyA = e0 < A.NP ? A.sortedKey[e0] : 0u;
+    const uint32_t keyB = e0 + 1 < A.NP ? A.sortedKey[e0 + 1] : 0u;
+    unsigned long long myCells = 0;
+    if (keyA != 0u) {      // keys descend: keyA == 0 implies keyB == 0
+        const uint32_t pA = A.sortedPair[e0];
+        const uint32_t pB = keyB ? A.sortedPair[e0 + 1] : pA;
+        const uint32_t qA = A.pairQ[pA], qB = A.pairQ[pB];
+        const uint32_t tiA = A.pairT[pA], tiB = A.pairT[pB];
+        const int lenA = (int)(keyA - 1u), lenB = keyB ? (int)(keyB - 1u) : 0;
+        const int LA = (int)(A.qoff[qA + 1] - A.qoff[qA]), LB = (int)(A.qoff[qB + 1] - A.qoff[qB]);
+#pragma unroll
+        for (int a = 0; a < SWF_PROF_ROWS; a++) {
+            s_prof[0][a][tid] = __ldg(A.prof16 + (size_t)qA * SWF_PROF_ROWS + a);
+            s_prof[1][a][tid] = __ldg(A.prof16 + (size_t)qB * SWF_PROF_ROWS + a);
+        }
+        // aligned 4-byte windows over the two targets (the residue buffer is padded by 64 bytes)
+        const uint8_t *tA = A.tres + A.toff[tiA], *tB = A.tres + A.toff[tiB];
+        const uint32_t *wA = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(tA) & ~(uintptr_t)3);
+        const uint32_t *wB = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(tB) & ~(uintptr_t)3);
+        const uint32_t shA = (uint32_t)(reinterpret_cast<uintptr_t>(tA) & 3) * 8u, shB = (uint32_t)(reinterpret_cast<uintptr_t>(tB) & 3) * 8u;
+        uint32_t curA = __ldg(wA), curB = __ldg(wB);
+        const uint32_t MGO = ((uint32_t)(-A.go) & 0xFFFFu) * 0x10001u, MGE = ((uint32_t)(-A.ge) & 0xFFFFu) * 0x10001u;
+        uint32_t H[SWF_ROWS], E[SWF_ROWS];
+#pragma unroll
+        for (int i = 0; i < SWF_ROWS; i++) { H[i] = 0; E[i] = 0; }
+        uint32_t best = 0;
+        int colA = -1, colB = -1, rowA = 0, rowB = 0;
+        const int n = max(lenA, lenB);
+        for (int j0 = 0; j0 < n; j0 += 4) {
+            const uint32_t nxA = __ldg(wA + (j0 >> 2) + 1), nxB = __ldg(wB + (j0 >> 2) + 1);
+            uint32_t resA = __funnelshift_r(curA, nxA, shA), resB = __funnelshift_r(curB, nxB, shB);
+            curA = nxA;
+            curB = nxB;
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const int j = j0 + jj;
+                uint32_t a = resA & 0xFFu, b = resB & 0xFFu;
+                resA >>= 8;
+                resB >>= 8;
+                if (j >= lenA || a > SPB_X) a = SWF_PAD;
+                if (j >= lenB || b > SPB_X) b = SWF_PAD;
+                const uint4 pa = s_prof[0][a][tid], pb = s_prof[1][b][tid];
+                const uint32_t paw[4] = {pa.x, pa.y, pa.z, pa.w}, pbw[4] = {pb.x, pb.y, pb.z, pb.w};
+                uint32_t Hd = 0, F = 0, colmax = 0;
+#pragma unroll
+                for (int i = 0; i < SWF_ROWS; i++) {
+                    const int r = i & 3;
+                    const uint32_t sel = (uint32_t)r | ((uint32_t)(r | 8) << 4) | ((uint32_t)(4 + r) << 8) | ((uint32_t)((4 + r) | 8) << 12);
+                    const uint32_t sc = prmt(paw[i >> 2], pbw[i >> 2], sel);       // {s_A(i), s_B(i)} sign-extended
+                    const uint32_t h1 = __viaddmax_s16x2_relu(Hd, sc, E[i]);        // max(Hd + s, E, 0)
+                    const uint32_t open = __vadd2(h1, MGO);                         // h1 - go (may be negative)
+                    E[i] = __viaddmax_s16x2_relu(E[i], MGE, open);                  // max(E - ge, h1 - go, 0)
+                    const uint32_t h = __vmaxs2(h1, F);
+                    F = __viaddmax_s16x2_relu(F, MGE, open);
+                    Hd = H[i];
+                    H[i] = h;
+                    colmax = __vmaxs2(colmax, h);
+                }
+                const uint32_t nb = __vmaxs2(best, colmax);
+                if (nb != best) {      // a strictly better column for at least one of the two pairs
+                    if ((nb & 0xFFFFu) != (best & 0xFFFFu)) {
+                        const uint32_t m = nb & 0xFFFFu;
+                        colA = j;
+#pragma unroll
+                        for (int i = SWF_ROWS - 1; i >= 0; i--) if ((H[i] & 0xFFFFu) == m) rowA = i;
+                    }
+                    if ((nb >> 16) != (best >> 16)) {
+                        const uint32_t m = nb >> 16;
+                        colB = j;
+#pragma unroll
+                        for (int i = SWF_ROWS - 1; i >= 0; i--) if ((H[i] >> 16) == m) rowB = i;
+                    }
+                    best = nb;
+                }
+            }
+        }
+        sw_finish_pair(A, pA, LA, lenA, A.qbias[qA], (int)(best & 0xFFFFu), colA, rowA);
+        myCells = (unsigned long long)LA * (unsigned long long)lenA;
+        if (keyB) {
+            sw_finish_pair(A, pB, LB, lenB, A.qbias[qB], (int)(best >> 16), colB, rowB);
+            myCells += (unsigned long long)LB * (unsigned long long)lenB;
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) myCells += __shfl_down_sync(0xffffffffu, myCells, d);
+    if ((tid & 31) == 0 && myCells) atomicAdd(A.cells, myCells);
+}
+
+// pair -> query map and the sort key of the register kernel (tLen + 1 for eligible queries, else 0)
+__global__ void pair_key_kernel(const uint64_t *__restrict__ pairOff, const uint32_t *__restrict__ pairT,
+                                const uint64_t *__restrict__ toff, const uint8_t *__restrict__ qfast, uint32_t Q,
+                                uint32_t *__restrict__ pairQ, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= Q) return;
+    const uint64_t a = pairOff[q], b = pairOff[q + 1];
+    const bool f = qfast[q] != 0;
+    for (uint64_t k = a + (threadIdx.x & 31); k < b; k += 32) {
+        const uint32_t t = pairT[k];
+        const uint64_t tl = toff[t + 1] - toff[t];
+        pairQ[k] = q;
+        keys[k] = (f && tl < 0x7FFFFFFFull) ? (uint32_t)tl + 1u : 0u;
+        vals[k] = (uint32_t)k;
+    }
 }
 
 // Reverse pass + banded traceback for accepted pairs: one thread per pair, scratch in global memory.
@@ -377,9 +559,10 @@ __global__ void sw_traceback_kernel(TbArgs A) {
 
 
 // ---- work-item construction, scratch sizing and row packing (all on the device) ----
-__global__ void item_count_kernel(const uint64_t *__restrict__ pairOff, uint32_t Q, uint32_t *__restrict__ cnt) {
+__global__ void item_count_kernel(const uint64_t *__restrict__ pairOff, const uint8_t *__restrict__ qfast, uint32_t Q,
+                                  uint32_t *__restrict__ cnt) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < Q) cnt[q] = (uint32_t)((pairOff[q + 1] - pairOff[q] + 31) >> 5);
+    if (q < Q) cnt[q] = qfast[q] ? 0u : (uint32_t)((pairOff[q + 1] - pairOff[q] + 31) >> 5);
     if (q == Q) cnt[q] = 0;
 }
 
@@ -389,6 +572,7 @@ __global__ void item_fill_kernel(const uint64_t *__restrict__ pairOff, const uin
     if (q >= Q) return;
     const uint64_t a = pairOff[q], b = pairOff[q + 1];
     uint32_t k = itemBase[q];
+    if (itemBase[q + 1] == k) return;      // query handled by the register kernel
     for (uint64_t s = a; s < b; s += 32, k++) {
         FwdItem it;
         it.query = q;
@@ -462,6 +646,8 @@ extern "C" int spb_align_set_targets(spb_ctx *c, const uint8_t *residues, const 
     c->aT = T;
     c->a_res = N;
     c->h_aoff.assign(offsets, offsets + T + 1);
+    c->a_maxlen = 0;
+    for (uint32_t i = 0; i < T; i++) c->a_maxlen = std::max<uint64_t>(c->a_maxlen, offsets[i + 1] - offsets[i]);
     c->h_akeys.resize(T);
     for (uint32_t i = 0; i < T; i++) c->h_akeys[i] = keys ? keys[i] : i;
     c->have_aln_targets = true;
@@ -497,33 +683,67 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
     const uint32_t maxL = c->q_maxlen;
     const int Lpad = (int)((maxL + 3) & ~3u);
     const size_t perWarp = (size_t)SPB_ALPHABET * Lpad + (size_t)Lpad * 32 * sizeof(short2);
-    SPB_CHECK(maxL > 0 && perWarp <= 200 * 1024, "spb_align: query length %u outside the supported range of the shared-memory kernel (1..%d)",
-              maxL, (int)(200 * 1024 / (SPB_ALPHABET + 128)));
+    SPB_CHECK(maxL > 0, "spb_align: empty query batch");
     const int warpsPerBlock = (int)std::min<size_t>(4, std::max<size_t>(1, (96 * 1024) / perWarp));
     const size_t smem = perWarp * warpsPerBlock;
     SPB_CUDA(cudaEventRecord(c->ev2, st));
 
-    // scratch: s_a cb i8[q_res], s_b qbias int[Q], s_c itemCnt/itemBase u32[Q+1] x2, s_d items, s_e accFlag u8[NP], s_f counters
+    // scratch: s_a cb i8[q_res], s_b qbias int[Q], s_c itemCnt/itemBase u32[Q+1] x2, s_d items, s_e accFlag u8[NP], s_f counters,
+    //          s_l prof16 [Q][22][16] i8, s_m qfast u8[Q], s_n/s_o sort keys u32[NP] x2, s_p/s_q sort values u32[NP] x2
     if (c->s_a.ensure(c->q_res + 64) || c->s_b.ensure((size_t)Q * 4 + 4) || c->s_c.ensure(((size_t)Q + 1) * 8) ||
         c->s_e.ensure(NP + 64) || c->s_f.ensure(128) || c->d_pairQ.ensure(NP * 4) || c->d_pairout.ensure(NP * sizeof(PairOut)) ||
-        c->d_acc.ensure(NP * 4)) return 1;
+        c->d_acc.ensure(NP * 4) || c->s_l.ensure((size_t)Q * SWF_PROF_ROWS * SWF_ROWS + 64) || c->s_m.ensure((size_t)Q + 64) ||
+        c->s_n.ensure(NP * 4 + 64) || c->s_o.ensure(NP * 4 + 64) || c->s_p.ensure(NP * 4 + 64) || c->s_q.ensure(NP * 4 + 64)) return 1;
     SPB_CUDA(cudaMemsetAsync(c->s_f.p, 0, 128, st));
+    SPB_CUDA(cudaMemsetAsync(c->s_e.p, 0, NP, st));
+    // register kernel eligibility: segLen == 1 in both emulated SIMD kernels and at most 16 rows
+    const int fastMaxL = std::min(SWF_ROWS, std::min(p->byte_lanes, p->word_lanes));
     align_profile_kernel<<<Q, 64, 0, st>>>(c->d_q.as<uint8_t>(), c->d_qoff64.as<uint64_t>(), Q, c->d_mat.as<Matrices>(), p->comp_bias,
-                                           c->s_a.as<signed char>(), c->s_b.as<int>());
+                                           c->s_a.as<signed char>(), c->s_b.as<int>(), c->s_l.as<signed char>(), c->s_m.as<uint8_t>(),
+                                           fastMaxL);
     SPB_CUDA(cudaGetLastError()); c->n_launches++;
-    uint32_t *itemCnt = c->s_c.as<uint32_t>(), *itemBase = itemCnt + (Q + 1);
-    item_count_kernel<<<(Q + 1 + 255) / 256, 256, 0, st>>>(c->d_pairoff.as<uint64_t>(), Q, itemCnt);
+    pair_key_kernel<<<(Q + 3) / 4, 128, 0, st>>>(c->d_pairoff.as<uint64_t>(), c->d_pairT.as<uint32_t>(), c->d_aoff.as<uint64_t>(),
+                                                 c->s_m.as<uint8_t>(), Q, c->d_pairQ.as<uint32_t>(), c->s_n.as<uint32_t>(),
+                                                 c->s_p.as<uint32_t>());
     SPB_CUDA(cudaGetLastError()); c->n_launches++;
     size_t tmpBytes = 0;
+    int keyBits = 1;
+    while (keyBits < 32 && ((uint64_t)1 << keyBits) <= c->a_maxlen + 1) keyBits++;
+    SPB_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmpBytes, c->s_n.as<uint32_t>(), c->s_o.as<uint32_t>(), c->s_p.as<uint32_t>(),
+                                                       c->s_q.as<uint32_t>(), (int)NP, 0, keyBits, st));
+    if (c->s_cub.ensure(tmpBytes)) return 1;
+    SPB_CUDA(cub::DeviceRadixSort::SortPairsDescending(c->s_cub.p, tmpBytes, c->s_n.as<uint32_t>(), c->s_o.as<uint32_t>(), c->s_p.as<uint32_t>(),
+                                                       c->s_q.as<uint32_t>(), (int)NP, 0, keyBits, st));
+    uint32_t *itemCnt = c->s_c.as<uint32_t>(), *itemBase = itemCnt + (Q + 1);
+    item_count_kernel<<<(Q + 1 + 255) / 256, 256, 0, st>>>(c->d_pairoff.as<uint64_t>(), c->s_m.as<uint8_t>(), Q, itemCnt);
+    SPB_CUDA(cudaGetLastError()); c->n_launches++;
     SPB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, itemCnt, itemBase, (int)(Q + 1), st));
     if (c->s_cub.ensure(tmpBytes)) return 1;
     SPB_CUDA(cub::DeviceScan::ExclusiveSum(c->s_cub.p, tmpBytes, itemCnt, itemBase, (int)(Q + 1), st));
     uint32_t nItems = 0;
     SPB_CUDA(cudaMemcpyAsync(&nItems, itemBase + Q, 4, cudaMemcpyDeviceToHost, st));
     SPB_CUDA(cudaStreamSynchronize(st));
-    if (c->s_d.ensure((size_t)nItems * sizeof(FwdItem) + 16)) return 1;
-    item_fill_kernel<<<(Q + 255) / 256, 256, 0, st>>>(c->d_pairoff.as<uint64_t>(), itemBase, Q, c->s_d.as<FwdItem>());
-    SPB_CUDA(cudaGetLastError()); c->n_launches++;
+
+    FastArgs F;
+    memset(&F, 0, sizeof(F));
+    F.sortedKey = c->s_o.as<uint32_t>();
+    F.sortedPair = c->s_q.as<uint32_t>();
+    F.NP = (uint32_t)NP;
+    F.pairQ = c->d_pairQ.as<uint32_t>();
+    F.pairT = c->d_pairT.as<uint32_t>();
+    F.qoff = c->d_qoff64.as<uint64_t>();
+    F.qbias = c->s_b.as<int>();
+    F.prof16 = c->s_l.as<uint4>();
+    F.tres = c->d_ares.as<uint8_t>();
+    F.toff = c->d_aoff.as<uint64_t>();
+    F.out = c->d_pairout.as<PairOut>();
+    F.accFlag = c->s_e.as<uint8_t>();
+    F.go = p->gap_open;
+    F.ge = p->gap_extend;
+    F.evalThr = p->eval_thr;
+    F.dbRes = (double)p->db_res_count;
+    F.g = p->gumbel;
+    F.cells = c->s_f.as<unsigned long long>();
 
     AlnArgs A;
     memset(&A, 0, sizeof(A));
@@ -534,7 +754,7 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
     A.tres = c->d_ares.as<uint8_t>();
     A.toff = c->d_aoff.as<uint64_t>();
     A.mat = c->d_mat.as<Matrices>();
-    A.items = c->s_d.as<FwdItem>();
+    A.items = nullptr;
     A.nItems = nItems;
     A.pairT = c->d_pairT.as<uint32_t>();
     A.pairQ = c->d_pairQ.as<uint32_t>();
@@ -549,10 +769,24 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
     A.g = p->gumbel;
     A.Lpad = Lpad;
     A.cells = c->s_f.as<unsigned long long>();
-    SPB_CUDA(cudaFuncSetAttribute(sw_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SPB_CUDA(cudaEventRecord(c->ev0, st));
-    sw_forward_kernel<<<(nItems + warpsPerBlock - 1) / warpsPerBlock, 32 * warpsPerBlock, smem, st>>>(A);
-    SPB_CUDA(cudaGetLastError()); c->n_launches++;
+    {
+        const uint32_t nThreads = (uint32_t)((NP + 1) / 2);
+        sw_fast_kernel<<<(nThreads + SWF_THREADS - 1) / SWF_THREADS, SWF_THREADS, 0, st>>>(F);
+        SPB_CUDA(cudaGetLastError()); c->n_launches++;
+    }
+    if (nItems) {
+        // queries longer than the register kernel's 16 rows: one warp per (query, <= 32 targets), H/E in shared memory
+        SPB_CHECK(perWarp <= 200 * 1024, "spb_align: query length %u outside the supported range of the shared-memory kernel (1..%d)",
+                  maxL, (int)(200 * 1024 / (SPB_ALPHABET + 128)));
+        if (c->s_d.ensure((size_t)nItems * sizeof(FwdItem) + 16)) return 1;
+        item_fill_kernel<<<(Q + 255) / 256, 256, 0, st>>>(c->d_pairoff.as<uint64_t>(), itemBase, Q, c->s_d.as<FwdItem>());
+        SPB_CUDA(cudaGetLastError()); c->n_launches++;
+        A.items = c->s_d.as<FwdItem>();
+        SPB_CUDA(cudaFuncSetAttribute(sw_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sw_forward_kernel<<<(nItems + warpsPerBlock - 1) / warpsPerBlock, 32 * warpsPerBlock, smem, st>>>(A);
+        SPB_CUDA(cudaGetLastError()); c->n_launches++;
+    }
     SPB_CUDA(cudaEventRecord(c->ev1, st));
 
     // ---- accepted pairs
@@ -560,6 +794,7 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
     uint32_t *d_nAcc = reinterpret_cast<uint32_t *>(d_ctr + 1);
     int *d_err = reinterpret_cast<int *>(d_ctr + 2);
     cub::CountingInputIterator<uint32_t> cnt_it(0);
+    tmpBytes = 0;
     SPB_CUDA(cub::DeviceSelect::Flagged(nullptr, tmpBytes, cnt_it, c->s_e.as<uint8_t>(), c->d_acc.as<uint32_t>(), d_nAcc, (int)NP, st));
     if (c->s_cub.ensure(tmpBytes)) return 1;
     SPB_CUDA(cub::DeviceSelect::Flagged(c->s_cub.p, tmpBytes, cnt_it, c->s_e.as<uint8_t>(), c->d_acc.as<uint32_t>(), d_nAcc, (int)NP, st));

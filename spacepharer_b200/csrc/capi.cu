@@ -50,7 +50,7 @@ void spb_ctx_destroy(spb_ctx *c) {
                            &c->d_ares, &c->d_aoff, &c->d_q, &c->d_qoff, &c->d_qoff64, &c->d_hits, &c->d_hitoff,
                            &c->d_pairoff, &c->d_pairT, &c->d_pairQ, &c->d_pairout, &c->d_acc, &c->d_cig,
                            &c->s_a, &c->s_b, &c->s_c, &c->s_d, &c->s_e, &c->s_f, &c->s_g, &c->s_h, &c->s_i, &c->s_j,
-                           &c->s_k, &c->s_cub};
+                           &c->s_k, &c->s_l, &c->s_m, &c->s_n, &c->s_o, &c->s_p, &c->s_q, &c->s_cub};
     for (spb::DevBuf *b : bufs) b->release();
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);

@@ -102,6 +102,7 @@ struct spb_ctx {
     bool have_aln_targets = false;
     uint32_t aT = 0;
     uint64_t a_res = 0;
+    uint64_t a_maxlen = 0;        // longest target (sort key width of the register SW kernel)
     spb::DevBuf d_ares;           // u8
     spb::DevBuf d_aoff;           // u64[aT+1]
     std::vector<uint64_t> h_aoff; // host copy (work ordering, row order)
@@ -136,7 +137,7 @@ struct spb_ctx {
     spb_align_result aln_stats;
 
     // ---- scratch (grow-only, reused across calls) ----
-    spb::DevBuf s_a, s_b, s_c, s_d, s_e, s_f, s_g, s_h, s_i, s_j, s_k, s_cub;
+    spb::DevBuf s_a, s_b, s_c, s_d, s_e, s_f, s_g, s_h, s_i, s_j, s_k, s_l, s_m, s_n, s_o, s_p, s_q, s_cub;
 };
 
 namespace spb {
