@@ -33,6 +33,10 @@ int spb_ctx_create(int device, spb_ctx **out) {
     SPB_CUDA(cudaSetDevice(device));
     spb_ctx *c = new spb_ctx();
     c->device = device;
+    {
+        int sm = 0;
+        if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sm > 0) c->n_sm = sm;
+    }
     SPB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SPB_CUDA(cudaEventCreate(&c->ev0));
     SPB_CUDA(cudaEventCreate(&c->ev1));
@@ -46,7 +50,7 @@ void spb_ctx_destroy(spb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    spb::DevBuf *bufs[] = {&c->d_mat, &c->d_tres, &c->d_toff, &c->d_koff, &c->d_post, &c->d_row3, &c->d_cnt3,
+    spb::DevBuf *bufs[] = {&c->d_mat, &c->d_tres, &c->d_toff, &c->d_koff, &c->d_post, &c->d_direct, &c->d_row3, &c->d_cnt3,
                            &c->d_ares, &c->d_aoff, &c->d_q, &c->d_qoff, &c->d_qoff64, &c->d_hits, &c->d_hitoff,
                            &c->d_pairoff, &c->d_pairT, &c->d_pairQ, &c->d_pairout, &c->d_acc, &c->d_cig,
                            &c->s_a, &c->s_b, &c->s_c, &c->s_d, &c->s_e, &c->s_f, &c->s_g, &c->s_h, &c->s_i, &c->s_j,

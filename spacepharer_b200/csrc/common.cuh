@@ -76,6 +76,7 @@ struct Matrices {
 
 struct spb_ctx {
     int device = 0;
+    int n_sm = 148;               // multiprocessors of the device (persistent grids)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     uint64_t n_launches = 0;      // hand-written kernels launched so far (library kernels such as cub's are not counted)
@@ -93,6 +94,7 @@ struct spb_ctx {
     spb::DevBuf d_toff;           // u32[T+1]
     spb::DevBuf d_koff;           // u32[20^6 + 1] CSR offsets
     spb::DevBuf d_post;           // u64[n_post]: id << 16 | pos
+    spb::DevBuf d_direct;         // u64[20^6] packed direct table: 0 empty | 1<<63 | posting (one target) | len << 32 | offset
     uint64_t n_post = 0, n_kmers_nonempty = 0;
     spb::DevBuf d_row3;           // u32[8000][8000]: (score + 256) << 16 | 3-mer index
     spb::DevBuf d_cnt3;           // u16[8000][512]: #entries with score >= v

@@ -8,6 +8,8 @@
 //   toff   u32[T+1]
 //   koff   u32[20^6+1]         CSR offsets, k-mer index = sum a_i 20^i (first residue lowest digit, Indexer.h:20-83)
 //   post   u64[n_post]         (id << 16) | pos, sorted by (kmer, id); one posting per (kmer, target): smallest pos
+//   direct u64[20^6]           packed per-k-mer entry (inline posting when one target, else len|offset) -- the table the
+//                              warp-per-query prefilter gathers from
 //   row3   u32[8000][8000]     3-mer neighbours by score desc, ties in cartesian order: (score+256) << 16 | index
 //   cnt3   u16[8000][512]      cnt3[x][v+256] = #neighbours of x with score >= v  (O(1) list lengths)
 #include <cub/cub.cuh>
@@ -139,6 +141,21 @@ __global__ void fill_offsets_kernel(const uint32_t *__restrict__ pk, uint64_t nP
     uint32_t to = (i == nPost) ? SPB_NK : pk[i];  // inclusive
     if (i < nPost && (i == 0 || pk[i - 1] != pk[i])) atomicAdd(nNonEmpty, 1ull);
     for (uint32_t k = from; k <= to && k <= SPB_NK; k++) koff[k] = (uint32_t)i;
+}
+
+// Packed direct table read by the warp-per-query prefilter: one 8-byte entry per k-mer.
+//   0                         no target contains the k-mer
+//   1 << 63 | id << 16 | pos  exactly one target: the posting itself (no second memory access)
+//   len << 32 | offset        len >= 2 postings at post[offset ..)
+__global__ void build_direct_kernel(const uint32_t *__restrict__ koff, const uint64_t *__restrict__ post,
+                                    uint64_t *__restrict__ direct) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= SPB_NK) return;
+    const uint32_t o0 = koff[k], len = koff[k + 1] - o0;
+    uint64_t v = 0;
+    if (len == 1) v = (1ull << 63) | post[o0];
+    else if (len > 1) v = ((uint64_t)len << 32) | o0;
+    direct[k] = v;
 }
 
 __global__ void export_postings_kernel(const uint32_t *__restrict__ koff, const uint64_t *__restrict__ post,
@@ -277,6 +294,9 @@ extern "C" int spb_index_build(spb_ctx *c, const uint8_t *residues, const uint64
         if (c->d_post.ensure(64)) { cleanup(); return 1; }
         IDX_CUDA(cudaMemsetAsync(c->d_koff.p, 0, ((size_t)SPB_NK + 2) * 4, st));
     }
+    if (c->d_direct.ensure((size_t)SPB_NK * 8)) { cleanup(); return 1; }
+    build_direct_kernel<<<(SPB_NK + 255) / 256, 256, 0, st>>>(c->d_koff.as<uint32_t>(), c->d_post.as<uint64_t>(), c->d_direct.as<uint64_t>());
+    IDX_CUDA(cudaGetLastError()); c->n_launches++;
     unsigned long long nonEmpty = 0;
     IDX_CUDA(cudaMemcpyAsync(&nonEmpty, d_nNonEmpty, 8, cudaMemcpyDeviceToHost, st));
     IDX_CUDA(cudaEventRecord(c->ev1, st));
@@ -300,7 +320,7 @@ extern "C" int spb_index_stats_get(spb_ctx *c, spb_index_stats *out) {
     out->n_residues = c->n_res;
     out->n_postings = c->n_post;
     out->n_kmers_nonempty = c->n_kmers_nonempty;
-    out->bytes_device = c->d_tres.cap + c->d_toff.cap + c->d_koff.cap + c->d_post.cap + c->d_row3.cap + c->d_cnt3.cap;
+    out->bytes_device = c->d_tres.cap + c->d_toff.cap + c->d_koff.cap + c->d_post.cap + c->d_direct.cap + c->d_row3.cap + c->d_cnt3.cap;
     out->build_ms = c->build_ms;
     return 0;
 }

@@ -22,7 +22,10 @@
 // few harmless extra hits.  The rank key is (a << 16 | b), the position in the nested 3-mer x 3-mer enumeration.
 #include <cub/cub.cuh>
 
+#include <stdlib.h>
+
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -66,6 +69,13 @@ struct PrefArgs {
     uint32_t *outCount;      // per query
     uint32_t *status;        // per query: ST_*
     uint32_t *need;          // per query: records needed when status == ST_CAPACITY
+    // warp-per-query kernel
+    const uint64_t *direct;  // [20^6] packed k-mer table (index.cu)
+    uint64_t *hitScratch;    // [warps in the grid][hitCap] hit records, L2-resident
+    uint32_t hitCap;
+    unsigned int *qCounter;  // dynamic query scheduler
+    const unsigned int *nListPtr;  // device: entries of qlist (team launch reads it, no host round trip)
+    uint32_t kCapSolo;       // TEAM = 1: queries with more similar k-mers go to the TEAM = 8 launch
 };
 
 #define ST_OK 0u
@@ -554,6 +564,667 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
     if (tid == 0) { A.outStart[qi] = base; A.outCount[qi] = (uint32_t)ns; A.status[qi] = ST_OK; }
 }
 
+// =========================================================================================================
+// Team prefilter: the production path.  A query is owned by a TEAM of warps -- one warp for the bulk of the spacer
+// frames (TEAM = 1, four independent warps per CTA, no CTA barriers), eight warps (one CTA) for the queries whose
+// similar-k-mer list is too long for one warp to walk without becoming the tail of the launch (TEAM = 8).
+//
+// Same rules as prefilter_kernel above, re-laid for memory-level parallelism:
+//  * the index is read through the packed direct table (one 8-byte read per similar k-mer; postings are touched only
+//    for k-mers occurring in >= 2 targets), four independent lookups per lane in flight;
+//  * the hit stream is enumerated ONCE.  All similar k-mers of the query are numbered 0..K-1 in reference order
+//    (window, outer neighbour a, inner neighbour b).  Inner counts are constant over outer neighbours of equal score,
+//    so the numbering is a run-length table in shared memory (one run per distinct outer score of a window: first a,
+//    inner count, first k); lane k finds its run by binary search and derives (a, b) with one division;
+//  * a hit record is one u64 (id << 32 | k << 16 | 16-bit diagonal) whose integer order is (target, stream order).
+//    Records go to a per-team scratch slice in global memory (written and re-read out of L2) while two shared-memory
+//    bitmaps mark targets seen once / twice; only records of targets seen twice (or with 8-bit diagonal 0, quirk B)
+//    are pulled back -- in groups of targets (hash partition) small enough for a warp to sort in shared memory --
+//    and run through the double-hit, de-duplication, ungapped-scoring and best-diagonal rules; the per-target winners
+//    are collected as final sort keys behind the hit records and sorted once at the end.
+// Anything that does not fit (query longer than 64, > 256 runs, >= 65536 k-mers, hit / group / candidate overflow,
+// truncation at max-seqs) is left to prefilter_kernel via status = ST_CAPACITY; queries with more than kCapSolo
+// k-mers are passed from the TEAM = 1 launch to the TEAM = 8 launch via ST_TEAM.  Results are identical on every path.
+// =========================================================================================================
+#define PW_WARPS 4           // independent warps per CTA in the TEAM = 1 launch
+#define PW_TEAM 8            // warps per query in the team launch
+#define PW_MAXL 64
+#define PW_RUNCAP 256
+#define PW_SCAP 256          // records a warp sorts at once
+#define PW_FCAP_SOLO 512     // per-target winners of one query (slots behind the hit records)
+#define PW_FCAP_TEAM 4096
+#define PW_BIG 1024          // TEAM = 8: records the CTA sorts at once in the final stage
+#define PW_U 4               // k-mer lookups per lane in flight
+#define ST_TEAM 4u
+
+struct Run { uint16_t a0, n2, cum, w; };   // cum holds the first concatenated row index until the prefix pass
+
+template <int BMW, int NRUNS>
+struct QuerySmem {
+    uint32_t seen1[BMW], seen2[BMW];
+    Run runs_[NRUNS];                    // TEAM = 1 keeps its runs in the (then idle) sort buffer of the warp instead
+    float cb[PW_MAXL];
+    uint16_t x1[PW_MAXL], x2[PW_MAXL];   // first / second 3-mer of every window
+    uint16_t n1[PW_MAXL];                // outer neighbours of every window
+    uint16_t rowbase[PW_MAXL + 2];       // exclusive prefix of n1
+    short thr[PW_MAXL];
+    uint8_t q[PW_MAXL];
+    signed char corr[PW_MAXL];
+    uint32_t v_qi, v_K, v_nRuns, v_slow, v_why, v_nHits, v_nSurv, v_nFin;
+    int v_minCorr;
+};
+struct WorkSmem {
+    uint64_t surv[PW_SCAP];
+    uint8_t cnt[PW_SCAP];
+};
+
+__device__ __forceinline__ void warp_bitonic_u64(uint64_t *a, int n_pow2) {
+    const int lane = threadIdx.x & 31;
+    for (int k = 2; k <= n_pow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            __syncwarp();
+            for (int t = lane; t < (n_pow2 >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int p = i | j;
+                const bool up = ((i & k) == 0);
+                const uint64_t x = a[i], y = a[p];
+                if (up ? (y < x) : (x < y)) { a[i] = y; a[p] = x; }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// CTA-wide bitonic sort of (key, payload) pairs by key (ascending); n_pow2 entries, padded by the caller
+__device__ __forceinline__ void block_bitonic_pairs(uint64_t *k, uint64_t *v, int n_pow2) {
+    for (int kk = 2; kk <= n_pow2; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (n_pow2 >> 1); t += blockDim.x) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int p = i | j;
+                const bool up = ((i & kk) == 0);
+                const uint64_t x = k[i], y = k[p];
+                if (up ? (y < x) : (x < y)) {
+                    k[i] = y; k[p] = x;
+                    const uint64_t vx = v[i];
+                    v[i] = v[p]; v[p] = vx;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template <int TEAM>
+__global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 ? 8 : 4) prefilter_team_kernel(PrefArgs A) {
+    constexpr bool SOLO = (TEAM == 1);
+    constexpr int BMW = SOLO ? 256 : 1024;          // bitmap words: 8192 / 32768 bits
+    constexpr int NQS = SOLO ? PW_WARPS : 1;
+    constexpr int NWS = SOLO ? PW_WARPS : TEAM;
+    __shared__ QuerySmem<BMW, SOLO ? 1 : PW_RUNCAP> s_qs[NQS];
+    __shared__ WorkSmem s_ws[NWS];
+    __shared__ signed char s_m40u[SPB_ALPHABET * SPB_ALPHABET];
+    __shared__ uint64_t s_big[SOLO ? 1 : 2 * PW_BIG];     // TEAM = 8: CTA-wide final sort (keys | payload)
+    __shared__ unsigned long long s_base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int tw = SOLO ? 0 : wid;                  // warp index inside the team
+    const unsigned lt = (1u << lane) - 1u;
+    for (int i = threadIdx.x; i < SPB_ALPHABET * SPB_ALPHABET; i += blockDim.x) s_m40u[i] = (signed char)A.mat->ungapped[i];
+    __syncthreads();
+    QuerySmem<BMW, SOLO ? 1 : PW_RUNCAP> &S = s_qs[SOLO ? wid : 0];
+    WorkSmem &W = s_ws[wid];
+    Run *const runs = SOLO ? reinterpret_cast<Run *>(W.surv) : S.runs_;
+    auto team_sync = [&]() { if (SOLO) __syncwarp(); else __syncthreads(); };
+    constexpr uint32_t FCAP = SOLO ? PW_FCAP_SOLO : PW_FCAP_TEAM;
+    // hit records | records grouped by target bucket | per-target winners (final key, truncation key)
+    const size_t slice = 2 * (size_t)A.hitCap + 2 * (size_t)FCAP;
+    uint64_t *scratch = A.hitScratch + (size_t)(SOLO ? blockIdx.x * PW_WARPS + wid : blockIdx.x) * slice;
+    uint64_t *finList = scratch + 2 * (size_t)A.hitCap;
+    const uint32_t HCAP = A.hitCap;
+    unsigned long long statK = 0, statM = 0, statE = 0, statS = 0;
+
+    for (;;) {
+        // ---------------- next query ----------------
+        if (tw == 0 && lane == 0) S.v_qi = atomicAdd(A.qCounter, 1u);
+        team_sync();
+        const uint32_t slot = S.v_qi;
+        if (slot >= (A.qlist ? *A.nListPtr : A.Q)) break;
+        const uint32_t qi = A.qlist ? A.qlist[slot] : slot;
+        const uint32_t qo = A.qoff[qi];
+        const int L = (int)(A.qoff[qi + 1] - qo);
+        const int P = L - A.pat.span + 1;
+        if (P < 2) {
+            if (tw == 0 && lane == 0) { A.outStart[qi] = 0; A.outCount[qi] = 0; A.status[qi] = ST_OK; }
+            team_sync();
+            continue;
+        }
+        for (int i = tw * 32 + lane; i < BMW; i += TEAM * 32) { S.seen1[i] = 0; S.seen2[i] = 0; }
+        if (tw == 0) {
+            // ======== set-up by the first warp of the team ========
+            uint32_t why = (L > PW_MAXL) ? ST_CAPACITY : ST_OK;   // status the query leaves this kernel with if not ST_OK
+            uint32_t reason = (L > PW_MAXL) ? 1u : 0u;            // why it was handed over (statistics)
+            int nRuns = 0;
+            uint32_t K = 0;
+            int minCorr = 0;
+            if (lane == 0) { S.v_nHits = 0; S.v_nSurv = 0; S.v_nFin = 0; }
+            if (why == ST_OK) {
+                // query, composition bias (as in prefilter_kernel), window thresholds
+                for (int i = lane; i < L; i += 32) S.q[i] = A.q[qo + i];
+                __syncwarp();
+                for (int i = lane; i < L; i += 32) {
+                    float d = 0.0f;
+                    if (A.compBias) {
+                        const int lo = max(0, i - 20), hi = min(L, i + 20);
+                        const int16_t *row = A.mat->seed + S.q[i] * SPB_ALPHABET;
+                        int sum = 0;
+                        for (int j = lo; j < hi; j++) sum += row[S.q[j]];
+                        sum -= row[S.q[i]];
+                        d = (float)sum;
+                        d = __double2float_rn(__ddiv_rn((double)d, -1.0 * (double)(float)(hi - lo)));
+                        for (int a = 0; a < SPB_ALPHABET; a++)
+                            d = __double2float_rn(__dadd_rn((double)d, __dmul_rn(A.mat->pback_seed[a], (double)(float)row[a])));
+                    }
+                    S.cb[i] = d;
+                    const float t4 = __fdiv_rn(d, 4.0f);
+                    const double dd = (d < 0.0f) ? __dsub_rn((double)t4, 0.5) : __dadd_rn((double)t4, 0.5);
+                    const signed char cc = (signed char)__double2float_rn(dd);
+                    S.corr[i] = cc;
+                    minCorr = min(minCorr, (int)cc);
+                }
+                for (int d = 16; d > 0; d >>= 1) minCorr = min(minCorr, __shfl_xor_sync(0xffffffffu, minCorr, d));
+                __syncwarp();
+                for (int w = lane; w < P; w += 32) {
+                    bool hasX = false;
+                    float b = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 6; k++) {
+                        hasX = hasX || (S.q[w + A.pat.pos[k]] >= SPB_X);
+                        b = __fadd_rn(b, S.cb[w + A.pat.pos[k]]);
+                    }
+                    const short bias = (short)((b < 0.0f) ? __dsub_rn((double)b, 0.5) : __dadd_rn((double)b, 0.5));
+                    const short thr = (short)max(A.kmerThr - (int)bias, 0);
+                    int n1 = 0, x1 = 0, x2 = 0;
+                    if (!hasX && w < P - 1) {   // quirk A: the last window is never counted
+                        x1 = S.q[w + A.pat.pos[0]] + 20 * S.q[w + A.pat.pos[1]] + 400 * S.q[w + A.pat.pos[2]];
+                        x2 = S.q[w + A.pat.pos[3]] + 20 * S.q[w + A.pat.pos[4]] + 400 * S.q[w + A.pat.pos[5]];
+                        const int best2 = (int)(__ldg(A.row3 + (size_t)x2 * SPB_N3) >> 16) - SPB_SCORE_OFF;
+                        const int cut1 = (int)thr - best2;
+                        if (cut1 <= SPB_CNT3_W - SPB_SCORE_OFF - 1)
+                            n1 = (int)__ldg(A.cnt3 + (size_t)x1 * SPB_CNT3_W + max(cut1, -SPB_SCORE_OFF) + SPB_SCORE_OFF);
+                    }
+                    S.thr[w] = thr;
+                    S.n1[w] = (unsigned short)n1;
+                    S.x1[w] = (unsigned short)x1;
+                    S.x2[w] = (unsigned short)x2;
+                }
+                __syncwarp();
+                uint32_t Rtot = 0;
+                if (lane == 0) {
+                    uint32_t acc = 0;
+                    for (int w = 0; w < P; w++) { S.rowbase[w] = (uint16_t)min(acc, 65535u); acc += S.n1[w]; }
+                    S.rowbase[P] = (uint16_t)min(acc, 65535u);
+                    Rtot = acc;
+                }
+                Rtot = __shfl_sync(0xffffffffu, Rtot, 0);
+                if (Rtot > 65535u) { why = ST_CAPACITY; reason = 2; }
+                __syncwarp();
+                // runs: maximal stretches of outer neighbours with equal score (hence equal inner count)
+                for (uint32_t g0 = 0; g0 < Rtot && why == ST_OK; g0 += 32) {
+                    const uint32_t g = g0 + lane;
+                    bool boundary = false;
+                    uint32_t a = 0, w = 0, n2 = 0;
+                    if (g < Rtot) {
+                        int lo = 0, hi = P - 1;   // largest w with rowbase[w] <= g
+                        while (lo < hi) {
+                            const int mid = (lo + hi + 1) >> 1;
+                            if ((uint32_t)S.rowbase[mid] <= g) lo = mid; else hi = mid - 1;
+                        }
+                        w = (uint32_t)lo;
+                        a = g - (uint32_t)S.rowbase[w];
+                        const uint32_t *r1 = A.row3 + (size_t)S.x1[w] * SPB_N3;
+                        const int s1 = (int)(__ldg(r1 + a) >> 16) - SPB_SCORE_OFF;
+                        boundary = (a == 0) || ((int)(__ldg(r1 + a - 1) >> 16) - SPB_SCORE_OFF != s1);
+                        if (boundary) {
+                            const int cut2 = (int)S.thr[w] - s1;
+                            if (cut2 <= SPB_CNT3_W - SPB_SCORE_OFF - 1)
+                                n2 = (uint32_t)__ldg(A.cnt3 + (size_t)S.x2[w] * SPB_CNT3_W + max(cut2, -SPB_SCORE_OFF) + SPB_SCORE_OFF);
+                        }
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, boundary);
+                    const int dst = nRuns + __popc(m & lt);
+                    if (boundary && dst < PW_RUNCAP) {
+                        Run r;
+                        r.a0 = (uint16_t)a; r.n2 = (uint16_t)n2; r.cum = (uint16_t)g; r.w = (uint16_t)w;
+                        runs[dst] = r;
+                    }
+                    nRuns += __popc(m);
+                    if (nRuns > PW_RUNCAP) { why = ST_CAPACITY; reason = 3; }
+                }
+                __syncwarp();
+                // first k of every run: exclusive prefix of (rows in the run) x (inner count)
+                for (int c0 = 0; c0 < nRuns && why == ST_OK; c0 += 32) {
+                    const int i = c0 + lane;
+                    uint32_t cntK = 0;
+                    if (i < nRuns) {
+                        const uint32_t gThis = runs[i].cum;
+                        const uint32_t gNext = (i + 1 < nRuns) ? (uint32_t)runs[i + 1].cum : Rtot;
+                        cntK = (gNext - gThis) * (uint32_t)runs[i].n2;
+                    }
+                    const uint32_t inc = (uint32_t)warp_incl_scan((int)cntK);
+                    const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+                    __syncwarp();
+                    if (K + tot > 65535u) { why = ST_CAPACITY; reason = 4; break; }
+                    if (i < nRuns) runs[i].cum = (uint16_t)(K + inc - cntK);
+                    K += tot;
+                    __syncwarp();
+                }
+                if (SOLO && why == ST_OK && K > A.kCapSolo) why = ST_TEAM;
+            }
+            if (lane == 0) { S.v_K = K; S.v_nRuns = (uint32_t)nRuns; S.v_slow = why; S.v_why = reason; S.v_minCorr = minCorr; }
+        }
+        team_sync();
+        const uint32_t K = S.v_K;
+        const int nRuns = (int)S.v_nRuns;
+        // ---------------- one pass over the hit stream ----------------
+        if (S.v_slow == ST_OK) {
+            for (uint32_t k0 = (uint32_t)tw * (32 * PW_U); k0 < K; k0 += TEAM * 32 * PW_U) {
+                uint64_t d[PW_U];
+                uint32_t ww[PW_U];
+#pragma unroll
+                for (int u = 0; u < PW_U; u++) {
+                    const uint32_t k = k0 + (uint32_t)(u * 32 + lane);
+                    d[u] = 0;
+                    ww[u] = 0;
+                    if (k < K) {
+                        int lo = 0, hi = nRuns - 1;   // largest r with runs[r].cum <= k
+                        while (lo < hi) {
+                            const int mid = (lo + hi + 1) >> 1;
+                            if ((uint32_t)runs[mid].cum <= k) lo = mid; else hi = mid - 1;
+                        }
+                        const Run r = runs[lo];
+                        const uint32_t rel = k - (uint32_t)r.cum;
+                        const uint32_t da = rel / (uint32_t)r.n2;
+                        const uint32_t b = rel - da * (uint32_t)r.n2;
+                        const uint32_t i1 = __ldg(A.row3 + (size_t)S.x1[r.w] * SPB_N3 + (uint32_t)r.a0 + da) & 0xFFFFu;
+                        const uint32_t i2 = __ldg(A.row3 + (size_t)S.x2[r.w] * SPB_N3 + b) & 0xFFFFu;
+                        ww[u] = r.w;
+                        d[u] = __ldg(A.direct + (i1 + 8000u * i2));
+                    }
+                }
+                // hit records: warp-aggregated append to the team's scratch slice + seen-once / seen-twice bitmaps
+                auto emit = [&](bool have, uint64_t pe, uint32_t k, uint32_t w) {
+                    const unsigned m = __ballot_sync(0xffffffffu, have);
+                    if (m == 0) return;
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&S.v_nHits, (uint32_t)__popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (have) {
+                        const uint32_t id = (uint32_t)(pe >> 16);
+                        const uint32_t dg = (w - (uint32_t)(pe & 0xFFFFull)) & 0xFFFFu;
+                        const uint32_t dst = base + (uint32_t)__popc(m & lt);
+                        if (dst < HCAP) __stcg(scratch + dst, ((uint64_t)id << 32) | ((uint64_t)k << 16) | dg);
+                        const uint32_t h = (id * 2654435761u) >> (SOLO ? 19 : 17);
+                        const uint32_t bm = 1u << (h & 31);
+                        const uint32_t old = atomicOr(&S.seen1[h >> 5], bm);
+                        if ((old & bm) || (dg & 0xFFu) == 0u) atomicOr(&S.seen2[h >> 5], bm);
+                    }
+                };
+#pragma unroll
+                for (int u = 0; u < PW_U; u++) {
+                    const uint64_t dv = d[u];
+                    const uint32_t kb = k0 + (uint32_t)(u * 32);
+                    const bool single = (dv >> 63) != 0;
+                    // k-mers of exactly one target carry their posting inline
+                    emit(single, dv & 0x0000FFFFFFFFFFFFull, kb + lane, ww[u]);
+                    // posting lists of the other k-mers, flattened over the warp: element p of the concatenated lists
+                    // belongs to the last lane whose exclusive prefix is <= p (coalesced reads, no per-lane walks)
+                    const uint32_t len = single ? 0u : (uint32_t)(dv >> 32);
+                    const uint32_t off = (uint32_t)dv;
+                    const uint32_t inc = (uint32_t)warp_incl_scan((int)len);
+                    const uint32_t excl = inc - len;
+                    const uint32_t T = __shfl_sync(0xffffffffu, inc, 31);
+                    for (uint32_t p0 = 0; p0 < T; p0 += 32) {
+                        const uint32_t pp = p0 + lane;
+                        int j = 0;
+#pragma unroll
+                        for (int step = 16; step > 0; step >>= 1) {
+                            const int cand = j + step;
+                            const uint32_t e = __shfl_sync(0xffffffffu, excl, cand & 31);
+                            if (cand < 32 && e <= pp) j = cand;
+                        }
+                        const uint32_t srcOff = __shfl_sync(0xffffffffu, off, j);
+                        const uint32_t srcEx = __shfl_sync(0xffffffffu, excl, j);
+                        const uint32_t srcW = __shfl_sync(0xffffffffu, ww[u], j);
+                        const bool have = pp < T;
+                        uint64_t pe = 0;
+                        if (have) pe = __ldg(A.post + srcOff + (pp - srcEx));
+                        emit(have, pe, kb + (uint32_t)j, srcW);
+                    }
+                }
+            }
+        }
+        team_sync();
+        const uint32_t nHits = S.v_nHits;
+        const bool live = (S.v_slow == ST_OK) && nHits <= HCAP;
+        team_sync();
+        if (S.v_slow == ST_OK && nHits > HCAP && tw == 0 && lane == 0) { S.v_slow = ST_CAPACITY; S.v_why = 5; }
+        // ---------------- survivors: records of targets seen twice (or with 8-bit diagonal 0) ----------------
+        // Pass A counts them per hash bucket (64 buckets of targets) and -- TEAM = 1 -- collects them optimistically into the
+        // warp's sort buffer.  If they do not fit one sort, pass B scatters them bucket by bucket behind the hit records and the
+        // buckets are merged into G contiguous groups of at most PW_SCAP records, each processed independently by one warp.
+        uint32_t *const cnt64 = S.seen1;            // dead after the gather: [0,64) counts, [64,128) starts, [128,192) fill cursors
+        if (live) for (int i = tw * 32 + lane; i < 192; i += TEAM * 32) cnt64[i] = 0;
+        team_sync();
+        int nS0 = 0;
+        if (live) {
+            for (uint32_t i0 = (uint32_t)tw * 128; i0 < nHits; i0 += TEAM * 128) {
+                uint64_t r[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = i0 + (uint32_t)(u * 32 + lane);
+                    r[u] = (i < nHits) ? __ldcg(scratch + i) : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = i0 + (uint32_t)(u * 32 + lane);
+                    const uint32_t id = (uint32_t)(r[u] >> 32);
+                    const uint32_t h = (id * 2654435761u) >> (SOLO ? 19 : 17);
+                    const bool keep = (i < nHits) && ((S.seen2[h >> 5] >> (h & 31)) & 1u);
+                    if (keep) atomicAdd(&cnt64[(id * 0x85EBCA6Bu) >> 26], 1u);
+                    if (SOLO) {
+                        const unsigned m = __ballot_sync(0xffffffffu, keep);
+                        const int dst = nS0 + __popc(m & lt);
+                        if (keep && dst < PW_SCAP) W.surv[dst] = r[u];
+                        nS0 += __popc(m);
+                    }
+                }
+            }
+        }
+        team_sync();
+        // group count: the smallest power of two whose merged buckets all fit one sort (every warp computes the same)
+        uint32_t nSurv = 0, G = 1;
+        if (live) {
+            const uint32_t c0 = cnt64[2 * lane], c1 = cnt64[2 * lane + 1];
+            uint32_t mx[7];     // mx[l]: largest merged bucket when 64 >> l groups are used
+            uint32_t sum = c0 + c1;
+            mx[0] = max(c0, c1);
+#pragma unroll
+            for (int l = 1; l < 7; l++) {
+                if (l > 1) sum += __shfl_xor_sync(0xffffffffu, sum, 1 << (l - 2));
+                mx[l] = sum;
+            }
+#pragma unroll
+            for (int l = 0; l < 7; l++)
+                for (int d = 16; d > 0; d >>= 1) mx[l] = max(mx[l], __shfl_xor_sync(0xffffffffu, mx[l], d));
+            nSurv = mx[6];
+            int lvl = 6;
+#pragma unroll
+            for (int l = 5; l >= 0; l--) if (mx[lvl] > PW_SCAP) lvl = l;
+            G = 64u >> lvl;
+            if (mx[lvl] > PW_SCAP && tw == 0 && lane == 0) { S.v_slow = ST_CAPACITY; S.v_why = 6; }   // one bucket alone overflows a sort
+            if (tw == 0) {   // bucket starts
+                uint32_t e0 = (uint32_t)warp_incl_scan((int)(c0 + c1)) - (c0 + c1);
+                cnt64[64 + 2 * lane] = e0;
+                cnt64[64 + 2 * lane + 1] = e0 + c0;
+            }
+        }
+        team_sync();
+        const bool scatter = live && (S.v_slow == ST_OK) && (!SOLO || G > 1);
+        uint64_t *const grouped = scratch + HCAP;
+        if (scatter) {
+            for (uint32_t i0 = (uint32_t)tw * 128; i0 < nHits; i0 += TEAM * 128) {
+                uint64_t r[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = i0 + (uint32_t)(u * 32 + lane);
+                    r[u] = (i < nHits) ? __ldcg(scratch + i) : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = i0 + (uint32_t)(u * 32 + lane);
+                    const uint32_t id = (uint32_t)(r[u] >> 32);
+                    const uint32_t h = (id * 2654435761u) >> (SOLO ? 19 : 17);
+                    if ((i < nHits) && ((S.seen2[h >> 5] >> (h & 31)) & 1u)) {
+                        const uint32_t bk = (id * 0x85EBCA6Bu) >> 26;
+                        __stcg(grouped + cnt64[64 + bk] + atomicAdd(&cnt64[128 + bk], 1u), r[u]);
+                    }
+                }
+            }
+        }
+        team_sync();
+        const int minCorr = S.v_minCorr;
+        const int ungBias = abs(A.minSubUngapped) + abs(min(minCorr, 0));
+        const int capScore = 255 - ungBias;
+        unsigned long long evAcc = 0;
+        if (live && S.v_slow == ST_OK) {
+            for (uint32_t g = (uint32_t)tw; g < G; g += TEAM) {
+                // ---- the group's records ----
+                int nS = nS0;
+                if (scatter) {
+                    const uint32_t per = 64u / G;
+                    const uint32_t lo = cnt64[64 + g * per];
+                    const uint32_t hi = ((g + 1) * per >= 64u) ? nSurv : cnt64[64 + (g + 1) * per];
+                    nS = (int)(hi - lo);
+                    for (int i = lane; i < nS; i += 32) W.surv[i] = __ldcg(grouped + lo + i);
+                }
+                // ---- sort by (target, stream order) ----
+                {
+                    const int np2 = next_pow2(max(nS, 2));
+                    for (int i = nS + lane; i < np2; i += 32) W.surv[i] = ~0ull;
+                    warp_bitonic_u64(W.surv, np2);
+                }
+                // ---- double-hit events, then de-duplication of consecutive equal events ----
+                int nkept = nS;
+                for (int pass = 0; pass < 2; pass++) {
+                    int outN = 0;
+                    uint64_t carryR = 0;
+                    for (int c0 = 0; c0 < nkept; c0 += 32) {
+                        const int i = c0 + lane;
+                        uint64_t r = 0;
+                        if (i < nkept) r = W.surv[i];
+                        uint64_t rp = __shfl_up_sync(0xffffffffu, r, 1);
+                        if (lane == 0) rp = carryR;
+                        bool keep = false;
+                        if (i < nkept) {
+                            const bool same = (i > 0) && ((uint32_t)(rp >> 32) == (uint32_t)(r >> 32));
+                            const bool eq8 = (((uint32_t)r ^ (uint32_t)rp) & 0xFFu) == 0u;
+                            keep = (pass == 0) ? (same ? eq8 : (((uint32_t)r & 0xFFu) == 0u)) : (!same || !eq8);
+                        }
+                        carryR = __shfl_sync(0xffffffffu, r, 31);
+                        const unsigned m = __ballot_sync(0xffffffffu, keep);
+                        __syncwarp();
+                        if (keep) W.surv[outN + __popc(m & lt)] = r;
+                        outN += __popc(m);
+                        __syncwarp();
+                    }
+                    nkept = outN;
+                }
+                evAcc += (unsigned long long)nkept;
+                // ---- ungapped diagonal scores; per target the first event reaching the target's maximum ----
+                for (int i = lane; i < nkept; i += 32) {
+                    const uint64_t r = W.surv[i];
+                    const int sc = ungapped_u16(A.tres, A.toff, (uint32_t)(r >> 32), S.q, L, S.corr, s_m40u, (uint32_t)r & 0xFFFFu);
+                    W.cnt[i] = (uint8_t)min(sc, capScore);
+                }
+                __syncwarp();
+                for (int c0 = 0; c0 < nkept; c0 += 32) {
+                    const int i = c0 + lane;
+                    bool keep = false;
+                    uint64_t f = 0, t = 0;
+                    if (i < nkept) {
+                        const uint64_t r0 = W.surv[i];
+                        const uint32_t id = (uint32_t)(r0 >> 32);
+                        const bool head = (i == 0) || ((uint32_t)(W.surv[i - 1] >> 32) != id);
+                        if (head) {
+                            int bi = i;
+                            uint8_t best = W.cnt[i];
+                            for (int j = i + 1; j < nkept && (uint32_t)(W.surv[j] >> 32) == id; j++)
+                                if (W.cnt[j] > best) { best = W.cnt[j]; bi = j; }
+                            if ((int)best >= A.minDiag) {
+                                keep = true;
+                                const uint32_t dg = (uint32_t)W.surv[bi] & 0xFFFFu;
+                                int sc = best;     // saturated counters get their exact score (getResult, QueryMatcher.cpp:371-374)
+                                if (sc >= capScore) sc = ungapped_u16(A.tres, A.toff, id, S.q, L, S.corr, s_m40u, dg);
+                                f = ((uint64_t)(0xFFFFu - (uint32_t)min(sc, 0xFFFF)) << 48) | ((uint64_t)id << 16) | dg;
+                                // truncation order of the reference's stable counting sorts: capped score desc, bin, stream order, id
+                                const uint32_t kk = (uint32_t)(W.surv[bi] >> 16) & 0xFFFFu;
+                                t = ((uint64_t)(255u - best) << 55) | ((uint64_t)((id + A.idBase) & A.binMask) << 44) | ((uint64_t)kk << 28) | id;
+                            }
+                        }
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, keep);
+                    if (m) {
+                        uint32_t base = 0;
+                        if (lane == 0) base = atomicAdd(&S.v_nFin, (uint32_t)__popc(m));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        const uint32_t dst = base + (uint32_t)__popc(m & lt);
+                        if (keep && dst < FCAP) { __stcg(finList + 2 * dst, f); __stcg(finList + 2 * dst + 1, t); }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        team_sync();
+        // ---------------- final order (score desc, id asc), output ----------------
+        if (SOLO) {
+            const uint32_t nc = S.v_nFin;
+            uint32_t why = S.v_slow;
+            uint32_t reason = S.v_why;
+            // truncation at max-seqs (and anything beyond one warp sort) is finished by the 8-warp team launch
+            if (why == ST_OK && (nc >= (uint32_t)A.maxHits || nc > PW_SCAP)) why = ST_TEAM;
+            if (why != ST_OK) {
+                if (lane == 0) { A.outStart[qi] = 0; A.outCount[qi] = 0; A.status[qi] = why; A.need[qi] = reason; }
+            } else {
+                statK += K;
+                statM += nHits;
+                statS += nSurv;
+                const int np2 = next_pow2(max((int)nc, 2));
+                for (int k = lane; k < np2; k += 32) W.surv[k] = (k < (int)nc) ? __ldcg(finList + 2 * k) : ~0ull;
+                warp_bitonic_u64(W.surv, np2);
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(A.cursor, (unsigned long long)nc);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base + (unsigned long long)nc > A.arenaCap) {
+                    if (lane == 0) { A.outStart[qi] = 0; A.outCount[qi] = 0; A.status[qi] = ST_ARENA; }
+                } else {
+                    for (int k = lane; k < (int)nc; k += 32) {
+                        const uint64_t f = W.surv[k];
+                        spb_hit h;
+                        h.id = (uint32_t)(f >> 16);
+                        h.score = (int32_t)(0xFFFFu - (uint32_t)(f >> 48));
+                        h.diag = (int32_t)(short)(uint16_t)(f & 0xFFFFull);
+                        A.arena[base + k] = h;
+                    }
+                    if (lane == 0) { A.outStart[qi] = base; A.outCount[qi] = nc; A.status[qi] = ST_OK; }
+                }
+            }
+        } else {
+            // whole CTA.  QueryMatcher.cpp:131-164: with >= max-seqs candidates the score histogram fixes the cut score; above
+            // max-seqs the candidates are taken in the order of the reference's stable counting sorts (truncation key).
+            uint64_t *const bigK = s_big, *const bigV = s_big + PW_BIG;
+            uint32_t *const hist = S.seen2;       // dead after the survivor passes
+            const uint32_t nc = S.v_nFin;
+            const uint32_t maxHits = (uint32_t)A.maxHits;
+            const int tid = threadIdx.x;
+            if (tid == 0) {
+                S.v_nSurv = 0;                    // reused: selected candidates
+                if (S.v_slow == ST_OK && nc > FCAP) { S.v_slow = ST_CAPACITY; S.v_why = 7; }
+            }
+            for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+            __syncthreads();
+            const bool ok0 = (S.v_slow == ST_OK);
+            const bool trunc = ok0 && nc >= maxHits;
+            if (trunc) {
+                for (uint32_t k = tid; k < nc; k += blockDim.x) atomicAdd(&hist[255u - (uint32_t)(__ldcg(finList + 2 * k + 1) >> 55)], 1u);
+                __syncthreads();
+                if (tid == 0) {     // computeScoreThreshold (QueryMatcher.h:199-209)
+                    uint32_t found = 0, thr = 0;
+                    for (int sc = 255; sc >= 1; sc--) {
+                        found += hist[sc];
+                        if (found >= maxHits) { thr = (uint32_t)sc; break; }
+                    }
+                    const uint32_t thrD = max(thr, (uint32_t)A.minDiag);
+                    S.v_nRuns = thrD;             // reused: cut score
+                    // all remaining candidates saturated -> rescoreHits (QueryMatcher.cpp:486-505) lives in prefilter_kernel
+                    if ((int)thrD >= capScore) { S.v_slow = ST_CAPACITY; S.v_why = 8; }
+                }
+                __syncthreads();
+            }
+            const bool ok1 = (S.v_slow == ST_OK);
+            uint32_t ns = nc;                     // rows to output
+            if (ok1) {
+                if (nc > maxHits) {
+                    const uint32_t thrD = S.v_nRuns;
+                    for (uint32_t k = tid; k < nc; k += blockDim.x) {
+                        const uint64_t t = __ldcg(finList + 2 * k + 1);
+                        if (255u - (uint32_t)(t >> 55) >= thrD) {
+                            const uint32_t dst = atomicAdd(&S.v_nSurv, 1u);
+                            if (dst < PW_BIG) { bigK[dst] = t; bigV[dst] = __ldcg(finList + 2 * k); }
+                        }
+                    }
+                    __syncthreads();
+                    const uint32_t nSel = S.v_nSurv;
+                    if (nSel > PW_BIG) {
+                        if (tid == 0) { S.v_slow = ST_CAPACITY; S.v_why = 7; }
+                    } else {
+                        const int np2 = next_pow2(max((int)nSel, 2));
+                        for (int i = (int)nSel + tid; i < np2; i += blockDim.x) { bigK[i] = ~0ull; bigV[i] = ~0ull; }
+                        block_bitonic_pairs(bigK, bigV, np2);
+                        ns = maxHits;
+                        const int nq2 = next_pow2(max((int)ns, 2));
+                        for (int i = tid; i < nq2; i += blockDim.x) bigK[i] = (i < (int)ns) ? bigV[i] : ~0ull;
+                        block_bitonic_sort(bigK, nq2, [](uint64_t x, uint64_t y) { return x < y; });
+                    }
+                } else if (nc > PW_BIG) {
+                    if (tid == 0) { S.v_slow = ST_CAPACITY; S.v_why = 7; }
+                } else {
+                    const int np2 = next_pow2(max((int)nc, 2));
+                    for (int i = tid; i < np2; i += blockDim.x) bigK[i] = (i < (int)nc) ? __ldcg(finList + 2 * i) : ~0ull;
+                    block_bitonic_sort(bigK, np2, [](uint64_t x, uint64_t y) { return x < y; });
+                }
+            }
+            __syncthreads();
+            if (S.v_slow != ST_OK) {
+                if (tid == 0) { A.outStart[qi] = 0; A.outCount[qi] = 0; A.status[qi] = S.v_slow; A.need[qi] = S.v_why; }
+            } else {
+                if (tid == 0) s_base = atomicAdd(A.cursor, (unsigned long long)ns);
+                __syncthreads();
+                const unsigned long long base = s_base;
+                if (base + (unsigned long long)ns > A.arenaCap) {
+                    if (tid == 0) { A.outStart[qi] = 0; A.outCount[qi] = 0; A.status[qi] = ST_ARENA; }
+                } else {
+                    for (uint32_t k = tid; k < ns; k += blockDim.x) {
+                        const uint64_t f = bigK[k];
+                        spb_hit h;
+                        h.id = (uint32_t)(f >> 16);
+                        h.score = (int32_t)(0xFFFFu - (uint32_t)(f >> 48));
+                        h.diag = (int32_t)(short)(uint16_t)(f & 0xFFFFull);
+                        A.arena[base + k] = h;
+                    }
+                    if (tid == 0) {
+                        A.outStart[qi] = base; A.outCount[qi] = ns; A.status[qi] = ST_OK;
+                        statK += K;
+                        statM += nHits;
+                        statS += nSurv;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (tw == 0 && lane == 0) S.v_slow = (A.status[qi] == ST_OK) ? ST_OK : ST_CAPACITY;
+        team_sync();
+        if (S.v_slow == ST_OK) statE += evAcc;     // events of the groups this warp processed
+    }
+    // counters of the queries finished on this path (the others are counted by the kernel that finishes them)
+    if (lane == 0) {
+        if (statK) atomicAdd(A.cursor + 1, statK);
+        if (statM) atomicAdd(A.cursor + 2, statM);
+        if (statE) atomicAdd(A.cursor + 3, statE);
+        if (statS) atomicAdd(A.cursor + 4, statS);
+    }
+}
+
 // gather per-query slices of the arena into query order
 __global__ void gather_hits_kernel(const spb_hit *__restrict__ arena, const uint64_t *__restrict__ start, const uint64_t *__restrict__ outOff,
                                    uint32_t Q, spb_hit *__restrict__ out) {
@@ -572,19 +1243,20 @@ __global__ void count_to_u64_kernel(const uint32_t *__restrict__ cnt, uint32_t Q
 
 // status scan: list of queries needing the global-memory variant, max need, error flags
 __global__ void status_scan_kernel(const uint32_t *__restrict__ status, const uint32_t *__restrict__ need, uint32_t Q,
-                                   uint32_t *__restrict__ list, unsigned int *__restrict__ ctr) {
-    // ctr: [0] nSlow, [1] maxNeed, [2] arena overflow, [3] layout error (query index + 1), [4] unprocessed
+                                   uint32_t *__restrict__ list, unsigned int *__restrict__ ctr, uint32_t listStatus) {
+    // ctr: [0] entries of `list` (queries whose status is listStatus), [1] maxNeed, [2] arena overflow,
+    //      [3] layout error (query index + 1), [4] unprocessed
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Q) return;
     const uint32_t s = status[i];
-    if (s == ST_CAPACITY) {
+    if (s == listStatus) {
         list[atomicAdd(&ctr[0], 1u)] = i;
         atomicMax(&ctr[1], need[i]);
     } else if (s == ST_ARENA) {
         atomicOr(&ctr[2], 1u);
     } else if (s == ST_LAYOUT) {
         atomicMax(&ctr[3], i + 1);
-    } else if (s != ST_OK) {
+    } else if (s != ST_OK && !(listStatus == ST_TEAM && s == ST_CAPACITY)) {
         atomicMax(&ctr[4], i + 1);
     }
 }
@@ -716,11 +1388,12 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
 
     // scratch: s_a start u64[Q], s_b count u32[Q], s_c status u32[Q], s_d need u32[Q], s_e slow list u32[Q], s_f counters, s_g arena
     if (c->s_a.ensure((size_t)Q * 8) || c->s_b.ensure((size_t)Q * 4) || c->s_c.ensure((size_t)Q * 4) || c->s_d.ensure((size_t)Q * 4) ||
-        c->s_e.ensure((size_t)Q * 4) || c->s_f.ensure(128)) return 1;
+        c->s_e.ensure((size_t)Q * 4) || c->s_f.ensure(512)) return 1;
     uint64_t arenaCap = std::min<uint64_t>((uint64_t)Q * (uint64_t)A.maxHits, std::max<uint64_t>((uint64_t)Q * 24, 1u << 20));
     float kernelMs = 0;
     uint64_t nSlow = 0;
-    unsigned long long h_cursor[8];
+    unsigned long long h_cursor[24];
+    unsigned int dbgWhy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     unsigned int h_ctr[8];
     SPB_CUDA(cudaEventRecord(c->ev2, st));
     for (int attempt = 0;; attempt++) {
@@ -736,14 +1409,41 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
         A.gScratch = nullptr;
         A.cap = PF_SMEM_CAP;
         unsigned int *d_ctr = reinterpret_cast<unsigned int *>(c->s_f.as<unsigned long long>() + 8);
-        SPB_CUDA(cudaMemsetAsync(c->s_f.p, 0, 128, st));
+        SPB_CUDA(cudaMemsetAsync(c->s_f.p, 0, 512, st));
         SPB_CUDA(cudaMemsetAsync(c->s_c.p, 0xFF, (size_t)Q * 4, st));
         const size_t smem = (size_t)PF_SMEM_CAP * sizeof(Rec);
+        // stage 1: team kernels.  TEAM = 1 over the whole batch (persistent grid, dynamic query scheduler); the queries it
+        // flags ST_TEAM (long similar-k-mer lists) are listed on the device and taken by the TEAM = 8 launch, which reads
+        // the list length from device memory -- no host round trip in between.
+        const int soloBlocks = c->n_sm * 8, teamBlocks = c->n_sm * 4;
+        A.direct = c->d_direct.as<uint64_t>();
+        const uint32_t hitCapSolo = 8192, hitCapTeam = 32768;
+        A.kCapSolo = 4096;
+        const size_t sliceSolo = 2 * (size_t)hitCapSolo + 2 * PW_FCAP_SOLO, sliceTeam = 2 * (size_t)hitCapTeam + 2 * PW_FCAP_TEAM;
+        if (c->s_j.ensure(std::max((size_t)soloBlocks * PW_WARPS * sliceSolo, (size_t)teamBlocks * sliceTeam) * sizeof(uint64_t)) ||
+            c->s_k.ensure((size_t)Q * 4 + 64)) return 1;
+        A.hitCap = hitCapSolo;
+        A.hitScratch = c->s_j.as<uint64_t>();
+        unsigned int *d_qc = reinterpret_cast<unsigned int *>(c->s_f.as<unsigned long long>() + 14);   // [0] solo, [1] team scheduler
+        unsigned int *d_ctrT = reinterpret_cast<unsigned int *>(c->s_f.as<unsigned long long>() + 24); // counters of the ST_TEAM scan
+        A.qCounter = d_qc;
+        A.qlist = nullptr;
+        A.nListPtr = nullptr;
         SPB_CUDA(cudaEventRecord(c->ev0, st));
-        prefilter_kernel<false><<<Q, PF_THREADS, smem, st>>>(A);
+        prefilter_team_kernel<1><<<soloBlocks, PW_WARPS * 32, 0, st>>>(A);
         SPB_CUDA(cudaGetLastError()); c->n_launches++;
+        status_scan_kernel<<<(Q + 255) / 256, 256, 0, st>>>(A.status, A.need, Q, c->s_k.as<uint32_t>(), d_ctrT, ST_TEAM);
+        SPB_CUDA(cudaGetLastError()); c->n_launches++;
+        A.qCounter = d_qc + 1;
+        A.qlist = c->s_k.as<uint32_t>();
+        A.nListPtr = d_ctrT;
+        A.hitCap = hitCapTeam;
+        prefilter_team_kernel<PW_TEAM><<<teamBlocks, PW_TEAM * 32, 0, st>>>(A);
+        SPB_CUDA(cudaGetLastError()); c->n_launches++;
+        A.qlist = nullptr;
+        A.nListPtr = nullptr;
         SPB_CUDA(cudaEventRecord(c->ev1, st));
-        status_scan_kernel<<<(Q + 255) / 256, 256, 0, st>>>(A.status, A.need, Q, c->s_e.as<uint32_t>(), d_ctr);
+        status_scan_kernel<<<(Q + 255) / 256, 256, 0, st>>>(A.status, A.need, Q, c->s_e.as<uint32_t>(), d_ctr, ST_CAPACITY);
         SPB_CUDA(cudaGetLastError()); c->n_launches++;
         SPB_CUDA(cudaMemcpyAsync(h_ctr, d_ctr, 32, cudaMemcpyDeviceToHost, st));
         SPB_CUDA(cudaStreamSynchronize(st));
@@ -753,9 +1453,39 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
         SPB_CHECK(h_ctr[3] == 0, "spb_prefilter: query %u is longer than the supported %d residues", h_ctr[3] - 1, PF_MAXL);
         SPB_CHECK(h_ctr[4] == 0, "spb_prefilter: query %u was not processed", h_ctr[4] - 1);
         bool arenaOverflow = h_ctr[2] != 0;
-        // queries whose kept-hit list does not fit shared memory run again on global-memory scratch
-        uint32_t nList = h_ctr[0], maxNeed = h_ctr[1], capG = 2048;
+        uint32_t nList = h_ctr[0], maxNeed = 0, capG = 2048;
         nSlow = nList;
+        if (getenv("SPB_DEBUG") && nList) {
+            std::vector<uint32_t> hl(nList), hn(Q);
+            cudaMemcpy(hl.data(), c->s_e.p, (size_t)nList * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(hn.data(), A.need, (size_t)Q * 4, cudaMemcpyDeviceToHost);
+            memset(dbgWhy, 0, sizeof(dbgWhy));
+            for (uint32_t i = 0; i < nList; i++) dbgWhy[std::min<uint32_t>(hn[hl[i]], 7)]++;
+        }
+        // stage 2: queries the warp kernel handed over (long, many hits, truncation at max-seqs): one CTA each,
+        // records in shared memory
+        if (nList && !arenaOverflow) {
+            if (c->s_i.ensure((size_t)Q * 4)) return 1;
+            SPB_CUDA(cudaEventRecord(c->ev0, st));
+            A.qlist = c->s_e.as<uint32_t>();
+            prefilter_kernel<false><<<nList, PF_THREADS, smem, st>>>(A);
+            SPB_CUDA(cudaGetLastError()); c->n_launches++;
+            SPB_CUDA(cudaEventRecord(c->ev1, st));
+            SPB_CUDA(cudaMemsetAsync(d_ctr, 0, 32, st));
+            status_scan_kernel<<<(Q + 255) / 256, 256, 0, st>>>(A.status, A.need, Q, c->s_i.as<uint32_t>(), d_ctr, ST_CAPACITY);
+            SPB_CUDA(cudaGetLastError()); c->n_launches++;
+            SPB_CUDA(cudaMemcpyAsync(h_ctr, d_ctr, 32, cudaMemcpyDeviceToHost, st));
+            SPB_CUDA(cudaStreamSynchronize(st));
+            SPB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+            kernelMs += ms;
+            SPB_CHECK(h_ctr[3] == 0, "spb_prefilter: query %u is longer than the supported %d residues", h_ctr[3] - 1, PF_MAXL);
+            SPB_CHECK(h_ctr[4] == 0, "spb_prefilter: query %u was not processed", h_ctr[4] - 1);
+            arenaOverflow = h_ctr[2] != 0;
+            nList = h_ctr[0];
+            maxNeed = h_ctr[1];
+            if (nList) SPB_CUDA(cudaMemcpyAsync(c->s_e.p, c->s_i.p, (size_t)nList * 4, cudaMemcpyDeviceToDevice, st));
+        }
+        // stage 3: queries whose kept-hit list does not fit shared memory run again on global-memory scratch
         while (nList && !arenaOverflow) {
             while (capG < maxNeed) capG <<= 1;
             SPB_CHECK(capG <= (1u << 28), "spb_prefilter: hit list of a query exceeds 2^28 records");
@@ -774,7 +1504,7 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
             // which of them still need more room (their status stays ST_CAPACITY)?
             if (c->s_i.ensure((size_t)Q * 4)) return 1;
             SPB_CUDA(cudaMemsetAsync(d_ctr, 0, 32, st));
-            status_scan_kernel<<<(Q + 255) / 256, 256, 0, st>>>(A.status, A.need, Q, c->s_i.as<uint32_t>(), d_ctr);
+            status_scan_kernel<<<(Q + 255) / 256, 256, 0, st>>>(A.status, A.need, Q, c->s_i.as<uint32_t>(), d_ctr, ST_CAPACITY);
             SPB_CUDA(cudaGetLastError()); c->n_launches++;
             SPB_CUDA(cudaMemcpyAsync(h_ctr, d_ctr, 32, cudaMemcpyDeviceToHost, st));
             SPB_CUDA(cudaStreamSynchronize(st));
@@ -792,7 +1522,7 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
         SPB_CHECK(arenaCap < (uint64_t)Q * (uint64_t)A.maxHits && attempt < 8, "spb_prefilter: result arena overflow could not be resolved");
         arenaCap = std::min<uint64_t>((uint64_t)Q * (uint64_t)A.maxHits, arenaCap * 4);
     }
-    SPB_CUDA(cudaMemcpyAsync(h_cursor, c->s_f.p, 64, cudaMemcpyDeviceToHost, st));
+    SPB_CUDA(cudaMemcpyAsync(h_cursor, c->s_f.p, 192, cudaMemcpyDeviceToHost, st));
 
     // ---- compact the arena into query order: offsets = exclusive scan of the counts
     if (c->s_i.ensure(((size_t)Q + 1) * 8)) return 1;
@@ -816,6 +1546,13 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
     float totalMs = 0;
     SPB_CUDA(cudaEventElapsedTime(&totalMs, c->ev2, c->ev3));
     c->n_hits = nHits;
+    if (getenv("SPB_DEBUG")) {
+        unsigned int nTeam = 0;
+        cudaMemcpy(&nTeam, reinterpret_cast<unsigned int *>(c->s_f.as<unsigned long long>() + 24), 4, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "spb_prefilter: %u queries, %u taken by the 8-warp team launch, %llu handed to the CTA kernel "
+                "(long query %u, rows %u, runs %u, k-mers %u, hits %u, bucket %u, max-seqs %u)\n", Q, nTeam,
+                (unsigned long long)nSlow, dbgWhy[1], dbgWhy[2], dbgWhy[3], dbgWhy[4], dbgWhy[5], dbgWhy[6], dbgWhy[7]);
+    }
     spb_prefilter_result &R = c->pref_stats;
     R.n_hits = nHits;
     R.n_kmers = h_cursor[1];
