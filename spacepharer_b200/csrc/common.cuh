@@ -118,6 +118,7 @@ struct spb_ctx {
     spb::DevBuf d_q;              // u8[q_res]
     spb::DevBuf d_qoff;           // u32[Q+1]
     spb::DevBuf d_qoff64;         // u64[Q+1]
+    spb::DevBuf d_qorder;         // u32[Q] prefilter processing order (longest first)
 
     // ---- resident prefilter result (query order) ----
     bool have_pref = false;

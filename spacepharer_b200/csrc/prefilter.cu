@@ -74,7 +74,8 @@ struct PrefArgs {
     uint64_t *hitScratch;    // [warps in the grid][hitCap] hit records, L2-resident
     uint32_t hitCap;
     unsigned int *qCounter;  // dynamic query scheduler
-    const unsigned int *nListPtr;  // device: entries of qlist (team launch reads it, no host round trip)
+    const unsigned int *nListPtr;  // device: entries of qlist (team launch reads it, no host round trip); NULL: nList
+    uint32_t nList;
     uint32_t kCapSolo;       // TEAM = 1: queries with more similar k-mers go to the TEAM = 8 launch
 };
 
@@ -127,20 +128,22 @@ __device__ __forceinline__ int ungapped_u16(const uint8_t *__restrict__ tres, co
     const uint32_t o = __ldg(toff + id);
     const uint32_t tLen = __ldg(toff + id + 1) - o;
     const uint8_t *t = tres + o;
-    if (L >= 32768 || tLen >= 32768) {
-        int totalMax = 0;
-        for (uint32_t d = 1; d <= 1 + tLen / 32768; d++) {
-            int real = (int)(-(long long)d * 65536 + (long long)diag16);
-            totalMax = max(totalMax, ungapped_diag(t, tLen, q, L, corr, m40u, real));
-        }
-        for (uint32_t d = 0; d <= (uint32_t)L / 65536; d++) {
-            int real = (int)(d * 65536 + diag16);
-            totalMax = max(totalMax, ungapped_diag(t, tLen, q, L, corr, m40u, real));
-        }
-        return totalMax;
+    // one loop over the candidate real diagonals (a single inlined copy of the scorer): the 16-bit diagonal itself, or
+    // for sequences >= 32768 every diagonal congruent to it (computeLongScore)
+    const bool isLong = (L >= 32768 || tLen >= 32768);
+    const uint32_t nNeg = isLong ? 1u + tLen / 32768u : 0u, nPos = isLong ? (uint32_t)L / 65536u + 1u : 0u;
+    const uint32_t nIter = isLong ? nNeg + nPos : 1u;
+    int totalMax = 0;
+    for (uint32_t it = 0; it < nIter; it++) {
+        int real;
+        if (!isLong) real = (int)(short)diag16;
+        else if (it < nNeg) real = (int)(-(long long)(it + 1u) * 65536 + (long long)diag16);
+        else real = (int)((it - nNeg) * 65536u + diag16);
+        totalMax = max(totalMax, ungapped_diag(t, tLen, q, L, corr, m40u, real));
     }
-    return ungapped_diag(t, tLen, q, L, corr, m40u, (int)(short)diag16);
+    return totalMax;
 }
+
 
 // In-place stable compaction of a[0..n) keeping elements with flag(i, a[i], a[i-1]); returns the new length.
 template <class Flag>
@@ -618,7 +621,7 @@ struct WorkSmem {
     uint8_t cnt[PW_SCAP];
 };
 
-__device__ __forceinline__ void warp_bitonic_u64(uint64_t *a, int n_pow2) {
+__device__ __noinline__ void warp_bitonic_u64(uint64_t *a, int n_pow2) {
     const int lane = threadIdx.x & 31;
     for (int k = 2; k <= n_pow2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -633,6 +636,64 @@ __device__ __forceinline__ void warp_bitonic_u64(uint64_t *a, int n_pow2) {
         }
     }
     __syncwarp();
+}
+
+__device__ __noinline__ int warp_incl_scan_ool(int v) { return warp_incl_scan(v); }
+
+// out-of-line copies for the team kernels: their instruction footprint must stay small (32 warps per SM run different
+// phases of different queries; an inlined kernel of 128 KB thrashes the instruction cache)
+__device__ __noinline__ int ungapped_u16_ool(const uint8_t *__restrict__ tres, const uint32_t *__restrict__ toff, uint32_t id,
+                                             const uint8_t *q, int L, const signed char *corr, const signed char *m40u, uint32_t diag16) {
+    return ungapped_u16(tres, toff, id, q, L, corr, m40u, diag16);
+}
+
+// hit records: warp-aggregated append to the team's scratch slice + seen-once / seen-twice bitmaps
+__device__ __noinline__ void pw_emit(bool have, uint64_t pe, uint32_t k, uint32_t w, uint32_t *nHitsCtr, uint64_t *scratch, uint32_t HCAP,
+                                     uint32_t *seen1, uint32_t *seen2, int hashShift) {
+    const int lane = threadIdx.x & 31;
+    const unsigned m = __ballot_sync(0xffffffffu, have);
+    if (m == 0) return;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(nHitsCtr, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (have) {
+        const uint32_t id = (uint32_t)(pe >> 16);
+        const uint32_t dg = (w - (uint32_t)(pe & 0xFFFFull)) & 0xFFFFu;
+        const uint32_t dst = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+        if (dst < HCAP) __stcg(scratch + dst, ((uint64_t)id << 32) | ((uint64_t)k << 16) | dg);
+        const uint32_t h = (id * 2654435761u) >> hashShift;
+        const uint32_t bm = 1u << (h & 31);
+        const uint32_t old = atomicOr(&seen1[h >> 5], bm);
+        if ((old & bm) || (dg & 0xFFu) == 0u) atomicOr(&seen2[h >> 5], bm);
+    }
+}
+
+// posting lists of the k-mers held by the lanes of a warp (len == 0: none), flattened over the warp: element p of the
+// concatenated lists belongs to the last lane whose exclusive prefix is <= p (coalesced reads, no per-lane walks)
+__device__ __noinline__ void pw_walk(uint32_t len, uint32_t off, uint32_t w, uint32_t kb, const uint64_t *__restrict__ post,
+                                     uint32_t *nHitsCtr, uint64_t *scratch, uint32_t HCAP, uint32_t *seen1, uint32_t *seen2, int hashShift) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t inc = (uint32_t)warp_incl_scan_ool((int)len);
+    const uint32_t excl = inc - len;
+    const uint32_t T = __shfl_sync(0xffffffffu, inc, 31);
+#pragma unroll 1
+    for (uint32_t p0 = 0; p0 < T; p0 += 32) {
+        const uint32_t pp = p0 + lane;
+        int j = 0;
+#pragma unroll 1
+        for (int step = 16; step > 0; step >>= 1) {
+            const int cand = j + step;
+            const uint32_t e = __shfl_sync(0xffffffffu, excl, cand & 31);
+            if (cand < 32 && e <= pp) j = cand;
+        }
+        const uint32_t srcOff = __shfl_sync(0xffffffffu, off, j);
+        const uint32_t srcEx = __shfl_sync(0xffffffffu, excl, j);
+        const uint32_t srcW = __shfl_sync(0xffffffffu, w, j);
+        const bool have = pp < T;
+        uint64_t pe = 0;
+        if (have) pe = __ldg(post + srcOff + (pp - srcEx));
+        pw_emit(have, pe, kb + (uint32_t)j, srcW, nHitsCtr, scratch, HCAP, seen1, seen2, hashShift);
+    }
 }
 
 // CTA-wide bitonic sort of (key, payload) pairs by key (ascending); n_pow2 entries, padded by the caller
@@ -689,7 +750,7 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
         if (tw == 0 && lane == 0) S.v_qi = atomicAdd(A.qCounter, 1u);
         team_sync();
         const uint32_t slot = S.v_qi;
-        if (slot >= (A.qlist ? *A.nListPtr : A.Q)) break;
+        if (slot >= (A.qlist ? (A.nListPtr ? *A.nListPtr : A.nList) : A.Q)) break;
         const uint32_t qi = A.qlist ? A.qlist[slot] : slot;
         const uint32_t qo = A.qoff[qi];
         const int L = (int)(A.qoff[qi + 1] - qo);
@@ -811,7 +872,7 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                         const uint32_t gNext = (i + 1 < nRuns) ? (uint32_t)runs[i + 1].cum : Rtot;
                         cntK = (gNext - gThis) * (uint32_t)runs[i].n2;
                     }
-                    const uint32_t inc = (uint32_t)warp_incl_scan((int)cntK);
+                    const uint32_t inc = (uint32_t)warp_incl_scan_ool((int)cntK);
                     const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
                     __syncwarp();
                     if (K + tot > 65535u) { why = ST_CAPACITY; reason = 4; break; }
@@ -852,23 +913,8 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                         d[u] = __ldg(A.direct + (i1 + 8000u * i2));
                     }
                 }
-                // hit records: warp-aggregated append to the team's scratch slice + seen-once / seen-twice bitmaps
                 auto emit = [&](bool have, uint64_t pe, uint32_t k, uint32_t w) {
-                    const unsigned m = __ballot_sync(0xffffffffu, have);
-                    if (m == 0) return;
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&S.v_nHits, (uint32_t)__popc(m));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (have) {
-                        const uint32_t id = (uint32_t)(pe >> 16);
-                        const uint32_t dg = (w - (uint32_t)(pe & 0xFFFFull)) & 0xFFFFu;
-                        const uint32_t dst = base + (uint32_t)__popc(m & lt);
-                        if (dst < HCAP) __stcg(scratch + dst, ((uint64_t)id << 32) | ((uint64_t)k << 16) | dg);
-                        const uint32_t h = (id * 2654435761u) >> (SOLO ? 19 : 17);
-                        const uint32_t bm = 1u << (h & 31);
-                        const uint32_t old = atomicOr(&S.seen1[h >> 5], bm);
-                        if ((old & bm) || (dg & 0xFFu) == 0u) atomicOr(&S.seen2[h >> 5], bm);
-                    }
+                    pw_emit(have, pe, k, w, &S.v_nHits, scratch, HCAP, S.seen1, S.seen2, SOLO ? 19 : 17);
                 };
 #pragma unroll
                 for (int u = 0; u < PW_U; u++) {
@@ -877,30 +923,10 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                     const bool single = (dv >> 63) != 0;
                     // k-mers of exactly one target carry their posting inline
                     emit(single, dv & 0x0000FFFFFFFFFFFFull, kb + lane, ww[u]);
-                    // posting lists of the other k-mers, flattened over the warp: element p of the concatenated lists
-                    // belongs to the last lane whose exclusive prefix is <= p (coalesced reads, no per-lane walks)
+                    // posting lists of the other k-mers, flattened over the warp
                     const uint32_t len = single ? 0u : (uint32_t)(dv >> 32);
-                    const uint32_t off = (uint32_t)dv;
-                    const uint32_t inc = (uint32_t)warp_incl_scan((int)len);
-                    const uint32_t excl = inc - len;
-                    const uint32_t T = __shfl_sync(0xffffffffu, inc, 31);
-                    for (uint32_t p0 = 0; p0 < T; p0 += 32) {
-                        const uint32_t pp = p0 + lane;
-                        int j = 0;
-#pragma unroll
-                        for (int step = 16; step > 0; step >>= 1) {
-                            const int cand = j + step;
-                            const uint32_t e = __shfl_sync(0xffffffffu, excl, cand & 31);
-                            if (cand < 32 && e <= pp) j = cand;
-                        }
-                        const uint32_t srcOff = __shfl_sync(0xffffffffu, off, j);
-                        const uint32_t srcEx = __shfl_sync(0xffffffffu, excl, j);
-                        const uint32_t srcW = __shfl_sync(0xffffffffu, ww[u], j);
-                        const bool have = pp < T;
-                        uint64_t pe = 0;
-                        if (have) pe = __ldg(A.post + srcOff + (pp - srcEx));
-                        emit(have, pe, kb + (uint32_t)j, srcW);
-                    }
+                    if (__any_sync(0xffffffffu, len != 0u))
+                        pw_walk(len, (uint32_t)dv, ww[u], kb, A.post, &S.v_nHits, scratch, HCAP, S.seen1, S.seen2, SOLO ? 19 : 17);
                 }
             }
         }
@@ -946,25 +972,23 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
         uint32_t nSurv = 0, G = 1;
         if (live) {
             const uint32_t c0 = cnt64[2 * lane], c1 = cnt64[2 * lane + 1];
-            uint32_t mx[7];     // mx[l]: largest merged bucket when 64 >> l groups are used
-            uint32_t sum = c0 + c1;
-            mx[0] = max(c0, c1);
-#pragma unroll
-            for (int l = 1; l < 7; l++) {
-                if (l > 1) sum += __shfl_xor_sync(0xffffffffu, sum, 1 << (l - 2));
-                mx[l] = sum;
+            // level l uses 64 >> l groups; the largest merged bucket grows with l, so the last level that fits wins
+            uint32_t sum = c0 + c1, mxFit = 0;
+            int lvl = -1;
+#pragma unroll 1
+            for (int l = 0; l < 7; l++) {
+                if (l >= 2) sum += __shfl_xor_sync(0xffffffffu, sum, 1 << (l - 2));
+                uint32_t m = (l == 0) ? max(c0, c1) : sum;
+#pragma unroll 1
+                for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+                if (m <= PW_SCAP) { lvl = l; mxFit = m; }
+                if (l == 6) nSurv = m;
             }
-#pragma unroll
-            for (int l = 0; l < 7; l++)
-                for (int d = 16; d > 0; d >>= 1) mx[l] = max(mx[l], __shfl_xor_sync(0xffffffffu, mx[l], d));
-            nSurv = mx[6];
-            int lvl = 6;
-#pragma unroll
-            for (int l = 5; l >= 0; l--) if (mx[lvl] > PW_SCAP) lvl = l;
-            G = 64u >> lvl;
-            if (mx[lvl] > PW_SCAP && tw == 0 && lane == 0) { S.v_slow = ST_CAPACITY; S.v_why = 6; }   // one bucket alone overflows a sort
+            (void)mxFit;
+            G = 64u >> max(lvl, 0);
+            if (lvl < 0 && tw == 0 && lane == 0) { S.v_slow = ST_CAPACITY; S.v_why = 6; }   // one bucket alone overflows a sort
             if (tw == 0) {   // bucket starts
-                uint32_t e0 = (uint32_t)warp_incl_scan((int)(c0 + c1)) - (c0 + c1);
+                uint32_t e0 = (uint32_t)warp_incl_scan_ool((int)(c0 + c1)) - (c0 + c1);
                 cnt64[64 + 2 * lane] = e0;
                 cnt64[64 + 2 * lane + 1] = e0 + c0;
             }
@@ -1044,7 +1068,7 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                 // ---- ungapped diagonal scores; per target the first event reaching the target's maximum ----
                 for (int i = lane; i < nkept; i += 32) {
                     const uint64_t r = W.surv[i];
-                    const int sc = ungapped_u16(A.tres, A.toff, (uint32_t)(r >> 32), S.q, L, S.corr, s_m40u, (uint32_t)r & 0xFFFFu);
+                    const int sc = ungapped_u16_ool(A.tres, A.toff, (uint32_t)(r >> 32), S.q, L, S.corr, s_m40u, (uint32_t)r & 0xFFFFu);
                     W.cnt[i] = (uint8_t)min(sc, capScore);
                 }
                 __syncwarp();
@@ -1065,7 +1089,7 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                                 keep = true;
                                 const uint32_t dg = (uint32_t)W.surv[bi] & 0xFFFFu;
                                 int sc = best;     // saturated counters get their exact score (getResult, QueryMatcher.cpp:371-374)
-                                if (sc >= capScore) sc = ungapped_u16(A.tres, A.toff, id, S.q, L, S.corr, s_m40u, dg);
+                                if (sc >= capScore) sc = ungapped_u16_ool(A.tres, A.toff, id, S.q, L, S.corr, s_m40u, dg);
                                 f = ((uint64_t)(0xFFFFu - (uint32_t)min(sc, 0xFFFF)) << 48) | ((uint64_t)id << 16) | dg;
                                 // truncation order of the reference's stable counting sorts: capped score desc, bin, stream order, id
                                 const uint32_t kk = (uint32_t)(W.surv[bi] >> 16) & 0xFFFFu;
@@ -1324,7 +1348,17 @@ extern "C" int spb_queries_set(spb_ctx *c, const uint8_t *q_residues, const uint
         off32[i] = (uint32_t)q_offsets[i];
         if (i) maxL = std::max(maxL, (uint32_t)(q_offsets[i] - q_offsets[i - 1]));
     }
-    if (c->d_q.ensure(NQ + 64) || c->d_qoff.ensure(((size_t)Q + 1) * 4) || c->d_qoff64.ensure(((size_t)Q + 1) * 8)) return 1;
+    // processing order of the prefilter: by length, longest first (counting sort, stable)
+    std::vector<uint32_t> order((size_t)Q);
+    {
+        std::vector<uint32_t> start((size_t)maxL + 2, 0);
+        for (uint32_t i = 0; i < Q; i++) start[maxL - (off32[i + 1] - off32[i]) + 1]++;
+        for (size_t l = 1; l < start.size(); l++) start[l] += start[l - 1];
+        for (uint32_t i = 0; i < Q; i++) order[start[maxL - (off32[i + 1] - off32[i])]++] = i;
+    }
+    if (c->d_q.ensure(NQ + 64) || c->d_qoff.ensure(((size_t)Q + 1) * 4) || c->d_qoff64.ensure(((size_t)Q + 1) * 8) ||
+        c->d_qorder.ensure((size_t)Q * 4 + 4)) return 1;
+    if (Q) SPB_CUDA(cudaMemcpyAsync(c->d_qorder.p, order.data(), (size_t)Q * 4, cudaMemcpyHostToDevice, c->stream));
     if (NQ) SPB_CUDA(cudaMemcpyAsync(c->d_q.p, q_residues, NQ, cudaMemcpyHostToDevice, c->stream));
     SPB_CUDA(cudaMemcpyAsync(c->d_qoff.p, off32.data(), off32.size() * 4, cudaMemcpyHostToDevice, c->stream));
     SPB_CUDA(cudaMemcpyAsync(c->d_qoff64.p, q_offsets, ((size_t)Q + 1) * 8, cudaMemcpyHostToDevice, c->stream));
@@ -1427,8 +1461,9 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
         unsigned int *d_qc = reinterpret_cast<unsigned int *>(c->s_f.as<unsigned long long>() + 14);   // [0] solo, [1] team scheduler
         unsigned int *d_ctrT = reinterpret_cast<unsigned int *>(c->s_f.as<unsigned long long>() + 24); // counters of the ST_TEAM scan
         A.qCounter = d_qc;
-        A.qlist = nullptr;
+        A.qlist = c->d_qorder.as<uint32_t>();     // longest queries first: their k-mer lists are the long ones (tail of the launch)
         A.nListPtr = nullptr;
+        A.nList = Q;
         SPB_CUDA(cudaEventRecord(c->ev0, st));
         prefilter_team_kernel<1><<<soloBlocks, PW_WARPS * 32, 0, st>>>(A);
         SPB_CUDA(cudaGetLastError()); c->n_launches++;
