@@ -1,0 +1,72 @@
+// db_io.h -- MMseqs2 on-disk DB reader / writer of the spb200 host binary.
+//
+// Byte-compatible with the reference's DBReader / DBWriter for the files the search path touches
+// (M/commons/DBReader.h:57-99, DBReader.cpp:105-368,541-550; M/commons/DBWriter.cpp:216-440):
+//   <name>         concatenated entries, each NUL-terminated (sequence entries are "residues\n\0")
+//   <name>.index   text lines  key \t offset \t length   (length includes the NUL; any line order)
+//   <name>.dbtype  4-byte little-endian int (0 amino acids, 5 alignment results, 7 prefilter results)
+// A multi-threaded reference writer may leave <name>.0 .. <name>.N-1 whose offsets live in the concatenated space.
+#pragma once
+
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+namespace spbhost {
+
+enum { DBTYPE_AMINO_ACIDS = 0, DBTYPE_ALIGNMENT_RES = 5, DBTYPE_PREFILTER_RES = 7 };
+
+struct DBEntry {
+    uint32_t key;
+    uint64_t offset;
+    uint64_t length;   // incl. the terminating NUL
+};
+
+class DBReader {
+public:
+    // throws std::runtime_error with the reference's wording on missing files
+    void open(const std::string &name);
+    size_t size() const { return entries_.size(); }
+    int dbtype() const { return dbtype_; }
+    // entries sorted by key (DBReader::NOSORT id order after sortIndex) ...
+    const DBEntry &byKey(size_t i) const { return entries_[i]; }
+    // ... and the LINEAR_ACCESS order (by data offset, DBReader.cpp:339-368): ids of the prefilter index
+    const DBEntry &linear(size_t id) const { return entries_[linear_[id]]; }
+    // position (in key order) of a key, or SIZE_MAX
+    size_t findKey(uint32_t key) const;
+    // id in LINEAR_ACCESS order of a key, or SIZE_MAX
+    size_t linearIdOfKey(uint32_t key) const;
+    const char *data(const DBEntry &e) const { return data_.data() + e.offset; }
+    // DBReader::getAminoAcidDBSize (DBReader.cpp:541-550): data bytes - 2 * entries
+    uint64_t aminoAcidDBSize() const { return dataSize_ - 2 * (uint64_t)entries_.size(); }
+    uint64_t dataSize() const { return dataSize_; }
+
+private:
+    std::vector<DBEntry> entries_;
+    std::vector<uint32_t> linear_, linearRank_;
+    std::vector<char> data_;
+    uint64_t dataSize_ = 0;
+    int dbtype_ = 0;
+};
+
+class DBWriter {
+public:
+    // entries are buffered per writer thread and laid out thread after thread on close(), like the reference's
+    // per-thread data files merged by DBWriter::mergeResults; the index is written sorted by key, <name>.dbtype last
+    // (the workflow scripts test for it: blastp.sh:31,39)
+    void open(const std::string &name, int dbtype, int threads);
+    void write(int thread, uint32_t key, const char *payload, size_t len);   // payload without the NUL
+    void close();
+
+private:
+    struct Part {
+        std::vector<char> data;
+        std::vector<DBEntry> idx;
+    };
+    std::string name_;
+    int dbtype_ = 0;
+    std::vector<Part> parts_;
+};
+
+}  // namespace spbhost

@@ -1,0 +1,608 @@
+// main.cpp -- spb200: drop-in `prefilter` and `align` modules over libspb200 (the C ABI in include/spb200.h).
+//
+// Accepts the argv the reference's workflow generates for these two steps (lib/mmseqs/data/workflow/blastp.sh:33,41;
+// flag sets M/commons/Parameters.cpp:337-398; the effective SpacePHARER command lines are in SURVEY.md 3.2), reads and
+// writes the MMseqs2 DB format byte-compatibly, and prints the rows exactly like QueryMatcher::prefilterHitToBuffer
+// (M/prefiltering/QueryMatcher.h:114-126) and Matcher::resultToBuffer (M/alignment/Matcher.cpp:323-370).
+//   spb200 prefilter <queryDB> <targetDB> <prefilterDB> [flags]     Prefiltering (M/prefiltering/Prefiltering.cpp)
+//   spb200 align     <queryDB> <targetDB> <prefilterDB> <alnDB> [flags]   Alignment (M/alignment/Alignment.cpp)
+//   spb200 search    <queryDB> <targetDB> <alnDB> [flags]           both steps with the hit lists kept in HBM
+// Host-only helpers used by the CPU tests: dumpmatrix, dbcopy, showparams.
+// Errors follow the reference: message on stderr, exit code 1 (Debug(Debug::ERROR) ... EXIT(EXIT_FAILURE)).
+#include <ctype.h>
+#include <limits.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../../../include/spb200.h"
+#include "db_io.h"
+#include "submat.h"
+
+using namespace spbhost;
+
+namespace {
+
+struct Fail : std::runtime_error {
+    explicit Fail(const std::string &m) : std::runtime_error(m) {}
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// parameters (names, defaults and meaning of M/commons/Parameters.cpp; SpacePHARER's predictmatch defaults are passed
+// explicitly by the workflow, the values below are MMseqs2's own defaults)
+// ---------------------------------------------------------------------------------------------------------
+struct Params {
+    std::vector<std::string> db;
+    std::string subMat = "nucl:nucleotide.out,aa:blosum62.out", seedSubMat = "nucl:nucleotide.out,aa:VTML80.out";
+    float sensitivity = 5.7f;
+    int kmerSize = 0, kmerScore = INT_MAX, maxSeqs = 300, minUngapped = 15, mask = 1, compBias = 1, diagScore = 1;
+    int split = 0, splitMode = 2, exactKmer = 0, spacedMode = 1, covMode = 0, addSelf = 0, maskLower = 0;
+    std::string spacedPattern;
+    double evalue = 1e-3, seqIdThr = 0, covThr = 0;
+    int addBacktrace = 0, alignmentMode = 0, altAli = 0, realign = 0, seqIdMode = 0, alnLenThr = 0;
+    int maxRejected = INT_MAX, maxAccept = INT_MAX;
+    std::string gapOpen = "nucl:5,aa:11", gapExtend = "nucl:2,aa:1";
+    double scoreBias = 0.0;
+    int threads = 1, verbosity = 3, compressed = 0;
+    // spb200-specific
+    int device = 0, binSize = 0, byteLanes = 32, wordLanes = 16;
+    std::string gumbel;
+    long batch = 1000000;
+};
+
+struct FlagDef { const char *name; int kind; void *dst; };   // kind: 0 int, 1 float, 2 double, 3 string, 4 ignored
+
+std::vector<FlagDef> flag_table(Params &p) {
+    static int ignoredInt;
+    (void)ignoredInt;
+    return {
+        {"--sub-mat", 3, &p.subMat}, {"--seed-sub-mat", 3, &p.seedSubMat}, {"-s", 1, &p.sensitivity}, {"-k", 0, &p.kmerSize},
+        {"--k-score", 0, &p.kmerScore}, {"--max-seqs", 0, &p.maxSeqs}, {"--min-ungapped-score", 0, &p.minUngapped},
+        {"--mask", 0, &p.mask}, {"--mask-lower-case", 0, &p.maskLower}, {"--comp-bias-corr", 0, &p.compBias},
+        {"--diag-score", 0, &p.diagScore}, {"--split", 0, &p.split}, {"--split-mode", 0, &p.splitMode},
+        {"--exact-kmer-matching", 0, &p.exactKmer}, {"--spaced-kmer-mode", 0, &p.spacedMode},
+        {"--spaced-kmer-pattern", 3, &p.spacedPattern}, {"--cov-mode", 0, &p.covMode}, {"-c", 2, &p.covThr},
+        {"--add-self-matches", 0, &p.addSelf}, {"-e", 2, &p.evalue}, {"--min-seq-id", 2, &p.seqIdThr},
+        {"-a", 0, &p.addBacktrace}, {"--alignment-mode", 0, &p.alignmentMode}, {"--alt-ali", 0, &p.altAli},
+        {"--realign", 0, &p.realign}, {"--seq-id-mode", 0, &p.seqIdMode}, {"--min-aln-len", 0, &p.alnLenThr},
+        {"--max-rejected", 0, &p.maxRejected}, {"--max-accept", 0, &p.maxAccept}, {"--gap-open", 3, &p.gapOpen},
+        {"--gap-extend", 3, &p.gapExtend}, {"--score-bias", 2, &p.scoreBias}, {"--threads", 0, &p.threads},
+        {"-v", 0, &p.verbosity}, {"--compressed", 0, &p.compressed},
+        // accepted and without influence on this path (profile / nucleotide / memory-management flags of the same modules)
+        {"--alph-size", 4, nullptr}, {"--max-seq-len", 4, nullptr}, {"--split-memory-limit", 4, nullptr},
+        {"--db-load-mode", 4, nullptr}, {"--pca", 4, nullptr}, {"--pcb", 4, nullptr}, {"--alignment-output-mode", 4, nullptr},
+        {"--wrapped-scoring", 4, nullptr}, {"--realign-score-bias", 4, nullptr}, {"--realign-max-seqs", 4, nullptr},
+        {"--zdrop", 4, nullptr}, {"--local-tmp", 4, nullptr}, {"--taxon-list", 4, nullptr}, {"--exhaustive-search-filter", 4, nullptr},
+        // spb200-specific
+        {"--device", 0, &p.device}, {"--bin-size", 0, &p.binSize}, {"--byte-lanes", 0, &p.byteLanes}, {"--word-lanes", 0, &p.wordLanes},
+        {"--gumbel", 3, &p.gumbel}, {"--batch", 0, nullptr},
+    };
+}
+
+void parse_args(int argc, const char **argv, int first, size_t nDb, Params &p) {
+    std::vector<FlagDef> table = flag_table(p);
+    for (int i = first; i < argc; i++) {
+        const std::string a = argv[i];
+        if (a.size() > 1 && a[0] == '-' && !(a.size() > 1 && (isdigit((unsigned char)a[1]) || a[1] == '.'))) {
+            const FlagDef *def = nullptr;
+            for (const FlagDef &f : table)
+                if (a == f.name) def = &f;
+            if (!def) throw Fail("Unrecognized parameter \"" + a + "\"");
+            if (i + 1 >= argc) throw Fail("Missing argument " + a);
+            const char *v = argv[++i];
+            char *end = nullptr;
+            if (a == "--batch") { p.batch = strtol(v, &end, 10); if (*end || p.batch < 1) throw Fail("Error in argument " + a); continue; }
+            switch (def->kind) {
+                case 0: {
+                    long x = strtol(v, &end, 10);
+                    if (end == v || *end) throw Fail("Error in argument " + a);
+                    *(int *)def->dst = (int)std::max<long>(INT_MIN, std::min<long>(INT_MAX, x));
+                    break;
+                }
+                case 1: *(float *)def->dst = strtof(v, &end); if (end == v || *end) throw Fail("Error in argument " + a); break;
+                case 2: *(double *)def->dst = strtod(v, &end); if (end == v || *end) throw Fail("Error in argument " + a); break;
+                case 3: *(std::string *)def->dst = v; break;
+                default: break;
+            }
+        } else {
+            p.db.push_back(a);
+        }
+    }
+    if (p.db.size() != nDb) throw Fail("expected " + std::to_string(nDb) + " database arguments, got " + std::to_string(p.db.size()));
+    if (p.compressed != 0) throw Fail("--compressed 1 is not supported");
+    if (p.threads < 1) p.threads = 1;
+}
+
+// Prefiltering::getKmerThreshold (M/prefiltering/Prefiltering.cpp:987-1021), sequence (non-profile) search
+int kmer_threshold(float sensitivity, int kmerScore, int kmerSize) {
+    double best = kmerScore;
+    if (kmerScore == INT_MAX) {
+        if (kmerSize == 6) {
+            float base = 163.2f;
+            best = base - (sensitivity * 8.917);
+        } else {
+            throw Fail("The k-mer size " + std::to_string(kmerSize) + " is not valid.");
+        }
+    }
+    return (int)best;
+}
+
+// QueryMatcher::initDiagonalMatcher (M/prefiltering/QueryMatcher.cpp:383-411) with Util::getL2CacheSize
+int bin_size_for(size_t dbsize) {
+    uint64_t l2 = 262144;
+#if defined(_SC_LEVEL2_CACHE_SIZE)
+    long c = sysconf(_SC_LEVEL2_CACHE_SIZE);
+    if (c > 0) l2 = (uint64_t)c;
+#endif
+    for (int b = 2; b <= 1024; b *= 2)
+        if (dbsize / (size_t)b < l2) return b;
+    return 2048;
+}
+
+// ALP parameter sets (M/alignment/EvalueComputation.h:56-75 table; VTML40 16/2 as estimated by the reference with seed 42,
+// SURVEY.md 8a-5).  Other combinations must come from the reference's estimator via --gumbel.
+bool gumbel_for(const std::string &mat, int go, int ge, const std::string &override_, spb_gumbel *g) {
+    double v[12];
+    if (!override_.empty()) {
+        const char *p = override_.c_str();
+        for (int i = 0; i < 12; i++) {
+            char *e = nullptr;
+            v[i] = strtod(p, &e);
+            if (e == p) return false;
+            p = (*e == ',') ? e + 1 : e;
+        }
+    } else if (mat == "VTML40.out" && go == 16 && ge == 2) {
+        const double t[12] = {0.34420393530174209, 0.27487374979561635, 0.22018895496520485, 0.026237512825550646,
+                              0.18481499377626534, 1.7126891360391483, 0.22018895496520485, 0.026237512825550646,
+                              0.18481499377626534, 1.7126891360391483, 0.18283871043913499, 1.7838353361758408};
+        memcpy(v, t, sizeof(v));
+    } else if (mat == "blosum62.out" && go == 11 && ge == 1) {
+        const double t[12] = {0.27359865037097330642, 0.044620920658722244834, 1.5938724404943873658, -19.959867650284412122,
+                              30.455610143099914211, -622.28684628915891608, 1.5938724404943873658, -19.959867650284412122,
+                              30.455610143099914211, -622.28684628915891608, 29.602444874818868215, -601.81087985041381216};
+        memcpy(v, t, sizeof(v));
+    } else {
+        return false;
+    }
+    g->lambda = v[0]; g->K = v[1]; g->a_I = v[2]; g->b_I = v[3]; g->alpha_I = v[4]; g->beta_I = v[5];
+    g->a_J = v[6]; g->b_J = v[7]; g->alpha_J = v[8]; g->beta_J = v[9]; g->sigma = v[10]; g->tau = v[11];
+    return true;
+}
+
+void check(int rc, const char *what) {
+    if (rc != 0) throw Fail(std::string(what) + ": " + spb_last_error());
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// sequence DBs -> numeric residues
+// ---------------------------------------------------------------------------------------------------------
+struct SeqSet {
+    std::vector<uint8_t> res;
+    std::vector<uint64_t> off;
+    std::vector<uint32_t> keys;   // DB key of every sequence (position = id)
+};
+
+// ids in LINEAR_ACCESS order (what Prefiltering / IndexBuilder use for both DBs, Prefiltering.cpp:163-164,187-188)
+void load_sequences(const DBReader &db, const SubMat &m, SeqSet &s) {
+    const size_t n = db.size();
+    s.off.assign(n + 1, 0);
+    s.keys.resize(n);
+    uint64_t total = 0;
+    for (size_t i = 0; i < n; i++) {
+        const DBEntry &e = db.linear(i);
+        const uint64_t len = e.length >= 2 ? e.length - 2 : 0;   // "residues\n\0"
+        s.off[i] = total;
+        s.keys[i] = e.key;
+        total += len;
+    }
+    s.off[n] = total;
+    s.res.resize(total + 1);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long i = 0; i < (long)n; i++) {
+        const DBEntry &e = db.linear((size_t)i);
+        m.encode(db.data(e), (size_t)(s.off[i + 1] - s.off[i]), s.res.data() + s.off[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// row formatting
+// ---------------------------------------------------------------------------------------------------------
+// Util::fastSeqIdToBuffer (M/commons/Util.cpp:278-307): the caller overwrites the last byte with '\t', hence "1.00"
+size_t seqid_to_buffer(float seqId, char *b) {
+    char *s = b;
+    if (seqId == 1.0f) {
+        memcpy(b, "1.00", 4);
+        return 4;
+    }
+    *b++ = '0';
+    *b++ = '.';
+    if (seqId < 0.10) *b++ = '0';
+    if (seqId < 0.01) *b++ = '0';
+    b += sprintf(b, "%d", (int)(seqId * 1000));
+    return (size_t)(b - s);
+}
+
+// Matcher::compressAlignment (M/alignment/Matcher.cpp:211-230): run lengths, counts always printed
+void compress_cigar(const char *ops, uint32_t n, std::string &out) {
+    char state = 'M';
+    unsigned count = 0;
+    char tmp[16];
+    for (uint32_t i = 0; i < n; i++) {
+        if (ops[i] != state) {
+            out.append(tmp, (size_t)sprintf(tmp, "%u%c", count, state));
+            state = ops[i];
+            count = 1;
+        } else {
+            count++;
+        }
+    }
+    out.append(tmp, (size_t)sprintf(tmp, "%u%c", count, state));
+}
+
+struct Engine {
+    spb_ctx *ctx = nullptr;
+    SubMat seed, ungapped, align;
+    ~Engine() { if (ctx) spb_ctx_destroy(ctx); }
+    void open(const Params &p) {
+        seed.load(p.seedSubMat, 8.0, -0.2);        // Prefiltering.cpp:64
+        ungapped.load(p.subMat, 2.0, -0.2);        // Prefiltering.cpp:65
+        align.load(p.subMat, 2.0, p.scoreBias);    // Alignment.cpp:159
+        check(spb_ctx_create(p.device, &ctx), "spb_ctx_create");
+        check(spb_set_matrices(ctx, seed.sub, seed.pback, ungapped.sub, align.sub, align.pback), "spb_set_matrices");
+    }
+};
+
+void log_line(const Params &p, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+void log_line(const Params &p, const char *fmt, ...) {
+    if (p.verbosity < 3) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vfprintf(stdout, fmt, ap);
+    va_end(ap);
+    fputc('\n', stdout);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// prefilter
+// ---------------------------------------------------------------------------------------------------------
+void build_target_index(Engine &E, const Params &p, const SeqSet &T, int kmerThr) {
+    std::vector<uint8_t> masked(T.res.begin(), T.res.end());
+    uint64_t nMasked = 0;
+    if (p.mask)   // IndexBuilder.cpp:137-149
+        check(spb_tantan_mask(E.seed.prob, E.seed.pback, masked.data(), T.off.data(), (uint32_t)T.keys.size(), p.threads, &nMasked), "spb_tantan_mask");
+    const std::string pattern = p.spacedPattern.empty() ? (p.spacedMode ? "11011101" : "111111") : p.spacedPattern;
+    // index-side threshold (Prefiltering.cpp:510-513): only for exact matching or when the k-mer threshold is small enough
+    check(spb_index_build(E.ctx, masked.data(), T.off.data(), (uint32_t)T.keys.size(), pattern.c_str(), kmerThr), "spb_index_build");
+    spb_index_stats st;
+    check(spb_index_stats_get(E.ctx, &st), "spb_index_stats_get");
+    log_line(p, "Index table: %llu targets, %llu residues (%llu masked), %llu postings, %.1f ms on the device",
+             (unsigned long long)st.n_targets, (unsigned long long)st.n_residues, (unsigned long long)nMasked,
+             (unsigned long long)st.n_postings, st.build_ms);
+}
+
+void check_search_params(const Params &p) {
+    if (p.kmerSize != 0 && p.kmerSize != 6) throw Fail("The k-mer size " + std::to_string(p.kmerSize) + " is not valid. (spb200 implements k = 6)");
+    if (p.diagScore != 1) throw Fail("--diag-score 0 is not supported");
+    if (p.exactKmer != 0) throw Fail("--exact-kmer-matching 1 is not supported");
+    if (p.split > 1) throw Fail("--split > 1: use the multi-GPU driver (target split over GPUs); a single device holds the whole index");
+    if (p.covThr != 0 || p.addSelf != 0) throw Fail("coverage thresholds / --add-self-matches are not supported on this path");
+}
+
+int run_prefilter(int argc, const char **argv) {
+    Params p;
+    parse_args(argc, argv, 2, 3, p);
+    check_search_params(p);
+    Engine E;
+    E.open(p);
+    DBReader qdb, tdb;
+    qdb.open(p.db[0]);
+    tdb.open(p.db[1]);
+    log_line(p, "Query database size: %zu type: Aminoacid", qdb.size());
+    log_line(p, "Target database size: %zu type: Aminoacid", tdb.size());
+    SeqSet Q, T;
+    load_sequences(qdb, E.seed, Q);
+    load_sequences(tdb, E.seed, T);
+    const int kmerThr = kmer_threshold(p.sensitivity, p.kmerScore, 6);
+    log_line(p, "k-mer similarity threshold: %d", kmerThr);
+    build_target_index(E, p, T, kmerThr);
+
+    spb_prefilter_params pp;
+    pp.kmer_thr = kmerThr;
+    pp.max_seqs = p.maxSeqs;
+    pp.min_diag_score = p.minUngapped;
+    pp.bin_size = p.binSize ? p.binSize : bin_size_for(T.keys.size());
+    pp.comp_bias = p.compBias;
+    pp.id_base = 0;
+
+    DBWriter out;
+    out.open(p.db[2], DBTYPE_PREFILTER_RES, p.threads);
+    const size_t nq = Q.keys.size();
+    double kernelMs = 0;
+    uint64_t nHits = 0;
+    for (size_t b0 = 0, b1 = 0; b0 < nq; b0 = b1) {
+        b1 = std::min(nq, b0 + (size_t)p.batch);
+        std::vector<uint64_t> off(b1 - b0 + 1);
+        for (size_t i = b0; i <= b1; i++) off[i - b0] = Q.off[i] - Q.off[b0];
+        spb_prefilter_result *r = nullptr;
+        check(spb_prefilter(E.ctx, Q.res.data() + Q.off[b0], off.data(), (uint32_t)(b1 - b0), &pp, &r), "spb_prefilter");
+        kernelMs += r->kernel_ms;
+        nHits += r->n_hits;
+#pragma omp parallel num_threads(p.threads)
+        {
+            int th = 0;
+#ifdef _OPENMP
+            th = omp_get_thread_num();
+#endif
+            std::string buf;
+            char tmp[64];
+            // contiguous blocks per thread keep every thread's part of the data file in query order
+#pragma omp for schedule(static)
+            for (long i = 0; i < (long)(b1 - b0); i++) {
+                buf.clear();
+                for (uint64_t h = r->offsets[i]; h < r->offsets[i + 1]; h++) {
+                    const spb_hit &x = r->hits[h];   // id -> DB key (Prefiltering.cpp:827-829)
+                    buf.append(tmp, (size_t)sprintf(tmp, "%u\t%d\t%d\n", T.keys[x.id], x.score, x.diag));
+                }
+                out.write(th, Q.keys[b0 + (size_t)i], buf.data(), buf.size());
+            }
+        }
+        spb_free_prefilter_result(r);
+    }
+    out.close();
+    log_line(p, "%llu prefilter hits for %zu queries; match kernels %.3f ms", (unsigned long long)nHits, nq, kernelMs);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// align
+// ---------------------------------------------------------------------------------------------------------
+void fill_align_params(const Params &p, const Engine &E, uint64_t dbRes, spb_align_params *ap) {
+    const int go = atoi(multiparam_aa(p.gapOpen).c_str()), ge = atoi(multiparam_aa(p.gapExtend).c_str());
+    memset(ap, 0, sizeof(*ap));
+    ap->gap_open = go;
+    ap->gap_extend = ge;
+    ap->eval_thr = p.evalue;
+    ap->db_res_count = dbRes;
+    ap->comp_bias = p.compBias;
+    ap->byte_lanes = p.byteLanes;
+    ap->word_lanes = p.wordLanes;
+    if (!gumbel_for(E.align.name, go, ge, p.gumbel, &ap->gumbel))
+        throw Fail("no Gumbel parameters for " + E.align.name + " gap open " + std::to_string(go) + " extend " + std::to_string(ge) +
+                   ": pass the twelve ALP values of the reference run with --gumbel lambda,K,a_I,b_I,alpha_I,beta_I,a_J,b_J,alpha_J,beta_J,sigma,tau");
+}
+
+void check_align_params(const Params &p) {
+    if (p.altAli != 0 || p.realign != 0) throw Fail("--alt-ali / --realign are not supported on this path");
+    if (p.seqIdThr != 0 || p.covThr != 0 || p.alnLenThr != 0) throw Fail("--min-seq-id / -c / --min-aln-len thresholds are not supported on this path");
+    if (p.seqIdMode != 0) throw Fail("--seq-id-mode != 0 is not supported");
+    if (p.maxRejected != INT_MAX || p.maxAccept != INT_MAX) throw Fail("--max-rejected / --max-accept are not supported");
+    // -a forces SCORE_COV_SEQID (Alignment.cpp:35-37); the other modes print fewer columns and are not implemented
+    if (!(p.addBacktrace == 1 || p.alignmentMode == 3)) throw Fail("only the -a 1 (backtrace) output of the predictmatch search is implemented");
+}
+
+void write_alignment_rows(const Params &p, const spb_align_result *r, const SeqSet &Q, size_t b0, const SeqSet &T, DBWriter &out) {
+#pragma omp parallel num_threads(p.threads)
+    {
+        int th = 0;
+#ifdef _OPENMP
+        th = omp_get_thread_num();
+#endif
+        std::string buf, cig;
+        char tmp[256];
+#pragma omp for schedule(static)
+        for (long i = 0; i < (long)r->n_queries; i++) {
+            buf.clear();
+            const int qLen = (int)(Q.off[b0 + i + 1] - Q.off[b0 + i]);
+            for (uint64_t k = r->offsets[i]; k < r->offsets[i + 1]; k++) {
+                const spb_aln &a = r->rows[k];
+                char *w = tmp;
+                w += sprintf(w, "%u\t%d\t", T.keys[a.target], a.bits);
+                w += seqid_to_buffer(a.seq_id, w);
+                w += sprintf(w, "\t%.3E\t%d\t%d\t%d\t%d\t%d\t%d\t", a.eval, a.q_start, a.q_end, qLen, a.t_start, a.t_end,
+                             (int)(T.off[a.target + 1] - T.off[a.target]));
+                buf.append(tmp, (size_t)(w - tmp));
+                cig.clear();
+                if (a.cigar_len) compress_cigar(r->cigar_ops + a.cigar_off, a.cigar_len, cig);
+                buf += cig;
+                buf.push_back('\n');
+            }
+            out.write(th, Q.keys[b0 + (size_t)i], buf.data(), buf.size());
+        }
+    }
+}
+
+int run_align(int argc, const char **argv) {
+    Params p;
+    parse_args(argc, argv, 2, 4, p);
+    check_align_params(p);
+    Engine E;
+    E.open(p);
+    DBReader qdb, tdb, pdb;
+    qdb.open(p.db[0]);
+    tdb.open(p.db[1]);
+    pdb.open(p.db[2]);
+    SeqSet Q, T;
+    // align reads the raw (unmasked) sequences; ids = key order here, rows carry DB keys anyway
+    load_sequences(qdb, E.align, Q);
+    load_sequences(tdb, E.align, T);
+    spb_align_params ap;
+    fill_align_params(p, E, tdb.aminoAcidDBSize(), &ap);   // Alignment.cpp:269
+    check(spb_align_set_targets(E.ctx, T.res.data(), T.off.data(), (uint32_t)T.keys.size(), T.keys.data()), "spb_align_set_targets");
+
+    // work list: one entry of the prefilter DB per query key, first column = target key (Alignment.cpp:348-392)
+    const size_t np = pdb.size();
+    SeqSet PQ;   // queries in prefilter-DB order
+    std::vector<uint64_t> pairOff(1, 0);
+    std::vector<uint32_t> pairT;
+    PQ.off.assign(1, 0);
+    for (size_t i = 0; i < np; i++) {
+        const DBEntry &e = pdb.byKey(i);
+        const size_t qid = qdb.linearIdOfKey(e.key);
+        if (qid == SIZE_MAX) throw Fail("Invalid query sequence " + std::to_string(e.key));
+        PQ.keys.push_back(e.key);
+        PQ.res.insert(PQ.res.end(), Q.res.begin() + (long)Q.off[qid], Q.res.begin() + (long)Q.off[qid + 1]);
+        PQ.off.push_back(PQ.res.size());
+        const char *d = pdb.data(e), *end = d + (e.length ? e.length - 1 : 0);
+        while (d < end) {
+            char *next = nullptr;
+            const unsigned long key = strtoul(d, &next, 10);
+            if (next == d) break;
+            const size_t tid = tdb.linearIdOfKey((uint32_t)key);
+            if (tid == SIZE_MAX) throw Fail("Invalid target sequence " + std::to_string(key) + " in the prefilter list of query " + std::to_string(e.key));
+            pairT.push_back((uint32_t)tid);
+            const char *nl = (const char *)memchr(next, '\n', (size_t)(end - next));
+            d = nl ? nl + 1 : end;
+        }
+        pairOff.push_back(pairT.size());
+    }
+    PQ.res.push_back(0);
+    DBWriter out;
+    out.open(p.db[3], DBTYPE_ALIGNMENT_RES, p.threads);
+    uint64_t nRows = 0, nCells = 0;
+    double kernelMs = 0;
+    for (size_t b0 = 0, b1 = 0; b0 < np; b0 = b1) {
+        b1 = std::min(np, b0 + (size_t)p.batch);
+        while (b1 > b0 + 1 && pairOff[b1] - pairOff[b0] > 0x7FFFFFF0ull) b1 = b0 + (b1 - b0) / 2;
+        std::vector<uint64_t> qo(b1 - b0 + 1), po(b1 - b0 + 1);
+        for (size_t i = b0; i <= b1; i++) { qo[i - b0] = PQ.off[i] - PQ.off[b0]; po[i - b0] = pairOff[i] - pairOff[b0]; }
+        spb_align_result *r = nullptr;
+        check(spb_align(E.ctx, PQ.res.data() + PQ.off[b0], qo.data(), (uint32_t)(b1 - b0), po.data(), pairT.data() + pairOff[b0], &ap, &r),
+              "spb_align");
+        nRows += r->n_rows;
+        nCells += r->n_cells;
+        kernelMs += r->kernel_ms;
+        write_alignment_rows(p, r, PQ, b0, T, out);
+        spb_free_align_result(r);
+    }
+    out.close();
+    log_line(p, "%llu alignments accepted of %zu pairs; %.2f GCUPS in the forward kernels", (unsigned long long)nRows, pairT.size(),
+             kernelMs > 0 ? (double)nCells / kernelMs / 1e6 : 0.0);
+    return 0;
+}
+
+// both steps, hit lists stay in HBM (what blastp.sh does with a pref DB in between)
+int run_search(int argc, const char **argv) {
+    Params p;
+    parse_args(argc, argv, 2, 3, p);
+    check_search_params(p);
+    check_align_params(p);
+    Engine E;
+    E.open(p);
+    DBReader qdb, tdb;
+    qdb.open(p.db[0]);
+    tdb.open(p.db[1]);
+    SeqSet Q, T;
+    load_sequences(qdb, E.seed, Q);
+    load_sequences(tdb, E.seed, T);
+    const int kmerThr = kmer_threshold(p.sensitivity, p.kmerScore, 6);
+    build_target_index(E, p, T, kmerThr);
+    check(spb_align_set_targets(E.ctx, T.res.data(), T.off.data(), (uint32_t)T.keys.size(), T.keys.data()), "spb_align_set_targets");
+    spb_prefilter_params pp;
+    pp.kmer_thr = kmerThr;
+    pp.max_seqs = p.maxSeqs;
+    pp.min_diag_score = p.minUngapped;
+    pp.bin_size = p.binSize ? p.binSize : bin_size_for(T.keys.size());
+    pp.comp_bias = p.compBias;
+    pp.id_base = 0;
+    spb_align_params ap;
+    fill_align_params(p, E, tdb.aminoAcidDBSize(), &ap);
+    DBWriter out;
+    out.open(p.db[2], DBTYPE_ALIGNMENT_RES, p.threads);
+    const size_t nq = Q.keys.size();
+    for (size_t b0 = 0, b1 = 0; b0 < nq; b0 = b1) {
+        b1 = std::min(nq, b0 + (size_t)p.batch);
+        std::vector<uint64_t> off(b1 - b0 + 1);
+        for (size_t i = b0; i <= b1; i++) off[i - b0] = Q.off[i] - Q.off[b0];
+        check(spb_queries_set(E.ctx, Q.res.data() + Q.off[b0], off.data(), (uint32_t)(b1 - b0)), "spb_queries_set");
+        check(spb_prefilter_resident(E.ctx, &pp), "spb_prefilter_resident");
+        check(spb_pairs_from_prefilter(E.ctx), "spb_pairs_from_prefilter");
+        check(spb_align_resident(E.ctx, &ap), "spb_align_resident");
+        spb_align_result *r = nullptr;
+        check(spb_align_fetch(E.ctx, &r), "spb_align_fetch");
+        write_alignment_rows(p, r, Q, b0, T, out);
+        spb_free_align_result(r);
+    }
+    out.close();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-only helpers (CPU tests)
+// ---------------------------------------------------------------------------------------------------------
+int run_dumpmatrix(int argc, const char **argv) {
+    if (argc < 5) throw Fail("usage: spb200 dumpmatrix <matrix> <bitFactor> <scoreBias>");
+    SubMat m;
+    m.load(argv[2], atof(argv[3]), atof(argv[4]));
+    printf("%s\n", m.num2aa);
+    for (int i = 0; i < SubMat::N; i++) {
+        for (int j = 0; j < SubMat::N; j++) printf("%d%c", m.sub[i * SubMat::N + j], j + 1 == SubMat::N ? '\n' : ' ');
+    }
+    for (int i = 0; i < SubMat::N; i++) printf("%.17g%c", m.pback[i], i + 1 == SubMat::N ? '\n' : ' ');
+    return 0;
+}
+
+int run_dbcopy(int argc, const char **argv) {
+    if (argc < 4) throw Fail("usage: spb200 dbcopy <inDB> <outDB> [threads]");
+    DBReader in;
+    in.open(argv[2]);
+    const int threads = argc > 4 ? atoi(argv[4]) : 1;
+    DBWriter out;
+    out.open(argv[3], in.dbtype(), threads);
+    const size_t n = in.size();
+    for (size_t i = 0; i < n; i++) {
+        const DBEntry &e = in.byKey(i);
+        out.write((int)(i * (size_t)threads / (n ? n : 1)), e.key, in.data(e), e.length ? e.length - 1 : 0);
+    }
+    out.close();
+    printf("%zu entries, %llu residues\n", n, (unsigned long long)in.aminoAcidDBSize());
+    return 0;
+}
+
+int run_showparams(int argc, const char **argv) {
+    if (argc < 3) throw Fail("usage: spb200 showparams prefilter|align <args...>");
+    const std::string mod = argv[2];
+    Params p;
+    parse_args(argc, argv, 3, mod == "align" ? 4 : 3, p);
+    if (mod == "align") check_align_params(p); else check_search_params(p);
+    printf("sub_mat=%s seed_sub_mat=%s kmer_thr=%d max_seqs=%d min_ungapped=%d mask=%d comp_bias=%d pattern=%s "
+           "evalue=%g gap_open=%s gap_extend=%s threads=%d\n",
+           multiparam_aa(p.subMat).c_str(), multiparam_aa(p.seedSubMat).c_str(), kmer_threshold(p.sensitivity, p.kmerScore, 6), p.maxSeqs,
+           p.minUngapped, p.mask, p.compBias, p.spacedPattern.empty() ? (p.spacedMode ? "11011101" : "111111") : p.spacedPattern.c_str(),
+           p.evalue, multiparam_aa(p.gapOpen).c_str(), multiparam_aa(p.gapExtend).c_str(), p.threads);
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, const char **argv) {
+    if (argc < 2) {
+        fprintf(stderr, "spb200 (%s): prefilter | align | search | dumpmatrix | dbcopy | showparams\n", spb_version());
+        return 1;
+    }
+    const std::string cmd = argv[1];
+    try {
+        if (cmd == "prefilter") return run_prefilter(argc, argv);
+        if (cmd == "align") return run_align(argc, argv);
+        if (cmd == "search") return run_search(argc, argv);
+        if (cmd == "dumpmatrix") return run_dumpmatrix(argc, argv);
+        if (cmd == "dbcopy") return run_dbcopy(argc, argv);
+        if (cmd == "showparams") return run_showparams(argc, argv);
+        fprintf(stderr, "Invalid Command: %s\n", cmd.c_str());
+        return 1;
+    } catch (const std::exception &e) {
+        fprintf(stderr, "%s\n", e.what());
+        return 1;
+    }
+}

@@ -1,0 +1,59 @@
+"""The spb200 binary (host C++ over the C ABI) on the reference's own example DBs: the prefilter and alignment DBs it
+writes hold, per query key, exactly the bytes of the reference's pref_0 / prot_result (tests/golden/config1)."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN, ROOT, read_dump
+from spacepharer_b200 import dbio
+from test_host_cli import ALN_FLAGS, BIN, PREF_FLAGS
+
+pytestmark = pytest.mark.gpu
+C1 = os.path.join(GOLDEN, "config1")
+
+
+def run(*args):
+    r = subprocess.run([BIN] + list(args), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    return r
+
+
+def entries_as_rows(db):
+    return {k: [l for l in v.decode().split("\n") if l] for k, v in dbio.read_entries(db).items()}
+
+
+def test_prefilter_and_align_dbs_match_reference(tmp_path):
+    pref, aln = str(tmp_path / "pref_0"), str(tmp_path / "aln")
+    run("prefilter", os.path.join(C1, "qsetdb"), os.path.join(C1, "targets"), pref, *PREF_FLAGS)
+    assert dbio.read_dbtype(pref) == dbio.DBTYPE_PREFILTER_RES
+    assert dbio.read_entries(pref) == dbio.read_entries(os.path.join(C1, "pref_0"))
+    run("align", os.path.join(C1, "qsetdb"), os.path.join(C1, "targets"), pref, aln, *ALN_FLAGS)
+    assert dbio.read_dbtype(aln) == dbio.DBTYPE_ALIGNMENT_RES
+    assert dbio.read_entries(aln) == dbio.read_entries(os.path.join(C1, "prot_result"))
+
+
+def test_align_reads_the_reference_prefilter_db(tmp_path):
+    aln = str(tmp_path / "aln")
+    run("align", os.path.join(C1, "qsetdb"), os.path.join(C1, "targets"), os.path.join(C1, "pref_0"), aln, *ALN_FLAGS)
+    assert dbio.read_entries(aln) == dbio.read_entries(os.path.join(C1, "prot_result"))
+
+
+def test_control_db_and_fused_search(tmp_path):
+    """reversed-ORF control setDB (second search of predictmatch) + the fused search command"""
+    pref, aln, fused = str(tmp_path / "pref_rev"), str(tmp_path / "aln_rev"), str(tmp_path / "fused")
+    run("prefilter", os.path.join(C1, "qsetdb"), os.path.join(C1, "targets_rev"), pref, *PREF_FLAGS)
+    got = {k: v for k, v in entries_as_rows(pref).items() if v}
+    assert got == read_dump(os.path.join(C1, "pref_0_rev.txt.gz"))
+    run("align", os.path.join(C1, "qsetdb"), os.path.join(C1, "targets_rev"), pref, aln, *ALN_FLAGS)
+    got = {k: v for k, v in entries_as_rows(aln).items() if v}
+    assert got == read_dump(os.path.join(C1, "prot_result_rev.txt.gz"))
+    # (flag, value) pairs must stay together: rebuild from both lists without duplicates
+    seen, merged = set(), []
+    for lst in (PREF_FLAGS, ALN_FLAGS):
+        for i in range(0, len(lst), 2):
+            if lst[i] not in seen:
+                seen.add(lst[i])
+                merged += [lst[i], lst[i + 1]]
+    run("search", os.path.join(C1, "qsetdb"), os.path.join(C1, "targets_rev"), fused, *merged)
+    assert {k: v for k, v in entries_as_rows(fused).items() if v} == read_dump(os.path.join(C1, "prot_result_rev.txt.gz"))

@@ -1,0 +1,101 @@
+"""Host side of the drop-in boundary (no GPU needed): the C-ABI library loads and exports every symbol of
+include/spb200.h, the spb200 binary parses the workflow-generated argv, builds the reference's matrices, reads and
+writes the MMseqs2 DB format, and fails loudly without a CUDA device."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+import common as Cm
+from conftest import GOLDEN, ROOT
+from spacepharer_b200 import capi, dbio
+
+BIN = os.path.join(ROOT, "spacepharer_b200", "lib", "spb200")
+
+# the exact flag strings the reference workflow generates for the two modules
+PREF_FLAGS = ("--sub-mat nucl:nucleotide.out,aa:VTML40.out --seed-sub-mat nucl:nucleotide.out,aa:VTML80.out -k 6 "
+              "--k-score 2147483647 --alph-size nucl:5,aa:21 --max-seq-len 65535 --max-seqs 300 --split 0 "
+              "--split-mode 2 --split-memory-limit 0 -c 0 --cov-mode 0 --comp-bias-corr 1 --diag-score 1 "
+              "--exact-kmer-matching 0 --mask 1 --mask-lower-case 0 --min-ungapped-score 15 --add-self-matches 0 "
+              "--spaced-kmer-mode 1 --db-load-mode 0 --pca 1 --pcb 1.5 --spaced-kmer-pattern 11011101 --threads 4 "
+              "--compressed 0 -v 3 -s 5.7").split()
+ALN_FLAGS = ("--sub-mat nucl:nucleotide.out,aa:VTML40.out -a 1 --alignment-mode 2 --alignment-output-mode 0 "
+             "--wrapped-scoring 0 -e 200 --min-seq-id 0 --min-aln-len 0 --seq-id-mode 0 --alt-ali 0 -c 0 --cov-mode 0 "
+             "--max-seq-len 65535 --comp-bias-corr 1 --max-rejected 2147483647 --max-accept 2147483647 "
+             "--add-self-matches 0 --db-load-mode 0 --pca 1 --pcb 1.5 --score-bias 0 --realign 0 "
+             "--realign-score-bias -0.2 --realign-max-seqs 2147483647 --gap-open nucl:10,aa:16 --gap-extend 2 "
+             "--zdrop 40 --threads 4 --compressed 0 -v 3").split()
+
+
+def run(*args, ok=True):
+    r = subprocess.run([BIN] + list(args), capture_output=True, text=True)
+    if ok:
+        assert r.returncode == 0, r.stderr
+    return r
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "spb200.h")).read()
+    declared = set(re.findall(r"\b(spb_[a-z0-9_]+)\s*\(", hdr))
+    lib = C.CDLL(capi.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+    assert lib.spb_version  # loads without a GPU; no compute call is made here
+
+
+@pytest.mark.parametrize("name,bf,bias,key", [("VTML40.out", 2.0, 0.0, "m40"), ("VTML40.out", 2.0, -0.2, "m40u"),
+                                              ("VTML80.out", 8.0, -0.2, "m80")])
+def test_host_matrices_equal_oracle(name, bf, bias, key):
+    m80, m40u, m40 = Cm.mats()
+    ref = {"m80": m80, "m40u": m40u, "m40": m40}[key]
+    out = run("dumpmatrix", name, str(bf), str(bias)).stdout.split("\n")
+    assert out[0] == "ACDEFGHIKLMNPQRSTVWYX"
+    sub = np.array([[int(x) for x in out[1 + i].split()] for i in range(21)])
+    assert (sub == O.matrix_sub(ref)).all()
+    pb = np.array([float(x) for x in out[22].split()])
+    assert (pb == np.array(list(ref.pBack))).all()      # bit-identical doubles
+
+
+@pytest.mark.parametrize("db", ["targets", "qsetdb", "pref_0", "prot_result"])
+@pytest.mark.parametrize("threads", [1, 3])
+def test_db_round_trip(tmp_path, db, threads):
+    """reader -> writer: same entries per key (the reference's multi-threaded writers leave them in any order),
+    index sorted by key, dbtype preserved"""
+    src = os.path.join(GOLDEN, "config1", db)
+    dst = str(tmp_path / "copy")
+    run("dbcopy", src, dst, str(threads))
+    assert dbio.read_entries(src) == dbio.read_entries(dst)
+    assert dbio.read_dbtype(src) == dbio.read_dbtype(dst)
+    keys = [int(l.split()[0]) for l in open(dst + ".index")]
+    assert keys == sorted(keys)
+
+
+def test_workflow_argv_is_accepted():
+    out = run("showparams", "prefilter", "q", "t", "p", *PREF_FLAGS).stdout
+    assert "kmer_thr=112" in out and "max_seqs=300" in out and "pattern=11011101" in out and "seed_sub_mat=VTML80.out" in out
+    out = run("showparams", "align", "q", "t", "p", "a", *ALN_FLAGS).stdout
+    assert "evalue=200" in out and "gap_open=16" in out and "gap_extend=2" in out and "sub_mat=VTML40.out" in out
+
+
+def test_errors_like_the_reference():
+    r = run("prefilter", "q", "t", "p", "--no-such-flag", "1", ok=False)
+    assert r.returncode == 1 and "Unrecognized parameter" in r.stderr
+    r = run("showparams", "align", "q", "t", "p", "a", "--alt-ali", "3", "-a", "1", ok=False)
+    assert r.returncode == 1 and "not supported" in r.stderr
+    r = run("dbcopy", "/nonexistent/db", "/tmp/x", ok=False)
+    assert r.returncode == 1 and "Could not open" in r.stderr
+
+
+def test_no_cpu_fallback(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    r = run("prefilter", os.path.join(GOLDEN, "config1", "qsetdb"), os.path.join(GOLDEN, "config1", "targets"),
+            str(tmp_path / "pref"), *PREF_FLAGS, ok=False)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
+    assert not os.path.exists(str(tmp_path / "pref.dbtype"))
