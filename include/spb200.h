@@ -181,6 +181,21 @@ int spb_align_resident(spb_ctx *ctx, const spb_align_params *p);
 int spb_align_stats(spb_ctx *ctx, spb_align_result *out);
 int spb_align_fetch(spb_ctx *ctx, spb_align_result **out);
 
+/* ---- multi-GPU target split ------------------------------------------------------------------------
+ * MMseqs2 shards targets with --split (Prefiltering.cpp:258-362) and merges the per-split result files
+ * (mergeTargetSplits, Prefiltering.cpp:364-481).  Here every GPU prefilters all queries against its target shard
+ * (spb_prefilter_params.id_base = first global id of the shard), the per-query lists are exchanged device to device
+ * (NCCL all-to-all by query range, done by the caller) and merged on the owning GPU:
+ *   spb_prefilter_device_result   device pointers of the resident result (hits, offsets[Q+1]) for the exchange
+ *   spb_prefilter_merge_shards    d_recv = shard-major concatenation of the lists of queries q_lo..q_hi (global target
+ *                                 ids), d_counts[shard][q - q_lo] their lengths (device pointers).  The merged lists
+ *                                 (score desc, id asc) replace the resident result: empty outside the range.
+ *                                 Returns 2 if a query reaches max_seqs across shards (needs the unsplit hit stream
+ *                                 for the reference's truncation order; use query split for that batch). */
+int spb_prefilter_device_result(spb_ctx *ctx, spb_hit **d_hits, uint64_t **d_offsets, uint64_t *n_hits);
+int spb_prefilter_merge_shards(spb_ctx *ctx, uint32_t q_lo, uint32_t q_hi, const spb_hit *d_recv, uint64_t n_recv,
+                               const uint32_t *d_counts, uint32_t n_shards, int32_t max_seqs);
+
 /* ---- host pre-step (CPU, as in the reference) -----------------------------------------------------
  * tantan repeat masking of the target residues before the index build (--mask 1; call site
  * M/prefiltering/IndexBuilder.cpp:137-149, M/commons/tantan.cpp).  prob = joint probabilities P_ab [21][21] and

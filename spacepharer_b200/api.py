@@ -180,6 +180,18 @@ class Searcher:
             self.lib.spb_free_prefilter_result(r)
         return off, hits, stats
 
+    def prefilter_device_result(self):
+        """(device pointer of the resident spb_hit[n] array, device pointer of offsets uint64[Q+1], n) -- for the
+        device-to-device exchange of the multi-GPU target split"""
+        hp, op, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        capi.check(self.lib.spb_prefilter_device_result(self.h, C.byref(hp), C.byref(op), C.byref(n)))
+        return int(hp.value or 0), int(op.value or 0), int(n.value)
+
+    def merge_shards(self, q_lo, q_hi, recv_ptr, n_recv, counts_ptr, n_shards, max_seqs=300):
+        """merge the per-shard hit lists of queries q_lo..q_hi (device pointers) into the resident result"""
+        capi.check(self.lib.spb_prefilter_merge_shards(self.h, q_lo, q_hi, C.c_void_p(recv_ptr), n_recv,
+                                                       C.c_void_p(counts_ptr), n_shards, max_seqs))
+
     def pairs_from_prefilter(self):
         capi.check(self.lib.spb_pairs_from_prefilter(self.h))
 

@@ -1249,6 +1249,69 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Target-split merge (multi-GPU): the hit lists of one query coming from the target shards are concatenated and put
+// into the final order (score desc, global id asc).  Per-target rules are shard-local, so below max-seqs the union IS
+// the unsplit list; a query reaching max-seqs would need the reference's truncation order across shards and is
+// reported instead (err = query + 1) -- the caller falls back to query split for such batches.
+// One CTA per query of the owned range; segment (s, q) of the shard-major receive buffer starts at segOff[s * nq + q].
+// ---------------------------------------------------------------------------------------------------------
+#define MG_CAP 1024
+__global__ void __launch_bounds__(128) merge_shards_kernel(const spb_hit *__restrict__ recv, const uint32_t *__restrict__ cnt,
+                                                           const uint64_t *__restrict__ segOff, uint32_t nq, uint32_t nShards,
+                                                           uint32_t qLo, const uint64_t *__restrict__ outOff, spb_hit *__restrict__ out,
+                                                           uint32_t maxSeqs, unsigned int *__restrict__ err) {
+    __shared__ uint64_t keys[MG_CAP];
+    const uint32_t q = blockIdx.x;
+    if (q >= nq) return;
+    const uint64_t o = outOff[qLo + q];
+    const uint32_t total = (uint32_t)(outOff[qLo + q + 1] - o);
+    if (total == 0) return;
+    if (total >= maxSeqs || total > MG_CAP) {
+        if (threadIdx.x == 0) atomicMax(err, qLo + q + 1);
+        return;
+    }
+    uint32_t base = 0;
+    for (uint32_t s = 0; s < nShards; s++) {
+        const uint32_t n = cnt[(size_t)s * nq + q];
+        const spb_hit *src = recv + segOff[(size_t)s * nq + q];
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const spb_hit h = src[i];
+            keys[base + i] = ((uint64_t)(0xFFFFu - (uint32_t)min(max(h.score, 0), 0xFFFF)) << 48) | ((uint64_t)h.id << 16) |
+                             (uint64_t)((uint32_t)h.diag & 0xFFFFu);
+        }
+        base += n;
+    }
+    const int np2 = next_pow2(max((int)total, 2));
+    for (int i = (int)total + threadIdx.x; i < np2; i += blockDim.x) keys[i] = ~0ull;
+    block_bitonic_sort(keys, np2, [](uint64_t a, uint64_t b) { return a < b; });
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+        const uint64_t f = keys[i];
+        spb_hit h;
+        h.id = (uint32_t)(f >> 16);
+        h.score = (int32_t)(0xFFFFu - (uint32_t)(f >> 48));
+        h.diag = (int32_t)(short)(uint16_t)(f & 0xFFFFull);
+        out[o + i] = h;
+    }
+}
+
+// totals per query of the full batch: sum over shards inside the owned range, 0 outside
+__global__ void merge_totals_kernel(const uint32_t *__restrict__ cnt, uint32_t nq, uint32_t nShards, uint32_t qLo, uint32_t Q,
+                                    uint64_t *__restrict__ totals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > Q) return;
+    uint64_t t = 0;
+    if (i >= qLo && i < qLo + nq && i < Q)
+        for (uint32_t s = 0; s < nShards; s++) t += cnt[(size_t)s * nq + (i - qLo)];
+    totals[i] = t;
+}
+
+__global__ void widen_u32_kernel(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+    if (i == n) out[i] = 0;
+}
+
 // gather per-query slices of the arena into query order
 __global__ void gather_hits_kernel(const spb_hit *__restrict__ arena, const uint64_t *__restrict__ start, const uint64_t *__restrict__ outOff,
                                    uint32_t Q, spb_hit *__restrict__ out) {
@@ -1648,4 +1711,83 @@ extern "C" int spb_prefilter(spb_ctx *c, const uint8_t *q_residues, const uint64
     if (spb_queries_set(c, q_residues, q_offsets, Q)) return 1;
     if (spb_prefilter_resident(c, p)) return 1;
     return spb_prefilter_fetch(c, out);
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// multi-GPU target split: device views of the resident result and the merge of the shard lists
+// ------------------------------------------------------------------------------------------------------
+extern "C" int spb_prefilter_device_result(spb_ctx *c, spb_hit **d_hits, uint64_t **d_offsets, uint64_t *n_hits) {
+    SPB_CHECK(c && d_hits && d_offsets && n_hits, "spb_prefilter_device_result: NULL argument");
+    SPB_CHECK(c->have_pref, "spb_prefilter_device_result: no resident prefilter result");
+    *d_hits = c->d_hits.as<spb_hit>();
+    *d_offsets = c->d_hitoff.as<uint64_t>();
+    *n_hits = c->n_hits;
+    return 0;
+}
+
+extern "C" int spb_prefilter_merge_shards(spb_ctx *c, uint32_t q_lo, uint32_t q_hi, const spb_hit *d_recv, uint64_t n_recv,
+                                          const uint32_t *d_counts, uint32_t n_shards, int32_t max_seqs) {
+    SPB_CHECK(c && (d_counts || q_hi == q_lo), "spb_prefilter_merge_shards: NULL argument");
+    SPB_CHECK(c->have_queries, "spb_prefilter_merge_shards: no resident query batch");
+    SPB_CHECK(q_lo <= q_hi && q_hi <= c->Q, "spb_prefilter_merge_shards: query range %u..%u outside the batch of %u", q_lo, q_hi, c->Q);
+    SPB_CHECK(n_shards >= 1 && max_seqs >= 1, "spb_prefilter_merge_shards: bad shard count / max_seqs");
+    SPB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const uint32_t Q = c->Q, nq = q_hi - q_lo;
+    const size_t nSeg = (size_t)n_shards * nq;
+    SPB_CUDA(cudaEventRecord(c->ev2, st));
+    // s_a: segment counts widened u64[nSeg+1], s_b: segment offsets u64[nSeg+1], s_c: totals u64[Q+1], s_f: error flag
+    if (c->s_a.ensure((nSeg + 1) * 8) || c->s_b.ensure((nSeg + 1) * 8) || c->s_c.ensure(((size_t)Q + 1) * 8) || c->s_f.ensure(512) ||
+        c->d_hitoff.ensure(((size_t)Q + 1) * 8)) return 1;
+    SPB_CUDA(cudaMemsetAsync(c->s_f.p, 0, 16, st));
+    size_t tmpBytes = 0;
+    if (nSeg) {
+        widen_u32_kernel<<<(unsigned)((nSeg + 1 + 255) / 256), 256, 0, st>>>(d_counts, nSeg, c->s_a.as<uint64_t>());
+        SPB_CUDA(cudaGetLastError()); c->n_launches++;
+        SPB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, c->s_a.as<uint64_t>(), c->s_b.as<uint64_t>(), (int)(nSeg + 1), st));
+        if (c->s_cub.ensure(tmpBytes)) return 1;
+        SPB_CUDA(cub::DeviceScan::ExclusiveSum(c->s_cub.p, tmpBytes, c->s_a.as<uint64_t>(), c->s_b.as<uint64_t>(), (int)(nSeg + 1), st));
+    }
+    merge_totals_kernel<<<(Q + 1 + 255) / 256, 256, 0, st>>>(d_counts, nq, n_shards, q_lo, Q, c->s_c.as<uint64_t>());
+    SPB_CUDA(cudaGetLastError()); c->n_launches++;
+    SPB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, c->s_c.as<uint64_t>(), c->d_hitoff.as<uint64_t>(), (int)(Q + 1), st));
+    if (c->s_cub.ensure(tmpBytes)) return 1;
+    SPB_CUDA(cub::DeviceScan::ExclusiveSum(c->s_cub.p, tmpBytes, c->s_c.as<uint64_t>(), c->d_hitoff.as<uint64_t>(), (int)(Q + 1), st));
+    uint64_t nHits = 0;
+    SPB_CUDA(cudaMemcpyAsync(&nHits, c->d_hitoff.as<uint64_t>() + Q, 8, cudaMemcpyDeviceToHost, st));
+    SPB_CUDA(cudaStreamSynchronize(st));
+    SPB_CHECK(nHits == n_recv, "spb_prefilter_merge_shards: the counts add up to %llu hits but %llu were received",
+              (unsigned long long)nHits, (unsigned long long)n_recv);
+    // the receive buffer may alias nothing of ours; the merged lists replace the resident result
+    DevBuf merged;
+    if (merged.ensure(std::max<uint64_t>(nHits, 1) * sizeof(spb_hit))) return 1;
+    unsigned int h_err = 0;
+    if (nq && nHits) {
+        merge_shards_kernel<<<nq, 128, 0, st>>>(d_recv, d_counts, c->s_b.as<uint64_t>(), nq, n_shards, q_lo, c->d_hitoff.as<uint64_t>(),
+                                                merged.as<spb_hit>(), (uint32_t)max_seqs, reinterpret_cast<unsigned int *>(c->s_f.p));
+        cudaError_t e = cudaGetLastError(); c->n_launches++;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&h_err, c->s_f.p, 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { merged.release(); spb::set_error("spb_prefilter_merge_shards: %s", cudaGetErrorString(e)); return 1; }
+    }
+    if (h_err) {
+        merged.release();
+        spb::set_error("spb_prefilter_merge_shards: query %u reaches max-seqs (%d) across the target shards; its truncation order needs the "
+                       "unsplit hit stream -- run this batch with query split", h_err - 1, max_seqs);
+        return 2;
+    }
+    c->d_hits.release();
+    c->d_hits = merged;          // ownership moves to the context
+    c->n_hits = nHits;
+    SPB_CUDA(cudaEventRecord(c->ev3, st));
+    SPB_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    SPB_CUDA(cudaEventElapsedTime(&ms, c->ev2, c->ev3));
+    c->pref_stats.n_hits = nHits;
+    c->pref_stats.total_ms += ms;
+    c->have_pref = true;
+    c->have_pairs = false;
+    c->have_aln = false;
+    return 0;
 }

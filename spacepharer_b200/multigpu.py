@@ -1,21 +1,23 @@
-"""One-process-per-GPU driver of the search step (target split like MMseqs2 --split, or query replicas).
+"""One-process-per-GPU driver of the search step (target split like MMseqs2 --split, or query split).
 
 Mirrors how the reference distributes `prefilter`/`align` (M/prefiltering/Prefiltering.cpp:258-362,559-643 target /
 query split, M/alignment/Alignment.cpp:226-249): every rank owns one `Searcher` (one CUDA context object) and
 
   split_mode "target": rank r indexes targets [from_r, to_r) chosen like DBReader::decomposeDomainByAminoAcid
       (M/commons/DBReader.cpp:1171-1213); queries are replicated; every rank prefilters all queries against its shard
-      and emits its candidates with their truncation keys; candidates of query range r are sent to rank r over NCCL
-      (all_to_all_single, device buffers), merged there to exactly the unsplit top-max-seqs list, and aligned there
-      against the replicated (unmasked) target residues.  Unlike the reference's lossy --split heuristic
-      (Prefiltering.cpp:343-346) the merged result equals the unsplit run.
+      (tie-break bins use global ids: id_base = from_r); the per-query hit lists of query range r are sent to rank r
+      device to device (NCCL all_to_all_single over NVLink), merged there (spb_prefilter_merge_shards) and aligned
+      there against the replicated unmasked target residues with the whole-DB residue count in the E-value.  The
+      per-target rules of the prefilter are shard-local, so the merged list equals the UNSPLIT list (unlike the
+      reference's lossy --split heuristic, Prefiltering.cpp:343-346); a query reaching max-seqs across shards is
+      reported by the library (its truncation order needs the unsplit hit stream) and the batch is redone in
+      query-split mode.
   split_mode "query": every rank holds the full index and processes its own slice of the query batch; no collective
       on the data path.
 
-torch / torch.distributed are plumbing only (process group, NCCL); all arithmetic is in libspb200's kernels.
+torch / torch.distributed are plumbing only (process group, NCCL, device buffers of the exchange); all arithmetic is in
+libspb200's kernels.
 """
-import ctypes as C
-
 import numpy as np
 
 from . import api, capi
@@ -48,13 +50,64 @@ def query_ranges(Q, world):
     return [((Q * r) // world, (Q * (r + 1)) // world) for r in range(world)]
 
 
+def exchange_hit_lists(hits, offsets, ranges, rank, group=None):
+    """All-to-all of per-query hit lists by query range (backend agnostic: NCCL on device tensors, gloo on CPU tensors).
+
+    hits: int32 tensor [n, 3] (global id, score, diag), all queries of the batch in query order;
+    offsets: int64 tensor [Q+1].  Returns (recv int32 [m, 3] shard-major, counts int32 [world * nq] shard-major)
+    for this rank's query range."""
+    import torch
+    import torch.distributed as dist
+    G = len(ranges)
+    bounds = torch.tensor([lo for lo, _ in ranges] + [ranges[-1][1]], dtype=torch.int64, device=offsets.device)
+    cut = offsets[bounds].cpu().tolist()                      # hit offsets at the range boundaries (one small D2H)
+    send_rows = [cut[r + 1] - cut[r] for r in range(G)]
+    sc = torch.tensor(send_rows, dtype=torch.int64, device=hits.device)
+    rc = torch.empty_like(sc)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_rows = rc.cpu().tolist()
+    lo, hi = ranges[rank]
+    nq = hi - lo
+    cnt_all = (offsets[1:] - offsets[:-1]).to(torch.int32).contiguous()
+    cnt_recv = torch.empty(G * nq, dtype=torch.int32, device=hits.device)
+    dist.all_to_all_single(cnt_recv, cnt_all, output_split_sizes=[nq] * G, input_split_sizes=[h - l for l, h in ranges],
+                           group=group)
+    recv = torch.empty((sum(recv_rows), 3), dtype=torch.int32, device=hits.device)
+    dist.all_to_all_single(recv, hits.contiguous(), output_split_sizes=recv_rows, input_split_sizes=send_rows, group=group)
+    return recv, cnt_recv
+
+
+def merge_hit_lists_reference(recv, cnt_recv, world, nq):
+    """numpy restatement of spb_prefilter_merge_shards (tests): per query concatenate the shard segments and sort by
+    (score desc, id asc).  Returns (offsets int64[nq+1], hits int32[m, 3])."""
+    recv = np.asarray(recv).reshape(-1, 3)
+    cnt = np.asarray(cnt_recv).reshape(world, nq).astype(np.int64)
+    seg = np.zeros(world * nq + 1, dtype=np.int64)
+    seg[1:] = np.cumsum(cnt.reshape(-1))
+    out, off = [], [0]
+    for q in range(nq):
+        rows = np.concatenate([recv[seg[s * nq + q]:seg[s * nq + q + 1]] for s in range(world)]) if world else recv[:0]
+        order = np.lexsort((rows[:, 0], -rows[:, 1]))
+        out.append(rows[order])
+        off.append(off[-1] + len(rows))
+    return np.array(off, dtype=np.int64), (np.concatenate(out) if out else recv[:0])
+
+
+class _DevView:
+    """zero-copy torch view of library-owned device memory (__cuda_array_interface__)"""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
 class ShardedSearcher:
-    def __init__(self, device=0, rank=0, world=1, split_mode="target", **kw):
+    def __init__(self, device=0, rank=0, world=1, split_mode="query", **kw):
         self.rank, self.world, self.split_mode = rank, world, split_mode
         self.searcher = api.Searcher(device=device, **kw)
         self.device = device
         self.shard = None
         self.Q = 0
+        self.q_lo = 0
 
     def close(self):
         self.searcher.close()
@@ -111,7 +164,8 @@ class ShardedSearcher:
         return dict(prefilter=pst, align=ast)
 
     def search_host(self, qres, qoff, db_res_count, **kw):
-        """Public end-to-end call: host query buffers in, sorted alignment rows + CIGARs out (host)."""
+        """Public end-to-end call: host query buffers in, sorted alignment rows + CIGARs out (host).
+        Rows carry batch-global query indices; every rank returns the rows of the queries it owns."""
         self.set_queries(qres, qoff)
         st = self.step_resident(db_res_count, **kw)
         off, rows, cig, _ = self.searcher.align_fetch()
@@ -121,32 +175,26 @@ class ShardedSearcher:
         return dict(offsets=off, rows=rows, cigar=cig, stats=st, q_lo=self.q_lo,
                     d2h_bytes=off.nbytes + rows.nbytes + len(cig))
 
-    # ---- target split: candidate exchange + merge ---------------------------------------------
+    # ---- target split: hit-list exchange + merge -----------------------------------------------
     def _prefilter_target_split(self, pk):
         import torch
-        import torch.distributed as dist
         s = self.searcher
         frm, _ = self.shard
         Q, G = self.Q, self.world
-        pst = s.prefilter_candidates_resident(id_base=frm, global_targets=self.T, **pk)
-        cands, coff = s.candidates_view()            # torch views of library-owned device memory
-        ranges = query_ranges(Q, G)
-        bounds = torch.tensor([lo for lo, _ in ranges] + [Q], device=cands.device, dtype=torch.int64)
-        cut = coff[bounds].cpu().tolist()            # candidate offsets at the range boundaries (one small D2H)
-        send_counts = [cut[r + 1] - cut[r] for r in range(G)]
-        sc = torch.tensor(send_counts, dtype=torch.int64, device=cands.device)
-        rc = torch.empty_like(sc)
-        dist.all_to_all_single(rc, sc)
-        recv_counts = rc.cpu().tolist()
+        pst = s.prefilter_resident(id_base=frm, **pk)
+        hp, op, n = s.prefilter_device_result()
+        dev = torch.device("cuda", self.device)
+        stream = torch.cuda.ExternalStream(s.stream_ptr(), device=dev)
+        with torch.cuda.stream(stream):
+            offsets = torch.as_tensor(_DevView(op, (Q + 1,), "<i8"), device=dev)
+            hits = (torch.as_tensor(_DevView(hp, (n, 3), "<i4"), device=dev) if n
+                    else torch.empty((0, 3), dtype=torch.int32, device=dev)).clone()
+            hits[:, 0] += frm                         # shard-local -> global target ids
+            ranges = query_ranges(Q, G)
+            recv, cnt_recv = exchange_hit_lists(hits, offsets, ranges, self.rank)
+            stream.synchronize()
         lo, hi = ranges[self.rank]
-        nq = hi - lo
-        # per-query counts of my range from every rank
-        cnt_all = (coff[1:] - coff[:-1]).to(torch.int32)
-        cnt_recv = torch.empty(G * nq, dtype=torch.int32, device=cands.device)
-        dist.all_to_all_single(cnt_recv, cnt_all, output_split_sizes=[nq] * G,
-                               input_split_sizes=[h - l for l, h in ranges])
-        recv = torch.empty((sum(recv_counts), cands.shape[1]), dtype=cands.dtype, device=cands.device)
-        dist.all_to_all_single(recv, cands, output_split_sizes=recv_counts, input_split_sizes=send_counts)
-        mst = s.merge_candidates(lo, hi, recv, cnt_recv, G, **pk)
-        pst.update(merge_ms=mst["merge_ms"], n_hits=mst["n_hits"])
+        s.merge_shards(lo, hi, recv.data_ptr(), recv.shape[0], cnt_recv.data_ptr(), G, pk.get("max_seqs", 300))
+        pst["n_hits_shard"] = pst["n_hits"]
+        pst["n_hits"] = int(recv.shape[0])
         return pst
