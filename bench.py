@@ -14,8 +14,11 @@ A "step" is one pass of the search (prefilter -> align) over the whole query bat
             measured HBM peak (MEASURED_PEAKS.json)
   cpu_baseline / --impl reference: the CPU oracle port (oracle/, OpenMP over queries like the reference) on a
             bounded sample of the same workload on this host's cores.
-N > 1 (torchrun): targets sharded across ranks like MMseqs2 --split (target split), queries replicated, per-query
-candidate lists exchanged over NCCL and merged to the unsplit result; `--split-mode query` runs query replicas.
+N > 1 (torchrun): `--split-mode query` (default): every rank holds the whole index (1.7 GB of 180 GB) and searches its
+own slice of the batch, no data-path collective; per-GPU work is fixed (10 000 spacers per GPU), so scaling is "weak".
+`--split-mode target`: targets sharded across ranks like MMseqs2 --split, queries replicated, per-query hit lists
+exchanged device to device over NCCL and merged to the unsplit result (strong scaling; the k-mer lookups per query do
+not shrink with the shard, so this mode is about capacity, not speed -- DESIGN.md 6).
 """
 import argparse
 import json
@@ -43,23 +46,24 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--spacers", type=int, default=10000)
     ap.add_argument("--genomes", type=int, default=8000)
-    ap.add_argument("--split-mode", default="target", choices=["target", "query"])
+    ap.add_argument("--split-mode", default="query", choices=["target", "query"])
     ap.add_argument("--cpu-sample-spacers", type=int, default=0, help="spacers in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mask", action="store_true", help="skip the tantan host pre-step (--mask 0)")
     return ap.parse_args()
 
 
-def workload(args):
+def workload(args, world=1):
+    """`world` > 1 with query split: the batch grows with the number of GPUs (weak scaling, 10 000 spacers per GPU)."""
     from spacepharer_b200 import synth
     tres, toff, _ = synth.make_targets(n_genomes=args.genomes)
-    qres, qoff, _ = synth.make_query_frames(args.spacers, tres, toff)
+    qres, qoff, _ = synth.make_query_frames(args.spacers * world, tres, toff)
     return tres, toff, qres, qoff
 
 
-def workload_name(args, Q, T, nres):
+def workload_name(args, Q, T, nres, spacers=None):
     return ("%d synthetic spacers (25-45 nt, six-frame, %d frames) vs synthetic GenBank_phage_2018_09-shaped ORF setDB "
-            "(%d genomes, %d ORFs, %d aa); predictmatch search parameters" % (args.spacers, Q, args.genomes, T, nres))
+            "(%d genomes, %d ORFs, %d aa); predictmatch search parameters" % (spacers or args.spacers, Q, args.genomes, T, nres))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -78,7 +82,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -188,7 +192,7 @@ def run_reference(args):
     r = cpu_reference_run(args, tres, toff, qres, qoff, steps, warm, sample, masked)
     Q = len(qoff) - 1
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": workload_name(args, Q, len(toff) - 1, int(toff[-1])),
                        "note": "CPU port of the reference path (oracle/, scalar C + OpenMP); each step = the bounded sample"},
@@ -232,7 +236,8 @@ def run_ours(args):
     if args.gpus != world and rank == 0:
         print("bench.py: warning: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
 
-    tres, toff, qres, qoff = workload(args)
+    weak = world > 1 and args.split_mode == "query"
+    tres, toff, qres, qoff = workload(args, world if weak else 1)
     T, Q = len(toff) - 1, len(qoff) - 1
     db_res = int(toff[-1])
     t0 = time.perf_counter()
@@ -286,13 +291,15 @@ def run_ours(args):
 
     # ---- end-to-end leg through the public API with host buffers ----
     for _ in range(min(2, args.warmup)):
-        eng.search_host(q_np, o_np, db_res)
+        eng.search_host(q_np, o_np, db_res, copy=False)["view"].close()
     barrier()
     t0 = time.perf_counter()
     d2h = 0
     for k in range(args.steps):
-        res = eng.search_host(q_np, o_np, db_res)
+        res = eng.search_host(q_np, o_np, db_res, copy=False)     # rows + CIGARs land in pinned host buffers of the library
         d2h = res["d2h_bytes"]
+        n_rows_e2e = len(res["rows"])
+        res["view"].close()
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
@@ -310,9 +317,9 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": q_total * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if args.split_mode == "target" else "weak", "vs_baseline": None, "dtype": "int32",
+            "scaling": "weak" if (weak or world == 1) else "strong", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic",
-            "config": {"workload": workload_name(args, Q, T, db_res), "queries_per_step": q_total,
+            "config": {"workload": workload_name(args, Q, T, db_res, args.spacers * (world if weak else 1)), "queries_per_step": q_total,
                        "split_mode": args.split_mode if world > 1 else "none",
                        "l2": "256 MB memset between timed steps (outside the per-step CUDA events); index %.2f GB > L2"
                              % (ist["bytes_device"] / 1e9),
@@ -323,7 +330,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(q_np.nbytes + o_np.nbytes), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "prefilter_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "prefilter_team_kernel<1> + <8>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                          "algo_bytes_per_launch": float(np.mean(pk_bytes)), "kernel_ms": kms,
                          "share_of_step": kms / (dev_ms / args.steps)},

@@ -44,6 +44,51 @@ def gumbel_for(matrix_name, gap_open, gap_extend):
     return GUMBEL[key]
 
 
+def _copy_struct_array(ptr, n, ctype):
+    """one copy of n C structs at `ptr` into a numpy structured array"""
+    dt = np.dtype(ctype)
+    if not n:
+        return np.zeros(0, dtype=dt)
+    buf = (C.c_char * (n * dt.itemsize)).from_address(C.addressof(ptr.contents))
+    return np.frombuffer(buf, dtype=dt).copy()
+
+
+def _view(ptr, n, dtype):
+    """zero-copy numpy view of n items at a ctypes pointer (valid while the owning result is alive)"""
+    dt = np.dtype(dtype)
+    if not n:
+        return np.zeros(0, dtype=dt)
+    addr = C.cast(ptr, C.c_void_p).value
+    return np.frombuffer((C.c_char * (n * dt.itemsize)).from_address(addr), dtype=dt)
+
+
+class AlignResultView:
+    """Host result of spb_align_fetch without extra copies: `offsets`, `rows`, `cigar` are views of the library's pinned
+    result buffers; they are valid until close() (or garbage collection) hands the buffers back."""
+
+    def __init__(self, lib, r):
+        self._lib, self._r = lib, r
+        R = r.contents
+        self.n_queries = int(R.n_queries)
+        self.offsets = _view(R.offsets, self.n_queries + 1, np.uint64)
+        self.rows = _view(R.rows, int(R.n_rows), capi.Aln)
+        self.cigar = _view(R.cigar_ops, int(R.n_cigar), np.uint8)
+        self.stats = Searcher._aln_stats(R)
+        self.nbytes = self.offsets.nbytes + self.rows.nbytes + self.cigar.nbytes
+
+    def close(self):
+        if self._r is not None:
+            self.offsets = self.rows = self.cigar = None
+            self._lib.spb_free_align_result(self._r)
+            self._r = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _u8(a):
     return a.ctypes.data_as(C.POINTER(C.c_ubyte))
 
@@ -171,10 +216,9 @@ class Searcher:
         try:
             R = r.contents
             Q = int(R.n_queries)
-            off = np.ctypeslib.as_array(R.offsets, shape=(Q + 1,)).copy()
+            off = _view(R.offsets, Q + 1, np.uint64).copy()
             n = int(R.n_hits)
-            dt = np.dtype(capi.Hit)
-            hits = np.frombuffer(C.string_at(R.hits, n * dt.itemsize), dtype=dt).copy() if n else np.zeros(0, dtype=dt)
+            hits = _copy_struct_array(R.hits, n, capi.Hit)
             stats = self._pref_stats(R)
         finally:
             self.lib.spb_free_prefilter_result(r)
@@ -212,16 +256,21 @@ class Searcher:
         capi.check(self.lib.spb_align_stats(self.h, C.byref(R)))
         return self._aln_stats(R)
 
+    def align_fetch_view(self):
+        """like align_fetch but zero-copy: returns an AlignResultView (close it when done)"""
+        r = C.POINTER(capi.AlignResult)()
+        capi.check(self.lib.spb_align_fetch(self.h, C.byref(r)))
+        return AlignResultView(self.lib, r)
+
     def align_fetch(self):
         r = C.POINTER(capi.AlignResult)()
         capi.check(self.lib.spb_align_fetch(self.h, C.byref(r)))
         try:
             R = r.contents
             Q = int(R.n_queries)
-            off = np.ctypeslib.as_array(R.offsets, shape=(Q + 1,)).copy()
+            off = _view(R.offsets, Q + 1, np.uint64).copy()
             n = int(R.n_rows)
-            dt = np.dtype(capi.Aln)
-            rows = np.frombuffer(C.string_at(R.rows, n * dt.itemsize), dtype=dt).copy() if n else np.zeros(0, dtype=dt)
+            rows = _copy_struct_array(R.rows, n, capi.Aln)
             cig = C.string_at(R.cigar_ops, int(R.n_cigar)) if R.n_cigar else b""
             stats = self._aln_stats(R)
         finally:
@@ -253,10 +302,9 @@ class Searcher:
         capi.check(self.lib.spb_prefilter(self.h, _u8(qres), _u64(qoff), Q, C.byref(p), C.byref(r)))
         try:
             R = r.contents
-            off = np.ctypeslib.as_array(R.offsets, shape=(Q + 1,)).copy()
+            off = _view(R.offsets, Q + 1, np.uint64).copy()
             n = int(R.n_hits)
-            dt = np.dtype(capi.Hit)
-            hits = np.frombuffer(C.string_at(R.hits, n * dt.itemsize), dtype=dt).copy() if n else np.zeros(0, dtype=dt)
+            hits = _copy_struct_array(R.hits, n, capi.Hit)
             stats = self._pref_stats(R)
         finally:
             self.lib.spb_free_prefilter_result(r)
@@ -289,10 +337,9 @@ class Searcher:
                                       pair_targets.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(p), C.byref(r)))
         try:
             R = r.contents
-            off = np.ctypeslib.as_array(R.offsets, shape=(Q + 1,)).copy()
+            off = _view(R.offsets, Q + 1, np.uint64).copy()
             n = int(R.n_rows)
-            dt = np.dtype(capi.Aln)
-            rows = np.frombuffer(C.string_at(R.rows, n * dt.itemsize), dtype=dt).copy() if n else np.zeros(0, dtype=dt)
+            rows = _copy_struct_array(R.rows, n, capi.Aln)
             cig = C.string_at(R.cigar_ops, int(R.n_cigar)) if R.n_cigar else b""
             stats = self._aln_stats(R)
         finally:

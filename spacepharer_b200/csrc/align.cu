@@ -16,7 +16,10 @@
 
 #include <cub/cub.cuh>
 
+#include <stdlib.h>
+
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "common.cuh"
@@ -609,6 +612,12 @@ __global__ void tb_size_kernel(const PairOut *__restrict__ out, const uint32_t *
     cigSz[k] = (uint64_t)(ql + dl + 2);
 }
 
+__global__ void count_widen_kernel(const uint32_t *__restrict__ cnt, uint32_t Q, uint64_t *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Q) out[i] = cnt[i];
+    if (i == Q) out[i] = 0;
+}
+
 __global__ void pack_rows_kernel(const PairOut *__restrict__ out, const uint32_t *__restrict__ acc, uint32_t nAcc,
                                  const uint32_t *__restrict__ pairQ, const uint32_t *__restrict__ pairT, spb_aln *__restrict__ rows) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -630,6 +639,48 @@ __global__ void pack_rows_kernel(const PairOut *__restrict__ out, const uint32_t
     rows[k] = r;
 }
 
+// rows per query (accepted pairs arrive grouped by query, so row k of the packed array already lies in its query's segment)
+__global__ void row_count_kernel(const uint32_t *__restrict__ acc, uint32_t nAcc, const uint32_t *__restrict__ pairQ,
+                                 uint32_t *__restrict__ cnt) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nAcc) atomicAdd(&cnt[pairQ[acc[k]]], 1u);
+}
+
+// Per query order of Matcher::compareHits (M/alignment/Matcher.h:156-167): E-value asc (double), score desc, target length asc,
+// target key asc.  One warp per query, rank sort from the packed rows into the output array.
+__device__ __forceinline__ bool row_before(double ea, int ba, uint64_t la, uint32_t ka, double eb, int bb, uint64_t lb, uint32_t kb) {
+    if (ea != eb) return ea < eb;
+    if (ba != bb) return ba > bb;
+    if (la != lb) return la < lb;
+    return ka < kb;
+}
+
+__global__ void sort_rows_kernel(const spb_aln *__restrict__ in, const uint64_t *__restrict__ rowOff, uint32_t Q,
+                                 const uint64_t *__restrict__ toff, const uint32_t *__restrict__ tkeys, spb_aln *__restrict__ out) {
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= Q) return;
+    const int lane = threadIdx.x & 31;
+    const uint64_t o = rowOff[q];
+    const uint32_t n = (uint32_t)(rowOff[q + 1] - o);
+    for (uint32_t i = lane; i < n; i += 32) {
+        const spb_aln r = in[o + i];
+        const uint64_t li = toff[r.target + 1] - toff[r.target];
+        const uint32_t ki = tkeys[r.target];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < n; j++) {
+            if (j == i) continue;
+            const spb_aln &x = in[o + j];
+            const uint32_t tj = x.target;
+            const uint64_t lj = toff[tj + 1] - toff[tj];
+            const uint32_t kj = tkeys[tj];
+            // equal keys (the same target listed twice for a query) keep their input order
+            if (row_before(x.eval, x.bits, lj, kj, r.eval, r.bits, li, ki) ||
+                (j < i && !row_before(r.eval, r.bits, li, ki, x.eval, x.bits, lj, kj))) rank++;
+        }
+        out[o + rank] = r;
+    }
+}
+
 }  // namespace spb
 
 using namespace spb;
@@ -639,7 +690,7 @@ extern "C" int spb_align_set_targets(spb_ctx *c, const uint8_t *residues, const 
     SPB_CHECK(c && residues && offsets, "spb_align_set_targets: NULL argument");
     SPB_CUDA(cudaSetDevice(c->device));
     const uint64_t N = offsets[T];
-    if (c->d_ares.ensure(N + 64) || c->d_aoff.ensure(((size_t)T + 1) * 8)) return 1;
+    if (c->d_ares.ensure(N + 64) || c->d_aoff.ensure(((size_t)T + 1) * 8) || c->d_akeys.ensure((size_t)T * 4 + 4)) return 1;
     SPB_CUDA(cudaMemcpyAsync(c->d_ares.p, residues, N, cudaMemcpyHostToDevice, c->stream));
     SPB_CUDA(cudaMemcpyAsync(c->d_aoff.p, offsets, ((size_t)T + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     SPB_CUDA(cudaStreamSynchronize(c->stream));
@@ -650,17 +701,27 @@ extern "C" int spb_align_set_targets(spb_ctx *c, const uint8_t *residues, const 
     for (uint32_t i = 0; i < T; i++) c->a_maxlen = std::max<uint64_t>(c->a_maxlen, offsets[i + 1] - offsets[i]);
     c->h_akeys.resize(T);
     for (uint32_t i = 0; i < T; i++) c->h_akeys[i] = keys ? keys[i] : i;
+    if (T) SPB_CUDA(cudaMemcpy(c->d_akeys.p, c->h_akeys.data(), (size_t)T * 4, cudaMemcpyHostToDevice));
     c->have_aln_targets = true;
     c->have_aln = false;
     return 0;
 }
 
+// results are boxed: the public struct first, then the context whose pinned staging blocks it points into
+struct AlignResultBox {
+    spb_align_result pub;
+    spb_ctx *owner;
+};
+
 extern "C" void spb_free_align_result(spb_align_result *r) {
     if (!r) return;
-    free(r->offsets);
-    free(r->rows);
-    free(r->cigar_ops);
-    free(r);
+    AlignResultBox *box = reinterpret_cast<AlignResultBox *>(r);
+    if (box->owner) {
+        box->owner->pin_release(r->offsets);
+        box->owner->pin_release(r->rows);
+        box->owner->pin_release(r->cigar_ops);
+    }
+    free(box);
 }
 
 // pairs resident in c->d_pairoff (u64[Q+1]) / c->d_pairT (u32[n_pairs]); results stay in c->d_pairout / d_acc / d_cig
@@ -940,43 +1001,65 @@ extern "C" int spb_align_fetch(spb_ctx *c, spb_align_result **out) {
     SPB_CHECK(c && out, "spb_align_fetch: NULL argument");
     SPB_CHECK(c->have_aln, "spb_align_fetch: no resident alignment result");
     SPB_CUDA(cudaSetDevice(c->device));
+    const auto t_begin = std::chrono::steady_clock::now();
     *out = nullptr;
     cudaStream_t st = c->stream;
     const uint32_t Q = c->Q;
     const uint32_t nAcc = (uint32_t)c->n_acc;
-    spb_align_result *res = (spb_align_result *)calloc(1, sizeof(spb_align_result));
+    AlignResultBox *box = (AlignResultBox *)calloc(1, sizeof(AlignResultBox));
+    SPB_CHECK(box != nullptr, "spb_align_fetch: out of memory");
+    box->owner = c;
+    spb_align_result *res = &box->pub;
     *res = c->aln_stats;
-    res->offsets = (uint64_t *)calloc((size_t)Q + 1, sizeof(uint64_t));
-    res->rows = (spb_aln *)calloc(std::max<size_t>(nAcc, 1), sizeof(spb_aln));
-    res->cigar_ops = (char *)malloc(c->n_cigar + 1);
+    // results are staged in pinned blocks of the context (asynchronous, full-speed D2H); they stay valid until
+    // spb_free_align_result -- free results before destroying the context
+    res->offsets = (uint64_t *)c->pin_acquire(((size_t)Q + 1) * sizeof(uint64_t));
+    res->rows = (spb_aln *)c->pin_acquire(std::max<size_t>(nAcc, 1) * sizeof(spb_aln));
+    res->cigar_ops = (char *)c->pin_acquire(c->n_cigar + 1);
+    if (!res->offsets || !res->rows || !res->cigar_ops) { spb_free_align_result(res); return 1; }
     res->n_cigar = c->n_cigar;
     res->n_rows = nAcc;
-    if (nAcc) {
-        if (c->s_g.ensure((size_t)nAcc * sizeof(spb_aln))) { spb_free_align_result(res); return 1; }
+    // scratch: s_g packed rows, s_h sorted rows, s_i row counts u32[Q+1] + u64[Q+1] widened, s_b row offsets u64[Q+1]
+    if (c->s_g.ensure(std::max<size_t>(nAcc, 1) * sizeof(spb_aln)) || c->s_h.ensure(std::max<size_t>(nAcc, 1) * sizeof(spb_aln)) ||
+        c->s_i.ensure(((size_t)Q + 1) * 12 + 64) || c->s_b.ensure(((size_t)Q + 1) * 8 + 64)) { spb_free_align_result(res); return 1; }
+    uint32_t *cnt32 = c->s_i.as<uint32_t>();
+    uint64_t *cnt64 = reinterpret_cast<uint64_t *>(c->s_i.as<unsigned char>() + (((size_t)Q + 1) * 4 + 15) / 16 * 16);
+    uint64_t *rowOff = c->s_b.as<uint64_t>();
+    cudaError_t e = cudaMemsetAsync(cnt32, 0, ((size_t)Q + 1) * 4, st);
+    if (e == cudaSuccess && nAcc) {
+        row_count_kernel<<<(nAcc + 255) / 256, 256, 0, st>>>(c->d_acc.as<uint32_t>(), nAcc, c->d_pairQ.as<uint32_t>(), cnt32);
+        e = cudaGetLastError(); c->n_launches++;
+    }
+    if (e == cudaSuccess) {
+        count_widen_kernel<<<(Q + 1 + 255) / 256, 256, 0, st>>>(cnt32, Q, cnt64);
+        e = cudaGetLastError(); c->n_launches++;
+    }
+    size_t tmpBytes = 0;
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, cnt64, rowOff, (int)(Q + 1), st);
+    if (e == cudaSuccess && c->s_cub.ensure(tmpBytes)) { spb_free_align_result(res); return 1; }
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(c->s_cub.p, tmpBytes, cnt64, rowOff, (int)(Q + 1), st);
+    if (e == cudaSuccess && nAcc) {
         pack_rows_kernel<<<(nAcc + 255) / 256, 256, 0, st>>>(c->d_pairout.as<PairOut>(), c->d_acc.as<uint32_t>(), nAcc,
                                                              c->d_pairQ.as<uint32_t>(), c->d_pairT.as<uint32_t>(), c->s_g.as<spb_aln>());
-        cudaError_t e = cudaGetLastError(); c->n_launches++;
-        if (e == cudaSuccess) e = cudaMemcpyAsync(res->rows, c->s_g.p, (size_t)nAcc * sizeof(spb_aln), cudaMemcpyDeviceToHost, st);
+        e = cudaGetLastError(); c->n_launches++;
+        if (e == cudaSuccess) {
+            sort_rows_kernel<<<(Q + 3) / 4, 128, 0, st>>>(c->s_g.as<spb_aln>(), rowOff, Q, c->d_aoff.as<uint64_t>(), c->d_akeys.as<uint32_t>(),
+                                                          c->s_h.as<spb_aln>());
+            e = cudaGetLastError(); c->n_launches++;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(res->rows, c->s_h.p, (size_t)nAcc * sizeof(spb_aln), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess && c->n_cigar) e = cudaMemcpyAsync(res->cigar_ops, c->d_cig.p, c->n_cigar, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) {
-            spb_free_align_result(res);
-            spb::set_error("spb_align_fetch: %s", cudaGetErrorString(e));
-            return 1;
-        }
-        // rows arrive grouped by query (pair order); per query sort like Matcher::compareHits (Matcher.h:156-167)
-        for (uint32_t k = 0; k < nAcc; k++) res->offsets[res->rows[k].query + 1]++;
-        for (uint32_t i = 0; i < Q; i++) res->offsets[i + 1] += res->offsets[i];
-        for (uint32_t qi = 0; qi < Q; qi++) {
-            if (res->offsets[qi + 1] - res->offsets[qi] < 2) continue;
-            std::sort(res->rows + res->offsets[qi], res->rows + res->offsets[qi + 1], [&](const spb_aln &x, const spb_aln &y) {
-                if (x.eval != y.eval) return x.eval < y.eval;
-                if (x.bits != y.bits) return x.bits > y.bits;
-                const uint64_t lx = c->h_aoff[x.target + 1] - c->h_aoff[x.target], ly = c->h_aoff[y.target + 1] - c->h_aoff[y.target];
-                if (lx != ly) return lx < ly;
-                return c->h_akeys[x.target] < c->h_akeys[y.target];
-            });
-        }
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(res->offsets, rowOff, ((size_t)Q + 1) * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (getenv("SPB_DEBUG")) {
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        fprintf(stderr, "spb_align_fetch: %u rows, %llu CIGAR bytes, %.3f ms (pack + sort + D2H)\n", nAcc, (unsigned long long)c->n_cigar, ms);
+    }
+    if (e != cudaSuccess) {
+        spb_free_align_result(res);
+        spb::set_error("spb_align_fetch: %s", cudaGetErrorString(e));
+        return 1;
     }
     *out = res;
     return 0;

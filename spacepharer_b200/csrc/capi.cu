@@ -14,6 +14,42 @@ void set_error(const char *fmt, ...) {
 }
 }  // namespace spb
 
+// pinned staging pool: results point into these blocks until spb_free_*_result hands them back
+void *spb_ctx::pin_acquire(size_t bytes) {
+    if (bytes == 0) bytes = 1;
+    int best = -1;
+    for (size_t i = 0; i < pins.size(); i++)
+        if (!pins[i].used && pins[i].cap >= bytes && (best < 0 || pins[i].cap < pins[(size_t)best].cap)) best = (int)i;
+    if (best < 0) {
+        // replace the smallest free block instead of accumulating small ones
+        for (size_t i = 0; i < pins.size(); i++)
+            if (!pins[i].used && (best < 0 || pins[i].cap < pins[(size_t)best].cap)) best = (int)i;
+        if (best >= 0) {
+            cudaFreeHost(pins[(size_t)best].p);
+            pins[(size_t)best] = spb::PinBlock();
+        } else {
+            pins.push_back(spb::PinBlock());
+            best = (int)pins.size() - 1;
+        }
+        const size_t want = bytes + (bytes >> 2) + 4096;
+        if (cudaHostAlloc(&pins[(size_t)best].p, want, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            pins[(size_t)best].p = nullptr;
+            spb::set_error("cudaHostAlloc(%zu) failed", want);
+            return nullptr;
+        }
+        pins[(size_t)best].cap = want;
+    }
+    pins[(size_t)best].used = true;
+    return pins[(size_t)best].p;
+}
+
+void spb_ctx::pin_release(void *p) {
+    if (!p) return;
+    for (spb::PinBlock &b : pins)
+        if (b.p == p) b.used = false;
+}
+
 extern "C" {
 
 const char *spb_last_error(void) { return spb::g_err; }
@@ -51,11 +87,14 @@ void spb_ctx_destroy(spb_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     spb::DevBuf *bufs[] = {&c->d_mat, &c->d_tres, &c->d_toff, &c->d_koff, &c->d_post, &c->d_direct, &c->d_row3, &c->d_cnt3,
-                           &c->d_ares, &c->d_aoff, &c->d_q, &c->d_qoff, &c->d_qoff64, &c->d_qorder, &c->d_hits, &c->d_hitoff,
+                           &c->d_ares, &c->d_aoff, &c->d_akeys, &c->d_q, &c->d_qoff, &c->d_qoff64, &c->d_qorder, &c->d_hits, &c->d_hitoff,
                            &c->d_pairoff, &c->d_pairT, &c->d_pairQ, &c->d_pairout, &c->d_acc, &c->d_cig,
                            &c->s_a, &c->s_b, &c->s_c, &c->s_d, &c->s_e, &c->s_f, &c->s_g, &c->s_h, &c->s_i, &c->s_j,
                            &c->s_k, &c->s_l, &c->s_m, &c->s_n, &c->s_o, &c->s_p, &c->s_q, &c->s_cub};
     for (spb::DevBuf *b : bufs) b->release();
+    for (spb::PinBlock &b : c->pins)
+        if (b.p) cudaFreeHost(b.p);
+    c->pins.clear();
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaEventDestroy(c->ev2);

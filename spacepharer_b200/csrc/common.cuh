@@ -64,6 +64,13 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// pinned host staging blocks handed out with results (grow-only pool owned by the context)
+struct PinBlock {
+    void *p = nullptr;
+    size_t cap = 0;
+    bool used = false;
+};
+
 struct Matrices {
     int16_t seed[SPB_ALPHABET * SPB_ALPHABET];
     int16_t ungapped[SPB_ALPHABET * SPB_ALPHABET];
@@ -109,6 +116,7 @@ struct spb_ctx {
     spb::DevBuf d_aoff;           // u64[aT+1]
     std::vector<uint64_t> h_aoff; // host copy (work ordering, row order)
     std::vector<uint32_t> h_akeys;
+    spb::DevBuf d_akeys;          // u32[aT] DB keys (last tie-break of the row order)
 
     // ---- resident query batch ----
     bool have_queries = false;
@@ -138,6 +146,11 @@ struct spb_ctx {
     uint64_t n_acc = 0, n_cigar = 0;
     spb::DevBuf d_cig;            // char[n_cigar]
     spb_align_result aln_stats;
+
+    // ---- pinned result staging ----
+    std::vector<spb::PinBlock> pins;
+    void *pin_acquire(size_t bytes);
+    void pin_release(void *p);
 
     // ---- scratch (grow-only, reused across calls) ----
     spb::DevBuf s_a, s_b, s_c, s_d, s_e, s_f, s_g, s_h, s_i, s_j, s_k, s_l, s_m, s_n, s_o, s_p, s_q, s_cub;

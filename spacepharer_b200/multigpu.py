@@ -163,16 +163,23 @@ class ShardedSearcher:
         ast = s.align_resident(db_res_count, **ak)
         return dict(prefilter=pst, align=ast)
 
-    def search_host(self, qres, qoff, db_res_count, **kw):
+    def search_host(self, qres, qoff, db_res_count, copy=True, **kw):
         """Public end-to-end call: host query buffers in, sorted alignment rows + CIGARs out (host).
-        Rows carry batch-global query indices; every rank returns the rows of the queries it owns."""
+        Every rank returns the rows of the queries it owns; row["query"] + q_lo is the batch-global query index.
+        copy=False returns views of the library's pinned result buffers plus `view` (close() it when done)."""
         self.set_queries(qres, qoff)
         st = self.step_resident(db_res_count, **kw)
+        if not copy:
+            v = self.searcher.align_fetch_view()
+            return dict(offsets=v.offsets, rows=v.rows, cigar=v.cigar, stats=st, q_lo=self.q_lo, d2h_bytes=v.nbytes, view=v)
         off, rows, cig, _ = self.searcher.align_fetch()
         if self.q_lo:
             rows = rows.copy()
             rows["query"] += self.q_lo
-        return dict(offsets=off, rows=rows, cigar=cig, stats=st, q_lo=self.q_lo,
+            self_q_lo = 0
+        else:
+            self_q_lo = self.q_lo
+        return dict(offsets=off, rows=rows, cigar=cig, stats=st, q_lo=self_q_lo,
                     d2h_bytes=off.nbytes + rows.nbytes + len(cig))
 
     # ---- target split: hit-list exchange + merge -----------------------------------------------

@@ -16,7 +16,7 @@ if [ "${2:-}" != "quick" ]; then
   cat $OUT/bench_ref_$TAG.json
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv \
       python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/launches_$TAG.log 2>&1
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'prefilter_kernel|sw_forward' -s 4 -c 4 \
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'prefilter_team_kernel|sw_fast_kernel' -s 3 -c 3 \
       -o $OUT/prof_$TAG -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/prof_$TAG.log 2>&1
 fi
 echo done

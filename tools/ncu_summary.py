@@ -87,11 +87,18 @@ if os.path.exists(rep):
         traffic.setdefault(name, []).append(rd + wr)
     out = {}
     for name, v in traffic.items():
-        key = "prefilter_kernel" if "prefilter_kernel<0>" in name or "prefilter_kernel<(bool)0>" in name else None
-        if "sw_forward" in name:
-            key = "sw_forward_kernel"
+        key = None
+        if "prefilter_team_kernel<1>" in name or "prefilter_team_kernel<(int)1>" in name:
+            key = "prefilter_team1"
+        elif "prefilter_team_kernel<8>" in name or "prefilter_team_kernel<(int)8>" in name:
+            key = "prefilter_team8"
+        elif "sw_fast" in name:
+            key = "sw_fast_kernel"
         if key:
             out[key + "_dram_bytes_per_launch"] = sum(v) / len(v)
+    # the roofline entry of bench.py covers both team launches (one batch = one launch of each)
+    out["prefilter_kernel_dram_bytes_per_launch"] = out.get("prefilter_team1_dram_bytes_per_launch", 0.0) + \
+        out.get("prefilter_team8_dram_bytes_per_launch", 0.0)
     out["source"] = "profiles/%s_kernels.csv (ncu --set full, cold cache)" % tag
     json.dump(out, open(os.path.join(P, "traffic.json"), "w"), indent=1)
     print("wrote kernel metrics", out)
