@@ -85,6 +85,8 @@ typedef struct spb_prefilter_params {
                                 M/prefiltering/QueryMatcher.cpp:383-411 -- only affects tie order under truncation */
     int32_t comp_bias;       /* --comp-bias-corr */
     uint32_t id_base;        /* added to local target ids for tie-order purposes (target shards) */
+    int32_t emit_trunc_keys; /* 1: keep the max-seqs truncation key of every hit on the device (target shards, see
+                                spb_prefilter_device_trunc_keys); requires max_seqs <= 4096 */
 } spb_prefilter_params;
 
 typedef struct spb_hit {     /* hit_t, M/prefiltering/QueryMatcher.h:35-52 */
@@ -186,15 +188,25 @@ int spb_align_fetch(spb_ctx *ctx, spb_align_result **out);
  * (mergeTargetSplits, Prefiltering.cpp:364-481).  Here every GPU prefilters all queries against its target shard
  * (spb_prefilter_params.id_base = first global id of the shard), the per-query lists are exchanged device to device
  * (NCCL all-to-all by query range, done by the caller) and merged on the owning GPU:
- *   spb_prefilter_device_result   device pointers of the resident result (hits, offsets[Q+1]) for the exchange
- *   spb_prefilter_merge_shards    d_recv = shard-major concatenation of the lists of queries q_lo..q_hi (global target
- *                                 ids), d_counts[shard][q - q_lo] their lengths (device pointers).  The merged lists
- *                                 (score desc, id asc) replace the resident result: empty outside the range.
- *                                 Returns 2 if a query reaches max_seqs across shards (needs the unsplit hit stream
- *                                 for the reference's truncation order; use query split for that batch). */
+ *   spb_prefilter_device_result      device pointers of the resident result (hits, offsets[Q+1]) for the exchange
+ *   spb_prefilter_device_trunc_keys  device pointer of the hits' truncation keys (u64 per hit; run the prefilter with
+ *                                    emit_trunc_keys = 1).  The reference cuts a list at max-seqs in the order of its
+ *                                    stable counting sorts (QueryMatcher.cpp:131-164, CacheFriendlyOperations.cpp:
+ *                                    311-341): capped score desc, id & (BINSIZE-1), stream order of the winning
+ *                                    double-hit event, id.  The key packs the first three (shard independent); with
+ *                                    the global id it orders the union of the shards' lists like the unsplit list.
+ *   spb_prefilter_merge_shards       d_recv = shard-major concatenation of the lists of queries q_lo..q_hi (global
+ *                                    target ids), d_recv_keys their truncation keys in the same layout (or NULL),
+ *                                    d_counts[shard][q - q_lo] their lengths (device pointers).  The merged lists
+ *                                    (score desc, id asc), cut at max_seqs in the reference's order, replace the
+ *                                    resident result: empty outside the range.  Returns 2 if a query reaches max_seqs
+ *                                    and d_recv_keys is NULL, or if its cut falls among saturated 8-bit counters (the
+ *                                    rescoreHits corner, QueryMatcher.cpp:486-505, needs the unsplit candidate set):
+ *                                    use query split for that batch. */
 int spb_prefilter_device_result(spb_ctx *ctx, spb_hit **d_hits, uint64_t **d_offsets, uint64_t *n_hits);
-int spb_prefilter_merge_shards(spb_ctx *ctx, uint32_t q_lo, uint32_t q_hi, const spb_hit *d_recv, uint64_t n_recv,
-                               const uint32_t *d_counts, uint32_t n_shards, int32_t max_seqs);
+int spb_prefilter_device_trunc_keys(spb_ctx *ctx, uint64_t **d_keys);
+int spb_prefilter_merge_shards(spb_ctx *ctx, uint32_t q_lo, uint32_t q_hi, const spb_hit *d_recv, const uint64_t *d_recv_keys,
+                               uint64_t n_recv, const uint32_t *d_counts, uint32_t n_shards, int32_t max_seqs);
 
 /* ---- host pre-step (CPU, as in the reference) -----------------------------------------------------
  * tantan repeat masking of the target residues before the index build (--mask 1; call site

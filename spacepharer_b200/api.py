@@ -203,8 +203,9 @@ class Searcher:
         return dict(n_rows=int(R.n_rows), n_pairs=int(R.n_pairs), n_cells=int(R.n_cells), kernel_ms=float(R.kernel_ms),
                     total_ms=float(R.total_ms))
 
-    def prefilter_resident(self, kmer_thr=112, max_seqs=300, min_ungapped_score=15, bin_size=2, comp_bias=1, id_base=0):
-        p = capi.PrefilterParams(kmer_thr, max_seqs, min_ungapped_score, bin_size, comp_bias, id_base)
+    def prefilter_resident(self, kmer_thr=112, max_seqs=300, min_ungapped_score=15, bin_size=2, comp_bias=1, id_base=0,
+                           emit_trunc_keys=0):
+        p = capi.PrefilterParams(kmer_thr, max_seqs, min_ungapped_score, bin_size, comp_bias, id_base, emit_trunc_keys)
         capi.check(self.lib.spb_prefilter_resident(self.h, C.byref(p)))
         R = capi.PrefilterResult()
         capi.check(self.lib.spb_prefilter_stats(self.h, C.byref(R)))
@@ -231,9 +232,17 @@ class Searcher:
         capi.check(self.lib.spb_prefilter_device_result(self.h, C.byref(hp), C.byref(op), C.byref(n)))
         return int(hp.value or 0), int(op.value or 0), int(n.value)
 
-    def merge_shards(self, q_lo, q_hi, recv_ptr, n_recv, counts_ptr, n_shards, max_seqs=300):
-        """merge the per-shard hit lists of queries q_lo..q_hi (device pointers) into the resident result"""
-        capi.check(self.lib.spb_prefilter_merge_shards(self.h, q_lo, q_hi, C.c_void_p(recv_ptr), n_recv,
+    def prefilter_device_trunc_keys(self):
+        """device pointer of the resident hits' truncation keys (uint64 per hit; prefilter_resident(emit_trunc_keys=1))"""
+        kp = C.c_void_p()
+        capi.check(self.lib.spb_prefilter_device_trunc_keys(self.h, C.byref(kp)))
+        return int(kp.value or 0)
+
+    def merge_shards(self, q_lo, q_hi, recv_ptr, n_recv, counts_ptr, n_shards, max_seqs=300, recv_keys_ptr=0):
+        """merge the per-shard hit lists of queries q_lo..q_hi (device pointers) into the resident result; with the
+        shards' truncation keys (recv_keys_ptr) lists reaching max_seqs are cut in the reference's order"""
+        capi.check(self.lib.spb_prefilter_merge_shards(self.h, q_lo, q_hi, C.c_void_p(recv_ptr),
+                                                       C.c_void_p(recv_keys_ptr) if recv_keys_ptr else None, n_recv,
                                                        C.c_void_p(counts_ptr), n_shards, max_seqs))
 
     def pairs_from_prefilter(self):
@@ -297,7 +306,7 @@ class Searcher:
         qres = np.ascontiguousarray(qres, dtype=np.uint8)
         qoff = np.ascontiguousarray(qoff, dtype=np.uint64)
         Q = len(qoff) - 1
-        p = capi.PrefilterParams(kmer_thr, max_seqs, min_ungapped_score, bin_size, comp_bias, id_base)
+        p = capi.PrefilterParams(kmer_thr, max_seqs, min_ungapped_score, bin_size, comp_bias, id_base, 0)
         r = C.POINTER(capi.PrefilterResult)()
         capi.check(self.lib.spb_prefilter(self.h, _u8(qres), _u64(qoff), Q, C.byref(p), C.byref(r)))
         try:

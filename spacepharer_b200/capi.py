@@ -20,7 +20,8 @@ class IndexStats(C.Structure):
 
 class PrefilterParams(C.Structure):
     _fields_ = [("kmer_thr", C.c_int32), ("max_seqs", C.c_int32), ("min_diag_score", C.c_int32),
-                ("bin_size", C.c_int32), ("comp_bias", C.c_int32), ("id_base", C.c_uint32)]
+                ("bin_size", C.c_int32), ("comp_bias", C.c_int32), ("id_base", C.c_uint32),
+                ("emit_trunc_keys", C.c_int32)]
 
 
 class Hit(C.Structure):
@@ -61,7 +62,7 @@ SYMBOLS = [
     "spb_free_prefilter_result", "spb_align_set_targets", "spb_align", "spb_free_align_result", "spb_evalue",
     "spb_bitscore", "spb_tantan_mask", "spb_queries_set", "spb_prefilter_resident", "spb_prefilter_stats",
     "spb_prefilter_fetch", "spb_pairs_set", "spb_pairs_from_prefilter", "spb_align_resident", "spb_align_stats",
-    "spb_align_fetch", "spb_prefilter_device_result", "spb_prefilter_merge_shards",
+    "spb_align_fetch", "spb_prefilter_device_result", "spb_prefilter_device_trunc_keys", "spb_prefilter_merge_shards",
 ]
 
 _lib = None
@@ -118,7 +119,8 @@ def load():
     L.spb_align_stats.argtypes = [vp, C.POINTER(AlignResult)]
     L.spb_align_fetch.argtypes = [vp, C.POINTER(C.POINTER(AlignResult))]
     L.spb_prefilter_device_result.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), u64p]
-    L.spb_prefilter_merge_shards.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp, C.c_uint32, C.c_int32]
+    L.spb_prefilter_merge_shards.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64, vp, C.c_uint32, C.c_int32]
+    L.spb_prefilter_device_trunc_keys.argtypes = [vp, C.POINTER(C.c_void_p)]
     L.spb_tantan_mask.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), u8p, u64p, C.c_uint32, C.c_int, u64p]
     _lib = L
     return L

@@ -133,6 +133,9 @@ struct spb_ctx {
     uint64_t n_hits = 0;
     spb::DevBuf d_hits;           // spb_hit[n_hits]
     spb::DevBuf d_hitoff;         // u64[Q+1]
+    bool have_tkeys = false;
+    spb::DevBuf d_hit_tkeys;      // u64[n_hits] truncation keys (spb_prefilter_params.emit_trunc_keys), query order
+    spb::DevBuf s_tk;             // arena of the same before the compaction
     spb_prefilter_result pref_stats;   // counters of the last run (pointers unused)
 
     // ---- resident alignment input / result ----

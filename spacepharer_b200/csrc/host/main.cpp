@@ -325,6 +325,7 @@ int run_prefilter(int argc, const char **argv) {
     pp.bin_size = p.binSize ? p.binSize : bin_size_for(T.keys.size());
     pp.comp_bias = p.compBias;
     pp.id_base = 0;
+    pp.emit_trunc_keys = 0;
 
     DBWriter out;
     out.open(p.db[2], DBTYPE_PREFILTER_RES, p.threads);
@@ -516,6 +517,7 @@ int run_search(int argc, const char **argv) {
     pp.bin_size = p.binSize ? p.binSize : bin_size_for(T.keys.size());
     pp.comp_bias = p.compBias;
     pp.id_base = 0;
+    pp.emit_trunc_keys = 0;
     spb_align_params ap;
     fill_align_params(p, E, tdb.aminoAcidDBSize(), &ap);
     DBWriter out;

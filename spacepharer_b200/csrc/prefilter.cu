@@ -63,6 +63,7 @@ struct PrefArgs {
     Rec *gScratch;           // [gridDim.x][cap] (global-memory variant)
     uint32_t cap;            // record capacity per CTA
     spb_hit *arena;
+    uint64_t *arenaT;        // optional: truncation key of every arena hit (target split, tkey_* below), else NULL
     unsigned long long *cursor;  // [0] arena cursor, [1] kmers, [2] dbMatches, [3] events, [4] kept hits
     uint64_t arenaCap;
     uint64_t *outStart;      // per query
@@ -78,6 +79,19 @@ struct PrefArgs {
     uint32_t nList;
     uint32_t kCapSolo;       // TEAM = 1: queries with more similar k-mers go to the TEAM = 8 launch
 };
+
+// Truncation key exported with a hit when the target shards of a multi-GPU run are merged (spb_prefilter_merge_shards).
+// The reference cuts a list at max-seqs in the order of its stable counting sorts (QueryMatcher.cpp:131-164,
+// CacheFriendlyOperations.cpp:311-341): capped score desc, id & (BINSIZE-1) asc, stream order of the winning event,
+// target id.  All four are shard independent (global ids via id_base), so the union of the shards' lists can be cut
+// exactly like the unsplit list.  Layout (ascending = earlier):
+//   [63] 1 = counter not saturated | [62:55] 255 - capped score | [54:44] bin | [43:16] similar-k-mer number | [15:0] 0
+// Saturated candidates (bit 63 = 0) all share the highest capped score, so the flag does not disturb the order; it lets the
+// merge detect the rescoreHits corner (QueryMatcher.cpp:486-505: the cut falls among saturated counters).
+__device__ __forceinline__ uint64_t tkey_make(uint32_t capped, bool saturated, uint32_t bin, uint32_t k) {
+    return ((uint64_t)(saturated ? 0u : 1u) << 63) | ((uint64_t)(255u - capped) << 55) | ((uint64_t)bin << 44) |
+           ((uint64_t)(k & 0x0FFFFFFFu) << 16);
+}
 
 #define ST_OK 0u
 #define ST_CAPACITY 1u
@@ -238,6 +252,7 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
     __shared__ unsigned int s_nHits;
     __shared__ int s_minCorr, s_thrD;
     __shared__ unsigned long long s_base, s_stat[2];
+    __shared__ uint32_t s_kbase[PF_MAXL + 1];   // first similar-k-mer number of every window (truncation keys only)
 
     const uint32_t qi = A.qlist ? A.qlist[blockIdx.x] : blockIdx.x;
     if (qi >= A.Q) return;
@@ -320,6 +335,29 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
     const int nUnits = s_ubase[P];
     const int ungBias = abs(A.minSubUngapped) + abs(min(s_minCorr, 0));
     const int capScore = 255 - ungBias;
+    // similar k-mers before (w, a): number of inner neighbours of every outer neighbour a' < a (KmerGenerator.cpp:186-216)
+    auto inner_count = [&](int w, int x1, int x2, int a) -> uint32_t {
+        const int s1 = (int)(__ldg(A.row3 + (size_t)x1 * SPB_N3 + a) >> 16) - SPB_SCORE_OFF;
+        const int cut2 = (int)s_thr[w] - s1;
+        if (cut2 > SPB_CNT3_W - SPB_SCORE_OFF - 1) return 0u;
+        return (uint32_t)__ldg(A.cnt3 + (size_t)x2 * SPB_CNT3_W + max(cut2, -SPB_SCORE_OFF) + SPB_SCORE_OFF);
+    };
+    if (A.arenaT) {
+        for (int w = wid; w < P; w += PF_WARPS) {
+            const int x1 = s_q[w + A.pat.pos[0]] + 20 * s_q[w + A.pat.pos[1]] + 400 * s_q[w + A.pat.pos[2]];
+            const int x2 = s_q[w + A.pat.pos[3]] + 20 * s_q[w + A.pat.pos[4]] + 400 * s_q[w + A.pat.pos[5]];
+            uint32_t acc = 0;
+            for (int a = lane; a < (int)s_n1[w]; a += 32) acc += inner_count(w, x1, x2, a);
+            for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+            if (lane == 0) s_kbase[w + 1] = acc;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            s_kbase[0] = 0;
+            for (int w = 0; w < P; w++) s_kbase[w + 1] += s_kbase[w];
+        }
+        __syncthreads();
+    }
 
     // ---------------- phase 2: two passes over the hit stream ----------------
     unsigned long long nk = 0, nm = 0;
@@ -378,10 +416,12 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
     int n = (int)s_nHits;
     // later stages keep events A[0..EV) (Rec), final keys B[0..EV) (u64), cnt u8[EV] and ord u16/u32[EV] in the buffer
     const uint32_t EV = CAP / 2;
-    if ((uint32_t)n > CAP || (uint32_t)next_pow2(max(A.maxHits, 2)) > EV) {
+    // with truncation keys the upper half of the final-key array holds them: twice the room
+    const uint32_t finNeed = (uint32_t)next_pow2(max(A.maxHits, 2)) * (A.arenaT ? 2u : 1u);
+    if ((uint32_t)n > CAP || finNeed > EV) {
         if (tid == 0) {
             A.outStart[qi] = 0; A.outCount[qi] = 0; A.status[qi] = ST_CAPACITY;
-            A.need[qi] = max((uint32_t)n, 2u * (uint32_t)next_pow2(max(A.maxHits, 2)));
+            A.need[qi] = max((uint32_t)n, 2u * finNeed);
         }
         return;
     }
@@ -535,7 +575,25 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
             sc = ungapped_u16(A.tres, A.toff, id, s_q, L, s_corr, s_m40u, rec_diag16(r));   // getResult, QueryMatcher.cpp:371-374
         }
         // (score desc, id asc): 16-bit inverted score | 32-bit id | 16-bit diagonal (scores < 64 * PF_MAXL fit 16 bits)
-        finB[k] = ((uint64_t)(0xFFFFu - (uint32_t)min(sc, 0xFFFF)) << 48) | ((uint64_t)id << 16) | rec_diag16(r);
+        if (!A.arenaT) {
+            finB[k] = ((uint64_t)(0xFFFFu - (uint32_t)min(sc, 0xFFFF)) << 48) | ((uint64_t)id << 16) | rec_diag16(r);
+        } else {
+            // truncation key (its low 16 bits carry the diagonal until the output) in the upper half of finB; the sort key
+            // carries the slot instead of the diagonal.  After rescoreHits the counters are no longer comparable across
+            // shards: key 0 (saturated) makes the merge report the corner.
+            uint64_t tk = 0;
+            if (!rescale) {
+                const int w = (int)((r.hi >> 16) & 0xFFFFu);
+                const int a = (int)(r.lo >> 16);
+                const int x1 = s_q[w + A.pat.pos[0]] + 20 * s_q[w + A.pat.pos[1]] + 400 * s_q[w + A.pat.pos[2]];
+                const int x2 = s_q[w + A.pat.pos[3]] + 20 * s_q[w + A.pat.pos[4]] + 400 * s_q[w + A.pat.pos[5]];
+                uint32_t kn = s_kbase[w] + (uint32_t)(r.lo & 0xFFFFu);
+                for (int aa = 0; aa < a; aa++) kn += inner_count(w, x1, x2, aa);
+                tk = tkey_make(cnt[i], (int)cnt[i] >= capScore, (id + A.idBase) & A.binMask, kn);
+            }
+            finB[EV / 2 + k] = tk | rec_diag16(r);
+            finB[k] = ((uint64_t)(0xFFFFu - (uint32_t)min(sc, 0xFFFF)) << 48) | ((uint64_t)id << 16) | (uint64_t)k;
+        }
     }
     {
         const int np2 = next_pow2(max(ns, 2));
@@ -561,7 +619,13 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
         spb_hit h;
         h.id = (uint32_t)(f >> 16);
         h.score = (int32_t)(0xFFFFu - (uint32_t)(f >> 48));
-        h.diag = (int32_t)(short)(uint16_t)(f & 0xFFFFull);
+        uint32_t dg = (uint32_t)(f & 0xFFFFull);
+        if (A.arenaT) {
+            const uint64_t tk = finB[EV / 2 + dg];
+            dg = (uint32_t)(tk & 0xFFFFull);
+            A.arenaT[base + k] = tk & ~0xFFFFull;
+        }
+        h.diag = (int32_t)(short)(uint16_t)dg;
         A.arena[base + k] = h;
     }
     if (tid == 0) { A.outStart[qi] = base; A.outCount[qi] = (uint32_t)ns; A.status[qi] = ST_OK; }
@@ -1124,7 +1188,14 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                 statM += nHits;
                 statS += nSurv;
                 const int np2 = next_pow2(max((int)nc, 2));
-                for (int k = lane; k < np2; k += 32) W.surv[k] = (k < (int)nc) ? __ldcg(finList + 2 * k) : ~0ull;
+                // with truncation keys the sort key carries the winner's slot instead of the diagonal (ids are unique, so the
+                // low 16 bits never decide the order); diagonal and key are read back from the slot afterwards
+                const bool wantT = A.arenaT != nullptr;
+                for (int k = lane; k < np2; k += 32) {
+                    uint64_t f = (k < (int)nc) ? __ldcg(finList + 2 * k) : ~0ull;
+                    if (wantT && k < (int)nc) f = (f & ~0xFFFFull) | (uint64_t)k;
+                    W.surv[k] = f;
+                }
                 warp_bitonic_u64(W.surv, np2);
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(A.cursor, (unsigned long long)nc);
@@ -1137,7 +1208,15 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                         spb_hit h;
                         h.id = (uint32_t)(f >> 16);
                         h.score = (int32_t)(0xFFFFu - (uint32_t)(f >> 48));
-                        h.diag = (int32_t)(short)(uint16_t)(f & 0xFFFFull);
+                        uint32_t dg = (uint32_t)(f & 0xFFFFull);
+                        if (wantT) {
+                            const uint64_t t = __ldcg(finList + 2 * dg + 1);
+                            dg = (uint32_t)(__ldcg(finList + 2 * dg) & 0xFFFFull);
+                            const uint32_t capped = 255u - (uint32_t)(t >> 55);
+                            A.arenaT[base + k] = tkey_make(capped, (int)capped >= capScore, (uint32_t)(t >> 44) & 0x7FFu,
+                                                           (uint32_t)(t >> 28) & 0xFFFFu);
+                        }
+                        h.diag = (int32_t)(short)(uint16_t)dg;
                         A.arena[base + k] = h;
                     }
                     if (lane == 0) { A.outStart[qi] = base; A.outCount[qi] = nc; A.status[qi] = ST_OK; }
@@ -1197,15 +1276,23 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                         block_bitonic_pairs(bigK, bigV, np2);
                         ns = maxHits;
                         const int nq2 = next_pow2(max((int)ns, 2));
-                        for (int i = tid; i < nq2; i += blockDim.x) bigK[i] = (i < (int)ns) ? bigV[i] : ~0ull;
-                        block_bitonic_sort(bigK, nq2, [](uint64_t x, uint64_t y) { return x < y; });
+                        // the first max-seqs in truncation order, re-sorted by the final key (truncation key as payload)
+                        for (int i = tid; i < nq2; i += blockDim.x) {
+                            const uint64_t t = bigK[i], f = bigV[i];
+                            bigK[i] = (i < (int)ns) ? f : ~0ull;
+                            bigV[i] = (i < (int)ns) ? t : ~0ull;
+                        }
+                        block_bitonic_pairs(bigK, bigV, nq2);
                     }
                 } else if (nc > PW_BIG) {
                     if (tid == 0) { S.v_slow = ST_CAPACITY; S.v_why = 7; }
                 } else {
                     const int np2 = next_pow2(max((int)nc, 2));
-                    for (int i = tid; i < np2; i += blockDim.x) bigK[i] = (i < (int)nc) ? __ldcg(finList + 2 * i) : ~0ull;
-                    block_bitonic_sort(bigK, np2, [](uint64_t x, uint64_t y) { return x < y; });
+                    for (int i = tid; i < np2; i += blockDim.x) {
+                        bigK[i] = (i < (int)nc) ? __ldcg(finList + 2 * i) : ~0ull;
+                        bigV[i] = (i < (int)nc) ? __ldcg(finList + 2 * i + 1) : ~0ull;
+                    }
+                    block_bitonic_pairs(bigK, bigV, np2);
                 }
             }
             __syncthreads();
@@ -1225,6 +1312,12 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                         h.score = (int32_t)(0xFFFFu - (uint32_t)(f >> 48));
                         h.diag = (int32_t)(short)(uint16_t)(f & 0xFFFFull);
                         A.arena[base + k] = h;
+                        if (A.arenaT) {
+                            const uint64_t t = bigV[k];
+                            const uint32_t capped = 255u - (uint32_t)(t >> 55);
+                            A.arenaT[base + k] = tkey_make(capped, (int)capped >= capScore, (uint32_t)(t >> 44) & 0x7FFu,
+                                                           (uint32_t)(t >> 28) & 0xFFFFu);
+                        }
                     }
                     if (tid == 0) {
                         A.outStart[qi] = base; A.outCount[qi] = ns; A.status[qi] = ST_OK;
@@ -1252,41 +1345,93 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
 // ---------------------------------------------------------------------------------------------------------
 // Target-split merge (multi-GPU): the hit lists of one query coming from the target shards are concatenated and put
 // into the final order (score desc, global id asc).  Per-target rules are shard-local, so below max-seqs the union IS
-// the unsplit list; a query reaching max-seqs would need the reference's truncation order across shards and is
-// reported instead (err = query + 1) -- the caller falls back to query split for such batches.
+// the unsplit list.  At or above max-seqs the union is cut like the unsplit list: every shard list is a prefix of its
+// candidates in truncation order (tkey_make above), so the first max-seqs of the union in (truncation key, id) order are
+// the reference's selection (QueryMatcher.cpp:131-164).  Without keys such a query is reported (err[0] = query + 1); a
+// cut that falls among saturated counters is the rescoreHits corner and is reported too (err[1]).
 // One CTA per query of the owned range; segment (s, q) of the shard-major receive buffer starts at segOff[s * nq + q].
+// Dynamic shared memory: u64 keysF[MG_CAP] | u64 keysT[MG_CAP] | u16 ord[MG_CAP].
 // ---------------------------------------------------------------------------------------------------------
-#define MG_CAP 1024
-__global__ void __launch_bounds__(128) merge_shards_kernel(const spb_hit *__restrict__ recv, const uint32_t *__restrict__ cnt,
-                                                           const uint64_t *__restrict__ segOff, uint32_t nq, uint32_t nShards,
-                                                           uint32_t qLo, const uint64_t *__restrict__ outOff, spb_hit *__restrict__ out,
+#define MG_CAP 4096
+#define MG_SMEM (MG_CAP * (8 + 8 + 2))
+__global__ void __launch_bounds__(256) merge_shards_kernel(const spb_hit *__restrict__ recv, const uint64_t *__restrict__ recvT,
+                                                           const uint32_t *__restrict__ cnt, const uint64_t *__restrict__ segOff,
+                                                           uint32_t nq, uint32_t nShards, uint32_t qLo,
+                                                           const uint64_t *__restrict__ outOff, spb_hit *__restrict__ out,
                                                            uint32_t maxSeqs, unsigned int *__restrict__ err) {
-    __shared__ uint64_t keys[MG_CAP];
+    extern __shared__ __align__(16) unsigned char mg_smem[];
+    uint64_t *keysF = reinterpret_cast<uint64_t *>(mg_smem);
+    uint64_t *keysT = keysF + MG_CAP;
+    uint16_t *ord = reinterpret_cast<uint16_t *>(keysT + MG_CAP);
     const uint32_t q = blockIdx.x;
     if (q >= nq) return;
     const uint64_t o = outOff[qLo + q];
-    const uint32_t total = (uint32_t)(outOff[qLo + q + 1] - o);
+    const uint32_t nOut = (uint32_t)(outOff[qLo + q + 1] - o);
+    uint32_t total = 0;
+    for (uint32_t s = 0; s < nShards; s++) total += cnt[(size_t)s * nq + q];
     if (total == 0) return;
-    if (total >= maxSeqs || total > MG_CAP) {
-        if (threadIdx.x == 0) atomicMax(err, qLo + q + 1);
+    const bool cut = total >= maxSeqs;
+    if ((cut && recvT == nullptr) || total > MG_CAP) {
+        if (threadIdx.x == 0) atomicMax(&err[0], qLo + q + 1);
         return;
     }
     uint32_t base = 0;
     for (uint32_t s = 0; s < nShards; s++) {
         const uint32_t n = cnt[(size_t)s * nq + q];
-        const spb_hit *src = recv + segOff[(size_t)s * nq + q];
+        const uint64_t so = segOff[(size_t)s * nq + q];
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-            const spb_hit h = src[i];
-            keys[base + i] = ((uint64_t)(0xFFFFu - (uint32_t)min(max(h.score, 0), 0xFFFF)) << 48) | ((uint64_t)h.id << 16) |
-                             (uint64_t)((uint32_t)h.diag & 0xFFFFu);
+            const spb_hit h = recv[so + i];
+            keysF[base + i] = ((uint64_t)(0xFFFFu - (uint32_t)min(max(h.score, 0), 0xFFFF)) << 48) | ((uint64_t)h.id << 16) |
+                              (uint64_t)((uint32_t)h.diag & 0xFFFFu);
+            if (cut) keysT[base + i] = recvT[so + i];
         }
         base += n;
     }
-    const int np2 = next_pow2(max((int)total, 2));
-    for (int i = (int)total + threadIdx.x; i < np2; i += blockDim.x) keys[i] = ~0ull;
-    block_bitonic_sort(keys, np2, [](uint64_t a, uint64_t b) { return a < b; });
-    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
-        const uint64_t f = keys[i];
+    uint32_t ns = total;
+    if (total > maxSeqs) {
+        // the first max-seqs in (truncation key, id) order
+        const int np2 = next_pow2((int)total);
+        for (int i = threadIdx.x; i < np2; i += blockDim.x) ord[i] = i < (int)total ? (uint16_t)i : (uint16_t)0xFFFFu;
+        __syncthreads();
+        block_bitonic_sort(ord, np2, [&](uint16_t a, uint16_t b) {
+            if (a == 0xFFFFu || b == 0xFFFFu) return a != 0xFFFFu && b == 0xFFFFu;
+            const uint64_t ta = keysT[a], tb = keysT[b];
+            if (ta != tb) return ta < tb;
+            return (uint32_t)(keysF[a] >> 16) < (uint32_t)(keysF[b] >> 16);
+        });
+        ns = maxSeqs;
+        // keysT is dead after the selection except for the corner test: keep the last selected key, reuse the array
+        const uint64_t lastT = keysT[ord[ns - 1]];
+        __syncthreads();
+        if ((lastT >> 63) == 0) {
+            if (threadIdx.x == 0) atomicMax(&err[1], qLo + q + 1);
+            return;
+        }
+        for (uint32_t i = threadIdx.x; i < ns; i += blockDim.x) keysT[i] = keysF[ord[i]];
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < ns; i += blockDim.x) keysF[i] = keysT[i];
+        __syncthreads();
+    } else if (cut) {
+        // exactly max-seqs candidates: nothing is dropped, but the reference still takes the rescoreHits path when even the
+        // lowest counter is saturated (thr >= 255 - bias)
+        __syncthreads();
+        bool allSat = true;
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) allSat = allSat && ((keysT[i] >> 63) == 0);
+        if (__syncthreads_and(allSat)) {
+            if (threadIdx.x == 0) atomicMax(&err[1], qLo + q + 1);
+            return;
+        }
+    }
+    const int np2 = next_pow2(max((int)ns, 2));
+    __syncthreads();
+    for (int i = (int)ns + threadIdx.x; i < np2; i += blockDim.x) keysF[i] = ~0ull;
+    block_bitonic_sort(keysF, np2, [](uint64_t a, uint64_t b) { return a < b; });
+    if (ns != nOut) {   // the offsets were built from min(total, maxSeqs)
+        if (threadIdx.x == 0) atomicMax(&err[2], qLo + q + 1);
+        return;
+    }
+    for (uint32_t i = threadIdx.x; i < ns; i += blockDim.x) {
+        const uint64_t f = keysF[i];
         spb_hit h;
         h.id = (uint32_t)(f >> 16);
         h.score = (int32_t)(0xFFFFu - (uint32_t)(f >> 48));
@@ -1295,15 +1440,15 @@ __global__ void __launch_bounds__(128) merge_shards_kernel(const spb_hit *__rest
     }
 }
 
-// totals per query of the full batch: sum over shards inside the owned range, 0 outside
+// rows per query of the full batch after the merge: min(sum over shards, max-seqs) inside the owned range, 0 outside
 __global__ void merge_totals_kernel(const uint32_t *__restrict__ cnt, uint32_t nq, uint32_t nShards, uint32_t qLo, uint32_t Q,
-                                    uint64_t *__restrict__ totals) {
+                                    uint32_t maxSeqs, uint64_t *__restrict__ totals) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i > Q) return;
     uint64_t t = 0;
     if (i >= qLo && i < qLo + nq && i < Q)
         for (uint32_t s = 0; s < nShards; s++) t += cnt[(size_t)s * nq + (i - qLo)];
-    totals[i] = t;
+    totals[i] = min(t, (uint64_t)maxSeqs);
 }
 
 __global__ void widen_u32_kernel(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out) {
@@ -1315,6 +1460,15 @@ __global__ void widen_u32_kernel(const uint32_t *__restrict__ in, uint64_t n, ui
 // gather per-query slices of the arena into query order
 __global__ void gather_hits_kernel(const spb_hit *__restrict__ arena, const uint64_t *__restrict__ start, const uint64_t *__restrict__ outOff,
                                    uint32_t Q, spb_hit *__restrict__ out) {
+    const uint32_t qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= Q) return;
+    const uint64_t s = start[qi], o = outOff[qi];
+    const uint32_t n = (uint32_t)(outOff[qi + 1] - o);
+    for (uint32_t k = threadIdx.x & 31; k < n; k += 32) out[o + k] = arena[s + k];
+}
+
+__global__ void gather_keys_kernel(const uint64_t *__restrict__ arena, const uint64_t *__restrict__ start, const uint64_t *__restrict__ outOff,
+                                   uint32_t Q, uint64_t *__restrict__ out) {
     const uint32_t qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (qi >= Q) return;
     const uint64_t s = start[qi], o = outOff[qi];
@@ -1444,12 +1598,14 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
               "spb_prefilter: bin_size %d must be a power of two in 2..2048", p->bin_size);
     SPB_CHECK(p->max_seqs >= 1, "spb_prefilter: max_seqs must be >= 1");
     SPB_CHECK(p->min_diag_score >= 0 && p->min_diag_score <= 255, "spb_prefilter: min_diag_score out of range");
+    SPB_CHECK(!p->emit_trunc_keys || p->max_seqs <= 4096, "spb_prefilter: emit_trunc_keys needs max_seqs <= 4096 (got %d)", p->max_seqs);
     SPB_CHECK(c->q_maxlen <= PF_MAXL, "spb_prefilter: query of %u residues exceeds the supported query length %d of the spacer path",
               c->q_maxlen, PF_MAXL);
     SPB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     const uint32_t Q = c->Q;
     c->have_pref = false;
+    c->have_tkeys = false;
     memset(&c->pref_stats, 0, sizeof(c->pref_stats));
     c->pref_stats.n_queries = Q;
     if (c->d_hitoff.ensure(((size_t)Q + 1) * 8)) return 1;
@@ -1495,7 +1651,9 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
     SPB_CUDA(cudaEventRecord(c->ev2, st));
     for (int attempt = 0;; attempt++) {
         if (c->s_g.ensure(arenaCap * sizeof(spb_hit) + 64)) return 1;
+        if (p->emit_trunc_keys && c->s_tk.ensure(arenaCap * sizeof(uint64_t) + 64)) return 1;
         A.arena = c->s_g.as<spb_hit>();
+        A.arenaT = p->emit_trunc_keys ? c->s_tk.as<uint64_t>() : nullptr;
         A.arenaCap = arenaCap;
         A.cursor = c->s_f.as<unsigned long long>();
         A.outStart = c->s_a.as<uint64_t>();
@@ -1639,6 +1797,15 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
                                                         c->d_hits.as<spb_hit>());
         SPB_CUDA(cudaGetLastError()); c->n_launches++;
     }
+    if (p->emit_trunc_keys) {
+        if (c->d_hit_tkeys.ensure(std::max<uint64_t>(nHits, 1) * sizeof(uint64_t))) return 1;
+        if (nHits) {
+            gather_keys_kernel<<<(Q + 3) / 4, 128, 0, st>>>(c->s_tk.as<uint64_t>(), c->s_a.as<uint64_t>(), c->d_hitoff.as<uint64_t>(), Q,
+                                                            c->d_hit_tkeys.as<uint64_t>());
+            SPB_CUDA(cudaGetLastError()); c->n_launches++;
+        }
+        c->have_tkeys = true;
+    }
     SPB_CUDA(cudaEventRecord(c->ev3, st));
     SPB_CUDA(cudaStreamSynchronize(st));
     float totalMs = 0;
@@ -1726,8 +1893,15 @@ extern "C" int spb_prefilter_device_result(spb_ctx *c, spb_hit **d_hits, uint64_
     return 0;
 }
 
-extern "C" int spb_prefilter_merge_shards(spb_ctx *c, uint32_t q_lo, uint32_t q_hi, const spb_hit *d_recv, uint64_t n_recv,
-                                          const uint32_t *d_counts, uint32_t n_shards, int32_t max_seqs) {
+extern "C" int spb_prefilter_device_trunc_keys(spb_ctx *c, uint64_t **d_keys) {
+    SPB_CHECK(c && d_keys, "spb_prefilter_device_trunc_keys: NULL argument");
+    SPB_CHECK(c->have_pref && c->have_tkeys, "spb_prefilter_device_trunc_keys: run the prefilter with emit_trunc_keys = 1 first");
+    *d_keys = c->d_hit_tkeys.as<uint64_t>();
+    return 0;
+}
+
+extern "C" int spb_prefilter_merge_shards(spb_ctx *c, uint32_t q_lo, uint32_t q_hi, const spb_hit *d_recv, const uint64_t *d_recv_keys,
+                                          uint64_t n_recv, const uint32_t *d_counts, uint32_t n_shards, int32_t max_seqs) {
     SPB_CHECK(c && (d_counts || q_hi == q_lo), "spb_prefilter_merge_shards: NULL argument");
     SPB_CHECK(c->have_queries, "spb_prefilter_merge_shards: no resident query batch");
     SPB_CHECK(q_lo <= q_hi && q_hi <= c->Q, "spb_prefilter_merge_shards: query range %u..%u outside the batch of %u", q_lo, q_hi, c->Q);
@@ -1737,19 +1911,21 @@ extern "C" int spb_prefilter_merge_shards(spb_ctx *c, uint32_t q_lo, uint32_t q_
     const uint32_t Q = c->Q, nq = q_hi - q_lo;
     const size_t nSeg = (size_t)n_shards * nq;
     SPB_CUDA(cudaEventRecord(c->ev2, st));
-    // s_a: segment counts widened u64[nSeg+1], s_b: segment offsets u64[nSeg+1], s_c: totals u64[Q+1], s_f: error flag
+    // s_a: segment counts widened u64[nSeg+1], s_b: segment offsets u64[nSeg+1], s_c: totals u64[Q+1], s_f: error flags
     if (c->s_a.ensure((nSeg + 1) * 8) || c->s_b.ensure((nSeg + 1) * 8) || c->s_c.ensure(((size_t)Q + 1) * 8) || c->s_f.ensure(512) ||
         c->d_hitoff.ensure(((size_t)Q + 1) * 8)) return 1;
     SPB_CUDA(cudaMemsetAsync(c->s_f.p, 0, 16, st));
     size_t tmpBytes = 0;
+    uint64_t nIn = 0;
     if (nSeg) {
         widen_u32_kernel<<<(unsigned)((nSeg + 1 + 255) / 256), 256, 0, st>>>(d_counts, nSeg, c->s_a.as<uint64_t>());
         SPB_CUDA(cudaGetLastError()); c->n_launches++;
         SPB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, c->s_a.as<uint64_t>(), c->s_b.as<uint64_t>(), (int)(nSeg + 1), st));
         if (c->s_cub.ensure(tmpBytes)) return 1;
         SPB_CUDA(cub::DeviceScan::ExclusiveSum(c->s_cub.p, tmpBytes, c->s_a.as<uint64_t>(), c->s_b.as<uint64_t>(), (int)(nSeg + 1), st));
+        SPB_CUDA(cudaMemcpyAsync(&nIn, c->s_b.as<uint64_t>() + nSeg, 8, cudaMemcpyDeviceToHost, st));
     }
-    merge_totals_kernel<<<(Q + 1 + 255) / 256, 256, 0, st>>>(d_counts, nq, n_shards, q_lo, Q, c->s_c.as<uint64_t>());
+    merge_totals_kernel<<<(Q + 1 + 255) / 256, 256, 0, st>>>(d_counts, nq, n_shards, q_lo, Q, (uint32_t)max_seqs, c->s_c.as<uint64_t>());
     SPB_CUDA(cudaGetLastError()); c->n_launches++;
     SPB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, c->s_c.as<uint64_t>(), c->d_hitoff.as<uint64_t>(), (int)(Q + 1), st));
     if (c->s_cub.ensure(tmpBytes)) return 1;
@@ -1757,26 +1933,44 @@ extern "C" int spb_prefilter_merge_shards(spb_ctx *c, uint32_t q_lo, uint32_t q_
     uint64_t nHits = 0;
     SPB_CUDA(cudaMemcpyAsync(&nHits, c->d_hitoff.as<uint64_t>() + Q, 8, cudaMemcpyDeviceToHost, st));
     SPB_CUDA(cudaStreamSynchronize(st));
-    SPB_CHECK(nHits == n_recv, "spb_prefilter_merge_shards: the counts add up to %llu hits but %llu were received",
-              (unsigned long long)nHits, (unsigned long long)n_recv);
+    SPB_CHECK(nIn == n_recv, "spb_prefilter_merge_shards: the counts add up to %llu hits but %llu were received",
+              (unsigned long long)nIn, (unsigned long long)n_recv);
     // the receive buffer may alias nothing of ours; the merged lists replace the resident result
     DevBuf merged;
     if (merged.ensure(std::max<uint64_t>(nHits, 1) * sizeof(spb_hit))) return 1;
-    unsigned int h_err = 0;
-    if (nq && nHits) {
-        merge_shards_kernel<<<nq, 128, 0, st>>>(d_recv, d_counts, c->s_b.as<uint64_t>(), nq, n_shards, q_lo, c->d_hitoff.as<uint64_t>(),
-                                                merged.as<spb_hit>(), (uint32_t)max_seqs, reinterpret_cast<unsigned int *>(c->s_f.p));
+    unsigned int h_err[4] = {0, 0, 0, 0};
+    if (nq && nIn) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            SPB_CUDA(cudaFuncSetAttribute(merge_shards_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
+            attr_done = true;
+        }
+        merge_shards_kernel<<<nq, 256, MG_SMEM, st>>>(d_recv, d_recv_keys, d_counts, c->s_b.as<uint64_t>(), nq, n_shards, q_lo,
+                                                      c->d_hitoff.as<uint64_t>(), merged.as<spb_hit>(), (uint32_t)max_seqs,
+                                                      reinterpret_cast<unsigned int *>(c->s_f.p));
         cudaError_t e = cudaGetLastError(); c->n_launches++;
-        if (e == cudaSuccess) e = cudaMemcpyAsync(&h_err, c->s_f.p, 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_err, c->s_f.p, 16, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { merged.release(); spb::set_error("spb_prefilter_merge_shards: %s", cudaGetErrorString(e)); return 1; }
     }
-    if (h_err) {
+    if (h_err[0]) {
         merged.release();
-        spb::set_error("spb_prefilter_merge_shards: query %u reaches max-seqs (%d) across the target shards; its truncation order needs the "
-                       "unsplit hit stream -- run this batch with query split", h_err - 1, max_seqs);
+        if (d_recv_keys)
+            spb::set_error("spb_prefilter_merge_shards: query %u has more than %d candidates across the target shards (merge capacity)",
+                           h_err[0] - 1, MG_CAP);
+        else
+            spb::set_error("spb_prefilter_merge_shards: query %u reaches max-seqs (%d) across the target shards; its truncation order needs "
+                           "the shards' truncation keys (emit_trunc_keys) -- or run this batch with query split", h_err[0] - 1, max_seqs);
         return 2;
     }
+    if (h_err[1]) {
+        merged.release();
+        spb::set_error("spb_prefilter_merge_shards: the max-seqs (%d) cut of query %u falls among saturated diagonal counters (rescoreHits, "
+                       "QueryMatcher.cpp:486-505), which needs the unsplit candidate set -- run this batch with query split",
+                       max_seqs, h_err[1] - 1);
+        return 2;
+    }
+    SPB_CHECK(h_err[2] == 0, "spb_prefilter_merge_shards: internal row count mismatch at query %u", h_err[2] - 1);
     c->d_hits.release();
     c->d_hits = merged;          // ownership moves to the context
     c->n_hits = nHits;
@@ -1787,6 +1981,7 @@ extern "C" int spb_prefilter_merge_shards(spb_ctx *c, uint32_t q_lo, uint32_t q_
     c->pref_stats.n_hits = nHits;
     c->pref_stats.total_ms += ms;
     c->have_pref = true;
+    c->have_tkeys = false;
     c->have_pairs = false;
     c->have_aln = false;
     return 0;

@@ -9,9 +9,10 @@ query split, M/alignment/Alignment.cpp:226-249): every rank owns one `Searcher` 
       device to device (NCCL all_to_all_single over NVLink), merged there (spb_prefilter_merge_shards) and aligned
       there against the replicated unmasked target residues with the whole-DB residue count in the E-value.  The
       per-target rules of the prefilter are shard-local, so the merged list equals the UNSPLIT list (unlike the
-      reference's lossy --split heuristic, Prefiltering.cpp:343-346); a query reaching max-seqs across shards is
-      reported by the library (its truncation order needs the unsplit hit stream) and the batch is redone in
-      query-split mode.
+      reference's lossy --split heuristic, Prefiltering.cpp:343-346).  Lists reaching max-seqs are cut in the
+      reference's order as well: every hit travels with its truncation key (capped score, id & (BINSIZE-1), stream
+      order of the winning event -- all shard independent), and the first max-seqs of the union in (key, global id)
+      order are the reference's selection (QueryMatcher.cpp:131-164).
   split_mode "query": every rank holds the full index and processes its own slice of the query batch; no collective
       on the data path.
 
@@ -50,11 +51,12 @@ def query_ranges(Q, world):
     return [((Q * r) // world, (Q * (r + 1)) // world) for r in range(world)]
 
 
-def exchange_hit_lists(hits, offsets, ranges, rank, group=None):
+def exchange_hit_lists(hits, offsets, ranges, rank, group=None, keys=None):
     """All-to-all of per-query hit lists by query range (backend agnostic: NCCL on device tensors, gloo on CPU tensors).
 
     hits: int32 tensor [n, 3] (global id, score, diag), all queries of the batch in query order;
-    offsets: int64 tensor [Q+1].  Returns (recv int32 [m, 3] shard-major, counts int32 [world * nq] shard-major)
+    offsets: int64 tensor [Q+1]; keys: optional int64 tensor [n] of truncation keys travelling with the hits.
+    Returns (recv int32 [m, 3] shard-major, counts int32 [world * nq] shard-major[, recv_keys int64 [m]])
     for this rank's query range."""
     import torch
     import torch.distributed as dist
@@ -74,19 +76,29 @@ def exchange_hit_lists(hits, offsets, ranges, rank, group=None):
                            group=group)
     recv = torch.empty((sum(recv_rows), 3), dtype=torch.int32, device=hits.device)
     dist.all_to_all_single(recv, hits.contiguous(), output_split_sizes=recv_rows, input_split_sizes=send_rows, group=group)
-    return recv, cnt_recv
+    if keys is None:
+        return recv, cnt_recv
+    recv_keys = torch.empty(sum(recv_rows), dtype=torch.int64, device=hits.device)
+    dist.all_to_all_single(recv_keys, keys.contiguous(), output_split_sizes=recv_rows, input_split_sizes=send_rows, group=group)
+    return recv, cnt_recv, recv_keys
 
 
-def merge_hit_lists_reference(recv, cnt_recv, world, nq):
+def merge_hit_lists_reference(recv, cnt_recv, world, nq, keys=None, max_seqs=None):
     """numpy restatement of spb_prefilter_merge_shards (tests): per query concatenate the shard segments and sort by
-    (score desc, id asc).  Returns (offsets int64[nq+1], hits int32[m, 3])."""
+    (score desc, id asc); with truncation keys, lists longer than max_seqs keep the first max_seqs in (key, id) order.
+    Returns (offsets int64[nq+1], hits int32[m, 3])."""
     recv = np.asarray(recv).reshape(-1, 3)
+    if keys is not None:
+        keys = np.asarray(keys).astype(np.uint64)
     cnt = np.asarray(cnt_recv).reshape(world, nq).astype(np.int64)
     seg = np.zeros(world * nq + 1, dtype=np.int64)
     seg[1:] = np.cumsum(cnt.reshape(-1))
     out, off = [], [0]
     for q in range(nq):
         rows = np.concatenate([recv[seg[s * nq + q]:seg[s * nq + q + 1]] for s in range(world)]) if world else recv[:0]
+        if keys is not None and max_seqs is not None and len(rows) > max_seqs:
+            kk = np.concatenate([keys[seg[s * nq + q]:seg[s * nq + q + 1]] for s in range(world)])
+            rows = rows[np.lexsort((rows[:, 0], kk))[:max_seqs]]
         order = np.lexsort((rows[:, 0], -rows[:, 1]))
         out.append(rows[order])
         off.append(off[-1] + len(rows))
@@ -188,8 +200,9 @@ class ShardedSearcher:
         s = self.searcher
         frm, _ = self.shard
         Q, G = self.Q, self.world
-        pst = s.prefilter_resident(id_base=frm, **pk)
+        pst = s.prefilter_resident(id_base=frm, emit_trunc_keys=1, **pk)
         hp, op, n = s.prefilter_device_result()
+        kp = s.prefilter_device_trunc_keys()
         dev = torch.device("cuda", self.device)
         stream = torch.cuda.ExternalStream(s.stream_ptr(), device=dev)
         with torch.cuda.stream(stream):
@@ -197,11 +210,14 @@ class ShardedSearcher:
             hits = (torch.as_tensor(_DevView(hp, (n, 3), "<i4"), device=dev) if n
                     else torch.empty((0, 3), dtype=torch.int32, device=dev)).clone()
             hits[:, 0] += frm                         # shard-local -> global target ids
+            keys = (torch.as_tensor(_DevView(kp, (n,), "<i8"), device=dev) if n
+                    else torch.empty((0,), dtype=torch.int64, device=dev))
             ranges = query_ranges(Q, G)
-            recv, cnt_recv = exchange_hit_lists(hits, offsets, ranges, self.rank)
+            recv, cnt_recv, recv_keys = exchange_hit_lists(hits, offsets, ranges, self.rank, keys=keys)
             stream.synchronize()
         lo, hi = ranges[self.rank]
-        s.merge_shards(lo, hi, recv.data_ptr(), recv.shape[0], cnt_recv.data_ptr(), G, pk.get("max_seqs", 300))
+        s.merge_shards(lo, hi, recv.data_ptr(), recv.shape[0], cnt_recv.data_ptr(), G, min(pk.get("max_seqs", 300), self.T),
+                       recv_keys_ptr=recv_keys.data_ptr())
         pst["n_hits_shard"] = pst["n_hits"]
         pst["n_hits"] = int(recv.shape[0])
         return pst

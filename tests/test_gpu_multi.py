@@ -18,8 +18,60 @@ def _workload():
     return tres, toff, qres, qoff
 
 
-def test_merge_of_target_shards_equals_unsplit():
+def _family_workload():
+    """families of near-identical targets: most queries see far more candidates than max-seqs, with many score ties"""
+    rng = np.random.default_rng(99)
+    T, Q = [], []
+    for f in range(30):
+        base = rng.integers(0, 20, 90).astype(np.uint8)
+        for _ in range(50):
+            t = base.copy()
+            for _ in range(int(rng.integers(0, 4))):
+                t[int(rng.integers(0, 90))] = rng.integers(0, 20)
+            T.append(np.concatenate([rng.integers(0, 20, int(rng.integers(0, 40))).astype(np.uint8), t]))
+        for _ in range(12):
+            L = int(rng.integers(10, 22))
+            p = int(rng.integers(0, 90 - L))
+            q = base[p:p + L].copy()
+            if rng.random() < 0.5:
+                q[int(rng.integers(0, L))] = rng.integers(0, 20)
+            Q.append(q)
+    order = rng.permutation(len(T))
+    tres, toff = O.concat([T[i] for i in order])
+    qres, qoff = O.concat(Q)
+    return tres, toff, qres, qoff
+
+
+def _shard_lists_on_one_gpu(s, tres, toff, qres, qoff, G, max_seqs, bin_size=2):
+    """every target shard prefiltered in turn on this GPU (as its own rank would), lists and truncation keys kept on the
+    device -> (recv int32[m,3] shard-major with global ids, keys int64[m], counts int32[G*Q])"""
     import torch
+    from spacepharer_b200 import multigpu
+    Q = len(qoff) - 1
+    parts = multigpu.decompose_by_amino_acid(toff, G)
+    hs, ks, cs = [], [], []
+    dev = torch.device("cuda", 0)
+    for frm, size in parts:
+        lo, hi = int(toff[frm]), int(toff[frm + size])
+        s.build_index(tres[lo:hi], toff[frm:frm + size + 1] - toff[frm])
+        s.set_queries(qres, qoff)
+        s.prefilter_resident(id_base=frm, emit_trunc_keys=1, max_seqs=max_seqs, bin_size=bin_size)
+        hp, op, n = s.prefilter_device_result()
+        kp = s.prefilter_device_trunc_keys()
+        torch.cuda.synchronize()
+        off = torch.as_tensor(multigpu._DevView(op, (Q + 1,), "<i8"), device=dev).clone()
+        h = (torch.as_tensor(multigpu._DevView(hp, (n, 3), "<i4"), device=dev).clone() if n
+             else torch.empty((0, 3), dtype=torch.int32, device=dev))
+        k = (torch.as_tensor(multigpu._DevView(kp, (n,), "<i8"), device=dev).clone() if n
+             else torch.empty((0,), dtype=torch.int64, device=dev))
+        h[:, 0] += frm
+        hs.append(h)
+        ks.append(k)
+        cs.append((off[1:] - off[:-1]).to(torch.int32))
+    return torch.cat(hs).contiguous(), torch.cat(ks).contiguous(), torch.cat(cs).contiguous()
+
+
+def test_merge_of_target_shards_equals_unsplit():
     from spacepharer_b200 import api, multigpu
     tres, toff, qres, qoff = _workload()
     Q = len(qoff) - 1
@@ -28,16 +80,7 @@ def test_merge_of_target_shards_equals_unsplit():
         s.build_index(tres, toff)
         off0, hits0, _ = s.prefilter(qres, qoff)
         G = 3
-        parts = multigpu.decompose_by_amino_acid(toff, G)
-        lists = []
-        for frm, size in parts:
-            lo, hi = int(toff[frm]), int(toff[frm + size])
-            s.build_index(tres[lo:hi], toff[frm:frm + size + 1] - toff[frm])
-            off, hits, _ = s.prefilter(qres, qoff, id_base=frm)
-            h = np.stack([hits["id"].astype(np.int64) + frm, hits["score"], hits["diag"]], axis=1).astype(np.int32)
-            lists.append((off.astype(np.int64), h))
-        recv = torch.from_numpy(np.concatenate([h for _, h in lists])).cuda()
-        cnt = torch.from_numpy(np.concatenate([np.diff(o) for o, _ in lists]).astype(np.int32)).cuda()
+        recv, keys, cnt = _shard_lists_on_one_gpu(s, tres, toff, qres, qoff, G, 300)
         s.set_queries(qres, qoff)
         s.merge_shards(0, Q, recv.data_ptr(), recv.shape[0], cnt.data_ptr(), G)
         off1, hits1, _ = s.prefilter_fetch()
@@ -46,9 +89,59 @@ def test_merge_of_target_shards_equals_unsplit():
         # numpy restatement of the merge agrees too
         moff, mh = multigpu.merge_hit_lists_reference(recv.cpu().numpy(), cnt.cpu().numpy(), G, Q)
         assert (moff == off0.astype(np.int64)).all() and (mh[:, 0] == hits0["id"]).all()
-        # reaching max-seqs across shards is reported, not silently truncated
+        # without the shards' truncation keys, reaching max-seqs across shards is reported, not silently truncated
         with pytest.raises(Exception, match="max-seqs"):
             s.merge_shards(0, Q, recv.data_ptr(), recv.shape[0], cnt.data_ptr(), G, max_seqs=2)
+    finally:
+        s.close()
+
+
+@pytest.mark.parametrize("G,max_seqs,bin_size", [(3, 4, 2), (2, 10, 8), (5, 2, 2), (4, 7, 2048), (8, 40, 2)])
+def test_merge_cuts_at_max_seqs_like_the_unsplit_list(G, max_seqs, bin_size):
+    """lists reaching max-seqs across the shards are cut in the reference's order (capped score, bin, stream order, id):
+    the merged result equals the unsplit prefilter, which the parity tests pin against the oracle and the golden lists"""
+    from spacepharer_b200 import api, multigpu
+    tres, toff, qres, qoff = _family_workload()
+    Q = len(qoff) - 1
+    s = api.Searcher(device=0)
+    try:
+        s.build_index(tres, toff)
+        off0, hits0, _ = s.prefilter(qres, qoff, max_seqs=max_seqs, bin_size=bin_size)
+        assert (np.diff(off0.astype(np.int64)) == max_seqs).sum() > Q // 2        # the cut is exercised
+        recv, keys, cnt = _shard_lists_on_one_gpu(s, tres, toff, qres, qoff, G, max_seqs, bin_size)
+        s.set_queries(qres, qoff)
+        s.merge_shards(0, Q, recv.data_ptr(), recv.shape[0], cnt.data_ptr(), G, max_seqs=max_seqs, recv_keys_ptr=keys.data_ptr())
+        off1, hits1, _ = s.prefilter_fetch()
+        assert (off1 == off0).all()
+        assert (hits1["id"] == hits0["id"]).all() and (hits1["score"] == hits0["score"]).all() and (hits1["diag"] == hits0["diag"]).all()
+        moff, mh = multigpu.merge_hit_lists_reference(recv.cpu().numpy(), cnt.cpu().numpy(), G, Q, keys=keys.cpu().numpy(),
+                                                      max_seqs=max_seqs)
+        assert (moff == off0.astype(np.int64)).all() and (mh[:, 0] == hits0["id"]).all() and (mh[:, 1] == hits0["score"]).all()
+    finally:
+        s.close()
+
+
+def test_merge_family_truncation_golden():
+    """the reference's own truncated lists (tests/golden/family: hundreds of near-identical targets per query) are
+    reproduced from three target shards"""
+    import common as Cm
+    from spacepharer_b200 import api
+    T, Qs = Cm.load_fasta_set("family")
+    tres, toff = O.concat(T)
+    qres, qoff = O.concat(Qs)
+    Q = len(Qs)
+    s = api.Searcher(device=0)
+    try:
+        tres, _ = api.tantan_mask(s.seed, tres, toff)        # --mask 1 like the reference run that wrote the fixtures
+        for fname, max_seqs in (("pref_max300.txt.gz", 300), ("pref_max10.txt.gz", 10)):
+            recv, keys, cnt = _shard_lists_on_one_gpu(s, tres, toff, qres, qoff, 3, max_seqs)
+            s.set_queries(qres, qoff)
+            s.merge_shards(0, Q, recv.data_ptr(), recv.shape[0], cnt.data_ptr(), 3, max_seqs=max_seqs, recv_keys_ptr=keys.data_ptr())
+            off, hits, _ = s.prefilter_fetch()
+            ref = Cm.dump("family", fname)
+            for i in range(Q):
+                got = api.format_prefilter_rows(hits[int(off[i]):int(off[i + 1])])
+                assert got == ref.get(i, []), (fname, i)
     finally:
         s.close()
 

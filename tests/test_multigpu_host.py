@@ -76,3 +76,49 @@ def test_exchange_and_merge_world2(tmp_path):
             rows = rows[np.lexsort((rows[:, 0], -rows[:, 1]))]
             got = z["hits"][z["off"][q - lo]:z["off"][q - lo + 1]]
             assert (got == rows).all(), q
+
+
+def _fake_keys(hits):
+    """a shard-independent truncation key per hit: higher score first, then a pseudo stream order derived from the id"""
+    return ((255 - np.minimum(hits[:, 1], 255)).astype(np.int64) << 55) | ((hits[:, 0].astype(np.int64) * 7919 % 1000) << 16) | (1 << 62)
+
+
+def _worker_keys(rank, world, port, Q, max_seqs, out_dir):
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    off, hits = _shard_lists(rank, world, Q)
+    ranges = multigpu.query_ranges(Q, world)
+    recv, cnt, rkeys = multigpu.exchange_hit_lists(torch.from_numpy(hits), torch.from_numpy(off), ranges, rank,
+                                                   keys=torch.from_numpy(_fake_keys(hits)))
+    lo, hi = ranges[rank]
+    assert (rkeys.numpy() == _fake_keys(recv.numpy())).all()        # keys stay aligned with their hits through the exchange
+    moff, mhits = multigpu.merge_hit_lists_reference(recv.numpy(), cnt.numpy(), world, hi - lo, keys=rkeys.numpy(), max_seqs=max_seqs)
+    np.savez(os.path.join(out_dir, "k%d.npz" % rank), off=moff, hits=mhits, lo=lo, hi=hi)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_exchange_with_truncation_keys_world2(tmp_path):
+    """the per-hit truncation keys travel with the hits; lists longer than max-seqs keep the first max-seqs in
+    (key, id) order and are then put into the final (score desc, id asc) order"""
+    import torch.multiprocessing as mp
+    world, Q, max_seqs = 2, 101, 3
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker_keys, args=(world, port, Q, max_seqs, str(tmp_path)), nprocs=world, join=True)
+    shards = [_shard_lists(r, world, Q) for r in range(world)]
+    cut = 0
+    for r in range(world):
+        z = np.load(str(tmp_path / ("k%d.npz" % r)))
+        lo, hi = int(z["lo"]), int(z["hi"])
+        for q in range(lo, hi):
+            rows = np.concatenate([h[o[q]:o[q + 1]] for o, h in shards])
+            if len(rows) > max_seqs:
+                rows = rows[np.lexsort((rows[:, 0], _fake_keys(rows)))[:max_seqs]]
+                cut += 1
+            rows = rows[np.lexsort((rows[:, 0], -rows[:, 1]))]
+            got = z["hits"][z["off"][q - lo]:z["off"][q - lo + 1]]
+            assert (got == rows).all(), q
+    assert cut > 10
