@@ -33,49 +33,54 @@ namespace spb {
 #define SWF_THREADS 64
 #define SWF_PROF_ROWS 22      // 21 residues + the pad symbol used beyond the end of a target
 #define SWF_PAD 21
-__global__ void align_profile_kernel(const uint8_t *__restrict__ q, const uint64_t *__restrict__ qoff, uint32_t Q,
-                                     const Matrices *__restrict__ mat, int compBias, signed char *__restrict__ cb,
+__global__ void __launch_bounds__(128) align_profile_kernel(const uint8_t *__restrict__ q, const uint64_t *__restrict__ qoff, uint32_t Q,
+                                     const Matrices *__restrict__ mat, int compBias, int matMin, signed char *__restrict__ cb,
                                      int *__restrict__ qbias, signed char *__restrict__ prof16, uint8_t *__restrict__ qfast,
                                      int fastMaxL) {
-    const uint32_t qi = blockIdx.x;
-    if (qi >= Q) return;
-    __shared__ int s_min;
-    if (threadIdx.x == 0) s_min = 0;
+    // one warp per query; matMin = min over the alignment matrix (byte-profile bias, StripedSmithWaterman.cpp:723-737)
+    __shared__ int16_t s_align[SPB_ALPHABET * SPB_ALPHABET];
+    __shared__ double s_pback[SPB_ALPHABET];
+    for (int i = threadIdx.x; i < SPB_ALPHABET * SPB_ALPHABET; i += blockDim.x) s_align[i] = mat->align[i];
+    if (threadIdx.x < SPB_ALPHABET) s_pback[threadIdx.x] = mat->pback_align[threadIdx.x];
     __syncthreads();
+    const uint32_t qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= Q) return;
+    const int lane = threadIdx.x & 31;
     const uint64_t o = qoff[qi];
     const int L = (int)(qoff[qi + 1] - o);
     const uint8_t *s = q + o;
-    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    int mn = 0;
+    for (int i = lane; i < L; i += 32) {
         signed char c = 0;
         if (compBias) {
             const int lo = max(0, i - 20), hi = min(L, i + 20);
-            const int16_t *row = mat->align + s[i] * SPB_ALPHABET;
+            const int16_t *row = s_align + s[i] * SPB_ALPHABET;
             int sum = 0;
             for (int j = lo; j < hi; j++) sum += row[s[j]];
             sum -= row[s[i]];
             float d = (float)sum;
             d = __double2float_rn(__ddiv_rn((double)d, -1.0 * (double)(float)(hi - lo)));
             for (int a = 0; a < SPB_ALPHABET; a++)
-                d = __double2float_rn(__dadd_rn((double)d, __dmul_rn(mat->pback_align[a], (double)(float)row[a])));
+                d = __double2float_rn(__dadd_rn((double)d, __dmul_rn(s_pback[a], (double)(float)row[a])));
             double r = (d < 0.0f) ? __dsub_rn((double)d, 0.5) : __dadd_rn((double)d, 0.5);
             c = (signed char)r;
         }
         cb[o + i] = c;
-        if (c < 0) atomicMin(&s_min, (int)c);
+        mn = min(mn, (int)c);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int mn = 0;
-        for (int i = 0; i < SPB_ALPHABET * SPB_ALPHABET; i++) mn = min(mn, (int)(signed char)mat->align[i]);
-        qbias[qi] = abs(mn) + abs(min(s_min, 0));
-        qfast[qi] = (uint8_t)(L >= 1 && L <= fastMaxL);
+    for (int d = 16; d > 0; d >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+    const bool fast = (L >= 1 && L <= fastMaxL);
+    if (lane == 0) {
+        qbias[qi] = abs(matMin) + abs(min(mn, 0));
+        qfast[qi] = (uint8_t)fast;
     }
-    if (L >= 1 && L <= fastMaxL) {
+    if (fast) {
+        __syncwarp();
         signed char *pq = prof16 + (size_t)qi * SWF_PROF_ROWS * SWF_ROWS;
-        for (int x = threadIdx.x; x < SWF_PROF_ROWS * SWF_ROWS; x += blockDim.x) {
+        for (int x = lane; x < SWF_PROF_ROWS * SWF_ROWS; x += 32) {
             const int a = x / SWF_ROWS, i = x % SWF_ROWS;
             int v = -128;
-            if (a < SPB_ALPHABET && i < L) v = (int)(signed char)mat->align[a * SPB_ALPHABET + s[i]] + (int)cb[o + i];
+            if (a < SPB_ALPHABET && i < L) v = (int)(signed char)s_align[a * SPB_ALPHABET + s[i]] + (int)cb[o + i];
             pq[x] = (signed char)v;
         }
     }
@@ -415,6 +420,7 @@ struct TbArgs {
     char *cigar;
 };
 
+#define TB_FAST_ROWS 32
 __global__ void sw_reverse_kernel(TbArgs A) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= A.nAcc) return;
@@ -432,7 +438,13 @@ __global__ void sw_reverse_kernel(TbArgs A) {
     const int16_t *M = A.mat->align;
     auto prof = [&](int i, int a) -> int { return (int)(signed char)M[a * SPB_ALPHABET + q[qEnd - i]] + (int)cb[qEnd - i]; };
     int score, col, row;
-    sw_pass(t, o.tEnd, -1, -1, rl, seg, A.go, A.ge, o.score, prof, A.heScratch + A.heOff[k], 1, score, col, row);
+    if (rl <= TB_FAST_ROWS) {
+        // spacer frames: the H/E column lives in (thread-interleaved, L1-cached) local memory instead of a global slice
+        short2 heL[TB_FAST_ROWS];
+        sw_pass(t, o.tEnd, -1, -1, rl, seg, A.go, A.ge, o.score, prof, heL, 1, score, col, row);
+    } else {
+        sw_pass(t, o.tEnd, -1, -1, rl, seg, A.go, A.ge, o.score, prof, A.heScratch + A.heOff[k], 1, score, col, row);
+    }
     if (score != o.score || col < 0) {
         o.status = -1;      // "Score of forward/backward SW differ" (StripedSmithWaterman.cpp:225-228)
     } else {
@@ -447,41 +459,18 @@ __global__ void sw_reverse_kernel(TbArgs A) {
 __device__ __forceinline__ int band_u(int w, int i, int j) { int x = i - w; x = x > 0 ? x : 0; return j - x + 1; }
 __device__ __forceinline__ int band_d(int w, int i, int j, int p) { int x = i - w; x = x > 0 ? x : 0; x = j - x; return x * 3 + p; }
 
-__global__ void sw_traceback_kernel(TbArgs A) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= A.nAcc) return;
-    const uint32_t pair = A.acc[k];
-    PairOut o = A.out[pair];
-    if (o.status != 1) return;
-    const uint32_t qi = A.pairQ[pair], ti = A.pairT[pair];
-    const uint64_t qo = A.qoff[qi];
-    const uint8_t *qs = A.q + qo + o.qStart;
-    const signed char *cb = A.qcb + qo + o.qStart;
-    const uint8_t *db = A.tres + A.toff[ti] + o.tStart;
-    const int16_t *M = A.mat->align;
-    const int dbLen = o.tEnd - o.tStart + 1, qLen = o.qEnd - o.qStart + 1;
-    const int score = o.score, go = A.go, ge = A.ge;
-    int bw = abs(dbLen - qLen) + 1;
-    // scratch layout: [h_b | e_b | h_c] int32 each Wmax, then direction bytes
-    const uint64_t bytes = A.tbOff[k + 1] - A.tbOff[k];
-    unsigned char *base = A.tbScratch + A.tbOff[k];
-    int bwMax = bw;
-    while (bwMax < max(qLen, dbLen)) bwMax *= 2;
-    const int64_t Wmax = (int64_t)bwMax * 2 + 3 + 2;
-    int32_t *h_b = reinterpret_cast<int32_t *>(base);
-    int32_t *e_b = h_b + Wmax;
-    int32_t *h_c = e_b + Wmax;
-    int8_t *direction = reinterpret_cast<int8_t *>(h_c + Wmax);
-    const int64_t dirCap = (int64_t)bytes - 3 * Wmax * 4;
-    for (int64_t x = 0; x < 3 * Wmax; x++) h_b[x] = 0;
-    int64_t width = 0, width_d = 0;
+// The band-doubling DP of banded_sw.  Returns false when the next band does not fit the given arrays (Wmax ints per row
+// array, dirCap direction bytes); on success bw is the band of the last pass and dl points at the last row's directions.
+__device__ __forceinline__ bool banded_fill(int32_t *h_b, int32_t *e_b, int32_t *h_c, int8_t *direction, int64_t Wmax, int64_t dirCap,
+                                            const uint8_t *qs, const signed char *cb, const uint8_t *db, const int16_t *M,
+                                            int qLen, int dbLen, int score, int go, int ge, int &bw, int64_t &width_d, int8_t *&dl) {
+    int64_t width = 0;
     int mx = 0;
-    int8_t *dl = direction;
-    bool bad = false;
+    dl = direction;
     do {
         width = (int64_t)bw * 2 + 3;
         width_d = (int64_t)bw * 2 + 1;
-        if (width + 1 > Wmax || width_d * qLen * 3 > dirCap) { bad = true; break; }
+        if (width + 1 > Wmax || width_d * qLen * 3 > dirCap) return false;
         for (int j = 1; j < width - 1; j++) h_b[j] = 0;
         for (int i = 0; i < qLen; i++) {
             int beg = 0, end = dbLen - 1, u = 0, edge, f, j;
@@ -517,25 +506,119 @@ __global__ void sw_traceback_kernel(TbArgs A) {
         }
         bw *= 2;
     } while (mx < score);
+    bw /= 2;
+    return true;
+}
+
+// Walk back from the bottom-right cell (StripedSmithWaterman.cpp:882-960); ops are produced last-to-first into cig[0..n).
+// Returns false on a direction code outside 1..5 or when cigCap is reached ("Trace back error").
+__device__ __forceinline__ bool banded_walk(const int8_t *dl, int64_t width_d, int bw, int qLen, int dbLen, char *cig, uint32_t cigCap,
+                                            uint32_t &n) {
+    int i = qLen - 1, j = dbLen - 1, st = 2;
+    n = 0;
+    while (i > 0 || j > 0) {
+        const int t1 = band_d(bw, i, j, st);
+        char op = 0;
+        switch (dl[t1]) {
+            case 1: --i; --j; st = 2; dl -= width_d * 3; op = 'M'; break;
+            case 2: --i; st = 0; dl -= width_d * 3; op = 'I'; break;
+            case 3: --i; st = 2; dl -= width_d * 3; op = 'I'; break;
+            case 4: --j; st = 1; op = 'D'; break;
+            case 5: --j; st = 2; op = 'D'; break;
+            default: return false;
+        }
+        if (n + 1 >= cigCap) return false;
+        cig[n++] = op;
+    }
+    return true;
+}
+
+#define TB_FAST_BW 4                                   // widest band of the local-memory path
+#define TB_FAST_W (2 * TB_FAST_BW + 5)                 // ints per row array
+#define TB_FAST_QLEN 21
+#define TB_FAST_DIR ((2 * TB_FAST_BW + 1) * TB_FAST_QLEN * 3)
+#define TB_FAST_CIG 64
+__global__ void sw_traceback_kernel(TbArgs A) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= A.nAcc) return;
+    const uint32_t pair = A.acc[k];
+    PairOut o = A.out[pair];
+    if (o.status != 1) return;
+    const uint32_t qi = A.pairQ[pair], ti = A.pairT[pair];
+    const uint64_t qo = A.qoff[qi];
+    const uint8_t *qs = A.q + qo + o.qStart;
+    const signed char *cb = A.qcb + qo + o.qStart;
+    const uint8_t *db = A.tres + A.toff[ti] + o.tStart;
+    const int16_t *M = A.mat->align;
+    const int dbLen = o.tEnd - o.tStart + 1, qLen = o.qEnd - o.qStart + 1;
+    const int score = o.score, go = A.go, ge = A.ge;
+    const int bw0 = abs(dbLen - qLen) + 1;
     char *cig = A.cigar + A.cigOff[k];
     const uint32_t cigCap = (uint32_t)(A.cigOff[k + 1] - A.cigOff[k]);
     uint32_t n = 0;
-    if (!bad) {
-        bw /= 2;
-        int i = qLen - 1, j = dbLen - 1, st = 2;
-        while (i > 0 || j > 0) {
-            const int t1 = band_d(bw, i, j, st);
-            char op = 0;
-            switch (dl[t1]) {
-                case 1: --i; --j; st = 2; dl -= width_d * 3; op = 'M'; break;
-                case 2: --i; st = 0; dl -= width_d * 3; op = 'I'; break;
-                case 3: --i; st = 2; dl -= width_d * 3; op = 'I'; break;
-                case 4: --j; st = 1; op = 'D'; break;
-                case 5: --j; st = 2; op = 'D'; break;
-                default: bad = true; break;
+    bool bad = false, done = false;
+    // Spacer-sized alignments: the band arrays, the direction bytes and the ops stay in thread-local memory (interleaved
+    // across the warp, L1-cached) -- same arithmetic, same order.  Anything that outgrows them (band doubled past
+    // TB_FAST_BW, long aligned span) replays the whole loop on the global scratch slice below.
+    if (bw0 <= TB_FAST_BW && qLen <= TB_FAST_QLEN && qLen + dbLen + 2 <= TB_FAST_CIG) {
+        int32_t hL[3 * TB_FAST_W];
+        int8_t dirL[TB_FAST_DIR];
+        char cigL[TB_FAST_CIG];
+        for (int x = 0; x < 3 * TB_FAST_W; x++) hL[x] = 0;
+        int bw = bw0;
+        int64_t width_d = 0;
+        int8_t *dl = dirL;
+        if (banded_fill(hL, hL + TB_FAST_W, hL + 2 * TB_FAST_W, dirL, TB_FAST_W, TB_FAST_DIR, qs, cb, db, M, qLen, dbLen, score, go, ge,
+                        bw, width_d, dl)) {
+            done = true;
+            bad = !banded_walk(dl, width_d, bw, qLen, dbLen, cigL, min(cigCap, (uint32_t)TB_FAST_CIG), n);
+            if (!bad) {
+                cigL[n++] = 'M';
+                // reversed copy to the output + identities (Matcher.cpp:61-187)
+                int ids = 0, qi2 = 0, ti2 = 0;
+                for (uint32_t x = 0; x < n; x++) {
+                    const char op = cigL[n - 1 - x];
+                    cig[x] = op;
+                    if (op == 'M') { ids += (qs[qi2] == db[ti2]); qi2++; ti2++; }
+                    else if (op == 'I') qi2++;
+                    else ti2++;
+                }
+                o.cigLen = n;
+                o.nIdent = ids;
+                o.alnLen = (int)n;
             }
-            if (bad || n + 1 >= cigCap) { bad = true; break; }
-            cig[n++] = op;
+        }
+    }
+    if (!done) {
+        // scratch layout: [h_b | e_b | h_c] int32 each Wmax, then direction bytes
+        const uint64_t bytes = A.tbOff[k + 1] - A.tbOff[k];
+        unsigned char *base = A.tbScratch + A.tbOff[k];
+        int bwMax = bw0;
+        while (bwMax < max(qLen, dbLen)) bwMax *= 2;
+        const int64_t Wmax = (int64_t)bwMax * 2 + 3 + 2;
+        int32_t *h_b = reinterpret_cast<int32_t *>(base);
+        int32_t *e_b = h_b + Wmax;
+        int32_t *h_c = e_b + Wmax;
+        int8_t *direction = reinterpret_cast<int8_t *>(h_c + Wmax);
+        const int64_t dirCap = (int64_t)bytes - 3 * Wmax * 4;
+        for (int64_t x = 0; x < 3 * Wmax; x++) h_b[x] = 0;
+        int bw = bw0;
+        int64_t width_d = 0;
+        int8_t *dl = direction;
+        bad = !banded_fill(h_b, e_b, h_c, direction, Wmax, dirCap, qs, cb, db, M, qLen, dbLen, score, go, ge, bw, width_d, dl);
+        if (!bad) bad = !banded_walk(dl, width_d, bw, qLen, dbLen, cig, cigCap, n);
+        if (!bad) {
+            cig[n++] = 'M';
+            for (uint32_t a = 0, b = n - 1; a < b; a++, b--) { char tmp = cig[a]; cig[a] = cig[b]; cig[b] = tmp; }
+            int ids = 0, qi2 = 0, ti2 = 0;
+            for (uint32_t x = 0; x < n; x++) {
+                if (cig[x] == 'M') { ids += (qs[qi2] == db[ti2]); qi2++; ti2++; }
+                else if (cig[x] == 'I') qi2++;
+                else ti2++;
+            }
+            o.cigLen = n;
+            o.nIdent = ids;
+            o.alnLen = (int)n;
         }
     }
     if (bad) {
@@ -543,18 +626,6 @@ __global__ void sw_traceback_kernel(TbArgs A) {
         o.cigLen = 0;
         o.nIdent = 0;
         o.alnLen = max(abs(o.qEnd - o.qStart), abs(o.tEnd - o.tStart)) + 1;
-    } else {
-        cig[n++] = 'M';
-        for (uint32_t a = 0, b = n - 1; a < b; a++, b--) { char tmp = cig[a]; cig[a] = cig[b]; cig[b] = tmp; }
-        int ids = 0, qi2 = 0, ti2 = 0;
-        for (uint32_t x = 0; x < n; x++) {
-            if (cig[x] == 'M') { ids += (qs[qi2] == db[ti2]); qi2++; ti2++; }
-            else if (cig[x] == 'I') qi2++;
-            else ti2++;
-        }
-        o.cigLen = n;
-        o.nIdent = ids;
-        o.alnLen = (int)n;
     }
     o.cigOff = (uint32_t)A.cigOff[k];
     A.out[pair] = o;
@@ -759,8 +830,10 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
     SPB_CUDA(cudaMemsetAsync(c->s_e.p, 0, NP, st));
     // register kernel eligibility: segLen == 1 in both emulated SIMD kernels and at most 16 rows
     const int fastMaxL = std::min(SWF_ROWS, std::min(p->byte_lanes, p->word_lanes));
-    align_profile_kernel<<<Q, 64, 0, st>>>(c->d_q.as<uint8_t>(), c->d_qoff64.as<uint64_t>(), Q, c->d_mat.as<Matrices>(), p->comp_bias,
-                                           c->s_a.as<signed char>(), c->s_b.as<int>(), c->s_l.as<signed char>(), c->s_m.as<uint8_t>(),
+    int matMin = 0;
+    for (int i = 0; i < SPB_ALPHABET * SPB_ALPHABET; i++) matMin = std::min(matMin, (int)(signed char)c->hm.align[i]);
+    align_profile_kernel<<<(Q + 3) / 4, 128, 0, st>>>(c->d_q.as<uint8_t>(), c->d_qoff64.as<uint64_t>(), Q, c->d_mat.as<Matrices>(), p->comp_bias,
+                                           matMin, c->s_a.as<signed char>(), c->s_b.as<int>(), c->s_l.as<signed char>(), c->s_m.as<uint8_t>(),
                                            fastMaxL);
     SPB_CUDA(cudaGetLastError()); c->n_launches++;
     pair_key_kernel<<<(Q + 3) / 4, 128, 0, st>>>(c->d_pairoff.as<uint64_t>(), c->d_pairT.as<uint32_t>(), c->d_aoff.as<uint64_t>(),
