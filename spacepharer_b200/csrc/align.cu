@@ -726,13 +726,54 @@ __device__ __forceinline__ bool row_before(double ea, int ba, uint64_t la, uint3
     return ka < kb;
 }
 
-__global__ void sort_rows_kernel(const spb_aln *__restrict__ in, const uint64_t *__restrict__ rowOff, uint32_t Q,
+// One warp per query, rank sort from the packed rows into the output array.  The four sort fields of a query's rows are
+// staged in shared memory once (up to SR_CAP rows, i.e. any list --max-seqs 300 can produce); longer lists read them
+// from global memory.
+#define SR_CAP 320
+#define SR_WARPS 4
+__global__ void __launch_bounds__(SR_WARPS * 32) sort_rows_kernel(const spb_aln *__restrict__ in, const uint64_t *__restrict__ rowOff, uint32_t Q,
                                  const uint64_t *__restrict__ toff, const uint32_t *__restrict__ tkeys, spb_aln *__restrict__ out) {
-    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    __shared__ double s_e[SR_WARPS][SR_CAP];
+    __shared__ int s_b[SR_WARPS][SR_CAP];
+    __shared__ uint32_t s_l[SR_WARPS][SR_CAP], s_k[SR_WARPS][SR_CAP];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t q = blockIdx.x * SR_WARPS + wid;
     if (q >= Q) return;
-    const int lane = threadIdx.x & 31;
     const uint64_t o = rowOff[q];
     const uint32_t n = (uint32_t)(rowOff[q + 1] - o);
+    if (n == 0) return;
+    if (n == 1) {
+        if (lane == 0) out[o] = in[o];
+        return;
+    }
+    if (n <= SR_CAP) {
+        for (uint32_t i = lane; i < n; i += 32) {
+            const spb_aln &x = in[o + i];
+            const uint32_t t = x.target;
+            s_e[wid][i] = x.eval;
+            s_b[wid][i] = x.bits;
+            s_l[wid][i] = (uint32_t)min((unsigned long long)(toff[t + 1] - toff[t]), 0xFFFFFFFFull);
+            s_k[wid][i] = tkeys[t];
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < n; i += 32) {
+            const double ei = s_e[wid][i];
+            const int bi = s_b[wid][i];
+            const uint32_t li = s_l[wid][i], ki = s_k[wid][i];
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < n; j++) {
+                const double ej = s_e[wid][j];
+                const int bj = s_b[wid][j];
+                const uint32_t lj = s_l[wid][j], kj = s_k[wid][j];
+                // equal keys (the same target listed twice for a query) keep their input order
+                const bool before = row_before(ej, bj, lj, kj, ei, bi, li, ki);
+                const bool equal = !before && !row_before(ei, bi, li, ki, ej, bj, lj, kj);
+                rank += (before || (equal && j < i)) ? 1u : 0u;
+            }
+            out[o + rank] = in[o + i];
+        }
+        return;
+    }
     for (uint32_t i = lane; i < n; i += 32) {
         const spb_aln r = in[o + i];
         const uint64_t li = toff[r.target + 1] - toff[r.target];
@@ -744,7 +785,6 @@ __global__ void sort_rows_kernel(const spb_aln *__restrict__ in, const uint64_t 
             const uint32_t tj = x.target;
             const uint64_t lj = toff[tj + 1] - toff[tj];
             const uint32_t kj = tkeys[tj];
-            // equal keys (the same target listed twice for a query) keep their input order
             if (row_before(x.eval, x.bits, lj, kj, r.eval, r.bits, li, ki) ||
                 (j < i && !row_before(r.eval, r.bits, li, ki, x.eval, x.bits, lj, kj))) rank++;
         }
@@ -811,7 +851,13 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
     c->aln_stats.n_pairs = NP;
     c->n_acc = 0;
     c->n_cigar = 0;
-    if (NP == 0) { c->have_aln = true; return 0; }
+    if (NP == 0) {
+        if (c->d_rowoff.ensure(((size_t)Q + 1) * 8 + 64)) return 1;
+        SPB_CUDA(cudaMemsetAsync(c->d_rowoff.p, 0, ((size_t)Q + 1) * 8, st));
+        SPB_CUDA(cudaStreamSynchronize(st));
+        c->have_aln = true;
+        return 0;
+    }
     const uint32_t maxL = c->q_maxlen;
     const int Lpad = (int)((maxL + 3) & ~3u);
     const size_t perWarp = (size_t)SPB_ALPHABET * Lpad + (size_t)Lpad * 32 * sizeof(short2);
@@ -991,6 +1037,33 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
         SPB_CUDA(cudaGetLastError()); c->n_launches++;
         c->n_cigar = cigTotal;
     }
+    // ---- result rows: per query in the order of Matcher::compareHits (part of the stage: `align` writes sorted entries)
+    {
+        // scratch: s_g packed rows, s_i row counts u32[Q+1] + u64[Q+1] widened
+        if (c->s_g.ensure(std::max<size_t>(nAcc, 1) * sizeof(spb_aln)) || c->d_rows.ensure(std::max<size_t>(nAcc, 1) * sizeof(spb_aln)) ||
+            c->s_i.ensure(((size_t)Q + 1) * 12 + 64) || c->d_rowoff.ensure(((size_t)Q + 1) * 8 + 64)) return 1;
+        uint32_t *cnt32 = c->s_i.as<uint32_t>();
+        uint64_t *cnt64 = reinterpret_cast<uint64_t *>(c->s_i.as<unsigned char>() + (((size_t)Q + 1) * 4 + 15) / 16 * 16);
+        uint64_t *rowOff = c->d_rowoff.as<uint64_t>();
+        SPB_CUDA(cudaMemsetAsync(cnt32, 0, ((size_t)Q + 1) * 4, st));
+        if (nAcc) {
+            row_count_kernel<<<(nAcc + 255) / 256, 256, 0, st>>>(c->d_acc.as<uint32_t>(), nAcc, c->d_pairQ.as<uint32_t>(), cnt32);
+            SPB_CUDA(cudaGetLastError()); c->n_launches++;
+        }
+        count_widen_kernel<<<(Q + 1 + 255) / 256, 256, 0, st>>>(cnt32, Q, cnt64);
+        SPB_CUDA(cudaGetLastError()); c->n_launches++;
+        SPB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, cnt64, rowOff, (int)(Q + 1), st));
+        if (c->s_cub.ensure(tmpBytes)) return 1;
+        SPB_CUDA(cub::DeviceScan::ExclusiveSum(c->s_cub.p, tmpBytes, cnt64, rowOff, (int)(Q + 1), st));
+        if (nAcc) {
+            pack_rows_kernel<<<(nAcc + 255) / 256, 256, 0, st>>>(c->d_pairout.as<PairOut>(), c->d_acc.as<uint32_t>(), nAcc,
+                                                                 c->d_pairQ.as<uint32_t>(), c->d_pairT.as<uint32_t>(), c->s_g.as<spb_aln>());
+            SPB_CUDA(cudaGetLastError()); c->n_launches++;
+            sort_rows_kernel<<<(Q + SR_WARPS - 1) / SR_WARPS, SR_WARPS * 32, 0, st>>>(c->s_g.as<spb_aln>(), rowOff, Q, c->d_aoff.as<uint64_t>(),
+                                                                                     c->d_akeys.as<uint32_t>(), c->d_rows.as<spb_aln>());
+            SPB_CUDA(cudaGetLastError()); c->n_launches++;
+        }
+    }
     SPB_CUDA(cudaEventRecord(c->ev3, st));
     SPB_CUDA(cudaStreamSynchronize(st));
     SPB_CUDA(cudaEventElapsedTime(&ms, c->ev2, c->ev3));
@@ -1092,42 +1165,17 @@ extern "C" int spb_align_fetch(spb_ctx *c, spb_align_result **out) {
     if (!res->offsets || !res->rows || !res->cigar_ops) { spb_free_align_result(res); return 1; }
     res->n_cigar = c->n_cigar;
     res->n_rows = nAcc;
-    // scratch: s_g packed rows, s_h sorted rows, s_i row counts u32[Q+1] + u64[Q+1] widened, s_b row offsets u64[Q+1]
-    if (c->s_g.ensure(std::max<size_t>(nAcc, 1) * sizeof(spb_aln)) || c->s_h.ensure(std::max<size_t>(nAcc, 1) * sizeof(spb_aln)) ||
-        c->s_i.ensure(((size_t)Q + 1) * 12 + 64) || c->s_b.ensure(((size_t)Q + 1) * 8 + 64)) { spb_free_align_result(res); return 1; }
-    uint32_t *cnt32 = c->s_i.as<uint32_t>();
-    uint64_t *cnt64 = reinterpret_cast<uint64_t *>(c->s_i.as<unsigned char>() + (((size_t)Q + 1) * 4 + 15) / 16 * 16);
-    uint64_t *rowOff = c->s_b.as<uint64_t>();
-    cudaError_t e = cudaMemsetAsync(cnt32, 0, ((size_t)Q + 1) * 4, st);
-    if (e == cudaSuccess && nAcc) {
-        row_count_kernel<<<(nAcc + 255) / 256, 256, 0, st>>>(c->d_acc.as<uint32_t>(), nAcc, c->d_pairQ.as<uint32_t>(), cnt32);
-        e = cudaGetLastError(); c->n_launches++;
-    }
-    if (e == cudaSuccess) {
-        count_widen_kernel<<<(Q + 1 + 255) / 256, 256, 0, st>>>(cnt32, Q, cnt64);
-        e = cudaGetLastError(); c->n_launches++;
-    }
-    size_t tmpBytes = 0;
-    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, cnt64, rowOff, (int)(Q + 1), st);
-    if (e == cudaSuccess && c->s_cub.ensure(tmpBytes)) { spb_free_align_result(res); return 1; }
-    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(c->s_cub.p, tmpBytes, cnt64, rowOff, (int)(Q + 1), st);
-    if (e == cudaSuccess && nAcc) {
-        pack_rows_kernel<<<(nAcc + 255) / 256, 256, 0, st>>>(c->d_pairout.as<PairOut>(), c->d_acc.as<uint32_t>(), nAcc,
-                                                             c->d_pairQ.as<uint32_t>(), c->d_pairT.as<uint32_t>(), c->s_g.as<spb_aln>());
-        e = cudaGetLastError(); c->n_launches++;
-        if (e == cudaSuccess) {
-            sort_rows_kernel<<<(Q + 3) / 4, 128, 0, st>>>(c->s_g.as<spb_aln>(), rowOff, Q, c->d_aoff.as<uint64_t>(), c->d_akeys.as<uint32_t>(),
-                                                          c->s_h.as<spb_aln>());
-            e = cudaGetLastError(); c->n_launches++;
-        }
-        if (e == cudaSuccess) e = cudaMemcpyAsync(res->rows, c->s_h.p, (size_t)nAcc * sizeof(spb_aln), cudaMemcpyDeviceToHost, st);
+    const uint64_t *rowOff = c->d_rowoff.as<uint64_t>();
+    cudaError_t e = cudaSuccess;
+    if (nAcc) {
+        e = cudaMemcpyAsync(res->rows, c->d_rows.p, (size_t)nAcc * sizeof(spb_aln), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess && c->n_cigar) e = cudaMemcpyAsync(res->cigar_ops, c->d_cig.p, c->n_cigar, cudaMemcpyDeviceToHost, st);
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(res->offsets, rowOff, ((size_t)Q + 1) * 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (getenv("SPB_DEBUG")) {
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
-        fprintf(stderr, "spb_align_fetch: %u rows, %llu CIGAR bytes, %.3f ms (pack + sort + D2H)\n", nAcc, (unsigned long long)c->n_cigar, ms);
+        fprintf(stderr, "spb_align_fetch: %u rows, %llu CIGAR bytes, %.3f ms (D2H)\n", nAcc, (unsigned long long)c->n_cigar, ms);
     }
     if (e != cudaSuccess) {
         spb_free_align_result(res);

@@ -148,6 +148,8 @@ struct spb_ctx {
     spb::DevBuf d_acc;            // u32[n_acc] accepted pair indices
     uint64_t n_acc = 0, n_cigar = 0;
     spb::DevBuf d_cig;            // char[n_cigar]
+    spb::DevBuf d_rows;           // spb_aln[n_acc] result rows, per query in the order of Matcher::compareHits
+    spb::DevBuf d_rowoff;         // u64[Q+1]
     spb_align_result aln_stats;
 
     // ---- pinned result staging ----
