@@ -101,7 +101,7 @@ struct spb_ctx {
     spb::DevBuf d_toff;           // u32[T+1]
     spb::DevBuf d_koff;           // u32[20^6 + 1] CSR offsets
     spb::DevBuf d_post;           // u64[n_post]: id << 16 | pos
-    spb::DevBuf d_direct;         // u64[20^6] packed direct table: 0 empty | 1<<63 | posting (one target) | len << 32 | offset
+    spb::DevBuf d_direct;         // ulonglong2[20^6] packed direct table: up to two postings inline, else len << 32 | offset (index.cu)
     uint64_t n_post = 0, n_kmers_nonempty = 0;
     spb::DevBuf d_row3;           // u32[8000][8000]: (score + 256) << 16 | 3-mer index
     spb::DevBuf d_cnt3;           // u16[8000][512]: #entries with score >= v

@@ -144,17 +144,19 @@ __global__ void fill_offsets_kernel(const uint32_t *__restrict__ pk, uint64_t nP
 }
 
 // Packed direct table read by the warp-per-query prefilter: one 8-byte entry per k-mer.
-//   0                         no target contains the k-mer
-//   1 << 63 | id << 16 | pos  exactly one target: the posting itself (no second memory access)
-//   len << 32 | offset        len >= 2 postings at post[offset ..)
+//   x = 0                                  no target contains the k-mer
+//   x = 1 << 63 | id << 16 | pos, y = 0    exactly one target: the posting itself (no second memory access)
+//   x, y = 1 << 63 | posting               exactly two targets: both postings inline (ascending id, like the list)
+//   x = len << 32 | offset                 len >= 3 postings at post[offset ..)
 __global__ void build_direct_kernel(const uint32_t *__restrict__ koff, const uint64_t *__restrict__ post,
-                                    uint64_t *__restrict__ direct) {
+                                    ulonglong2 *__restrict__ direct) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= SPB_NK) return;
     const uint32_t o0 = koff[k], len = koff[k + 1] - o0;
-    uint64_t v = 0;
-    if (len == 1) v = (1ull << 63) | post[o0];
-    else if (len > 1) v = ((uint64_t)len << 32) | o0;
+    ulonglong2 v = make_ulonglong2(0ull, 0ull);
+    if (len == 1) v.x = (1ull << 63) | post[o0];
+    else if (len == 2) { v.x = (1ull << 63) | post[o0]; v.y = (1ull << 63) | post[o0 + 1]; }
+    else if (len > 2) v.x = ((uint64_t)len << 32) | o0;
     direct[k] = v;
 }
 
@@ -294,8 +296,8 @@ extern "C" int spb_index_build(spb_ctx *c, const uint8_t *residues, const uint64
         if (c->d_post.ensure(64)) { cleanup(); return 1; }
         IDX_CUDA(cudaMemsetAsync(c->d_koff.p, 0, ((size_t)SPB_NK + 2) * 4, st));
     }
-    if (c->d_direct.ensure((size_t)SPB_NK * 8)) { cleanup(); return 1; }
-    build_direct_kernel<<<(SPB_NK + 255) / 256, 256, 0, st>>>(c->d_koff.as<uint32_t>(), c->d_post.as<uint64_t>(), c->d_direct.as<uint64_t>());
+    if (c->d_direct.ensure((size_t)SPB_NK * 16)) { cleanup(); return 1; }
+    build_direct_kernel<<<(SPB_NK + 255) / 256, 256, 0, st>>>(c->d_koff.as<uint32_t>(), c->d_post.as<uint64_t>(), c->d_direct.as<ulonglong2>());
     IDX_CUDA(cudaGetLastError()); c->n_launches++;
     unsigned long long nonEmpty = 0;
     IDX_CUDA(cudaMemcpyAsync(&nonEmpty, d_nNonEmpty, 8, cudaMemcpyDeviceToHost, st));

@@ -71,7 +71,7 @@ struct PrefArgs {
     uint32_t *status;        // per query: ST_*
     uint32_t *need;          // per query: records needed when status == ST_CAPACITY
     // warp-per-query kernel
-    const uint64_t *direct;  // [20^6] packed k-mer table (index.cu)
+    const ulonglong2 *direct;  // [20^6] packed k-mer table, 16 bytes per k-mer (index.cu)
     uint64_t *hitScratch;    // [warps in the grid][hitCap] hit records, L2-resident
     uint32_t hitCap;
     unsigned int *qCounter;  // dynamic query scheduler
@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
 #define PW_FCAP_SOLO 512     // per-target winners of one query (slots behind the hit records)
 #define PW_FCAP_TEAM 4096
 #define PW_BIG 1024          // TEAM = 8: records the CTA sorts at once in the final stage
-#define PW_U 4               // k-mer lookups per lane in flight
+#define PW_U 2               // consecutive similar k-mers per lane (16-byte table entries: as many bytes in flight as 4 x 8)
 #define ST_TEAM 4u
 
 struct Run { uint16_t a0, n2, cum, w; };   // cum holds the first concatenated row index until the prefix pass
@@ -734,7 +734,7 @@ __device__ __noinline__ void pw_emit(bool have, uint64_t pe, uint32_t k, uint32_
 
 // posting lists of the k-mers held by the lanes of a warp (len == 0: none), flattened over the warp: element p of the
 // concatenated lists belongs to the last lane whose exclusive prefix is <= p (coalesced reads, no per-lane walks)
-__device__ __noinline__ void pw_walk(uint32_t len, uint32_t off, uint32_t w, uint32_t kb, const uint64_t *__restrict__ post,
+__device__ __noinline__ void pw_walk(uint32_t len, uint32_t off, uint32_t w, uint32_t kb, uint32_t kmul, const uint64_t *__restrict__ post,
                                      uint32_t *nHitsCtr, uint64_t *scratch, uint32_t HCAP, uint32_t *seen1, uint32_t *seen2, int hashShift) {
     const int lane = threadIdx.x & 31;
     const uint32_t inc = (uint32_t)warp_incl_scan_ool((int)len);
@@ -756,7 +756,7 @@ __device__ __noinline__ void pw_walk(uint32_t len, uint32_t off, uint32_t w, uin
         const bool have = pp < T;
         uint64_t pe = 0;
         if (have) pe = __ldg(post + srcOff + (pp - srcEx));
-        pw_emit(have, pe, kb + (uint32_t)j, srcW, nHitsCtr, scratch, HCAP, seen1, seen2, hashShift);
+        pw_emit(have, pe, kb + (uint32_t)j * kmul, srcW, nHitsCtr, scratch, HCAP, seen1, seen2, hashShift);
     }
 }
 
@@ -952,45 +952,95 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
         const uint32_t K = S.v_K;
         const int nRuns = (int)S.v_nRuns;
         // ---------------- one pass over the hit stream ----------------
+        // Lane l of a pass owns the PW_U consecutive similar k-mers k0 + l * PW_U ...: one run search and one division give
+        // (outer neighbour, inner neighbour) of the first, the others follow by stepping.  A table entry carries up to two
+        // postings inline (95 % of the k-mers of a GenBank-phage-sized index occur in at most two ORFs), so most hits are
+        // written straight from the entry: one scan, one reservation, no second memory access.  Longer lists are walked
+        // warp-wide (pw_walk).
         if (S.v_slow == ST_OK) {
+            constexpr int HSH = SOLO ? 19 : 17;
             for (uint32_t k0 = (uint32_t)tw * (32 * PW_U); k0 < K; k0 += TEAM * 32 * PW_U) {
-                uint64_t d[PW_U];
-                uint32_t ww[PW_U];
+                const uint32_t kBeg = k0 + (uint32_t)lane * PW_U;
+                ulonglong2 d[PW_U];
+                uint32_t wPack = 0;
 #pragma unroll
-                for (int u = 0; u < PW_U; u++) {
-                    const uint32_t k = k0 + (uint32_t)(u * 32 + lane);
-                    d[u] = 0;
-                    ww[u] = 0;
-                    if (k < K) {
-                        int lo = 0, hi = nRuns - 1;   // largest r with runs[r].cum <= k
-                        while (lo < hi) {
-                            const int mid = (lo + hi + 1) >> 1;
-                            if ((uint32_t)runs[mid].cum <= k) lo = mid; else hi = mid - 1;
+                for (int u = 0; u < PW_U; u++) d[u] = make_ulonglong2(0ull, 0ull);
+                if (kBeg < K) {
+                    int lo = 0, hi = nRuns - 1;   // largest r with runs[r].cum <= kBeg
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if ((uint32_t)runs[mid].cum <= kBeg) lo = mid; else hi = mid - 1;
+                    }
+                    int ri = lo;
+                    Run r = runs[ri];
+                    uint32_t nextCum = (ri + 1 < nRuns) ? (uint32_t)runs[ri + 1].cum : 0xFFFFFFFFu;
+                    const uint32_t rel = kBeg - (uint32_t)r.cum;
+                    uint32_t da = rel / (uint32_t)r.n2;
+                    uint32_t b = rel - da * (uint32_t)r.n2;
+                    const uint32_t *row1 = A.row3 + (size_t)S.x1[r.w] * SPB_N3 + (uint32_t)r.a0;
+                    const uint32_t *row2 = A.row3 + (size_t)S.x2[r.w] * SPB_N3;
+                    uint32_t i1 = __ldg(row1 + da) & 0xFFFFu;
+#pragma unroll
+                    for (int u = 0; u < PW_U; u++) {
+                        const uint32_t k = kBeg + (uint32_t)u;
+                        if (k < K) {
+                            const uint32_t i2 = __ldg(row2 + b) & 0xFFFFu;
+                            d[u] = __ldg(A.direct + (i1 + 8000u * i2));
+                            wPack |= (uint32_t)r.w << (8 * u);
+                            if (u + 1 < PW_U && k + 1 < K) {
+                                if (++b == (uint32_t)r.n2) {
+                                    b = 0;
+                                    da++;
+                                    if (k + 1 >= nextCum) {   // next run holding a k-mer (runs without inner neighbours share their cum)
+                                        ri++;
+                                        while (ri + 1 < nRuns && (uint32_t)runs[ri + 1].cum <= k + 1) ri++;
+                                        r = runs[ri];
+                                        nextCum = (ri + 1 < nRuns) ? (uint32_t)runs[ri + 1].cum : 0xFFFFFFFFu;
+                                        da = 0;
+                                        row1 = A.row3 + (size_t)S.x1[r.w] * SPB_N3 + (uint32_t)r.a0;
+                                        row2 = A.row3 + (size_t)S.x2[r.w] * SPB_N3;
+                                    }
+                                    i1 = __ldg(row1 + da) & 0xFFFFu;
+                                }
+                            }
                         }
-                        const Run r = runs[lo];
-                        const uint32_t rel = k - (uint32_t)r.cum;
-                        const uint32_t da = rel / (uint32_t)r.n2;
-                        const uint32_t b = rel - da * (uint32_t)r.n2;
-                        const uint32_t i1 = __ldg(A.row3 + (size_t)S.x1[r.w] * SPB_N3 + (uint32_t)r.a0 + da) & 0xFFFFu;
-                        const uint32_t i2 = __ldg(A.row3 + (size_t)S.x2[r.w] * SPB_N3 + b) & 0xFFFFu;
-                        ww[u] = r.w;
-                        d[u] = __ldg(A.direct + (i1 + 8000u * i2));
                     }
                 }
-                auto emit = [&](bool have, uint64_t pe, uint32_t k, uint32_t w) {
-                    pw_emit(have, pe, k, w, &S.v_nHits, scratch, HCAP, S.seen1, S.seen2, SOLO ? 19 : 17);
-                };
+                // inline postings
+                uint32_t cnt = 0;
+#pragma unroll
+                for (int u = 0; u < PW_U; u++) cnt += (uint32_t)(d[u].x >> 63) + (uint32_t)((d[u].x >> 63) & (d[u].y >> 63));
+                const uint32_t inc = (uint32_t)warp_incl_scan_ool((int)cnt);
+                const uint32_t T = __shfl_sync(0xffffffffu, inc, 31);
+                if (T) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&S.v_nHits, T);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    uint32_t dst = base + inc - cnt;
+#pragma unroll
+                    for (int s2 = 0; s2 < 2 * PW_U; s2++) {
+                        const int u = s2 >> 1;
+                        const uint64_t pe = (s2 & 1) ? d[u].y : d[u].x;
+                        if ((pe >> 63) && (d[u].x >> 63)) {
+                            const uint32_t id = (uint32_t)(pe >> 16);
+                            const uint32_t w = (wPack >> (8 * u)) & 0xFFu;
+                            const uint32_t dg = (w - (uint32_t)(pe & 0xFFFFull)) & 0xFFFFu;
+                            if (dst < HCAP) __stcg(scratch + dst, ((uint64_t)id << 32) | ((uint64_t)(kBeg + (uint32_t)u) << 16) | dg);
+                            dst++;
+                            const uint32_t h = (id * 2654435761u) >> HSH;
+                            const uint32_t bm = 1u << (h & 31);
+                            const uint32_t old = atomicOr(&S.seen1[h >> 5], bm);
+                            if ((old & bm) || (dg & 0xFFu) == 0u) atomicOr(&S.seen2[h >> 5], bm);
+                        }
+                    }
+                }
+                // posting lists of the k-mers in three or more targets, flattened over the warp
 #pragma unroll
                 for (int u = 0; u < PW_U; u++) {
-                    const uint64_t dv = d[u];
-                    const uint32_t kb = k0 + (uint32_t)(u * 32);
-                    const bool single = (dv >> 63) != 0;
-                    // k-mers of exactly one target carry their posting inline
-                    emit(single, dv & 0x0000FFFFFFFFFFFFull, kb + lane, ww[u]);
-                    // posting lists of the other k-mers, flattened over the warp
-                    const uint32_t len = single ? 0u : (uint32_t)(dv >> 32);
+                    const uint32_t len = (d[u].x >> 63) ? 0u : (uint32_t)(d[u].x >> 32);
                     if (__any_sync(0xffffffffu, len != 0u))
-                        pw_walk(len, (uint32_t)dv, ww[u], kb, A.post, &S.v_nHits, scratch, HCAP, S.seen1, S.seen2, SOLO ? 19 : 17);
+                        pw_walk(len, (uint32_t)d[u].x, (wPack >> (8 * u)) & 0xFFu, k0 + (uint32_t)u, PW_U, A.post, &S.v_nHits, scratch, HCAP,
+                                S.seen1, S.seen2, HSH);
                 }
             }
         }
@@ -1671,7 +1721,7 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
         // flags ST_TEAM (long similar-k-mer lists) are listed on the device and taken by the TEAM = 8 launch, which reads
         // the list length from device memory -- no host round trip in between.
         const int soloBlocks = c->n_sm * 8, teamBlocks = c->n_sm * 4;
-        A.direct = c->d_direct.as<uint64_t>();
+        A.direct = c->d_direct.as<ulonglong2>();
         const uint32_t hitCapSolo = 8192, hitCapTeam = 32768;
         A.kCapSolo = 4096;
         const size_t sliceSolo = 2 * (size_t)hitCapSolo + 2 * PW_FCAP_SOLO, sliceTeam = 2 * (size_t)hitCapTeam + 2 * PW_FCAP_TEAM;
