@@ -7,6 +7,14 @@
 //   spb200 prefilter <queryDB> <targetDB> <prefilterDB> [flags]     Prefiltering (M/prefiltering/Prefiltering.cpp)
 //   spb200 align     <queryDB> <targetDB> <prefilterDB> <alnDB> [flags]   Alignment (M/alignment/Alignment.cpp)
 //   spb200 search    <queryDB> <targetDB> <alnDB> [flags]           both steps with the hit lists kept in HBM
+// and the set-level stages that consume the alignment DB in predictmatch (data/predictmatch.sh:57-116; setscore.h):
+//   spb200 besthitperset <querySetDB> <targetSetDB> <alnDB> <outDB> [--simple-best-hit 1]
+//   spb200 mergeresultsbyset <querySetDB>_set_to_member <resultDB> <outDB>
+//   spb200 combinescore <querySetDB> <targetSetDB> <mergedDB> <outDB> <tmpDir>
+//   spb200 filtermatchbyfdr <cScoreDB> <controlcScoreDB> <matchDB> [--fdr 0.05 --report-fdr 0]
+//   spb200 predictmatch <querySetDB> <targetSetDB> <controlTargetSetDB> <matchDB> <tmpDir> [search flags, --fdr ...]
+//       search against the target and the reversed-ORF control setDB on the GPU, then the four stages in memory;
+//       writes the `match` DB of predictmatch.sh (--perform-nucl-aln 0 branch).
 // Host-only helpers used by the CPU tests: dumpmatrix, dbcopy, showparams.
 // Errors follow the reference: message on stderr, exit code 1 (Debug(Debug::ERROR) ... EXIT(EXIT_FAILURE)).
 #include <ctype.h>
@@ -29,6 +37,7 @@
 
 #include "../../../include/spb200.h"
 #include "db_io.h"
+#include "setscore.h"
 #include "submat.h"
 
 using namespace spbhost;
@@ -60,6 +69,9 @@ struct Params {
     int device = 0, binSize = 0, byteLanes = 32, wordLanes = 16;
     std::string gumbel;
     long batch = 1000000;
+    // set-level stages (M/commons/Parameters.cpp:217,2277; src/commons/LocalParameters.h:75-77,171-176)
+    int simpleBestHit = 1, reportFdr = 0, performNuclAln = 1, keepIntermediate = 0;
+    float fdr = 0.05f;
 };
 
 struct FlagDef { const char *name; int kind; void *dst; };   // kind: 0 int, 1 float, 2 double, 3 string, 4 ignored
@@ -85,7 +97,10 @@ std::vector<FlagDef> flag_table(Params &p) {
         {"--db-load-mode", 4, nullptr}, {"--pca", 4, nullptr}, {"--pcb", 4, nullptr}, {"--alignment-output-mode", 4, nullptr},
         {"--wrapped-scoring", 4, nullptr}, {"--realign-score-bias", 4, nullptr}, {"--realign-max-seqs", 4, nullptr},
         {"--zdrop", 4, nullptr}, {"--local-tmp", 4, nullptr}, {"--taxon-list", 4, nullptr}, {"--exhaustive-search-filter", 4, nullptr},
+        {"--simple-best-hit", 0, &p.simpleBestHit}, {"--fdr", 1, &p.fdr}, {"--report-fdr", 0, &p.reportFdr},
+        {"--perform-nucl-aln", 0, &p.performNuclAln}, {"--tax-fdr", 4, nullptr}, {"--remove-tmp-files", 4, nullptr},
         // spb200-specific
+        {"--keep-intermediate", 0, &p.keepIntermediate},
         {"--device", 0, &p.device}, {"--bin-size", 0, &p.binSize}, {"--byte-lanes", 0, &p.byteLanes}, {"--word-lanes", 0, &p.wordLanes},
         {"--gumbel", 3, &p.gumbel}, {"--batch", 0, nullptr},
     };
@@ -393,7 +408,10 @@ void check_align_params(const Params &p) {
     if (!(p.addBacktrace == 1 || p.alignmentMode == 3)) throw Fail("only the -a 1 (backtrace) output of the predictmatch search is implemented");
 }
 
-void write_alignment_rows(const Params &p, const spb_align_result *r, const SeqSet &Q, size_t b0, const SeqSet &T, DBWriter &out) {
+// rows of one batch as text, one entry per query (Matcher::resultToBuffer, M/alignment/Matcher.cpp:323-370); sink(thread,
+// batch-local query index, payload) is called once per query from an OpenMP team
+template <class Sink>
+void format_alignment_rows(const Params &p, const spb_align_result *r, const SeqSet &Q, size_t b0, const SeqSet &T, Sink sink) {
 #pragma omp parallel num_threads(p.threads)
     {
         int th = 0;
@@ -419,9 +437,13 @@ void write_alignment_rows(const Params &p, const spb_align_result *r, const SeqS
                 buf += cig;
                 buf.push_back('\n');
             }
-            out.write(th, Q.keys[b0 + (size_t)i], buf.data(), buf.size());
+            sink(th, (size_t)i, buf);
         }
     }
+}
+
+void write_alignment_rows(const Params &p, const spb_align_result *r, const SeqSet &Q, size_t b0, const SeqSet &T, DBWriter &out) {
+    format_alignment_rows(p, r, Q, b0, T, [&](int th, size_t i, const std::string &buf) { out.write(th, Q.keys[b0 + i], buf.data(), buf.size()); });
 }
 
 int run_align(int argc, const char **argv) {
@@ -493,17 +515,14 @@ int run_align(int argc, const char **argv) {
     return 0;
 }
 
-// both steps, hit lists stay in HBM (what blastp.sh does with a pref DB in between)
-int run_search(int argc, const char **argv) {
-    Params p;
-    parse_args(argc, argv, 2, 3, p);
-    check_search_params(p);
-    check_align_params(p);
+// both steps, hit lists stay in HBM (what blastp.sh does with a pref DB in between); sink(thread, query key, rows text)
+template <class Sink>
+void search_dbs(const Params &p, const std::string &qName, const std::string &tName, Sink sink) {
     Engine E;
     E.open(p);
     DBReader qdb, tdb;
-    qdb.open(p.db[0]);
-    tdb.open(p.db[1]);
+    qdb.open(qName);
+    tdb.open(tName);
     SeqSet Q, T;
     load_sequences(qdb, E.seed, Q);
     load_sequences(tdb, E.seed, T);
@@ -520,8 +539,6 @@ int run_search(int argc, const char **argv) {
     pp.emit_trunc_keys = 0;
     spb_align_params ap;
     fill_align_params(p, E, tdb.aminoAcidDBSize(), &ap);
-    DBWriter out;
-    out.open(p.db[2], DBTYPE_ALIGNMENT_RES, p.threads);
     const size_t nq = Q.keys.size();
     for (size_t b0 = 0, b1 = 0; b0 < nq; b0 = b1) {
         b1 = std::min(nq, b0 + (size_t)p.batch);
@@ -533,10 +550,151 @@ int run_search(int argc, const char **argv) {
         check(spb_align_resident(E.ctx, &ap), "spb_align_resident");
         spb_align_result *r = nullptr;
         check(spb_align_fetch(E.ctx, &r), "spb_align_fetch");
-        write_alignment_rows(p, r, Q, b0, T, out);
+        format_alignment_rows(p, r, Q, b0, T, [&](int th, size_t i, const std::string &buf) { sink(th, Q.keys[b0 + i], buf); });
         spb_free_align_result(r);
     }
+}
+
+int run_search(int argc, const char **argv) {
+    Params p;
+    parse_args(argc, argv, 2, 3, p);
+    check_search_params(p);
+    check_align_params(p);
+    DBWriter out;
+    out.open(p.db[2], DBTYPE_ALIGNMENT_RES, p.threads);
+    search_dbs(p, p.db[0], p.db[1], [&](int th, uint32_t key, const std::string &buf) { out.write(th, key, buf.data(), buf.size()); });
     out.close();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// set-level stages (setscore.h): module commands with the reference's argv, and the fused predictmatch
+// ---------------------------------------------------------------------------------------------------------
+int run_besthitperset(int argc, const char **argv) {
+    Params p;
+    parse_args(argc, argv, 2, 4, p);     // <queryDB> <targetDB> <resultDB> <outDB>  (besthitperset.cpp:123-128: db2, db3, db4)
+    KeyMap m2s, ssz;
+    m2s.load(p.db[1] + "_member_to_set");
+    ssz.load(p.db[1] + "_set_size");
+    TextDB in, out;
+    in.load(p.db[2]);
+    best_hit_per_set(in, m2s, ssz, p.simpleBestHit != 0, p.threads, out);
+    out.save(p.db[3], p.threads);
+    return 0;
+}
+
+int run_mergeresultsbyset(int argc, const char **argv) {
+    Params p;
+    parse_args(argc, argv, 2, 3, p);     // <setDB> <resultDB> <outDB>
+    TextDB sets, in, out;
+    sets.load(p.db[0]);
+    in.load(p.db[1]);
+    merge_results_by_set(sets, in, p.threads, out);
+    out.save(p.db[2], p.threads);
+    return 0;
+}
+
+int run_combinescore(int argc, const char **argv) {
+    Params p;
+    parse_args(argc, argv, 2, 5, p);     // <queryDB> <targetDB> <resultDB> <outDB> <tmpDir>
+    KeyMap m2s, qsz;
+    m2s.load(p.db[1] + "_member_to_set");
+    qsz.load(p.db[0] + "_set_size");
+    TextDB in, out;
+    in.load(p.db[2]);
+    combine_score(in, m2s, qsz, p.threads, out);
+    out.save(p.db[3], p.threads);
+    return 0;
+}
+
+void log_fdr(const Params &p, const FdrReport &rep) {
+    if (rep.mode == 0) {
+        log_line(p, "Combined score threshold is %f with FDR of %f.", rep.threshold, (double)p.fdr);
+        log_line(p, "%g matches passed combined score threshold.", rep.passed);
+    } else if (rep.mode == 1) {
+        if (p.fdr < 1) log_line(p, "Combined score list too short. Using threshold %f", 0.0);
+        else log_line(p, "FDR cutoff is set to 1. Printing all matches. ");
+    } else {
+        log_line(p, "Combined score list of control set is empty. Printing all matches");
+    }
+}
+
+int run_filtermatchbyfdr(int argc, const char **argv) {
+    Params p;
+    parse_args(argc, argv, 2, 3, p);     // <cScoreDB> <controlcScoreDB> <outDB>
+    TextDB pos, neg, out;
+    pos.load(p.db[0]);
+    neg.load(p.db[1]);
+    FdrReport rep;
+    filter_match_by_fdr(pos, neg, p.fdr, p.reportFdr, p.threads, out, &rep);
+    log_fdr(p, rep);
+    out.save(p.db[2], p.threads);
+    return 0;
+}
+
+// setpredictmatchDefaults (src/workflow/PredictMatch.cpp:9-31) + the search defaults the workflow passes down
+// (SURVEY.md 3.2): what `predictmatch` runs when no flag is given
+void set_predictmatch_defaults(Params &p) {
+    p.sensitivity = 5.7f;
+    p.evalue = 200;
+    p.addBacktrace = 1;
+    p.alignmentMode = 2;
+    p.kmerSize = 6;
+    p.spacedMode = 1;
+    p.spacedPattern = "11011101";
+    p.subMat = "nucl:nucleotide.out,aa:VTML40.out";
+    p.gapOpen = "nucl:10,aa:16";
+    p.gapExtend = "nucl:2,aa:2";
+    p.simpleBestHit = 1;
+}
+
+// data/predictmatch.sh:47-116 without the nucleotide re-alignment branch: search + besthitperset + mergeresultsbyset +
+// combinescore against the target and the control setDB, then filtermatchbyfdr; intermediates stay in memory
+int run_predictmatch(int argc, const char **argv) {
+    Params p;
+    set_predictmatch_defaults(p);
+    parse_args(argc, argv, 2, 5, p);     // <querySetDB> <targetSetDB> <controlTargetSetDB> <matchDB> <tmpDir>
+    check_search_params(p);
+    check_align_params(p);
+    if (p.performNuclAln != 0)
+        throw Fail("predictmatch: the nucleotide re-alignment branch (proteinaln2nucl + combineprotnuclaln) is not part of spb200; "
+                   "pass --perform-nucl-aln 0");
+    KeyMap qsz;
+    qsz.load(p.db[0] + "_set_size");
+    TextDB qSets;
+    qSets.load(p.db[0] + "_set_to_member");
+    TextDB cScore[2];
+    for (int side = 0; side < 2; side++) {
+        const std::string &tName = p.db[1 + side];
+        const char *suffix = side ? "_rev" : "";
+        // the search rows of every query frame, keyed like the alignment DB
+        DBReader qdb;
+        qdb.open(p.db[0]);
+        TextDB result;
+        result.dbtype = DBTYPE_ALIGNMENT_RES;
+        result.keys.resize(qdb.size());
+        for (size_t i = 0; i < qdb.size(); i++) result.keys[i] = qdb.byKey(i).key;
+        result.data.assign(result.keys.size(), std::string());
+        search_dbs(p, p.db[0], tName, [&](int, uint32_t key, const std::string &buf) { result.data[result.find(key)] = buf; });
+        KeyMap m2s, ssz;
+        m2s.load(tName + "_member_to_set");
+        ssz.load(tName + "_set_size");
+        TextDB aggregate, merged;
+        best_hit_per_set(result, m2s, ssz, p.simpleBestHit != 0, p.threads, aggregate);
+        merge_results_by_set(qSets, aggregate, p.threads, merged);
+        combine_score(merged, m2s, qsz, p.threads, cScore[side]);
+        if (p.keepIntermediate) {
+            result.save(p.db[4] + "/result" + suffix, p.threads);
+            aggregate.save(p.db[4] + "/aggregate" + suffix, p.threads);
+            merged.save(p.db[4] + "/aggregate_merged" + suffix, p.threads);
+            cScore[side].save(p.db[4] + "/cScore" + suffix, p.threads);
+        }
+    }
+    TextDB match;
+    FdrReport rep;
+    filter_match_by_fdr(cScore[0], cScore[1], p.fdr, p.reportFdr, p.threads, match, &rep);
+    log_fdr(p, rep);
+    match.save(p.db[3], p.threads);
     return 0;
 }
 
@@ -590,7 +748,7 @@ int run_showparams(int argc, const char **argv) {
 
 int main(int argc, const char **argv) {
     if (argc < 2) {
-        fprintf(stderr, "spb200 (%s): prefilter | align | search | dumpmatrix | dbcopy | showparams\n", spb_version());
+        fprintf(stderr, "spb200 (%s): prefilter | align | search | besthitperset | mergeresultsbyset | combinescore | filtermatchbyfdr | predictmatch | dumpmatrix | dbcopy | showparams\n", spb_version());
         return 1;
     }
     const std::string cmd = argv[1];
@@ -598,6 +756,11 @@ int main(int argc, const char **argv) {
         if (cmd == "prefilter") return run_prefilter(argc, argv);
         if (cmd == "align") return run_align(argc, argv);
         if (cmd == "search") return run_search(argc, argv);
+        if (cmd == "besthitperset") return run_besthitperset(argc, argv);
+        if (cmd == "mergeresultsbyset") return run_mergeresultsbyset(argc, argv);
+        if (cmd == "combinescore") return run_combinescore(argc, argv);
+        if (cmd == "filtermatchbyfdr") return run_filtermatchbyfdr(argc, argv);
+        if (cmd == "predictmatch") return run_predictmatch(argc, argv);
         if (cmd == "dumpmatrix") return run_dumpmatrix(argc, argv);
         if (cmd == "dbcopy") return run_dbcopy(argc, argv);
         if (cmd == "showparams") return run_showparams(argc, argv);

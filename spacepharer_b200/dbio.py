@@ -78,3 +78,25 @@ def write_db(name, entries, dbtype):
 
 def write_sequence_db(name, keys, seqs):
     write_db(name, ((k, s + b"\n") for k, s in zip(keys, seqs)), DBTYPE_AMINO_ACIDS)
+
+
+DBTYPE_GENERIC_DB = 12
+
+
+def write_set_db(name, res, off, set_of):
+    """A set database like `createsetdb` leaves it for the search and the set-level stages (data/createsetdb.sh:115-160):
+    the amino-acid sequence DB <name> (key = sequence index) plus <name>_member_to_set (sequence -> set key),
+    <name>_set_to_member (set -> its sequences, one per line) and <name>_set_size (set -> number of sequences)."""
+    import numpy as np
+    lut = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWYX", dtype=np.uint8)
+    txt = lut[np.asarray(res)]
+    n = len(off) - 1
+    write_sequence_db(name, range(n), (txt[int(off[i]):int(off[i + 1])].tobytes() for i in range(n)))
+    set_of = np.asarray(set_of, dtype=np.int64)
+    write_db(name + "_member_to_set", ((i, b"%d\n" % set_of[i]) for i in range(n)), DBTYPE_ALIGNMENT_RES)
+    order = np.argsort(set_of, kind="stable")
+    sets, first = np.unique(set_of[order], return_index=True)
+    bounds = list(first) + [n]
+    write_db(name + "_set_to_member",
+             ((int(s), b"".join(b"%d\n" % m for m in order[bounds[j]:bounds[j + 1]])) for j, s in enumerate(sets)), DBTYPE_ALIGNMENT_RES)
+    write_db(name + "_set_size", ((int(s), b"%d\n" % (bounds[j + 1] - bounds[j])) for j, s in enumerate(sets)), DBTYPE_GENERIC_DB)

@@ -56,8 +56,10 @@ def reverse_targets(res, off):
     return out
 
 
-def make_spacers(n_spacers, tres, toff, seed=None, planted=0.3, min_nt=25, max_nt=45, max_subst=4):
-    """Nucleotide spacers as a padded array: returns (nt uint8[n, max_nt] with 255 padding, lens)."""
+def make_spacers(n_spacers, tres, toff, seed=None, planted=0.3, min_nt=25, max_nt=45, max_subst=4, genome_of=None, set_of=None):
+    """Nucleotide spacers as a padded array: returns (nt uint8[n, max_nt] with 255 padding, lens).
+    genome_of (int64[n], -1 = none) + set_of (genome of every ORF, ascending): planted spacers copy an ORF of THAT genome
+    (spacers of one CRISPR array hitting one phage); spacers with genome -1 stay random."""
     if seed is None:
         seed = 42 + n_spacers
     rng = np.random.default_rng(seed)
@@ -71,6 +73,15 @@ def make_spacers(n_spacers, tres, toff, seed=None, planted=0.3, min_nt=25, max_n
         naa = (max_nt + 2) // 3 + 1  # residues needed to cover the window in any codon phase
         ok = np.nonzero(tlen >= naa)[0]
         tsel = ok[rng.integers(0, len(ok), size=len(pl))]
+        if genome_of is not None:
+            g = np.asarray(genome_of, dtype=np.int64)[pl]
+            first = np.searchsorted(set_of, np.maximum(g, 0), side="left")
+            cnt = np.searchsorted(set_of, np.maximum(g, 0), side="right") - first
+            pick = first + (rng.random(len(pl)) * np.maximum(cnt, 1)).astype(np.int64)
+            usable = (g >= 0) & (cnt > 0) & (tlen[np.minimum(pick, T - 1)] >= naa)
+            tsel = np.where(usable, np.minimum(pick, T - 1), tsel)
+            keep = usable
+            pl, tsel = pl[keep], tsel[keep]
         start_aa = (rng.random(len(pl)) * (tlen[tsel] - naa + 1)).astype(np.int64)
         phase = rng.integers(0, 3, size=len(pl))
         aa = tres[(toff[tsel].astype(np.int64) + start_aa)[:, None] + np.arange(naa)[None, :]]
@@ -161,6 +172,39 @@ def six_frame_fragments(nt, lens, min_aa=9):
         qres[(dst0[:, None] + cols)[mask]] = src[mask].astype(np.uint8)
         base += m
     return qres, qoff, sp[perm].astype(np.uint32)
+
+
+def make_spacer_arrays(n_arrays, tres, toff, set_of, seed=7, min_spacers=2, max_spacers=25, hit_arrays=0.4, planted=0.5, **kw):
+    """CRISPR arrays (query SETS): array a holds U{min..max} spacers; a fraction hit_arrays of the arrays targets one random
+    genome (their planted spacers copy ORFs of it).  Returns (qres, qoff, set_of_frame uint32[Q], n_arrays): the frames of
+    all spacers (six-frame, as make_query_frames) with the array every frame belongs to."""
+    rng = np.random.default_rng(seed)
+    n_sp = rng.integers(min_spacers, max_spacers + 1, size=n_arrays)
+    array_of = np.repeat(np.arange(n_arrays, dtype=np.int64), n_sp)
+    G = int(set_of[-1]) + 1 if len(set_of) else 0
+    genome = np.where(rng.random(n_arrays) < hit_arrays, rng.integers(0, max(G, 1), size=n_arrays), -1)
+    nt, lens = make_spacers(int(n_sp.sum()), tres, toff, seed=seed + 1, planted=planted, genome_of=genome[array_of], set_of=set_of, **kw)
+    qres, qoff, sp = six_frame_fragments(nt, lens)
+    return qres, qoff, array_of[sp].astype(np.uint32), n_arrays
+
+
+def write_array_search_dbs(work, n_genomes=150, target_seed=20180901, n_arrays=140, array_seed=11):
+    """BASELINE config 3 at a chosen scale as MMseqs2 set DBs under `work`: `targets` (phage ORF setDB), `targets_rev`
+    (reversed-ORF control setDB) and `qsetdb` (frames of synthetic CRISPR arrays), each with its _member_to_set /
+    _set_to_member / _set_size files.  Returns the SHA-256 over the generated arrays (pinned next to the golden outputs)."""
+    import hashlib
+    import os
+    from . import dbio
+    tres, toff, set_of = make_targets(n_genomes=n_genomes, seed=target_seed)
+    rres = reverse_targets(tres, toff)
+    qres, qoff, qset, _ = make_spacer_arrays(n_arrays, tres, toff, set_of, seed=array_seed)
+    dbio.write_set_db(os.path.join(work, "targets"), tres, toff, set_of)
+    dbio.write_set_db(os.path.join(work, "targets_rev"), rres, toff, set_of)
+    dbio.write_set_db(os.path.join(work, "qsetdb"), qres, qoff, qset)
+    h = hashlib.sha256()
+    for a in (tres, toff, set_of, rres, qres, qoff, qset):
+        h.update(a.tobytes())
+    return h.hexdigest()
 
 
 def make_query_frames(n_spacers, tres, toff, seed=None, **kw):

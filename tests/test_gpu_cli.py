@@ -57,3 +57,36 @@ def test_control_db_and_fused_search(tmp_path):
                 merged += [lst[i], lst[i + 1]]
     run("search", os.path.join(C1, "qsetdb"), os.path.join(C1, "targets_rev"), fused, *merged)
     assert {k: v for k, v in entries_as_rows(fused).items() if v} == read_dump(os.path.join(C1, "prot_result_rev.txt.gz"))
+
+
+def test_predictmatch_reference_example(tmp_path):
+    """BASELINE config 1 + control through the set-level stages: the `match` DB of predictmatch (--perform-nucl-aln 0)"""
+    out = str(tmp_path)
+    r = run("predictmatch", os.path.join(C1, "qsetdb"), os.path.join(C1, "targets"), os.path.join(C1, "targets_rev"), out + "/match", out,
+            "--perform-nucl-aln", "0", "--threads", "2", "--keep-intermediate", "1")
+    assert dbio.read_dbtype(out + "/match") == dbio.DBTYPE_GENERIC_DB
+    for n, g in (("result", "prot_result"), ("result_rev", "prot_result_rev"), ("aggregate", "sets_aggregate"), ("cScore", "sets_cScore"),
+                 ("cScore_rev", "sets_cScore_rev"), ("match", "sets_match")):
+        assert {k: v for k, v in entries_as_rows(out + "/" + n).items() if v} == read_dump(os.path.join(C1, g + ".txt.gz")), n
+    assert "Combined score list too short" in r.stdout
+    # the default (nucleotide re-alignment on) is refused, not silently skipped
+    r = subprocess.run([BIN, "predictmatch", os.path.join(C1, "qsetdb"), os.path.join(C1, "targets"), os.path.join(C1, "targets_rev"),
+                        out + "/m2", out], capture_output=True, text=True)
+    assert r.returncode == 1 and "--perform-nucl-aln 0" in r.stderr
+
+
+def test_predictmatch_synthetic_arrays(tmp_path):
+    """BASELINE config 3, scaled down: synthetic CRISPR arrays vs synthetic phage setDB + reversed-ORF control, search on the
+    GPU, set-level stages and FDR filter in memory; alignment rows, combined scores and the match DB are byte-identical to
+    the reference's (tests/golden/sets)."""
+    from spacepharer_b200 import synth
+    sets = os.path.join(GOLDEN, "sets")
+    w, out = str(tmp_path / "db"), str(tmp_path / "out")
+    os.makedirs(w)
+    os.makedirs(out)
+    assert synth.write_array_search_dbs(w) == open(os.path.join(sets, "inputs.sha256")).read().strip()
+    run("predictmatch", w + "/qsetdb", w + "/targets", w + "/targets_rev", out + "/match", out, "--perform-nucl-aln", "0", "--threads", "4",
+        "--keep-intermediate", "1", "--fdr", "0.05")
+    for n in ("result", "result_rev", "aggregate", "aggregate_rev", "aggregate_merged", "cScore", "cScore_rev", "match"):
+        assert {k: v for k, v in entries_as_rows(out + "/" + n).items() if v} == read_dump(os.path.join(sets, n + ".txt.gz")), n
+    assert len(read_dump(os.path.join(sets, "match.txt.gz"))) > 10

@@ -43,6 +43,25 @@ for r in rows[2:]:
     p[0] += s; p[1] += n; ts += s; ti += n
 text = open(src).read().split("\n")
 print("samples", ts, "warp instructions", ti)
-for ln, (s, n) in sorted(per.items(), key=lambda x: -x[1][0])[:top]:
+for ln, (s, n) in sorted(per.items(), key=lambda x: -x[1][1 if os.environ.get("BY_INS") else 0])[:top]:
     t = text[ln[1] - 1].strip()[:100] if ln and ln[0] == os.path.basename(src) else str(ln)
     print("%6.2f%% smp %6.2f%% ins  %-6s %s" % (100 * s / max(ts, 1), 100 * n / max(ti, 1), ln[1] if ln else "?", t))
+# optional phase totals: RANGES="name:lo-hi,name:lo-hi" (source lines of <source.cu>; other files are listed under their own name)
+if os.environ.get("RANGES"):
+    rng = []
+    for part in os.environ["RANGES"].split(","):
+        nm, r = part.split(":")
+        lo, hi = r.split("-")
+        rng.append((nm, int(lo), int(hi)))
+    tot = {}
+    for ln, (s, n) in per.items():
+        nm = "?"
+        if ln and ln[0] == os.path.basename(src):
+            nm = next((a for a, lo, hi in rng if lo <= ln[1] <= hi), "other")
+        elif ln:
+            nm = ln[0]
+        p = tot.setdefault(nm, [0, 0])
+        p[0] += s; p[1] += n
+    print("--- phases")
+    for nm, (s, n) in sorted(tot.items(), key=lambda x: -x[1][1]):
+        print("%6.2f%% smp %6.2f%% ins  %s" % (100 * s / max(ts, 1), 100 * n / max(ti, 1), nm))
