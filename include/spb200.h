@@ -183,6 +183,27 @@ int spb_align_resident(spb_ctx *ctx, const spb_align_params *p);
 int spb_align_stats(spb_ctx *ctx, spb_align_result *out);
 int spb_align_fetch(spb_ctx *ctx, spb_align_result **out);
 
+/* ---- exhaustive search (BASELINE config 5) ---------------------------------------------------------
+ * Every resident query against EVERY alignment target, no k-mer stage.  The reference equivalent is `align`
+ * (M/alignment/Alignment.cpp:263-520) fed with a prefilter DB that lists all targets for every query (SURVEY.md 0 #4,
+ * 8d; at this MMseqs2 commit --exhaustive-search itself is the sliced, swapped search of M/workflow/Search.cpp:317-351).
+ * spb_pairs_exhaustive scores all Q x T pairs with the streaming register kernel and leaves, as the resident pair
+ * list, the pairs whose Smith-Waterman score reaches the E-value threshold (queries too long for the register kernel
+ * keep every target); spb_align_resident / spb_align_fetch then produce the rows exactly as for an explicit list. */
+typedef struct spb_exhaustive_stats {
+    uint64_t n_queries, n_targets;
+    uint64_t n_scored;       /* pairs scored by the streaming kernel */
+    uint64_t n_cells;        /* their forward cells (sum qLen * tLen) */
+    uint64_t n_kept;         /* of those, pairs whose score reaches the threshold */
+    uint64_t n_unfiltered;   /* pairs of long queries, passed on without filtering */
+    uint64_t n_pairs;        /* resident pair list = n_kept + n_unfiltered */
+    double kernel_ms;        /* device time of the streaming kernel launches */
+    double total_ms;
+} spb_exhaustive_stats;
+int spb_pairs_exhaustive(spb_ctx *ctx, const spb_align_params *p, spb_exhaustive_stats *stats);
+int spb_align_exhaustive(spb_ctx *ctx, const uint8_t *q_residues, const uint64_t *q_offsets, uint32_t Q,
+                         const spb_align_params *p, spb_align_result **out, spb_exhaustive_stats *stats);
+
 /* ---- multi-GPU target split ------------------------------------------------------------------------
  * MMseqs2 shards targets with --split (Prefiltering.cpp:258-362) and merges the per-split result files
  * (mergeTargetSplits, Prefiltering.cpp:364-481).  Here every GPU prefilters all queries against its target shard

@@ -265,6 +265,27 @@ class Searcher:
         capi.check(self.lib.spb_align_stats(self.h, C.byref(R)))
         return self._aln_stats(R)
 
+    def pairs_exhaustive(self, db_res_count, evalue=200.0, gap_open=16, gap_extend=2, comp_bias=1, gumbel=None,
+                         byte_lanes=32, word_lanes=16):
+        """Exhaustive search (BASELINE config 5): score the resident queries against EVERY alignment target with the
+        streaming register kernel; the pairs reaching the E-value threshold become the resident pair list.
+        -> stats dict (n_scored, n_cells, n_kept, n_unfiltered, n_pairs, kernel_ms, total_ms, gcups)"""
+        p = self._align_params(db_res_count, evalue, gap_open, gap_extend, comp_bias, gumbel, byte_lanes, word_lanes)
+        E = capi.ExhaustiveStats()
+        capi.check(self.lib.spb_pairs_exhaustive(self.h, C.byref(p), C.byref(E)))
+        st = {n: getattr(E, n) for n, _ in capi.ExhaustiveStats._fields_}
+        st["gcups"] = (st["n_cells"] / (st["kernel_ms"] * 1e6)) if st["kernel_ms"] > 0 else 0.0
+        return st
+
+    def align_exhaustive(self, qres, qoff, db_res_count, **kw):
+        """all queries x all targets -> (offsets, rows, cigar, stats) with the rows `align` writes for an all-pairs
+        prefilter DB"""
+        self.set_queries(qres, qoff)
+        est = self.pairs_exhaustive(db_res_count, **kw)
+        ast = self.align_resident(db_res_count, **kw)
+        off, rows, cig, _ = self.align_fetch()
+        return off, rows, cig, dict(exhaustive=est, align=ast)
+
     def align_fetch_view(self):
         """like align_fetch but zero-copy: returns an AlignResultView (close it when done)"""
         r = C.POINTER(capi.AlignResult)()

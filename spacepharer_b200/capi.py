@@ -55,6 +55,12 @@ class AlignResult(C.Structure):
                 ("total_ms", C.c_double)]
 
 
+class ExhaustiveStats(C.Structure):
+    _fields_ = [("n_queries", C.c_uint64), ("n_targets", C.c_uint64), ("n_scored", C.c_uint64), ("n_cells", C.c_uint64),
+                ("n_kept", C.c_uint64), ("n_unfiltered", C.c_uint64), ("n_pairs", C.c_uint64),
+                ("kernel_ms", C.c_double), ("total_ms", C.c_double)]
+
+
 # every symbol include/spb200.h declares (tests check the library exports exactly these)
 SYMBOLS = [
     "spb_ctx_create", "spb_ctx_destroy", "spb_last_error", "spb_version", "spb_ctx_stream", "spb_set_matrices",
@@ -63,6 +69,7 @@ SYMBOLS = [
     "spb_bitscore", "spb_tantan_mask", "spb_queries_set", "spb_prefilter_resident", "spb_prefilter_stats",
     "spb_prefilter_fetch", "spb_pairs_set", "spb_pairs_from_prefilter", "spb_align_resident", "spb_align_stats",
     "spb_align_fetch", "spb_prefilter_device_result", "spb_prefilter_device_trunc_keys", "spb_prefilter_merge_shards",
+    "spb_pairs_exhaustive", "spb_align_exhaustive",
 ]
 
 _lib = None
@@ -121,6 +128,9 @@ def load():
     L.spb_prefilter_device_result.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), u64p]
     L.spb_prefilter_merge_shards.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64, vp, C.c_uint32, C.c_int32]
     L.spb_prefilter_device_trunc_keys.argtypes = [vp, C.POINTER(C.c_void_p)]
+    L.spb_pairs_exhaustive.argtypes = [vp, C.POINTER(AlignParams), C.POINTER(ExhaustiveStats)]
+    L.spb_align_exhaustive.argtypes = [vp, u8p, u64p, C.c_uint32, C.POINTER(AlignParams),
+                                       C.POINTER(C.POINTER(AlignResult)), C.POINTER(ExhaustiveStats)]
     L.spb_tantan_mask.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), u8p, u64p, C.c_uint32, C.c_int, u64p]
     _lib = L
     return L

@@ -792,6 +792,149 @@ __global__ void __launch_bounds__(SR_WARPS * 32) sort_rows_kernel(const spb_aln 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Exhaustive search (BASELINE config 5): every query frame against EVERY target, no k-mer stage.
+// The reference equivalent is `align` fed with a prefilter DB that lists all targets for every query; its result is
+// the set of pairs whose Smith-Waterman E-value passes -e.  Here a streaming kernel scores all Q x T pairs and keeps
+// the (query, target) pairs whose score reaches the query's minimal accepted score; that pair list then goes through
+// the ordinary alignment stage (coordinates, reverse pass, traceback, rows), so the rows are those of the list path.
+//
+// sw_exhaustive_kernel<ROWS>: a thread owns TWO queries (int16 halves, as sw_fast_kernel) of at most ROWS residues and
+// keeps their DP columns in registers; all threads of a CTA walk the same chunk of targets, so the target residue is
+// uniform over the CTA (one broadcast load) and only the profile rows come from shared memory (conflict-free
+// LDS.128).  No end-coordinate bookkeeping: 7 packed instructions per row (2 cells).  Queries are grouped by length
+// (tiles of 128, longest first) and each tile runs the instantiation with the fewest rows that holds it.
+// ---------------------------------------------------------------------------------------------------------
+#define EXH_TILE (2 * SWF_THREADS)
+struct ExhArgs {
+    const uint32_t *qlist;       // fast queries, longest first, padded to EXH_TILE with 0xFFFFFFFF
+    const uint4 *prof16;
+    const uint16_t *minScore;    // per query: smallest accepted raw score (0xFFFF: none)
+    const uint8_t *tres;
+    const uint64_t *toff;
+    const uint32_t *chunkStart;  // [nChunks + 1] target index boundaries
+    uint32_t nChunks;
+    uint32_t tile0, nTiles;      // tiles of this launch
+    unsigned long long *cand;    // out: query << 32 | target
+    unsigned long long candCap;
+    unsigned long long *nCand;
+    uint32_t *qCount;            // out: candidates per query
+    int go, ge;
+};
+
+template <int ROWS>
+__global__ void __launch_bounds__(SWF_THREADS) sw_exhaustive_kernel(ExhArgs A) {
+    __shared__ uint4 s_prof[2][SWF_PROF_ROWS][SWF_THREADS];
+    const int tid = threadIdx.x;
+    const uint32_t tile = A.tile0 + blockIdx.x % A.nTiles, chunk = blockIdx.x / A.nTiles;
+    const uint32_t qA = A.qlist[(size_t)tile * EXH_TILE + 2 * tid], qB = A.qlist[(size_t)tile * EXH_TILE + 2 * tid + 1];
+    const uint4 none = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+#pragma unroll
+    for (int a = 0; a < SWF_PROF_ROWS; a++) {
+        s_prof[0][a][tid] = qA != 0xFFFFFFFFu ? __ldg(A.prof16 + (size_t)qA * SWF_PROF_ROWS + a) : none;
+        s_prof[1][a][tid] = qB != 0xFFFFFFFFu ? __ldg(A.prof16 + (size_t)qB * SWF_PROF_ROWS + a) : none;
+    }
+    const uint32_t minA = qA != 0xFFFFFFFFu ? A.minScore[qA] : 0xFFFFu, minB = qB != 0xFFFFFFFFu ? A.minScore[qB] : 0xFFFFu;
+    const uint32_t MGO = ((uint32_t)(-A.go) & 0xFFFFu) * 0x10001u, MGE = ((uint32_t)(-A.ge) & 0xFFFFu) * 0x10001u;
+    const uint32_t tBegin = A.chunkStart[chunk], tEnd = A.chunkStart[chunk + 1];
+    uint64_t to = A.toff[tBegin];
+    for (uint32_t t = tBegin; t < tEnd; t++) {
+        const uint64_t tn = A.toff[t + 1];
+        const int len = (int)(tn - to);
+        const uint8_t *tp = A.tres + to;
+        to = tn;
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(tp) & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(tp) & 3) * 8u;
+        uint32_t cur = __ldg(w);
+        uint32_t H[ROWS], E[ROWS];
+#pragma unroll
+        for (int i = 0; i < ROWS; i++) { H[i] = 0; E[i] = 0; }
+        uint32_t best = 0;
+        for (int j0 = 0; j0 < len; j0 += 4) {
+            const uint32_t nx = __ldg(w + (j0 >> 2) + 1);
+            uint32_t res = __funnelshift_r(cur, nx, sh);
+            cur = nx;
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                uint32_t a = res & 0xFFu;
+                res >>= 8;
+                if (j0 + jj >= len || a > SPB_X) a = SWF_PAD;
+                const uint4 pa = s_prof[0][a][tid], pb = s_prof[1][a][tid];
+                const uint32_t paw[4] = {pa.x, pa.y, pa.z, pa.w}, pbw[4] = {pb.x, pb.y, pb.z, pb.w};
+                uint32_t Hd = 0, F = 0;
+#pragma unroll
+                for (int i = 0; i < ROWS; i++) {
+                    const int r = i & 3;
+                    const uint32_t sel = (uint32_t)r | ((uint32_t)(r | 8) << 4) | ((uint32_t)(4 + r) << 8) | ((uint32_t)((4 + r) | 8) << 12);
+                    const uint32_t sc = prmt(paw[i >> 2], pbw[i >> 2], sel);
+                    const uint32_t h1 = __viaddmax_s16x2_relu(Hd, sc, E[i]);
+                    const uint32_t open = __vadd2(h1, MGO);
+                    E[i] = __viaddmax_s16x2_relu(E[i], MGE, open);
+                    const uint32_t h = __vmaxs2(h1, F);
+                    F = __viaddmax_s16x2_relu(F, MGE, open);
+                    Hd = H[i];
+                    H[i] = h;
+                    best = __vmaxs2(best, h);
+                }
+            }
+        }
+        const bool okA = (best & 0xFFFFu) >= minA, okB = (best >> 16) >= minB;
+        if (okA | okB) {
+            if (okA) {
+                const unsigned long long k = atomicAdd(A.nCand, 1ull);
+                if (k < A.candCap) A.cand[k] = ((unsigned long long)qA << 32) | t;
+                atomicAdd(A.qCount + qA, 1u);
+            }
+            if (okB) {
+                const unsigned long long k = atomicAdd(A.nCand, 1ull);
+                if (k < A.candCap) A.cand[k] = ((unsigned long long)qB << 32) | t;
+                atomicAdd(A.qCount + qB, 1u);
+            }
+        }
+    }
+}
+
+// smallest raw score whose E-value passes (the decision of sw_finish_pair: score > 0 and !(eval > thr)); every score
+// below it is rejected by construction, scores above it are re-checked by the alignment stage
+__global__ void exh_min_score_kernel(const uint64_t *__restrict__ qoff, uint32_t Q, spb_gumbel g, double evalThr, double dbRes,
+                                     int maxScore, uint16_t *__restrict__ minScore) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    const double L = (double)(qoff[q + 1] - qoff[q]);
+    int s = 1;
+    for (; s <= maxScore; s++)
+        if (!(dev_evalue(g, (double)s, L, dbRes) > evalThr)) break;
+    minScore[q] = s <= maxScore ? (uint16_t)s : (uint16_t)0xFFFFu;
+}
+
+// pairs per query: accepted candidates of a register-kernel query, all targets otherwise
+__global__ void exh_pair_count_kernel(const uint32_t *__restrict__ qCount, const uint8_t *__restrict__ qfast, uint32_t Q, uint32_t T,
+                                      uint64_t *__restrict__ candCnt, uint64_t *__restrict__ pairCnt) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q > Q) return;
+    const uint64_t c = q < Q ? qCount[q] : 0;
+    candCnt[q] = c;
+    pairCnt[q] = q < Q ? (qfast[q] ? c : (uint64_t)T) : 0;
+}
+
+__global__ void exh_scatter_kernel(const unsigned long long *__restrict__ cand, uint64_t n, const uint64_t *__restrict__ candOff,
+                                   const uint64_t *__restrict__ pairOff, uint32_t *__restrict__ pairT) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const unsigned long long key = cand[k];
+    const uint32_t q = (uint32_t)(key >> 32);
+    pairT[pairOff[q] + (k - candOff[q])] = (uint32_t)key;
+}
+
+__global__ void exh_fill_all_kernel(const uint32_t *__restrict__ slow, uint32_t nSlow, uint32_t T, const uint64_t *__restrict__ pairOff,
+                                    uint32_t *__restrict__ pairT) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (uint64_t)nSlow * T) return;
+    const uint32_t s = (uint32_t)(k / T), t = (uint32_t)(k - (uint64_t)s * T);
+    pairT[pairOff[slow[s]] + t] = t;
+}
+
 }  // namespace spb
 
 using namespace spb;
@@ -1193,6 +1336,207 @@ extern "C" int spb_align(spb_ctx *c, const uint8_t *q_residues, const uint64_t *
     *out = nullptr;
     if (spb_queries_set(c, q_residues, q_offsets, Q)) return 1;
     if (spb_pairs_set(c, pair_offsets, pair_targets)) return 1;
+    if (spb_align_resident(c, p)) return 1;
+    return spb_align_fetch(c, out);
+}
+
+// ---- exhaustive search: all resident queries x all alignment targets -> resident pair list ----
+template <int ROWS>
+static cudaError_t launch_exhaustive(const ExhArgs &A, uint32_t blocks, cudaStream_t st) {
+    sw_exhaustive_kernel<ROWS><<<blocks, SWF_THREADS, 0, st>>>(A);
+    return cudaGetLastError();
+}
+
+extern "C" int spb_pairs_exhaustive(spb_ctx *c, const spb_align_params *p, spb_exhaustive_stats *stats) {
+    SPB_CHECK(c && p, "spb_pairs_exhaustive: NULL argument");
+    SPB_CHECK(c->have_matrices, "spb_pairs_exhaustive: call spb_set_matrices first");
+    SPB_CHECK(c->have_aln_targets, "spb_pairs_exhaustive: call spb_align_set_targets first");
+    SPB_CHECK(c->have_queries, "spb_pairs_exhaustive: no resident query batch (spb_queries_set)");
+    SPB_CHECK(p->gap_open >= 0 && p->gap_open <= 255 && p->gap_extend >= 0 && p->gap_extend <= 255, "spb_pairs_exhaustive: gap costs out of range");
+    SPB_CHECK(p->byte_lanes > 0 && p->word_lanes > 0, "spb_pairs_exhaustive: lanes must be positive");
+    SPB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const uint32_t Q = c->Q, T = c->aT;
+    spb_exhaustive_stats es;
+    memset(&es, 0, sizeof(es));
+    es.n_queries = Q;
+    es.n_targets = T;
+    c->have_pairs = false;
+    c->have_aln = false;
+    if (c->d_pairoff.ensure(((size_t)Q + 1) * 8 + 64)) return 1;
+    if (Q == 0 || T == 0) {
+        SPB_CUDA(cudaMemsetAsync(c->d_pairoff.p, 0, ((size_t)Q + 1) * 8, st));
+        SPB_CUDA(cudaStreamSynchronize(st));
+        if (c->d_pairT.ensure(16)) return 1;
+        c->n_pairs = 0;
+        c->have_pairs = true;
+        if (stats) *stats = es;
+        return 0;
+    }
+    SPB_CUDA(cudaEventRecord(c->ev2, st));
+    // profiles and register-kernel eligibility exactly as the list path computes them
+    const int fastMaxL = std::min(SWF_ROWS, std::min(p->byte_lanes, p->word_lanes));
+    int matMin = 0, matMax = 0;
+    for (int i = 0; i < SPB_ALPHABET * SPB_ALPHABET; i++) {
+        matMin = std::min(matMin, (int)(signed char)c->hm.align[i]);
+        matMax = std::max(matMax, (int)(signed char)c->hm.align[i]);
+    }
+    if (c->s_a.ensure(c->q_res + 64) || c->s_b.ensure((size_t)Q * 4 + 4) || c->s_l.ensure((size_t)Q * SWF_PROF_ROWS * SWF_ROWS + 64) ||
+        c->s_m.ensure((size_t)Q + 64) || c->s_n.ensure((size_t)Q * 2 + 64) || c->s_c.ensure((size_t)Q * 4 + 64) || c->s_f.ensure(128)) return 1;
+    align_profile_kernel<<<(Q + 3) / 4, 128, 0, st>>>(c->d_q.as<uint8_t>(), c->d_qoff64.as<uint64_t>(), Q, c->d_mat.as<Matrices>(), p->comp_bias,
+                                           matMin, c->s_a.as<signed char>(), c->s_b.as<int>(), c->s_l.as<signed char>(), c->s_m.as<uint8_t>(),
+                                           fastMaxL);
+    SPB_CUDA(cudaGetLastError()); c->n_launches++;
+    // a local score never exceeds rows x (largest profile entry): matrix maximum + largest composition bias (int8)
+    const int maxScore = std::min(32766, SWF_ROWS * (matMax + 127));
+    exh_min_score_kernel<<<(Q + 127) / 128, 128, 0, st>>>(c->d_qoff64.as<uint64_t>(), Q, p->gumbel, p->eval_thr, (double)p->db_res_count,
+                                                          maxScore, c->s_n.as<uint16_t>());
+    SPB_CUDA(cudaGetLastError()); c->n_launches++;
+
+    // host plan: register-kernel queries longest first in tiles of EXH_TILE; the others take every target
+    std::vector<uint32_t> qlist, slow;
+    std::vector<uint8_t> mode((size_t)Q);       // 1: register kernel, 0: all targets (what exh_pair_count_kernel reads as qfast)
+    uint64_t fastRes = 0;
+    for (uint32_t k = 0; k < Q; k++) {
+        const uint32_t q = c->h_qorder[k], L = c->h_qlen[q];
+        if (L >= 1 && (int)L <= fastMaxL) { qlist.push_back(q); mode[q] = 1; fastRes += L; }
+        else { slow.push_back(q); mode[q] = 0; }
+    }
+    const uint32_t nFast = (uint32_t)qlist.size(), nSlow = (uint32_t)slow.size();
+    const uint32_t nTiles = (nFast + EXH_TILE - 1) / EXH_TILE;
+    qlist.resize((size_t)nTiles * EXH_TILE, 0xFFFFFFFFu);
+    // target chunks: enough (tile, chunk) units for ~16 waves of resident CTAs, at least ~2048 residues each
+    std::vector<uint32_t> chunkStart;
+    {
+        const uint64_t wantUnits = (uint64_t)c->n_sm * 5 * 16;
+        uint64_t nChunks = nTiles ? (wantUnits + nTiles - 1) / nTiles : 1;
+        nChunks = std::max<uint64_t>(1, std::min<uint64_t>(nChunks, std::min<uint64_t>(T, c->a_res / 2048 + 1)));
+        const uint64_t per = (c->a_res + nChunks - 1) / nChunks;
+        chunkStart.push_back(0);
+        uint64_t acc = 0;
+        for (uint32_t t = 0; t < T; t++) {
+            acc += c->h_aoff[t + 1] - c->h_aoff[t];
+            if (acc >= per && t + 1 < T) { chunkStart.push_back(t + 1); acc = 0; }
+        }
+        chunkStart.push_back(T);
+    }
+    const uint32_t nChunks = (uint32_t)chunkStart.size() - 1;
+    unsigned long long candCap = std::max<unsigned long long>(1ull << 22, 1024ull * Q);
+    candCap = std::min<unsigned long long>(candCap, std::min<unsigned long long>((unsigned long long)Q * T, 0x7FFFFFF0ull));
+    if (c->s_d.ensure(qlist.size() * 4 + 64) || c->s_e.ensure(chunkStart.size() * 4 + 64) || c->s_o.ensure(candCap * 8 + 64) ||
+        c->s_p.ensure(candCap * 8 + 64) || c->s_g.ensure((size_t)nSlow * 4 + 64) || c->s_i.ensure(((size_t)Q + 1) * 32 + 64)) return 1;
+    if (!qlist.empty()) SPB_CUDA(cudaMemcpyAsync(c->s_d.p, qlist.data(), qlist.size() * 4, cudaMemcpyHostToDevice, st));
+    SPB_CUDA(cudaMemcpyAsync(c->s_e.p, chunkStart.data(), chunkStart.size() * 4, cudaMemcpyHostToDevice, st));
+    if (nSlow) SPB_CUDA(cudaMemcpyAsync(c->s_g.p, slow.data(), (size_t)nSlow * 4, cudaMemcpyHostToDevice, st));
+    SPB_CUDA(cudaMemcpyAsync(c->s_m.p, mode.data(), Q, cudaMemcpyHostToDevice, st));
+    SPB_CUDA(cudaMemsetAsync(c->s_f.p, 0, 128, st));
+    SPB_CUDA(cudaMemsetAsync(c->s_c.p, 0, (size_t)Q * 4, st));
+
+    ExhArgs A;
+    memset(&A, 0, sizeof(A));
+    A.qlist = c->s_d.as<uint32_t>();
+    A.prof16 = c->s_l.as<uint4>();
+    A.minScore = c->s_n.as<uint16_t>();
+    A.tres = c->d_ares.as<uint8_t>();
+    A.toff = c->d_aoff.as<uint64_t>();
+    A.chunkStart = c->s_e.as<uint32_t>();
+    A.nChunks = nChunks;
+    A.cand = c->s_o.as<unsigned long long>();
+    A.candCap = candCap;
+    A.nCand = c->s_f.as<unsigned long long>();
+    A.qCount = c->s_c.as<uint32_t>();
+    A.go = p->gap_open;
+    A.ge = p->gap_extend;
+    SPB_CUDA(cudaEventRecord(c->ev0, st));
+    for (uint32_t t0 = 0; t0 < nTiles;) {      // runs of tiles with the same row count
+        auto rowsOf = [&](uint32_t tile) { return std::max<uint32_t>(8, c->h_qlen[qlist[(size_t)tile * EXH_TILE]]); };
+        const uint32_t rows = rowsOf(t0);
+        uint32_t t1 = t0 + 1;
+        while (t1 < nTiles && rowsOf(t1) == rows) t1++;
+        A.tile0 = t0;
+        A.nTiles = t1 - t0;
+        const uint64_t blocks = (uint64_t)A.nTiles * nChunks;
+        SPB_CHECK(blocks < 0x7FFFFFFFull, "spb_pairs_exhaustive: too many work units; split the query batch");
+        cudaError_t e = cudaSuccess;
+        switch (rows) {
+            case 8: e = launch_exhaustive<8>(A, (uint32_t)blocks, st); break;
+            case 9: e = launch_exhaustive<9>(A, (uint32_t)blocks, st); break;
+            case 10: e = launch_exhaustive<10>(A, (uint32_t)blocks, st); break;
+            case 11: e = launch_exhaustive<11>(A, (uint32_t)blocks, st); break;
+            case 12: e = launch_exhaustive<12>(A, (uint32_t)blocks, st); break;
+            case 13: e = launch_exhaustive<13>(A, (uint32_t)blocks, st); break;
+            case 14: e = launch_exhaustive<14>(A, (uint32_t)blocks, st); break;
+            case 15: e = launch_exhaustive<15>(A, (uint32_t)blocks, st); break;
+            default: e = launch_exhaustive<16>(A, (uint32_t)blocks, st); break;
+        }
+        SPB_CUDA(e); c->n_launches++;
+        t0 = t1;
+    }
+    SPB_CUDA(cudaEventRecord(c->ev1, st));
+    unsigned long long nCand = 0;
+    SPB_CUDA(cudaMemcpyAsync(&nCand, c->s_f.p, 8, cudaMemcpyDeviceToHost, st));
+    SPB_CUDA(cudaStreamSynchronize(st));
+    SPB_CHECK(nCand <= candCap, "spb_pairs_exhaustive: %llu pairs pass the E-value threshold, more than the %llu one batch can hold; "
+              "lower -e or split the query batch", nCand, candCap);
+    // candidates ordered by (query, target); CSR offsets over all queries
+    size_t tmpBytes = 0;
+    int endBit = 32;
+    while (endBit < 64 && ((uint64_t)1 << (endBit - 32)) < (uint64_t)Q) endBit++;
+    if (nCand) {
+        SPB_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmpBytes, c->s_o.as<unsigned long long>(), c->s_p.as<unsigned long long>(),
+                                                (int)nCand, 0, endBit, st));
+        if (c->s_cub.ensure(tmpBytes)) return 1;
+        SPB_CUDA(cub::DeviceRadixSort::SortKeys(c->s_cub.p, tmpBytes, c->s_o.as<unsigned long long>(), c->s_p.as<unsigned long long>(),
+                                                (int)nCand, 0, endBit, st));
+    }
+    uint64_t *candCnt = c->s_i.as<uint64_t>(), *pairCnt = candCnt + (Q + 1), *candOff = pairCnt + (Q + 1);
+    uint64_t *pairOff = c->d_pairoff.as<uint64_t>();
+    exh_pair_count_kernel<<<(Q + 1 + 255) / 256, 256, 0, st>>>(c->s_c.as<uint32_t>(), c->s_m.as<uint8_t>(), Q, T, candCnt, pairCnt);
+    SPB_CUDA(cudaGetLastError()); c->n_launches++;
+    SPB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, candCnt, candOff, (int)(Q + 1), st));
+    if (c->s_cub.ensure(tmpBytes)) return 1;
+    SPB_CUDA(cub::DeviceScan::ExclusiveSum(c->s_cub.p, tmpBytes, candCnt, candOff, (int)(Q + 1), st));
+    SPB_CUDA(cub::DeviceScan::ExclusiveSum(c->s_cub.p, tmpBytes, pairCnt, pairOff, (int)(Q + 1), st));
+    uint64_t NP = 0;
+    SPB_CUDA(cudaMemcpyAsync(&NP, pairOff + Q, 8, cudaMemcpyDeviceToHost, st));
+    SPB_CUDA(cudaStreamSynchronize(st));
+    SPB_CHECK(NP < 0x7FFFFFF0ull, "spb_pairs_exhaustive: more than 2^31 pairs to align (%u queries longer than %d residues take every target); "
+              "split the query batch", nSlow, fastMaxL);
+    if (c->d_pairT.ensure(NP * 4 + 16)) return 1;
+    if (nCand) {
+        exh_scatter_kernel<<<(unsigned)((nCand + 255) / 256), 256, 0, st>>>(c->s_p.as<unsigned long long>(), nCand, candOff, pairOff,
+                                                                            c->d_pairT.as<uint32_t>());
+        SPB_CUDA(cudaGetLastError()); c->n_launches++;
+    }
+    if (nSlow) {
+        const uint64_t n = (uint64_t)nSlow * T;
+        exh_fill_all_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->s_g.as<uint32_t>(), nSlow, T, pairOff, c->d_pairT.as<uint32_t>());
+        SPB_CUDA(cudaGetLastError()); c->n_launches++;
+    }
+    SPB_CUDA(cudaEventRecord(c->ev3, st));
+    SPB_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    SPB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    es.kernel_ms = ms;
+    SPB_CUDA(cudaEventElapsedTime(&ms, c->ev2, c->ev3));
+    es.total_ms = ms;
+    es.n_scored = (uint64_t)nFast * T;
+    es.n_cells = fastRes * c->a_res;
+    es.n_kept = nCand;
+    es.n_unfiltered = (uint64_t)nSlow * T;
+    es.n_pairs = NP;
+    c->n_pairs = NP;
+    c->have_pairs = true;
+    if (stats) *stats = es;
+    return 0;
+}
+
+extern "C" int spb_align_exhaustive(spb_ctx *c, const uint8_t *q_residues, const uint64_t *q_offsets, uint32_t Q,
+                                    const spb_align_params *p, spb_align_result **out, spb_exhaustive_stats *stats) {
+    SPB_CHECK(c && q_offsets && p && out, "spb_align_exhaustive: NULL argument");
+    *out = nullptr;
+    if (spb_queries_set(c, q_residues, q_offsets, Q)) return 1;
+    if (spb_pairs_exhaustive(c, p, stats)) return 1;
     if (spb_align_resident(c, p)) return 1;
     return spb_align_fetch(c, out);
 }

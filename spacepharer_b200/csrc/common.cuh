@@ -127,6 +127,7 @@ struct spb_ctx {
     spb::DevBuf d_qoff;           // u32[Q+1]
     spb::DevBuf d_qoff64;         // u64[Q+1]
     spb::DevBuf d_qorder;         // u32[Q] prefilter processing order (longest first)
+    std::vector<uint32_t> h_qorder, h_qlen;   // host copies: that order, query lengths (exhaustive-search tiling)
 
     // ---- resident prefilter result (query order) ----
     bool have_pref = false;

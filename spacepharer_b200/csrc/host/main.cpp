@@ -71,6 +71,9 @@ struct Params {
     long batch = 1000000;
     // set-level stages (M/commons/Parameters.cpp:217,2277; src/commons/LocalParameters.h:75-77,171-176)
     int simpleBestHit = 1, reportFdr = 0, performNuclAln = 1, keepIntermediate = 0;
+    // 1: no k-mer stage, Smith-Waterman of every query against every target (BASELINE config 5; the result of the reference's
+    // `align` over an all-pairs prefilter DB -- the reference's own flag of this name is the sliced search)
+    int exhaustive = 0;
     float fdr = 0.05f;
 };
 
@@ -97,6 +100,7 @@ std::vector<FlagDef> flag_table(Params &p) {
         {"--db-load-mode", 4, nullptr}, {"--pca", 4, nullptr}, {"--pcb", 4, nullptr}, {"--alignment-output-mode", 4, nullptr},
         {"--wrapped-scoring", 4, nullptr}, {"--realign-score-bias", 4, nullptr}, {"--realign-max-seqs", 4, nullptr},
         {"--zdrop", 4, nullptr}, {"--local-tmp", 4, nullptr}, {"--taxon-list", 4, nullptr}, {"--exhaustive-search-filter", 4, nullptr},
+        {"--exhaustive-search", 0, &p.exhaustive},
         {"--simple-best-hit", 0, &p.simpleBestHit}, {"--fdr", 1, &p.fdr}, {"--report-fdr", 0, &p.reportFdr},
         {"--perform-nucl-aln", 0, &p.performNuclAln}, {"--tax-fdr", 4, nullptr}, {"--remove-tmp-files", 4, nullptr},
         // spb200-specific
@@ -527,7 +531,7 @@ void search_dbs(const Params &p, const std::string &qName, const std::string &tN
     load_sequences(qdb, E.seed, Q);
     load_sequences(tdb, E.seed, T);
     const int kmerThr = kmer_threshold(p.sensitivity, p.kmerScore, 6);
-    build_target_index(E, p, T, kmerThr);
+    if (!p.exhaustive) build_target_index(E, p, T, kmerThr);
     check(spb_align_set_targets(E.ctx, T.res.data(), T.off.data(), (uint32_t)T.keys.size(), T.keys.data()), "spb_align_set_targets");
     spb_prefilter_params pp;
     pp.kmer_thr = kmerThr;
@@ -545,8 +549,15 @@ void search_dbs(const Params &p, const std::string &qName, const std::string &tN
         std::vector<uint64_t> off(b1 - b0 + 1);
         for (size_t i = b0; i <= b1; i++) off[i - b0] = Q.off[i] - Q.off[b0];
         check(spb_queries_set(E.ctx, Q.res.data() + Q.off[b0], off.data(), (uint32_t)(b1 - b0)), "spb_queries_set");
-        check(spb_prefilter_resident(E.ctx, &pp), "spb_prefilter_resident");
-        check(spb_pairs_from_prefilter(E.ctx), "spb_pairs_from_prefilter");
+        if (p.exhaustive) {
+            spb_exhaustive_stats es;
+            check(spb_pairs_exhaustive(E.ctx, &ap, &es), "spb_pairs_exhaustive");
+            log_line(p, "Exhaustive search: %llu pairs scored, %llu kept, %.2f GCUPS in the streaming kernel", (unsigned long long)es.n_scored,
+                     (unsigned long long)es.n_pairs, es.kernel_ms > 0 ? (double)es.n_cells / es.kernel_ms / 1e6 : 0.0);
+        } else {
+            check(spb_prefilter_resident(E.ctx, &pp), "spb_prefilter_resident");
+            check(spb_pairs_from_prefilter(E.ctx), "spb_pairs_from_prefilter");
+        }
         check(spb_align_resident(E.ctx, &ap), "spb_align_resident");
         spb_align_result *r = nullptr;
         check(spb_align_fetch(E.ctx, &r), "spb_align_fetch");

@@ -1630,6 +1630,9 @@ extern "C" int spb_queries_set(spb_ctx *c, const uint8_t *q_residues, const uint
     SPB_CUDA(cudaMemcpyAsync(c->d_qoff.p, off32.data(), off32.size() * 4, cudaMemcpyHostToDevice, c->stream));
     SPB_CUDA(cudaMemcpyAsync(c->d_qoff64.p, q_offsets, ((size_t)Q + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     SPB_CUDA(cudaStreamSynchronize(c->stream));
+    c->h_qlen.resize(Q);
+    for (uint32_t i = 0; i < Q; i++) c->h_qlen[i] = off32[i + 1] - off32[i];
+    c->h_qorder.swap(order);
     c->Q = Q;
     c->q_res = NQ;
     c->q_maxlen = maxL;

@@ -90,3 +90,25 @@ def test_predictmatch_synthetic_arrays(tmp_path):
     for n in ("result", "result_rev", "aggregate", "aggregate_rev", "aggregate_merged", "cScore", "cScore_rev", "match"):
         assert {k: v for k, v in entries_as_rows(out + "/" + n).items() if v} == read_dump(os.path.join(sets, n + ".txt.gz")), n
     assert len(read_dump(os.path.join(sets, "match.txt.gz"))) > 10
+
+
+def test_search_exhaustive_contains_the_prefiltered_rows(tmp_path):
+    """--exhaustive-search 1 (no k-mer stage, BASELINE config 5) on the reference's example DBs: every row the reference's
+    prefilter+align search reports is reported, byte-identical and in the same relative order, among the all-vs-all rows"""
+    ex = str(tmp_path / "ex")
+    seen, merged = set(), []
+    for lst in (PREF_FLAGS, ALN_FLAGS):
+        for i in range(0, len(lst), 2):
+            if lst[i] not in seen:
+                seen.add(lst[i])
+                merged += [lst[i], lst[i + 1]]
+    r = run("search", os.path.join(C1, "qsetdb"), os.path.join(C1, "targets"), ex, *merged, "--exhaustive-search", "1")
+    assert "Exhaustive search" in r.stdout
+    got = entries_as_rows(ex)
+    ref = read_dump(os.path.join(C1, "prot_result.txt.gz"))
+    more = 0
+    for k, rows in ref.items():
+        tk = {x.split("\t")[0] for x in rows}
+        assert [x for x in got[k] if x.split("\t")[0] in tk] == rows, k
+        more += len(got[k]) - len(rows)
+    assert more > 0
