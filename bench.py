@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-spacers", type=int, default=0, help="spacers in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mask", action="store_true", help="skip the tantan host pre-step (--mask 0)")
+    ap.add_argument("--exhaustive-spacers", type=int, default=1000,
+                    help="spacers per GPU in the exhaustive-search leg (BASELINE config 5: all frames x all ORFs, no k-mer stage); 0 = skip")
     return ap.parse_args()
 
 
@@ -304,10 +306,27 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    # ---- exhaustive-search leg (config 5): a bounded sample of the batch against EVERY target, streaming SW kernel ----
+    exh = None
+    if args.exhaustive_spacers > 0:
+        per = Q // world if weak else Q
+        lo = rank * per if weak else 0
+        nq = int(min(per, max(1, round(args.exhaustive_spacers * Q / float(args.spacers * (world if weak else 1))))))
+        base = int(o_np[lo])
+        eng.searcher.set_queries(q_np[base:int(o_np[lo + nq])], (o_np[lo:lo + nq + 1] - np.uint64(base)).astype(np.uint64))
+        eng.searcher.pairs_exhaustive(db_res)
+        barrier()
+        runs = [eng.searcher.pairs_exhaustive(db_res) for _ in range(2)]
+        barrier()
+        exh = {"kernel_ms": float(np.mean([r["kernel_ms"] for r in runs])), "cells": float(runs[-1]["n_cells"]),
+               "scored": float(runs[-1]["n_scored"]), "kept": float(runs[-1]["n_kept"]), "queries": nq}
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, exh["kernel_ms"] if exh else 0.0], dtype=torch.float64, device="cuda")
+    tsum = torch.tensor([exh["cells"], exh["scored"], exh["kept"], exh["queries"]] if exh else [0.0] * 4, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms, exh_ms = float(t[0]), float(t[1]), float(t[2])
     q_total = eng.queries_per_step(Q)
 
     if rank == 0:
@@ -340,6 +359,13 @@ def run_ours(args):
             "clocks": clocks,
             "wall_s_value_leg": wall_value,
         }
+        if exh:
+            line["sw_exhaustive"] = {
+                "gcups": float(tsum[0]) / (exh_ms * 1e-3) / 1e9 if exh_ms > 0 else None, "kernel_ms": exh_ms,
+                "cells": float(tsum[0]), "pairs_scored": int(tsum[1]), "pairs_kept": int(tsum[2]),
+                "workload": "config 5 (--exhaustive-search, no k-mer stage): %d frames (%d spacers per GPU) x all %d ORFs, "
+                            "sw_exhaustive_kernel; cells = sum qLen*tLen, time = max over ranks of the kernel's CUDA-event time, mean of 2 runs"
+                            % (int(tsum[3]), args.exhaustive_spacers, T)}
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             sample = min(args.spacers, args.cpu_sample_spacers or auto_sample(cores))

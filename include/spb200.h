@@ -204,6 +204,33 @@ int spb_pairs_exhaustive(spb_ctx *ctx, const spb_align_params *p, spb_exhaustive
 int spb_align_exhaustive(spb_ctx *ctx, const uint8_t *q_residues, const uint64_t *q_offsets, uint32_t Q,
                          const spb_align_params *p, spb_align_result **out, spb_exhaustive_stats *stats);
 
+/* ---- query preparation: nucleotide spacers -> six-frame peptide fragments ---------------------------
+ * The spacer query set is prepared by createsetdb --extractorf-spacer 1 (data/createsetdb.sh:88-113) as
+ *   extractorfs --min-length 9 --orf-start-mode 1   M/util/extractorfs.cpp:19-160, Orf::findForward M/commons/Orf.cpp:230-352
+ *   translatenucs (canonical table)                 M/util/translatenucs.cpp:13-115
+ * spb_spacer_frames does both on the device.  nt: numeric nucleotides 0..3 = A C G T, anything else = ambiguous (N);
+ * nt_offsets[N+1].  Fragments come out in the reference's order (per sequence: forward strand then reverse complement,
+ * by the position of the codon that ends them), i.e. entry i here is DB key i of the reference's <db>_nucl_orf / <db>.
+ * residues are numeric amino acids (SPB_ALPHABET order).  make_resident != 0 additionally installs the fragments as
+ * the resident query batch (as spb_queries_set would), so spacers go from nucleotides to the search in HBM. */
+typedef struct spb_orf {     /* Orf::SequenceLocation, M/commons/Orf.h */
+    uint32_t contig;         /* index of the input sequence */
+    uint32_t from, to;       /* first / last nucleotide of the fragment on its strand (0-based, inclusive) */
+    uint8_t strand;          /* 0 forward, 1 reverse complement */
+    uint8_t incomplete_start, incomplete_end, pad;
+} spb_orf;
+typedef struct spb_frames_result {
+    uint32_t n_sequences, n_frames;
+    uint64_t n_residues;
+    uint64_t *offsets;       /* [n_frames+1] */
+    uint8_t *residues;
+    spb_orf *orfs;           /* [n_frames] */
+    double kernel_ms;
+} spb_frames_result;
+int spb_spacer_frames(spb_ctx *ctx, const uint8_t *nt, const uint64_t *nt_offsets, uint32_t N, int min_codons,
+                      int max_codons, int make_resident, spb_frames_result **out);
+void spb_free_frames_result(spb_frames_result *r);
+
 /* ---- multi-GPU target split ------------------------------------------------------------------------
  * MMseqs2 shards targets with --split (Prefiltering.cpp:258-362) and merges the per-split result files
  * (mergeTargetSplits, Prefiltering.cpp:364-481).  Here every GPU prefilters all queries against its target shard

@@ -82,6 +82,11 @@ GUMBEL_VTML40_16_2 = dict(
     sigma=0.18283871043913499, tau=1.7838353361758408)
 
 
+class Orf(C.Structure):
+    _fields_ = [("from_", C.c_uint32), ("to", C.c_uint32), ("strand", C.c_int), ("incomplete_start", C.c_int),
+                ("incomplete_end", C.c_int)]
+
+
 def build(force=False):
     so = os.path.join(_HERE, "libsp_oracle.so")
     src = [os.path.join(_HERE, f) for f in ("sp_oracle.c", "sp_oracle.h")]
@@ -127,6 +132,9 @@ def lib():
     L.spo_align_batch.argtypes = [C.POINTER(Matrix), C.POINTER(AlignParams), u8p, C.POINTER(C.c_uint64), C.c_uint32, u8p,
                                   C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_void_p, C.c_int]
     L.spo_align_batch.restype = None
+    L.spo_extract_frames.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(Orf), C.c_int, C.c_char_p, C.c_int,
+                                     C.POINTER(C.c_int)]
+    L.spo_extract_frames.restype = C.c_int
     L.spo_format_row.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(Aln), C.c_int, C.c_int]
     L.spo_format_row.restype = C.c_int
     _LIB = L
@@ -314,3 +322,26 @@ def align_batch(m40, p, qres, qoff, tres, toff, pair_off, pair_t, threads=0):
                           toff.ctypes.data_as(u64p), pair_off.ctypes.data_as(u64p),
                           pair_t.ctypes.data_as(C.POINTER(C.c_uint32)), rows.ctypes.data, threads)
     return rows[: int(pair_off[-1])]
+
+
+def extract_frames(seq, min_codons=9, max_codons=32734):
+    """one ASCII nucleotide sequence -> [(from, to, strand, incomplete_start, incomplete_end, aa string)] in the order
+    of the reference's extractorfs output (M/util/extractorfs.cpp, Orf::findForward)"""
+    b = seq.encode() if isinstance(seq, str) else bytes(seq)
+    cap = max(16, 2 * len(b))
+    orfs = (Orf * cap)()
+    aa = C.create_string_buffer(2 * len(b) + 16)
+    off = (C.c_int * (cap + 1))()
+    n = lib().spo_extract_frames(b, len(b), min_codons, max_codons, orfs, cap, aa, len(aa), off)
+    assert n <= cap
+    return [(orfs[k].from_, orfs[k].to, orfs[k].strand, orfs[k].incomplete_start, orfs[k].incomplete_end,
+             aa.raw[off[k]:off[k + 1]].decode()) for k in range(n)]
+
+
+def orf_header(key, length, o):
+    """Orf::writeOrfHeader (M/commons/Orf.cpp:440-457) with the minus-strand flip of M/util/extractorfs.cpp:93-98"""
+    f, t = o[0], o[1]
+    if o[2] == 1:
+        f, t = (length - 1) - f, (length - 1) - t
+    flags = int(o[3]) | (int(o[4]) << 1)
+    return "%d\t%d%s%d%s" % (key, f, "+" if f < t else "-", abs(f - t), ("\t%d" % flags) if flags else "")

@@ -1191,3 +1191,124 @@ int spo_format_row(char *buf, uint32_t tKey, const spo_aln *a, int qLen, int tLe
     return sprintf(buf, "%u\t%d\t%s\t%.3E\t%d\t%d\t%d\t%d\t%d\t%d\t%s\n", tKey, a->bits, sid, a->eval,
                    a->qStart, a->qEnd, qLen, a->tStart, a->tEnd, tLen, a->cigar);
 }
+
+/* =========================================================================================================
+ * Query preparation: extractorfs --orf-start-mode 1 (ANY_TO_STOP) + translatenucs, canonical table.
+ * Follows Orf::setSequence / Orf::findAll / Orf::findForward (M/commons/Orf.cpp:130-159,172-191,230-352),
+ * the caller's filter and coordinate flip (M/util/extractorfs.cpp:76-99) and TranslateNucl::translate
+ * (M/commons/TranslateNucl.h:488-503) on ASCII nucleotides.
+ * ========================================================================================================= */
+#define SPO_CHAR_MAX 127
+
+static char spo_complement(char c) {
+    /* Orf::iupacReverseComplementTable, M/commons/Orf.cpp:48-52 */
+    static const char *tab =
+        "................................................................"
+        ".TVGH..CD..M.KN...YSAABW.R.......tvgh..cd..m.kn...ysaabw.r......"
+        "................................................................"
+        "................................................................";
+    return tab[(unsigned char)c];
+}
+
+static int spo_is_stop(const char *codon) {
+    /* TranslateNucl::getStopCodons of the canonical table: TAA TAG TGA; exact match as isInCodons does */
+    return codon[0] == 'T' && ((codon[1] == 'A' && (codon[2] == 'A' || codon[2] == 'G')) || (codon[1] == 'G' && codon[2] == 'A'));
+}
+
+static int spo_nt_index(char c) {   /* T C A G -> 0..3 (ncbieaa order), -1 ambiguous */
+    switch (c) {
+        case 'T': case 't': case 'U': case 'u': return 0;
+        case 'C': case 'c': return 1;
+        case 'A': case 'a': return 2;
+        case 'G': case 'g': return 3;
+        default: return -1;
+    }
+}
+
+char spo_translate_codon(const char *codon) {
+    /* the NCBI automaton of TranslateNucl returns the residue shared by all expansions of an ambiguous codon, else X
+     * (restricted here to the ambiguity N: any base) */
+    static const char *ncbieaa = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+    int lo[3], hi[3];
+    for (int k = 0; k < 3; k++) {
+        const int x = spo_nt_index(codon[k]);
+        lo[k] = x < 0 ? 0 : x;
+        hi[k] = x < 0 ? 3 : x;
+    }
+    char res = 0;
+    for (int a = lo[0]; a <= hi[0]; a++)
+        for (int b = lo[1]; b <= hi[1]; b++)
+            for (int c = lo[2]; c <= hi[2]; c++) {
+                const char r = ncbieaa[16 * a + 4 * b + c];
+                if (res == 0) res = r;
+                else if (res != r) return 'X';
+            }
+    return res;
+}
+
+static int spo_find_forward(const char *sequence, size_t sequenceLength, size_t minLength, size_t maxLength, int strand,
+                            spo_orf *out, int cap, int n) {
+    int isInsideOrf[3] = {1, 1, 1}, hasStartCodon[3] = {0, 0, 0};
+    size_t countLength[3] = {0, 0, 0}, from[3] = {0, 1, 2};
+    char codon[3];
+    for (size_t i = 0; i < sequenceLength - 2; i += 3) {
+        for (size_t position = i; position < i + 3; position++) {
+            for (int k = 0; k < 3; k++)
+                codon[k] = sequence[position + k] == SPO_CHAR_MAX ? SPO_CHAR_MAX : (char)(sequence[position + k] & ~0x20);
+            const size_t frame = position % 3;
+            const int thisIncomplete = codon[0] == SPO_CHAR_MAX || codon[1] == SPO_CHAR_MAX || codon[2] == SPO_CHAR_MAX;
+            const char *nx = sequence + position + 3;
+            const int isLast = !thisIncomplete && (nx[0] == SPO_CHAR_MAX || nx[1] == SPO_CHAR_MAX || nx[2] == SPO_CHAR_MAX);
+            if (!isInsideOrf[frame]) {   /* ANY_TO_STOP: shouldStart */
+                isInsideOrf[frame] = 1;
+                hasStartCodon[frame] = 1;
+                from[frame] = position;
+                countLength[frame] = 0;
+            }
+            const int stop = spo_is_stop(codon);
+            if (isInsideOrf[frame] && !stop) countLength[frame]++;
+            if (isInsideOrf[frame] && (stop || isLast)) {
+                isInsideOrf[frame] = 0;
+                if (countLength[frame] == 0 && stop) continue;
+                const size_t to = position + ((isLast && !stop) ? 2 : -1);
+                if (countLength[frame] > maxLength || countLength[frame] < minLength) continue;
+                if (n < cap) {
+                    out[n].from = (uint32_t)from[frame];
+                    out[n].to = (uint32_t)to;
+                    out[n].strand = strand;
+                    out[n].incomplete_start = !hasStartCodon[frame];
+                    out[n].incomplete_end = !stop;
+                }
+                n++;
+            }
+        }
+    }
+    return n;
+}
+
+int spo_extract_frames(const char *seq, int length, int minCodons, int maxCodons, spo_orf *out, int cap, char *aa, int aaCap,
+                       int *aaOff) {
+    if (length < 3) return 0;
+    char *fwd = (char *)malloc((size_t)length + 40), *rev = (char *)malloc((size_t)length + 40);
+    for (int i = 0; i < length; i++) fwd[i] = (seq[i] == 'u') ? 't' : seq[i];      /* Orf.cpp:141-144: only 'u' survives the two assignments */
+    for (int i = 0; i < length; i++) {
+        rev[i] = spo_complement(fwd[length - i - 1]);
+        if (rev[i] == '.') rev[i] = 'N';
+    }
+    for (int i = length; i < length + 40; i++) fwd[i] = rev[i] = SPO_CHAR_MAX;
+    int n = spo_find_forward(fwd, (size_t)length, (size_t)minCodons, (size_t)maxCodons, 0, out, cap, 0);
+    n = spo_find_forward(rev, (size_t)length, (size_t)minCodons, (size_t)maxCodons, 1, out, cap, n);
+    int w = 0;
+    for (int k = 0; k < n && k < cap; k++) {
+        const char *s = out[k].strand ? rev : fwd;
+        aaOff[k] = w;
+        for (uint32_t p = out[k].from; p + 2 <= out[k].to; p += 3) {
+            if (w < aaCap) aa[w] = spo_translate_codon(s + p);
+            w++;
+        }
+    }
+    if (n <= cap) aaOff[n < cap ? n : cap] = w;
+    free(fwd);
+    free(rev);
+    return n;
+}

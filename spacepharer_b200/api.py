@@ -192,6 +192,30 @@ class Searcher:
         self.Q = len(qoff) - 1
         capi.check(self.lib.spb_queries_set(self.h, _u8(qres), _u64(qoff), self.Q))
 
+    def spacer_frames(self, nt, nt_off, min_codons=9, max_codons=32734, make_resident=False):
+        """Nucleotide spacers -> six-frame peptide fragments on the device (extractorfs --min-length 9 --orf-start-mode 1
+        + translatenucs of createsetdb --extractorf-spacer 1).  nt: numeric nucleotides (0..3 = ACGT, else N), nt_off[N+1].
+        -> (qres uint8, qoff uint64[F+1], orfs structured array (contig, from_, to, strand, incomplete_start/_end), stats);
+        make_resident: the fragments also become the resident query batch (no host round trip before the search)."""
+        nt = np.ascontiguousarray(nt, dtype=np.uint8)
+        nt_off = np.ascontiguousarray(nt_off, dtype=np.uint64)
+        N = len(nt_off) - 1
+        r = C.POINTER(capi.FramesResult)()
+        capi.check(self.lib.spb_spacer_frames(self.h, _u8(nt), _u64(nt_off), N, min_codons, max_codons, 1 if make_resident else 0,
+                                              C.byref(r)))
+        try:
+            R = r.contents
+            F = int(R.n_frames)
+            qoff = _view(R.offsets, F + 1, np.uint64).copy()
+            qres = _view(R.residues, int(R.n_residues), np.uint8).copy()
+            orfs = _copy_struct_array(R.orfs, F, capi.Orf)
+            stats = dict(n_frames=F, n_residues=int(R.n_residues), kernel_ms=float(R.kernel_ms))
+        finally:
+            self.lib.spb_free_frames_result(r)
+        if make_resident:
+            self.Q = F
+        return qres, qoff, orfs, stats
+
     @staticmethod
     def _pref_stats(R):
         return dict(n_hits=int(R.n_hits), n_kmers=int(R.n_kmers), n_db_matches=int(R.n_db_matches),
@@ -375,6 +399,22 @@ class Searcher:
         finally:
             self.lib.spb_free_align_result(r)
         return off, rows, cig, stats
+
+
+def format_orf_headers(orfs, nt_lens, keys=None):
+    """Orf::writeOrfHeader (M/commons/Orf.cpp:440-457) as extractorfs calls it (M/util/extractorfs.cpp:93-99):
+    contig key \t from(+|-)|from-to| [\t incompleteStart | incompleteEnd << 1]"""
+    out = []
+    for o in orfs:
+        c = int(o["contig"])
+        L = int(nt_lens[c])
+        f, t = int(o["from_"]), int(o["to"])
+        if int(o["strand"]) == 1:
+            f, t = (L - 1) - f, (L - 1) - t
+        flags = int(o["incomplete_start"]) | (int(o["incomplete_end"]) << 1)
+        out.append("%d\t%d%s%d%s" % (int(keys[c]) if keys is not None else c, f, "+" if f < t else "-", abs(f - t),
+                                    ("\t%d" % flags) if flags else ""))
+    return out
 
 
 def format_prefilter_rows(hits, keys=None):

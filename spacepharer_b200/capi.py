@@ -61,6 +61,17 @@ class ExhaustiveStats(C.Structure):
                 ("kernel_ms", C.c_double), ("total_ms", C.c_double)]
 
 
+class Orf(C.Structure):
+    _fields_ = [("contig", C.c_uint32), ("from_", C.c_uint32), ("to", C.c_uint32), ("strand", C.c_uint8),
+                ("incomplete_start", C.c_uint8), ("incomplete_end", C.c_uint8), ("pad", C.c_uint8)]
+
+
+class FramesResult(C.Structure):
+    _fields_ = [("n_sequences", C.c_uint32), ("n_frames", C.c_uint32), ("n_residues", C.c_uint64),
+                ("offsets", C.POINTER(C.c_uint64)), ("residues", C.POINTER(C.c_ubyte)), ("orfs", C.POINTER(Orf)),
+                ("kernel_ms", C.c_double)]
+
+
 # every symbol include/spb200.h declares (tests check the library exports exactly these)
 SYMBOLS = [
     "spb_ctx_create", "spb_ctx_destroy", "spb_last_error", "spb_version", "spb_ctx_stream", "spb_set_matrices",
@@ -69,7 +80,7 @@ SYMBOLS = [
     "spb_bitscore", "spb_tantan_mask", "spb_queries_set", "spb_prefilter_resident", "spb_prefilter_stats",
     "spb_prefilter_fetch", "spb_pairs_set", "spb_pairs_from_prefilter", "spb_align_resident", "spb_align_stats",
     "spb_align_fetch", "spb_prefilter_device_result", "spb_prefilter_device_trunc_keys", "spb_prefilter_merge_shards",
-    "spb_pairs_exhaustive", "spb_align_exhaustive",
+    "spb_pairs_exhaustive", "spb_align_exhaustive", "spb_spacer_frames", "spb_free_frames_result",
 ]
 
 _lib = None
@@ -131,6 +142,9 @@ def load():
     L.spb_pairs_exhaustive.argtypes = [vp, C.POINTER(AlignParams), C.POINTER(ExhaustiveStats)]
     L.spb_align_exhaustive.argtypes = [vp, u8p, u64p, C.c_uint32, C.POINTER(AlignParams),
                                        C.POINTER(C.POINTER(AlignResult)), C.POINTER(ExhaustiveStats)]
+    L.spb_spacer_frames.argtypes = [vp, u8p, u64p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(C.POINTER(FramesResult))]
+    L.spb_free_frames_result.argtypes = [C.POINTER(FramesResult)]
+    L.spb_free_frames_result.restype = None
     L.spb_tantan_mask.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), u8p, u64p, C.c_uint32, C.c_int, u64p]
     _lib = L
     return L

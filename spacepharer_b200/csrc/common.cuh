@@ -164,6 +164,9 @@ struct spb_ctx {
 
 namespace spb {
 
+// installs a query batch as the resident one (spb_queries_set; residues may already live on the device)
+int queries_install(spb_ctx *c, const uint8_t *q_residues, bool on_device, const uint64_t *q_offsets, uint32_t Q);
+
 // ---------------------------------------------------------------------------------------------
 // block-level primitives (blockDim.x threads, multiple of 32, <= 1024)
 // ---------------------------------------------------------------------------------------------

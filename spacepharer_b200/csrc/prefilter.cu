@@ -1603,6 +1603,11 @@ extern "C" int spb_similar_kmers(spb_ctx *c, const uint8_t *kmer6, int thr, uint
 // resident pipeline
 // ------------------------------------------------------------------------------------------------------
 extern "C" int spb_queries_set(spb_ctx *c, const uint8_t *q_residues, const uint64_t *q_offsets, uint32_t Q) {
+    return spb::queries_install(c, q_residues, false, q_offsets, Q);
+}
+
+// residues on the host (spb_queries_set) or already on the device (frames produced by spb_spacer_frames); offsets on the host
+int spb::queries_install(spb_ctx *c, const uint8_t *q_residues, bool on_device, const uint64_t *q_offsets, uint32_t Q) {
     SPB_CHECK(c && q_offsets, "spb_queries_set: NULL argument");
     SPB_CUDA(cudaSetDevice(c->device));
     const uint64_t NQ = q_offsets[Q];
@@ -1626,7 +1631,7 @@ extern "C" int spb_queries_set(spb_ctx *c, const uint8_t *q_residues, const uint
     if (c->d_q.ensure(NQ + 64) || c->d_qoff.ensure(((size_t)Q + 1) * 4) || c->d_qoff64.ensure(((size_t)Q + 1) * 8) ||
         c->d_qorder.ensure((size_t)Q * 4 + 4)) return 1;
     if (Q) SPB_CUDA(cudaMemcpyAsync(c->d_qorder.p, order.data(), (size_t)Q * 4, cudaMemcpyHostToDevice, c->stream));
-    if (NQ) SPB_CUDA(cudaMemcpyAsync(c->d_q.p, q_residues, NQ, cudaMemcpyHostToDevice, c->stream));
+    if (NQ) SPB_CUDA(cudaMemcpyAsync(c->d_q.p, q_residues, NQ, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
     SPB_CUDA(cudaMemcpyAsync(c->d_qoff.p, off32.data(), off32.size() * 4, cudaMemcpyHostToDevice, c->stream));
     SPB_CUDA(cudaMemcpyAsync(c->d_qoff64.p, q_offsets, ((size_t)Q + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     SPB_CUDA(cudaStreamSynchronize(c->stream));

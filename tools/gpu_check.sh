@@ -15,8 +15,10 @@ if [ "${2:-}" != "quick" ]; then
   timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "ref rc=$?"
   cat $OUT/bench_ref_$TAG.json
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv \
-      python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/launches_$TAG.log 2>&1
+      python bench.py --steps 2 --warmup 1 --no-cpu-baseline --exhaustive-spacers 50 > $OUT/launches_$TAG.log 2>&1
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'prefilter_team_kernel|sw_fast_kernel' -s 3 -c 3 \
-      -o $OUT/prof_$TAG -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/prof_$TAG.log 2>&1
+      -o $OUT/prof_$TAG -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline --exhaustive-spacers 0 > $OUT/prof_$TAG.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'sw_exhaustive_kernel' -s 2 -c 2 \
+      -o $OUT/prof_exh_$TAG -f python tools/exh_probe.py 8000 100 > $OUT/prof_exh_$TAG.log 2>&1
 fi
 echo done

@@ -103,6 +103,22 @@ if os.path.exists(rep):
     json.dump(out, open(os.path.join(P, "traffic.json"), "w"), indent=1)
     print("wrote kernel metrics", out)
 
+rep = os.path.join(G, "prof_exh_%s.ncu-rep" % tag)
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    r = list(csv.reader(io.StringIO(raw)))
+    h, units, data = r[0], r[1], r[2:]
+    with open(os.path.join(P, "%s_exhaustive_kernels.csv" % tag), "w") as f:
+        w = csv.writer(f)
+        cols = ["Kernel Name"] + [k for k in KEYS + ["smsp__inst_executed_pipe_alu.sum", "smsp__inst_executed_pipe_fmaheavy.sum",
+                                                     "smsp__inst_executed_pipe_fmalite.sum", "sm__inst_executed_pipe_alu.sum"] if k in h]
+        cols = list(collections.OrderedDict.fromkeys(cols))
+        w.writerow(cols)
+        w.writerow([""] + [units[h.index(k)] for k in cols[1:]])
+        for row in data:
+            w.writerow([row[h.index(k)] for k in cols])
+    print("wrote exhaustive kernel metrics")
+
 for name in ("bench_%s.json" % tag, "bench_ref_%s.json" % tag):
     src = os.path.join(G, name)
     if os.path.exists(src) and os.path.getsize(src):
