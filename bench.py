@@ -201,7 +201,7 @@ def run_reference(args):
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def oracle_mask(tres, toff):
@@ -371,7 +371,7 @@ def run_ours(args):
             sample = min(args.spacers, args.cpu_sample_spacers or auto_sample(cores))
             r = cpu_reference_run(args, tres, toff, qres, qoff, 1, 0, sample, masked if not args.no_mask else None)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -386,8 +386,26 @@ def ncu_traffic():
         return None
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else (NCCL banners, library chatter) was moved to stderr"""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     args = parse_args()
+    # keep stdout clean for the JSON line: native libraries (NCCL prints its version banner there) write to fd 1 directly
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -133,6 +133,7 @@ struct spb_ctx {
     bool have_pref = false;
     uint64_t n_hits = 0;
     spb::DevBuf d_hits;           // spb_hit[n_hits]
+    spb::DevBuf d_hits_alt;       // second hit buffer: merged lists of the target split are built here, then swapped
     spb::DevBuf d_hitoff;         // u64[Q+1]
     bool have_tkeys = false;
     spb::DevBuf d_hit_tkeys;      // u64[n_hits] truncation keys (spb_prefilter_params.emit_trunc_keys), query order

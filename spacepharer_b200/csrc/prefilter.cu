@@ -1994,7 +1994,8 @@ extern "C" int spb_prefilter_merge_shards(spb_ctx *c, uint32_t q_lo, uint32_t q_
     SPB_CHECK(nIn == n_recv, "spb_prefilter_merge_shards: the counts add up to %llu hits but %llu were received",
               (unsigned long long)nIn, (unsigned long long)n_recv);
     // the receive buffer may alias nothing of ours; the merged lists replace the resident result
-    DevBuf merged;
+    // (grow-only second hit buffer of the context, swapped in below: no allocation on the per-batch path)
+    DevBuf &merged = c->d_hits_alt;
     if (merged.ensure(std::max<uint64_t>(nHits, 1) * sizeof(spb_hit))) return 1;
     unsigned int h_err[4] = {0, 0, 0, 0};
     if (nq && nIn) {
@@ -2009,10 +2010,9 @@ extern "C" int spb_prefilter_merge_shards(spb_ctx *c, uint32_t q_lo, uint32_t q_
         cudaError_t e = cudaGetLastError(); c->n_launches++;
         if (e == cudaSuccess) e = cudaMemcpyAsync(h_err, c->s_f.p, 16, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) { merged.release(); spb::set_error("spb_prefilter_merge_shards: %s", cudaGetErrorString(e)); return 1; }
+        if (e != cudaSuccess) { spb::set_error("spb_prefilter_merge_shards: %s", cudaGetErrorString(e)); return 1; }
     }
     if (h_err[0]) {
-        merged.release();
         if (d_recv_keys)
             spb::set_error("spb_prefilter_merge_shards: query %u has more than %d candidates across the target shards (merge capacity)",
                            h_err[0] - 1, MG_CAP);
@@ -2022,15 +2022,13 @@ extern "C" int spb_prefilter_merge_shards(spb_ctx *c, uint32_t q_lo, uint32_t q_
         return 2;
     }
     if (h_err[1]) {
-        merged.release();
         spb::set_error("spb_prefilter_merge_shards: the max-seqs (%d) cut of query %u falls among saturated diagonal counters (rescoreHits, "
                        "QueryMatcher.cpp:486-505), which needs the unsplit candidate set -- run this batch with query split",
                        max_seqs, h_err[1] - 1);
         return 2;
     }
     SPB_CHECK(h_err[2] == 0, "spb_prefilter_merge_shards: internal row count mismatch at query %u", h_err[2] - 1);
-    c->d_hits.release();
-    c->d_hits = merged;          // ownership moves to the context
+    std::swap(c->d_hits, c->d_hits_alt);   // the merged lists become the resident result
     c->n_hits = nHits;
     SPB_CUDA(cudaEventRecord(c->ev3, st));
     SPB_CUDA(cudaStreamSynchronize(st));

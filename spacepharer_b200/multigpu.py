@@ -64,16 +64,14 @@ def exchange_hit_lists(hits, offsets, ranges, rank, group=None, keys=None):
     bounds = torch.tensor([lo for lo, _ in ranges] + [ranges[-1][1]], dtype=torch.int64, device=offsets.device)
     cut = offsets[bounds].cpu().tolist()                      # hit offsets at the range boundaries (one small D2H)
     send_rows = [cut[r + 1] - cut[r] for r in range(G)]
-    sc = torch.tensor(send_rows, dtype=torch.int64, device=hits.device)
-    rc = torch.empty_like(sc)
-    dist.all_to_all_single(rc, sc, group=group)
-    recv_rows = rc.cpu().tolist()
     lo, hi = ranges[rank]
     nq = hi - lo
     cnt_all = (offsets[1:] - offsets[:-1]).to(torch.int32).contiguous()
     cnt_recv = torch.empty(G * nq, dtype=torch.int32, device=hits.device)
     dist.all_to_all_single(cnt_recv, cnt_all, output_split_sizes=[nq] * G, input_split_sizes=[h - l for l, h in ranges],
                            group=group)
+    # rows to expect from every shard = the sum of its per-query counts (no separate size exchange)
+    recv_rows = cnt_recv.view(G, nq).sum(dim=1, dtype=torch.int64).cpu().tolist() if nq else [0] * G
     recv = torch.empty((sum(recv_rows), 3), dtype=torch.int32, device=hits.device)
     dist.all_to_all_single(recv, hits.contiguous(), output_split_sizes=recv_rows, input_split_sizes=send_rows, group=group)
     if keys is None:
