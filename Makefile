@@ -5,7 +5,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-fopenmp --expt-extended-lambda -ccbin $(CXX)
 CSRC      := spacepharer_b200/csrc
 LIBDIR    := spacepharer_b200/lib
-CU        := $(CSRC)/capi.cu $(CSRC)/index.cu $(CSRC)/prefilter.cu $(CSRC)/align.cu $(CSRC)/frames.cu
+CU        := $(CSRC)/capi.cu $(CSRC)/index.cu $(CSRC)/prefilter.cu $(CSRC)/align.cu $(CSRC)/frames.cu $(CSRC)/nuclaln.cu
 OBJ       := $(patsubst $(CSRC)/%.cu,build/%.o,$(CU))
 HOSTLIBSRC := $(CSRC)/host/tantan.cpp
 HOSTLIBOBJ := $(patsubst $(CSRC)/host/%.cpp,build/host_%.o,$(HOSTLIBSRC))

@@ -231,6 +231,47 @@ int spb_spacer_frames(spb_ctx *ctx, const uint8_t *nt, const uint64_t *nt_offset
                       int max_codons, int make_resident, spb_frames_result **out);
 void spb_free_frames_result(spb_frames_result *r);
 
+/* ---- nucleotide re-alignment branch of predictmatch (--perform-nucl-aln 1, the reference's default) ------
+ * data/predictmatch.sh:27-45,74-92 runs, after each protein search,
+ *   proteinaln2nucl     lib/mmseqs/src/util/proteinaln2nucl.cpp:84-175   every alignment row is re-scored on the nucleotide
+ *                       ORFs (<db>_nucl_orf, same keys as <db>) along its protein backtrace: coordinates x 3, M columns scored
+ *                       with nucleotide.out (+2 / -3) and counted for identity, gap runs cost open + ((len-1)*3)*extend,
+ *                       bit score / E-value from the nucleotide ALP set with the nucleotide query length
+ *   combineprotnuclaln  src/util/CombineProtNuclAln.cpp:55-95           (text only; host side)
+ * Here the nucleotide ORFs stay resident next to the alignment targets and one kernel re-scores all rows of a batch.
+ * nt: raw ASCII nucleotides of the entries back to back (identity is a character comparison, as in the reference),
+ * offsets[n+1], start_codon (nullable): 1 where the amino-acid entry begins with '*'.  Target index i / query index i is
+ * the same index spb_align_set_targets / the query batch uses. */
+typedef struct spb_nucl_params {
+    int32_t gap_open, gap_extend;   /* nucl:10 / 2 */
+    uint64_t db_res_count;          /* DBReader::getAminoAcidDBSize of the target <db>_nucl_orf */
+    spb_gumbel gumbel;              /* ALP set of the nucleotide matrix and gap costs */
+    uint8_t letter[256];            /* NucleotideMatrix::setupLetterMapping, ASCII -> 0..4 (A C T G X) */
+    int16_t sub[25];                /* nucleotide matrix [5][5], bit factor 1, bias 0 */
+} spb_nucl_params;
+typedef struct spb_nucl_aln {       /* the Matcher::result_t proteinaln2nucl writes */
+    int32_t raw_score;              /* nucleotide score along the backtrace (may be negative) */
+    int32_t bits;                   /* (int) computeBitScore(raw): truncated */
+    double eval;
+    int32_t q_start, q_end, t_start, t_end;
+    uint32_t q_len, t_len;          /* nucleotide lengths */
+    uint32_t n_ident, aln_len;
+    float seq_id;
+    uint32_t err;                   /* 0 ok; 1 a start codon '*' is aligned (the reference exits: "Alignment contains
+                                       unalignable character"); 2 the backtrace leaves the nucleotide entry; 3 bad index */
+} spb_nucl_aln;
+int spb_nucl_set_targets(spb_ctx *ctx, const uint8_t *nt, const uint64_t *offsets, uint32_t T, const uint8_t *start_codon);
+int spb_nucl_set_queries(spb_ctx *ctx, const uint8_t *nt, const uint64_t *offsets, uint32_t Q, const uint8_t *start_codon);
+/* re-score explicit rows (what the module reads from an alignment DB): rows[i].query / .target index the resident
+ * nucleotide entries, rows[i].cigar_off / cigar_len slice cigar_ops (one op per column).  *out: n_rows results owned by
+ * the context until spb_free_nucl_result. */
+int spb_nucl_rescore(spb_ctx *ctx, const spb_nucl_params *p, const spb_aln *rows, uint64_t n_rows, const char *cigar_ops,
+                     uint64_t n_cigar, spb_nucl_aln **out);
+/* re-score the resident alignment result (after spb_align_resident; the rows never leave HBM): out[i] belongs to row i
+ * of spb_align_fetch.  kernel_ms (nullable): device time of the kernel. */
+int spb_nucl_rescore_resident(spb_ctx *ctx, const spb_nucl_params *p, spb_nucl_aln **out, uint64_t *n_rows, double *kernel_ms);
+void spb_free_nucl_result(spb_ctx *ctx, spb_nucl_aln *r);
+
 /* ---- multi-GPU target split ------------------------------------------------------------------------
  * MMseqs2 shards targets with --split (Prefiltering.cpp:258-362) and merges the per-split result files
  * (mergeTargetSplits, Prefiltering.cpp:364-481).  Here every GPU prefilters all queries against its target shard

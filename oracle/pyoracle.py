@@ -82,6 +82,27 @@ GUMBEL_VTML40_16_2 = dict(
     sigma=0.18283871043913499, tau=1.7838353361758408)
 
 
+# ALP parameters of nucleotide.out, gap open 10 / extend 2 (proteinaln2nucl; probed from the reference build, seed 42)
+GUMBEL_NUCL_10_2 = dict(
+    lambda_=0.63361984397325744, K=0.42150719938226583,
+    a_I=0.68666204026925159, b_I=0.18923575026627315,
+    alpha_I=0.71225621255786731, beta_I=2.9058945364387716,
+    a_J=0.68666204026925159, b_J=0.18923575026627315,
+    alpha_J=0.71225621255786731, beta_J=2.9058945364387716,
+    sigma=0.7125673897037631, tau=2.8984262849372726)
+
+
+class NuclParams(C.Structure):
+    _fields_ = [("gapOpen", C.c_int), ("gapExtend", C.c_int), ("dbResCount", C.c_uint64), ("g", Gumbel),
+                ("letter", C.c_ubyte * 256), ("sub", (C.c_short * 5) * 5)]
+
+
+class NuclRow(C.Structure):
+    _fields_ = [("err", C.c_int), ("rawScore", C.c_int), ("bits", C.c_int), ("eval", C.c_double),
+                ("qStart", C.c_int), ("qEnd", C.c_int), ("tStart", C.c_int), ("tEnd", C.c_int), ("qLen", C.c_int), ("tLen", C.c_int),
+                ("idCnt", C.c_uint), ("alnLen", C.c_uint), ("seqId", C.c_float), ("cigar", C.c_char * 1024)]
+
+
 class Orf(C.Structure):
     _fields_ = [("from_", C.c_uint32), ("to", C.c_uint32), ("strand", C.c_int), ("incomplete_start", C.c_int),
                 ("incomplete_end", C.c_int)]
@@ -137,6 +158,15 @@ def lib():
     L.spo_extract_frames.restype = C.c_int
     L.spo_format_row.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(Aln), C.c_int, C.c_int]
     L.spo_format_row.restype = C.c_int
+    L.spo_nucl_default_params.argtypes = [C.POINTER(NuclParams), C.c_uint64]
+    L.spo_nucl_default_params.restype = None
+    L.spo_nucl_rescore.argtypes = [C.POINTER(NuclParams), C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(NuclRow)]
+    L.spo_nucl_rescore.restype = None
+    L.spo_format_nucl_row.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(NuclRow)]
+    L.spo_format_nucl_row.restype = C.c_int
+    L.spo_combine_evalue.argtypes = [C.c_double, C.c_double]
+    L.spo_combine_evalue.restype = C.c_double
     _LIB = L
     return L
 
@@ -345,3 +375,42 @@ def orf_header(key, length, o):
         f, t = (length - 1) - f, (length - 1) - t
     flags = int(o[3]) | (int(o[4]) << 1)
     return "%d\t%d%s%d%s" % (key, f, "+" if f < t else "-", abs(f - t), ("\t%d" % flags) if flags else "")
+
+
+# ---- nucleotide re-alignment branch (--perform-nucl-aln 1) -------------------------------------------------------
+def nucl_params(db_res_count):
+    p = NuclParams()
+    lib().spo_nucl_default_params(C.byref(p), int(db_res_count))
+    return p
+
+
+def nucl_rescore(p, q_nt, t_nt, q_start, q_end, t_start, t_end, cigar, q_start_codon=False, t_start_codon=False):
+    """proteinaln2nucl for one protein alignment row; q_nt / t_nt: ASCII nucleotides (bytes) of the two ORFs."""
+    r = NuclRow()
+    lib().spo_nucl_rescore(C.byref(p), q_nt, len(q_nt), int(q_start_codon), t_nt, len(t_nt), int(t_start_codon),
+                           q_start, q_end, t_start, t_end, cigar.encode() if isinstance(cigar, str) else cigar, C.byref(r))
+    return r
+
+
+def format_nucl_row(tkey, r):
+    buf = C.create_string_buffer(2048)
+    n = lib().spo_format_nucl_row(buf, tkey, C.byref(r))
+    return buf.raw[:n].decode()
+
+
+def combine_prot_nucl(prot_rows, nucl_rows):
+    """combineprotnuclaln for one query entry (src/util/CombineProtNuclAln.cpp:55-95) on text rows: per protein row the LAST
+    nucleotide row of the same target key gives the sequence identity and min(geometric mean, nucleotide) E-value, both
+    re-read from their printed form and printed with %.3E."""
+    out = []
+    for pr in prot_rows:
+        f = pr.split("\t")
+        upd, sid = 3.40282346638528859811704183484516925e+38, 0.0
+        for nr in nucl_rows:
+            g = nr.split("\t")
+            if g[0] != f[0]:
+                continue
+            sid = float(g[2])
+            upd = lib().spo_combine_evalue(float(f[3]), float(g[3]))
+        out.append("\t".join(f[:2] + ["%.3E" % sid, "%.3E" % upd] + f[4:]))
+    return out

@@ -1312,3 +1312,92 @@ int spo_extract_frames(const char *seq, int length, int minCodons, int maxCodons
     free(rev);
     return n;
 }
+
+/* =========================================================================================================
+ * Nucleotide re-alignment branch of predictmatch (--perform-nucl-aln 1).
+ * ========================================================================================================= */
+/* NucleotideMatrix::setupLetterMapping (M/commons/NucleotideMatrix.cpp:18-63) over the alphabet order of
+ * lib/mmseqs/data/nucleotide.out (A C T G X); scores of that file at bit factor 1, bias 0; ALP parameters of
+ * nucleotide.out with gap open 10 / extend 2 as EvalueComputation::init estimates them (EvalueComputation.h:48-154,
+ * seed 42; probed from the reference build, identical over runs -- an input like the VTML40 set) */
+void spo_nucl_default_params(spo_nucl_params *p, uint64_t dbResCount) {
+    memset(p, 0, sizeof(*p));
+    p->gapOpen = 10; p->gapExtend = 2; p->dbResCount = dbResCount;
+    for (int c = 0; c < 256; c++) {
+        int u = toupper(c), n;
+        switch (u) {
+            case 'A': n = 0; break;
+            case 'C': case 'M': case 'Y': case 'H': n = 1; break;
+            case 'T': case 'U': case 'W': n = 2; break;
+            case 'G': case 'K': case 'B': case 'D': case 'V': case 'R': case 'S': n = 3; break;
+            default: n = 4; break;
+        }
+        p->letter[c] = (unsigned char)n;
+    }
+    for (int i = 0; i < 5; i++)
+        for (int j = 0; j < 5; j++) p->sub[i][j] = (short)((i == j && i < 4) ? 2 : -3);
+    spo_gumbel g = {0.63361984397325744, 0.42150719938226583, 0.68666204026925159, 0.18923575026627315,
+                    0.71225621255786731, 2.9058945364387716, 0.68666204026925159, 0.18923575026627315,
+                    0.71225621255786731, 2.9058945364387716, 0.7125673897037631, 2.8984262849372726};
+    p->g = g;
+}
+
+/* proteinaln2nucl, per alignment row (lib/mmseqs/src/util/proteinaln2nucl.cpp:113-172): coordinates times three (minus
+ * one codon when the amino-acid entry starts with '*'), the protein backtrace walked codon by codon over the raw
+ * nucleotide characters: M = three columns scored with the ASCII nucleotide matrix and compared for identity,
+ * I / D = gapOpen + ((cnt - 1) * 3) * gapExtend; bit score truncated to int, E-value with the NUCLEOTIDE query length */
+void spo_nucl_rescore(const spo_nucl_params *p, const char *q, int qLen, int qStartCodon, const char *t, int tLen, int tStartCodon,
+                      int qStart, int qEnd, int tStart, int tEnd, const char *cigar, spo_nucl_row *out) {
+    memset(out, 0, sizeof(*out));
+    if ((qStartCodon && qStart == 0) || (tStartCodon && tStart == 0)) { out->err = 1; return; }
+    out->tStart = tStart * 3 + (tStartCodon ? -3 : 0);
+    out->tEnd = tEnd * 3 + 2 + (tStartCodon ? -3 : 0);
+    out->tLen = tLen;
+    out->qStart = qStart * 3 + (qStartCodon ? -3 : 0);
+    out->qEnd = qEnd * 3 + 2 + (qStartCodon ? -3 : 0);
+    out->qLen = qLen;
+    int qPos = out->qStart, tPos = out->tStart, score = 0;
+    unsigned idCnt = 0, alnLen = 0;
+    char *w = out->cigar;
+    for (const char *c = cigar; *c;) {
+        int cnt = 0;
+        while (isdigit((unsigned char)*c)) cnt = cnt * 10 + (*c++ - '0');
+        char op = *c++;
+        if (op == 'M') {
+            for (int bt = 0; bt < cnt * 3; bt++) {
+                idCnt += (q[qPos] == t[tPos]);
+                score += p->sub[p->letter[(unsigned char)q[qPos]]][p->letter[(unsigned char)t[tPos]]];
+                tPos++; qPos++;
+            }
+        } else if (op == 'D') {
+            tPos += cnt * 3;
+            score -= p->gapOpen + ((cnt - 1) * 3) * p->gapExtend;
+        } else if (op == 'I') {
+            qPos += cnt * 3;
+            score -= p->gapOpen + ((cnt - 1) * 3) * p->gapExtend;
+        } else {
+            continue;
+        }
+        alnLen += (unsigned)cnt * 3;
+        w += sprintf(w, "%d%c", cnt * 3, op);
+    }
+    out->rawScore = score;
+    out->bits = (int)spo_bitscore(&p->g, score);
+    out->eval = spo_evalue(&p->g, score, qLen, (double)p->dbResCount);
+    out->idCnt = idCnt; out->alnLen = alnLen;
+    out->seqId = (float)idCnt / (float)alnLen;
+}
+
+int spo_format_nucl_row(char *buf, uint32_t tKey, const spo_nucl_row *r) {
+    spo_aln a;
+    memset(&a, 0, sizeof(a));
+    a.bits = r->bits; a.eval = r->eval; a.seqId = r->seqId;
+    a.qStart = r->qStart; a.qEnd = r->qEnd; a.tStart = r->tStart; a.tEnd = r->tEnd;
+    strcpy(a.cigar, r->cigar);
+    return spo_format_row(buf, tKey, &a, r->qLen, r->tLen);
+}
+
+/* src/util/CombineProtNuclAln.cpp:85 */
+double spo_combine_evalue(double protEval, double nuclEval) {
+    return ((log(protEval) * 0.5 + log(nuclEval) * 0.5) < log(nuclEval)) ? exp(log(protEval) * 0.5 + log(nuclEval) * 0.5) : nuclEval;
+}

@@ -8,6 +8,7 @@ layouts.  All arithmetic of the hot path runs in libspb200's CUDA kernels; there
 """
 import ctypes as C
 import math
+import re
 
 import numpy as np
 
@@ -399,6 +400,108 @@ class Searcher:
         finally:
             self.lib.spb_free_align_result(r)
         return off, rows, cig, stats
+
+
+    # ---- nucleotide re-alignment branch (predictmatch --perform-nucl-aln 1) ----------------------------------
+    def _set_nt(self, fn, seqs, start_codon):
+        lens = np.fromiter((len(x) for x in seqs), dtype=np.uint64, count=len(seqs))
+        off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        np.cumsum(lens, out=off[1:])
+        nt = np.frombuffer(b"".join(seqs), dtype=np.uint8) if len(seqs) else np.zeros(0, dtype=np.uint8)
+        sc = None if start_codon is None else np.ascontiguousarray(start_codon, dtype=np.uint8)
+        capi.check(fn(self.h, _u8(np.ascontiguousarray(nt)), _u64(off), len(seqs), _u8(sc) if sc is not None else None))
+
+    def set_nucl_targets(self, seqs, start_codon=None):
+        """seqs: ASCII nucleotide ORFs (bytes) of the alignment targets, same order (the <db>_nucl_orf entries)"""
+        self._set_nt(self.lib.spb_nucl_set_targets, seqs, start_codon)
+
+    def set_nucl_queries(self, seqs, start_codon=None):
+        self._set_nt(self.lib.spb_nucl_set_queries, seqs, start_codon)
+
+    def nucl_rescore(self, db_res_count, rows=None, cigar=b"", gap_open=10, gap_extend=2, gumbel=None):
+        """proteinaln2nucl (lib/mmseqs/src/util/proteinaln2nucl.cpp:84-175) on the device: rows=None re-scores the
+        resident alignment result (row i belongs to row i of align_fetch), else the given rows (structured array of
+        capi.Aln + their cigar ops).  -> (structured array of capi.NuclAln, kernel_ms)"""
+        p = nucl_params(db_res_count, gap_open, gap_extend, gumbel)
+        r = C.POINTER(capi.NuclAln)()
+        ms = C.c_double(0)
+        if rows is None:
+            n = C.c_uint64(0)
+            capi.check(self.lib.spb_nucl_rescore_resident(self.h, C.byref(p), C.byref(r), C.byref(n), C.byref(ms)))
+            n = int(n.value)
+        else:
+            rows = np.ascontiguousarray(rows)
+            n = len(rows)
+            capi.check(self.lib.spb_nucl_rescore(self.h, C.byref(p), rows.ctypes.data_as(C.POINTER(capi.Aln)), n, bytes(cigar),
+                                                 len(cigar), C.byref(r)))
+        try:
+            out = _copy_struct_array(r, n, capi.NuclAln)
+        finally:
+            self.lib.spb_free_nucl_result(self.h, r)
+        return out, float(ms.value)
+
+
+# ALP parameters of nucleotide.out with gap open 10 / extend 2 (what proteinaln2nucl uses in predictmatch); like the
+# VTML40 set they are estimated by the reference at start-up (EvalueComputation.h:48-154, seed 42) and are an input here
+GUMBEL_NUCL_10_2 = (0.63361984397325744, 0.42150719938226583, 0.68666204026925159, 0.18923575026627315, 0.71225621255786731,
+                    2.9058945364387716, 0.68666204026925159, 0.18923575026627315, 0.71225621255786731, 2.9058945364387716,
+                    0.7125673897037631, 2.8984262849372726)
+
+
+def nucl_params(db_res_count, gap_open=10, gap_extend=2, gumbel=None):
+    """NucleotideMatrix(nucleotide.out, 1.0, 0.0) + its letter mapping (M/commons/NucleotideMatrix.cpp:18-63)"""
+    if gumbel is None:
+        if (gap_open, gap_extend) != (10, 2):
+            raise ValueError("no ALP parameter set for nucleotide.out %d/%d: pass gumbel=" % (gap_open, gap_extend))
+        gumbel = GUMBEL_NUCL_10_2
+    p = capi.NuclParams()
+    p.gap_open, p.gap_extend, p.db_res_count = gap_open, gap_extend, int(db_res_count)
+    p.gumbel = capi.Gumbel(*gumbel)
+    groups = {"A": 0, "C": 1, "M": 1, "Y": 1, "H": 1, "T": 2, "U": 2, "W": 2, "G": 3, "K": 3, "B": 3, "D": 3, "V": 3, "R": 3, "S": 3}
+    for c in range(256):
+        p.letter[c] = groups.get(chr(c).upper(), 4) if c < 128 else 4
+    for i in range(5):
+        for j in range(5):
+            p.sub[i * 5 + j] = 2 if (i == j and i < 4) else -3
+    return p
+
+
+def format_nucl_rows(nrows, rows, cigar, keys=None):
+    """Matcher::resultToBuffer of the rows proteinaln2nucl writes: the protein backtrace with every run length tripled"""
+    out = []
+    for n, r in zip(nrows, rows):
+        if int(n["err"]):
+            raise capi.SpbError("Alignment contains unalignable character" if int(n["err"]) == 1 else
+                                "nucleotide re-alignment: row outside its nucleotide entry (err %d)" % int(n["err"]))
+        t = int(r["target"])
+        ops = cigar[int(r["cigar_off"]): int(r["cigar_off"]) + int(r["cigar_len"])].decode()
+        bt = "".join("%d%s" % (3 * int(c), o) for c, o in re.findall(r"(\d+)([MID])", compress_cigar(ops))) if ops else ""
+        out.append("%d\t%d\t%s\t%.3E\t%d\t%d\t%d\t%d\t%d\t%d\t%s" % (
+            int(keys[t]) if keys is not None else t, int(n["bits"]), format_seq_id(n["seq_id"]), float(n["eval"]),
+            int(n["q_start"]), int(n["q_end"]), int(n["q_len"]), int(n["t_start"]), int(n["t_end"]), int(n["t_len"]), bt))
+    return out
+
+
+def combine_prot_nucl_rows(prot_rows, nucl_rows):
+    """combineprotnuclaln (src/util/CombineProtNuclAln.cpp:55-95) for one query entry, on text rows: per protein row the
+    last nucleotide row of the same target key replaces the sequence identity and gives the updated E-value
+    min(sqrt(protE * nuclE), nuclE), both re-read from their printed form and printed with %.3E (SSTR(double))."""
+    import math
+    out = []
+    for pr in prot_rows:
+        f = pr.split("\t")
+        upd, sid = 3.40282346638528859811704183484516925e+38, 0.0   # FLT_MAX, 0
+        for nr in nucl_rows:
+            g = nr.split("\t")
+            if int(g[0]) != int(f[0]):
+                continue
+            sid = float(g[2])
+            pe, ne = float(f[3]), float(g[3])
+            lp = math.log(pe) if pe > 0 else -math.inf
+            ln = math.log(ne) if ne > 0 else -math.inf
+            upd = math.exp(lp * 0.5 + ln * 0.5) if (lp * 0.5 + ln * 0.5) < ln else ne
+        out.append("\t".join(f[:2] + ["%.3E" % sid, "%.3E" % upd] + f[4:]))
+    return out
 
 
 def format_orf_headers(orfs, nt_lens, keys=None):

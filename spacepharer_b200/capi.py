@@ -86,6 +86,17 @@ SYMBOLS = [
 _lib = None
 
 
+class NuclParams(C.Structure):
+    _fields_ = [("gap_open", C.c_int32), ("gap_extend", C.c_int32), ("db_res_count", C.c_uint64), ("gumbel", Gumbel),
+                ("letter", C.c_uint8 * 256), ("sub", C.c_int16 * 25)]
+
+
+class NuclAln(C.Structure):
+    _fields_ = [("raw_score", C.c_int32), ("bits", C.c_int32), ("eval", C.c_double), ("q_start", C.c_int32), ("q_end", C.c_int32),
+                ("t_start", C.c_int32), ("t_end", C.c_int32), ("q_len", C.c_uint32), ("t_len", C.c_uint32),
+                ("n_ident", C.c_uint32), ("aln_len", C.c_uint32), ("seq_id", C.c_float), ("err", C.c_uint32)]
+
+
 class SpbError(RuntimeError):
     pass
 
@@ -145,6 +156,13 @@ def load():
     L.spb_spacer_frames.argtypes = [vp, u8p, u64p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(C.POINTER(FramesResult))]
     L.spb_free_frames_result.argtypes = [C.POINTER(FramesResult)]
     L.spb_free_frames_result.restype = None
+    L.spb_nucl_set_targets.argtypes = [vp, u8p, u64p, C.c_uint32, u8p]
+    L.spb_nucl_set_queries.argtypes = [vp, u8p, u64p, C.c_uint32, u8p]
+    L.spb_nucl_rescore.argtypes = [vp, C.POINTER(NuclParams), C.POINTER(Aln), C.c_uint64, C.c_char_p, C.c_uint64,
+                                   C.POINTER(C.POINTER(NuclAln))]
+    L.spb_nucl_rescore_resident.argtypes = [vp, C.POINTER(NuclParams), C.POINTER(C.POINTER(NuclAln)), u64p, C.POINTER(C.c_double)]
+    L.spb_free_nucl_result.argtypes = [vp, C.POINTER(NuclAln)]
+    L.spb_free_nucl_result.restype = None
     L.spb_tantan_mask.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), u8p, u64p, C.c_uint32, C.c_int, u64p]
     _lib = L
     return L

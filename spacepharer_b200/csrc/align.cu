@@ -86,28 +86,6 @@ __global__ void __launch_bounds__(128) align_profile_kernel(const uint8_t *__res
     }
 }
 
-// ---- E-value on the device (lib/alp/sls_pvalues.cpp:366-541) ----
-__device__ __forceinline__ double dev_evalue(const spb_gumbel &g, double y, double n, double m) {
-    const double const_val = 0.3989422804014326779;  // 1/sqrt(2 pi)
-    double m_li_y = m - (g.a_I * y + g.b_I);
-    double vi_y = fmax(2.0 * g.alpha_I / g.lambda, g.alpha_I * y + g.beta_I);
-    double sqrt_vi_y = sqrt(vi_y);
-    double m_F = sqrt_vi_y == 0.0 ? 1e100 : m_li_y / sqrt_vi_y;
-    double P_m_F = 0.5 * erfc(-sqrt(0.5) * m_F);
-    double E_m_F = -const_val * exp(-0.5 * m_F * m_F);
-    double p1 = m_li_y * P_m_F - sqrt_vi_y * E_m_F;
-    double n_lj_y = n - (g.a_J * y + g.b_J);
-    double vj_y = fmax(2.0 * g.alpha_J / g.lambda, g.alpha_J * y + g.beta_J);
-    double sqrt_vj_y = sqrt(vj_y);
-    double n_F = sqrt_vj_y == 0.0 ? 1e100 : n_lj_y / sqrt_vj_y;
-    double P_n_F = 0.5 * erfc(-sqrt(0.5) * n_F);
-    double E_n_F = -const_val * exp(-0.5 * n_F * n_F);
-    double p2 = n_lj_y * P_n_F - sqrt_vj_y * E_n_F;
-    double c_y = fmax(2.0 * g.sigma / g.lambda, g.sigma * y + g.tau);
-    double area = p1 * p2 + c_y * (P_m_F * P_n_F);
-    return g.K * exp(-g.lambda * y) * area;
-}
-
 struct PairOut {      // per pair, written by the forward kernel, completed by reverse / traceback
     int32_t score, qEnd, tEnd, word;
     int32_t qStart, tStart;

@@ -14,7 +14,11 @@
 //   spb200 filtermatchbyfdr <cScoreDB> <controlcScoreDB> <matchDB> [--fdr 0.05 --report-fdr 0]
 //   spb200 predictmatch <querySetDB> <targetSetDB> <controlTargetSetDB> <matchDB> <tmpDir> [search flags, --fdr ...]
 //       search against the target and the reversed-ORF control setDB on the GPU, then the four stages in memory;
-//       writes the `match` DB of predictmatch.sh (--perform-nucl-aln 0 branch).
+//       writes the `match` DB of predictmatch.sh; --perform-nucl-aln 1 (the reference's default) re-scores every alignment on
+//       the <db>_nucl_orf entries on the device and combines the E-values before the set stages.
+// and the two modules of that nucleotide branch (data/predictmatch.sh:35-45):
+//   spb200 proteinaln2nucl <queryDB>_nucl_orf <targetDB>_nucl_orf <queryDB> <targetDB> <alnDB> <outDB>
+//   spb200 combineprotnuclaln <protAlnDB> <nuclAlnDB> <outDB>
 // Host-only helpers used by the CPU tests: dumpmatrix, dbcopy, showparams.
 // Errors follow the reference: message on stderr, exit code 1 (Debug(Debug::ERROR) ... EXIT(EXIT_FAILURE)).
 #include <ctype.h>
@@ -28,6 +32,7 @@
 
 #include <algorithm>
 #include <stdexcept>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -67,7 +72,7 @@ struct Params {
     int threads = 1, verbosity = 3, compressed = 0;
     // spb200-specific
     int device = 0, binSize = 0, byteLanes = 32, wordLanes = 16;
-    std::string gumbel;
+    std::string gumbel, gumbelNucl;
     long batch = 1000000;
     // set-level stages (M/commons/Parameters.cpp:217,2277; src/commons/LocalParameters.h:75-77,171-176)
     int simpleBestHit = 1, reportFdr = 0, performNuclAln = 1, keepIntermediate = 0;
@@ -106,7 +111,7 @@ std::vector<FlagDef> flag_table(Params &p) {
         // spb200-specific
         {"--keep-intermediate", 0, &p.keepIntermediate},
         {"--device", 0, &p.device}, {"--bin-size", 0, &p.binSize}, {"--byte-lanes", 0, &p.byteLanes}, {"--word-lanes", 0, &p.wordLanes},
-        {"--gumbel", 3, &p.gumbel}, {"--batch", 0, nullptr},
+        {"--gumbel", 3, &p.gumbel}, {"--gumbel-nucl", 3, &p.gumbelNucl}, {"--batch", 0, nullptr},
     };
 }
 
@@ -186,6 +191,18 @@ bool gumbel_for(const std::string &mat, int go, int ge, const std::string &overr
         const double t[12] = {0.34420393530174209, 0.27487374979561635, 0.22018895496520485, 0.026237512825550646,
                               0.18481499377626534, 1.7126891360391483, 0.22018895496520485, 0.026237512825550646,
                               0.18481499377626534, 1.7126891360391483, 0.18283871043913499, 1.7838353361758408};
+        memcpy(v, t, sizeof(v));
+    } else if (mat == "nucleotide.out" && go == 10 && ge == 2) {
+        // estimated by the reference at start-up like the VTML40 set (EvalueComputation.h:48-154, seed 42); probed from the
+        // reference build for proteinaln2nucl's NucleotideMatrix(nucleotide.out, 1.0, 0.0) with --gap-open nucl:10 --gap-extend 2
+        const double t[12] = {0.63361984397325744, 0.42150719938226583, 0.68666204026925159, 0.18923575026627315,
+                              0.71225621255786731, 2.9058945364387716, 0.68666204026925159, 0.18923575026627315,
+                              0.71225621255786731, 2.9058945364387716, 0.7125673897037631, 2.8984262849372726};
+        memcpy(v, t, sizeof(v));
+    } else if (mat == "nucleotide.out" && go == 7 && ge == 1) {   // EvalueComputation.h:57-62
+        const double t[12] = {1.0960171987681839, 0.33538787507026158, 2.0290734315292083, -0.46514786408422282,
+                              5.0543294182155085, 15.130999712620039, 2.0290734315292083, -0.46514786408422282,
+                              5.0543294182155085, 15.130999712620039, 5.0543962679167036, 15.129930117400917};
         memcpy(v, t, sizeof(v));
     } else if (mat == "blosum62.out" && go == 11 && ge == 1) {
         const double t[12] = {0.27359865037097330642, 0.044620920658722244834, 1.5938724404943873658, -19.959867650284412122,
@@ -519,9 +536,192 @@ int run_align(int argc, const char **argv) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// nucleotide re-alignment branch (proteinaln2nucl on the device, combineprotnuclaln in setscore.cpp)
+// ---------------------------------------------------------------------------------------------------------
+void set_predictmatch_defaults(struct Params &p);
+
+struct NuclSet {
+    std::vector<uint8_t> nt;          // raw ASCII nucleotides, entries back to back
+    std::vector<uint64_t> off;
+    std::vector<uint8_t> startCodon;  // the amino-acid entry begins with '*' (proteinaln2nucl.cpp:92-96,113-118)
+    uint64_t dbSize = 0;              // getAminoAcidDBSize of the nucleotide DB
+};
+
+// entry i = the <db>_nucl_orf entry with key keys[i] (the reference looks both DBs up by key, proteinaln2nucl.cpp:88-112)
+void load_nucl(const std::string &nuclName, const DBReader &aaDb, const std::vector<uint32_t> &keys, NuclSet &N) {
+    DBReader ndb;
+    ndb.open(nuclName);
+    if (ndb.dbtype() != 1 || aaDb.dbtype() != DBTYPE_AMINO_ACIDS) throw Fail("Wrong query and target database input");
+    N.dbSize = ndb.aminoAcidDBSize();
+    const size_t n = keys.size();
+    N.off.assign(n + 1, 0);
+    N.startCodon.assign(n + 1, 0);
+    std::vector<size_t> pos(n);
+    for (size_t i = 0; i < n; i++) {
+        pos[i] = ndb.findKey(keys[i]);
+        if (pos[i] == SIZE_MAX) throw Fail("Invalid database key " + std::to_string(keys[i]) + " in " + nuclName);
+        const DBEntry &e = ndb.byKey(pos[i]);
+        N.off[i + 1] = N.off[i] + (e.length >= 2 ? e.length - 2 : 0);     // DBReader::getSeqLen
+        const size_t a = aaDb.findKey(keys[i]);
+        if (a != SIZE_MAX && aaDb.byKey(a).length > 0 && aaDb.data(aaDb.byKey(a))[0] == '*') N.startCodon[i] = 1;
+    }
+    N.nt.resize(N.off[n] + 1);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long i = 0; i < (long)n; i++) memcpy(N.nt.data() + N.off[i], ndb.data(ndb.byKey(pos[(size_t)i])), (size_t)(N.off[i + 1] - N.off[i]));
+}
+
+void fill_nucl_params(const Params &p, uint64_t dbSize, spb_nucl_params *np) {
+    memset(np, 0, sizeof(*np));
+    std::string mat = multiparam_nucl(p.subMat);
+    const size_t slash = mat.find_last_of('/');
+    if (slash != std::string::npos) mat = mat.substr(slash + 1);
+    if (mat != "nucleotide.out") throw Fail("nucleotide re-alignment: only nucleotide.out is supported as nucleotide matrix, got '" + mat + "'");
+    np->gap_open = atoi(multiparam_nucl(p.gapOpen).c_str());
+    np->gap_extend = atoi(multiparam_nucl(p.gapExtend).c_str());
+    np->db_res_count = dbSize;
+    if (!gumbel_for(mat, np->gap_open, np->gap_extend, p.gumbelNucl, &np->gumbel))
+        throw Fail("no Gumbel parameters for " + mat + " gap open " + std::to_string(np->gap_open) + " extend " + std::to_string(np->gap_extend) +
+                   ": pass the twelve ALP values of the reference run with --gumbel-nucl");
+    // NucleotideMatrix::setupLetterMapping (M/commons/NucleotideMatrix.cpp:18-63), alphabet order of nucleotide.out: A C T G X
+    for (int c = 0; c < 256; c++) {
+        int n = 4;
+        switch (c < 128 ? toupper(c) : 0) {
+            case 'A': n = 0; break;
+            case 'C': case 'M': case 'Y': case 'H': n = 1; break;
+            case 'T': case 'U': case 'W': n = 2; break;
+            case 'G': case 'K': case 'B': case 'D': case 'V': case 'R': case 'S': n = 3; break;
+            default: break;
+        }
+        np->letter[c] = (uint8_t)n;
+    }
+    // nucleotide.out at bit factor 1, bias 0 (lib/mmseqs/data/nucleotide.out): match 2, everything else -3
+    for (int i = 0; i < 5; i++)
+        for (int j = 0; j < 5; j++) np->sub[i * 5 + j] = (int16_t)((i == j && i < 4) ? 2 : -3);
+}
+
+void nucl_row_error(const spb_nucl_aln &n) {
+    if (n.err == 1) throw Fail("Alignment contains unalignable character");
+    if (n.err) throw Fail("nucleotide re-alignment: an alignment row does not fit its nucleotide entry (code " + std::to_string(n.err) + ")");
+}
+
+// the row proteinaln2nucl writes (Matcher::resultToBuffer, proteinaln2nucl.cpp:160-172): nucleotide coordinates / lengths and
+// the protein backtrace with every run length tripled
+void append_nucl_row(std::string &buf, uint32_t tKey, const spb_nucl_aln &n, const char *ops, uint32_t nOps) {
+    char tmp[256];
+    char *w = tmp;
+    w += sprintf(w, "%u\t%d\t", tKey, n.bits);
+    w += seqid_to_buffer(n.seq_id, w);
+    w += sprintf(w, "\t%.3E\t%d\t%d\t%u\t%d\t%d\t%u\t", n.eval, n.q_start, n.q_end, n.q_len, n.t_start, n.t_end, n.t_len);
+    buf.append(tmp, (size_t)(w - tmp));
+    for (uint32_t i = 0; i < nOps;) {
+        uint32_t j = i;
+        while (j < nOps && ops[j] == ops[i]) j++;
+        buf.append(tmp, (size_t)sprintf(tmp, "%u%c", (j - i) * 3, ops[i]));
+        i = j;
+    }
+    buf.push_back('\n');
+}
+
+// <queryDB>_nucl_orf <targetDB>_nucl_orf <queryDB> <targetDB> <alnDB> <outDB>   (proteinaln2nucl.cpp:13-72)
+int run_proteinaln2nucl(int argc, const char **argv) {
+    Params p;
+    set_predictmatch_defaults(p);
+    parse_args(argc, argv, 2, 6, p);
+    DBReader qaa, taa, aln;
+    qaa.open(p.db[2]);
+    taa.open(p.db[3]);
+    aln.open(p.db[4]);
+    std::vector<uint32_t> qkeys(aln.size()), tkeys(taa.size());
+    for (size_t i = 0; i < aln.size(); i++) qkeys[i] = aln.byKey(i).key;
+    for (size_t i = 0; i < taa.size(); i++) tkeys[i] = taa.byKey(i).key;
+    NuclSet QN, TN;
+    load_nucl(p.db[0], qaa, qkeys, QN);
+    load_nucl(p.db[1], taa, tkeys, TN);
+    spb_nucl_params np;
+    fill_nucl_params(p, TN.dbSize, &np);
+    // Matcher::parseAlignmentRecord (M/alignment/Matcher.cpp:232-321): key score seqId eval qStart qEnd qLen dbStart dbEnd dbLen backtrace
+    std::vector<spb_aln> rows;
+    std::vector<uint64_t> rowOff(aln.size() + 1, 0);
+    std::string ops;
+    for (size_t i = 0; i < aln.size(); i++) {
+        const DBEntry &e = aln.byKey(i);
+        const char *d = aln.data(e), *end = d + strnlen(d, e.length ? (size_t)e.length - 1 : 0);
+        while (d < end) {
+            const char *nl = (const char *)memchr(d, '\n', (size_t)(end - d));
+            const char *le = nl ? nl : end;
+            std::vector<std::string> f;
+            for (const char *c = d; c < le;) {
+                const char *t = (const char *)memchr(c, '\t', (size_t)(le - c));
+                f.emplace_back(c, (size_t)((t ? t : le) - c));
+                c = t ? t + 1 : le;
+            }
+            if (f.size() < 11 || f[10].empty()) throw Fail("This module only supports database input with backtrace string");
+            spb_aln a;
+            memset(&a, 0, sizeof(a));
+            a.query = (uint32_t)i;
+            const uint32_t tKey = (uint32_t)strtoul(f[0].c_str(), nullptr, 10);
+            const size_t tid = taa.findKey(tKey);
+            if (tid == SIZE_MAX) throw Fail("Invalid target database key " + f[0]);
+            a.target = (uint32_t)tid;
+            a.q_start = atoi(f[4].c_str()); a.q_end = atoi(f[5].c_str());
+            a.t_start = atoi(f[7].c_str()); a.t_end = atoi(f[8].c_str());
+            a.cigar_off = (uint32_t)ops.size();
+            for (const char *c = f[10].c_str(); *c;) {
+                unsigned cnt = 0;
+                while (isdigit((unsigned char)*c)) cnt = cnt * 10 + (unsigned)(*c++ - '0');
+                if (!*c) break;
+                if (*c == 'M' || *c == 'D' || *c == 'I') ops.append(cnt, *c);
+                c++;
+            }
+            a.cigar_len = (uint32_t)ops.size() - a.cigar_off;
+            rows.push_back(a);
+            d = nl ? nl + 1 : end;
+        }
+        rowOff[i + 1] = rows.size();
+    }
+    Engine E;
+    check(spb_ctx_create(p.device, &E.ctx), "spb_ctx_create");
+    check(spb_nucl_set_targets(E.ctx, TN.nt.data(), TN.off.data(), (uint32_t)tkeys.size(), TN.startCodon.data()), "spb_nucl_set_targets");
+    check(spb_nucl_set_queries(E.ctx, QN.nt.data(), QN.off.data(), (uint32_t)qkeys.size(), QN.startCodon.data()), "spb_nucl_set_queries");
+    spb_nucl_aln *nr = nullptr;
+    check(spb_nucl_rescore(E.ctx, &np, rows.data(), rows.size(), ops.data(), ops.size(), &nr), "spb_nucl_rescore");
+    DBWriter out;
+    out.open(p.db[5], DBTYPE_ALIGNMENT_RES, p.threads);
+    std::string buf;
+    for (size_t i = 0; i < aln.size(); i++) {
+        buf.clear();
+        for (uint64_t k = rowOff[i]; k < rowOff[i + 1]; k++) {
+            nucl_row_error(nr[k]);
+            append_nucl_row(buf, tkeys[rows[k].target], nr[k], ops.data() + rows[k].cigar_off, rows[k].cigar_len);
+        }
+        out.write((int)(i * (size_t)p.threads / (aln.size() ? aln.size() : 1)), qkeys[i], buf.data(), buf.size());
+    }
+    out.close();
+    spb_free_nucl_result(E.ctx, nr);
+    return 0;
+}
+
+// <protAlnDB> <nuclAlnDB> <outDB>   (CombineProtNuclAln.cpp:13-25)
+int run_combineprotnuclaln(int argc, const char **argv) {
+    Params p;
+    parse_args(argc, argv, 2, 3, p);
+    TextDB prot, nucl, out;
+    prot.load(p.db[0]);
+    nucl.load(p.db[1]);
+    combine_prot_nucl_aln(prot, nucl, p.threads, out);
+    out.save(p.db[2], p.threads);
+    return 0;
+}
+
 // both steps, hit lists stay in HBM (what blastp.sh does with a pref DB in between); sink(thread, query key, rows text)
+// nucl: the nucleotide re-alignment branch (predictmatch.sh:27-45) fused in -- after the alignment stage the resident rows are
+// re-scored on the resident <db>_nucl_orf entries (spb_nucl_rescore_resident) and combined like combineprotnuclaln; the sink
+// then receives the combined rows, and extra(thread, key, protein rows, nucleotide rows), if given, the two intermediates
+typedef std::function<void(int, uint32_t, const std::string &, const std::string &)> NuclExtraSink;
 template <class Sink>
-void search_dbs(const Params &p, const std::string &qName, const std::string &tName, Sink sink) {
+void search_dbs(const Params &p, const std::string &qName, const std::string &tName, Sink sink, bool nucl = false,
+                const NuclExtraSink *extra = nullptr) {
     Engine E;
     E.open(p);
     DBReader qdb, tdb;
@@ -530,6 +730,14 @@ void search_dbs(const Params &p, const std::string &qName, const std::string &tN
     SeqSet Q, T;
     load_sequences(qdb, E.seed, Q);
     load_sequences(tdb, E.seed, T);
+    NuclSet QN, TN;
+    spb_nucl_params np;
+    if (nucl) {
+        load_nucl(qName + "_nucl_orf", qdb, Q.keys, QN);
+        load_nucl(tName + "_nucl_orf", tdb, T.keys, TN);
+        fill_nucl_params(p, TN.dbSize, &np);
+        check(spb_nucl_set_targets(E.ctx, TN.nt.data(), TN.off.data(), (uint32_t)T.keys.size(), TN.startCodon.data()), "spb_nucl_set_targets");
+    }
     const int kmerThr = kmer_threshold(p.sensitivity, p.kmerScore, 6);
     if (!p.exhaustive) build_target_index(E, p, T, kmerThr);
     check(spb_align_set_targets(E.ctx, T.res.data(), T.off.data(), (uint32_t)T.keys.size(), T.keys.data()), "spb_align_set_targets");
@@ -559,9 +767,42 @@ void search_dbs(const Params &p, const std::string &qName, const std::string &tN
             check(spb_pairs_from_prefilter(E.ctx), "spb_pairs_from_prefilter");
         }
         check(spb_align_resident(E.ctx, &ap), "spb_align_resident");
+        spb_nucl_aln *nr = nullptr;
+        if (nucl) {
+            std::vector<uint64_t> noff(b1 - b0 + 1);
+            for (size_t i = b0; i <= b1; i++) noff[i - b0] = QN.off[i] - QN.off[b0];
+            check(spb_nucl_set_queries(E.ctx, QN.nt.data() + QN.off[b0], noff.data(), (uint32_t)(b1 - b0), QN.startCodon.data() + b0),
+                  "spb_nucl_set_queries");
+            uint64_t nRows = 0;
+            double ms = 0;
+            check(spb_nucl_rescore_resident(E.ctx, &np, &nr, &nRows, &ms), "spb_nucl_rescore_resident");
+            log_line(p, "Nucleotide re-alignment: %llu rows re-scored on the device in %.3f ms", (unsigned long long)nRows, ms);
+        }
         spb_align_result *r = nullptr;
         check(spb_align_fetch(E.ctx, &r), "spb_align_fetch");
-        format_alignment_rows(p, r, Q, b0, T, [&](int th, size_t i, const std::string &buf) { sink(th, Q.keys[b0 + i], buf); });
+        if (!nucl) {
+            format_alignment_rows(p, r, Q, b0, T, [&](int th, size_t i, const std::string &buf) { sink(th, Q.keys[b0 + i], buf); });
+        } else {
+            std::string err;
+            format_alignment_rows(p, r, Q, b0, T, [&](int th, size_t i, const std::string &prot) {
+                std::string nuc, comb;
+                try {
+                    for (uint64_t k = r->offsets[i]; k < r->offsets[i + 1]; k++) {
+                        const spb_aln &a = r->rows[k];
+                        nucl_row_error(nr[k]);
+                        append_nucl_row(nuc, T.keys[a.target], nr[k], r->cigar_ops + a.cigar_off, a.cigar_len);
+                    }
+                    combine_prot_nucl_entry(prot, nuc, comb);
+                } catch (const std::exception &e) {
+#pragma omp critical
+                    err = e.what();
+                }
+                if (extra) (*extra)(th, Q.keys[b0 + i], prot, nuc);
+                sink(th, Q.keys[b0 + i], comb);
+            });
+            spb_free_nucl_result(E.ctx, nr);
+            if (!err.empty()) { spb_free_align_result(r); throw Fail(err); }
+        }
         spb_free_align_result(r);
     }
 }
@@ -659,17 +900,16 @@ void set_predictmatch_defaults(Params &p) {
     p.simpleBestHit = 1;
 }
 
-// data/predictmatch.sh:47-116 without the nucleotide re-alignment branch: search + besthitperset + mergeresultsbyset +
-// combinescore against the target and the control setDB, then filtermatchbyfdr; intermediates stay in memory
+// data/predictmatch.sh:27-116: search (+ the nucleotide re-alignment branch unless --perform-nucl-aln 0: proteinaln2nucl on the
+// device, combineprotnuclaln) + besthitperset + mergeresultsbyset + combinescore against the target and the control setDB,
+// then filtermatchbyfdr; intermediates stay in memory
 int run_predictmatch(int argc, const char **argv) {
     Params p;
     set_predictmatch_defaults(p);
     parse_args(argc, argv, 2, 5, p);     // <querySetDB> <targetSetDB> <controlTargetSetDB> <matchDB> <tmpDir>
     check_search_params(p);
     check_align_params(p);
-    if (p.performNuclAln != 0)
-        throw Fail("predictmatch: the nucleotide re-alignment branch (proteinaln2nucl + combineprotnuclaln) is not part of spb200; "
-                   "pass --perform-nucl-aln 0");
+    const bool nucl = p.performNuclAln != 0;   // the reference's default (LocalParameters.h:176)
     KeyMap qsz;
     qsz.load(p.db[0] + "_set_size");
     TextDB qSets;
@@ -686,7 +926,20 @@ int run_predictmatch(int argc, const char **argv) {
         result.keys.resize(qdb.size());
         for (size_t i = 0; i < qdb.size(); i++) result.keys[i] = qdb.byKey(i).key;
         result.data.assign(result.keys.size(), std::string());
-        search_dbs(p, p.db[0], tName, [&](int, uint32_t key, const std::string &buf) { result.data[result.find(key)] = buf; });
+        TextDB protResult, nuclResult;
+        NuclExtraSink extra = [&](int, uint32_t key, const std::string &prot, const std::string &nuc) {
+            const size_t i = result.find(key);
+            protResult.data[i] = prot;
+            nuclResult.data[i] = nuc;
+        };
+        if (nucl && p.keepIntermediate) {
+            protResult.dbtype = nuclResult.dbtype = DBTYPE_ALIGNMENT_RES;
+            protResult.keys = nuclResult.keys = result.keys;
+            protResult.data.assign(result.keys.size(), std::string());
+            nuclResult.data.assign(result.keys.size(), std::string());
+        }
+        search_dbs(p, p.db[0], tName, [&](int, uint32_t key, const std::string &buf) { result.data[result.find(key)] = buf; }, nucl,
+                   nucl && p.keepIntermediate ? &extra : nullptr);
         KeyMap m2s, ssz;
         m2s.load(tName + "_member_to_set");
         ssz.load(tName + "_set_size");
@@ -695,6 +948,10 @@ int run_predictmatch(int argc, const char **argv) {
         merge_results_by_set(qSets, aggregate, p.threads, merged);
         combine_score(merged, m2s, qsz, p.threads, cScore[side]);
         if (p.keepIntermediate) {
+            if (nucl) {
+                protResult.save(p.db[4] + "/prot_result" + suffix, p.threads);
+                nuclResult.save(p.db[4] + "/nucl_result" + suffix, p.threads);
+            }
             result.save(p.db[4] + "/result" + suffix, p.threads);
             aggregate.save(p.db[4] + "/aggregate" + suffix, p.threads);
             merged.save(p.db[4] + "/aggregate_merged" + suffix, p.threads);
@@ -759,7 +1016,7 @@ int run_showparams(int argc, const char **argv) {
 
 int main(int argc, const char **argv) {
     if (argc < 2) {
-        fprintf(stderr, "spb200 (%s): prefilter | align | search | besthitperset | mergeresultsbyset | combinescore | filtermatchbyfdr | predictmatch | dumpmatrix | dbcopy | showparams\n", spb_version());
+        fprintf(stderr, "spb200 (%s): prefilter | align | search | besthitperset | mergeresultsbyset | combinescore | filtermatchbyfdr | predictmatch | proteinaln2nucl | combineprotnuclaln | dumpmatrix | dbcopy | showparams\n", spb_version());
         return 1;
     }
     const std::string cmd = argv[1];
@@ -772,6 +1029,8 @@ int main(int argc, const char **argv) {
         if (cmd == "combinescore") return run_combinescore(argc, argv);
         if (cmd == "filtermatchbyfdr") return run_filtermatchbyfdr(argc, argv);
         if (cmd == "predictmatch") return run_predictmatch(argc, argv);
+        if (cmd == "proteinaln2nucl") return run_proteinaln2nucl(argc, argv);
+        if (cmd == "combineprotnuclaln") return run_combineprotnuclaln(argc, argv);
         if (cmd == "dumpmatrix") return run_dumpmatrix(argc, argv);
         if (cmd == "dbcopy") return run_dbcopy(argc, argv);
         if (cmd == "showparams") return run_showparams(argc, argv);

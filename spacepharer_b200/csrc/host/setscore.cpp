@@ -78,6 +78,86 @@ static void append_e3(std::string &out, double v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// combineprotnuclaln (src/util/CombineProtNuclAln.cpp:55-95)
+// ---------------------------------------------------------------------------------------------------------
+// Util::getWordsOfLine (M/commons/Util.h:167-190): words separated by blanks / tabs up to the end of the line
+static size_t words_of_line(const char *d, const char *end, const char **w, size_t maxw) {
+    size_t n = 0;
+    while (d < end && *d != '\n' && n < maxw) {
+        while (d < end && (*d == ' ' || *d == '\t')) d++;
+        if (d >= end || *d == '\n') break;
+        w[n++] = d;
+        while (d < end && *d != ' ' && *d != '\t' && *d != '\n') d++;
+    }
+    return n;
+}
+
+void combine_prot_nucl_entry(const std::string &protEntry, const std::string &nuclEntry, std::string &out) {
+    out.clear();
+    const char *pd = protEntry.data(), *pend = pd + protEntry.size();
+    const char *nbeg = nuclEntry.data(), *nend = nbeg + nuclEntry.size();
+    const char *pw[16], *nw[16];
+    while (pd < pend) {
+        const char *nl = (const char *)memchr(pd, '\n', (size_t)(pend - pd));
+        const char *le = nl ? nl : pend;
+        if (words_of_line(pd, le, pw, 16) < 10) throw std::runtime_error("Invalid alignment result record");
+        const uint32_t target = fast_atou(pw[0]);
+        const double protEval = strtod(pw[3], nullptr);
+        double updatedEval = FLT_MAX, nuclSeqId = 0;
+        for (const char *nd = nbeg; nd < nend;) {
+            const char *nnl = (const char *)memchr(nd, '\n', (size_t)(nend - nd));
+            const char *nle = nnl ? nnl : nend;
+            if (fast_atou(nd) == target) {
+                if (words_of_line(nd, nle, nw, 16) < 10) throw std::runtime_error("Invalid alignment result record");
+                nuclSeqId = strtod(nw[2], nullptr);
+                const double nuclEval = strtod(nw[3], nullptr);
+                updatedEval = ((log(protEval) * 0.5 + log(nuclEval) * 0.5) < log(nuclEval)) ? exp(log(protEval) * 0.5 + log(nuclEval) * 0.5)
+                                                                                             : nuclEval;
+            }
+            nd = nnl ? nnl + 1 : nend;
+        }
+        out.append(pw[0], (size_t)(pw[2] - pw[0]));
+        append_e3(out, nuclSeqId);
+        out.push_back('\t');
+        append_e3(out, updatedEval);
+        out.push_back('\t');
+        out.append(pw[4], (size_t)(le - pw[4]));
+        out.push_back('\n');
+        pd = nl ? nl + 1 : pend;
+    }
+}
+
+void combine_prot_nucl_aln(const TextDB &prot, const TextDB &nucl, int threads, TextDB &out) {
+    out.dbtype = prot.dbtype;
+    std::vector<std::string> tmp(prot.keys.size());
+    std::vector<char> have(prot.keys.size(), 0);
+    std::string err;
+#pragma omp parallel for schedule(dynamic, 10) num_threads(threads > 0 ? threads : 1)
+    for (long i = 0; i < (long)prot.keys.size(); i++) {
+        const size_t j = nucl.find(prot.keys[(size_t)i]);
+        if (j == SIZE_MAX) continue;
+        try {
+            combine_prot_nucl_entry(prot.data[(size_t)i], nucl.data[j], tmp[(size_t)i]);
+        } catch (const std::exception &e) {
+#pragma omp critical
+            err = e.what();
+        }
+        have[(size_t)i] = 1;
+    }
+    if (!err.empty()) throw std::runtime_error(err);
+    out.keys.clear();
+    out.data.clear();
+    for (size_t i = 0; i < prot.keys.size(); i++) {
+        if (!have[i]) {
+            fprintf(stderr, "Missing nucleotide alignment result for key %u \n", prot.keys[i]);
+            continue;
+        }
+        out.keys.push_back(prot.keys[i]);
+        out.data.push_back(std::move(tmp[i]));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Aggregation (M/multihit/Aggregation.cpp:24-90): the lines of one query entry grouped by the SET of their target,
 // sets visited in ascending key order (std::map), lines of a set in entry order; columns split at tabs (Util::split =
 // strtok: empty columns vanish).

@@ -46,6 +46,20 @@ std::string multiparam_aa(const std::string &spec) {
     return fallback;
 }
 
+std::string multiparam_nucl(const std::string &spec) {
+    size_t start = 0;
+    std::string fallback;
+    while (start <= spec.size()) {
+        size_t comma = spec.find(',', start);
+        std::string part = spec.substr(start, comma == std::string::npos ? std::string::npos : comma - start);
+        if (part.compare(0, 5, "nucl:") == 0) return part.substr(5);
+        if (part.compare(0, 3, "aa:") != 0 && fallback.empty()) fallback = part;
+        if (comma == std::string::npos) break;
+        start = comma + 1;
+    }
+    return fallback;
+}
+
 void SubMat::load(const std::string &spec, double bitFactor, double scoreBias) {
     const std::string path = multiparam_aa(spec);
     if (path.empty()) throw std::runtime_error("no amino-acid substitution matrix in '" + spec + "'");

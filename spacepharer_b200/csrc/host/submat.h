@@ -31,5 +31,7 @@ struct SubMat {
 
 // "nucl:10,aa:16" / "16" -> amino-acid value
 std::string multiparam_aa(const std::string &spec);
+// ... -> nucleotide value
+std::string multiparam_nucl(const std::string &spec);
 
 }  // namespace spbhost

@@ -13,6 +13,7 @@ import struct
 import numpy as np
 
 DBTYPE_AMINO_ACIDS = 0
+DBTYPE_NUCLEOTIDES = 1
 DBTYPE_ALIGNMENT_RES = 5
 DBTYPE_PREFILTER_RES = 7
 

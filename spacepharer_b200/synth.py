@@ -106,11 +106,12 @@ def make_spacers(n_spacers, tres, toff, seed=None, planted=0.3, min_nt=25, max_n
     return nt, lens.astype(np.int64)
 
 
-def six_frame_fragments(nt, lens, min_aa=9):
+def six_frame_fragments(nt, lens, min_aa=9, return_loc=False):
     """Six-frame translation, split at stop codons, keep fragments >= min_aa.
 
     Returns (qres uint8, qoff uint64[Q+1], spacer_of_frame uint32[Q]).  Frame order per spacer:
-    forward frames 1,2,3 then reverse frames 1,2,3; fragments left to right (extractorfs order)."""
+    forward frames 1,2,3 then reverse frames 1,2,3; fragments left to right (extractorfs order).
+    return_loc: additionally int64[Q, 3] = (strand * 3 + frame, first codon, codons) of every fragment."""
     n, W = nt.shape
     comp = nt.copy()
     valid = comp != 255
@@ -132,7 +133,7 @@ def six_frame_fragments(nt, lens, min_aa=9):
             aa = np.where(full, _AA_OF_CODON[idx], 254)  # 255 = stop, 254 = beyond end
             out_chunks.append((strand * 3 + f, aa))
     # split every (spacer, frame) row at stops; done with run-length logic on a flattened view
-    order_res, order_off, order_sp, order_key = [], [], [], []
+    order_res, order_off, order_sp, order_key, order_loc = [], [], [], [], []
     for fidx, aa in out_chunks:
         n_, C_ = aa.shape
         is_res = aa < 21
@@ -146,6 +147,7 @@ def six_frame_fragments(nt, lens, min_aa=9):
         keep = flen >= min_aa
         srow, scol, flen = srow[keep], scol[keep], flen[keep]
         order_sp.append(srow)
+        order_loc.append(np.stack([np.full(len(srow), fidx, dtype=np.int64), scol.astype(np.int64), flen.astype(np.int64)], axis=1))
         order_key.append(srow.astype(np.int64) * 1000 + fidx * 100 + scol)
         order_res.append((aa, srow, scol, flen))
     sp = np.concatenate(order_sp) if order_sp else np.zeros(0, dtype=np.int64)
@@ -171,10 +173,44 @@ def six_frame_fragments(nt, lens, min_aa=9):
         src = aa[srow[:, None], np.minimum(scol[:, None] + cols, aa.shape[1] - 1)]
         qres[(dst0[:, None] + cols)[mask]] = src[mask].astype(np.uint8)
         base += m
+    if return_loc:
+        loc = np.concatenate(order_loc) if order_loc else np.zeros((0, 3), dtype=np.int64)
+        return qres, qoff, sp[perm].astype(np.uint32), loc[perm]
     return qres, qoff, sp[perm].astype(np.uint32)
 
 
-def make_spacer_arrays(n_arrays, tres, toff, set_of, seed=7, min_spacers=2, max_spacers=25, hit_arrays=0.4, planted=0.5, **kw):
+_NT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def fragment_nucleotides(nt, lens, sp, loc):
+    """ASCII nucleotides of every fragment of six_frame_fragments(..., return_loc=True): the codons the fragment was
+    translated from, on its strand (what <db>_nucl_orf holds next to <db>, data/createsetdb.sh:88-113)."""
+    out = []
+    for q in range(len(sp)):
+        row, (fidx, scol, flen) = int(sp[q]), (int(x) for x in loc[q])
+        L = int(lens[row])
+        a = nt[row, :L]
+        if fidx >= 3:
+            a = (3 - a)[::-1]
+        f = fidx % 3
+        out.append(_NT[a[f + 3 * scol:f + 3 * (scol + flen)]].tobytes())
+    return out
+
+
+def back_translate(res, off, reverse_codons=False):
+    """ASCII coding sequence of every ORF under the fixed codon table (_CODON_OF_AA); reverse_codons: codon order
+    reversed, every codon intact (reverseseqbycodon, src/util/ReverseSeqByCodon.cpp:40-53 -- translates to the reversed ORF)."""
+    cod = _CODON_OF_AA[np.asarray(res)]
+    bases = _NT[np.stack([cod // 16, (cod // 4) % 4, cod % 4], axis=1)]
+    out = []
+    for i in range(len(off) - 1):
+        b = bases[int(off[i]):int(off[i + 1])]
+        out.append((b[::-1] if reverse_codons else b).tobytes())
+    return out
+
+
+def make_spacer_arrays(n_arrays, tres, toff, set_of, seed=7, min_spacers=2, max_spacers=25, hit_arrays=0.4, planted=0.5,
+                       return_nucl=False, **kw):
     """CRISPR arrays (query SETS): array a holds U{min..max} spacers; a fraction hit_arrays of the arrays targets one random
     genome (their planted spacers copy ORFs of it).  Returns (qres, qoff, set_of_frame uint32[Q], n_arrays): the frames of
     all spacers (six-frame, as make_query_frames) with the array every frame belongs to."""
@@ -184,11 +220,14 @@ def make_spacer_arrays(n_arrays, tres, toff, set_of, seed=7, min_spacers=2, max_
     G = int(set_of[-1]) + 1 if len(set_of) else 0
     genome = np.where(rng.random(n_arrays) < hit_arrays, rng.integers(0, max(G, 1), size=n_arrays), -1)
     nt, lens = make_spacers(int(n_sp.sum()), tres, toff, seed=seed + 1, planted=planted, genome_of=genome[array_of], set_of=set_of, **kw)
+    if return_nucl:
+        qres, qoff, sp, loc = six_frame_fragments(nt, lens, return_loc=True)
+        return qres, qoff, array_of[sp].astype(np.uint32), n_arrays, fragment_nucleotides(nt, lens, sp, loc)
     qres, qoff, sp = six_frame_fragments(nt, lens)
     return qres, qoff, array_of[sp].astype(np.uint32), n_arrays
 
 
-def write_array_search_dbs(work, n_genomes=150, target_seed=20180901, n_arrays=140, array_seed=11):
+def write_array_search_dbs(work, n_genomes=150, target_seed=20180901, n_arrays=140, array_seed=11, nucl=False):
     """BASELINE config 3 at a chosen scale as MMseqs2 set DBs under `work`: `targets` (phage ORF setDB), `targets_rev`
     (reversed-ORF control setDB) and `qsetdb` (frames of synthetic CRISPR arrays), each with its _member_to_set /
     _set_to_member / _set_size files.  Returns the SHA-256 over the generated arrays (pinned next to the golden outputs)."""
@@ -197,7 +236,11 @@ def write_array_search_dbs(work, n_genomes=150, target_seed=20180901, n_arrays=1
     from . import dbio
     tres, toff, set_of = make_targets(n_genomes=n_genomes, seed=target_seed)
     rres = reverse_targets(tres, toff)
-    qres, qoff, qset, _ = make_spacer_arrays(n_arrays, tres, toff, set_of, seed=array_seed)
+    qres, qoff, qset, _, qnt = make_spacer_arrays(n_arrays, tres, toff, set_of, seed=array_seed, return_nucl=True)
+    if nucl:
+        # the nucleotide ORF DBs of the --perform-nucl-aln 1 branch (same keys as the amino-acid DBs)
+        for name, seqs in (("targets", back_translate(tres, toff)), ("targets_rev", back_translate(rres, toff)), ("qsetdb", qnt)):
+            dbio.write_db(os.path.join(work, name + "_nucl_orf"), ((i, s + b"\n") for i, s in enumerate(seqs)), dbio.DBTYPE_NUCLEOTIDES)
     dbio.write_set_db(os.path.join(work, "targets"), tres, toff, set_of)
     dbio.write_set_db(os.path.join(work, "targets_rev"), rres, toff, set_of)
     dbio.write_set_db(os.path.join(work, "qsetdb"), qres, qoff, qset)

@@ -69,10 +69,11 @@ def test_predictmatch_reference_example(tmp_path):
                  ("cScore_rev", "sets_cScore_rev"), ("match", "sets_match")):
         assert {k: v for k, v in entries_as_rows(out + "/" + n).items() if v} == read_dump(os.path.join(C1, g + ".txt.gz")), n
     assert "Combined score list too short" in r.stdout
-    # the default (nucleotide re-alignment on) is refused, not silently skipped
+    # the default (nucleotide re-alignment on, tests/test_nuclaln.py) needs the <db>_nucl_orf DBs: without them (only their
+    # gzipped data files live in this directory) it fails loudly instead of silently skipping the branch
     r = subprocess.run([BIN, "predictmatch", os.path.join(C1, "qsetdb"), os.path.join(C1, "targets"), os.path.join(C1, "targets_rev"),
                         out + "/m2", out], capture_output=True, text=True)
-    assert r.returncode == 1 and "--perform-nucl-aln 0" in r.stderr
+    assert r.returncode == 1 and "_nucl_orf" in r.stderr
 
 
 def test_predictmatch_synthetic_arrays(tmp_path):
