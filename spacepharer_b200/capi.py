@@ -81,6 +81,7 @@ SYMBOLS = [
     "spb_prefilter_fetch", "spb_pairs_set", "spb_pairs_from_prefilter", "spb_align_resident", "spb_align_stats",
     "spb_align_fetch", "spb_prefilter_device_result", "spb_prefilter_device_trunc_keys", "spb_prefilter_merge_shards",
     "spb_pairs_exhaustive", "spb_align_exhaustive", "spb_spacer_frames", "spb_free_frames_result",
+    "spb_nucl_set_targets", "spb_nucl_set_queries", "spb_nucl_rescore", "spb_nucl_rescore_resident", "spb_free_nucl_result",
 ]
 
 _lib = None
