@@ -7,6 +7,8 @@
 //   spb200 prefilter <queryDB> <targetDB> <prefilterDB> [flags]     Prefiltering (M/prefiltering/Prefiltering.cpp)
 //   spb200 align     <queryDB> <targetDB> <prefilterDB> <alnDB> [flags]   Alignment (M/alignment/Alignment.cpp)
 //   spb200 search    <queryDB> <targetDB> <alnDB> [flags]           both steps with the hit lists kept in HBM
+//   spb200 createindex <targetDB> <tmpDir> [flags]                  writes <targetDB>.spbidx (tantan-masked residues; the k-mer
+//                                                                   table itself is rebuilt on the device), picked up by the above
 // and the set-level stages that consume the alignment DB in predictmatch (data/predictmatch.sh:57-116; setscore.h):
 //   spb200 besthitperset <querySetDB> <targetSetDB> <alnDB> <outDB> [--simple-best-hit 1]
 //   spb200 mergeresultsbyset <querySetDB>_set_to_member <resultDB> <outDB>
@@ -313,19 +315,87 @@ void log_line(const Params &p, const char *fmt, ...) {
 // ---------------------------------------------------------------------------------------------------------
 // prefilter
 // ---------------------------------------------------------------------------------------------------------
-void build_target_index(Engine &E, const Params &p, const SeqSet &T, int kmerThr) {
-    std::vector<uint8_t> masked(T.res.begin(), T.res.end());
-    uint64_t nMasked = 0;
+// ---- persistent index (the reference: createindex -> <targetDB>.idx, PrefilteringIndexReader.cpp) ----
+// The reference serialises the whole k-mer table because building it costs CPU-seconds.  Here the table is rebuilt on the device
+// in ~20 ms (index.cu) -- faster than reading 1.7 GB back -- so the cache holds what is expensive on the HOST side: the
+// tantan-masked residues (SEQINDEXDATA of the reference's index) plus the parameters they depend on.  Layout of
+// <targetDB>.spbidx: IdxHeader, keys u32[T], offsets u64[T+1], masked residues u8[N].
+struct IdxHeader {
+    char magic[8];            // "SPBIDX1"
+    uint32_t version, mask, maskLower, pad;
+    uint64_t nTargets, nResidues, srcDataSize, checksum;   // checksum: FNV-1a over keys, offsets and the UNMASKED residues
+    char seedMatrix[64];
+};
+
+uint64_t fnv1a(const void *d, size_t n, uint64_t h) {
+    const unsigned char *p = (const unsigned char *)d;
+    for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ULL; }
+    return h;
+}
+
+uint64_t seqset_checksum(const SeqSet &T) {
+    uint64_t h = 1469598103934665603ULL;
+    h = fnv1a(T.keys.data(), T.keys.size() * 4, h);
+    h = fnv1a(T.off.data(), T.off.size() * 8, h);
+    return fnv1a(T.res.data(), (size_t)T.off.back(), h);
+}
+
+void fill_idx_header(const Params &p, const Engine &E, const SeqSet &T, uint64_t srcDataSize, IdxHeader *h) {
+    memset(h, 0, sizeof(*h));
+    memcpy(h->magic, "SPBIDX1", 8);
+    h->version = 1;
+    h->mask = (uint32_t)p.mask;
+    h->maskLower = (uint32_t)p.maskLower;
+    h->nTargets = T.keys.size();
+    h->nResidues = T.off.back();
+    h->srcDataSize = srcDataSize;
+    h->checksum = seqset_checksum(T);
+    snprintf(h->seedMatrix, sizeof(h->seedMatrix), "%s", E.seed.name.c_str());
+}
+
+void mask_targets(Engine &E, const Params &p, const SeqSet &T, std::vector<uint8_t> &masked, uint64_t *nMasked) {
+    masked.assign(T.res.begin(), T.res.end());
+    *nMasked = 0;
     if (p.mask)   // IndexBuilder.cpp:137-149
-        check(spb_tantan_mask(E.seed.prob, E.seed.pback, masked.data(), T.off.data(), (uint32_t)T.keys.size(), p.threads, &nMasked), "spb_tantan_mask");
+        check(spb_tantan_mask(E.seed.prob, E.seed.pback, masked.data(), T.off.data(), (uint32_t)T.keys.size(), p.threads, nMasked), "spb_tantan_mask");
+}
+
+// true if <name>.spbidx exists and belongs to exactly this target set and these masking parameters
+bool load_index_cache(const std::string &name, const Params &p, const Engine &E, const SeqSet &T, uint64_t srcDataSize,
+                      std::vector<uint8_t> &masked) {
+    FILE *f = fopen((name + ".spbidx").c_str(), "rb");
+    if (!f) return false;
+    IdxHeader want, got;
+    fill_idx_header(p, E, T, srcDataSize, &want);
+    bool ok = fread(&got, sizeof(got), 1, f) == 1 && memcmp(&got, &want, sizeof(got)) == 0;
+    if (ok) {
+        ok = fseek(f, (long)(sizeof(got) + T.keys.size() * 4 + T.off.size() * 8), SEEK_SET) == 0;
+        masked.resize(T.res.size());
+        ok = ok && fread(masked.data(), 1, (size_t)want.nResidues, f) == (size_t)want.nResidues;
+    }
+    fclose(f);
+    if (!ok) log_line(p, "Index cache %s.spbidx does not match this database / these parameters: ignored", name.c_str());
+    return ok;
+}
+
+void build_target_index(Engine &E, const Params &p, const SeqSet &T, int kmerThr, const std::string &tName = std::string(),
+                        uint64_t srcDataSize = 0) {
+    std::vector<uint8_t> masked;
+    uint64_t nMasked = 0;
+    const bool cached = !tName.empty() && load_index_cache(tName, p, E, T, srcDataSize, masked);
+    if (!cached) mask_targets(E, p, T, masked, &nMasked);
     const std::string pattern = p.spacedPattern.empty() ? (p.spacedMode ? "11011101" : "111111") : p.spacedPattern;
     // index-side threshold (Prefiltering.cpp:510-513): only for exact matching or when the k-mer threshold is small enough
     check(spb_index_build(E.ctx, masked.data(), T.off.data(), (uint32_t)T.keys.size(), pattern.c_str(), kmerThr), "spb_index_build");
     spb_index_stats st;
     check(spb_index_stats_get(E.ctx, &st), "spb_index_stats_get");
-    log_line(p, "Index table: %llu targets, %llu residues (%llu masked), %llu postings, %.1f ms on the device",
-             (unsigned long long)st.n_targets, (unsigned long long)st.n_residues, (unsigned long long)nMasked,
-             (unsigned long long)st.n_postings, st.build_ms);
+    if (cached)
+        log_line(p, "Index table: %llu targets, %llu residues (masked residues from %s.spbidx), %llu postings, %.1f ms on the device",
+                 (unsigned long long)st.n_targets, (unsigned long long)st.n_residues, tName.c_str(), (unsigned long long)st.n_postings, st.build_ms);
+    else
+        log_line(p, "Index table: %llu targets, %llu residues (%llu masked), %llu postings, %.1f ms on the device",
+                 (unsigned long long)st.n_targets, (unsigned long long)st.n_residues, (unsigned long long)nMasked,
+                 (unsigned long long)st.n_postings, st.build_ms);
 }
 
 void check_search_params(const Params &p) {
@@ -352,7 +422,7 @@ int run_prefilter(int argc, const char **argv) {
     load_sequences(tdb, E.seed, T);
     const int kmerThr = kmer_threshold(p.sensitivity, p.kmerScore, 6);
     log_line(p, "k-mer similarity threshold: %d", kmerThr);
-    build_target_index(E, p, T, kmerThr);
+    build_target_index(E, p, T, kmerThr, p.db[1], tdb.dataSize());
 
     spb_prefilter_params pp;
     pp.kmer_thr = kmerThr;
@@ -739,7 +809,7 @@ void search_dbs(const Params &p, const std::string &qName, const std::string &tN
         check(spb_nucl_set_targets(E.ctx, TN.nt.data(), TN.off.data(), (uint32_t)T.keys.size(), TN.startCodon.data()), "spb_nucl_set_targets");
     }
     const int kmerThr = kmer_threshold(p.sensitivity, p.kmerScore, 6);
-    if (!p.exhaustive) build_target_index(E, p, T, kmerThr);
+    if (!p.exhaustive) build_target_index(E, p, T, kmerThr, tName, tdb.dataSize());
     check(spb_align_set_targets(E.ctx, T.res.data(), T.off.data(), (uint32_t)T.keys.size(), T.keys.data()), "spb_align_set_targets");
     spb_prefilter_params pp;
     pp.kmer_thr = kmerThr;
@@ -805,6 +875,34 @@ void search_dbs(const Params &p, const std::string &qName, const std::string &tN
         }
         spb_free_align_result(r);
     }
+}
+
+// spb200 createindex <targetDB> <tmpDir> [prefilter flags]   (M/workflow/CreateIndex.cpp; host-only: no GPU needed)
+int run_createindex(int argc, const char **argv) {
+    Params p;
+    set_predictmatch_defaults(p);
+    parse_args(argc, argv, 2, 2, p);
+    Engine E;
+    E.seed.load(p.seedSubMat, 8.0, -0.2);
+    DBReader tdb;
+    tdb.open(p.db[0]);
+    SeqSet T;
+    load_sequences(tdb, E.seed, T);
+    std::vector<uint8_t> masked;
+    uint64_t nMasked = 0;
+    mask_targets(E, p, T, masked, &nMasked);
+    IdxHeader h;
+    fill_idx_header(p, E, T, tdb.dataSize(), &h);
+    const std::string tmp = p.db[0] + ".spbidx.tmp";
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) throw Fail("Could not open " + tmp + " for writing");
+    bool ok = fwrite(&h, sizeof(h), 1, f) == 1 && fwrite(T.keys.data(), 4, T.keys.size(), f) == T.keys.size() &&
+              fwrite(T.off.data(), 8, T.off.size(), f) == T.off.size() && fwrite(masked.data(), 1, (size_t)h.nResidues, f) == (size_t)h.nResidues;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), (p.db[0] + ".spbidx").c_str()) != 0) throw Fail("Could not write " + p.db[0] + ".spbidx");
+    log_line(p, "Index cache %s.spbidx: %llu targets, %llu residues, %llu masked", p.db[0].c_str(), (unsigned long long)h.nTargets,
+             (unsigned long long)h.nResidues, (unsigned long long)nMasked);
+    return 0;
 }
 
 int run_search(int argc, const char **argv) {
@@ -1016,7 +1114,7 @@ int run_showparams(int argc, const char **argv) {
 
 int main(int argc, const char **argv) {
     if (argc < 2) {
-        fprintf(stderr, "spb200 (%s): prefilter | align | search | besthitperset | mergeresultsbyset | combinescore | filtermatchbyfdr | predictmatch | proteinaln2nucl | combineprotnuclaln | dumpmatrix | dbcopy | showparams\n", spb_version());
+        fprintf(stderr, "spb200 (%s): prefilter | align | search | createindex | besthitperset | mergeresultsbyset | combinescore | filtermatchbyfdr | predictmatch | proteinaln2nucl | combineprotnuclaln | dumpmatrix | dbcopy | showparams\n", spb_version());
         return 1;
     }
     const std::string cmd = argv[1];
@@ -1024,6 +1122,7 @@ int main(int argc, const char **argv) {
         if (cmd == "prefilter") return run_prefilter(argc, argv);
         if (cmd == "align") return run_align(argc, argv);
         if (cmd == "search") return run_search(argc, argv);
+        if (cmd == "createindex") return run_createindex(argc, argv);
         if (cmd == "besthitperset") return run_besthitperset(argc, argv);
         if (cmd == "mergeresultsbyset") return run_mergeresultsbyset(argc, argv);
         if (cmd == "combinescore") return run_combinescore(argc, argv);

@@ -113,3 +113,21 @@ def test_search_exhaustive_contains_the_prefiltered_rows(tmp_path):
         assert [x for x in got[k] if x.split("\t")[0] in tk] == rows, k
         more += len(got[k]) - len(rows)
     assert more > 0
+
+
+def test_createindex_cache_is_used_and_validated(tmp_path):
+    """<targetDB>.spbidx written by `spb200 createindex` replaces the tantan pre-step of prefilter / search with identical
+    results; a cache written for other masking parameters is ignored"""
+    import shutil
+    for f in os.listdir(C1):
+        if f.startswith("targets") and "_" not in f:
+            shutil.copyfile(os.path.join(C1, f), str(tmp_path / f))
+    db, pref = str(tmp_path / "targets"), str(tmp_path / "pref")
+    run("createindex", db, str(tmp_path / "tmp"), "--threads", "2")
+    r = run("prefilter", os.path.join(C1, "qsetdb"), db, pref, *PREF_FLAGS)
+    assert "masked residues from" in r.stdout
+    assert dbio.read_entries(pref) == dbio.read_entries(os.path.join(C1, "pref_0"))
+    run("createindex", db, str(tmp_path / "tmp"), "--mask", "0")
+    r = run("prefilter", os.path.join(C1, "qsetdb"), db, pref + "2", *PREF_FLAGS)
+    assert "ignored" in r.stdout and "masked residues from" not in r.stdout
+    assert dbio.read_entries(pref + "2") == dbio.read_entries(os.path.join(C1, "pref_0"))

@@ -99,3 +99,31 @@ def test_no_cpu_fallback(tmp_path):
             str(tmp_path / "pref"), *PREF_FLAGS, ok=False)
     assert r.returncode == 1 and "no CPU fallback" in r.stderr
     assert not os.path.exists(str(tmp_path / "pref.dbtype"))
+
+
+def test_createindex_writes_the_masked_residue_cache(tmp_path):
+    """spb200 createindex is host-only: <targetDB>.spbidx holds the tantan-masked residues the index build
+    consumes -- the same masking as the oracle's restatement of tantan (IndexBuilder.cpp:137-149)"""
+    import shutil
+    import struct
+    c1 = os.path.join(GOLDEN, "config1")
+    for f in os.listdir(c1):
+        if f.startswith("targets") and "_" not in f:
+            shutil.copyfile(os.path.join(c1, f), str(tmp_path / f))
+    db = str(tmp_path / "targets")
+    r = run("createindex", db, str(tmp_path / "tmp"), "--threads", "2")
+    assert "866 masked" in r.stdout
+    raw = open(db + ".spbidx", "rb").read()
+    assert raw[:7] == b"SPBIDX1"
+    version, mask, mask_lower, _ = struct.unpack_from("<4I", raw, 8)
+    T, N, src, _ = struct.unpack_from("<4Q", raw, 24)
+    assert (version, mask, mask_lower) == (1, 1, 0) and src == os.path.getsize(db)
+    assert raw[56:66] == b"VTML80.out"
+    keys, seqs = dbio.read_sequence_db(db)
+    assert T == len(keys) and N == sum(len(s) for s in seqs)
+    m80, _, _ = Cm.mats()
+    masked = np.frombuffer(raw, dtype=np.uint8, count=N, offset=56 + 64 + 4 * T + 8 * (T + 1))
+    # entries are stored in data-offset order (the prefilter's target ids)
+    order = np.argsort(dbio.read_db(db)[1], kind="stable")
+    want = np.concatenate([O.tantan_mask(m80, O.encode(seqs[i], m80))[0] for i in order])
+    assert (masked == want).all() and int((want == 20).sum()) >= 866
