@@ -2,7 +2,8 @@
 NVCC      ?= /usr/local/cuda/bin/nvcc
 CXX       := $(shell test -x /usr/bin/g++ && echo /usr/bin/g++ || echo g++)
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-fopenmp --expt-extended-lambda -ccbin $(CXX)
+PHASEFLAG := $(if $(PHASE),-DSPB_PHASE_TIMING,)
+NVFLAGS   := $(PHASEFLAG) $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-fopenmp --expt-extended-lambda -ccbin $(CXX)
 CSRC      := spacepharer_b200/csrc
 LIBDIR    := spacepharer_b200/lib
 CU        := $(CSRC)/capi.cu $(CSRC)/index.cu $(CSRC)/prefilter.cu $(CSRC)/align.cu $(CSRC)/frames.cu $(CSRC)/nuclaln.cu

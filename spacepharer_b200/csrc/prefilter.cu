@@ -781,6 +781,13 @@ __device__ __forceinline__ void block_bitonic_pairs(uint64_t *k, uint64_t *v, in
     __syncthreads();
 }
 
+// per-phase warp-cycle counters (development builds only: make PHASE=1; read back with SPB_DEBUG)
+#ifdef SPB_PHASE_TIMING
+#define PH_MARK(i) do { const long long _t = clock64(); phase[i] += _t - phT; phT = _t; } while (0)
+#else
+#define PH_MARK(i) do { } while (0)
+#endif
+
 template <int TEAM>
 __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 ? 8 : 4) prefilter_team_kernel(PrefArgs A) {
     constexpr bool SOLO = (TEAM == 1);
@@ -808,8 +815,12 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
     uint64_t *finList = scratch + 2 * (size_t)A.hitCap;
     const uint32_t HCAP = A.hitCap;
     unsigned long long statK = 0, statM = 0, statE = 0, statS = 0;
+#ifdef SPB_PHASE_TIMING
+    long long phase[6] = {0, 0, 0, 0, 0, 0}, phT = clock64();
+#endif
 
     for (;;) {
+        PH_MARK(5);
         // ---------------- next query ----------------
         if (tw == 0 && lane == 0) S.v_qi = atomicAdd(A.qCounter, 1u);
         team_sync();
@@ -949,6 +960,7 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
             if (lane == 0) { S.v_K = K; S.v_nRuns = (uint32_t)nRuns; S.v_slow = why; S.v_why = reason; S.v_minCorr = minCorr; }
         }
         team_sync();
+        PH_MARK(0);
         const uint32_t K = S.v_K;
         const int nRuns = (int)S.v_nRuns;
         // ---------------- one pass over the hit stream ----------------
@@ -1034,7 +1046,9 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                         }
                     }
                 }
-                // posting lists of the k-mers in three or more targets, flattened over the warp
+                // posting lists of the k-mers in three or more targets, flattened over the warp.  (Deferring them to a per-warp
+                // queue drained in bulk was measured in round 1h: no gain in the lookup phase, and the extra shared memory
+                // of the TEAM = 1 launch cost more than it saved.)
 #pragma unroll
                 for (int u = 0; u < PW_U; u++) {
                     const uint32_t len = (d[u].x >> 63) ? 0u : (uint32_t)(d[u].x >> 32);
@@ -1045,6 +1059,7 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
             }
         }
         team_sync();
+        PH_MARK(1);
         const uint32_t nHits = S.v_nHits;
         const bool live = (S.v_slow == ST_OK) && nHits <= HCAP;
         team_sync();
@@ -1131,6 +1146,7 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
             }
         }
         team_sync();
+        PH_MARK(2);
         const int minCorr = S.v_minCorr;
         const int ungBias = abs(A.minSubUngapped) + abs(min(minCorr, 0));
         const int capScore = 255 - ungBias;
@@ -1224,6 +1240,7 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
             }
         }
         team_sync();
+        PH_MARK(3);
         // ---------------- final order (score desc, id asc), output ----------------
         if (SOLO) {
             const uint32_t nc = S.v_nFin;
@@ -1382,7 +1399,12 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
         if (tw == 0 && lane == 0) S.v_slow = (A.status[qi] == ST_OK) ? ST_OK : ST_CAPACITY;
         team_sync();
         if (S.v_slow == ST_OK) statE += evAcc;     // events of the groups this warp processed
+        PH_MARK(4);
     }
+#ifdef SPB_PHASE_TIMING
+    if (lane == 0)
+        for (int i = 0; i < 6; i++) atomicAdd(A.cursor + (SOLO ? 40 : 48) + i, (unsigned long long)phase[i]);
+#endif
     // counters of the queries finished on this path (the others are counted by the kernel that finishes them)
     if (lane == 0) {
         if (statK) atomicAdd(A.cursor + 1, statK);
@@ -1730,8 +1752,10 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
         // the list length from device memory -- no host round trip in between.
         const int soloBlocks = c->n_sm * 8, teamBlocks = c->n_sm * 4;
         A.direct = c->d_direct.as<ulonglong2>();
-        const uint32_t hitCapSolo = 8192, hitCapTeam = 32768;
+        uint32_t hitCapSolo = 8192, hitCapTeam = 32768;
         A.kCapSolo = 4096;
+        if (const char *e = getenv("SPB_KCAP_SOLO")) A.kCapSolo = (uint32_t)atoi(e);        // tuning aids (tools/perf_probe.py)
+        if (const char *e = getenv("SPB_HITCAP_SOLO")) hitCapSolo = (uint32_t)atoi(e);
         const size_t sliceSolo = 2 * (size_t)hitCapSolo + 2 * PW_FCAP_SOLO, sliceTeam = 2 * (size_t)hitCapTeam + 2 * PW_FCAP_TEAM;
         if (c->s_j.ensure(std::max((size_t)soloBlocks * PW_WARPS * sliceSolo, (size_t)teamBlocks * sliceTeam) * sizeof(uint64_t)) ||
             c->s_k.ensure((size_t)Q * 4 + 64)) return 1;
@@ -1764,6 +1788,19 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
         float ms = 0;
         SPB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         kernelMs += ms;
+#ifdef SPB_PHASE_TIMING
+        if (getenv("SPB_DEBUG")) {
+            unsigned long long ph[16];
+            cudaMemcpy(ph, c->s_f.as<unsigned long long>() + 40, sizeof(ph), cudaMemcpyDeviceToHost);
+            for (int t = 0; t < 2; t++) {
+                double tot = 0;
+                for (int i = 0; i < 6; i++) tot += (double)ph[8 * t + i];
+                fprintf(stderr, "phase cycles TEAM=%d: setup %.1f%% lookup %.1f%% survivors %.1f%% groups %.1f%% final %.1f%% idle/sched %.1f%% (total %.3g warp-cycles)\n",
+                        t ? 8 : 1, 100 * ph[8 * t] / tot, 100 * ph[8 * t + 1] / tot, 100 * ph[8 * t + 2] / tot, 100 * ph[8 * t + 3] / tot,
+                        100 * ph[8 * t + 4] / tot, 100 * ph[8 * t + 5] / tot, tot);
+            }
+        }
+#endif
         SPB_CHECK(h_ctr[3] == 0, "spb_prefilter: query %u is longer than the supported %d residues", h_ctr[3] - 1, PF_MAXL);
         SPB_CHECK(h_ctr[4] == 0, "spb_prefilter: query %u was not processed", h_ctr[4] - 1);
         bool arenaOverflow = h_ctr[2] != 0;
