@@ -760,6 +760,40 @@ __device__ __noinline__ void pw_walk(uint32_t len, uint32_t off, uint32_t w, uin
     }
 }
 
+// the same for the PW_U = 2 consecutive k-mers a lane owns in one lookup iteration: both lists of a lane are concatenated
+// (k-mer 2 * lane first), so one scan and one pass serve the 64 k-mers of the iteration instead of two of each
+__device__ __noinline__ void pw_walk2(uint32_t len0, uint32_t off0, uint32_t len1, uint32_t off1, uint32_t wPack, uint32_t k0,
+                                      const uint64_t *__restrict__ post, uint32_t *nHitsCtr, uint64_t *scratch, uint32_t HCAP,
+                                      uint32_t *seen1, uint32_t *seen2, int hashShift) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t lenS = len0 + len1;
+    const uint32_t inc = (uint32_t)warp_incl_scan_ool((int)lenS);
+    const uint32_t excl = inc - lenS;
+    const uint32_t T = __shfl_sync(0xffffffffu, inc, 31);
+#pragma unroll 1
+    for (uint32_t p0 = 0; p0 < T; p0 += 32) {
+        const uint32_t pp = p0 + lane;
+        int j = 0;
+#pragma unroll 1
+        for (int step = 16; step > 0; step >>= 1) {
+            const int cand = j + step;
+            const uint32_t e = __shfl_sync(0xffffffffu, excl, cand & 31);
+            if (cand < 32 && e <= pp) j = cand;
+        }
+        const uint32_t rel = pp - __shfl_sync(0xffffffffu, excl, j);
+        const uint32_t sL0 = __shfl_sync(0xffffffffu, len0, j);
+        const uint32_t sO0 = __shfl_sync(0xffffffffu, off0, j);
+        const uint32_t sO1 = __shfl_sync(0xffffffffu, off1, j);
+        const uint32_t sW = __shfl_sync(0xffffffffu, wPack, j);
+        const bool second = rel >= sL0;
+        const bool have = pp < T;
+        uint64_t pe = 0;
+        if (have) pe = __ldg(post + (second ? sO1 + (rel - sL0) : sO0 + rel));
+        pw_emit(have, pe, k0 + 2u * (uint32_t)j + (second ? 1u : 0u), (sW >> (second ? 8 : 0)) & 0xFFu, nHitsCtr, scratch, HCAP, seen1, seen2,
+                hashShift);
+    }
+}
+
 // CTA-wide bitonic sort of (key, payload) pairs by key (ascending); n_pow2 entries, padded by the caller
 __device__ __forceinline__ void block_bitonic_pairs(uint64_t *k, uint64_t *v, int n_pow2) {
     for (int kk = 2; kk <= n_pow2; kk <<= 1) {
@@ -1049,12 +1083,13 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                 // posting lists of the k-mers in three or more targets, flattened over the warp.  (Deferring them to a per-warp
                 // queue drained in bulk was measured in round 1h: no gain in the lookup phase, and the extra shared memory
                 // of the TEAM = 1 launch cost more than it saved.)
-#pragma unroll
-                for (int u = 0; u < PW_U; u++) {
-                    const uint32_t len = (d[u].x >> 63) ? 0u : (uint32_t)(d[u].x >> 32);
-                    if (__any_sync(0xffffffffu, len != 0u))
-                        pw_walk(len, (uint32_t)d[u].x, (wPack >> (8 * u)) & 0xFFu, k0 + (uint32_t)u, PW_U, A.post, &S.v_nHits, scratch, HCAP,
-                                S.seen1, S.seen2, HSH);
+                static_assert(PW_U == 2, "pw_walk2 serves exactly two k-mers per lane");
+                {
+                    const uint32_t len0 = (d[0].x >> 63) ? 0u : (uint32_t)(d[0].x >> 32);
+                    const uint32_t len1 = (d[1].x >> 63) ? 0u : (uint32_t)(d[1].x >> 32);
+                    if (__any_sync(0xffffffffu, (len0 | len1) != 0u))
+                        pw_walk2(len0, (uint32_t)d[0].x, len1, (uint32_t)d[1].x, wPack, k0, A.post, &S.v_nHits, scratch, HCAP, S.seen1,
+                                 S.seen2, HSH);
                 }
             }
         }
