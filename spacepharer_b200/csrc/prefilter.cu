@@ -687,6 +687,24 @@ struct WorkSmem {
 
 __device__ __noinline__ void warp_bitonic_u64(uint64_t *a, int n_pow2) {
     const int lane = threadIdx.x & 31;
+    if (n_pow2 <= 32) {
+        // up to one element per lane (the common case: a spacer frame has ~11 winners and a few dozen survivor records):
+        // the whole network runs in registers over shuffles -- no shared-memory round trips, no barriers between stages
+        __syncwarp();
+        uint64_t v = (lane < n_pow2) ? a[lane] : ~0ull;
+#pragma unroll 1
+        for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll 1
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                const uint64_t o = __shfl_xor_sync(0xffffffffu, v, j);
+                const bool takeMin = (((lane & k) == 0) == ((lane & j) == 0));
+                v = takeMin ? (o < v ? o : v) : (o > v ? o : v);
+            }
+        }
+        if (lane < n_pow2) a[lane] = v;
+        __syncwarp();
+        return;
+    }
     for (int k = 2; k <= n_pow2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             __syncwarp();
