@@ -182,6 +182,12 @@ int spb_pairs_from_prefilter(spb_ctx *ctx);
 int spb_align_resident(spb_ctx *ctx, const spb_align_params *p);
 int spb_align_stats(spb_ctx *ctx, spb_align_result *out);
 int spb_align_fetch(spb_ctx *ctx, spb_align_result **out);
+/* pipelined fetch for batch streams (1 M spacers = many batches): _begin snapshots the resident result (device-to-device,
+ * on the context's stream) and starts the copy to pinned host memory on a second stream, then returns; the caller may
+ * immediately upload and run the next batch.  The result's pointers are valid after spb_align_fetch_wait(result); free it
+ * with spb_free_align_result as usual.  (The reference's equivalent is the writer thread behind DBWriter::writeData.) */
+int spb_align_fetch_begin(spb_ctx *ctx, spb_align_result **out);
+int spb_align_fetch_wait(spb_align_result *result);
 
 /* ---- exhaustive search (BASELINE config 5) ---------------------------------------------------------
  * Every resident query against EVERY alignment target, no k-mer stage.  The reference equivalent is `align`

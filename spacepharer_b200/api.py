@@ -67,8 +67,22 @@ class AlignResultView:
     """Host result of spb_align_fetch without extra copies: `offsets`, `rows`, `cigar` are views of the library's pinned
     result buffers; they are valid until close() (or garbage collection) hands the buffers back."""
 
-    def __init__(self, lib, r):
+    def __init__(self, lib, r, pending=False):
         self._lib, self._r = lib, r
+        self._pending = pending
+        if not pending:
+            self._bind()
+
+    def wait(self):
+        """pipelined fetch (Searcher.align_fetch_begin): block until the copy has landed, then expose the views"""
+        if self._pending:
+            capi.check(self._lib.spb_align_fetch_wait(self._r))
+            self._pending = False
+            self._bind()
+        return self
+
+    def _bind(self):
+        r = self._r
         R = r.contents
         self.n_queries = int(R.n_queries)
         self.offsets = _view(R.offsets, self.n_queries + 1, np.uint64)
@@ -316,6 +330,13 @@ class Searcher:
         r = C.POINTER(capi.AlignResult)()
         capi.check(self.lib.spb_align_fetch(self.h, C.byref(r)))
         return AlignResultView(self.lib, r)
+
+    def align_fetch_begin(self):
+        """start copying the resident alignment result to pinned host memory on a second stream and return at once; the next
+        batch can be uploaded and searched meanwhile.  -> AlignResultView whose views exist after .wait()"""
+        r = C.POINTER(capi.AlignResult)()
+        capi.check(self.lib.spb_align_fetch_begin(self.h, C.byref(r)))
+        return AlignResultView(self.lib, r, pending=True)
 
     def align_fetch(self):
         r = C.POINTER(capi.AlignResult)()

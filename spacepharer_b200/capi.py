@@ -81,6 +81,7 @@ SYMBOLS = [
     "spb_prefilter_fetch", "spb_pairs_set", "spb_pairs_from_prefilter", "spb_align_resident", "spb_align_stats",
     "spb_align_fetch", "spb_prefilter_device_result", "spb_prefilter_device_trunc_keys", "spb_prefilter_merge_shards",
     "spb_pairs_exhaustive", "spb_align_exhaustive", "spb_spacer_frames", "spb_free_frames_result",
+    "spb_align_fetch_begin", "spb_align_fetch_wait",
     "spb_nucl_set_targets", "spb_nucl_set_queries", "spb_nucl_rescore", "spb_nucl_rescore_resident", "spb_free_nucl_result",
 ]
 
@@ -148,6 +149,8 @@ def load():
     L.spb_align_resident.argtypes = [vp, C.POINTER(AlignParams)]
     L.spb_align_stats.argtypes = [vp, C.POINTER(AlignResult)]
     L.spb_align_fetch.argtypes = [vp, C.POINTER(C.POINTER(AlignResult))]
+    L.spb_align_fetch_begin.argtypes = [vp, C.POINTER(C.POINTER(AlignResult))]
+    L.spb_align_fetch_wait.argtypes = [C.POINTER(AlignResult)]
     L.spb_prefilter_device_result.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), u64p]
     L.spb_prefilter_merge_shards.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64, vp, C.c_uint32, C.c_int32]
     L.spb_prefilter_device_trunc_keys.argtypes = [vp, C.POINTER(C.c_void_p)]

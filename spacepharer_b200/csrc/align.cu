@@ -943,6 +943,7 @@ extern "C" int spb_align_set_targets(spb_ctx *c, const uint8_t *residues, const 
 struct AlignResultBox {
     spb_align_result pub;
     spb_ctx *owner;
+    cudaEvent_t done;      // spb_align_fetch_begin: recorded behind the D2H copies on the copy stream (nullptr: synchronous fetch)
 };
 
 extern "C" void spb_free_align_result(spb_align_result *r) {
@@ -952,6 +953,10 @@ extern "C" void spb_free_align_result(spb_align_result *r) {
         box->owner->pin_release(r->offsets);
         box->owner->pin_release(r->rows);
         box->owner->pin_release(r->cigar_ops);
+    }
+    if (box->done) {
+        cudaEventSynchronize(box->done);     // the pinned blocks must not be handed out again under a running copy
+        cudaEventDestroy(box->done);
     }
     free(box);
 }
@@ -1304,6 +1309,74 @@ extern "C" int spb_align_fetch(spb_ctx *c, spb_align_result **out) {
         return 1;
     }
     *out = res;
+    return 0;
+}
+
+// Pipelined fetch: the sorted rows, CIGARs and offsets of the resident result are copied device-to-device into staging
+// buffers on the compute stream (microseconds) and from there to pinned host memory on a second stream, so the next batch
+// (spb_queries_set .. spb_align_resident) runs while the previous result crosses PCIe.  One staging set: a second _begin
+// makes the compute stream wait until the previous D2H has left the staging buffers (it has, long before the next batch
+// is through its kernels).
+extern "C" int spb_align_fetch_begin(spb_ctx *c, spb_align_result **out) {
+    SPB_CHECK(c && out, "spb_align_fetch_begin: NULL argument");
+    SPB_CHECK(c->have_aln, "spb_align_fetch_begin: no resident alignment result");
+    SPB_CUDA(cudaSetDevice(c->device));
+    *out = nullptr;
+    if (!c->copy_stream) {
+        SPB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        SPB_CUDA(cudaEventCreateWithFlags(&c->ev_staged, cudaEventDisableTiming));
+        SPB_CUDA(cudaEventCreateWithFlags(&c->ev_stage_free, cudaEventDisableTiming));
+    }
+    const uint32_t Q = c->Q;
+    const size_t nAcc = (size_t)c->n_acc, nCig = (size_t)c->n_cigar;
+    if (c->d_st_rows.ensure(std::max<size_t>(nAcc, 1) * sizeof(spb_aln)) || c->d_st_cig.ensure(nCig + 16) ||
+        c->d_st_off.ensure(((size_t)Q + 1) * 8)) return 1;
+    AlignResultBox *box = (AlignResultBox *)calloc(1, sizeof(AlignResultBox));
+    SPB_CHECK(box != nullptr, "spb_align_fetch_begin: out of memory");
+    box->owner = c;
+    spb_align_result *res = &box->pub;
+    *res = c->aln_stats;
+    res->offsets = (uint64_t *)c->pin_acquire(((size_t)Q + 1) * sizeof(uint64_t));
+    res->rows = (spb_aln *)c->pin_acquire(std::max<size_t>(nAcc, 1) * sizeof(spb_aln));
+    res->cigar_ops = (char *)c->pin_acquire(nCig + 1);
+    if (!res->offsets || !res->rows || !res->cigar_ops) { spb_free_align_result(res); return 1; }
+    res->n_cigar = nCig;
+    res->n_rows = nAcc;
+    cudaStream_t st = c->stream, cs = c->copy_stream;
+    cudaError_t e = cudaEventCreateWithFlags(&box->done, cudaEventDisableTiming);
+    if (e == cudaSuccess && c->stage_busy) e = cudaStreamWaitEvent(st, c->ev_stage_free, 0);
+    if (e == cudaSuccess && nAcc) e = cudaMemcpyAsync(c->d_st_rows.p, c->d_rows.p, nAcc * sizeof(spb_aln), cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess && nCig) e = cudaMemcpyAsync(c->d_st_cig.p, c->d_cig.p, nCig, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_st_off.p, c->d_rowoff.p, ((size_t)Q + 1) * 8, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_staged, st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, c->ev_staged, 0);
+    // in pieces: the control path of the next batch reads small counters back on the compute stream, and the D2H copy engine
+    // arbitrates between streams per copy -- behind one 12 MB transfer each of those reads would wait for all of it
+    auto d2h_chunked = [&](void *dst, const void *src, size_t bytes) {
+        const size_t CH = 1u << 20;
+        for (size_t o = 0; o < bytes && e == cudaSuccess; o += CH)
+            e = cudaMemcpyAsync((char *)dst + o, (const char *)src + o, std::min(CH, bytes - o), cudaMemcpyDeviceToHost, cs);
+    };
+    if (e == cudaSuccess && nAcc) d2h_chunked(res->rows, c->d_st_rows.p, nAcc * sizeof(spb_aln));
+    if (e == cudaSuccess && nCig) d2h_chunked(res->cigar_ops, c->d_st_cig.p, nCig);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(res->offsets, c->d_st_off.p, ((size_t)Q + 1) * 8, cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_stage_free, cs);
+    if (e == cudaSuccess) e = cudaEventRecord(box->done, cs);
+    if (e != cudaSuccess) {
+        cudaStreamSynchronize(cs);
+        spb_free_align_result(res);
+        spb::set_error("spb_align_fetch_begin: %s", cudaGetErrorString(e));
+        return 1;
+    }
+    c->stage_busy = true;
+    *out = res;
+    return 0;
+}
+
+extern "C" int spb_align_fetch_wait(spb_align_result *r) {
+    SPB_CHECK(r != nullptr, "spb_align_fetch_wait: NULL argument");
+    AlignResultBox *box = reinterpret_cast<AlignResultBox *>(r);
+    if (box->done) SPB_CUDA(cudaEventSynchronize(box->done));
     return 0;
 }
 

@@ -161,6 +161,12 @@ struct spb_ctx {
     spb::DevBuf d_qnt, d_qntoff, d_qntsc;
     spb::DevBuf d_nrows;                    // spb_nucl_aln[n] last result
 
+    // ---- pipelined result fetch (spb_align_fetch_begin / _wait): device staging copy + D2H on a second stream ----
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_staged = nullptr, ev_stage_free = nullptr;
+    bool stage_busy = false;
+    spb::DevBuf d_st_rows, d_st_cig, d_st_off;
+
     // ---- pinned result staging ----
     std::vector<spb::PinBlock> pins;
     void *pin_acquire(size_t bytes);

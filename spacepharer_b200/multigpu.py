@@ -192,6 +192,14 @@ class ShardedSearcher:
         return dict(offsets=off, rows=rows, cigar=cig, stats=st, q_lo=self_q_lo,
                     d2h_bytes=off.nbytes + rows.nbytes + len(cig))
 
+    def search_host_begin(self, qres, qoff, db_res_count, **kw):
+        """Pipelined form of search_host for a stream of batches: uploads and searches the batch, starts the copy of its
+        rows + CIGARs to pinned host memory on a second stream and returns; result["view"].wait() gives the views (offsets,
+        rows, cigar) once they have landed -- typically after the NEXT batch has been submitted."""
+        self.set_queries(qres, qoff)
+        st = self.step_resident(db_res_count, **kw)
+        return dict(view=self.searcher.align_fetch_begin(), stats=st, q_lo=self.q_lo)
+
     # ---- target split: hit-list exchange + merge -----------------------------------------------
     def _prefilter_target_split(self, pk):
         import torch

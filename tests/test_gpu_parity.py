@@ -326,3 +326,42 @@ def test_fused_search_equals_two_step(searcher):
     ref = Cm.dump("family", "aln_max300.txt.gz")
     got = {i: a[int(off[i]):int(off[i + 1])] for i in range(len(Q)) if off[i + 1] > off[i]}
     assert got == ref
+
+
+def row_cigars(rows, cig):
+    """the CIGAR buffer has unused slack between the rows' slices: compare what the rows point at"""
+    return [cig[int(r["cigar_off"]): int(r["cigar_off"]) + int(r["cigar_len"])] for r in rows]
+
+
+def test_pipelined_fetch_matches_synchronous_fetch():
+    """spb_align_fetch_begin / _wait (result copied out on a second stream while the next batch runs): two batches in
+    flight, each result byte-identical to the synchronous spb_align_fetch of the same batch"""
+    from spacepharer_b200 import api, synth
+    tres, toff, _ = synth.make_targets(n_genomes=50, seed=12)
+    batches = [synth.make_query_frames(800, tres, toff, seed=s) for s in (21, 22, 23)]
+    s = api.Searcher(device=0)
+    masked, _ = api.tantan_mask(s.seed, tres, toff)
+    s.build_index(masked, toff)
+    s.set_align_targets(tres, toff)
+    db_res = int(toff[-1])
+    want = []
+    for qres, qoff, _ in batches:
+        s.set_queries(qres, qoff)
+        s.prefilter_resident()
+        s.pairs_from_prefilter()
+        s.align_resident(db_res)
+        off, rows, cig, _ = s.align_fetch()
+        want.append((off.tobytes(), rows.tobytes(), row_cigars(rows, bytes(cig))))
+    pend = []
+    for qres, qoff, _ in batches:
+        s.set_queries(qres, qoff)
+        s.prefilter_resident()
+        s.pairs_from_prefilter()
+        s.align_resident(db_res)
+        pend.append(s.align_fetch_begin())       # all three stay outstanding
+    for v, w in zip(pend, want):
+        v.wait()
+        assert (v.offsets.tobytes(), v.rows.tobytes(), row_cigars(v.rows, v.cigar.tobytes())) == w
+        v.close()
+    assert len(want[0][1]) > 0 and want[0] != want[1]
+    s.close()
