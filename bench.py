@@ -6,11 +6,14 @@ against a synthetic GenBank_phage_2018_09-shaped ORF set (8 000 genomes, ~0.5 M 
 predictmatch parameters (VTML80 seeding, -s 5.7, k = 6 spaced 11011101, --max-seqs 300, VTML40 16/2, -e 200, -a 1).
 
 A "step" is one pass of the search (prefilter -> align) over the whole query batch against the resident index:
-  value   : device-resident pass (queries already in HBM), CUDA events on the library's stream, L2 flushed
-            between steps, max over ranks
-  e2e     : a stream of such passes through the public API with HOST buffers (pinned): every step uploads its frames
-            (H2D), runs the kernels and reads its sorted result rows + CIGARs back (D2H, spb_align_fetch_begin/_wait: the
-            read-back of step k overlaps the kernels of step k+1); wall clock from the first upload to the last row landed
+  value   : device-resident passes (queries already in HBM) over `--lanes` contexts per GPU that share one index and run
+            concurrently (one host thread each; the kernels of one lane fill the tails and host-sync bubbles of the other):
+            K steps in total, CUDA events on the lane streams (latest end - earliest start), L2 flushed before every step,
+            max over ranks.  `single_lane` repeats the figure for one context (the kernels alone on the device); the
+            roofline numbers come from that segment
+  e2e     : a stream of batches through the public API with HOST buffers (pinned), over the same lanes: every step uploads
+            its frames (H2D), runs the kernels and reads its sorted result rows + CIGARs back (D2H); wall clock from the
+            first upload to the last row landed
   roofline: the prefilter match kernel (dominant kernel), algorithmic bytes / its CUDA-event duration against the
             measured HBM peak (MEASURED_PEAKS.json)
   cpu_baseline / --impl reference: the CPU oracle port (oracle/, OpenMP over queries like the reference) on a
@@ -49,6 +52,8 @@ def parse_args():
     ap.add_argument("--genomes", type=int, default=8000)
     ap.add_argument("--split-mode", default="query", choices=["target", "query"])
     ap.add_argument("--cpu-sample-spacers", type=int, default=0, help="spacers in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--lanes", type=int, default=2,
+                    help="contexts per GPU sharing one index; batches of different lanes overlap on the device (query split / 1 GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mask", action="store_true", help="skip the tantan host pre-step (--mask 0)")
     ap.add_argument("--exhaustive-spacers", type=int, default=1000,
@@ -244,7 +249,8 @@ def run_ours(args):
     T, Q = len(toff) - 1, len(qoff) - 1
     db_res = int(toff[-1])
     t0 = time.perf_counter()
-    eng = multigpu.ShardedSearcher(device=local, rank=rank, world=world, split_mode=args.split_mode)
+    n_lanes = 1 if (world > 1 and args.split_mode == "target") else max(1, args.lanes)
+    eng = multigpu.ShardedSearcher(device=local, rank=rank, world=world, split_mode=args.split_mode, lanes=n_lanes)
     masked, n_masked = (tres, 0) if args.no_mask else api.tantan_mask(eng.searcher.seed, tres, toff)
     mask_s = time.perf_counter() - t0
     t0 = time.perf_counter()
@@ -291,35 +297,78 @@ def run_ours(args):
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = eng.launches() - launches0
     last = st
+    single_ms = dev_ms
 
-    # ---- end-to-end leg through the public API with host buffers ----
-    for _ in range(min(2, args.warmup)):
-        eng.search_host(q_np, o_np, db_res, copy=False)["view"].close()
-    warm = [eng.search_host_begin(q_np, o_np, db_res) for _ in range(max(2, min(3, args.warmup)))]   # two result sets in flight
-    for w in warm:
-        w["view"].wait().close()
-    barrier()
-    t0 = time.perf_counter()
+    # ---- device-resident leg over the lanes: the whole-job throughput ("value") ----
+    # K steps shared by n_lanes contexts (one host thread each, every lane holds the batch resident); one CUDA event per lane
+    # stream before the first and after the last step, device time = latest end - earliest start; the per-step L2 flush runs
+    # on the lane's stream INSIDE the timed span here
+    if n_lanes > 1:
+        lanes = eng.lanes()
+        dev = torch.device("cuda", local)
+        ext = [torch.cuda.ExternalStream(ln.stream_ptr(), device=dev) for ln in lanes]
+        fl = [flush] + [torch.empty(256 << 20, dtype=torch.uint8, device="cuda") for _ in lanes[1:]]
+
+        def before_step(l, ln):
+            with torch.cuda.stream(ext[l]):
+                fl[l].zero_()
+
+        eng.run_stream([(q_np, o_np)], db_res, steps=max(args.warmup, 2) * n_lanes, resident=True, before_step=before_step)
+        launches0 = eng.launches()
+        e0 = [torch.cuda.Event(enable_timing=True) for _ in lanes]
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in lanes]
+        barrier()
+        t_wall0 = time.perf_counter()
+        for l in range(len(lanes)):
+            e0[l].record(ext[l])
+        eng.run_stream([(q_np, o_np)], db_res, steps=args.steps, resident=True, before_step=before_step)
+        for l in range(len(lanes)):
+            e1[l].record(ext[l])
+        barrier()
+        wall_value = time.perf_counter() - t_wall0
+        dev_ms = max(a.elapsed_time(b) for a in e0 for b in e1)
+        launches = eng.launches() - launches0
+        eng.set_queries(q_np, o_np)
+
+    # ---- end-to-end leg through the public API with HOST buffers ----
+    # a stream of batches: every step uploads its queries from pinned host memory (H2D), searches, and reads its rows + CIGARs
+    # back into pinned host buffers of the library (D2H); wall clock from the first upload to the last row landed
     d2h = 0
-    # a stream of batches through the public API: every step uploads its queries from pinned host memory, searches, and
-    # reads its rows + CIGARs back into pinned host buffers of the library; the read-back of batch k (second stream) overlaps
-    # the search of batch k+1, and the timed region ends when the last batch's rows have landed
-    pending = None
+    if n_lanes > 1:
+        eng.run_stream([(q_np, o_np)], db_res, steps=2 * n_lanes)
+        barrier()
+        t0 = time.perf_counter()
+        sts = eng.run_stream([(q_np, o_np)], db_res, steps=args.steps)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        d2h, n_rows_e2e = sts[-1]["d2h_bytes"], sts[-1]["rows"]
+        e2e_how = ("%d lanes per GPU (contexts sharing one index, one host thread each): upload, kernels and read-back of different "
+                   "batches overlap; all copies inside the timed region" % n_lanes)
+    else:
+        for _ in range(min(2, args.warmup)):
+            eng.search_host(q_np, o_np, db_res, copy=False)["view"].close()
+        warm = [eng.search_host_begin(q_np, o_np, db_res) for _ in range(max(2, min(3, args.warmup)))]
+        for w in warm:
+            w["view"].wait().close()
+        barrier()
+        t0 = time.perf_counter()
+        pending = None
 
-    def consume(p):
-        v = p["view"].wait()
-        n = (v.nbytes, len(v.rows))
-        v.close()
-        return n
+        def consume(p):
+            v = p["view"].wait()
+            n = (v.nbytes, len(v.rows))
+            v.close()
+            return n
 
-    for k in range(args.steps):
-        cur = eng.search_host_begin(q_np, o_np, db_res)
-        if pending is not None:
-            d2h, n_rows_e2e = consume(pending)
-        pending = cur
-    d2h, n_rows_e2e = consume(pending)
-    barrier()
-    e2e_s = time.perf_counter() - t0
+        for k in range(args.steps):
+            cur = eng.search_host_begin(q_np, o_np, db_res)
+            if pending is not None:
+                d2h, n_rows_e2e = consume(pending)
+            pending = cur
+        d2h, n_rows_e2e = consume(pending)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        e2e_how = "D2H of step k on a second stream while step k+1 runs (spb_align_fetch_begin/_wait); all copies inside the timed region"
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- exhaustive-search leg (config 5): a bounded sample of the batch against EVERY target, streaming SW kernel ----
@@ -337,12 +386,12 @@ def run_ours(args):
         exh = {"kernel_ms": float(np.mean([r["kernel_ms"] for r in runs])), "cells": float(runs[-1]["n_cells"]),
                "scored": float(runs[-1]["n_scored"]), "kept": float(runs[-1]["n_kept"]), "queries": nq}
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3, exh["kernel_ms"] if exh else 0.0], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s * 1e3, exh["kernel_ms"] if exh else 0.0, single_ms], dtype=torch.float64, device="cuda")
     tsum = torch.tensor([exh["cells"], exh["scored"], exh["kept"], exh["queries"]] if exh else [0.0] * 4, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-    dev_ms, e2e_ms, exh_ms = float(t[0]), float(t[1]), float(t[2])
+    dev_ms, e2e_ms, exh_ms, single_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     q_total = eng.queries_per_step(Q)
 
     if rank == 0:
@@ -356,20 +405,25 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args, Q, T, db_res, args.spacers * (world if weak else 1)), "queries_per_step": q_total,
                        "split_mode": args.split_mode if world > 1 else "none",
-                       "l2": "256 MB memset between timed steps (outside the per-step CUDA events); index %.2f GB > L2"
-                             % (ist["bytes_device"] / 1e9),
-                       "timing": "sum of per-step CUDA-event intervals on the library stream, max over ranks",
+                       "lanes": n_lanes,
+                       "l2": "256 MB memset on the lane's stream before every step (inside the timed span with lanes > 1, outside the "
+                             "per-step events of the single-lane segment); index %.2f GB > L2" % (ist["bytes_device"] / 1e9),
+                       "timing": ("CUDA events on the lane streams: latest end - earliest start over %d steps shared by %d lanes, max over ranks"
+                                  % (args.steps, n_lanes)) if n_lanes > 1 else
+                                 "sum of per-step CUDA-event intervals on the library stream, max over ranks",
                        "index": "resident (built once: %.1f ms device, %.2f s wall incl. H2D; tantan host pre-step %.2f s, %d residues masked)"
                                 % (ist["build_ms"], build_s, mask_s, n_masked)},
             "e2e": {"value": q_total * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(q_np.nbytes + o_np.nbytes), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps,
-                    "pipeline": "D2H of step k on a second stream while step k+1 runs; all copies inside the timed region"},
+                    "pipeline": e2e_how},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "prefilter_team_kernel<1> + <8>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                          "algo_bytes_per_launch": float(np.mean(pk_bytes)), "kernel_ms": kms,
-                         "share_of_step": kms / (dev_ms / args.steps)},
+                         "share_of_step": kms / (single_ms / args.steps),
+                         "measured": "single-lane segment (%d steps, the kernel alone on the device, CUDA events on its stream)" % args.steps},
+            "single_lane": {"value": q_total * args.steps / (single_ms * 1e-3), "ms_per_step": single_ms / args.steps},
             "sw": {"gcups": float(np.mean(sw_cells)) / (float(np.mean(sw_ms)) * 1e-3) / 1e9 if np.mean(sw_ms) > 0 else None,
                    "kernel_ms": float(np.mean(sw_ms)), "cells_per_step": float(np.mean(sw_cells)),
                    "pairs": last["align"]["n_pairs"], "rows": last["align"]["n_rows"]},

@@ -39,6 +39,12 @@ typedef struct spb_ctx spb_ctx;
 /* ---- life cycle ------------------------------------------------------------------------------- */
 int spb_ctx_create(int device, spb_ctx **out);
 void spb_ctx_destroy(spb_ctx *ctx);
+/* A lane of `parent`: a context on the same device with its own stream, query batch, results and scratch that READS the
+ * parent's matrices, k-mer index, alignment targets and nucleotide targets in place (nothing is copied).  One host thread per
+ * lane, like one QueryMatcher / Matcher per OpenMP thread in the reference (Prefiltering.cpp:776-800, Alignment.cpp:285-321);
+ * batches submitted to different lanes overlap on the GPU.  Create lanes after the parent's index / targets are set; do not
+ * rebuild those or destroy the parent while a lane exists.  A lane cannot build an index or set targets itself. */
+int spb_ctx_create_lane(spb_ctx *parent, spb_ctx **out);
 const char *spb_last_error(void);
 const char *spb_version(void);
 /* the CUDA stream all work of this context is enqueued on (cudaStream_t as void*) */

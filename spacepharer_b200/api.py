@@ -149,6 +149,17 @@ class Searcher:
                                              p40.ctypes.data_as(f64)))
         self.T = 0
 
+    def lane(self):
+        """A second context on the same GPU that reads this searcher's index / alignment targets / nucleotide targets in place
+        (spb_ctx_create_lane) and has its own stream, query batch and results.  Drive every lane from its own host thread:
+        batches of different lanes overlap on the device.  Close lanes before the parent."""
+        ln = Searcher.__new__(Searcher)
+        ln.__dict__.update({k: v for k, v in self.__dict__.items() if k != "h"})
+        h = C.c_void_p()
+        capi.check(self.lib.spb_ctx_create_lane(self.h, C.byref(h)))
+        ln.h = h
+        return ln
+
     def stream_ptr(self):
         """cudaStream_t (as int) all work of this searcher is enqueued on"""
         return int(self.lib.spb_ctx_stream(self.h) or 0)

@@ -81,7 +81,7 @@ SYMBOLS = [
     "spb_prefilter_fetch", "spb_pairs_set", "spb_pairs_from_prefilter", "spb_align_resident", "spb_align_stats",
     "spb_align_fetch", "spb_prefilter_device_result", "spb_prefilter_device_trunc_keys", "spb_prefilter_merge_shards",
     "spb_pairs_exhaustive", "spb_align_exhaustive", "spb_spacer_frames", "spb_free_frames_result",
-    "spb_align_fetch_begin", "spb_align_fetch_wait",
+    "spb_ctx_create_lane", "spb_align_fetch_begin", "spb_align_fetch_wait",
     "spb_nucl_set_targets", "spb_nucl_set_queries", "spb_nucl_rescore", "spb_nucl_rescore_resident", "spb_free_nucl_result",
 ]
 
@@ -113,6 +113,7 @@ def load():
     L = C.CDLL(LIB_PATH)
     vp, u8p, u64p, u32p = C.c_void_p, C.POINTER(C.c_ubyte), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
     L.spb_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.spb_ctx_create_lane.argtypes = [vp, C.POINTER(vp)]
     L.spb_ctx_destroy.argtypes = [vp]
     L.spb_ctx_destroy.restype = None
     L.spb_last_error.restype = C.c_char_p

@@ -919,6 +919,7 @@ using namespace spb;
 
 extern "C" int spb_align_set_targets(spb_ctx *c, const uint8_t *residues, const uint64_t *offsets, uint32_t T,
                                      const uint32_t *keys) {
+    SPB_CHECK(!c || !c->is_lane, "spb_align_set_targets: a lane context borrows its parent's index / targets");
     SPB_CHECK(c && residues && offsets, "spb_align_set_targets: NULL argument");
     SPB_CUDA(cudaSetDevice(c->device));
     const uint64_t N = offsets[T];

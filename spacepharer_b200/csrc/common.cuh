@@ -42,8 +42,13 @@ void set_error(const char *fmt, ...);
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    bool borrowed = false;   // read-only view of another context's buffer (spb_ctx_create_lane): never freed or grown here
     int ensure(size_t bytes) {
         if (bytes <= cap) return 0;
+        if (borrowed) {
+            set_error("a lane context cannot rebuild the index / targets it borrows from its parent");
+            return 1;
+        }
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
@@ -57,9 +62,15 @@ struct DevBuf {
         return 0;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p && !borrowed) cudaFree(p);
         p = nullptr;
         cap = 0;
+        borrowed = false;
+    }
+    DevBuf view() const {
+        DevBuf v = *this;
+        v.borrowed = true;
+        return v;
     }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
@@ -83,6 +94,7 @@ struct Matrices {
 
 struct spb_ctx {
     int device = 0;
+    bool is_lane = false;         // spb_ctx_create_lane: index / targets / matrices are borrowed from the parent, read-only
     int n_sm = 148;               // multiprocessors of the device (persistent grids)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;

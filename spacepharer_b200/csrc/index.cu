@@ -192,6 +192,7 @@ using namespace spb;
 
 extern "C" int spb_index_build(spb_ctx *c, const uint8_t *residues, const uint64_t *offsets, uint32_t T,
                                const char *pattern, int kmer_thr) {
+    SPB_CHECK(!c || !c->is_lane, "spb_index_build: a lane context borrows its parent's index / targets");
     SPB_CHECK(c && residues && offsets && pattern, "spb_index_build: NULL argument");
     SPB_CHECK(c->have_matrices, "spb_index_build: call spb_set_matrices first");
     SPB_CUDA(cudaSetDevice(c->device));

@@ -144,6 +144,7 @@ static int rescore(spb_ctx *c, const spb_nucl_params *p, const spb_aln *d_rows, 
 extern "C" {
 
 int spb_nucl_set_targets(spb_ctx *c, const uint8_t *nt, const uint64_t *offsets, uint32_t T, const uint8_t *start_codon) {
+    SPB_CHECK(!c || !c->is_lane, "spb_nucl_set_targets: a lane context borrows its parent's index / targets");
     if (spb::upload_nt(c, nt, offsets, T, start_codon, c->d_tnt, c->d_tntoff, c->d_tntsc, "spb_nucl_set_targets")) return 1;
     c->ntT = T;
     c->have_nt_targets = true;

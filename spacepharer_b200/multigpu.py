@@ -111,8 +111,12 @@ class _DevView:
 
 
 class ShardedSearcher:
-    def __init__(self, device=0, rank=0, world=1, split_mode="query", **kw):
+    def __init__(self, device=0, rank=0, world=1, split_mode="query", lanes=1, **kw):
+        """lanes > 1: that many contexts per GPU sharing one index (api.Searcher.lane), used by run_stream for a stream of
+        batches -- the kernels of one lane fill the tails and host-sync bubbles of the others."""
         self.rank, self.world, self.split_mode = rank, world, split_mode
+        self.n_lanes = max(1, int(lanes))
+        self._lanes = None
         self.searcher = api.Searcher(device=device, **kw)
         self.device = device
         self.shard = None
@@ -120,10 +124,78 @@ class ShardedSearcher:
         self.q_lo = 0
 
     def close(self):
+        for ln in (self._lanes or [])[1:]:
+            ln.close()
+        self._lanes = None
         self.searcher.close()
 
     def launches(self):
-        return self.searcher.launches()
+        return sum(ln.launches() for ln in (self._lanes or [self.searcher]))
+
+    def lanes(self):
+        """the lane contexts (lane 0 is the searcher itself); created on first use, after the targets are loaded"""
+        if self._lanes is None:
+            self._lanes = [self.searcher] + [self.searcher.lane() for _ in range(self.n_lanes - 1)]
+        return self._lanes
+
+    def run_stream(self, batches, db_res_count, steps=None, resident=False, consume=None, before_step=None, **kw):
+        """A stream of query batches over the lanes, one host thread per lane (ctypes releases the GIL inside the library).
+        batches: list of (qres, qoff) host buffers; step i searches batches[i % len(batches)] (steps defaults to one pass).
+        resident=False: every step uploads its batch, searches it and reads rows + CIGARs back into pinned host buffers;
+        consume(step, q_lo, view), if given, sees the zero-copy result view before it is handed back.
+        resident=True: the batches are uploaded once per lane (lane l owns batches[l]), the steps only run the kernels.
+        before_step(lane, searcher), if given, runs in the lane's thread ahead of every step (bench.py: L2 flush).
+        Returns a list with one stats dict per step (step order).  Query split / single GPU only."""
+        import threading
+        assert not (self.world > 1 and self.split_mode == "target"), "run_stream: lanes are for query split / one GPU"
+        lanes = self.lanes()
+        steps = len(batches) if steps is None else steps
+        pk = {k: kw[k] for k in ("kmer_thr", "max_seqs", "min_ungapped_score", "bin_size", "comp_bias") if k in kw}
+        ak = {k: kw[k] for k in ("evalue", "gap_open", "gap_extend", "comp_bias", "gumbel", "byte_lanes", "word_lanes") if k in kw}
+        mine = [self._my_queries(q, o) for q, o in batches]
+        if resident:
+            for l, ln in enumerate(lanes):
+                q, o, _ = mine[l % len(mine)]
+                ln.set_queries(q, o)
+        out, errs = [None] * steps, []
+        nxt, lock = [0], threading.Lock()
+
+        def work(l):
+            ln = lanes[l]
+            try:
+                while True:
+                    with lock:
+                        i = nxt[0]
+                        nxt[0] += 1
+                    if i >= steps:
+                        return
+                    q, o, q_lo = mine[(l if resident else i) % len(mine)]
+                    if before_step is not None:
+                        before_step(l, ln)
+                    if not resident:
+                        ln.set_queries(q, o)
+                    pst = ln.prefilter_resident(**pk)
+                    ln.pairs_from_prefilter()
+                    ast = ln.align_resident(db_res_count, **ak)
+                    st = dict(prefilter=pst, align=ast, lane=l)
+                    if not resident:
+                        v = ln.align_fetch_view()
+                        st["d2h_bytes"], st["rows"] = v.nbytes, len(v.rows)
+                        if consume is not None:
+                            consume(i, q_lo, v)
+                        v.close()
+                    out[i] = st
+            except Exception as e:  # noqa: BLE001 -- re-raised in the caller's thread
+                errs.append(e)
+
+        th = [threading.Thread(target=work, args=(l,)) for l in range(len(lanes))]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0]
+        return out
 
     # ---- targets -----------------------------------------------------------------------------
     def load_targets(self, masked, tres, toff, keys=None):

@@ -365,3 +365,46 @@ def test_pipelined_fetch_matches_synchronous_fetch():
         v.close()
     assert len(want[0][1]) > 0 and want[0] != want[1]
     s.close()
+
+
+def row_fields(rows):
+    """rows without the struct's padding bytes and without the CIGAR slack offsets (both may differ between contexts)"""
+    return tuple(np.asarray(rows[n]).tobytes() for n in rows.dtype.names if n != "cigar_off")
+
+
+def test_lanes_stream_matches_single_context():
+    """spb_ctx_create_lane: three contexts sharing one index search a stream of different batches concurrently (one host thread
+    per lane); every batch's rows are byte-identical to the single-context search, and a lane refuses to rebuild what it borrows"""
+    from spacepharer_b200 import api, capi, multigpu, synth
+    tres, toff, _ = synth.make_targets(n_genomes=80, seed=31)
+    batches = [synth.make_query_frames(600 + 50 * i, tres, toff, seed=40 + i)[:2] for i in range(7)]
+    eng = multigpu.ShardedSearcher(device=0, lanes=3)
+    masked, _ = api.tantan_mask(eng.searcher.seed, tres, toff)
+    eng.load_targets(masked, tres, toff)
+    db_res = int(toff[-1])
+    want = []
+    for qres, qoff in batches:
+        r = eng.search_host(qres, qoff, db_res)
+        want.append((r["offsets"].tobytes(), row_fields(r["rows"]), row_cigars(r["rows"], bytes(r["cigar"]))))
+    got = {}
+
+    def consume(i, q_lo, v):
+        got[i] = (v.offsets.tobytes(), row_fields(v.rows), row_cigars(v.rows, v.cigar.tobytes()))
+
+    for _ in range(2):      # twice: the second pass runs on warm lanes
+        got.clear()
+        sts = eng.run_stream(batches, db_res, consume=consume)
+        assert sorted(got) == list(range(len(batches)))
+        for i in range(len(batches)):
+            assert got[i] == want[i], i
+    assert len({st["lane"] for st in sts}) > 1, "the stream never used a second lane"
+    assert len(want[0][1]) > 0
+    # resident mode (no upload / fetch): same counters as the single context
+    sts = eng.run_stream(batches[:3], db_res, steps=6, resident=True)
+    assert all(st["align"]["n_rows"] > 0 for st in sts)
+    ln = eng.lanes()[1]
+    with pytest.raises(capi.SpbError, match="lane"):
+        ln.build_index(masked, toff)
+    with pytest.raises(capi.SpbError, match="lane"):
+        ln.set_align_targets(tres, toff)
+    eng.close()
