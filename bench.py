@@ -249,7 +249,8 @@ def run_ours(args):
     T, Q = len(toff) - 1, len(qoff) - 1
     db_res = int(toff[-1])
     t0 = time.perf_counter()
-    n_lanes = 1 if (world > 1 and args.split_mode == "target") else max(1, args.lanes)
+    # one busy host thread per lane and rank: never more lanes than host cores per rank
+    n_lanes = 1 if (world > 1 and args.split_mode == "target") else max(1, min(args.lanes, (os.cpu_count() or 1) // max(world, 1)))
     eng = multigpu.ShardedSearcher(device=local, rank=rank, world=world, split_mode=args.split_mode, lanes=n_lanes)
     masked, n_masked = (tres, 0) if args.no_mask else api.tantan_mask(eng.searcher.seed, tres, toff)
     mask_s = time.perf_counter() - t0
