@@ -52,7 +52,7 @@ def parse_args():
     ap.add_argument("--genomes", type=int, default=8000)
     ap.add_argument("--split-mode", default="query", choices=["target", "query"])
     ap.add_argument("--cpu-sample-spacers", type=int, default=0, help="spacers in the CPU baseline sample (0 = auto)")
-    ap.add_argument("--lanes", type=int, default=2,
+    ap.add_argument("--lanes", type=int, default=3,
                     help="contexts per GPU sharing one index; batches of different lanes overlap on the device (query split / 1 GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mask", action="store_true", help="skip the tantan host pre-step (--mask 0)")
