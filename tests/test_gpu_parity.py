@@ -328,6 +328,11 @@ def test_fused_search_equals_two_step(searcher):
     assert got == ref
 
 
+def row_fields(rows):
+    """rows without the struct's padding bytes and without the CIGAR slack offsets (both may differ between runs and contexts)"""
+    return tuple(np.asarray(rows[n]).tobytes() for n in rows.dtype.names if n != "cigar_off")
+
+
 def row_cigars(rows, cig):
     """the CIGAR buffer has unused slack between the rows' slices: compare what the rows point at"""
     return [cig[int(r["cigar_off"]): int(r["cigar_off"]) + int(r["cigar_len"])] for r in rows]
@@ -351,7 +356,7 @@ def test_pipelined_fetch_matches_synchronous_fetch():
         s.pairs_from_prefilter()
         s.align_resident(db_res)
         off, rows, cig, _ = s.align_fetch()
-        want.append((off.tobytes(), rows.tobytes(), row_cigars(rows, bytes(cig))))
+        want.append((off.tobytes(), row_fields(rows), row_cigars(rows, bytes(cig))))
     pend = []
     for qres, qoff, _ in batches:
         s.set_queries(qres, qoff)
@@ -361,15 +366,10 @@ def test_pipelined_fetch_matches_synchronous_fetch():
         pend.append(s.align_fetch_begin())       # all three stay outstanding
     for v, w in zip(pend, want):
         v.wait()
-        assert (v.offsets.tobytes(), v.rows.tobytes(), row_cigars(v.rows, v.cigar.tobytes())) == w
+        assert (v.offsets.tobytes(), row_fields(v.rows), row_cigars(v.rows, v.cigar.tobytes())) == w
         v.close()
     assert len(want[0][1]) > 0 and want[0] != want[1]
     s.close()
-
-
-def row_fields(rows):
-    """rows without the struct's padding bytes and without the CIGAR slack offsets (both may differ between contexts)"""
-    return tuple(np.asarray(rows[n]).tobytes() for n in rows.dtype.names if n != "cigar_off")
 
 
 def test_lanes_stream_matches_single_context():
