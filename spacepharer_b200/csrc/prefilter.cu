@@ -958,35 +958,52 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                 if (Rtot > 65535u) { why = ST_CAPACITY; reason = 2; }
                 __syncwarp();
                 // runs: maximal stretches of outer neighbours with equal score (hence equal inner count)
-                for (uint32_t g0 = 0; g0 < Rtot && why == ST_OK; g0 += 32) {
-                    const uint32_t g = g0 + lane;
-                    bool boundary = false;
-                    uint32_t a = 0, w = 0, n2 = 0;
-                    if (g < Rtot) {
-                        int lo = 0, hi = P - 1;   // largest w with rowbase[w] <= g
-                        while (lo < hi) {
-                            const int mid = (lo + hi + 1) >> 1;
-                            if ((uint32_t)S.rowbase[mid] <= g) lo = mid; else hi = mid - 1;
-                        }
-                        w = (uint32_t)lo;
-                        a = g - (uint32_t)S.rowbase[w];
-                        const uint32_t *r1 = A.row3 + (size_t)S.x1[w] * SPB_N3;
-                        const int s1 = (int)(__ldg(r1 + a) >> 16) - SPB_SCORE_OFF;
-                        boundary = (a == 0) || ((int)(__ldg(r1 + a - 1) >> 16) - SPB_SCORE_OFF != s1);
-                        if (boundary) {
-                            const int cut2 = (int)S.thr[w] - s1;
-                            if (cut2 <= SPB_CNT3_W - SPB_SCORE_OFF - 1)
-                                n2 = (uint32_t)__ldg(A.cnt3 + (size_t)S.x2[w] * SPB_CNT3_W + max(cut2, -SPB_SCORE_OFF) + SPB_SCORE_OFF);
+                // (two chunks of 32 outer neighbours per trip: their row3 / cnt3 reads are independent and go out together)
+                for (uint32_t g0 = 0; g0 < Rtot && why == ST_OK; g0 += 64) {
+                    uint32_t av[2], wv[2], n2v[2], cur[2], prv[2];
+                    bool bnd[2];
+#pragma unroll
+                    for (int v = 0; v < 2; v++) {
+                        const uint32_t g = g0 + (uint32_t)(32 * v + lane);
+                        av[v] = 0; wv[v] = 0; n2v[v] = 0; cur[v] = 0; prv[v] = 0;
+                        if (g < Rtot) {
+                            int lo = 0, hi = P - 1;   // largest w with rowbase[w] <= g
+                            while (lo < hi) {
+                                const int mid = (lo + hi + 1) >> 1;
+                                if ((uint32_t)S.rowbase[mid] <= g) lo = mid; else hi = mid - 1;
+                            }
+                            wv[v] = (uint32_t)lo;
+                            av[v] = g - (uint32_t)S.rowbase[lo];
+                            const uint32_t *r1 = A.row3 + (size_t)S.x1[lo] * SPB_N3;
+                            cur[v] = __ldg(r1 + av[v]);
+                            prv[v] = av[v] ? __ldg(r1 + av[v] - 1) : 0u;
                         }
                     }
-                    const unsigned m = __ballot_sync(0xffffffffu, boundary);
-                    const int dst = nRuns + __popc(m & lt);
-                    if (boundary && dst < PW_RUNCAP) {
-                        Run r;
-                        r.a0 = (uint16_t)a; r.n2 = (uint16_t)n2; r.cum = (uint16_t)g; r.w = (uint16_t)w;
-                        runs[dst] = r;
+#pragma unroll
+                    for (int v = 0; v < 2; v++) {
+                        const uint32_t g = g0 + (uint32_t)(32 * v + lane);
+                        bnd[v] = false;
+                        if (g < Rtot) {
+                            const int s1 = (int)(cur[v] >> 16) - SPB_SCORE_OFF;
+                            bnd[v] = (av[v] == 0) || ((int)(prv[v] >> 16) - SPB_SCORE_OFF != s1);
+                            if (bnd[v]) {
+                                const int cut2 = (int)S.thr[wv[v]] - s1;
+                                if (cut2 <= SPB_CNT3_W - SPB_SCORE_OFF - 1)
+                                    n2v[v] = (uint32_t)__ldg(A.cnt3 + (size_t)S.x2[wv[v]] * SPB_CNT3_W + max(cut2, -SPB_SCORE_OFF) + SPB_SCORE_OFF);
+                            }
+                        }
                     }
-                    nRuns += __popc(m);
+#pragma unroll
+                    for (int v = 0; v < 2; v++) {
+                        const unsigned m = __ballot_sync(0xffffffffu, bnd[v]);
+                        const int dst = nRuns + __popc(m & lt);
+                        if (bnd[v] && dst < PW_RUNCAP) {
+                            Run r;
+                            r.a0 = (uint16_t)av[v]; r.n2 = (uint16_t)n2v[v]; r.cum = (uint16_t)(g0 + (uint32_t)(32 * v + lane)); r.w = (uint16_t)wv[v];
+                            runs[dst] = r;
+                        }
+                        nRuns += __popc(m);
+                    }
                     if (nRuns > PW_RUNCAP) { why = ST_CAPACITY; reason = 3; }
                 }
                 __syncwarp();
