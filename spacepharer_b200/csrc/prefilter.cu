@@ -751,34 +751,8 @@ __device__ __noinline__ void pw_emit(bool have, uint64_t pe, uint32_t k, uint32_
 }
 
 // posting lists of the k-mers held by the lanes of a warp (len == 0: none), flattened over the warp: element p of the
-// concatenated lists belongs to the last lane whose exclusive prefix is <= p (coalesced reads, no per-lane walks)
-__device__ __noinline__ void pw_walk(uint32_t len, uint32_t off, uint32_t w, uint32_t kb, uint32_t kmul, const uint64_t *__restrict__ post,
-                                     uint32_t *nHitsCtr, uint64_t *scratch, uint32_t HCAP, uint32_t *seen1, uint32_t *seen2, int hashShift) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t inc = (uint32_t)warp_incl_scan_ool((int)len);
-    const uint32_t excl = inc - len;
-    const uint32_t T = __shfl_sync(0xffffffffu, inc, 31);
-#pragma unroll 1
-    for (uint32_t p0 = 0; p0 < T; p0 += 32) {
-        const uint32_t pp = p0 + lane;
-        int j = 0;
-#pragma unroll 1
-        for (int step = 16; step > 0; step >>= 1) {
-            const int cand = j + step;
-            const uint32_t e = __shfl_sync(0xffffffffu, excl, cand & 31);
-            if (cand < 32 && e <= pp) j = cand;
-        }
-        const uint32_t srcOff = __shfl_sync(0xffffffffu, off, j);
-        const uint32_t srcEx = __shfl_sync(0xffffffffu, excl, j);
-        const uint32_t srcW = __shfl_sync(0xffffffffu, w, j);
-        const bool have = pp < T;
-        uint64_t pe = 0;
-        if (have) pe = __ldg(post + srcOff + (pp - srcEx));
-        pw_emit(have, pe, kb + (uint32_t)j * kmul, srcW, nHitsCtr, scratch, HCAP, seen1, seen2, hashShift);
-    }
-}
-
-// the same for the PW_U = 2 consecutive k-mers a lane owns in one lookup iteration: both lists of a lane are concatenated
+// concatenated lists belongs to the last lane whose exclusive prefix is <= p (coalesced reads, no per-lane walks);
+// the PW_U = 2 consecutive k-mers a lane owns in one lookup iteration are served together: both lists of a lane are concatenated
 // (k-mer 2 * lane first), so one scan and one pass serve the 64 k-mers of the iteration instead of two of each
 __device__ __noinline__ void pw_walk2(uint32_t len0, uint32_t off0, uint32_t len1, uint32_t off1, uint32_t wPack, uint32_t k0,
                                       const uint64_t *__restrict__ post, uint32_t *nHitsCtr, uint64_t *scratch, uint32_t HCAP,
@@ -1037,7 +1011,7 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
         // (outer neighbour, inner neighbour) of the first, the others follow by stepping.  A table entry carries up to two
         // postings inline (95 % of the k-mers of a GenBank-phage-sized index occur in at most two ORFs), so most hits are
         // written straight from the entry: one scan, one reservation, no second memory access.  Longer lists are walked
-        // warp-wide (pw_walk).
+        // warp-wide (pw_walk2).
         if (S.v_slow == ST_OK) {
             constexpr int HSH = SOLO ? 19 : 17;
             for (uint32_t k0 = (uint32_t)tw * (32 * PW_U); k0 < K; k0 += TEAM * 32 * PW_U) {
