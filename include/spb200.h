@@ -141,6 +141,7 @@ typedef struct spb_aln {     /* Matcher::result_t, M/alignment/Matcher.h:24-119 
     int32_t n_ident, aln_len;
     float seq_id;
     uint32_t cigar_off, cigar_len;  /* slice of spb_align_result::cigar_ops (one op char per column: M/I/D) */
+    uint32_t reserved;              /* 0 (the struct is 64 bytes; rows are bytewise reproducible) */
 } spb_aln;
 
 typedef struct spb_align_result {

@@ -45,7 +45,7 @@ class Aln(C.Structure):
     _fields_ = [("query", C.c_uint32), ("target", C.c_uint32), ("score", C.c_int32), ("bits", C.c_int32),
                 ("eval", C.c_double), ("q_start", C.c_int32), ("q_end", C.c_int32), ("t_start", C.c_int32),
                 ("t_end", C.c_int32), ("n_ident", C.c_int32), ("aln_len", C.c_int32), ("seq_id", C.c_float),
-                ("cigar_off", C.c_uint32), ("cigar_len", C.c_uint32)]
+                ("cigar_off", C.c_uint32), ("cigar_len", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class AlignResult(C.Structure):

@@ -685,6 +685,7 @@ __global__ void pack_rows_kernel(const PairOut *__restrict__ out, const uint32_t
     r.seq_id = (float)o.nIdent / (float)o.alnLen;   // Util::computeSeqId, --seq-id-mode 0
     r.cigar_off = o.cigOff;
     r.cigar_len = o.cigLen;
+    r.reserved = 0;
     rows[k] = r;
 }
 
@@ -925,6 +926,7 @@ extern "C" int spb_align_set_targets(spb_ctx *c, const uint8_t *residues, const 
     const uint64_t N = offsets[T];
     if (c->d_ares.ensure(N + 64) || c->d_aoff.ensure(((size_t)T + 1) * 8) || c->d_akeys.ensure((size_t)T * 4 + 4)) return 1;
     SPB_CUDA(cudaMemcpyAsync(c->d_ares.p, residues, N, cudaMemcpyHostToDevice, c->stream));
+    SPB_CUDA(cudaMemsetAsync((uint8_t *)c->d_ares.p + N, SPB_X, 64, c->stream));   // the SW kernels read aligned 4-byte windows past the end
     SPB_CUDA(cudaMemcpyAsync(c->d_aoff.p, offsets, ((size_t)T + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     SPB_CUDA(cudaStreamSynchronize(c->stream));
     c->aT = T;
@@ -1156,6 +1158,8 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
         SPB_CUDA(cudaStreamSynchronize(st));
         SPB_CHECK(h_err == 0, "spb_align: forward and reverse Smith-Waterman scores differ (accepted pair #%d)", h_err - 1);
         if (c->s_k.ensure(tbTotal + 64) || c->d_cig.ensure(cigTotal + 64)) return 1;
+        // slices are sized by an upper bound of the alignment length: the slack between them is copied out with the result
+        SPB_CUDA(cudaMemsetAsync(c->d_cig.p, 0, cigTotal, st));
         B.tbOff = tbOff;
         B.tbScratch = c->s_k.as<unsigned char>();
         B.cigOff = cigOff;

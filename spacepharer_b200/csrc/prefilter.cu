@@ -1440,6 +1440,7 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
             }
             __syncthreads();
         }
+        team_sync();     // every lane has read v_slow above (the TEAM = 1 hand-over branch has no barrier of its own)
         if (tw == 0 && lane == 0) S.v_slow = (A.status[qi] == ST_OK) ? ST_OK : ST_CAPACITY;
         team_sync();
         if (S.v_slow == ST_OK) statE += evAcc;     // events of the groups this warp processed
