@@ -7,6 +7,8 @@
 //   spb200 prefilter <queryDB> <targetDB> <prefilterDB> [flags]     Prefiltering (M/prefiltering/Prefiltering.cpp)
 //   spb200 align     <queryDB> <targetDB> <prefilterDB> <alnDB> [flags]   Alignment (M/alignment/Alignment.cpp)
 //   spb200 search    <queryDB> <targetDB> <alnDB> [flags]           both steps with the hit lists kept in HBM
+//   spb200 extractframes <nuclSeqDB> <outDB> [--min-length 9]        extractorfs --orf-start-mode 1 + translatenucs fused on the device:
+//                                                                   <outDB>_nucl_orf(+_h) and the amino-acid query DB <outDB>(+_h)
 //   spb200 createindex <targetDB> <tmpDir> [flags]                  writes <targetDB>.spbidx (tantan-masked residues; the k-mer
 //                                                                   table itself is rebuilt on the device), picked up by the above
 // and the set-level stages that consume the alignment DB in predictmatch (data/predictmatch.sh:57-116; setscore.h):
@@ -877,6 +879,99 @@ void search_dbs(const Params &p, const std::string &qName, const std::string &tN
     }
 }
 
+// spb200 extractframes <nuclSeqDB> <outDB> [--min-length 9 --threads N]
+// The two query-preparation steps createsetdb runs back to back for spacers (data/createsetdb.sh:88-113):
+//   extractorfs <db>_nucl <db>_nucl_orf --min-length 9 --orf-start-mode 1   (M/util/extractorfs.cpp:19-160)
+//   translatenucs <db>_nucl_orf <db>                                        (M/util/translatenucs.cpp:13-115)
+// fused on the device (spb_spacer_frames): writes <outDB>_nucl_orf (+ _h: the Orf::writeOrfHeader lines, Orf.cpp:440-457) and
+// the amino-acid DB <outDB> (+ _h) with the fragment keys 0..n-1 in the reference's order.
+int run_extractframes(int argc, const char **argv) {
+    Params p;
+    int minLength = 9;
+    std::vector<const char *> rest;
+    for (int i = 0; i < argc; i++) {
+        if (i + 1 < argc && std::string(argv[i]) == "--min-length") { minLength = atoi(argv[++i]); continue; }
+        if (i + 1 < argc && (std::string(argv[i]) == "--orf-start-mode" || std::string(argv[i]) == "--create-lookup")) { ++i; continue; }
+        rest.push_back(argv[i]);
+    }
+    parse_args((int)rest.size(), rest.data(), 2, 2, p);
+    DBReader in;
+    in.open(p.db[0]);
+    if (in.dbtype() != 1) throw Fail("extractframes: " + p.db[0] + " is not a nucleotide database");
+    const size_t n = in.size();
+    // entries in key order (extractorfs walks the DB by id); numeric nucleotides 0..3 = A C G T, everything else ambiguous
+    std::vector<uint64_t> off(n + 1, 0);
+    for (size_t i = 0; i < n; i++) off[i + 1] = off[i] + (in.byKey(i).length >= 2 ? in.byKey(i).length - 2 : 0);
+    std::vector<uint8_t> nt(off[n] + 1);
+    uint8_t code[256];
+    memset(code, 4, sizeof(code));
+    code['A'] = code['a'] = 0; code['C'] = code['c'] = 1; code['G'] = code['g'] = 2; code['T'] = code['t'] = 3; code['U'] = code['u'] = 3;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long i = 0; i < (long)n; i++) {
+        const char *d = in.data(in.byKey((size_t)i));
+        for (uint64_t k = off[i]; k < off[i + 1]; k++) nt[k] = code[(unsigned char)d[k - off[i]]];
+    }
+    Engine E;
+    check(spb_ctx_create(p.device, &E.ctx), "spb_ctx_create");
+    spb_frames_result *fr = nullptr;
+    check(spb_spacer_frames(E.ctx, nt.data(), off.data(), (uint32_t)n, minLength, 32734, 0, &fr), "spb_spacer_frames");
+    log_line(p, "Fragments: %u from %zu sequences, %.3f ms on the device", fr->n_frames, n, fr->kernel_ms);
+    // Orf::iupacReverseComplementTable (M/commons/Orf.cpp:48-52), letters only
+    static const char *comp = "TVGH..CD..M.KN...YSAABW.R.";   // complements of 'A'..'Z'
+    auto complement = [&](char c) -> char {
+        if (c >= 'A' && c <= 'Z') return comp[c - 'A'];
+        if (c >= 'a' && c <= 'z') return (char)tolower(comp[c - 'a']);
+        return '.';
+    };
+    DBWriter wNuc, wNucH, wAA, wAAH;
+    wNuc.open(p.db[1] + "_nucl_orf", 1, p.threads);
+    wNucH.open(p.db[1] + "_nucl_orf_h", DBTYPE_GENERIC_DB, p.threads);
+    wAA.open(p.db[1], DBTYPE_AMINO_ACIDS, p.threads);
+    wAAH.open(p.db[1] + "_h", DBTYPE_GENERIC_DB, p.threads);
+    static const char AAS[] = "ACDEFGHIKLMNPQRSTVWYX";
+    const uint32_t F = fr->n_frames;
+#pragma omp parallel num_threads(p.threads)
+    {
+        int th = 0;
+#ifdef _OPENMP
+        th = omp_get_thread_num();
+#endif
+        std::string buf;
+        char hdr[64];
+#pragma omp for schedule(static)
+        for (long f = 0; f < (long)F; f++) {
+            const spb_orf &o = fr->orfs[f];
+            const DBEntry &e = in.byKey(o.contig);
+            const char *d = in.data(e);
+            const long L = (long)(off[o.contig + 1] - off[o.contig]);
+            buf.clear();
+            if (o.strand == 0) {
+                buf.assign(d + o.from, (size_t)(o.to - o.from + 1));
+            } else {
+                for (uint32_t x = o.from; x <= o.to; x++) buf.push_back(complement(d[L - 1 - (long)x]));
+            }
+            buf.push_back('\n');
+            wNuc.write(th, (uint32_t)f, buf.data(), buf.size());
+            // positions on the forward strand of the contig (extractorfs.cpp:93-99), Orf::writeOrfHeader
+            long from = o.from, to = o.to;
+            if (o.strand == 1) { from = (L - 1) - from; to = (L - 1) - to; }
+            const int flags = (int)o.incomplete_start | ((int)o.incomplete_end << 1);
+            int hl = sprintf(hdr, "%u\t%ld%c%ld", e.key, from, from < to ? '+' : '-', labs(from - to));
+            if (flags) hl += sprintf(hdr + hl, "\t%d", flags);
+            hdr[hl++] = '\n';
+            wNucH.write(th, (uint32_t)f, hdr, (size_t)hl);
+            wAAH.write(th, (uint32_t)f, hdr, (size_t)hl);
+            buf.clear();
+            for (uint64_t k = fr->offsets[f]; k < fr->offsets[f + 1]; k++) buf.push_back(AAS[fr->residues[k] <= 20 ? fr->residues[k] : 20]);
+            buf.push_back('\n');
+            wAA.write(th, (uint32_t)f, buf.data(), buf.size());
+        }
+    }
+    wNuc.close(); wNucH.close(); wAA.close(); wAAH.close();
+    spb_free_frames_result(fr);
+    return 0;
+}
+
 // spb200 createindex <targetDB> <tmpDir> [prefilter flags]   (M/workflow/CreateIndex.cpp; host-only: no GPU needed)
 int run_createindex(int argc, const char **argv) {
     Params p;
@@ -1114,7 +1209,7 @@ int run_showparams(int argc, const char **argv) {
 
 int main(int argc, const char **argv) {
     if (argc < 2) {
-        fprintf(stderr, "spb200 (%s): prefilter | align | search | createindex | besthitperset | mergeresultsbyset | combinescore | filtermatchbyfdr | predictmatch | proteinaln2nucl | combineprotnuclaln | dumpmatrix | dbcopy | showparams\n", spb_version());
+        fprintf(stderr, "spb200 (%s): prefilter | align | search | createindex | extractframes | besthitperset | mergeresultsbyset | combinescore | filtermatchbyfdr | predictmatch | proteinaln2nucl | combineprotnuclaln | dumpmatrix | dbcopy | showparams\n", spb_version());
         return 1;
     }
     const std::string cmd = argv[1];
@@ -1123,6 +1218,7 @@ int main(int argc, const char **argv) {
         if (cmd == "align") return run_align(argc, argv);
         if (cmd == "search") return run_search(argc, argv);
         if (cmd == "createindex") return run_createindex(argc, argv);
+        if (cmd == "extractframes") return run_extractframes(argc, argv);
         if (cmd == "besthitperset") return run_besthitperset(argc, argv);
         if (cmd == "mergeresultsbyset") return run_mergeresultsbyset(argc, argv);
         if (cmd == "combinescore") return run_combinescore(argc, argv);

@@ -134,3 +134,37 @@ def test_gpu_frames_resident_search(searcher):
     x = sorted(qres[int(qoff[i]):int(qoff[i + 1])].tobytes() for i in range(len(qoff) - 1))
     y = sorted(sres[int(soff[i]):int(soff[i + 1])].tobytes() for i in range(len(soff) - 1))
     assert x == y
+
+
+@pytest.mark.gpu
+def test_gpu_extractframes_host_command(tmp_path):
+    """spb200 extractframes = extractorfs --min-length 9 --orf-start-mode 1 + translatenucs (data/createsetdb.sh:88-113) on the
+    reference's own input: amino-acid DB and ORF headers byte-identical to the reference's, nucleotide ORF DB consistent"""
+    import subprocess
+    from spacepharer_b200 import dbio, synth
+    from test_host_cli import BIN
+    inp, aa, hdr = _golden()
+    db = str(tmp_path / "q_nucl")
+    dbio.write_db(db, ((k, (s + "\n").encode()) for k, s in inp), dbio.DBTYPE_NUCLEOTIDES)
+    out = str(tmp_path / "q")
+    r = subprocess.run([BIN, "extractframes", db, out, "--min-length", "9", "--orf-start-mode", "1", "--create-lookup", "1", "--threads", "3"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got_aa = dbio.read_entries(out)
+    assert sorted(got_aa) == list(range(len(aa)))
+    assert [got_aa[i].decode().rstrip("\n") for i in range(len(aa))] == aa
+    assert dbio.read_dbtype(out) == dbio.DBTYPE_AMINO_ACIDS and dbio.read_dbtype(out + "_nucl_orf") == dbio.DBTYPE_NUCLEOTIDES
+    for h in (out + "_nucl_orf_h", out + "_h"):
+        got_h = dbio.read_entries(h)
+        assert [got_h[i].decode().rstrip("\n") for i in range(len(hdr))] == hdr
+    # the nucleotide fragments translate to the peptides (canonical table; ambiguous codons -> X)
+    nuc = dbio.read_entries(out + "_nucl_orf")
+    import ctypes as C
+    L = O.lib()
+    L.spo_translate_codon.argtypes = [C.c_char_p]
+    L.spo_translate_codon.restype = C.c_char
+    for i in range(len(aa)):
+        s = nuc[i].decode().rstrip("\n")
+        assert len(s) == 3 * len(aa[i]), i
+        tr = "".join(L.spo_translate_codon(s[j:j + 3].encode()).decode() for j in range(0, len(s), 3))
+        assert tr == aa[i], i
