@@ -1795,7 +1795,15 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
         // stage 1: team kernels.  TEAM = 1 over the whole batch (persistent grid, dynamic query scheduler); the queries it
         // flags ST_TEAM (long similar-k-mer lists) are listed on the device and taken by the TEAM = 8 launch, which reads
         // the list length from device memory -- no host round trip in between.
-        const int soloBlocks = c->n_sm * 8, teamBlocks = c->n_sm * 4;
+        int soloPerSm = 8;
+        if (const char *e = getenv("SPB_SOLO_CTAS")) soloPerSm = std::max(1, std::min(8, atoi(e)));   // tuning aid (L1 carve-out experiments)
+        if (const char *e = getenv("SPB_SOLO_CARVEOUT"))    // percent of the 228 KB given to shared memory (the rest is L1)
+            cudaFuncSetAttribute(prefilter_team_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+        int teamPerSm = 4;
+        if (const char *e = getenv("SPB_TEAM_CTAS")) teamPerSm = std::max(1, std::min(4, atoi(e)));
+        if (const char *e = getenv("SPB_TEAM_CARVEOUT"))
+            cudaFuncSetAttribute(prefilter_team_kernel<PW_TEAM>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+        const int soloBlocks = c->n_sm * soloPerSm, teamBlocks = c->n_sm * teamPerSm;
         A.direct = c->d_direct.as<ulonglong2>();
         uint32_t hitCapSolo = 8192, hitCapTeam = 32768;
         A.kCapSolo = 4096;
