@@ -670,9 +670,7 @@ template <int BMW, int NRUNS>
 struct QuerySmem {
     uint32_t seen1[BMW], seen2[BMW];
     Run runs_[NRUNS];                    // TEAM = 1 keeps its runs in the (then idle) sort buffer of the warp instead
-    float cb[PW_MAXL];
     uint16_t x1[PW_MAXL], x2[PW_MAXL];   // first / second 3-mer of every window
-    uint16_t n1[PW_MAXL];                // outer neighbours of every window
     uint16_t rowbase[PW_MAXL + 2];       // exclusive prefix of n1
     short thr[PW_MAXL];
     uint8_t q[PW_MAXL];
@@ -680,9 +678,12 @@ struct QuerySmem {
     uint32_t v_qi, v_K, v_nRuns, v_slow, v_why, v_nHits, v_nSurv, v_nFin;
     int v_minCorr;
 };
+// Shared memory is budgeted per warp: 8 CTAs x 4 warps must fit the 164 KB carve-out, which leaves 64 KB of L1 for the row3
+// reads (with the 196 KB carve-out the kernel is 12 % slower).  Set-up temporaries therefore live in buffers that are idle at
+// that time: the composition bias (float[64]) and the outer-neighbour counts (u16[64]) in the head of the sort buffer (dead
+// before the runs are written there), the capped per-record scores (u8[256]) behind the bucket counters in seen1.
 struct WorkSmem {
     uint64_t surv[PW_SCAP];
-    uint8_t cnt[PW_SCAP];
 };
 
 __device__ __noinline__ void warp_bitonic_u64(uint64_t *a, int n_pow2) {
@@ -833,6 +834,10 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
     QuerySmem<BMW, SOLO ? 1 : PW_RUNCAP> &S = s_qs[SOLO ? wid : 0];
     WorkSmem &W = s_ws[wid];
     Run *const runs = SOLO ? reinterpret_cast<Run *>(W.surv) : S.runs_;
+    float *const cbuf = reinterpret_cast<float *>(W.surv);                       // [PW_MAXL], set-up only
+    uint16_t *const n1buf = reinterpret_cast<uint16_t *>(W.surv) + 2 * PW_MAXL;   // [PW_MAXL] behind it, set-up only
+    uint8_t *const wcnt = reinterpret_cast<uint8_t *>(S.seen1) + 768 + (SOLO ? 0 : tw * PW_SCAP);   // [PW_SCAP], group phase
+    static_assert(PW_MAXL * 4 + PW_MAXL * 2 <= PW_SCAP * 8 && 768 + (SOLO ? 1 : TEAM) * PW_SCAP <= BMW * 4, "aliased buffers fit");
     auto team_sync = [&]() { if (SOLO) __syncwarp(); else __syncthreads(); };
     constexpr uint32_t FCAP = SOLO ? PW_FCAP_SOLO : PW_FCAP_TEAM;
     // hit records | records grouped by target bucket | per-target winners (final key, truncation key)
@@ -887,7 +892,7 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                         for (int a = 0; a < SPB_ALPHABET; a++)
                             d = __double2float_rn(__dadd_rn((double)d, __dmul_rn(A.mat->pback_seed[a], (double)(float)row[a])));
                     }
-                    S.cb[i] = d;
+                    cbuf[i] = d;
                     const float t4 = __fdiv_rn(d, 4.0f);
                     const double dd = (d < 0.0f) ? __dsub_rn((double)t4, 0.5) : __dadd_rn((double)t4, 0.5);
                     const signed char cc = (signed char)__double2float_rn(dd);
@@ -902,7 +907,7 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
 #pragma unroll
                     for (int k = 0; k < 6; k++) {
                         hasX = hasX || (S.q[w + A.pat.pos[k]] >= SPB_X);
-                        b = __fadd_rn(b, S.cb[w + A.pat.pos[k]]);
+                        b = __fadd_rn(b, cbuf[w + A.pat.pos[k]]);
                     }
                     const short bias = (short)((b < 0.0f) ? __dsub_rn((double)b, 0.5) : __dadd_rn((double)b, 0.5));
                     const short thr = (short)max(A.kmerThr - (int)bias, 0);
@@ -916,7 +921,7 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                             n1 = (int)__ldg(A.cnt3 + (size_t)x1 * SPB_CNT3_W + max(cut1, -SPB_SCORE_OFF) + SPB_SCORE_OFF);
                     }
                     S.thr[w] = thr;
-                    S.n1[w] = (unsigned short)n1;
+                    n1buf[w] = (unsigned short)n1;
                     S.x1[w] = (unsigned short)x1;
                     S.x2[w] = (unsigned short)x2;
                 }
@@ -924,7 +929,7 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                 uint32_t Rtot = 0;
                 if (lane == 0) {
                     uint32_t acc = 0;
-                    for (int w = 0; w < P; w++) { S.rowbase[w] = (uint16_t)min(acc, 65535u); acc += S.n1[w]; }
+                    for (int w = 0; w < P; w++) { S.rowbase[w] = (uint16_t)min(acc, 65535u); acc += n1buf[w]; }
                     S.rowbase[P] = (uint16_t)min(acc, 65535u);
                     Rtot = acc;
                 }
@@ -1243,7 +1248,7 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                 for (int i = lane; i < nkept; i += 32) {
                     const uint64_t r = W.surv[i];
                     const int sc = ungapped_u16_ool(A.tres, A.toff, (uint32_t)(r >> 32), S.q, L, S.corr, s_m40u, (uint32_t)r & 0xFFFFu);
-                    W.cnt[i] = (uint8_t)min(sc, capScore);
+                    wcnt[i] = (uint8_t)min(sc, capScore);
                 }
                 __syncwarp();
                 for (int c0 = 0; c0 < nkept; c0 += 32) {
@@ -1256,9 +1261,9 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                         const bool head = (i == 0) || ((uint32_t)(W.surv[i - 1] >> 32) != id);
                         if (head) {
                             int bi = i;
-                            uint8_t best = W.cnt[i];
+                            uint8_t best = wcnt[i];
                             for (int j = i + 1; j < nkept && (uint32_t)(W.surv[j] >> 32) == id; j++)
-                                if (W.cnt[j] > best) { best = W.cnt[j]; bi = j; }
+                                if (wcnt[j] > best) { best = wcnt[j]; bi = j; }
                             if ((int)best >= A.minDiag) {
                                 keep = true;
                                 const uint32_t dg = (uint32_t)W.surv[bi] & 0xFFFFu;
