@@ -36,8 +36,10 @@
 
 #include <algorithm>
 #include <stdexcept>
+#include <exception>
 #include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 #ifdef _OPENMP
@@ -824,6 +826,26 @@ void search_dbs(const Params &p, const std::string &qName, const std::string &tN
     spb_align_params ap;
     fill_align_params(p, E, tdb.aminoAcidDBSize(), &ap);
     const size_t nq = Q.keys.size();
+    std::thread formatter;
+    std::exception_ptr fmtError;
+    spb_align_result *prevR = nullptr;
+    spb_nucl_aln *prevNr = nullptr;
+    auto finish_previous = [&]() {
+        if (formatter.joinable()) formatter.join();
+        if (prevNr) spb_free_nucl_result(E.ctx, prevNr);
+        if (prevR) spb_free_align_result(prevR);
+        prevNr = nullptr;
+        prevR = nullptr;
+        if (fmtError) {
+            std::exception_ptr e = fmtError;
+            fmtError = nullptr;
+            std::rethrow_exception(e);
+        }
+    };
+    struct JoinGuard {       // an exception on the GPU path must not leave the formatter running on freed state
+        std::thread &t;
+        ~JoinGuard() { if (t.joinable()) t.join(); }
+    } guard{formatter};
     for (size_t b0 = 0, b1 = 0; b0 < nq; b0 = b1) {
         b1 = std::min(nq, b0 + (size_t)p.batch);
         std::vector<uint64_t> off(b1 - b0 + 1);
@@ -850,33 +872,45 @@ void search_dbs(const Params &p, const std::string &qName, const std::string &tN
             check(spb_nucl_rescore_resident(E.ctx, &np, &nr, &nRows, &ms), "spb_nucl_rescore_resident");
             log_line(p, "Nucleotide re-alignment: %llu rows re-scored on the device in %.3f ms", (unsigned long long)nRows, ms);
         }
+        // the rows leave the device on a second stream (spb_align_fetch_begin) and are turned into text by a formatter thread
+        // while this thread already drives the next batch through the GPU; results are freed here, by the thread that owns
+        // the context, once the formatter has finished with them
         spb_align_result *r = nullptr;
-        check(spb_align_fetch(E.ctx, &r), "spb_align_fetch");
-        if (!nucl) {
-            format_alignment_rows(p, r, Q, b0, T, [&](int th, size_t i, const std::string &buf) { sink(th, Q.keys[b0 + i], buf); });
-        } else {
-            std::string err;
-            format_alignment_rows(p, r, Q, b0, T, [&](int th, size_t i, const std::string &prot) {
-                std::string nuc, comb;
-                try {
-                    for (uint64_t k = r->offsets[i]; k < r->offsets[i + 1]; k++) {
-                        const spb_aln &a = r->rows[k];
-                        nucl_row_error(nr[k]);
-                        append_nucl_row(nuc, T.keys[a.target], nr[k], r->cigar_ops + a.cigar_off, a.cigar_len);
-                    }
-                    combine_prot_nucl_entry(prot, nuc, comb);
-                } catch (const std::exception &e) {
+        check(spb_align_fetch_begin(E.ctx, &r), "spb_align_fetch_begin");
+        finish_previous();
+        prevR = r;
+        prevNr = nr;
+        formatter = std::thread([&, r, nr, b0]() {
+            try {
+                check(spb_align_fetch_wait(r), "spb_align_fetch_wait");
+                if (!nucl) {
+                    format_alignment_rows(p, r, Q, b0, T, [&](int th, size_t i, const std::string &buf) { sink(th, Q.keys[b0 + i], buf); });
+                } else {
+                    std::string err;
+                    format_alignment_rows(p, r, Q, b0, T, [&](int th, size_t i, const std::string &prot) {
+                        std::string nuc, comb;
+                        try {
+                            for (uint64_t k = r->offsets[i]; k < r->offsets[i + 1]; k++) {
+                                const spb_aln &a = r->rows[k];
+                                nucl_row_error(nr[k]);
+                                append_nucl_row(nuc, T.keys[a.target], nr[k], r->cigar_ops + a.cigar_off, a.cigar_len);
+                            }
+                            combine_prot_nucl_entry(prot, nuc, comb);
+                        } catch (const std::exception &e) {
 #pragma omp critical
-                    err = e.what();
+                            err = e.what();
+                        }
+                        if (extra) (*extra)(th, Q.keys[b0 + i], prot, nuc);
+                        sink(th, Q.keys[b0 + i], comb);
+                    });
+                    if (!err.empty()) throw Fail(err);
                 }
-                if (extra) (*extra)(th, Q.keys[b0 + i], prot, nuc);
-                sink(th, Q.keys[b0 + i], comb);
-            });
-            spb_free_nucl_result(E.ctx, nr);
-            if (!err.empty()) { spb_free_align_result(r); throw Fail(err); }
-        }
-        spb_free_align_result(r);
+            } catch (...) {
+                fmtError = std::current_exception();
+            }
+        });
     }
+    finish_previous();
 }
 
 // spb200 extractframes <nuclSeqDB> <outDB> [--min-length 9 --threads N]

@@ -176,6 +176,14 @@ def test_predictmatch_default_synthetic_arrays(sets_dbs, tmp_path):
                  ("aggregate", "nucl_aggregate"), ("cScore", "nucl_cScore"), ("cScore_rev", "nucl_cScore_rev"), ("match", "nucl_match")):
         assert rows_of(out + "/" + n) == read_dump(os.path.join(SETS, g + ".txt.gz")), n
     assert len(read_dump(os.path.join(SETS, "nucl_match.txt.gz"))) > 10
+    # several batches: the formatter thread of batch k runs while batch k+1 is on the GPU -- same DBs
+    out2 = out + "/b"
+    os.makedirs(out2)
+    r = run("predictmatch", w + "/qsetdb", w + "/targets", w + "/targets_rev", out2 + "/match", out2, "--threads", "3", "--keep-intermediate", "1",
+            "--fdr", "0.05", "--batch", "1500")
+    assert r.stdout.count("Nucleotide re-alignment") >= 2 * 4
+    for n in ("prot_result", "nucl_result_rev", "result", "result_rev", "cScore", "match"):
+        assert dbio.read_entries(out2 + "/" + n) == dbio.read_entries(out + "/" + n), n
     # without the nucleotide DBs the default branch fails loudly instead of silently searching proteins only
     for f in os.listdir(w):
         if "_nucl_orf" in f:
