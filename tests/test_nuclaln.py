@@ -245,3 +245,40 @@ def test_python_mirror_resident_rescore_vs_oracle():
         with pytest.raises(Exception):
             api.format_nucl_rows(bad[:1], rows[:1], cig)
     s.close()
+
+
+@pytest.mark.gpu
+def test_nucl_rescore_error_codes_and_lanes():
+    """rows that do not fit their nucleotide entries are flagged, never read out of bounds; a lane re-scores on the parent's
+    resident nucleotide targets"""
+    from spacepharer_b200 import api, capi
+    tres, toff, set_of = synth.make_targets(n_genomes=20, seed=6)
+    tnt = synth.back_translate(tres, toff)
+    s = api.Searcher(device=0)
+    masked, _ = api.tantan_mask(s.seed, tres, toff)
+    s.build_index(masked, toff)
+    s.set_align_targets(tres, toff)
+    s.set_nucl_targets(tnt)
+    q_aa = tres[int(toff[3]):int(toff[3]) + 12].copy()
+    qnt = [synth.back_translate(q_aa, np.array([0, 12], dtype=np.uint64))[0]]
+    s.set_nucl_queries(qnt)
+    rows = np.zeros(4, dtype=np.dtype(capi.Aln))
+    cig = b"M" * 12
+    for i in range(4):
+        rows[i]["query"], rows[i]["target"] = 0, 3
+        rows[i]["q_start"], rows[i]["q_end"], rows[i]["t_start"], rows[i]["t_end"] = 0, 11, 0, 11
+        rows[i]["cigar_off"], rows[i]["cigar_len"] = 0, 12
+    rows[1]["q_start"] = 5                      # 12 aligned columns from codon 5 leave a 12-codon query
+    rows[2]["target"] = len(toff) + 7           # no such target
+    rows[3]["cigar_off"] = 100                  # backtrace outside the buffer
+    n, _ = s.nucl_rescore(3 * int(toff[-1]), rows=rows, cigar=cig)
+    assert [int(x) for x in n["err"]] == [0, 2, 3, 3]
+    assert int(n[0]["n_ident"]) == 36 and int(n[0]["raw_score"]) == 72 and int(n[0]["aln_len"]) == 36
+    ln = s.lane()
+    ln.set_nucl_queries(qnt)
+    n2, _ = ln.nucl_rescore(3 * int(toff[-1]), rows=rows[:1], cigar=cig)
+    assert n2[0].tobytes() == n[0].tobytes()
+    with pytest.raises(capi.SpbError, match="lane"):
+        ln.set_nucl_targets(tnt)
+    ln.close()
+    s.close()
