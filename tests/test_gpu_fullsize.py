@@ -6,11 +6,14 @@ The oracle cannot run these sizes whole in seconds, so the CUDA path is checked
     depend on what else is in the batch, nor on the batch order), sortedness of the hit lists
     (QueryMatcher.h:40-50) and of the alignment rows (Matcher.h:156-167), the max-seqs / min-ungapped-score / E-value
     bounds, coordinate bounds and CIGAR consistency (Matcher.cpp:61-187)."""
+import os
+
 import numpy as np
 import pytest
 
 from oracle import pyoracle as O
 import common as Cm
+from conftest import GOLDEN, ROOT
 
 pytestmark = pytest.mark.gpu
 
@@ -214,3 +217,36 @@ def test_config4_one_million_spacers_in_one_batch(world):
             assert (big[f] == crows[f]).all(), "%s differs in chunk %d" % (f, c)
         assert (crows["query"] == big["query"] - lo).all()
         assert (_cigar_concat(cigs, big) == _cigar_concat(np.frombuffer(ccig, dtype=np.uint8), crows)).all(), "CIGARs differ in chunk %d" % c
+
+
+def test_config2_byte_identical_to_the_reference_binary(tmp_path):
+    """BASELINE config 2 at full size -- the workload bench.py measures -- through the spb200 binary: the prefilter DB and the
+    alignment DB are byte-identical to the REFERENCE binary's (tests/golden/config2_digest.json holds the SHA-256 of the
+    reference's DBs in canonical form, written by tools/gen_golden_config2.py; the inputs are regenerated from fixed seeds)"""
+    import hashlib
+    import json
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from gen_golden_config2 import db_digest, write_config2
+    from test_host_cli import ALN_FLAGS, BIN, PREF_FLAGS
+    want = json.load(open(os.path.join(GOLDEN, "config2_digest.json")))
+    w = str(tmp_path)
+    nq, nt = write_config2(w)
+    assert (nq, nt) == (want["n_queries"], want["n_targets"])
+    for args in (["prefilter", w + "/queries", w + "/targets", w + "/pref"] + PREF_FLAGS,
+                 ["align", w + "/queries", w + "/targets", w + "/pref", w + "/aln"] + ALN_FLAGS):
+        r = subprocess.run([BIN] + args, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    assert db_digest(w + "/pref") == (want["pref_sha256"], want["pref_rows"])
+    assert db_digest(w + "/aln") == (want["aln_sha256"], want["aln_rows"])
+    # the fused search (hit lists stay in HBM) writes the same alignment DB
+    seen, merged = set(), []
+    for lst in (PREF_FLAGS, ALN_FLAGS):
+        for i in range(0, len(lst), 2):
+            if lst[i] not in seen:
+                seen.add(lst[i])
+                merged += [lst[i], lst[i + 1]]
+    r = subprocess.run([BIN, "search", w + "/queries", w + "/targets", w + "/fused"] + merged + ["--batch", "10000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert db_digest(w + "/fused") == (want["aln_sha256"], want["aln_rows"])
