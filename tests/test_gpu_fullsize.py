@@ -250,3 +250,34 @@ def test_config2_byte_identical_to_the_reference_binary(tmp_path):
     r = subprocess.run([BIN, "search", w + "/queries", w + "/targets", w + "/fused"] + merged + ["--batch", "10000"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert db_digest(w + "/fused") == (want["aln_sha256"], want["aln_rows"])
+
+
+def test_config4_one_million_spacers_byte_identical_to_the_reference_binary(tmp_path):
+    """BASELINE config 4 on one GPU: 1 000 000 synthetic spacers (3 789 911 frames) against the 495 567-ORF set through the
+    spb200 binary -- 42.8 M prefilter hits and 13.9 M alignment rows, byte-identical to the reference binary's DBs
+    (tests/golden/config4_digest.json).  The fused search runs four batches with the formatter thread overlapping the GPU."""
+    import json
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from gen_golden_config2 import db_digest, write_config2
+    from test_host_cli import ALN_FLAGS, BIN, PREF_FLAGS
+    want = json.load(open(os.path.join(GOLDEN, "config4_digest.json")))
+    w = str(tmp_path)
+    nq, nt = write_config2(w, want["spacers"])
+    assert (nq, nt) == (want["n_queries"], want["n_targets"])
+    threads = str(min(16, os.cpu_count() or 1))
+    pf = [threads if PREF_FLAGS[i - 1] == "--threads" else x for i, x in enumerate(PREF_FLAGS)]
+    r = subprocess.run([BIN, "prefilter", w + "/queries", w + "/targets", w + "/pref"] + pf, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert db_digest(w + "/pref") == (want["pref_sha256"], want["pref_rows"])
+    os.remove(w + "/pref")
+    seen, merged = set(), []
+    for lst in (PREF_FLAGS, ALN_FLAGS):
+        for i in range(0, len(lst), 2):
+            if lst[i] not in seen:
+                seen.add(lst[i])
+                merged += [lst[i], threads if lst[i] == "--threads" else lst[i + 1]]
+    r = subprocess.run([BIN, "search", w + "/queries", w + "/targets", w + "/aln"] + merged, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert db_digest(w + "/aln") == (want["aln_sha256"], want["aln_rows"])
