@@ -282,3 +282,24 @@ def test_nucl_rescore_error_codes_and_lanes():
         ln.set_nucl_targets(tnt)
     ln.close()
     s.close()
+
+
+@pytest.mark.gpu
+def test_predictmatch_default_at_scale_matches_reference_digests(tmp_path):
+    """BASELINE config 3 at a larger scale (2000 genomes = 124 k ORFs + reversed control, 3000 CRISPR arrays = 153 k frames): the
+    reference's DEFAULT predictmatch (search, nucleotide re-alignment, set stages, FDR filter) run module by module with the
+    reference binary vs the fused `spb200 predictmatch`; every result DB has the reference's SHA-256 (207 k alignment rows,
+    198 k combined set scores, 1160 reported matches; tests/golden/config3_digest.json, tools/gen_golden_config3.py)"""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "tools"))
+    from gen_golden_config2 import db_digest
+    want = json.load(open(os.path.join(GOLDEN, "config3_digest.json")))
+    w, out = str(tmp_path / "db"), str(tmp_path / "out")
+    os.makedirs(w)
+    os.makedirs(out)
+    assert synth.write_array_search_dbs(w, nucl=True, **want["shape"]) == want["inputs_sha256"]
+    run("predictmatch", w + "/qsetdb", w + "/targets", w + "/targets_rev", out + "/match", out, "--threads", "8", "--keep-intermediate", "1",
+        "--fdr", "0.05", "--batch", "50000")
+    for n in ("prot_result", "nucl_result", "result", "result_rev", "aggregate", "cScore", "cScore_rev", "match"):
+        assert db_digest(out + "/" + n) == (want[n]["sha256"], want[n]["rows"]), n
