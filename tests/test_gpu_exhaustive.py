@@ -155,3 +155,31 @@ def test_exhaustive_superset_of_prefilter_path():
         extra += len(set(b) - set(a))
     assert est["exhaustive"]["n_kept"] >= len(erows)
     assert extra > 0
+
+
+def test_exhaustive_search_at_scale_matches_reference_digest(tmp_path):
+    """BASELINE config 5 at medium scale: 593 frames x 62 177 ORFs = 36.9 M pairs, no k-mer stage.  The reference side is its `align`
+    over an all-pairs prefilter DB; `spb200 search --exhaustive-search 1` writes the same alignment DB byte for byte (68 005 rows;
+    tests/golden/config5_digest.json, tools/gen_golden_config5.py)"""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import GOLDEN, ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from gen_golden_config2 import db_digest
+    from gen_golden_config5 import write_config5
+    from test_host_cli import ALN_FLAGS, BIN, PREF_FLAGS
+    want = json.load(open(os.path.join(GOLDEN, "config5_digest.json")))
+    w = str(tmp_path)
+    assert write_config5(w, **want["shape"]) == (want["n_queries"], want["n_targets"])
+    seen, merged = set(), []
+    for lst in (PREF_FLAGS, ALN_FLAGS):
+        for i in range(0, len(lst), 2):
+            if lst[i] not in seen:
+                seen.add(lst[i])
+                merged += [lst[i], lst[i + 1]]
+    r = subprocess.run([BIN, "search", w + "/queries", w + "/targets", w + "/aln", "--exhaustive-search", "1"] + merged, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Exhaustive search" in r.stdout
+    assert db_digest(w + "/aln") == (want["aln_sha256"], want["aln_rows"])
