@@ -186,3 +186,58 @@ def test_two_gpus_equal_one(tmp_path, mode):
     for f in ("query", "target", "score", "bits", "q_start", "q_end", "t_start", "t_end", "n_ident", "aln_len", "cigar_len"):
         assert (rows[f] == rows0[f]).all(), f
     assert np.allclose(rows["eval"], rows0["eval"], rtol=1e-12)
+
+
+def _rank_main_config2(rank, world, port, out_dir):
+    import pickle
+    import torch
+    import torch.distributed as dist
+    from spacepharer_b200 import api, multigpu, synth
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    tres, toff, _ = synth.make_targets(n_genomes=8000)
+    qres, qoff, _ = synth.make_query_frames(10000, tres, toff)
+    eng = multigpu.ShardedSearcher(device=rank, rank=rank, world=world, split_mode="target")
+    masked, _ = api.tantan_mask(eng.searcher.seed, tres, toff)
+    eng.load_targets(masked, tres, toff)
+    res = eng.search_host(qres, qoff, int(toff[-1]))
+    rows = res["rows"]
+    lines = api.format_align_rows(rows, res["cigar"], np.diff(qoff).astype(np.int64), np.diff(toff).astype(np.int64))
+    with open(os.path.join(out_dir, "cfg2_r%d.pkl" % rank), "wb") as f:
+        pickle.dump((rows["query"].astype(np.int64), lines), f)
+    eng.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_target_split_config2_equals_the_reference_binary(tmp_path):
+    """BASELINE config 2 with the targets sharded over two GPUs (index per shard, hit lists exchanged over NCCL, merged on the
+    owning GPU, aligned there): the union of the ranks' alignment rows is, byte for byte, the UNSPLIT reference binary's
+    alignment DB (tests/golden/config2_digest.json)"""
+    import hashlib
+    import json
+    import pickle
+    import torch
+    import torch.multiprocessing as mp
+    from conftest import GOLDEN
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    want = json.load(open(os.path.join(GOLDEN, "config2_digest.json")))
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    mp.spawn(_rank_main_config2, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    entries = {}
+    n_rows = 0
+    for r in range(2):
+        qs, lines = pickle.load(open(str(tmp_path / ("cfg2_r%d.pkl" % r)), "rb"))
+        for q, line in zip(qs, lines):
+            entries.setdefault(int(q), []).append(line)
+        n_rows += len(lines)
+    h = hashlib.sha256()
+    for k in range(want["n_queries"]):
+        h.update(b"%d\n" % k)
+        h.update("".join(x + "\n" for x in entries.get(k, [])).encode())
+    assert n_rows == want["aln_rows"]
+    assert h.hexdigest() == want["aln_sha256"]
