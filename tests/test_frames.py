@@ -168,3 +168,25 @@ def test_gpu_extractframes_host_command(tmp_path):
         assert len(s) == 3 * len(aa[i]), i
         tr = "".join(L.spo_translate_codon(s[j:j + 3].encode()).decode() for j in range(0, len(s), 3))
         assert tr == aa[i], i
+
+
+@pytest.mark.gpu
+def test_gpu_extractframes_at_scale_matches_reference_digests(tmp_path):
+    """200 000 nucleotide spacers (some with ambiguous bases) -> 759 138 fragments: the nucleotide ORF DB, its header DB and the
+    amino-acid query DB written by `spb200 extractframes` have the SHA-256 of the reference's extractorfs + translatenucs output
+    (tests/golden/frames_digest.json, tools/gen_golden_frames_scale.py)"""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from gen_golden_config2 import db_digest
+    from gen_golden_frames_scale import write_spacer_db
+    from test_host_cli import BIN
+    want = json.load(open(os.path.join(GOLDEN, "frames_digest.json")))
+    db, out = str(tmp_path / "sp_nucl"), str(tmp_path / "q")
+    write_spacer_db(db, **want["shape"])
+    r = subprocess.run([BIN, "extractframes", db, out, "--min-length", "9", "--orf-start-mode", "1", "--threads", "8"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for name, path in (("aa", out), ("nucl_orf_h", out + "_nucl_orf_h"), ("nucl_orf", out + "_nucl_orf")):
+        assert db_digest(path) == (want[name]["sha256"], want[name]["rows"]), name
