@@ -79,7 +79,7 @@ struct Params {
     // spb200-specific
     int device = 0, binSize = 0, byteLanes = 32, wordLanes = 16;
     std::string gumbel, gumbelNucl;
-    long batch = 1000000;
+    long batch = 250000;       // frames per GPU pass: formatting of batch k overlaps the kernels of batch k+1 (1 M spacers: 4.2 -> 3.7 s)
     // set-level stages (M/commons/Parameters.cpp:217,2277; src/commons/LocalParameters.h:75-77,171-176)
     int simpleBestHit = 1, reportFdr = 0, performNuclAln = 1, keepIntermediate = 0;
     // 1: no k-mer stage, Smith-Waterman of every query against every target (BASELINE config 5; the result of the reference's
