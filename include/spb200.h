@@ -111,6 +111,7 @@ typedef struct spb_prefilter_result {
     double kernel_ms;        /* device time of the match kernel(s) */
     double total_ms;         /* device time of the whole resident stage */
     uint64_t algo_bytes;     /* algorithmic bytes moved by the match kernel */
+    double expand_ms, lookup_ms, bookkeep_ms;   /* device time of the three kernel classes inside kernel_ms */
 } spb_prefilter_result;
 
 int spb_prefilter(spb_ctx *ctx, const uint8_t *q_residues, const uint64_t *q_offsets, uint32_t Q,

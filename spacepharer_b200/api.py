@@ -246,7 +246,8 @@ class Searcher:
     def _pref_stats(R):
         return dict(n_hits=int(R.n_hits), n_kmers=int(R.n_kmers), n_db_matches=int(R.n_db_matches),
                     n_events=int(R.n_events), n_slow_path=int(R.n_slow_path), kernel_ms=float(R.kernel_ms),
-                    total_ms=float(R.total_ms), algo_bytes=int(R.algo_bytes))
+                    total_ms=float(R.total_ms), algo_bytes=int(R.algo_bytes), expand_ms=float(R.expand_ms),
+                    lookup_ms=float(R.lookup_ms), bookkeep_ms=float(R.bookkeep_ms))
 
     @staticmethod
     def _aln_stats(R):

@@ -32,7 +32,8 @@ class PrefilterResult(C.Structure):
     _fields_ = [("n_queries", C.c_uint32), ("offsets", C.POINTER(C.c_uint64)), ("hits", C.POINTER(Hit)),
                 ("n_hits", C.c_uint64), ("n_kmers", C.c_uint64), ("n_db_matches", C.c_uint64),
                 ("n_events", C.c_uint64), ("n_slow_path", C.c_uint64), ("kernel_ms", C.c_double),
-                ("total_ms", C.c_double), ("algo_bytes", C.c_uint64)]
+                ("total_ms", C.c_double), ("algo_bytes", C.c_uint64), ("expand_ms", C.c_double),
+                ("lookup_ms", C.c_double), ("bookkeep_ms", C.c_double)]
 
 
 class AlignParams(C.Structure):

@@ -99,7 +99,7 @@ int spb_ctx_create_lane(spb_ctx *parent, spb_ctx **out) {
     c->T = parent->T; c->n_res = parent->n_res; c->span = parent->span;
     memcpy(c->pat, parent->pat, sizeof(c->pat));
     c->d_tres = parent->d_tres.view(); c->d_toff = parent->d_toff.view(); c->d_koff = parent->d_koff.view();
-    c->d_post = parent->d_post.view(); c->d_direct = parent->d_direct.view();
+    c->d_post = parent->d_post.view(); c->d_direct = parent->d_direct.view(); c->d_kbits = parent->d_kbits.view();
     c->d_row3 = parent->d_row3.view(); c->d_cnt3 = parent->d_cnt3.view();
     c->n_post = parent->n_post; c->n_kmers_nonempty = parent->n_kmers_nonempty; c->build_ms = parent->build_ms;
     c->have_aln_targets = parent->have_aln_targets;
@@ -119,11 +119,12 @@ void spb_ctx_destroy(spb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    spb::DevBuf *bufs[] = {&c->d_mat, &c->d_tres, &c->d_toff, &c->d_koff, &c->d_post, &c->d_direct, &c->d_row3, &c->d_cnt3,
+    spb::DevBuf *bufs[] = {&c->d_mat, &c->d_tres, &c->d_toff, &c->d_koff, &c->d_post, &c->d_direct, &c->d_kbits, &c->d_row3, &c->d_cnt3,
                            &c->d_ares, &c->d_aoff, &c->d_akeys, &c->d_q, &c->d_qoff, &c->d_qoff64, &c->d_qorder, &c->d_hits, &c->d_hits_alt, &c->d_hitoff, &c->d_hit_tkeys, &c->s_tk,
                            &c->d_pairoff, &c->d_pairT, &c->d_pairQ, &c->d_pairout, &c->d_acc, &c->d_cig, &c->d_rows, &c->d_rowoff, &c->d_st_rows, &c->d_st_cig, &c->d_st_off, &c->d_tnt, &c->d_tntoff, &c->d_tntsc, &c->d_qnt, &c->d_qntoff, &c->d_qntsc, &c->d_nrows,
                            &c->s_a, &c->s_b, &c->s_c, &c->s_d, &c->s_e, &c->s_f, &c->s_g, &c->s_h, &c->s_i, &c->s_j,
-                           &c->s_k, &c->s_l, &c->s_m, &c->s_n, &c->s_o, &c->s_p, &c->s_q, &c->s_cub};
+                           &c->s_k, &c->s_l, &c->s_m, &c->s_n, &c->s_o, &c->s_p, &c->s_q, &c->s_cub,
+                           &c->p_recs, &c->p_ctab, &c->p_ccnt, &c->p_harena, &c->p_meta, &c->p_retry};
     for (spb::DevBuf *b : bufs) b->release();
     for (spb::PinBlock &b : c->pins)
         if (b.p) cudaFreeHost(b.p);
@@ -134,6 +135,7 @@ void spb_ctx_destroy(spb_ctx *c) {
         cudaEventDestroy(c->ev_staged);
         cudaEventDestroy(c->ev_stage_free);
     }
+    for (cudaEvent_t ev : c->ev_phase) cudaEventDestroy(ev);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaEventDestroy(c->ev2);

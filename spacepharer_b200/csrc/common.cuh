@@ -114,6 +114,7 @@ struct spb_ctx {
     spb::DevBuf d_koff;           // u32[20^6 + 1] CSR offsets
     spb::DevBuf d_post;           // u64[n_post]: id << 16 | pos
     spb::DevBuf d_direct;         // ulonglong2[20^6] packed direct table: up to two postings inline, else len << 32 | offset (index.cu)
+    spb::DevBuf d_kbits;          // u32[20^6 / 32] occupancy bit per k-mer (pre-check of the gather, L2-resident)
     uint64_t n_post = 0, n_kmers_nonempty = 0;
     spb::DevBuf d_row3;           // u32[8000][8000]: (score + 256) << 16 | 3-mer index
     spb::DevBuf d_cnt3;           // u16[8000][512]: #entries with score >= v
@@ -183,6 +184,15 @@ struct spb_ctx {
     std::vector<spb::PinBlock> pins;
     void *pin_acquire(size_t bytes);
     void pin_release(void *p);
+
+    // ---- prefilter tile arenas (prefilter.cu: expand -> lookup -> bookkeeping) ----
+    spb::DevBuf p_recs;           // u32[chunkCap][256] slot records
+    spb::DevBuf p_ctab;           // uint2[chunkCap] (query, first stream-order number)
+    spb::DevBuf p_ccnt;           // uint2[chunkCap] (first hit record, hits) per chunk
+    spb::DevBuf p_harena;         // u64[] hit records, chunk after chunk
+    spb::DevBuf p_meta;           // QMeta[Q]
+    spb::DevBuf p_retry;          // u32[Q] queries of the next round
+    std::vector<cudaEvent_t> ev_phase;   // five per tile
 
     // ---- scratch (grow-only, reused across calls) ----
     spb::DevBuf s_a, s_b, s_c, s_d, s_e, s_f, s_g, s_h, s_i, s_j, s_k, s_l, s_m, s_n, s_o, s_p, s_q, s_cub;

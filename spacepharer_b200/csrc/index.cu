@@ -8,8 +8,9 @@
 //   toff   u32[T+1]
 //   koff   u32[20^6+1]         CSR offsets, k-mer index = sum a_i 20^i (first residue lowest digit, Indexer.h:20-83)
 //   post   u64[n_post]         (id << 16) | pos, sorted by (kmer, id); one posting per (kmer, target): smallest pos
-//   direct u64[20^6]           packed per-k-mer entry (inline posting when one target, else len|offset) -- the table the
-//                              warp-per-query prefilter gathers from
+//   direct u64x2[20^6]         packed per-k-mer entry (up to two postings inline, else len|offset) -- the table the
+//                              lookup kernel of the prefilter gathers from
+//   kbits  u32[20^6 / 32]      occupancy bit per k-mer (L2-resident pre-check of the gather)
 //   row3   u32[8000][8000]     3-mer neighbours by score desc, ties in cartesian order: (score+256) << 16 | index
 //   cnt3   u16[8000][512]      cnt3[x][v+256] = #neighbours of x with score >= v  (O(1) list lengths)
 #include <cub/cub.cuh>
@@ -148,16 +149,23 @@ __global__ void fill_offsets_kernel(const uint32_t *__restrict__ pk, uint64_t nP
 //   x = 1 << 63 | id << 16 | pos, y = 0    exactly one target: the posting itself (no second memory access)
 //   x, y = 1 << 63 | posting               exactly two targets: both postings inline (ascending id, like the list)
 //   x = len << 32 | offset                 len >= 3 postings at post[offset ..)
+// kbits: one bit per k-mer (set = some target contains it), 8 MB, L2-resident: the lookup kernel asks it first, so the ~46 % of
+// the similar k-mers that no target contains never touch the 1 GB table in DRAM.  SPB_NK is a multiple of 32 and of the block size.
 __global__ void build_direct_kernel(const uint32_t *__restrict__ koff, const uint64_t *__restrict__ post,
-                                    ulonglong2 *__restrict__ direct) {
+                                    ulonglong2 *__restrict__ direct, uint32_t *__restrict__ kbits) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= SPB_NK) return;
-    const uint32_t o0 = koff[k], len = koff[k + 1] - o0;
-    ulonglong2 v = make_ulonglong2(0ull, 0ull);
-    if (len == 1) v.x = (1ull << 63) | post[o0];
-    else if (len == 2) { v.x = (1ull << 63) | post[o0]; v.y = (1ull << 63) | post[o0 + 1]; }
-    else if (len > 2) v.x = ((uint64_t)len << 32) | o0;
-    direct[k] = v;
+    uint32_t len = 0;
+    if (k < SPB_NK) {
+        const uint32_t o0 = koff[k];
+        len = koff[k + 1] - o0;
+        ulonglong2 v = make_ulonglong2(0ull, 0ull);
+        if (len == 1) v.x = (1ull << 63) | post[o0];
+        else if (len == 2) { v.x = (1ull << 63) | post[o0]; v.y = (1ull << 63) | post[o0 + 1]; }
+        else if (len > 2) v.x = ((uint64_t)len << 32) | o0;
+        direct[k] = v;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, len != 0);
+    if ((threadIdx.x & 31) == 0 && k < SPB_NK) kbits[k >> 5] = m;
 }
 
 __global__ void export_postings_kernel(const uint32_t *__restrict__ koff, const uint64_t *__restrict__ post,
@@ -297,8 +305,9 @@ extern "C" int spb_index_build(spb_ctx *c, const uint8_t *residues, const uint64
         if (c->d_post.ensure(64)) { cleanup(); return 1; }
         IDX_CUDA(cudaMemsetAsync(c->d_koff.p, 0, ((size_t)SPB_NK + 2) * 4, st));
     }
-    if (c->d_direct.ensure((size_t)SPB_NK * 16)) { cleanup(); return 1; }
-    build_direct_kernel<<<(SPB_NK + 255) / 256, 256, 0, st>>>(c->d_koff.as<uint32_t>(), c->d_post.as<uint64_t>(), c->d_direct.as<ulonglong2>());
+    if (c->d_direct.ensure((size_t)SPB_NK * 16) || c->d_kbits.ensure((size_t)(SPB_NK / 32) * 4 + 64)) { cleanup(); return 1; }
+    build_direct_kernel<<<(SPB_NK + 255) / 256, 256, 0, st>>>(c->d_koff.as<uint32_t>(), c->d_post.as<uint64_t>(), c->d_direct.as<ulonglong2>(),
+                                                              c->d_kbits.as<uint32_t>());
     IDX_CUDA(cudaGetLastError()); c->n_launches++;
     unsigned long long nonEmpty = 0;
     IDX_CUDA(cudaMemcpyAsync(&nonEmpty, d_nNonEmpty, 8, cudaMemcpyDeviceToHost, st));
@@ -323,7 +332,7 @@ extern "C" int spb_index_stats_get(spb_ctx *c, spb_index_stats *out) {
     out->n_residues = c->n_res;
     out->n_postings = c->n_post;
     out->n_kmers_nonempty = c->n_kmers_nonempty;
-    out->bytes_device = c->d_tres.cap + c->d_toff.cap + c->d_koff.cap + c->d_post.cap + c->d_direct.cap + c->d_row3.cap + c->d_cnt3.cap;
+    out->bytes_device = c->d_tres.cap + c->d_toff.cap + c->d_koff.cap + c->d_post.cap + c->d_direct.cap + c->d_kbits.cap + c->d_row3.cap + c->d_cnt3.cap;
     out->build_ms = c->build_ms;
     return 0;
 }

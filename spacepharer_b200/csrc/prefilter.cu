@@ -70,14 +70,26 @@ struct PrefArgs {
     uint32_t *outCount;      // per query
     uint32_t *status;        // per query: ST_*
     uint32_t *need;          // per query: records needed when status == ST_CAPACITY
-    // warp-per-query kernel
+    // expand / lookup / bookkeeping kernels
     const ulonglong2 *direct;  // [20^6] packed k-mer table, 16 bytes per k-mer (index.cu)
-    uint64_t *hitScratch;    // [warps in the grid][hitCap] hit records, L2-resident
+    const uint32_t *kbits;   // [20^6 / 32] occupancy bit per k-mer
+    uint32_t *recs;          // [chunkCap][256] slot records: k-mer | window << 26
+    uint2 *chunkTab;         // [chunkCap] (query, stream-order number of the chunk's first slot)
+    uint2 *chunkHits;        // [chunkCap] (first hit record of the chunk in hitArena, number of hits | PX_OVER)
+    uint64_t *hitArena;      // [hitArenaCap] hit records, chunk after chunk: id << 32 | k << 16 | 16-bit diagonal
+    unsigned int *hitCursor; // records appended in this tile
+    uint32_t hitArenaCap;
+    struct QMeta *meta;      // [Q]
+    unsigned int *chunkCursor;   // chunks allocated in this tile
+    uint32_t chunkCap;
+    uint64_t *hitScratch;    // [teams in the grid][hitCap + 2 * FCAP] survivors grouped by target bucket | per-target winners
     uint32_t hitCap;
     unsigned int *qCounter;  // dynamic query scheduler
     const unsigned int *nListPtr;  // device: entries of qlist (team launch reads it, no host round trip); NULL: nList
-    uint32_t nList;
-    uint32_t kCapSolo;       // TEAM = 1: queries with more similar k-mers go to the TEAM = 8 launch
+    uint32_t nList, listOff, listStride;   // query of slot s: qlist[listOff + s * listStride]
+    uint32_t hitsSolo;       // TEAM = 1: queries with more hits go to the TEAM = 8 launch
+    uint32_t *teamList;      // queries handed to the TEAM = 8 launch
+    unsigned int *teamCount;
 };
 
 // Truncation key exported with a hit when the target shards of a multi-GPU run are merged (spb_prefilter_merge_shards).
@@ -632,56 +644,291 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
 }
 
 // =========================================================================================================
-// Team prefilter: the production path.  A query is owned by a TEAM of warps -- one warp for the bulk of the spacer
-// frames (TEAM = 1, four independent warps per CTA, no CTA barriers), eight warps (one CTA) for the queries whose
-// similar-k-mer list is too long for one warp to walk without becoming the tail of the launch (TEAM = 8).
+// The production path: three throughput-shaped kernels per tile of queries ("expand -> gather -> bookkeeping").
 //
-// Same rules as prefilter_kernel above, re-laid for memory-level parallelism:
-//  * the index is read through the packed direct table (one 8-byte read per similar k-mer; postings are touched only
-//    for k-mers occurring in >= 2 targets), four independent lookups per lane in flight;
-//  * the hit stream is enumerated ONCE.  All similar k-mers of the query are numbered 0..K-1 in reference order
-//    (window, outer neighbour a, inner neighbour b).  Inner counts are constant over outer neighbours of equal score,
-//    so the numbering is a run-length table in shared memory (one run per distinct outer score of a window: first a,
-//    inner count, first k); lane k finds its run by binary search and derives (a, b) with one division;
-//  * a hit record is one u64 (id << 32 | k << 16 | 16-bit diagonal) whose integer order is (target, stream order).
-//    Records go to a per-team scratch slice in global memory (written and re-read out of L2) while two shared-memory
-//    bitmaps mark targets seen once / twice; only records of targets seen twice (or with 8-bit diagonal 0, quirk B)
-//    are pulled back -- in groups of targets (hash partition) small enough for a warp to sort in shared memory --
-//    and run through the double-hit, de-duplication, ungapped-scoring and best-diagonal rules; the per-target winners
-//    are collected as final sort keys behind the hit records and sorted once at the end.
-// Anything that does not fit (query longer than 64, > 256 runs, >= 65536 k-mers, hit / group / candidate overflow,
-// truncation at max-seqs) is left to prefilter_kernel via status = ST_CAPACITY; queries with more than kCapSolo
-// k-mers are passed from the TEAM = 1 launch to the TEAM = 8 launch via ST_TEAM.  Results are identical on every path.
+//  expand_kernel    one warp per query: composition bias, window thresholds, and the similar k-mers of the query written
+//                   as flat 4-byte SLOT records (k-mer | window << 26) in the reference's enumeration order (window, outer
+//                   neighbour a, inner neighbour b: KmerGenerator.cpp:107-216).  Outer neighbours of equal score share their
+//                   inner count, so the list of a window is a handful of dense rectangles (rows x inner count) whose sizes
+//                   come straight out of the score-count table cnt3 -- no 3-mer row is scanned to find them.  A query owns a
+//                   run of CHUNKS of 256 slots (the tail padded with an invalid k-mer) allocated with one atomic.
+//  lookup_kernel    the gather, one thread per slot over all chunks of the tile -- every query, light or heavy, is the same
+//                   uniform work, so there is no tail and no team launch for long k-mer lists.  A slot asks the 8 MB occupancy
+//                   bitmap (L2-resident) first; only k-mers some target contains read their 16-byte table entry (streaming
+//                   load, does not displace the bitmap / hit records in L2).  Hits (id << 32 | k << 16 | 16-bit diagonal, k =
+//                   slot number inside the query = stream order) are compacted per chunk into the chunk's own region.
+//  bookkeep_kernel  the order-dependent rules per query (TEAM = 1: a warp; TEAM = 8: a CTA for queries with many hits): pass
+//                   over the query's hit chunks marking targets seen once / twice in shared-memory bitmaps, second pass keeping
+//                   the records of targets seen twice (or with 8-bit diagonal 0, quirk B), grouped sort by (target, stream
+//                   order), double-hit rule, de-duplication, ungapped score, per-target winner, final order, output.
+// Anything that does not fit (query longer than 64, >= 65536 k-mers, chunk region / group / candidate overflow, the
+// all-saturated rescoring corner) is left to prefilter_kernel via status = ST_CAPACITY; a query that found the slot arena of
+// its tile full is run again in a later tile (ST_RETRY).  Results are identical on every path.
 // =========================================================================================================
 #define PW_WARPS 4           // independent warps per CTA in the TEAM = 1 launch
 #define PW_TEAM 8            // warps per query in the team launch
 #define PW_MAXL 64
-#define PW_RUNCAP 256
 #define PW_SCAP 256          // records a warp sorts at once
-#define PW_FCAP_SOLO 512     // per-target winners of one query (slots behind the hit records)
+#define PW_FCAP_SOLO 512     // per-target winners of one query (slots behind the grouped records)
 #define PW_FCAP_TEAM 4096
 #define PW_BIG 1024          // TEAM = 8: records the CTA sorts at once in the final stage
-#define PW_U 2               // consecutive similar k-mers per lane (16-byte table entries: as many bytes in flight as 4 x 8)
+#define PX_CH 256            // slots per chunk = threads per CTA of the lookup kernel
+#define PX_OVER 0xFFFFFFFFu   // chunkHits[c].y: the hit arena was full
+#define PX_INVALID 0xFFFFFFFFu
 #define ST_TEAM 4u
+#define ST_RETRY 5u          // slot arena of the tile was full: the query runs in a later tile
+#define ST_PENDING 6u        // expanded, waiting for its bookkeeping
 
-struct Run { uint16_t a0, n2, cum, w; };   // cum holds the first concatenated row index until the prefix pass
+struct QMeta {               // per query, expand -> bookkeeping
+    uint32_t chunk0, nChunks, K;
+    int32_t minCorr;
+    signed char corr[PW_MAXL];
+};
 
-template <int BMW, int NRUNS>
-struct QuerySmem {
-    uint32_t seen1[BMW], seen2[BMW];
-    Run runs_[NRUNS];                    // TEAM = 1 keeps its runs in the (then idle) sort buffer of the warp instead
+struct ExpSmem {
+    float cb[PW_MAXL];
     uint16_t x1[PW_MAXL], x2[PW_MAXL];   // first / second 3-mer of every window
-    uint16_t rowbase[PW_MAXL + 2];       // exclusive prefix of n1
     short thr[PW_MAXL];
+    short best1[PW_MAXL], cut1[PW_MAXL]; // best outer score / lowest outer score of the window (best1 = -32768: no k-mers)
+    uint8_t q[PW_MAXL];
+    uint32_t v_qi;
+};
+
+__device__ __noinline__ int warp_incl_scan_ool(int v) { return warp_incl_scan(v); }
+
+// One window of a query: the rectangles of its similar-k-mer list, 32 outer score values per round (lane = score value,
+// descending = ascending outer rank).  EXPAND = false: returns the number of k-mers.  EXPAND = true: writes the slot records
+// from `dst` on (dst[k] for the k-th k-mer of the window) and returns the same count.
+template <bool EXPAND>
+__device__ __forceinline__ uint32_t window_kmers(const uint32_t *__restrict__ row3, const uint16_t *__restrict__ cnt3, int x1, int x2,
+                                                 int thr, int best1, int cut1, uint32_t w, uint32_t *dst) {
+    const int lane = threadIdx.x & 31;
+    const int vlo = max(cut1, -SPB_SCORE_OFF);
+    const uint16_t *c1 = cnt3 + (size_t)x1 * SPB_CNT3_W;
+    const uint16_t *c2 = cnt3 + (size_t)x2 * SPB_CNT3_W;
+    uint32_t done = 0;
+    for (int v0 = best1; v0 >= vlo; v0 -= 32) {
+        const int v = v0 - lane;
+        uint32_t rows = 0, c = 0, a0 = 0;
+        if (v >= vlo) {
+            const int idx = v + SPB_SCORE_OFF;                    // 0 .. 511
+            const uint32_t ge = __ldg(c1 + idx);                   // outer neighbours with score >= v
+            a0 = (idx + 1 < SPB_CNT3_W) ? (uint32_t)__ldg(c1 + idx + 1) : 0u;   // ... with score > v: rank of the first of score v
+            rows = ge - a0;
+            const int cut2 = thr - v;
+            if (rows && cut2 <= SPB_CNT3_W - SPB_SCORE_OFF - 1) c = __ldg(c2 + max(cut2, -SPB_SCORE_OFF) + SPB_SCORE_OFF);
+        }
+        const uint32_t cnt = rows * c;
+        const uint32_t inc = (uint32_t)warp_incl_scan_ool((int)cnt);
+        const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+        if (EXPAND) {
+            // magic reciprocal of the inner count: p / c == umulhi(p, M) for p < 2^16, 1 < c < 2^16 (M = floor(2^32 / c) + 1)
+            const uint32_t M = (c > 1) ? (0xFFFFFFFFu / c + 1u) : 0u;
+            const uint32_t kst = done + inc - cnt;
+            unsigned m = __ballot_sync(0xffffffffu, cnt != 0);
+            while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t ra0 = __shfl_sync(0xffffffffu, a0, j), rc = __shfl_sync(0xffffffffu, c, j);
+                const uint32_t rn = __shfl_sync(0xffffffffu, cnt, j), rM = __shfl_sync(0xffffffffu, M, j);
+                const uint32_t rk = __shfl_sync(0xffffffffu, kst, j);
+                const uint32_t *row1 = row3 + (size_t)x1 * SPB_N3 + ra0;
+                const uint32_t *row2 = row3 + (size_t)x2 * SPB_N3;
+                for (uint32_t p = (uint32_t)lane; p < rn; p += 32) {
+                    const uint32_t ar = (rc > 1) ? __umulhi(p, rM) : p;
+                    const uint32_t b = p - ar * rc;
+                    const uint32_t i1 = __ldg(row1 + ar) & 0xFFFFu, i2 = __ldg(row2 + b) & 0xFFFFu;
+                    dst[rk + p] = (i1 + 8000u * i2) | (w << 26);
+                }
+            }
+        }
+        done += tot;
+    }
+    return done;
+}
+
+__global__ void __launch_bounds__(PW_WARPS * 32, 8) expand_kernel(PrefArgs A) {
+    __shared__ ExpSmem s_e[PW_WARPS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    ExpSmem &S = s_e[wid];
+    for (;;) {
+        if (lane == 0) S.v_qi = atomicAdd(A.qCounter, 1u);
+        __syncwarp();
+        const uint32_t slot = S.v_qi;
+        __syncwarp();
+        if (slot >= A.nList) break;
+        const uint32_t qi = A.qlist[A.listOff + (size_t)slot * A.listStride];
+        const uint32_t qo = A.qoff[qi];
+        const int L = (int)(A.qoff[qi + 1] - qo);
+        const int P = L - A.pat.span + 1;
+        if (P < 2) {   // no window, or only the (never counted) last one
+            if (lane == 0) { A.outStart[qi] = 0; A.outCount[qi] = 0; A.status[qi] = ST_OK; }
+            continue;
+        }
+        if (L > PW_MAXL) {
+            if (lane == 0) { A.outStart[qi] = 0; A.outCount[qi] = 0; A.status[qi] = ST_CAPACITY; A.need[qi] = 1; }
+            continue;
+        }
+        QMeta &M = A.meta[qi];
+        // query, composition bias (SubstitutionMatrix.cpp:85-114: float accumulator, the division and every pBack * score
+        // term in double; explicit _rn intrinsics keep the compiler from fusing into FMA), ungapped-profile correction
+        for (int i = lane; i < L; i += 32) S.q[i] = A.q[qo + i];
+        __syncwarp();
+        int minCorr = 0;
+        for (int i = lane; i < L; i += 32) {
+            float d = 0.0f;
+            if (A.compBias) {
+                const int lo = max(0, i - 20), hi = min(L, i + 20);
+                const int16_t *row = A.mat->seed + S.q[i] * SPB_ALPHABET;
+                int sum = 0;
+                for (int j = lo; j < hi; j++) sum += row[S.q[j]];
+                sum -= row[S.q[i]];
+                d = (float)sum;
+                d = __double2float_rn(__ddiv_rn((double)d, -1.0 * (double)(float)(hi - lo)));
+                for (int a = 0; a < SPB_ALPHABET; a++)
+                    d = __double2float_rn(__dadd_rn((double)d, __dmul_rn(A.mat->pback_seed[a], (double)(float)row[a])));
+            }
+            S.cb[i] = d;
+            // UngappedAlignment::createProfile (UngappedAlignment.cpp:322-328)
+            const float t4 = __fdiv_rn(d, 4.0f);
+            const double dd = (d < 0.0f) ? __dsub_rn((double)t4, 0.5) : __dadd_rn((double)t4, 0.5);
+            const signed char cc = (signed char)__double2float_rn(dd);
+            M.corr[i] = cc;
+            minCorr = min(minCorr, (int)cc);
+        }
+        for (int d = 16; d > 0; d >>= 1) minCorr = min(minCorr, __shfl_xor_sync(0xffffffffu, minCorr, d));
+        __syncwarp();
+        for (int w = lane; w < P; w += 32) {
+            bool hasX = false;
+            float b = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                hasX = hasX || (S.q[w + A.pat.pos[k]] >= SPB_X);
+                b = __fadd_rn(b, S.cb[w + A.pat.pos[k]]);
+            }
+            // QueryMatcher::match (QueryMatcher.cpp:205-219)
+            const short bias = (short)((b < 0.0f) ? __dsub_rn((double)b, 0.5) : __dadd_rn((double)b, 0.5));
+            const short thr = (short)max(A.kmerThr - (int)bias, 0);
+            int x1 = 0, x2 = 0, best1 = -32768, cut1 = 0;
+            if (!hasX && w < P - 1) {   // quirk A: the last window is never counted
+                x1 = S.q[w + A.pat.pos[0]] + 20 * S.q[w + A.pat.pos[1]] + 400 * S.q[w + A.pat.pos[2]];
+                x2 = S.q[w + A.pat.pos[3]] + 20 * S.q[w + A.pat.pos[4]] + 400 * S.q[w + A.pat.pos[5]];
+                const int best2 = (int)(__ldg(A.row3 + (size_t)x2 * SPB_N3) >> 16) - SPB_SCORE_OFF;
+                cut1 = (int)thr - best2;
+                if (cut1 <= SPB_CNT3_W - SPB_SCORE_OFF - 1) best1 = (int)(__ldg(A.row3 + (size_t)x1 * SPB_N3) >> 16) - SPB_SCORE_OFF;
+            }
+            S.thr[w] = thr;
+            S.x1[w] = (unsigned short)x1;
+            S.x2[w] = (unsigned short)x2;
+            S.best1[w] = (short)best1;
+            S.cut1[w] = (short)cut1;
+        }
+        __syncwarp();
+        // similar k-mers of the query: count, allocate chunks, write
+        uint32_t K = 0;
+        for (int w = 0; w < P - 1; w++)
+            if (S.best1[w] != -32768)
+                K += window_kmers<false>(A.row3, A.cnt3, S.x1[w], S.x2[w], S.thr[w], S.best1[w], S.cut1[w], (uint32_t)w, nullptr);
+        if (K > 65535u) {
+            if (lane == 0) { A.outStart[qi] = 0; A.outCount[qi] = 0; A.status[qi] = ST_CAPACITY; A.need[qi] = 4; }
+            continue;
+        }
+        const uint32_t nCh = (K + PX_CH - 1) / PX_CH;
+        uint32_t base = 0;
+        if (lane == 0 && nCh) base = atomicAdd(A.chunkCursor, nCh);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base + nCh > A.chunkCap) {
+            // the chunks of the claim that lie inside the arena are visited by the lookup kernel: make them empty
+            for (uint32_t ch = base; ch < min(base + nCh, A.chunkCap); ch++) {
+                for (int i = lane; i < PX_CH; i += 32) A.recs[(size_t)ch * PX_CH + i] = PX_INVALID;
+                if (lane == 0) A.chunkTab[ch] = make_uint2(qi, 0u);
+            }
+            if (lane == 0) { A.outStart[qi] = 0; A.outCount[qi] = 0; A.status[qi] = ST_RETRY; }
+            continue;
+        }
+        uint32_t *dst = A.recs + (size_t)base * PX_CH;
+        uint32_t kk = 0;
+        for (int w = 0; w < P - 1; w++)
+            if (S.best1[w] != -32768)
+                kk += window_kmers<true>(A.row3, A.cnt3, S.x1[w], S.x2[w], S.thr[w], S.best1[w], S.cut1[w], (uint32_t)w, dst + kk);
+        for (uint32_t k = K + (uint32_t)lane; k < nCh * PX_CH; k += 32) dst[k] = PX_INVALID;
+        for (uint32_t i = (uint32_t)lane; i < nCh; i += 32) A.chunkTab[base + i] = make_uint2(qi, i * PX_CH);
+        if (lane == 0) { M.chunk0 = base; M.nChunks = nCh; M.K = K; M.minCorr = minCorr; A.status[qi] = ST_PENDING; }
+    }
+}
+
+// The gather.  CTA = one chunk of 256 slots per trip (grid-stride over the chunks the tile allocated; the count is read from
+// device memory, no host round trip after expand_kernel).  The hits of a chunk are compacted (CTA-wide scan) and appended to
+// the tile's dense hit arena with ONE atomic reservation per chunk; chunkHits[c] = (first record, count).  k-mer frequencies
+// are far from uniform (a 6-mer of common residues occurs dozens of times), so a chunk holds anything from 0 to thousands
+// of hits.  A chunk that finds the arena full stores count = PX_OVER and its query is run again in the next round.
+__global__ void __launch_bounds__(PX_CH) lookup_kernel(PrefArgs A) {
+    __shared__ uint32_t s_w[PX_CH / 32];
+    __shared__ uint32_t s_hbase;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t nCh = min(*A.chunkCursor, A.chunkCap);
+    const uint64_t *__restrict__ post = A.post;
+    for (uint32_t c = blockIdx.x; c < nCh; c += gridDim.x) {
+        const uint32_t rec = __ldcs(A.recs + (size_t)c * PX_CH + tid);
+        const uint32_t kmer = rec & 0x03FFFFFFu, w = rec >> 26;
+        ulonglong2 e = make_ulonglong2(0ull, 0ull);
+        uint32_t n = 0;
+        if (kmer < SPB_NK && ((__ldg(A.kbits + (kmer >> 5)) >> (kmer & 31)) & 1u)) {
+            e = __ldcs(A.direct + kmer);
+            n = (e.x >> 63) ? 1u + (uint32_t)(e.y >> 63) : (uint32_t)(e.x >> 32);
+        }
+        const uint32_t inc = (uint32_t)warp_incl_scan((int)n);
+        if (lane == 31) s_w[wid] = inc;
+        __syncthreads();
+        uint32_t off = inc - n, total = 0;
+#pragma unroll
+        for (int i = 0; i < PX_CH / 32; i++) {
+            const uint32_t v = s_w[i];
+            if (i < wid) off += v;
+            total += v;
+        }
+        if (tid == 0) {
+            uint32_t hb = 0;
+            if (total) hb = atomicAdd(A.hitCursor, total);
+            const bool fits = (uint64_t)hb + total <= (uint64_t)A.hitArenaCap;
+            A.chunkHits[c] = make_uint2(hb, fits ? total : PX_OVER);
+            s_hbase = fits ? hb : PX_OVER;
+        }
+        __syncthreads();
+        const uint32_t hb = s_hbase;
+        if (n && hb != PX_OVER) {
+            const uint32_t k = A.chunkTab[c].y + (uint32_t)tid;
+            uint64_t *__restrict__ dst = A.hitArena + (size_t)hb + off;
+            const uint64_t kw = (uint64_t)k << 16;
+            if (e.x >> 63) {
+                dst[0] = ((e.x >> 16) << 32) | kw | (uint64_t)((w - (uint32_t)(e.x & 0xFFFFull)) & 0xFFFFu);
+                if (e.y >> 63) dst[1] = ((e.y >> 16) << 32) | kw | (uint64_t)((w - (uint32_t)(e.y & 0xFFFFull)) & 0xFFFFu);
+            } else {
+                // list of three or more postings: four independent loads in flight per trip
+                const uint64_t *__restrict__ pl = post + (uint32_t)e.x;
+                for (uint32_t z = 0; z < n; z += 4) {
+                    uint64_t pe[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) pe[u] = (z + u < n) ? __ldg(pl + z + u) : 0ull;
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (z + u < n) dst[z + u] = ((pe[u] >> 16) << 32) | kw | (uint64_t)((w - (uint32_t)(pe[u] & 0xFFFFull)) & 0xFFFFu);
+                }
+            }
+        }
+    }
+}
+
+template <int BM1, int BM2>
+struct QuerySmem {
+    uint32_t seen1[BM1], seen2[BM2];
     uint8_t q[PW_MAXL];
     signed char corr[PW_MAXL];
-    uint32_t v_qi, v_K, v_nRuns, v_slow, v_why, v_nHits, v_nSurv, v_nFin;
+    uint32_t v_qi, v_K, v_slow, v_why, v_nHits, v_nSurv, v_nFin, v_cut, v_chunk0, v_nCh;
     int v_minCorr;
 };
-// Shared memory is budgeted per warp: 8 CTAs x 4 warps must fit the 164 KB carve-out, which leaves 64 KB of L1 for the row3
-// reads (with the 196 KB carve-out the kernel is 12 % slower).  Set-up temporaries therefore live in buffers that are idle at
-// that time: the composition bias (float[64]) and the outer-neighbour counts (u16[64]) in the head of the sort buffer (dead
-// before the runs are written there), the capped per-record scores (u8[256]) behind the bucket counters in seen1.
+// Shared memory is budgeted per warp: 8 CTAs x 4 warps must fit the 164 KB carve-out, which leaves 64 KB of L1.  The capped
+// per-record scores (u8[256] per warp) live behind the bucket counters in seen1, which is dead by then.
 struct WorkSmem {
     uint64_t surv[PW_SCAP];
 };
@@ -721,70 +968,11 @@ __device__ __noinline__ void warp_bitonic_u64(uint64_t *a, int n_pow2) {
     __syncwarp();
 }
 
-__device__ __noinline__ int warp_incl_scan_ool(int v) { return warp_incl_scan(v); }
-
-// out-of-line copies for the team kernels: their instruction footprint must stay small (32 warps per SM run different
-// phases of different queries; an inlined kernel of 128 KB thrashes the instruction cache)
+// out-of-line copies for the bookkeeping kernels: their instruction footprint must stay small (32 warps per SM run different
+// phases of different queries; a fully inlined kernel thrashes the instruction cache)
 __device__ __noinline__ int ungapped_u16_ool(const uint8_t *__restrict__ tres, const uint32_t *__restrict__ toff, uint32_t id,
                                              const uint8_t *q, int L, const signed char *corr, const signed char *m40u, uint32_t diag16) {
     return ungapped_u16(tres, toff, id, q, L, corr, m40u, diag16);
-}
-
-// hit records: warp-aggregated append to the team's scratch slice + seen-once / seen-twice bitmaps
-__device__ __noinline__ void pw_emit(bool have, uint64_t pe, uint32_t k, uint32_t w, uint32_t *nHitsCtr, uint64_t *scratch, uint32_t HCAP,
-                                     uint32_t *seen1, uint32_t *seen2, int hashShift) {
-    const int lane = threadIdx.x & 31;
-    const unsigned m = __ballot_sync(0xffffffffu, have);
-    if (m == 0) return;
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(nHitsCtr, (uint32_t)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (have) {
-        const uint32_t id = (uint32_t)(pe >> 16);
-        const uint32_t dg = (w - (uint32_t)(pe & 0xFFFFull)) & 0xFFFFu;
-        const uint32_t dst = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
-        if (dst < HCAP) __stcg(scratch + dst, ((uint64_t)id << 32) | ((uint64_t)k << 16) | dg);
-        const uint32_t h = (id * 2654435761u) >> hashShift;
-        const uint32_t bm = 1u << (h & 31);
-        const uint32_t old = atomicOr(&seen1[h >> 5], bm);
-        if ((old & bm) || (dg & 0xFFu) == 0u) atomicOr(&seen2[h >> 5], bm);
-    }
-}
-
-// posting lists of the k-mers held by the lanes of a warp (len == 0: none), flattened over the warp: element p of the
-// concatenated lists belongs to the last lane whose exclusive prefix is <= p (coalesced reads, no per-lane walks);
-// the PW_U = 2 consecutive k-mers a lane owns in one lookup iteration are served together: both lists of a lane are concatenated
-// (k-mer 2 * lane first), so one scan and one pass serve the 64 k-mers of the iteration instead of two of each
-__device__ __noinline__ void pw_walk2(uint32_t len0, uint32_t off0, uint32_t len1, uint32_t off1, uint32_t wPack, uint32_t k0,
-                                      const uint64_t *__restrict__ post, uint32_t *nHitsCtr, uint64_t *scratch, uint32_t HCAP,
-                                      uint32_t *seen1, uint32_t *seen2, int hashShift) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t lenS = len0 + len1;
-    const uint32_t inc = (uint32_t)warp_incl_scan_ool((int)lenS);
-    const uint32_t excl = inc - lenS;
-    const uint32_t T = __shfl_sync(0xffffffffu, inc, 31);
-#pragma unroll 1
-    for (uint32_t p0 = 0; p0 < T; p0 += 32) {
-        const uint32_t pp = p0 + lane;
-        int j = 0;
-#pragma unroll 1
-        for (int step = 16; step > 0; step >>= 1) {
-            const int cand = j + step;
-            const uint32_t e = __shfl_sync(0xffffffffu, excl, cand & 31);
-            if (cand < 32 && e <= pp) j = cand;
-        }
-        const uint32_t rel = pp - __shfl_sync(0xffffffffu, excl, j);
-        const uint32_t sL0 = __shfl_sync(0xffffffffu, len0, j);
-        const uint32_t sO0 = __shfl_sync(0xffffffffu, off0, j);
-        const uint32_t sO1 = __shfl_sync(0xffffffffu, off1, j);
-        const uint32_t sW = __shfl_sync(0xffffffffu, wPack, j);
-        const bool second = rel >= sL0;
-        const bool have = pp < T;
-        uint64_t pe = 0;
-        if (have) pe = __ldg(post + (second ? sO1 + (rel - sL0) : sO0 + rel));
-        pw_emit(have, pe, k0 + 2u * (uint32_t)j + (second ? 1u : 0u), (sW >> (second ? 8 : 0)) & 0xFFu, nHitsCtr, scratch, HCAP, seen1, seen2,
-                hashShift);
-    }
 }
 
 // CTA-wide bitonic sort of (key, payload) pairs by key (ascending); n_pow2 entries, padded by the caller
@@ -816,12 +1004,16 @@ __device__ __forceinline__ void block_bitonic_pairs(uint64_t *k, uint64_t *v, in
 #endif
 
 template <int TEAM>
-__global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 ? 8 : 4) prefilter_team_kernel(PrefArgs A) {
+__global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 ? 8 : 4) bookkeep_kernel(PrefArgs A) {
     constexpr bool SOLO = (TEAM == 1);
-    constexpr int BMW = SOLO ? 256 : 1024;          // bitmap words: 8192 / 32768 bits
+    // "seen once" / "seen twice" bitmaps over hashed target ids.  TEAM = 1: 16384 / 4096 bits -- with ~600 hits per frame a
+    // dozen pairs collide in seen1, and the coarser seen2 adds a handful of false survivors, so the survivor set usually
+    // fits the register sort (<= 32); TEAM = 8: 32768 / 32768 bits.
+    constexpr int H1 = SOLO ? 14 : 15, H2 = SOLO ? 12 : 15;
+    constexpr int BM1 = (1 << H1) / 32, BM2 = (1 << H2) / 32;
     constexpr int NQS = SOLO ? PW_WARPS : 1;
     constexpr int NWS = SOLO ? PW_WARPS : TEAM;
-    __shared__ QuerySmem<BMW, SOLO ? 1 : PW_RUNCAP> s_qs[NQS];
+    __shared__ QuerySmem<BM1, BM2> s_qs[NQS];
     __shared__ WorkSmem s_ws[NWS];
     __shared__ signed char s_m40u[SPB_ALPHABET * SPB_ALPHABET];
     __shared__ uint64_t s_big[SOLO ? 1 : 2 * PW_BIG];     // TEAM = 8: CTA-wide final sort (keys | payload)
@@ -831,24 +1023,40 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
     const unsigned lt = (1u << lane) - 1u;
     for (int i = threadIdx.x; i < SPB_ALPHABET * SPB_ALPHABET; i += blockDim.x) s_m40u[i] = (signed char)A.mat->ungapped[i];
     __syncthreads();
-    QuerySmem<BMW, SOLO ? 1 : PW_RUNCAP> &S = s_qs[SOLO ? wid : 0];
+    QuerySmem<BM1, BM2> &S = s_qs[SOLO ? wid : 0];
     WorkSmem &W = s_ws[wid];
-    Run *const runs = SOLO ? reinterpret_cast<Run *>(W.surv) : S.runs_;
-    float *const cbuf = reinterpret_cast<float *>(W.surv);                       // [PW_MAXL], set-up only
-    uint16_t *const n1buf = reinterpret_cast<uint16_t *>(W.surv) + 2 * PW_MAXL;   // [PW_MAXL] behind it, set-up only
     uint8_t *const wcnt = reinterpret_cast<uint8_t *>(S.seen1) + 768 + (SOLO ? 0 : tw * PW_SCAP);   // [PW_SCAP], group phase
-    static_assert(PW_MAXL * 4 + PW_MAXL * 2 <= PW_SCAP * 8 && 768 + (SOLO ? 1 : TEAM) * PW_SCAP <= BMW * 4, "aliased buffers fit");
+    static_assert(768 + (SOLO ? 1 : TEAM) * PW_SCAP <= BM1 * 4, "aliased buffers fit");
     auto team_sync = [&]() { if (SOLO) __syncwarp(); else __syncthreads(); };
     constexpr uint32_t FCAP = SOLO ? PW_FCAP_SOLO : PW_FCAP_TEAM;
-    // hit records | records grouped by target bucket | per-target winners (final key, truncation key)
-    const size_t slice = 2 * (size_t)A.hitCap + 2 * (size_t)FCAP;
-    uint64_t *scratch = A.hitScratch + (size_t)(SOLO ? blockIdx.x * PW_WARPS + wid : blockIdx.x) * slice;
-    uint64_t *finList = scratch + 2 * (size_t)A.hitCap;
+    // records grouped by target bucket | per-target winners (final key, truncation key)
+    const size_t slice = (size_t)A.hitCap + 2 * (size_t)FCAP;
+    uint64_t *grouped = A.hitScratch + (size_t)(SOLO ? blockIdx.x * PW_WARPS + wid : blockIdx.x) * slice;
+    uint64_t *finList = grouped + (size_t)A.hitCap;
     const uint32_t HCAP = A.hitCap;
     unsigned long long statK = 0, statM = 0, statE = 0, statS = 0;
 #ifdef SPB_PHASE_TIMING
     long long phase[6] = {0, 0, 0, 0, 0, 0}, phT = clock64();
 #endif
+    // f(record, valid) is called warp-wide for the hit records of the chunks this warp owns (TEAM = 8: chunks round-robin)
+    auto for_hits = [&](auto f) {
+        const uint32_t nCh = S.v_nCh, c0 = S.v_chunk0;
+        for (uint32_t ch = (uint32_t)tw; ch < nCh; ch += TEAM) {
+            const uint2 cb = __ldcg(A.chunkHits + c0 + ch);
+            const uint32_t n = cb.y;
+            const uint64_t *src = A.hitArena + (size_t)cb.x;
+            for (uint32_t i0 = 0; i0 < n; i0 += 128) {
+                uint64_t r[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = i0 + (uint32_t)(u * 32 + lane);
+                    r[u] = (i < n) ? __ldcg(src + i) : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) f(r[u], i0 + (uint32_t)(u * 32 + lane) < n);
+            }
+        }
+    };
 
     for (;;) {
         PH_MARK(5);
@@ -856,343 +1064,125 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
         if (tw == 0 && lane == 0) S.v_qi = atomicAdd(A.qCounter, 1u);
         team_sync();
         const uint32_t slot = S.v_qi;
-        if (slot >= (A.qlist ? (A.nListPtr ? *A.nListPtr : A.nList) : A.Q)) break;
-        const uint32_t qi = A.qlist ? A.qlist[slot] : slot;
-        const uint32_t qo = A.qoff[qi];
-        const int L = (int)(A.qoff[qi + 1] - qo);
-        const int P = L - A.pat.span + 1;
-        if (P < 2) {
-            if (tw == 0 && lane == 0) { A.outStart[qi] = 0; A.outCount[qi] = 0; A.status[qi] = ST_OK; }
+        if (slot >= (A.nListPtr ? *A.nListPtr : A.nList)) break;
+        const uint32_t qi = A.qlist[A.listOff + (size_t)slot * A.listStride];
+        if (A.status[qi] != (SOLO ? ST_PENDING : ST_TEAM)) {   // decided by expand_kernel (no window, handed over, retry)
             team_sync();
             continue;
         }
-        for (int i = tw * 32 + lane; i < BMW; i += TEAM * 32) { S.seen1[i] = 0; S.seen2[i] = 0; }
+        const uint32_t qo = A.qoff[qi];
+        const int L = (int)(A.qoff[qi + 1] - qo);
+        const QMeta &M = A.meta[qi];
+        for (int i = tw * 32 + lane; i < BM1; i += TEAM * 32) S.seen1[i] = 0;
+        for (int i = tw * 32 + lane; i < BM2; i += TEAM * 32) S.seen2[i] = 0;
         if (tw == 0) {
-            // ======== set-up by the first warp of the team ========
-            uint32_t why = (L > PW_MAXL) ? ST_CAPACITY : ST_OK;   // status the query leaves this kernel with if not ST_OK
-            uint32_t reason = (L > PW_MAXL) ? 1u : 0u;            // why it was handed over (statistics)
-            int nRuns = 0;
-            uint32_t K = 0;
-            int minCorr = 0;
-            if (lane == 0) { S.v_nHits = 0; S.v_nSurv = 0; S.v_nFin = 0; }
-            if (why == ST_OK) {
-                // query, composition bias (as in prefilter_kernel), window thresholds
-                for (int i = lane; i < L; i += 32) S.q[i] = A.q[qo + i];
-                __syncwarp();
-                for (int i = lane; i < L; i += 32) {
-                    float d = 0.0f;
-                    if (A.compBias) {
-                        const int lo = max(0, i - 20), hi = min(L, i + 20);
-                        const int16_t *row = A.mat->seed + S.q[i] * SPB_ALPHABET;
-                        int sum = 0;
-                        for (int j = lo; j < hi; j++) sum += row[S.q[j]];
-                        sum -= row[S.q[i]];
-                        d = (float)sum;
-                        d = __double2float_rn(__ddiv_rn((double)d, -1.0 * (double)(float)(hi - lo)));
-                        for (int a = 0; a < SPB_ALPHABET; a++)
-                            d = __double2float_rn(__dadd_rn((double)d, __dmul_rn(A.mat->pback_seed[a], (double)(float)row[a])));
-                    }
-                    cbuf[i] = d;
-                    const float t4 = __fdiv_rn(d, 4.0f);
-                    const double dd = (d < 0.0f) ? __dsub_rn((double)t4, 0.5) : __dadd_rn((double)t4, 0.5);
-                    const signed char cc = (signed char)__double2float_rn(dd);
-                    S.corr[i] = cc;
-                    minCorr = min(minCorr, (int)cc);
-                }
-                for (int d = 16; d > 0; d >>= 1) minCorr = min(minCorr, __shfl_xor_sync(0xffffffffu, minCorr, d));
-                __syncwarp();
-                for (int w = lane; w < P; w += 32) {
-                    bool hasX = false;
-                    float b = 0.0f;
-#pragma unroll
-                    for (int k = 0; k < 6; k++) {
-                        hasX = hasX || (S.q[w + A.pat.pos[k]] >= SPB_X);
-                        b = __fadd_rn(b, cbuf[w + A.pat.pos[k]]);
-                    }
-                    const short bias = (short)((b < 0.0f) ? __dsub_rn((double)b, 0.5) : __dadd_rn((double)b, 0.5));
-                    const short thr = (short)max(A.kmerThr - (int)bias, 0);
-                    int n1 = 0, x1 = 0, x2 = 0;
-                    if (!hasX && w < P - 1) {   // quirk A: the last window is never counted
-                        x1 = S.q[w + A.pat.pos[0]] + 20 * S.q[w + A.pat.pos[1]] + 400 * S.q[w + A.pat.pos[2]];
-                        x2 = S.q[w + A.pat.pos[3]] + 20 * S.q[w + A.pat.pos[4]] + 400 * S.q[w + A.pat.pos[5]];
-                        const int best2 = (int)(__ldg(A.row3 + (size_t)x2 * SPB_N3) >> 16) - SPB_SCORE_OFF;
-                        const int cut1 = (int)thr - best2;
-                        if (cut1 <= SPB_CNT3_W - SPB_SCORE_OFF - 1)
-                            n1 = (int)__ldg(A.cnt3 + (size_t)x1 * SPB_CNT3_W + max(cut1, -SPB_SCORE_OFF) + SPB_SCORE_OFF);
-                    }
-                    S.thr[w] = thr;
-                    n1buf[w] = (unsigned short)n1;
-                    S.x1[w] = (unsigned short)x1;
-                    S.x2[w] = (unsigned short)x2;
-                }
-                __syncwarp();
-                uint32_t Rtot = 0;
-                if (lane == 0) {
-                    uint32_t acc = 0;
-                    for (int w = 0; w < P; w++) { S.rowbase[w] = (uint16_t)min(acc, 65535u); acc += n1buf[w]; }
-                    S.rowbase[P] = (uint16_t)min(acc, 65535u);
-                    Rtot = acc;
-                }
-                Rtot = __shfl_sync(0xffffffffu, Rtot, 0);
-                if (Rtot > 65535u) { why = ST_CAPACITY; reason = 2; }
-                __syncwarp();
-                // runs: maximal stretches of outer neighbours with equal score (hence equal inner count)
-                // (two chunks of 32 outer neighbours per trip: their row3 / cnt3 reads are independent and go out together)
-                for (uint32_t g0 = 0; g0 < Rtot && why == ST_OK; g0 += 64) {
-                    uint32_t av[2], wv[2], n2v[2], cur[2], prv[2];
-                    bool bnd[2];
-#pragma unroll
-                    for (int v = 0; v < 2; v++) {
-                        const uint32_t g = g0 + (uint32_t)(32 * v + lane);
-                        av[v] = 0; wv[v] = 0; n2v[v] = 0; cur[v] = 0; prv[v] = 0;
-                        if (g < Rtot) {
-                            int lo = 0, hi = P - 1;   // largest w with rowbase[w] <= g
-                            while (lo < hi) {
-                                const int mid = (lo + hi + 1) >> 1;
-                                if ((uint32_t)S.rowbase[mid] <= g) lo = mid; else hi = mid - 1;
-                            }
-                            wv[v] = (uint32_t)lo;
-                            av[v] = g - (uint32_t)S.rowbase[lo];
-                            const uint32_t *r1 = A.row3 + (size_t)S.x1[lo] * SPB_N3;
-                            cur[v] = __ldg(r1 + av[v]);
-                            prv[v] = av[v] ? __ldg(r1 + av[v] - 1) : 0u;
-                        }
-                    }
-#pragma unroll
-                    for (int v = 0; v < 2; v++) {
-                        const uint32_t g = g0 + (uint32_t)(32 * v + lane);
-                        bnd[v] = false;
-                        if (g < Rtot) {
-                            const int s1 = (int)(cur[v] >> 16) - SPB_SCORE_OFF;
-                            bnd[v] = (av[v] == 0) || ((int)(prv[v] >> 16) - SPB_SCORE_OFF != s1);
-                            if (bnd[v]) {
-                                const int cut2 = (int)S.thr[wv[v]] - s1;
-                                if (cut2 <= SPB_CNT3_W - SPB_SCORE_OFF - 1)
-                                    n2v[v] = (uint32_t)__ldg(A.cnt3 + (size_t)S.x2[wv[v]] * SPB_CNT3_W + max(cut2, -SPB_SCORE_OFF) + SPB_SCORE_OFF);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int v = 0; v < 2; v++) {
-                        const unsigned m = __ballot_sync(0xffffffffu, bnd[v]);
-                        const int dst = nRuns + __popc(m & lt);
-                        if (bnd[v] && dst < PW_RUNCAP) {
-                            Run r;
-                            r.a0 = (uint16_t)av[v]; r.n2 = (uint16_t)n2v[v]; r.cum = (uint16_t)(g0 + (uint32_t)(32 * v + lane)); r.w = (uint16_t)wv[v];
-                            runs[dst] = r;
-                        }
-                        nRuns += __popc(m);
-                    }
-                    if (nRuns > PW_RUNCAP) { why = ST_CAPACITY; reason = 3; }
-                }
-                __syncwarp();
-                // first k of every run: exclusive prefix of (rows in the run) x (inner count)
-                for (int c0 = 0; c0 < nRuns && why == ST_OK; c0 += 32) {
-                    const int i = c0 + lane;
-                    uint32_t cntK = 0;
-                    if (i < nRuns) {
-                        const uint32_t gThis = runs[i].cum;
-                        const uint32_t gNext = (i + 1 < nRuns) ? (uint32_t)runs[i + 1].cum : Rtot;
-                        cntK = (gNext - gThis) * (uint32_t)runs[i].n2;
-                    }
-                    const uint32_t inc = (uint32_t)warp_incl_scan_ool((int)cntK);
-                    const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
-                    __syncwarp();
-                    if (K + tot > 65535u) { why = ST_CAPACITY; reason = 4; break; }
-                    if (i < nRuns) runs[i].cum = (uint16_t)(K + inc - cntK);
-                    K += tot;
-                    __syncwarp();
-                }
-                if (SOLO && why == ST_OK && K > A.kCapSolo) why = ST_TEAM;
+            for (int i = lane; i < L; i += 32) { S.q[i] = A.q[qo + i]; S.corr[i] = M.corr[i]; }
+            // hits of the query = sum of its chunk counts; a chunk that found the hit arena full sends the query to the next round
+            const uint32_t nCh = M.nChunks, c0 = M.chunk0;
+            uint32_t sum = 0, over = 0;
+            for (uint32_t ch = (uint32_t)lane; ch < nCh; ch += 32) {
+                const uint32_t n = __ldcg(A.chunkHits + c0 + ch).y;
+                over |= (n == PX_OVER) ? 1u : 0u;
+                sum += (n == PX_OVER) ? 0u : n;
             }
-            if (lane == 0) { S.v_K = K; S.v_nRuns = (uint32_t)nRuns; S.v_slow = why; S.v_why = reason; S.v_minCorr = minCorr; }
+            for (int d = 16; d > 0; d >>= 1) {
+                sum += __shfl_xor_sync(0xffffffffu, sum, d);
+                over |= __shfl_xor_sync(0xffffffffu, over, d);
+            }
+            if (lane == 0) {
+                uint32_t why = ST_OK, reason = 0;
+                if (over) why = ST_RETRY;
+                else if (SOLO && sum > A.hitsSolo) why = ST_TEAM;
+                S.v_K = M.K; S.v_nHits = sum; S.v_nSurv = 0; S.v_nFin = 0; S.v_slow = why; S.v_why = reason;
+                S.v_minCorr = M.minCorr; S.v_chunk0 = c0; S.v_nCh = nCh;
+            }
         }
         team_sync();
         PH_MARK(0);
         const uint32_t K = S.v_K;
-        const int nRuns = (int)S.v_nRuns;
-        // ---------------- one pass over the hit stream ----------------
-        // Lane l of a pass owns the PW_U consecutive similar k-mers k0 + l * PW_U ...: one run search and one division give
-        // (outer neighbour, inner neighbour) of the first, the others follow by stepping.  A table entry carries up to two
-        // postings inline (95 % of the k-mers of a GenBank-phage-sized index occur in at most two ORFs), so most hits are
-        // written straight from the entry: one scan, one reservation, no second memory access.  Longer lists are walked
-        // warp-wide (pw_walk2).
-        if (S.v_slow == ST_OK) {
-            constexpr int HSH = SOLO ? 19 : 17;
-            for (uint32_t k0 = (uint32_t)tw * (32 * PW_U); k0 < K; k0 += TEAM * 32 * PW_U) {
-                const uint32_t kBeg = k0 + (uint32_t)lane * PW_U;
-                ulonglong2 d[PW_U];
-                uint32_t wPack = 0;
-#pragma unroll
-                for (int u = 0; u < PW_U; u++) d[u] = make_ulonglong2(0ull, 0ull);
-                if (kBeg < K) {
-                    int lo = 0, hi = nRuns - 1;   // largest r with runs[r].cum <= kBeg
-                    while (lo < hi) {
-                        const int mid = (lo + hi + 1) >> 1;
-                        if ((uint32_t)runs[mid].cum <= kBeg) lo = mid; else hi = mid - 1;
-                    }
-                    int ri = lo;
-                    Run r = runs[ri];
-                    uint32_t nextCum = (ri + 1 < nRuns) ? (uint32_t)runs[ri + 1].cum : 0xFFFFFFFFu;
-                    const uint32_t rel = kBeg - (uint32_t)r.cum;
-                    uint32_t da = rel / (uint32_t)r.n2;
-                    uint32_t b = rel - da * (uint32_t)r.n2;
-                    const uint32_t *row1 = A.row3 + (size_t)S.x1[r.w] * SPB_N3 + (uint32_t)r.a0;
-                    const uint32_t *row2 = A.row3 + (size_t)S.x2[r.w] * SPB_N3;
-                    uint32_t i1 = __ldg(row1 + da) & 0xFFFFu;
-#pragma unroll
-                    for (int u = 0; u < PW_U; u++) {
-                        const uint32_t k = kBeg + (uint32_t)u;
-                        if (k < K) {
-                            const uint32_t i2 = __ldg(row2 + b) & 0xFFFFu;
-                            d[u] = __ldg(A.direct + (i1 + 8000u * i2));
-                            wPack |= (uint32_t)r.w << (8 * u);
-                            if (u + 1 < PW_U && k + 1 < K) {
-                                if (++b == (uint32_t)r.n2) {
-                                    b = 0;
-                                    da++;
-                                    if (k + 1 >= nextCum) {   // next run holding a k-mer (runs without inner neighbours share their cum)
-                                        ri++;
-                                        while (ri + 1 < nRuns && (uint32_t)runs[ri + 1].cum <= k + 1) ri++;
-                                        r = runs[ri];
-                                        nextCum = (ri + 1 < nRuns) ? (uint32_t)runs[ri + 1].cum : 0xFFFFFFFFu;
-                                        da = 0;
-                                        row1 = A.row3 + (size_t)S.x1[r.w] * SPB_N3 + (uint32_t)r.a0;
-                                        row2 = A.row3 + (size_t)S.x2[r.w] * SPB_N3;
-                                    }
-                                    i1 = __ldg(row1 + da) & 0xFFFFu;
-                                }
-                            }
-                        }
+        const uint32_t nHits = S.v_nHits;
+        const bool live = (S.v_slow == ST_OK);
+        // ---------------- pass 1 over the hit stream: targets seen once / twice ----------------
+        if (live) {
+            for_hits([&](uint64_t r, bool valid) {
+                if (valid) {
+                    const uint32_t h = ((uint32_t)(r >> 32) * 2654435761u) >> (32 - H1);
+                    const uint32_t bm = 1u << (h & 31);
+                    const uint32_t old = atomicOr(&S.seen1[h >> 5], bm);
+                    if ((old & bm) || ((uint32_t)r & 0xFFu) == 0u) {
+                        const uint32_t h2 = h >> (H1 - H2);
+                        atomicOr(&S.seen2[h2 >> 5], 1u << (h2 & 31));
                     }
                 }
-                // inline postings
-                uint32_t cnt = 0;
-#pragma unroll
-                for (int u = 0; u < PW_U; u++) cnt += (uint32_t)(d[u].x >> 63) + (uint32_t)((d[u].x >> 63) & (d[u].y >> 63));
-                const uint32_t inc = (uint32_t)warp_incl_scan_ool((int)cnt);
-                const uint32_t T = __shfl_sync(0xffffffffu, inc, 31);
-                if (T) {
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&S.v_nHits, T);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    uint32_t dst = base + inc - cnt;
-#pragma unroll
-                    for (int s2 = 0; s2 < 2 * PW_U; s2++) {
-                        const int u = s2 >> 1;
-                        const uint64_t pe = (s2 & 1) ? d[u].y : d[u].x;
-                        if ((pe >> 63) && (d[u].x >> 63)) {
-                            const uint32_t id = (uint32_t)(pe >> 16);
-                            const uint32_t w = (wPack >> (8 * u)) & 0xFFu;
-                            const uint32_t dg = (w - (uint32_t)(pe & 0xFFFFull)) & 0xFFFFu;
-                            if (dst < HCAP) __stcg(scratch + dst, ((uint64_t)id << 32) | ((uint64_t)(kBeg + (uint32_t)u) << 16) | dg);
-                            dst++;
-                            const uint32_t h = (id * 2654435761u) >> HSH;
-                            const uint32_t bm = 1u << (h & 31);
-                            const uint32_t old = atomicOr(&S.seen1[h >> 5], bm);
-                            if ((old & bm) || (dg & 0xFFu) == 0u) atomicOr(&S.seen2[h >> 5], bm);
-                        }
-                    }
-                }
-                // posting lists of the k-mers in three or more targets, flattened over the warp.  (Deferring them to a per-warp
-                // queue drained in bulk was measured in round 1h: no gain in the lookup phase, and the extra shared memory
-                // of the TEAM = 1 launch cost more than it saved.)
-                static_assert(PW_U == 2, "pw_walk2 serves exactly two k-mers per lane");
-                {
-                    const uint32_t len0 = (d[0].x >> 63) ? 0u : (uint32_t)(d[0].x >> 32);
-                    const uint32_t len1 = (d[1].x >> 63) ? 0u : (uint32_t)(d[1].x >> 32);
-                    if (__any_sync(0xffffffffu, (len0 | len1) != 0u))
-                        pw_walk2(len0, (uint32_t)d[0].x, len1, (uint32_t)d[1].x, wPack, k0, A.post, &S.v_nHits, scratch, HCAP, S.seen1,
-                                 S.seen2, HSH);
-                }
-            }
+            });
         }
         team_sync();
         PH_MARK(1);
-        const uint32_t nHits = S.v_nHits;
-        const bool live = (S.v_slow == ST_OK) && nHits <= HCAP;
-        team_sync();
-        if (S.v_slow == ST_OK && nHits > HCAP && tw == 0 && lane == 0) { S.v_slow = ST_CAPACITY; S.v_why = 5; }
         // ---------------- survivors: records of targets seen twice (or with 8-bit diagonal 0) ----------------
         // Pass A counts them per hash bucket (64 buckets of targets) and -- TEAM = 1 -- collects them optimistically into the
-        // warp's sort buffer.  If they do not fit one sort, pass B scatters them bucket by bucket behind the hit records and the
-        // buckets are merged into G contiguous groups of at most PW_SCAP records, each processed independently by one warp.
-        uint32_t *const cnt64 = S.seen1;            // dead after the gather: [0,64) counts, [64,128) starts, [128,192) fill cursors
+        // warp's sort buffer.  If they do not fit one sort, pass B scatters them bucket by bucket into the team's scratch slice
+        // and the buckets are merged into G contiguous groups of at most PW_SCAP records, each processed by one warp.
+        uint32_t *const cnt64 = S.seen1;            // dead after pass 1: [0,64) counts, [64,128) starts, [128,192) fill cursors
         if (live) for (int i = tw * 32 + lane; i < 192; i += TEAM * 32) cnt64[i] = 0;
         team_sync();
         int nS0 = 0;
         if (live) {
-            for (uint32_t i0 = (uint32_t)tw * 128; i0 < nHits; i0 += TEAM * 128) {
-                uint64_t r[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint32_t i = i0 + (uint32_t)(u * 32 + lane);
-                    r[u] = (i < nHits) ? __ldcg(scratch + i) : 0ull;
+            for_hits([&](uint64_t r, bool valid) {
+                const uint32_t id = (uint32_t)(r >> 32);
+                const uint32_t h2 = (id * 2654435761u) >> (32 - H2);
+                const bool keep = valid && ((S.seen2[h2 >> 5] >> (h2 & 31)) & 1u);
+                if (keep) atomicAdd(&cnt64[(id * 0x85EBCA6Bu) >> 26], 1u);
+                if (SOLO) {
+                    const unsigned m = __ballot_sync(0xffffffffu, keep);
+                    const int dst = nS0 + __popc(m & lt);
+                    if (keep && dst < PW_SCAP) W.surv[dst] = r;
+                    nS0 += __popc(m);
                 }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint32_t i = i0 + (uint32_t)(u * 32 + lane);
-                    const uint32_t id = (uint32_t)(r[u] >> 32);
-                    const uint32_t h = (id * 2654435761u) >> (SOLO ? 19 : 17);
-                    const bool keep = (i < nHits) && ((S.seen2[h >> 5] >> (h & 31)) & 1u);
-                    if (keep) atomicAdd(&cnt64[(id * 0x85EBCA6Bu) >> 26], 1u);
-                    if (SOLO) {
-                        const unsigned m = __ballot_sync(0xffffffffu, keep);
-                        const int dst = nS0 + __popc(m & lt);
-                        if (keep && dst < PW_SCAP) W.surv[dst] = r[u];
-                        nS0 += __popc(m);
-                    }
-                }
-            }
+            });
         }
         team_sync();
         // group count: the smallest power of two whose merged buckets all fit one sort (every warp computes the same)
         uint32_t nSurv = 0, G = 1;
         if (live) {
             const uint32_t c0 = cnt64[2 * lane], c1 = cnt64[2 * lane + 1];
-            // level l uses 64 >> l groups; the largest merged bucket grows with l, so the last level that fits wins
-            uint32_t sum = c0 + c1, mxFit = 0;
-            int lvl = -1;
+            if (SOLO && nS0 <= PW_SCAP) {
+                nSurv = (uint32_t)nS0;    // everything already sits in the sort buffer: one group, no scatter
+            } else {
+                // level l uses 64 >> l groups; the largest merged bucket grows with l, so the last level that fits wins
+                uint32_t sum = c0 + c1;
+                int lvl = -1;
 #pragma unroll 1
-            for (int l = 0; l < 7; l++) {
-                if (l >= 2) sum += __shfl_xor_sync(0xffffffffu, sum, 1 << (l - 2));
-                uint32_t m = (l == 0) ? max(c0, c1) : sum;
+                for (int l = 0; l < 7; l++) {
+                    if (l >= 2) sum += __shfl_xor_sync(0xffffffffu, sum, 1 << (l - 2));
+                    uint32_t m = (l == 0) ? max(c0, c1) : sum;
 #pragma unroll 1
-                for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
-                if (m <= PW_SCAP) { lvl = l; mxFit = m; }
-                if (l == 6) nSurv = m;
-            }
-            (void)mxFit;
-            G = 64u >> max(lvl, 0);
-            if (lvl < 0 && tw == 0 && lane == 0) { S.v_slow = ST_CAPACITY; S.v_why = 6; }   // one bucket alone overflows a sort
-            if (tw == 0) {   // bucket starts
-                uint32_t e0 = (uint32_t)warp_incl_scan_ool((int)(c0 + c1)) - (c0 + c1);
-                cnt64[64 + 2 * lane] = e0;
-                cnt64[64 + 2 * lane + 1] = e0 + c0;
+                    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+                    if (m <= PW_SCAP) lvl = l;
+                    if (l == 6) nSurv = m;
+                }
+                G = 64u >> max(lvl, 0);
+                if (tw == 0 && lane == 0) {
+                    if (lvl < 0) { S.v_slow = ST_CAPACITY; S.v_why = 6; }            // one bucket alone overflows a sort
+                    else if (nSurv > HCAP) { S.v_slow = ST_CAPACITY; S.v_why = 5; }  // the scratch slice cannot hold them
+                }
+                if (tw == 0) {   // bucket starts
+                    const uint32_t e0 = (uint32_t)warp_incl_scan_ool((int)(c0 + c1)) - (c0 + c1);
+                    cnt64[64 + 2 * lane] = e0;
+                    cnt64[64 + 2 * lane + 1] = e0 + c0;
+                }
             }
         }
         team_sync();
-        const bool scatter = live && (S.v_slow == ST_OK) && (!SOLO || G > 1);
-        uint64_t *const grouped = scratch + HCAP;
+        const bool scatter = live && (S.v_slow == ST_OK) && (!SOLO || nS0 > PW_SCAP);
         if (scatter) {
-            for (uint32_t i0 = (uint32_t)tw * 128; i0 < nHits; i0 += TEAM * 128) {
-                uint64_t r[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint32_t i = i0 + (uint32_t)(u * 32 + lane);
-                    r[u] = (i < nHits) ? __ldcg(scratch + i) : 0ull;
+            for_hits([&](uint64_t r, bool valid) {
+                const uint32_t id = (uint32_t)(r >> 32);
+                const uint32_t h2 = (id * 2654435761u) >> (32 - H2);
+                if (valid && ((S.seen2[h2 >> 5] >> (h2 & 31)) & 1u)) {
+                    const uint32_t bk = (id * 0x85EBCA6Bu) >> 26;
+                    __stcg(grouped + cnt64[64 + bk] + atomicAdd(&cnt64[128 + bk], 1u), r);
                 }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint32_t i = i0 + (uint32_t)(u * 32 + lane);
-                    const uint32_t id = (uint32_t)(r[u] >> 32);
-                    const uint32_t h = (id * 2654435761u) >> (SOLO ? 19 : 17);
-                    if ((i < nHits) && ((S.seen2[h >> 5] >> (h & 31)) & 1u)) {
-                        const uint32_t bk = (id * 0x85EBCA6Bu) >> 26;
-                        __stcg(grouped + cnt64[64 + bk] + atomicAdd(&cnt64[128 + bk], 1u), r[u]);
-                    }
-                }
-            }
+            });
         }
         team_sync();
         PH_MARK(2);
@@ -1298,7 +1288,11 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
             // truncation at max-seqs (and anything beyond one warp sort) is finished by the 8-warp team launch
             if (why == ST_OK && (nc >= (uint32_t)A.maxHits || nc > PW_SCAP)) why = ST_TEAM;
             if (why != ST_OK) {
-                if (lane == 0) { A.outStart[qi] = 0; A.outCount[qi] = 0; A.status[qi] = why; A.need[qi] = reason; }
+                if (lane == 0) {
+                    A.outStart[qi] = 0; A.outCount[qi] = 0; A.need[qi] = reason;
+                    if (why == ST_TEAM) A.teamList[atomicAdd(A.teamCount, 1u)] = qi;
+                    A.status[qi] = why;
+                }
             } else {
                 statK += K;
                 statM += nHits;
@@ -1342,7 +1336,6 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
             // whole CTA.  QueryMatcher.cpp:131-164: with >= max-seqs candidates the score histogram fixes the cut score; above
             // max-seqs the candidates are taken in the order of the reference's stable counting sorts (truncation key).
             uint64_t *const bigK = s_big, *const bigV = s_big + PW_BIG;
-            uint32_t *const hist = S.seen2;       // dead after the survivor passes
             const uint32_t nc = S.v_nFin;
             const uint32_t maxHits = (uint32_t)A.maxHits;
             const int tid = threadIdx.x;
@@ -1350,21 +1343,23 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                 S.v_nSurv = 0;                    // reused: selected candidates
                 if (S.v_slow == ST_OK && nc > FCAP) { S.v_slow = ST_CAPACITY; S.v_why = 7; }
             }
-            for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
             __syncthreads();
             const bool ok0 = (S.v_slow == ST_OK);
             const bool trunc = ok0 && nc >= maxHits;
             if (trunc) {
-                for (uint32_t k = tid; k < nc; k += blockDim.x) atomicAdd(&hist[255u - (uint32_t)(__ldcg(finList + 2 * k + 1) >> 55)], 1u);
+                uint32_t *const histS = S.seen2;  // dead after the survivor passes; 1024 words in the team kernel
+                for (int i = tid; i < 256; i += blockDim.x) histS[i] = 0;
+                __syncthreads();
+                for (uint32_t k = tid; k < nc; k += blockDim.x) atomicAdd(&histS[255u - (uint32_t)(__ldcg(finList + 2 * k + 1) >> 55)], 1u);
                 __syncthreads();
                 if (tid == 0) {     // computeScoreThreshold (QueryMatcher.h:199-209)
                     uint32_t found = 0, thr = 0;
                     for (int sc = 255; sc >= 1; sc--) {
-                        found += hist[sc];
+                        found += histS[sc];
                         if (found >= maxHits) { thr = (uint32_t)sc; break; }
                     }
                     const uint32_t thrD = max(thr, (uint32_t)A.minDiag);
-                    S.v_nRuns = thrD;             // reused: cut score
+                    S.v_cut = thrD;
                     // all remaining candidates saturated -> rescoreHits (QueryMatcher.cpp:486-505) lives in prefilter_kernel
                     if ((int)thrD >= capScore) { S.v_slow = ST_CAPACITY; S.v_why = 8; }
                 }
@@ -1374,7 +1369,7 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
             uint32_t ns = nc;                     // rows to output
             if (ok1) {
                 if (nc > maxHits) {
-                    const uint32_t thrD = S.v_nRuns;
+                    const uint32_t thrD = S.v_cut;
                     for (uint32_t k = tid; k < nc; k += blockDim.x) {
                         const uint64_t t = __ldcg(finList + 2 * k + 1);
                         if (255u - (uint32_t)(t >> 55) >= thrD) {
@@ -1606,9 +1601,10 @@ __global__ void count_to_u64_kernel(const uint32_t *__restrict__ cnt, uint32_t Q
 
 // status scan: list of queries needing the global-memory variant, max need, error flags
 __global__ void status_scan_kernel(const uint32_t *__restrict__ status, const uint32_t *__restrict__ need, uint32_t Q,
-                                   uint32_t *__restrict__ list, unsigned int *__restrict__ ctr, uint32_t listStatus) {
+                                   uint32_t *__restrict__ list, unsigned int *__restrict__ ctr, uint32_t listStatus,
+                                   uint32_t *__restrict__ retryList) {
     // ctr: [0] entries of `list` (queries whose status is listStatus), [1] maxNeed, [2] arena overflow,
-    //      [3] layout error (query index + 1), [4] unprocessed
+    //      [3] layout error (query index + 1), [4] unprocessed, [5] entries of `retryList` (ST_RETRY; NULL: none expected)
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Q) return;
     const uint32_t s = status[i];
@@ -1619,33 +1615,27 @@ __global__ void status_scan_kernel(const uint32_t *__restrict__ status, const ui
         atomicOr(&ctr[2], 1u);
     } else if (s == ST_LAYOUT) {
         atomicMax(&ctr[3], i + 1);
-    } else if (s != ST_OK && !(listStatus == ST_TEAM && s == ST_CAPACITY)) {
+    } else if (s == ST_RETRY && retryList) {
+        retryList[atomicAdd(&ctr[5], 1u)] = i;
+    } else if (s != ST_OK) {
         atomicMax(&ctr[4], i + 1);
     }
 }
 
+// test hook: the similar-k-mer list of one 6-mer through the enumerator of expand_kernel (one warp)
 __global__ void similar_kmers_test_kernel(const uint32_t *row3, const uint16_t *cnt3, const uint8_t *k6, int thr, uint32_t *out,
                                           uint32_t cap, uint32_t *n) {
-    __shared__ int s_excl[32];
-    __shared__ uint32_t s_i1[32];
     const int x1 = k6[0] + 20 * k6[1] + 400 * k6[2];
     const int x2 = k6[3] + 20 * k6[4] + 400 * k6[5];
+    const int best1 = (int)(row3[(size_t)x1 * SPB_N3] >> 16) - SPB_SCORE_OFF;
     const int best2 = (int)(row3[(size_t)x2 * SPB_N3] >> 16) - SPB_SCORE_OFF;
     const int cut1 = thr - best2;
-    int n1 = 0;
-    if (cut1 <= SPB_CNT3_W - SPB_SCORE_OFF - 1) n1 = cnt3[(size_t)x1 * SPB_CNT3_W + max(cut1, -SPB_SCORE_OFF) + SPB_SCORE_OFF];
-    uint32_t base = 0;
-    for (int a0 = 0; a0 < n1; a0 += 32) {
-        uint32_t tot = warp_unit_kmers(row3, cnt3, x1, x2, thr, n1, a0, s_excl, s_i1, [&](uint32_t kmer, uint32_t a, uint32_t b, bool valid) {
-            // rank within the unit: position in (a, b) order == base + (exclusive count of a) + b
-            if (valid) {
-                const uint32_t r = base + (uint32_t)s_excl[a - a0] + b;
-                if (r < cap) out[r] = kmer;
-            }
-        });
-        base += tot;
+    uint32_t K = 0;
+    if (cut1 <= SPB_CNT3_W - SPB_SCORE_OFF - 1) {
+        K = window_kmers<false>(row3, cnt3, x1, x2, thr, best1, cut1, 0u, nullptr);
+        if (K <= cap) window_kmers<true>(row3, cnt3, x1, x2, thr, best1, cut1, 0u, out);
     }
-    if (threadIdx.x == 0) *n = base;
+    if (threadIdx.x == 0) *n = K;
 }
 
 }  // namespace spb
@@ -1665,7 +1655,12 @@ extern "C" int spb_similar_kmers(spb_ctx *c, const uint8_t *kmer6, int thr, uint
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(n, dn.p, 4, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    if (e == cudaSuccess && *n) e = cudaMemcpy(out, dout.p, (size_t)(*n < cap ? *n : cap) * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && *n > cap) {
+        dk.release(); dout.release(); dn.release();
+        spb::set_error("spb_similar_kmers: %u similar k-mers exceed the capacity %u of the output array", *n, cap);
+        return 1;
+    }
+    if (e == cudaSuccess && *n) e = cudaMemcpy(out, dout.p, (size_t)*n * 4, cudaMemcpyDeviceToHost);
     dk.release(); dout.release(); dn.release();
     SPB_CHECK(e == cudaSuccess, "spb_similar_kmers: %s", cudaGetErrorString(e));
     return 0;
@@ -1774,6 +1769,7 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
         c->s_e.ensure((size_t)Q * 4) || c->s_f.ensure(512)) return 1;
     uint64_t arenaCap = std::min<uint64_t>((uint64_t)Q * (uint64_t)A.maxHits, std::max<uint64_t>((uint64_t)Q * 24, 1u << 20));
     float kernelMs = 0;
+    double phaseMs[4] = {0, 0, 0, 0};   // expand, lookup, bookkeeping TEAM = 1, TEAM = 8 (summed over tiles)
     uint64_t nSlow = 0;
     unsigned long long h_cursor[24];
     unsigned int dbgWhy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -1797,55 +1793,131 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
         SPB_CUDA(cudaMemsetAsync(c->s_f.p, 0, 512, st));
         SPB_CUDA(cudaMemsetAsync(c->s_c.p, 0xFF, (size_t)Q * 4, st));
         const size_t smem = (size_t)PF_SMEM_CAP * sizeof(Rec);
-        // stage 1: team kernels.  TEAM = 1 over the whole batch (persistent grid, dynamic query scheduler); the queries it
-        // flags ST_TEAM (long similar-k-mer lists) are listed on the device and taken by the TEAM = 8 launch, which reads
-        // the list length from device memory -- no host round trip in between.
+        // stage 1: expand -> lookup -> bookkeeping, tile by tile (a tile = every nTiles-th query of the longest-first order, so
+        // all tiles have the same length mix; its slot / hit arenas are reused by the next tile in stream order).  The
+        // TEAM = 1 bookkeeping lists the queries it hands to the TEAM = 8 launch on the device -- no host round trip inside a
+        // tile; one status scan + read-back per round.  Queries that found the slot arena full (ST_RETRY) form the next round.
         int soloPerSm = 8;
-        if (const char *e = getenv("SPB_SOLO_CTAS")) soloPerSm = std::max(1, std::min(8, atoi(e)));   // tuning aid (L1 carve-out experiments)
+        if (const char *e = getenv("SPB_SOLO_CTAS")) soloPerSm = std::max(1, std::min(8, atoi(e)));   // tuning aids
         if (const char *e = getenv("SPB_SOLO_CARVEOUT"))    // percent of the 228 KB given to shared memory (the rest is L1)
-            cudaFuncSetAttribute(prefilter_team_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+            cudaFuncSetAttribute(bookkeep_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
         int teamPerSm = 4;
         if (const char *e = getenv("SPB_TEAM_CTAS")) teamPerSm = std::max(1, std::min(4, atoi(e)));
-        if (const char *e = getenv("SPB_TEAM_CARVEOUT"))
-            cudaFuncSetAttribute(prefilter_team_kernel<PW_TEAM>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+        int lookupPerSm = 8, expandPerSm = 8;
+        if (const char *e = getenv("SPB_LOOKUP_CTAS")) lookupPerSm = std::max(1, std::min(16, atoi(e)));
+        if (const char *e = getenv("SPB_EXPAND_CTAS")) expandPerSm = std::max(1, std::min(16, atoi(e)));
         const int soloBlocks = c->n_sm * soloPerSm, teamBlocks = c->n_sm * teamPerSm;
         A.direct = c->d_direct.as<ulonglong2>();
-        uint32_t hitCapSolo = 8192, hitCapTeam = 32768;
-        A.kCapSolo = 4096;
-        if (const char *e = getenv("SPB_KCAP_SOLO")) A.kCapSolo = (uint32_t)atoi(e);        // tuning aids (tools/perf_probe.py)
-        if (const char *e = getenv("SPB_HITCAP_SOLO")) hitCapSolo = (uint32_t)atoi(e);
-        const size_t sliceSolo = 2 * (size_t)hitCapSolo + 2 * PW_FCAP_SOLO, sliceTeam = 2 * (size_t)hitCapTeam + 2 * PW_FCAP_TEAM;
+        A.kbits = c->d_kbits.as<uint32_t>();
+        A.hitsSolo = 4096;
+        if (const char *e = getenv("SPB_HITS_SOLO")) A.hitsSolo = (uint32_t)std::max(1, atoi(e));
+        const uint32_t hitCapSolo = std::max<uint32_t>(A.hitsSolo, PW_SCAP), hitCapTeam = 32768;
+        const size_t sliceSolo = (size_t)hitCapSolo + 2 * PW_FCAP_SOLO, sliceTeam = (size_t)hitCapTeam + 2 * PW_FCAP_TEAM;
+        uint32_t tileQ = 49152;
+        if (const char *e = getenv("SPB_PF_TILEQ")) tileQ = (uint32_t)std::max(256, atoi(e));
+        // chunks of 256 slots a tile may allocate: 12 per query is 2.5 x the mean at -s 5.7; grown when a round had to retry
+        uint32_t chunkCap = (uint32_t)std::min<uint64_t>(1u << 19, (uint64_t)std::min(Q, tileQ) * 12 + 1024);
+        if (const char *e = getenv("SPB_PF_CHUNKS")) chunkCap = (uint32_t)std::max(256, atoi(e));
+        uint32_t hitsPerChunk = 256;
+        if (const char *e = getenv("SPB_PF_HITS_PER_CHUNK")) hitsPerChunk = (uint32_t)std::max(1, atoi(e));
         if (c->s_j.ensure(std::max((size_t)soloBlocks * PW_WARPS * sliceSolo, (size_t)teamBlocks * sliceTeam) * sizeof(uint64_t)) ||
-            c->s_k.ensure((size_t)Q * 4 + 64)) return 1;
-        A.hitCap = hitCapSolo;
+            c->s_k.ensure((size_t)Q * 4 + 64) || c->p_retry.ensure((size_t)Q * 4 + 64) || c->p_meta.ensure((size_t)Q * sizeof(QMeta))) return 1;
         A.hitScratch = c->s_j.as<uint64_t>();
-        unsigned int *d_qc = reinterpret_cast<unsigned int *>(c->s_f.as<unsigned long long>() + 14);   // [0] solo, [1] team scheduler
-        unsigned int *d_ctrT = reinterpret_cast<unsigned int *>(c->s_f.as<unsigned long long>() + 24); // counters of the ST_TEAM scan
-        A.qCounter = d_qc;
-        A.qlist = c->d_qorder.as<uint32_t>();     // longest queries first: their k-mer lists are the long ones (tail of the launch)
-        A.nListPtr = nullptr;
-        A.nList = Q;
-        SPB_CUDA(cudaEventRecord(c->ev0, st));
-        prefilter_team_kernel<1><<<soloBlocks, PW_WARPS * 32, 0, st>>>(A);
-        SPB_CUDA(cudaGetLastError()); c->n_launches++;
-        status_scan_kernel<<<(Q + 255) / 256, 256, 0, st>>>(A.status, A.need, Q, c->s_k.as<uint32_t>(), d_ctrT, ST_TEAM);
-        SPB_CUDA(cudaGetLastError()); c->n_launches++;
-        A.qCounter = d_qc + 1;
-        A.qlist = c->s_k.as<uint32_t>();
-        A.nListPtr = d_ctrT;
-        A.hitCap = hitCapTeam;
-        prefilter_team_kernel<PW_TEAM><<<teamBlocks, PW_TEAM * 32, 0, st>>>(A);
-        SPB_CUDA(cudaGetLastError()); c->n_launches++;
-        A.qlist = nullptr;
-        A.nListPtr = nullptr;
-        SPB_CUDA(cudaEventRecord(c->ev1, st));
-        status_scan_kernel<<<(Q + 255) / 256, 256, 0, st>>>(A.status, A.need, Q, c->s_e.as<uint32_t>(), d_ctr, ST_CAPACITY);
-        SPB_CUDA(cudaGetLastError()); c->n_launches++;
-        SPB_CUDA(cudaMemcpyAsync(h_ctr, d_ctr, 32, cudaMemcpyDeviceToHost, st));
-        SPB_CUDA(cudaStreamSynchronize(st));
-        float ms = 0;
-        SPB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-        kernelMs += ms;
+        A.meta = c->p_meta.as<QMeta>();
+        A.teamList = c->s_k.as<uint32_t>();
+        // tile counters: [0] expand scheduler, [1] TEAM = 1 scheduler, [2] TEAM = 8 scheduler, [3] chunks allocated, [4] team list,
+        // [5] hit records appended
+        unsigned int *tc = reinterpret_cast<unsigned int *>(c->s_f.as<unsigned long long>() + 16);
+        const uint32_t *curList = c->d_qorder.as<uint32_t>();   // longest queries first (tail of a launch)
+        uint32_t curN = Q;
+        unsigned int nTilesRun = 0;
+        bool arenaOverflow = false;
+        for (int round = 0; curN; round++) {
+            // hit arena: 0.56 hits per slot at GenBank-phage size, i.e. ~145 per chunk; 256 per chunk leaves 1.75 x
+            const uint32_t hitArenaCap = (uint32_t)std::min<uint64_t>(0xFFFFFF00ull, (uint64_t)chunkCap * hitsPerChunk);
+            if (c->p_recs.ensure((size_t)chunkCap * PX_CH * 4) || c->p_ctab.ensure((size_t)chunkCap * sizeof(uint2)) ||
+                c->p_ccnt.ensure((size_t)chunkCap * sizeof(uint2)) || c->p_harena.ensure((size_t)hitArenaCap * 8)) return 1;
+            A.recs = c->p_recs.as<uint32_t>();
+            A.chunkTab = c->p_ctab.as<uint2>();
+            A.chunkHits = c->p_ccnt.as<uint2>();
+            A.hitArena = c->p_harena.as<uint64_t>();
+            A.chunkCap = chunkCap;
+            A.hitArenaCap = hitArenaCap;
+            const uint32_t nTiles = (curN + tileQ - 1) / tileQ;
+            SPB_CUDA(cudaEventRecord(c->ev0, st));
+            for (uint32_t t = 0; t < nTiles; t++) {
+                while (c->ev_phase.size() < (size_t)(nTilesRun + 1) * 5) {
+                    cudaEvent_t ev;
+                    SPB_CUDA(cudaEventCreate(&ev));
+                    c->ev_phase.push_back(ev);
+                }
+                cudaEvent_t *ep = c->ev_phase.data() + (size_t)nTilesRun * 5;
+                SPB_CUDA(cudaMemsetAsync(tc, 0, 32, st));
+                A.qlist = curList;
+                A.listOff = t;
+                A.listStride = nTiles;
+                A.nList = (curN - t + nTiles - 1) / nTiles;
+                A.nListPtr = nullptr;
+                A.chunkCursor = tc + 3;
+                A.teamCount = tc + 4;
+                A.hitCursor = tc + 5;
+                A.qCounter = tc + 0;
+                SPB_CUDA(cudaEventRecord(ep[0], st));
+                expand_kernel<<<c->n_sm * expandPerSm, PW_WARPS * 32, 0, st>>>(A);
+                SPB_CUDA(cudaGetLastError()); c->n_launches++;
+                SPB_CUDA(cudaEventRecord(ep[1], st));
+                lookup_kernel<<<c->n_sm * lookupPerSm, PX_CH, 0, st>>>(A);
+                SPB_CUDA(cudaGetLastError()); c->n_launches++;
+                SPB_CUDA(cudaEventRecord(ep[2], st));
+                A.qCounter = tc + 1;
+                A.hitCap = hitCapSolo;
+                bookkeep_kernel<1><<<soloBlocks, PW_WARPS * 32, 0, st>>>(A);
+                SPB_CUDA(cudaGetLastError()); c->n_launches++;
+                SPB_CUDA(cudaEventRecord(ep[3], st));
+                A.qCounter = tc + 2;
+                A.qlist = c->s_k.as<uint32_t>();
+                A.listOff = 0;
+                A.listStride = 1;
+                A.nListPtr = tc + 4;
+                A.hitCap = hitCapTeam;
+                bookkeep_kernel<PW_TEAM><<<teamBlocks, PW_TEAM * 32, 0, st>>>(A);
+                SPB_CUDA(cudaGetLastError()); c->n_launches++;
+                SPB_CUDA(cudaEventRecord(ep[4], st));
+                nTilesRun++;
+            }
+            A.qlist = nullptr;
+            A.nListPtr = nullptr;
+            SPB_CUDA(cudaEventRecord(c->ev1, st));
+            SPB_CUDA(cudaMemsetAsync(d_ctr, 0, 32, st));
+            status_scan_kernel<<<(Q + 255) / 256, 256, 0, st>>>(A.status, A.need, Q, c->s_e.as<uint32_t>(), d_ctr, ST_CAPACITY,
+                                                                c->p_retry.as<uint32_t>());
+            SPB_CUDA(cudaGetLastError()); c->n_launches++;
+            SPB_CUDA(cudaMemcpyAsync(h_ctr, d_ctr, 32, cudaMemcpyDeviceToHost, st));
+            SPB_CUDA(cudaStreamSynchronize(st));
+            float ms = 0;
+            SPB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+            kernelMs += ms;
+            SPB_CHECK(h_ctr[3] == 0, "spb_prefilter: query %u is longer than the supported %d residues", h_ctr[3] - 1, PF_MAXL);
+            SPB_CHECK(h_ctr[4] == 0, "spb_prefilter: query %u was not processed", h_ctr[4] - 1);
+            arenaOverflow = h_ctr[2] != 0;
+            if (arenaOverflow) break;
+            SPB_CHECK(h_ctr[5] < curN || chunkCap < (1u << 21), "spb_prefilter: the slot arena cannot hold a single query");
+            curList = c->p_retry.as<uint32_t>();
+            curN = h_ctr[5];
+            if (curN) {   // next round: larger arenas (the skew of this DB / sensitivity is above the default headroom)
+                chunkCap = (uint32_t)std::min<uint64_t>(1u << 21, (uint64_t)chunkCap * 2);
+                hitsPerChunk = std::min<uint32_t>(hitsPerChunk * 2, 2048);
+            }
+        }
+        for (unsigned int t = 0; t < nTilesRun; t++) {
+            cudaEvent_t *ep = c->ev_phase.data() + (size_t)t * 5;
+            float e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+            SPB_CUDA(cudaEventElapsedTime(&e0, ep[0], ep[1]));
+            SPB_CUDA(cudaEventElapsedTime(&e1, ep[1], ep[2]));
+            SPB_CUDA(cudaEventElapsedTime(&e2, ep[2], ep[3]));
+            SPB_CUDA(cudaEventElapsedTime(&e3, ep[3], ep[4]));
+            phaseMs[0] += e0; phaseMs[1] += e1; phaseMs[2] += e2; phaseMs[3] += e3;
+        }
 #ifdef SPB_PHASE_TIMING
         if (getenv("SPB_DEBUG")) {
             unsigned long long ph[16];
@@ -1859,10 +1931,8 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
             }
         }
 #endif
-        SPB_CHECK(h_ctr[3] == 0, "spb_prefilter: query %u is longer than the supported %d residues", h_ctr[3] - 1, PF_MAXL);
-        SPB_CHECK(h_ctr[4] == 0, "spb_prefilter: query %u was not processed", h_ctr[4] - 1);
-        bool arenaOverflow = h_ctr[2] != 0;
         uint32_t nList = h_ctr[0], maxNeed = 0, capG = 2048;
+        float ms = 0;
         nSlow = nList;
         if (getenv("SPB_DEBUG") && nList) {
             std::vector<uint32_t> hl(nList), hn(Q);
@@ -1881,7 +1951,7 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
             SPB_CUDA(cudaGetLastError()); c->n_launches++;
             SPB_CUDA(cudaEventRecord(c->ev1, st));
             SPB_CUDA(cudaMemsetAsync(d_ctr, 0, 32, st));
-            status_scan_kernel<<<(Q + 255) / 256, 256, 0, st>>>(A.status, A.need, Q, c->s_i.as<uint32_t>(), d_ctr, ST_CAPACITY);
+            status_scan_kernel<<<(Q + 255) / 256, 256, 0, st>>>(A.status, A.need, Q, c->s_i.as<uint32_t>(), d_ctr, ST_CAPACITY, nullptr);
             SPB_CUDA(cudaGetLastError()); c->n_launches++;
             SPB_CUDA(cudaMemcpyAsync(h_ctr, d_ctr, 32, cudaMemcpyDeviceToHost, st));
             SPB_CUDA(cudaStreamSynchronize(st));
@@ -1913,7 +1983,7 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
             // which of them still need more room (their status stays ST_CAPACITY)?
             if (c->s_i.ensure((size_t)Q * 4)) return 1;
             SPB_CUDA(cudaMemsetAsync(d_ctr, 0, 32, st));
-            status_scan_kernel<<<(Q + 255) / 256, 256, 0, st>>>(A.status, A.need, Q, c->s_i.as<uint32_t>(), d_ctr, ST_CAPACITY);
+            status_scan_kernel<<<(Q + 255) / 256, 256, 0, st>>>(A.status, A.need, Q, c->s_i.as<uint32_t>(), d_ctr, ST_CAPACITY, nullptr);
             SPB_CUDA(cudaGetLastError()); c->n_launches++;
             SPB_CUDA(cudaMemcpyAsync(h_ctr, d_ctr, 32, cudaMemcpyDeviceToHost, st));
             SPB_CUDA(cudaStreamSynchronize(st));
@@ -1965,11 +2035,12 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
     SPB_CUDA(cudaEventElapsedTime(&totalMs, c->ev2, c->ev3));
     c->n_hits = nHits;
     if (getenv("SPB_DEBUG")) {
-        unsigned int nTeam = 0;
-        cudaMemcpy(&nTeam, reinterpret_cast<unsigned int *>(c->s_f.as<unsigned long long>() + 24), 4, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "spb_prefilter: %u queries, %u taken by the 8-warp team launch, %llu handed to the CTA kernel "
-                "(long query %u, rows %u, runs %u, k-mers %u, hits %u, bucket %u, max-seqs %u)\n", Q, nTeam,
-                (unsigned long long)nSlow, dbgWhy[1], dbgWhy[2], dbgWhy[3], dbgWhy[4], dbgWhy[5], dbgWhy[6], dbgWhy[7]);
+        unsigned int tcs[8];
+        cudaMemcpy(tcs, reinterpret_cast<unsigned int *>(c->s_f.as<unsigned long long>() + 16), 32, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "spb_prefilter: %u queries; last tile: %u chunks, %u queries taken by the 8-warp team launch; %llu handed to the "
+                "CTA kernel (long query %u, k-mers %u, chunk/scratch %u, bucket %u, max-seqs %u); expand %.3f lookup %.3f "
+                "bookkeeping %.3f + %.3f ms\n", Q, tcs[3], tcs[4], (unsigned long long)nSlow, dbgWhy[1], dbgWhy[4], dbgWhy[5],
+                dbgWhy[6], dbgWhy[7], phaseMs[0], phaseMs[1], phaseMs[2], phaseMs[3]);
     }
     spb_prefilter_result &R = c->pref_stats;
     R.n_hits = nHits;
@@ -1979,6 +2050,9 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
     R.n_slow_path = nSlow;
     R.kernel_ms = kernelMs;
     R.total_ms = totalMs;
+    R.expand_ms = phaseMs[0];
+    R.lookup_ms = phaseMs[1];
+    R.bookkeep_ms = phaseMs[2] + phaseMs[3];
     // algorithmic bytes of one pass over the hit stream: per similar k-mer one 3-mer row entry (4 B) and two
     // CSR offsets (8 B), per index hit one posting (8 B), per query its residues, per output hit 12 B
     R.algo_bytes = R.n_kmers * 12ull + R.n_db_matches * 8ull + c->q_res + nHits * 12ull;
