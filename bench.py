@@ -16,8 +16,9 @@ A "step" is one pass of the search (prefilter -> align) over the whole query bat
             first upload to the last row landed
   roofline: the prefilter match kernel (dominant kernel), algorithmic bytes / its CUDA-event duration against the
             measured HBM peak (MEASURED_PEAKS.json)
-  cpu_baseline / --impl reference: the CPU oracle port (oracle/, OpenMP over queries like the reference) on a
-            bounded sample of the same workload on this host's cores.
+  cpu_baseline / --impl reference: the reference's own CPU implementation -- the unmodified reference binary built by
+            `make -C oracle ref` (oracle/_ref/spacepharer, AVX2 + OpenMP), `prefilter` + `align` with all host threads on DBs
+            written from the same seeds; the oracle port only if that build is missing (said in the line).
 N > 1 (torchrun): `--split-mode query` (default): every rank holds the whole index (1.7 GB of 180 GB) and searches its
 own slice of the batch, no data-path collective; per-GPU work is fixed (10 000 spacers per GPU), so scaling is "weak".
 `--split-mode target`: targets sharded across ranks like MMseqs2 --split, queries replicated, per-query hit lists
@@ -178,6 +179,43 @@ def cpu_reference_run(args, tres, toff, qres, qoff, steps, warmup, sample_spacer
             "ms_per_step": mean * 1e3, "sample_queries": nq, "rows": rows_acc}
 
 
+def reference_binary_run(args, tres, toff, qres, qoff, steps, warmup, single_thread=True):
+    """Times the reference's own CPU implementation of the path: oracle/_ref/spacepharer (the unmodified reference, AVX2 +
+    OpenMP build: `make -C oracle ref`) runs `prefilter` and `align` with the workflow's argv and all host threads on DBs written
+    from the same seeds.  A step = the whole batch; its time = what the modules print themselves ('Time for processing' of
+    prefilter minus 'Time for index table init' -- the GPU arm keeps its index resident too -- plus 'Time for processing' of
+    align)."""
+    from oracle import refbin
+    cores = os.cpu_count() or 1
+    Q = len(qoff) - 1
+    wd = refbin.Workdir(tres, toff)
+    try:
+        wd.add_queries(qres, qoff)
+        runs = []
+        for it in range(warmup + steps):
+            r = refbin.search(wd, threads=cores, tag="s%d" % it, mask=0 if args.no_mask else 1)
+            if it >= warmup:
+                runs.append(r)
+        step = float(np.mean([r["step_s"] for r in runs]))
+        out = {"value": Q / step, "unit": UNIT, "cores": cores, "kind": "reference", "ms_per_step": step * 1e3,
+               "sample_queries": Q, "rows": runs[-1]["rows"],
+               "prefilter_ms": float(np.mean([r["prefilter_s"] for r in runs])) * 1e3,
+               "align_ms": float(np.mean([r["align_s"] for r in runs])) * 1e3,
+               "index_build_s": float(np.mean([r["index_s"] for r in runs])),
+               "sample": "the whole batch (%d frames, %d spacers), %d step(s) of `spacepharer prefilter` + `align --threads %d` "
+                         "(reference binary, AVX2/OpenMP); module-reported processing time, index table init (%.1f s per run) excluded"
+                         % (Q, args.spacers, len(runs), cores, float(np.mean([r["index_s"] for r in runs])))}
+        if single_thread:
+            nq = int(min(Q, max(1, round(500 * Q / float(args.spacers)))))
+            wd.add_queries(qres[: int(qoff[nq])], qoff[: nq + 1], name="queries1")
+            r1 = refbin.search(wd, queries="queries1", threads=1, tag="t1", mask=0 if args.no_mask else 1)
+            out["single_thread"] = {"value": nq / r1["step_s"], "unit": UNIT, "sample_queries": nq,
+                                    "note": "--threads 1 on the first %d frames, same target DB" % nq}
+        return out
+    finally:
+        wd.close()
+
+
 def auto_sample(cores):
     # the scalar port does roughly 350 frames/s/core; aim at ~10 s per CPU step
     return int(max(500, min(10000, 900 * cores)))
@@ -187,24 +225,34 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import refbin
     tres, toff, qres, qoff = workload(args)
     cores = os.cpu_count() or 1
-    sample = args.cpu_sample_spacers or auto_sample(cores)
-    sample = min(sample, args.spacers)
-    masked = None
-    if not args.no_mask:
-        from oracle import pyoracle as O  # noqa: F401  (the port masks with its own tantan restatement)
-        masked = oracle_mask(tres, toff)
-    steps = max(1, min(args.steps, 3))
-    warm = 1 if args.warmup > 0 else 0
-    r = cpu_reference_run(args, tres, toff, qres, qoff, steps, warm, sample, masked)
+    if refbin.available():
+        # the reference itself, same --steps / --warmup as the GPU arm
+        steps, warm = max(1, args.steps), max(0, args.warmup)
+        r = reference_binary_run(args, tres, toff, qres, qoff, steps, warm)
+        note = ("the unmodified reference binary (oracle/_ref/spacepharer, AVX2 + OpenMP) on this host's %d threads; each step = "
+                "prefilter + align of the whole batch, module-reported processing time without the index table init" % cores)
+    else:
+        # fallback, said loudly: the reference build is missing from this snapshot -> scalar C port of the path
+        sys.stderr.write("bench.py: oracle/_ref/spacepharer not found (make -C oracle ref); timing the oracle PORT instead\n")
+        sample = args.cpu_sample_spacers or auto_sample(cores)
+        sample = min(sample, args.spacers)
+        masked = None
+        if not args.no_mask:
+            masked = oracle_mask(tres, toff)
+        steps = max(1, min(args.steps, 3))
+        warm = 1 if args.warmup > 0 else 0
+        r = cpu_reference_run(args, tres, toff, qres, qoff, steps, warm, sample, masked)
+        note = "FALLBACK: CPU port of the reference path (oracle/, scalar C + OpenMP) because the reference build is missing; each step = the bounded sample"
     Q = len(qoff) - 1
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": workload_name(args, Q, len(toff) - 1, int(toff[-1])),
-                       "note": "CPU port of the reference path (oracle/, scalar C + OpenMP); each step = the bounded sample"},
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "config": {"workload": workload_name(args, Q, len(toff) - 1, int(toff[-1])), "note": note},
+            "cpu_baseline": {k: r[k] for k in r if k in ("value", "unit", "cores", "kind", "sample", "prefilter_ms", "align_ms",
+                                                        "index_build_s", "single_thread")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -439,10 +487,16 @@ def run_ours(args):
                             "sw_exhaustive_kernel; cells = sum qLen*tLen, time = max over ranks of the kernel's CUDA-event time, mean of 2 runs"
                             % (int(tsum[3]), args.exhaustive_spacers, T)}
         if not args.no_cpu_baseline and world == 1:
+            from oracle import refbin
             cores = os.cpu_count() or 1
-            sample = min(args.spacers, args.cpu_sample_spacers or auto_sample(cores))
-            r = cpu_reference_run(args, tres, toff, qres, qoff, 1, 0, sample, masked if not args.no_mask else None)
-            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            if refbin.available():   # the reference binary itself, one pass over the whole batch (~10 s of CPU work incl. its index build)
+                r = reference_binary_run(args, tres, toff, qres, qoff, 1, 0, single_thread=False)
+            else:
+                sys.stderr.write("bench.py: oracle/_ref/spacepharer not found (make -C oracle ref); cpu_baseline falls back to the oracle PORT\n")
+                sample = min(args.spacers, args.cpu_sample_spacers or auto_sample(cores))
+                r = cpu_reference_run(args, tres, toff, qres, qoff, 1, 0, sample, masked if not args.no_mask else None)
+            line["cpu_baseline"] = {k: r[k] for k in r if k in ("value", "unit", "cores", "kind", "sample", "prefilter_ms", "align_ms",
+                                                                "index_build_s")}
         emit(line)
     eng.close()
     if world > 1:

@@ -1,6 +1,7 @@
 // capi.cu -- context life cycle, error plumbing, matrices, host-side E-value helpers.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -73,6 +74,7 @@ int spb_ctx_create(int device, spb_ctx **out) {
         int sm = 0;
         if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sm > 0) c->n_sm = sm;
     }
+    if (const char *e = getenv("SPB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));   // tuning aid
     SPB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SPB_CUDA(cudaEventCreate(&c->ev0));
     SPB_CUDA(cudaEventCreate(&c->ev1));

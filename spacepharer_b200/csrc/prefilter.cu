@@ -77,7 +77,6 @@ struct PrefArgs {
     uint2 *chunkTab;         // [chunkCap] (query, stream-order number of the chunk's first slot)
     uint2 *chunkHits;        // [chunkCap] (first hit record of the chunk in hitArena, number of hits | PX_OVER)
     uint64_t *hitArena;      // [hitArenaCap] hit records, chunk after chunk: id << 32 | k << 16 | 16-bit diagonal
-    unsigned int *hitCursor; // records appended in this tile
     uint32_t hitArenaCap;
     struct QMeta *meta;      // [Q]
     unsigned int *chunkCursor;   // chunks allocated in this tile
@@ -857,65 +856,104 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 8) expand_kernel(PrefArgs A) {
     }
 }
 
-// The gather.  CTA = one chunk of 256 slots per trip (grid-stride over the chunks the tile allocated; the count is read from
-// device memory, no host round trip after expand_kernel).  The hits of a chunk are compacted (CTA-wide scan) and appended to
-// the tile's dense hit arena with ONE atomic reservation per chunk; chunkHits[c] = (first record, count).  k-mer frequencies
-// are far from uniform (a 6-mer of common residues occurs dozens of times), so a chunk holds anything from 0 to thousands
-// of hits.  A chunk that finds the arena full stores count = PX_OVER and its query is run again in the next round.
-__global__ void __launch_bounds__(PX_CH) lookup_kernel(PrefArgs A) {
-    __shared__ uint32_t s_w[PX_CH / 32];
-    __shared__ uint32_t s_hbase;
+// The gather.  A CTA takes a PAIR of chunks (512 slots, two per thread) per trip, grid-stride over the chunks the tile
+// allocated (the count is read from device memory: no host round trip after expand_kernel).  Per slot: occupancy bit (L2) ->
+// 16-byte table entry (DRAM, streaming load) -> 0, 1 or 2 inline postings or a posting list; the slot records of the next
+// pair are already in flight.  The hits of the pair are compacted in slot order (two CTA-wide scans sharing ONE barrier) and
+// appended to the CTA's private stretch of the tile's hit arena -- every thread advances the same private cursor, so there is
+// no atomic and no second barrier on the path; chunkHits[c] = (first record, count).  k-mer frequencies are far from uniform
+// (a 6-mer of common residues occurs dozens of times: 5 % of the looked-up k-mers hold 38 % of the hits in lists of three or
+// more), so a chunk holds anything from 0 to thousands of hits.  A pair that finds its stretch full stores count = PX_OVER
+// and its queries run again in the next round.
+__device__ __forceinline__ uint64_t hit_record(uint64_t pe, uint64_t kw, uint32_t w) {
+    return ((pe >> 16) << 32) | kw | (uint64_t)((w - (uint32_t)(pe & 0xFFFFull)) & 0xFFFFu);
+}
+
+__global__ void __launch_bounds__(PX_CH, 6) lookup_kernel(PrefArgs A) {
+    __shared__ uint32_t s_w[2][2][PX_CH / 32];     // [trip parity][chunk of the pair][warp]
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t nCh = min(*A.chunkCursor, A.chunkCap);
     const uint64_t *__restrict__ post = A.post;
-    for (uint32_t c = blockIdx.x; c < nCh; c += gridDim.x) {
-        const uint32_t rec = __ldcs(A.recs + (size_t)c * PX_CH + tid);
-        const uint32_t kmer = rec & 0x03FFFFFFu, w = rec >> 26;
-        ulonglong2 e = make_ulonglong2(0ull, 0ull);
-        uint32_t n = 0;
-        if (kmer < SPB_NK && ((__ldg(A.kbits + (kmer >> 5)) >> (kmer & 31)) & 1u)) {
-            e = __ldcs(A.direct + kmer);
-            n = (e.x >> 63) ? 1u + (uint32_t)(e.y >> 63) : (uint32_t)(e.x >> 32);
-        }
-        const uint32_t inc = (uint32_t)warp_incl_scan((int)n);
-        if (lane == 31) s_w[wid] = inc;
-        __syncthreads();
-        uint32_t off = inc - n, total = 0;
+    uint64_t *__restrict__ arena = A.hitArena;
+    const uint32_t nPairs = (nCh + 1) >> 1;
+    // private stretch of the hit arena
+    const uint32_t stretch = A.hitArenaCap / gridDim.x;
+    uint32_t cur = blockIdx.x * stretch;
+    const uint32_t curEnd = cur + stretch;
+    uint32_t rec[2] = {PX_INVALID, PX_INVALID};
+    if (blockIdx.x < nPairs) {
 #pragma unroll
-        for (int i = 0; i < PX_CH / 32; i++) {
-            const uint32_t v = s_w[i];
-            if (i < wid) off += v;
-            total += v;
+        for (int u = 0; u < 2; u++)
+            if (2 * blockIdx.x + u < nCh) rec[u] = __ldcs(A.recs + (size_t)(2 * blockIdx.x + u) * PX_CH + tid);
+    }
+    int par = 0;
+    for (uint32_t pr = blockIdx.x; pr < nPairs; pr += gridDim.x, par ^= 1) {
+        const uint32_t c0 = 2 * pr;
+        uint32_t kmer[2], w[2], n[2];
+        ulonglong2 e[2];
+        bool occ[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            kmer[u] = rec[u] & 0x03FFFFFFu;
+            w[u] = rec[u] >> 26;
+            occ[u] = kmer[u] < SPB_NK && ((__ldg(A.kbits + (kmer[u] >> 5)) >> (kmer[u] & 31)) & 1u);
         }
+        // slot records of the next pair: in flight while this one waits for its table entries
+        const uint32_t prN = pr + gridDim.x;
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+            rec[u] = (prN < nPairs && 2 * prN + u < nCh) ? __ldcs(A.recs + (size_t)(2 * prN + u) * PX_CH + tid) : PX_INVALID;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            e[u] = make_ulonglong2(0ull, 0ull);
+            if (occ[u]) e[u] = __ldcs(A.direct + kmer[u]);
+        }
+        uint32_t inc[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            n[u] = (e[u].x >> 63) ? 1u + (uint32_t)(e[u].y >> 63) : (uint32_t)(e[u].x >> 32);
+            inc[u] = (uint32_t)warp_incl_scan((int)n[u]);
+            if (lane == 31) s_w[par][u][wid] = inc[u];
+        }
+        __syncthreads();     // the only barrier of the trip (the warp totals are double-buffered by trip parity)
+        // prefix over the warps of the CTA: lanes 0..7 hold the warp totals, two warp reductions give (before me, all)
+        uint32_t off[2], total[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const uint32_t v = (lane < PX_CH / 32) ? s_w[par][u][lane] : 0u;
+            total[u] = __reduce_add_sync(0xffffffffu, v);
+            off[u] = __reduce_add_sync(0xffffffffu, lane < wid ? v : 0u) + inc[u] - n[u];
+        }
+        const uint32_t tt = total[0] + total[1];
+        const bool fits = tt <= curEnd - cur;
         if (tid == 0) {
-            uint32_t hb = 0;
-            if (total) hb = atomicAdd(A.hitCursor, total);
-            const bool fits = (uint64_t)hb + total <= (uint64_t)A.hitArenaCap;
-            A.chunkHits[c] = make_uint2(hb, fits ? total : PX_OVER);
-            s_hbase = fits ? hb : PX_OVER;
+            A.chunkHits[c0] = make_uint2(cur, fits ? total[0] : PX_OVER);
+            if (c0 + 1 < nCh) A.chunkHits[c0 + 1] = make_uint2(cur + total[0], fits ? total[1] : PX_OVER);
         }
-        __syncthreads();
-        const uint32_t hb = s_hbase;
-        if (n && hb != PX_OVER) {
-            const uint32_t k = A.chunkTab[c].y + (uint32_t)tid;
-            uint64_t *__restrict__ dst = A.hitArena + (size_t)hb + off;
-            const uint64_t kw = (uint64_t)k << 16;
-            if (e.x >> 63) {
-                dst[0] = ((e.x >> 16) << 32) | kw | (uint64_t)((w - (uint32_t)(e.x & 0xFFFFull)) & 0xFFFFu);
-                if (e.y >> 63) dst[1] = ((e.y >> 16) << 32) | kw | (uint64_t)((w - (uint32_t)(e.y & 0xFFFFull)) & 0xFFFFu);
-            } else {
-                // list of three or more postings: four independent loads in flight per trip
-                const uint64_t *__restrict__ pl = post + (uint32_t)e.x;
-                for (uint32_t z = 0; z < n; z += 4) {
-                    uint64_t pe[4];
+        if (!fits) continue;
 #pragma unroll
-                    for (int u = 0; u < 4; u++) pe[u] = (z + u < n) ? __ldg(pl + z + u) : 0ull;
+        for (int u = 0; u < 2; u++) {
+            if (n[u]) {
+                uint64_t *__restrict__ dst = arena + (size_t)(cur + (u ? total[0] : 0u) + off[u]);
+                const uint64_t kw = (uint64_t)(A.chunkTab[c0 + u].y + (uint32_t)tid) << 16;
+                if (e[u].x >> 63) {
+                    dst[0] = hit_record(e[u].x, kw, w[u]);
+                    if (e[u].y >> 63) dst[1] = hit_record(e[u].y, kw, w[u]);
+                } else {
+                    // list of three or more postings: four independent loads in flight per trip
+                    const uint64_t *__restrict__ pl = post + (uint32_t)e[u].x;
+                    for (uint32_t z = 0; z < n[u]; z += 4) {
+                        uint64_t pe[4];
 #pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if (z + u < n) dst[z + u] = ((pe[u] >> 16) << 32) | kw | (uint64_t)((w - (uint32_t)(pe[u] & 0xFFFFull)) & 0xFFFFu);
+                        for (int v = 0; v < 4; v++) pe[v] = (z + v < n[u]) ? __ldg(pl + z + v) : 0ull;
+#pragma unroll
+                        for (int v = 0; v < 4; v++)
+                            if (z + v < n[u]) dst[z + v] = hit_record(pe[v], kw, w[u]);
+                    }
                 }
             }
         }
+        cur += tt;
     }
 }
 
@@ -1006,9 +1044,9 @@ __device__ __forceinline__ void block_bitonic_pairs(uint64_t *k, uint64_t *v, in
 template <int TEAM>
 __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 ? 8 : 4) bookkeep_kernel(PrefArgs A) {
     constexpr bool SOLO = (TEAM == 1);
-    // "seen once" / "seen twice" bitmaps over hashed target ids.  TEAM = 1: 16384 / 4096 bits -- with ~600 hits per frame a
-    // dozen pairs collide in seen1, and the coarser seen2 adds a handful of false survivors, so the survivor set usually
-    // fits the register sort (<= 32); TEAM = 8: 32768 / 32768 bits.
+    // seen1: hashed (target, 8-bit diagonal) pairs seen once; seen2: hashed targets with a repeated pair.  TEAM = 1: 16384 /
+    // 4096 bits -- with ~600 hits per frame a dozen pairs collide in seen1 and the coarser seen2 adds a handful of false
+    // survivors, so the survivor set usually fits the register sort (<= 32); TEAM = 8: 32768 / 32768 bits.
     constexpr int H1 = SOLO ? 14 : 15, H2 = SOLO ? 12 : 15;
     constexpr int BM1 = (1 << H1) / 32, BM2 = (1 << H2) / 32;
     constexpr int NQS = SOLO ? PW_WARPS : 1;
@@ -1102,15 +1140,22 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
         const uint32_t K = S.v_K;
         const uint32_t nHits = S.v_nHits;
         const bool live = (S.v_slow == ST_OK);
-        // ---------------- pass 1 over the hit stream: targets seen once / twice ----------------
+        // ---------------- pass 1 over the hit stream: (target, 8-bit diagonal) pairs seen once; targets with a repeated pair ----------------
+        // An event needs the previous hit of its target on the same 8-bit diagonal (or, first hit, diagonal 0: quirk B), so
+        // only targets in which some (target, diagonal) pair occurs twice -- or a diagonal 0 -- can produce one; ALL records of
+        // such a target are kept below (hits on other diagonals in between break the adjacency).  Random second hits of a
+        // target lie on another diagonal 255 times out of 256, so the survivor set is the true diagonal matches plus a few
+        // hash collisions instead of every target hit twice.
         if (live) {
             for_hits([&](uint64_t r, bool valid) {
                 if (valid) {
-                    const uint32_t h = ((uint32_t)(r >> 32) * 2654435761u) >> (32 - H1);
+                    const uint32_t x = (uint32_t)(r >> 32) * 2654435761u;
+                    const uint32_t d8 = (uint32_t)r & 0xFFu;
+                    const uint32_t h = ((x + d8 * 0x9E3779B9u) * 0x85EBCA6Bu) >> (32 - H1);
                     const uint32_t bm = 1u << (h & 31);
                     const uint32_t old = atomicOr(&S.seen1[h >> 5], bm);
-                    if ((old & bm) || ((uint32_t)r & 0xFFu) == 0u) {
-                        const uint32_t h2 = h >> (H1 - H2);
+                    if ((old & bm) || d8 == 0u) {
+                        const uint32_t h2 = x >> (32 - H2);
                         atomicOr(&S.seen2[h2 >> 5], 1u << (h2 & 31));
                     }
                 }
@@ -1146,7 +1191,45 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
         if (live) {
             const uint32_t c0 = cnt64[2 * lane], c1 = cnt64[2 * lane + 1];
             if (SOLO && nS0 <= PW_SCAP) {
-                nSurv = (uint32_t)nS0;    // everything already sits in the sort buffer: one group, no scatter
+                // everything already sits in the sort buffer: one group, no scatter.  More than one register sort's worth: most
+                // of it is hash collisions of pass 1 (they grow with the square of the hits).  Run the (target, diagonal) test
+                // once more on the survivors alone, with other hash functions, and keep the targets that pass again.
+                if (nS0 > 32) {
+                    for (int i = lane; i < BM1; i += 32) S.seen1[i] = 0;
+                    for (int i = lane; i < BM2; i += 32) S.seen2[i] = 0;
+                    __syncwarp();
+                    for (int i = lane; i < nS0; i += 32) {
+                        const uint64_t r = W.surv[i];
+                        const uint32_t x = (uint32_t)(r >> 32) * 0xC2B2AE35u;
+                        const uint32_t d8 = (uint32_t)r & 0xFFu;
+                        const uint32_t h = ((x ^ (d8 * 0x27D4EB2Fu)) * 0x165667B1u) >> (32 - H1);
+                        const uint32_t bm = 1u << (h & 31);
+                        const uint32_t old = atomicOr(&S.seen1[h >> 5], bm);
+                        if ((old & bm) || d8 == 0u) {
+                            const uint32_t h2 = x >> (32 - H2);
+                            atomicOr(&S.seen2[h2 >> 5], 1u << (h2 & 31));
+                        }
+                    }
+                    __syncwarp();
+                    int outN = 0;
+                    for (int c0i = 0; c0i < nS0; c0i += 32) {
+                        const int i = c0i + lane;
+                        uint64_t r = 0;
+                        bool keep = false;
+                        if (i < nS0) {
+                            r = W.surv[i];
+                            const uint32_t h2 = ((uint32_t)(r >> 32) * 0xC2B2AE35u) >> (32 - H2);
+                            keep = (S.seen2[h2 >> 5] >> (h2 & 31)) & 1u;
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, keep);
+                        __syncwarp();
+                        if (keep) W.surv[outN + __popc(m & lt)] = r;
+                        outN += __popc(m);
+                        __syncwarp();
+                    }
+                    nS0 = outN;
+                }
+                nSurv = (uint32_t)nS0;
             } else {
                 // level l uses 64 >> l groups; the largest merged bucket grows with l, so the last level that fits wins
                 uint32_t sum = c0 + c1;
@@ -1803,7 +1886,7 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
             cudaFuncSetAttribute(bookkeep_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
         int teamPerSm = 4;
         if (const char *e = getenv("SPB_TEAM_CTAS")) teamPerSm = std::max(1, std::min(4, atoi(e)));
-        int lookupPerSm = 8, expandPerSm = 8;
+        int lookupPerSm = 6, expandPerSm = 8;
         if (const char *e = getenv("SPB_LOOKUP_CTAS")) lookupPerSm = std::max(1, std::min(16, atoi(e)));
         if (const char *e = getenv("SPB_EXPAND_CTAS")) expandPerSm = std::max(1, std::min(16, atoi(e)));
         const int soloBlocks = c->n_sm * soloPerSm, teamBlocks = c->n_sm * teamPerSm;
@@ -1825,8 +1908,7 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
         A.hitScratch = c->s_j.as<uint64_t>();
         A.meta = c->p_meta.as<QMeta>();
         A.teamList = c->s_k.as<uint32_t>();
-        // tile counters: [0] expand scheduler, [1] TEAM = 1 scheduler, [2] TEAM = 8 scheduler, [3] chunks allocated, [4] team list,
-        // [5] hit records appended
+        // tile counters: [0] expand scheduler, [1] TEAM = 1 scheduler, [2] TEAM = 8 scheduler, [3] chunks allocated, [4] team list
         unsigned int *tc = reinterpret_cast<unsigned int *>(c->s_f.as<unsigned long long>() + 16);
         const uint32_t *curList = c->d_qorder.as<uint32_t>();   // longest queries first (tail of a launch)
         uint32_t curN = Q;
@@ -1860,13 +1942,12 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
                 A.nListPtr = nullptr;
                 A.chunkCursor = tc + 3;
                 A.teamCount = tc + 4;
-                A.hitCursor = tc + 5;
                 A.qCounter = tc + 0;
                 SPB_CUDA(cudaEventRecord(ep[0], st));
                 expand_kernel<<<c->n_sm * expandPerSm, PW_WARPS * 32, 0, st>>>(A);
                 SPB_CUDA(cudaGetLastError()); c->n_launches++;
                 SPB_CUDA(cudaEventRecord(ep[1], st));
-                lookup_kernel<<<c->n_sm * lookupPerSm, PX_CH, 0, st>>>(A);
+                lookup_kernel<<<c->n_sm * lookupPerSm, PX_CH, 0, st>>>(A);   // persistent: lookupPerSm CTAs per SM
                 SPB_CUDA(cudaGetLastError()); c->n_launches++;
                 SPB_CUDA(cudaEventRecord(ep[2], st));
                 A.qCounter = tc + 1;

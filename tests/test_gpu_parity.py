@@ -94,6 +94,40 @@ def test_prefilter_family_truncation_golden(searcher, fname, maxseqs):
     assert not bad, bad[:5]
 
 
+@pytest.mark.parametrize("sens,thr", [("1.0", 154), ("4.0", 127), ("7.5", 96)])
+def test_prefilter_small_sensitivities_golden(searcher, sens, thr):
+    """-s 1.0 / 4.0 / 7.5: index-side self-score pruning (thr 127, 154: IndexTable.h:141-148) and doubled similar-k-mer
+    lists (thr 96), against the reference binary's lists and the oracle"""
+    from spacepharer_b200 import api
+    assert api.kmer_threshold(float(sens)) == thr
+    T, Q = Cm.load_fasta_set("small")
+    tres, toff = _product_mask(searcher, T)
+    searcher.build_index(tres, toff, kmer_thr=thr)
+    qres, qoff = O.concat(Q)
+    off, hits, st = searcher.prefilter(qres, qoff, kmer_thr=thr)
+    rows = [api.format_prefilter_rows(hits[int(off[i]):int(off[i + 1])]) for i in range(len(Q))]
+    ref = Cm.dump("small", "pref_s%s.txt.gz" % sens)
+    bad = [(i, rows[i][:3], ref.get(i, [])[:3]) for i in range(len(Q)) if rows[i] != ref.get(i, [])]
+    assert not bad, bad[:5]
+    m80, m40u, _ = Cm.mats()
+    pf = O.Prefilter(tres, toff, m80, m40u, kmer_thr=thr)
+    ooff, ohits = pf.batch(qres, qoff)
+    pf.close()
+    assert (off == ooff).all() and (hits["id"] == ohits["id"]).all() and (hits["score"] == ohits["score"]).all()
+    assert st["n_kmers"] > 0
+
+
+@pytest.mark.parametrize("maxseqs", [300, 10, 3])
+def test_prefilter_saturated_families_golden(searcher, maxseqs):
+    """the all-saturated cut (rescoreHits, QueryMatcher.cpp:149-155,486-505): 60-140-aa queries against 40-member families"""
+    T, Q = Cm.load_fasta_set("saturated")
+    tres, toff = _product_mask(searcher, T)
+    rows, st = _gpu_prefilter_rows(searcher, tres, toff, Q, max_seqs=maxseqs)
+    ref = Cm.dump("saturated", "pref_max%d.txt.gz" % maxseqs)
+    bad = [(i, rows[i][:3], ref.get(i, [])[:3]) for i in range(len(Q)) if rows[i] != ref.get(i, [])]
+    assert not bad, bad[:5]
+
+
 def test_prefilter_long_golden(searcher):
     T, Q = Cm.load_fasta_set("long")
     tres, toff = _product_mask(searcher, T)

@@ -166,6 +166,44 @@ def test_predictmatch_default_reference_example(c1_dbs, tmp_path):
 
 
 @pytest.mark.gpu
+def test_final_tsv_identical_to_reference(c1_dbs, tmp_path):
+    """BASELINE config 1 down to the final match TSV: `spb200 predictmatch` (default pipeline) writes `aggregate` and `match`;
+    the reference's own six post-processing modules (data/predictmatch.sh:127-168, run by the reference binary as the checker)
+    turn them into result.tsv, which must equal the reference's easy-predict output byte for byte."""
+    import common as Cm
+    from oracle import refbin
+    if not refbin.available():
+        pytest.skip("reference build (oracle/_ref/spacepharer, make -C oracle ref) not in this snapshot")
+    w, out = c1_dbs, str(tmp_path / "pm")
+    os.makedirs(out)
+    run("predictmatch", w + "/qsetdb", w + "/targets", w + "/targets_rev", out + "/match", out, "--threads", "2", "--keep-intermediate", "1")
+    post = str(tmp_path / "post")
+    os.makedirs(post)
+    tsv = Cm.reference_postprocess(post, out + "/aggregate", out + "/match")
+    gold = open(os.path.join(C1, "result.tsv"), "rb").read()
+    assert tsv == gold
+    assert tsv.count(b"\n") == 8 and b"AY369265.2\t1.224E+01" in tsv      # SURVEY 8c: 1 + 5 hits under two set lines
+
+
+def test_reference_postprocess_harness_reproduces_the_golden_tsv(tmp_path):
+    """CPU: the checker itself -- the reference's post-processing on the reference's own aggregate / match rows (golden dumps)
+    gives the committed result.tsv, so a difference in the GPU test above can only come from our DBs"""
+    import common as Cm
+    from oracle import refbin
+    if not refbin.available():
+        pytest.skip("reference build (oracle/_ref/spacepharer, make -C oracle ref) not in this snapshot")
+    w = str(tmp_path)
+    qkeys = sorted(dbio.read_entries(os.path.join(C1, "qsetdb")))
+    # aggregate is keyed by query sequence, match by query set
+    db_from_dump(w + "/agg", os.path.join(C1, "nucl_sets_aggregate.txt.gz"), qkeys)
+    skeys = sorted(dbio.read_entries(os.path.join(C1, "qsetdb_set_size")))
+    db_from_dump(w + "/match", os.path.join(C1, "nucl_sets_match.txt.gz"), skeys, dbtype=dbio.DBTYPE_GENERIC_DB)
+    post = w + "/post"
+    os.makedirs(post)
+    assert Cm.reference_postprocess(post, w + "/agg", w + "/match") == open(os.path.join(C1, "result.tsv"), "rb").read()
+
+
+@pytest.mark.gpu
 def test_predictmatch_default_synthetic_arrays(sets_dbs, tmp_path):
     w, out = sets_dbs, str(tmp_path)
     r = run("predictmatch", w + "/qsetdb", w + "/targets", w + "/targets_rev", out + "/match", out, "--threads", "4", "--keep-intermediate", "1",

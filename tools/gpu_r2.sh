@@ -19,4 +19,22 @@ if [[ " $* " == *" ncu "* ]]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'expand_kernel|lookup_kernel|bookkeep_kernel' -s 4 -c 4 \
       -o $OUT/prof_$TAG -f python tools/perf_probe.py > $OUT/prof_$TAG.log 2>&1; echo "ncu rc=$?"
 fi
+if [[ " $* " == *" l2 "* ]]; then   # (r2c: cudaLimitMaxL2FetchGranularity 32/64/128 leaves the DRAM bytes unchanged)
+  for g in 32 64 128; do
+    SPB_L2_FETCH=$g timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+        -k regex:'lookup_kernel|bookkeep_kernel|expand_kernel' -s 4 -c 4 --csv --log-file $OUT/l2fetch_${g}_$TAG.csv python tools/perf_probe.py > /dev/null 2>&1
+    SPB_L2_FETCH=$g SPB_DEBUG=1 timeout 600 python tools/perf_probe.py 2>&1 | grep "spb_prefilter:" | tail -1 > $OUT/l2fetch_${g}_$TAG.txt
+  done
+fi
+if [[ " $* " == *" sweep "* ]]; then
+  for v in 1024 2048 8192; do
+    echo "SPB_HITS_SOLO=$v"; SPB_HITS_SOLO=$v SPB_DEBUG=1 timeout 600 python tools/perf_probe.py 2>&1 | grep "spb_prefilter:" | tail -1 | grep -o "expand.*"
+  done
+  for v in 4 5 8; do
+    echo "SPB_LOOKUP_CTAS=$v"; SPB_LOOKUP_CTAS=$v SPB_DEBUG=1 timeout 600 python tools/perf_probe.py 2>&1 | grep "spb_prefilter:" | tail -1 | grep -o "expand.*"
+  done
+  for v in 6 10; do
+    echo "SPB_EXPAND_CTAS=$v"; SPB_EXPAND_CTAS=$v SPB_DEBUG=1 timeout 600 python tools/perf_probe.py 2>&1 | grep "spb_prefilter:" | tail -1 | grep -o "expand.*"
+  done
+fi
 echo done
