@@ -19,9 +19,12 @@ static bool file_exists(const std::string &p) {
 static void append_file(const std::string &p, std::vector<char> &out) {
     FILE *f = fopen(p.c_str(), "rb");
     if (!f) throw std::runtime_error("Could not open data file " + p + "!");
-    fseek(f, 0, SEEK_END);
-    long n = ftell(f);
-    fseek(f, 0, SEEK_SET);
+    long n = -1;
+    if (fseek(f, 0, SEEK_END) == 0) n = ftell(f);
+    if (n < 0 || fseek(f, 0, SEEK_SET) != 0) {
+        fclose(f);
+        throw std::runtime_error("Failed to read data file " + p);
+    }
     size_t at = out.size();
     out.resize(at + (size_t)n);
     if (n > 0 && fread(out.data() + at, 1, (size_t)n, f) != (size_t)n) {
@@ -111,34 +114,66 @@ void DBWriter::write(int thread, uint32_t key, const char *payload, size_t len) 
     p.idx.push_back(e);
 }
 
+// Every write is checked: a failed or short write (ENOSPC, I/O error) must not leave a DB behind that looks finished -- the
+// workflow scripts take <name>.dbtype as the "step done" marker (blastp.sh:31,39), so it is written last, via a temporary file
+// and rename().
+static void write_all(const std::string &path, const char *mode, const void *data, size_t n) {
+    FILE *f = fopen(path.c_str(), mode);
+    if (!f) throw std::runtime_error("Could not open " + path + " for writing!");
+    const bool ok = (n == 0 || fwrite(data, 1, n, f) == n);
+    const bool closed = (fclose(f) == 0);
+    if (!ok || !closed) {
+        remove(path.c_str());
+        throw std::runtime_error("Could not write to " + path);
+    }
+}
+
+static inline char *put_u64(char *p, unsigned long long v) {
+    char tmp[24];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
 void DBWriter::close() {
     FILE *f = fopen(name_.c_str(), "wb");
     if (!f) throw std::runtime_error("Could not open " + name_ + " for writing!");
     std::vector<DBEntry> all;
     uint64_t base = 0;
+    bool ok = true;
     for (Part &p : parts_) {
-        if (!p.data.empty() && fwrite(p.data.data(), 1, p.data.size(), f) != p.data.size()) {
-            fclose(f);
-            throw std::runtime_error("Could not write to " + name_);
-        }
+        if (!p.data.empty() && fwrite(p.data.data(), 1, p.data.size(), f) != p.data.size()) ok = false;
         for (DBEntry e : p.idx) {
             e.offset += base;
             all.push_back(e);
         }
         base += p.data.size();
     }
-    fclose(f);
+    if (fclose(f) != 0) ok = false;
+    if (!ok) {
+        remove(name_.c_str());
+        throw std::runtime_error("Could not write to " + name_);
+    }
     std::stable_sort(all.begin(), all.end(), [](const DBEntry &a, const DBEntry &b) { return a.key < b.key; });
-    FILE *ix = fopen((name_ + ".index").c_str(), "w");
-    if (!ix) throw std::runtime_error("Could not open " + name_ + ".index for writing!");
-    for (const DBEntry &e : all) fprintf(ix, "%u\t%llu\t%llu\n", e.key, (unsigned long long)e.offset, (unsigned long long)e.length);
-    fclose(ix);
-    FILE *t = fopen((name_ + ".dbtype").c_str(), "wb");
-    if (!t) throw std::runtime_error("Could not open " + name_ + ".dbtype for writing!");
-    unsigned char b[4] = {(unsigned char)(dbtype_ & 0xFF), (unsigned char)((dbtype_ >> 8) & 0xFF), (unsigned char)((dbtype_ >> 16) & 0xFF),
-                          (unsigned char)((dbtype_ >> 24) & 0xFF)};
-    fwrite(b, 1, 4, t);
-    fclose(t);
+    // index lines "key\toffset\tlength\n", formatted into one buffer (no stdio call per entry)
+    std::string ix;
+    ix.resize(all.size() * 64 + 64);
+    char *w = &ix[0];
+    for (const DBEntry &e : all) {
+        w = put_u64(w, e.key); *w++ = '\t';
+        w = put_u64(w, (unsigned long long)e.offset); *w++ = '\t';
+        w = put_u64(w, (unsigned long long)e.length); *w++ = '\n';
+    }
+    write_all(name_ + ".index", "wb", ix.data(), (size_t)(w - ix.data()));
+    const unsigned char b[4] = {(unsigned char)(dbtype_ & 0xFF), (unsigned char)((dbtype_ >> 8) & 0xFF), (unsigned char)((dbtype_ >> 16) & 0xFF),
+                                (unsigned char)((dbtype_ >> 24) & 0xFF)};
+    const std::string tmp = name_ + ".dbtype.tmp";
+    write_all(tmp, "wb", b, 4);
+    if (rename(tmp.c_str(), (name_ + ".dbtype").c_str()) != 0) {
+        remove(tmp.c_str());
+        throw std::runtime_error("Could not write to " + name_ + ".dbtype");
+    }
     parts_.clear();
 }
 

@@ -77,6 +77,10 @@ struct Params {
     double scoreBias = 0.0;
     int threads = 1, verbosity = 3, compressed = 0;
     // spb200-specific
+    // flags whose non-default values would change the reference's result but are not implemented: parsed so that they can be
+    // refused (check_unimplemented_flags) instead of being silently ignored
+    std::string alphSize = "nucl:5,aa:21", taxonList;
+    int maxSeqLen = 65535;
     int device = 0, binSize = 0, byteLanes = 32, wordLanes = 16;
     std::string gumbel, gumbelNucl;
     long batch = 250000;       // frames per GPU pass: formatting of batch k overlaps the kernels of batch k+1 (1 M spacers: 4.2 -> 3.7 s)
@@ -107,10 +111,10 @@ std::vector<FlagDef> flag_table(Params &p) {
         {"--gap-extend", 3, &p.gapExtend}, {"--score-bias", 2, &p.scoreBias}, {"--threads", 0, &p.threads},
         {"-v", 0, &p.verbosity}, {"--compressed", 0, &p.compressed},
         // accepted and without influence on this path (profile / nucleotide / memory-management flags of the same modules)
-        {"--alph-size", 4, nullptr}, {"--max-seq-len", 4, nullptr}, {"--split-memory-limit", 4, nullptr},
+        {"--alph-size", 3, &p.alphSize}, {"--max-seq-len", 0, &p.maxSeqLen}, {"--split-memory-limit", 4, nullptr},
         {"--db-load-mode", 4, nullptr}, {"--pca", 4, nullptr}, {"--pcb", 4, nullptr}, {"--alignment-output-mode", 4, nullptr},
         {"--wrapped-scoring", 4, nullptr}, {"--realign-score-bias", 4, nullptr}, {"--realign-max-seqs", 4, nullptr},
-        {"--zdrop", 4, nullptr}, {"--local-tmp", 4, nullptr}, {"--taxon-list", 4, nullptr}, {"--exhaustive-search-filter", 4, nullptr},
+        {"--zdrop", 4, nullptr}, {"--local-tmp", 4, nullptr}, {"--taxon-list", 3, &p.taxonList}, {"--exhaustive-search-filter", 4, nullptr},
         {"--exhaustive-search", 0, &p.exhaustive},
         {"--simple-best-hit", 0, &p.simpleBestHit}, {"--fdr", 1, &p.fdr}, {"--report-fdr", 0, &p.reportFdr},
         {"--perform-nucl-aln", 0, &p.performNuclAln}, {"--tax-fdr", 4, nullptr}, {"--remove-tmp-files", 4, nullptr},
@@ -402,7 +406,37 @@ void build_target_index(Engine &E, const Params &p, const SeqSet &T, int kmerThr
                  (unsigned long long)st.n_postings, st.build_ms);
 }
 
+// Flags of the prefilter / align modules that change the reference's output and that this path does not implement keep the
+// reference's default here; any other value is refused (a drop-in must not exit 0 with a different DB).  Flags that stay in
+// the "accepted, no influence" class are inert under the settings this path already requires: --cov-mode (needs -c > 0),
+// --split-mode (needs --split > 1), --realign-score-bias / --realign-max-seqs (need --realign 1), --zdrop (nucleotide
+// alignment only), --alignment-output-mode 0, --pca / --pcb (profiles), --db-load-mode, --split-memory-limit (memory management).
+void check_unimplemented_flags(const Params &p) {
+    if (p.maskLower != 0) throw Fail("--mask-lower-case 1 is not supported (lower-case masking is not applied to the index)");
+    {
+        // "--alph-size nucl:5,aa:21" or a single number for both
+        std::string aa = p.alphSize;
+        const size_t at = aa.find("aa:");
+        if (at != std::string::npos) aa = aa.substr(at + 3);
+        const size_t comma = aa.find(',');
+        if (comma != std::string::npos) aa = aa.substr(0, comma);
+        if (aa.find("nucl:") == 0) aa = "21";
+        if (atoi(aa.c_str()) != 21) throw Fail("--alph-size " + p.alphSize + ": only the full amino-acid alphabet (aa:21) is supported");
+    }
+    if (!p.taxonList.empty()) throw Fail("--taxon-list is not supported");
+    if (p.maxSeqLen < 1) throw Fail("Error in argument --max-seq-len");
+}
+
+// --max-seq-len: the reference splits / truncates longer sequences (Sequence.cpp); here longer entries are refused
+void check_seq_len(const Params &p, const std::vector<uint64_t> &off, const char *what) {
+    for (size_t i = 0; i + 1 < off.size(); i++)
+        if (off[i + 1] - off[i] > (uint64_t)p.maxSeqLen)
+            throw Fail(std::string(what) + " sequence " + std::to_string(i) + " is longer than --max-seq-len " + std::to_string(p.maxSeqLen) +
+                       "; splitting long sequences is not supported on this path");
+}
+
 void check_search_params(const Params &p) {
+    check_unimplemented_flags(p);
     if (p.kmerSize != 0 && p.kmerSize != 6) throw Fail("The k-mer size " + std::to_string(p.kmerSize) + " is not valid. (spb200 implements k = 6)");
     if (p.diagScore != 1) throw Fail("--diag-score 0 is not supported");
     if (p.exactKmer != 0) throw Fail("--exact-kmer-matching 1 is not supported");
@@ -424,6 +458,8 @@ int run_prefilter(int argc, const char **argv) {
     SeqSet Q, T;
     load_sequences(qdb, E.seed, Q);
     load_sequences(tdb, E.seed, T);
+    check_seq_len(p, Q.off, "query");
+    check_seq_len(p, T.off, "target");
     const int kmerThr = kmer_threshold(p.sensitivity, p.kmerScore, 6);
     log_line(p, "k-mer similarity threshold: %d", kmerThr);
     build_target_index(E, p, T, kmerThr, p.db[1], tdb.dataSize());
@@ -495,12 +531,14 @@ void fill_align_params(const Params &p, const Engine &E, uint64_t dbRes, spb_ali
 }
 
 void check_align_params(const Params &p) {
+    check_unimplemented_flags(p);
     if (p.altAli != 0 || p.realign != 0) throw Fail("--alt-ali / --realign are not supported on this path");
     if (p.seqIdThr != 0 || p.covThr != 0 || p.alnLenThr != 0) throw Fail("--min-seq-id / -c / --min-aln-len thresholds are not supported on this path");
     if (p.seqIdMode != 0) throw Fail("--seq-id-mode != 0 is not supported");
     if (p.maxRejected != INT_MAX || p.maxAccept != INT_MAX) throw Fail("--max-rejected / --max-accept are not supported");
     // -a forces SCORE_COV_SEQID (Alignment.cpp:35-37); the other modes print fewer columns and are not implemented
-    if (!(p.addBacktrace == 1 || p.alignmentMode == 3)) throw Fail("only the -a 1 (backtrace) output of the predictmatch search is implemented");
+    // (--alignment-mode 3 without -a writes the ten columns without the backtrace in the reference, Matcher::resultToBuffer)
+    if (p.addBacktrace != 1) throw Fail("only the -a 1 (backtrace) output of the predictmatch search is implemented");
 }
 
 // rows of one batch as text, one entry per query (Matcher::resultToBuffer, M/alignment/Matcher.cpp:323-370); sink(thread,
@@ -555,6 +593,8 @@ int run_align(int argc, const char **argv) {
     // align reads the raw (unmasked) sequences; ids = key order here, rows carry DB keys anyway
     load_sequences(qdb, E.align, Q);
     load_sequences(tdb, E.align, T);
+    check_seq_len(p, Q.off, "query");
+    check_seq_len(p, T.off, "target");
     spb_align_params ap;
     fill_align_params(p, E, tdb.aminoAcidDBSize(), &ap);   // Alignment.cpp:269
     check(spb_align_set_targets(E.ctx, T.res.data(), T.off.data(), (uint32_t)T.keys.size(), T.keys.data()), "spb_align_set_targets");
@@ -804,6 +844,8 @@ void search_dbs(const Params &p, const std::string &qName, const std::string &tN
     SeqSet Q, T;
     load_sequences(qdb, E.seed, Q);
     load_sequences(tdb, E.seed, T);
+    check_seq_len(p, Q.off, "query");
+    check_seq_len(p, T.off, "target");
     NuclSet QN, TN;
     spb_nucl_params np;
     if (nucl) {

@@ -959,7 +959,7 @@ __global__ void __launch_bounds__(PX_CH, 6) lookup_kernel(PrefArgs A) {
 
 template <int BM1, int BM2>
 struct QuerySmem {
-    uint32_t seen1[BM1], seen2[BM2];
+    uint32_t seen1[BM1], seen2[BM2], seen3[BM2];
     uint8_t q[PW_MAXL];
     signed char corr[PW_MAXL];
     uint32_t v_qi, v_K, v_slow, v_why, v_nHits, v_nSurv, v_nFin, v_cut, v_chunk0, v_nCh;
@@ -1168,14 +1168,22 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
         // warp's sort buffer.  If they do not fit one sort, pass B scatters them bucket by bucket into the team's scratch slice
         // and the buckets are merged into G contiguous groups of at most PW_SCAP records, each processed by one warp.
         uint32_t *const cnt64 = S.seen1;            // dead after pass 1: [0,64) counts, [64,128) starts, [128,192) fill cursors
-        if (live) for (int i = tw * 32 + lane; i < 192; i += TEAM * 32) cnt64[i] = 0;
-        team_sync();
+        bool two = false;                           // after the refinement a survivor must pass both target bitmaps
+        auto surv_keep = [&](uint32_t id) -> bool {
+            const uint32_t h2 = (id * 2654435761u) >> (32 - H2);
+            bool k = (S.seen2[h2 >> 5] >> (h2 & 31)) & 1u;
+            if (two) {
+                const uint32_t h3 = (id * 0xC2B2AE35u) >> (32 - H2);
+                k = k && ((S.seen3[h3 >> 5] >> (h3 & 31)) & 1u);
+            }
+            return k;
+        };
         int nS0 = 0;
-        if (live) {
+        auto pass_a = [&]() {
+            nS0 = 0;
             for_hits([&](uint64_t r, bool valid) {
                 const uint32_t id = (uint32_t)(r >> 32);
-                const uint32_t h2 = (id * 2654435761u) >> (32 - H2);
-                const bool keep = valid && ((S.seen2[h2 >> 5] >> (h2 & 31)) & 1u);
+                const bool keep = valid && surv_keep(id);
                 if (keep) atomicAdd(&cnt64[(id * 0x85EBCA6Bu) >> 26], 1u);
                 if (SOLO) {
                     const unsigned m = __ballot_sync(0xffffffffu, keep);
@@ -1184,6 +1192,44 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                     nS0 += __popc(m);
                 }
             });
+        };
+        if (live) for (int i = tw * 32 + lane; i < 192; i += TEAM * 32) cnt64[i] = 0;
+        team_sync();
+        if (live) pass_a();
+        team_sync();
+        // Refinement.  The false survivors of pass 1 are hash collisions, which grow with the square of the hits: a query with
+        // thousands of hits keeps hundreds of records that would all be sorted.  When the survivors do not fit one sort, the
+        // (target, diagonal) test runs once more over them with other hash functions into a second target bitmap; a record
+        // must then pass both, which leaves the true diagonal matches and a handful of records.
+        if (live) {
+            uint32_t tot = cnt64[2 * lane] + cnt64[2 * lane + 1];
+#pragma unroll 1
+            for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
+            team_sync();
+            if (tot > PW_SCAP) {
+                for (int i = tw * 32 + lane; i < BM1; i += TEAM * 32) S.seen1[i] = 0;
+                for (int i = tw * 32 + lane; i < BM2; i += TEAM * 32) S.seen3[i] = 0;
+                team_sync();
+                for_hits([&](uint64_t r, bool valid) {
+                    const uint32_t id = (uint32_t)(r >> 32);
+                    if (valid && surv_keep(id)) {
+                        const uint32_t x = id * 0xC2B2AE35u;
+                        const uint32_t d8 = (uint32_t)r & 0xFFu;
+                        const uint32_t h = ((x ^ (d8 * 0x27D4EB2Fu)) * 0x165667B1u) >> (32 - H1);
+                        const uint32_t bm = 1u << (h & 31);
+                        const uint32_t old = atomicOr(&S.seen1[h >> 5], bm);
+                        if ((old & bm) || d8 == 0u) {
+                            const uint32_t h3 = x >> (32 - H2);
+                            atomicOr(&S.seen3[h3 >> 5], 1u << (h3 & 31));
+                        }
+                    }
+                });
+                team_sync();
+                two = true;
+                for (int i = tw * 32 + lane; i < 192; i += TEAM * 32) cnt64[i] = 0;
+                team_sync();
+                pass_a();
+            }
         }
         team_sync();
         // group count: the smallest power of two whose merged buckets all fit one sort (every warp computes the same)
@@ -1200,9 +1246,9 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                     __syncwarp();
                     for (int i = lane; i < nS0; i += 32) {
                         const uint64_t r = W.surv[i];
-                        const uint32_t x = (uint32_t)(r >> 32) * 0xC2B2AE35u;
+                        const uint32_t x = (uint32_t)(r >> 32) * 0x7FEB352Du;
                         const uint32_t d8 = (uint32_t)r & 0xFFu;
-                        const uint32_t h = ((x ^ (d8 * 0x27D4EB2Fu)) * 0x165667B1u) >> (32 - H1);
+                        const uint32_t h = ((x ^ (d8 * 0x846CA68Bu)) * 0x2C1B3C6Du) >> (32 - H1);
                         const uint32_t bm = 1u << (h & 31);
                         const uint32_t old = atomicOr(&S.seen1[h >> 5], bm);
                         if ((old & bm) || d8 == 0u) {
@@ -1218,7 +1264,7 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                         bool keep = false;
                         if (i < nS0) {
                             r = W.surv[i];
-                            const uint32_t h2 = ((uint32_t)(r >> 32) * 0xC2B2AE35u) >> (32 - H2);
+                            const uint32_t h2 = ((uint32_t)(r >> 32) * 0x7FEB352Du) >> (32 - H2);
                             keep = (S.seen2[h2 >> 5] >> (h2 & 31)) & 1u;
                         }
                         const unsigned m = __ballot_sync(0xffffffffu, keep);
@@ -1260,8 +1306,7 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
         if (scatter) {
             for_hits([&](uint64_t r, bool valid) {
                 const uint32_t id = (uint32_t)(r >> 32);
-                const uint32_t h2 = (id * 2654435761u) >> (32 - H2);
-                if (valid && ((S.seen2[h2 >> 5] >> (h2 & 31)) & 1u)) {
+                if (valid && surv_keep(id)) {
                     const uint32_t bk = (id * 0x85EBCA6Bu) >> 26;
                     __stcg(grouped + cnt64[64 + bk] + atomicAdd(&cnt64[128 + bk], 1u), r);
                 }
@@ -1892,7 +1937,7 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
         const int soloBlocks = c->n_sm * soloPerSm, teamBlocks = c->n_sm * teamPerSm;
         A.direct = c->d_direct.as<ulonglong2>();
         A.kbits = c->d_kbits.as<uint32_t>();
-        A.hitsSolo = 4096;
+        A.hitsSolo = 2048;     // r2d sweep: 1024 / 2048 / 4096 / 8192 -> 0.62 / 0.54 / 0.61 / 0.90 ms of bookkeeping
         if (const char *e = getenv("SPB_HITS_SOLO")) A.hitsSolo = (uint32_t)std::max(1, atoi(e));
         const uint32_t hitCapSolo = std::max<uint32_t>(A.hitsSolo, PW_SCAP), hitCapTeam = 32768;
         const size_t sliceSolo = (size_t)hitCapSolo + 2 * PW_FCAP_SOLO, sliceTeam = (size_t)hitCapTeam + 2 * PW_FCAP_TEAM;
@@ -2249,11 +2294,8 @@ extern "C" int spb_prefilter_merge_shards(spb_ctx *c, uint32_t q_lo, uint32_t q_
     if (merged.ensure(std::max<uint64_t>(nHits, 1) * sizeof(spb_hit))) return 1;
     unsigned int h_err[4] = {0, 0, 0, 0};
     if (nq && nIn) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            SPB_CUDA(cudaFuncSetAttribute(merge_shards_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
-            attr_done = true;
-        }
+        // per device and cheap: set before every launch (a process may hold contexts on several GPUs)
+        SPB_CUDA(cudaFuncSetAttribute(merge_shards_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
         merge_shards_kernel<<<nq, 256, MG_SMEM, st>>>(d_recv, d_recv_keys, d_counts, c->s_b.as<uint64_t>(), nq, n_shards, q_lo,
                                                       c->d_hitoff.as<uint64_t>(), merged.as<spb_hit>(), (uint32_t)max_seqs,
                                                       reinterpret_cast<unsigned int *>(c->s_f.p));

@@ -91,6 +91,20 @@ def test_errors_like_the_reference():
     assert r.returncode == 1 and "Could not open" in r.stderr
 
 
+@pytest.mark.parametrize("module,flags", [
+    ("prefilter", ["--mask-lower-case", "1"]), ("prefilter", ["--alph-size", "nucl:5,aa:13"]), ("prefilter", ["--alph-size", "13"]),
+    ("prefilter", ["--taxon-list", "10239"]), ("align", ["--alignment-mode", "3", "-a", "0"]), ("align", ["--mask-lower-case", "1"])])
+def test_flags_that_would_change_the_result_are_refused(module, flags):
+    """A drop-in must not exit 0 with a DB that differs from the reference's: flags of the two modules that this path does not
+    implement keep the reference default and any other value fails loudly."""
+    base = PREF_FLAGS if module == "prefilter" else ALN_FLAGS
+    dbs = ["q", "t", "p"] if module == "prefilter" else ["q", "t", "p", "a"]
+    r = run("showparams", module, *dbs, *base, *flags, ok=False)
+    assert r.returncode == 1 and ("not supported" in r.stderr or "only the" in r.stderr), r.stderr
+    # the workflow's own values of the same flags pass
+    run("showparams", module, *dbs, *base)
+
+
 def test_no_cpu_fallback(tmp_path):
     import torch
     if torch.cuda.is_available():
