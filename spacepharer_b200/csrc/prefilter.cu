@@ -81,7 +81,7 @@ struct PrefArgs {
     struct QMeta *meta;      // [Q]
     unsigned int *chunkCursor;   // chunks allocated in this tile
     uint32_t chunkCap;
-    uint64_t *hitScratch;    // [teams in the grid][hitCap + 2 * FCAP] survivors grouped by target bucket | per-target winners
+    uint64_t *hitScratch;    // [teams in the grid][2 * hitCap + 2 * FCAP] survivor list | grouped by target bucket | per-target winners
     uint32_t hitCap;
     unsigned int *qCounter;  // dynamic query scheduler
     const unsigned int *nListPtr;  // device: entries of qlist (team launch reads it, no host round trip); NULL: nList
@@ -1067,10 +1067,10 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
     static_assert(768 + (SOLO ? 1 : TEAM) * PW_SCAP <= BM1 * 4, "aliased buffers fit");
     auto team_sync = [&]() { if (SOLO) __syncwarp(); else __syncthreads(); };
     constexpr uint32_t FCAP = SOLO ? PW_FCAP_SOLO : PW_FCAP_TEAM;
-    // records grouped by target bucket | per-target winners (final key, truncation key)
-    const size_t slice = (size_t)A.hitCap + 2 * (size_t)FCAP;
+    // survivor list | the same grouped by target bucket | per-target winners (final key, truncation key)
+    const size_t slice = 2 * (size_t)A.hitCap + 2 * (size_t)FCAP;
     uint64_t *grouped = A.hitScratch + (size_t)(SOLO ? blockIdx.x * PW_WARPS + wid : blockIdx.x) * slice;
-    uint64_t *finList = grouped + (size_t)A.hitCap;
+    uint64_t *finList = grouped + 2 * (size_t)A.hitCap;
     const uint32_t HCAP = A.hitCap;
     unsigned long long statK = 0, statM = 0, statE = 0, statS = 0;
 #ifdef SPB_PHASE_TIMING
@@ -1163,57 +1163,100 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
         }
         team_sync();
         PH_MARK(1);
-        // ---------------- survivors: records of targets seen twice (or with 8-bit diagonal 0) ----------------
-        // Pass A counts them per hash bucket (64 buckets of targets) and -- TEAM = 1 -- collects them optimistically into the
-        // warp's sort buffer.  If they do not fit one sort, pass B scatters them bucket by bucket into the team's scratch slice
-        // and the buckets are merged into G contiguous groups of at most PW_SCAP records, each processed by one warp.
+        // ---------------- survivors: the records of the marked targets ----------------
+        // Pass 2 over the hit stream appends them to a flat list in the team's scratch slice (TEAM = 1 also keeps the first
+        // PW_SCAP in the warp's sort buffer); everything after that reads the list, a small fraction of the hits.
+        //  * up to PW_SCAP survivors: one group, sorted by one warp -- after a second (target, diagonal) test in shared memory
+        //    with other hash functions when they exceed a register sort, since most of them are hash collisions of pass 1
+        //    (those grow with the square of the hits);
+        //  * more: the same second test runs over the list into a second target bitmap, then the records that pass both are
+        //    counted per hash bucket (64 buckets of targets), the buckets are merged into the fewest contiguous groups of at
+        //    most PW_SCAP records and the list is scattered group by group behind itself; one warp per group.
         uint32_t *const cnt64 = S.seen1;            // dead after pass 1: [0,64) counts, [64,128) starts, [128,192) fill cursors
-        bool two = false;                           // after the refinement a survivor must pass both target bitmaps
-        auto surv_keep = [&](uint32_t id) -> bool {
-            const uint32_t h2 = (id * 2654435761u) >> (32 - H2);
-            bool k = (S.seen2[h2 >> 5] >> (h2 & 31)) & 1u;
-            if (two) {
-                const uint32_t h3 = (id * 0xC2B2AE35u) >> (32 - H2);
-                k = k && ((S.seen3[h3 >> 5] >> (h3 & 31)) & 1u);
-            }
-            return k;
-        };
+        uint64_t *const list = grouped, *const bucketed = grouped + HCAP;
         int nS0 = 0;
-        auto pass_a = [&]() {
-            nS0 = 0;
+        if (live) {
             for_hits([&](uint64_t r, bool valid) {
-                const uint32_t id = (uint32_t)(r >> 32);
-                const bool keep = valid && surv_keep(id);
-                if (keep) atomicAdd(&cnt64[(id * 0x85EBCA6Bu) >> 26], 1u);
-                if (SOLO) {
-                    const unsigned m = __ballot_sync(0xffffffffu, keep);
-                    const int dst = nS0 + __popc(m & lt);
-                    if (keep && dst < PW_SCAP) W.surv[dst] = r;
+                const uint32_t h2 = ((uint32_t)(r >> 32) * 2654435761u) >> (32 - H2);
+                const bool keep = valid && ((S.seen2[h2 >> 5] >> (h2 & 31)) & 1u);
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (m) {
+                    uint32_t base = (uint32_t)nS0;
+                    if (!SOLO) {
+                        if (lane == 0) base = atomicAdd(&S.v_nSurv, (uint32_t)__popc(m));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                    }
+                    const uint32_t dst = base + (uint32_t)__popc(m & lt);
+                    if (keep) {
+                        if (SOLO && dst < PW_SCAP) W.surv[dst] = r;
+                        if ((!SOLO || dst >= PW_SCAP) && dst < HCAP) __stcg(list + dst, r);
+                    }
                     nS0 += __popc(m);
                 }
             });
-        };
-        if (live) for (int i = tw * 32 + lane; i < 192; i += TEAM * 32) cnt64[i] = 0;
+        }
         team_sync();
-        if (live) pass_a();
-        team_sync();
-        // Refinement.  The false survivors of pass 1 are hash collisions, which grow with the square of the hits: a query with
-        // thousands of hits keeps hundreds of records that would all be sorted.  When the survivors do not fit one sort, the
-        // (target, diagonal) test runs once more over them with other hash functions into a second target bitmap; a record
-        // must then pass both, which leaves the true diagonal matches and a handful of records.
+        uint32_t nSurv = 0, G = 1;
+        bool scatter = false;
         if (live) {
-            uint32_t tot = cnt64[2 * lane] + cnt64[2 * lane + 1];
-#pragma unroll 1
-            for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
-            team_sync();
-            if (tot > PW_SCAP) {
+            const uint32_t nL = SOLO ? (uint32_t)nS0 : S.v_nSurv;     // survivors of pass 2
+            nSurv = nL;
+            if (nL > HCAP) {
+                if (tw == 0 && lane == 0) { S.v_slow = ST_CAPACITY; S.v_why = 5; }       // the scratch slice cannot hold them
+            } else if (nL <= PW_SCAP) {
+                // one group, held by the first warp of the team
+                nS0 = 0;
+                if (tw == 0) {
+                    nS0 = (int)nL;
+                    if (!SOLO) for (int i = lane; i < nS0; i += 32) W.surv[i] = __ldcg(list + i);
+                    if (nS0 > 32) {
+                        for (int i = lane; i < BM1; i += 32) S.seen1[i] = 0;
+                        for (int i = lane; i < BM2; i += 32) S.seen2[i] = 0;
+                        __syncwarp();
+                        for (int i = lane; i < nS0; i += 32) {
+                            const uint64_t r = W.surv[i];
+                            const uint32_t x = (uint32_t)(r >> 32) * 0x7FEB352Du;
+                            const uint32_t d8 = (uint32_t)r & 0xFFu;
+                            const uint32_t h = ((x ^ (d8 * 0x846CA68Bu)) * 0x2C1B3C6Du) >> (32 - H1);
+                            const uint32_t bm = 1u << (h & 31);
+                            const uint32_t old = atomicOr(&S.seen1[h >> 5], bm);
+                            if ((old & bm) || d8 == 0u) {
+                                const uint32_t h2 = x >> (32 - H2);
+                                atomicOr(&S.seen2[h2 >> 5], 1u << (h2 & 31));
+                            }
+                        }
+                        __syncwarp();
+                        int outN = 0;
+                        for (int c0i = 0; c0i < nS0; c0i += 32) {
+                            const int i = c0i + lane;
+                            uint64_t r = 0;
+                            bool keep = false;
+                            if (i < nS0) {
+                                r = W.surv[i];
+                                const uint32_t h2 = ((uint32_t)(r >> 32) * 0x7FEB352Du) >> (32 - H2);
+                                keep = (S.seen2[h2 >> 5] >> (h2 & 31)) & 1u;
+                            }
+                            const unsigned m = __ballot_sync(0xffffffffu, keep);
+                            __syncwarp();
+                            if (keep) W.surv[outN + __popc(m & lt)] = r;
+                            outN += __popc(m);
+                            __syncwarp();
+                        }
+                        nS0 = outN;
+                    }
+                    nSurv = (uint32_t)nS0;
+                }
+            } else {
+                // second (target, diagonal) test over the list, then bucket counts of the records that pass both
+                const uint32_t nLr = (nL + 31u) & ~31u;
+                if (SOLO) for (int i = lane; i < PW_SCAP; i += 32) __stcg(list + i, W.surv[i]);   // the head of the list sits in the sort buffer
                 for (int i = tw * 32 + lane; i < BM1; i += TEAM * 32) S.seen1[i] = 0;
                 for (int i = tw * 32 + lane; i < BM2; i += TEAM * 32) S.seen3[i] = 0;
                 team_sync();
-                for_hits([&](uint64_t r, bool valid) {
-                    const uint32_t id = (uint32_t)(r >> 32);
-                    if (valid && surv_keep(id)) {
-                        const uint32_t x = id * 0xC2B2AE35u;
+                for (uint32_t i = (uint32_t)(tw * 32 + lane); i < nLr; i += TEAM * 32) {
+                    if (i < nL) {
+                        const uint64_t r = __ldcg(list + i);
+                        const uint32_t x = (uint32_t)(r >> 32) * 0xC2B2AE35u;
                         const uint32_t d8 = (uint32_t)r & 0xFFu;
                         const uint32_t h = ((x ^ (d8 * 0x27D4EB2Fu)) * 0x165667B1u) >> (32 - H1);
                         const uint32_t bm = 1u << (h & 31);
@@ -1223,60 +1266,20 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                             atomicOr(&S.seen3[h3 >> 5], 1u << (h3 & 31));
                         }
                     }
-                });
+                }
                 team_sync();
-                two = true;
                 for (int i = tw * 32 + lane; i < 192; i += TEAM * 32) cnt64[i] = 0;
                 team_sync();
-                pass_a();
-            }
-        }
-        team_sync();
-        // group count: the smallest power of two whose merged buckets all fit one sort (every warp computes the same)
-        uint32_t nSurv = 0, G = 1;
-        if (live) {
-            const uint32_t c0 = cnt64[2 * lane], c1 = cnt64[2 * lane + 1];
-            if (SOLO && nS0 <= PW_SCAP) {
-                // everything already sits in the sort buffer: one group, no scatter.  More than one register sort's worth: most
-                // of it is hash collisions of pass 1 (they grow with the square of the hits).  Run the (target, diagonal) test
-                // once more on the survivors alone, with other hash functions, and keep the targets that pass again.
-                if (nS0 > 32) {
-                    for (int i = lane; i < BM1; i += 32) S.seen1[i] = 0;
-                    for (int i = lane; i < BM2; i += 32) S.seen2[i] = 0;
-                    __syncwarp();
-                    for (int i = lane; i < nS0; i += 32) {
-                        const uint64_t r = W.surv[i];
-                        const uint32_t x = (uint32_t)(r >> 32) * 0x7FEB352Du;
-                        const uint32_t d8 = (uint32_t)r & 0xFFu;
-                        const uint32_t h = ((x ^ (d8 * 0x846CA68Bu)) * 0x2C1B3C6Du) >> (32 - H1);
-                        const uint32_t bm = 1u << (h & 31);
-                        const uint32_t old = atomicOr(&S.seen1[h >> 5], bm);
-                        if ((old & bm) || d8 == 0u) {
-                            const uint32_t h2 = x >> (32 - H2);
-                            atomicOr(&S.seen2[h2 >> 5], 1u << (h2 & 31));
-                        }
+                for (uint32_t i = (uint32_t)(tw * 32 + lane); i < nLr; i += TEAM * 32) {
+                    if (i < nL) {
+                        const uint32_t id = (uint32_t)(__ldcg(list + i) >> 32);
+                        const uint32_t h3 = (id * 0xC2B2AE35u) >> (32 - H2);
+                        if ((S.seen3[h3 >> 5] >> (h3 & 31)) & 1u) atomicAdd(&cnt64[(id * 0x85EBCA6Bu) >> 26], 1u);
                     }
-                    __syncwarp();
-                    int outN = 0;
-                    for (int c0i = 0; c0i < nS0; c0i += 32) {
-                        const int i = c0i + lane;
-                        uint64_t r = 0;
-                        bool keep = false;
-                        if (i < nS0) {
-                            r = W.surv[i];
-                            const uint32_t h2 = ((uint32_t)(r >> 32) * 0x7FEB352Du) >> (32 - H2);
-                            keep = (S.seen2[h2 >> 5] >> (h2 & 31)) & 1u;
-                        }
-                        const unsigned m = __ballot_sync(0xffffffffu, keep);
-                        __syncwarp();
-                        if (keep) W.surv[outN + __popc(m & lt)] = r;
-                        outN += __popc(m);
-                        __syncwarp();
-                    }
-                    nS0 = outN;
                 }
-                nSurv = (uint32_t)nS0;
-            } else {
+                team_sync();
+                // group count: the smallest power of two whose merged buckets all fit one sort (every warp computes the same)
+                const uint32_t c0 = cnt64[2 * lane], c1 = cnt64[2 * lane + 1];
                 // level l uses 64 >> l groups; the largest merged bucket grows with l, so the last level that fits wins
                 uint32_t sum = c0 + c1;
                 int lvl = -1;
@@ -1290,27 +1293,30 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                     if (l == 6) nSurv = m;
                 }
                 G = 64u >> max(lvl, 0);
-                if (tw == 0 && lane == 0) {
-                    if (lvl < 0) { S.v_slow = ST_CAPACITY; S.v_why = 6; }            // one bucket alone overflows a sort
-                    else if (nSurv > HCAP) { S.v_slow = ST_CAPACITY; S.v_why = 5; }  // the scratch slice cannot hold them
-                }
-                if (tw == 0) {   // bucket starts
-                    const uint32_t e0 = (uint32_t)warp_incl_scan_ool((int)(c0 + c1)) - (c0 + c1);
-                    cnt64[64 + 2 * lane] = e0;
-                    cnt64[64 + 2 * lane + 1] = e0 + c0;
+                team_sync();
+                if (lvl < 0) {
+                    if (tw == 0 && lane == 0) { S.v_slow = ST_CAPACITY; S.v_why = 6; }   // one bucket alone overflows a sort
+                } else {
+                    if (tw == 0) {   // bucket starts
+                        const uint32_t e0 = (uint32_t)warp_incl_scan_ool((int)(c0 + c1)) - (c0 + c1);
+                        cnt64[64 + 2 * lane] = e0;
+                        cnt64[64 + 2 * lane + 1] = e0 + c0;
+                    }
+                    team_sync();
+                    for (uint32_t i = (uint32_t)(tw * 32 + lane); i < nLr; i += TEAM * 32) {
+                        if (i < nL) {
+                            const uint64_t r = __ldcg(list + i);
+                            const uint32_t id = (uint32_t)(r >> 32);
+                            const uint32_t h3 = (id * 0xC2B2AE35u) >> (32 - H2);
+                            if ((S.seen3[h3 >> 5] >> (h3 & 31)) & 1u) {
+                                const uint32_t bk = (id * 0x85EBCA6Bu) >> 26;
+                                __stcg(bucketed + cnt64[64 + bk] + atomicAdd(&cnt64[128 + bk], 1u), r);
+                            }
+                        }
+                    }
+                    scatter = true;
                 }
             }
-        }
-        team_sync();
-        const bool scatter = live && (S.v_slow == ST_OK) && (!SOLO || nS0 > PW_SCAP);
-        if (scatter) {
-            for_hits([&](uint64_t r, bool valid) {
-                const uint32_t id = (uint32_t)(r >> 32);
-                if (valid && surv_keep(id)) {
-                    const uint32_t bk = (id * 0x85EBCA6Bu) >> 26;
-                    __stcg(grouped + cnt64[64 + bk] + atomicAdd(&cnt64[128 + bk], 1u), r);
-                }
-            });
         }
         team_sync();
         PH_MARK(2);
@@ -1327,7 +1333,7 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                     const uint32_t lo = cnt64[64 + g * per];
                     const uint32_t hi = ((g + 1) * per >= 64u) ? nSurv : cnt64[64 + (g + 1) * per];
                     nS = (int)(hi - lo);
-                    for (int i = lane; i < nS; i += 32) W.surv[i] = __ldcg(grouped + lo + i);
+                    for (int i = lane; i < nS; i += 32) W.surv[i] = __ldcg(bucketed + lo + i);
                 }
                 // ---- sort by (target, stream order) ----
                 {
@@ -1940,7 +1946,7 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
         A.hitsSolo = 2048;     // r2d sweep: 1024 / 2048 / 4096 / 8192 -> 0.62 / 0.54 / 0.61 / 0.90 ms of bookkeeping
         if (const char *e = getenv("SPB_HITS_SOLO")) A.hitsSolo = (uint32_t)std::max(1, atoi(e));
         const uint32_t hitCapSolo = std::max<uint32_t>(A.hitsSolo, PW_SCAP), hitCapTeam = 32768;
-        const size_t sliceSolo = (size_t)hitCapSolo + 2 * PW_FCAP_SOLO, sliceTeam = (size_t)hitCapTeam + 2 * PW_FCAP_TEAM;
+        const size_t sliceSolo = 2 * (size_t)hitCapSolo + 2 * PW_FCAP_SOLO, sliceTeam = 2 * (size_t)hitCapTeam + 2 * PW_FCAP_TEAM;
         uint32_t tileQ = 49152;
         if (const char *e = getenv("SPB_PF_TILEQ")) tileQ = (uint32_t)std::max(256, atoi(e));
         // chunks of 256 slots a tile may allocate: 12 per query is 2.5 x the mean at -s 5.7; grown when a round had to retry
