@@ -311,6 +311,25 @@ int spb_prefilter_device_trunc_keys(spb_ctx *ctx, uint64_t **d_keys);
 int spb_prefilter_merge_shards(spb_ctx *ctx, uint32_t q_lo, uint32_t q_hi, const spb_hit *d_recv, const uint64_t *d_recv_keys,
                                uint64_t n_recv, const uint32_t *d_counts, uint32_t n_shards, int32_t max_seqs);
 
+/* ---- multi-GPU index split: the k-mer table sharded over the GPUs' HBM, read through NVLink peer memory ------
+ * The second way to spread one target DB over the GPUs of a box (MMseqs2 only has the target split above, because a CPU
+ * node cannot read its neighbours' memory): the k-mer table -- the 16-byte-per-k-mer direct table plus the posting lists,
+ * the bulk of IndexTable (M/prefiltering/IndexTable.h:65-76) -- is cut into `world` contiguous k-mer ranges, GPU r keeps
+ * range r, and the lookup kernel of every GPU gathers the entries of the other ranges with plain loads on peer-mapped
+ * pointers (NVLink / NVSwitch).  Queries are partitioned (every GPU runs expand -> lookup -> bookkeeping -> align for its own
+ * queries), so no hit list is exchanged or merged and the result is the unsplit result by construction; only the 8 MB
+ * occupancy bitmap and the residues are replicated.  Works across processes (CUDA IPC handles, one process per GPU) and inside
+ * one process (several contexts; peer access is enabled between their devices).
+ *   spb_index_shard          after spb_index_build: keep k-mer range `rank` of `world`, free the rest of the table
+ *   spb_index_shard_export   CUDA IPC handles of this context's shard (2 x 64 bytes: table, posting lists)
+ *   spb_index_shard_attach_ipc   map the shard of rank `peer` from its exported handles (another process)
+ *   spb_index_shard_attach_ctx   ... or from a context of the same process
+ * Every rank must be attached before the first prefilter call; lanes of a context inherit its shard map. */
+int spb_index_shard(spb_ctx *ctx, int rank, int world);
+int spb_index_shard_export(spb_ctx *ctx, void *handles128);
+int spb_index_shard_attach_ipc(spb_ctx *ctx, int peer, const void *handles128);
+int spb_index_shard_attach_ctx(spb_ctx *ctx, int peer, spb_ctx *peer_ctx);
+
 /* ---- host pre-step (CPU, as in the reference) -----------------------------------------------------
  * tantan repeat masking of the target residues before the index build (--mask 1; call site
  * M/prefiltering/IndexBuilder.cpp:137-149, M/commons/tantan.cpp).  prob = joint probabilities P_ab [21][21] and

@@ -296,6 +296,24 @@ class Searcher:
                                                        C.c_void_p(recv_keys_ptr) if recv_keys_ptr else None, n_recv,
                                                        C.c_void_p(counts_ptr), n_shards, max_seqs))
 
+    # ---- multi-GPU index split: k-mer ranges of the table on different GPUs, gathered through peer memory ----
+    def shard_index(self, rank, world):
+        """keep k-mer range `rank` of `world` of the built table (spb_index_shard); attach the other ranges before searching"""
+        capi.check(self.lib.spb_index_shard(self.h, rank, world))
+
+    def shard_export(self):
+        """CUDA IPC handles of this context's shard (128 bytes) for a peer process"""
+        buf = C.create_string_buffer(128)
+        capi.check(self.lib.spb_index_shard_export(self.h, buf))
+        return buf.raw
+
+    def shard_attach_ipc(self, peer, handles):
+        capi.check(self.lib.spb_index_shard_attach_ipc(self.h, peer, C.c_char_p(bytes(handles))))
+
+    def shard_attach(self, peer, other):
+        """attach the shard held by another Searcher of this process (same or peer-accessible device)"""
+        capi.check(self.lib.spb_index_shard_attach_ctx(self.h, peer, other.h))
+
     def pairs_from_prefilter(self):
         capi.check(self.lib.spb_pairs_from_prefilter(self.h))
 

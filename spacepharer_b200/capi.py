@@ -84,6 +84,7 @@ SYMBOLS = [
     "spb_pairs_exhaustive", "spb_align_exhaustive", "spb_spacer_frames", "spb_free_frames_result",
     "spb_ctx_create_lane", "spb_align_fetch_begin", "spb_align_fetch_wait",
     "spb_nucl_set_targets", "spb_nucl_set_queries", "spb_nucl_rescore", "spb_nucl_rescore_resident", "spb_free_nucl_result",
+    "spb_index_shard", "spb_index_shard_export", "spb_index_shard_attach_ipc", "spb_index_shard_attach_ctx",
 ]
 
 _lib = None
@@ -156,6 +157,10 @@ def load():
     L.spb_prefilter_device_result.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), u64p]
     L.spb_prefilter_merge_shards.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64, vp, C.c_uint32, C.c_int32]
     L.spb_prefilter_device_trunc_keys.argtypes = [vp, C.POINTER(C.c_void_p)]
+    L.spb_index_shard.argtypes = [vp, C.c_int, C.c_int]
+    L.spb_index_shard_export.argtypes = [vp, C.c_char_p]
+    L.spb_index_shard_attach_ipc.argtypes = [vp, C.c_int, C.c_char_p]
+    L.spb_index_shard_attach_ctx.argtypes = [vp, C.c_int, vp]
     L.spb_pairs_exhaustive.argtypes = [vp, C.POINTER(AlignParams), C.POINTER(ExhaustiveStats)]
     L.spb_align_exhaustive.argtypes = [vp, u8p, u64p, C.c_uint32, C.POINTER(AlignParams),
                                        C.POINTER(C.POINTER(AlignResult)), C.POINTER(ExhaustiveStats)]

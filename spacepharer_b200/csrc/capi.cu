@@ -104,6 +104,8 @@ int spb_ctx_create_lane(spb_ctx *parent, spb_ctx **out) {
     c->d_post = parent->d_post.view(); c->d_direct = parent->d_direct.view(); c->d_kbits = parent->d_kbits.view();
     c->d_row3 = parent->d_row3.view(); c->d_cnt3 = parent->d_cnt3.view();
     c->n_post = parent->n_post; c->n_kmers_nonempty = parent->n_kmers_nonempty; c->build_ms = parent->build_ms;
+    c->n_shards = parent->n_shards; c->shard_rank = parent->shard_rank; c->shard_R = parent->shard_R;
+    for (int i = 0; i < SPB_MAX_SHARDS; i++) { c->shard_direct[i] = parent->shard_direct[i]; c->shard_post[i] = parent->shard_post[i]; }
     c->have_aln_targets = parent->have_aln_targets;
     c->aT = parent->aT; c->a_res = parent->a_res; c->a_maxlen = parent->a_maxlen;
     c->d_ares = parent->d_ares.view(); c->d_aoff = parent->d_aoff.view(); c->d_akeys = parent->d_akeys.view();
@@ -126,8 +128,10 @@ void spb_ctx_destroy(spb_ctx *c) {
                            &c->d_pairoff, &c->d_pairT, &c->d_pairQ, &c->d_pairout, &c->d_acc, &c->d_cig, &c->d_rows, &c->d_rowoff, &c->d_st_rows, &c->d_st_cig, &c->d_st_off, &c->d_tnt, &c->d_tntoff, &c->d_tntsc, &c->d_qnt, &c->d_qntoff, &c->d_qntsc, &c->d_nrows,
                            &c->s_a, &c->s_b, &c->s_c, &c->s_d, &c->s_e, &c->s_f, &c->s_g, &c->s_h, &c->s_i, &c->s_j,
                            &c->s_k, &c->s_l, &c->s_m, &c->s_n, &c->s_o, &c->s_p, &c->s_q, &c->s_cub,
-                           &c->p_recs, &c->p_ctab, &c->p_ccnt, &c->p_harena, &c->p_meta, &c->p_retry};
+                           &c->p_recs, &c->p_ctab, &c->p_ccnt, &c->p_harena, &c->p_meta, &c->p_retry, &c->p_team2};
     for (spb::DevBuf *b : bufs) b->release();
+    for (void *m : c->ipc_mapped) cudaIpcCloseMemHandle(m);
+    c->ipc_mapped.clear();
     for (spb::PinBlock &b : c->pins)
         if (b.p) cudaFreeHost(b.p);
     c->pins.clear();
@@ -138,6 +142,12 @@ void spb_ctx_destroy(spb_ctx *c) {
         cudaEventDestroy(c->ev_stage_free);
     }
     for (cudaEvent_t ev : c->ev_phase) cudaEventDestroy(ev);
+    if (c->aux_stream) {
+        cudaStreamSynchronize(c->aux_stream);
+        cudaStreamDestroy(c->aux_stream);
+        cudaEventDestroy(c->ev_fork);
+        cudaEventDestroy(c->ev_join);
+    }
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaEventDestroy(c->ev2);

@@ -16,6 +16,7 @@
 #define SPB_NK 64000000u      // 20^6
 #define SPB_CNT3_W 512        // score-count table width: scores -256 .. 255
 #define SPB_SCORE_OFF 256
+#define SPB_MAX_SHARDS 8
 
 namespace spb {
 
@@ -115,6 +116,13 @@ struct spb_ctx {
     spb::DevBuf d_post;           // u64[n_post]: id << 16 | pos
     spb::DevBuf d_direct;         // ulonglong2[20^6] packed direct table: up to two postings inline, else len << 32 | offset (index.cu)
     spb::DevBuf d_kbits;          // u32[20^6 / 32] occupancy bit per k-mer (pre-check of the gather, L2-resident)
+    // k-mer-range shards of the table (spb_index_shard): shard r holds k-mers [r * shard_R, (r + 1) * shard_R); own shard in
+    // d_direct / d_post (re-based), the others peer-mapped.  n_shards == 1: shard 0 is the whole table.
+    int n_shards = 1, shard_rank = 0;
+    uint32_t shard_R = SPB_NK;
+    const void *shard_direct[SPB_MAX_SHARDS] = {nullptr};
+    const void *shard_post[SPB_MAX_SHARDS] = {nullptr};
+    std::vector<void *> ipc_mapped;       // cudaIpcOpenMemHandle results to close
     uint64_t n_post = 0, n_kmers_nonempty = 0;
     spb::DevBuf d_row3;           // u32[8000][8000]: (score + 256) << 16 | 3-mer index
     spb::DevBuf d_cnt3;           // u16[8000][512]: #entries with score >= v
@@ -192,6 +200,9 @@ struct spb_ctx {
     spb::DevBuf p_harena;         // u64[] hit records, chunk after chunk
     spb::DevBuf p_meta;           // QMeta[Q]
     spb::DevBuf p_retry;          // u32[Q] queries of the next round
+    spb::DevBuf p_team2;          // u32[Q] queries the warp-per-query bookkeeping hands to the CTA launch
+    cudaStream_t aux_stream = nullptr;   // the CTA-per-query bookkeeping runs beside the warp-per-query one
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::vector<cudaEvent_t> ev_phase;   // five per tile
 
     // ---- scratch (grow-only, reused across calls) ----

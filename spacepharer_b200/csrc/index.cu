@@ -15,6 +15,8 @@
 //   cnt3   u16[8000][512]      cnt3[x][v+256] = #neighbours of x with score >= v  (O(1) list lengths)
 #include <cub/cub.cuh>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace spb {
@@ -179,6 +181,16 @@ __global__ void export_postings_kernel(const uint32_t *__restrict__ koff, const 
     }
 }
 
+// copy of k-mer range [k0, k0 + n) of the direct table with the list offsets re-based to the shard's own posting slice
+__global__ void shard_copy_kernel(const ulonglong2 *__restrict__ direct, uint32_t k0, uint32_t n, uint32_t postBase,
+                                  ulonglong2 *__restrict__ out) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    ulonglong2 v = direct[k0 + k];
+    if (v.x != 0ull && !(v.x >> 63)) v.x = (v.x & 0xFFFFFFFF00000000ull) | (uint64_t)((uint32_t)v.x - postBase);
+    out[k] = v;
+}
+
 static int parse_pattern(const char *p, Pattern *out) {
     int span = (int)strlen(p), k = 0;
     if (span < 6 || span > 32) return 1;
@@ -321,7 +333,103 @@ extern "C" int spb_index_build(spb_ctx *c, const uint8_t *residues, const uint64
     c->n_post = nPost;
     c->n_kmers_nonempty = nonEmpty;
     c->build_ms = ms;
+    c->n_shards = 1;
+    c->shard_rank = 0;
+    c->shard_R = SPB_NK;
+    for (int i = 0; i < SPB_MAX_SHARDS; i++) { c->shard_direct[i] = nullptr; c->shard_post[i] = nullptr; }
+    c->shard_direct[0] = c->d_direct.p;
+    c->shard_post[0] = c->d_post.p;
     c->have_index = true;
+    return 0;
+}
+
+extern "C" int spb_index_shard(spb_ctx *c, int rank, int world) {
+    SPB_CHECK(c && !c->is_lane, "spb_index_shard: needs a root context");
+    SPB_CHECK(c->have_index && c->n_shards == 1, "spb_index_shard: build the (whole) index first");
+    SPB_CHECK(world >= 1 && world <= SPB_MAX_SHARDS && rank >= 0 && rank < world, "spb_index_shard: rank %d / world %d out of range (max %d)",
+              rank, world, SPB_MAX_SHARDS);
+    if (world == 1) return 0;
+    SPB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    // contiguous k-mer ranges, a multiple of 32 k-mers so that occupancy words never straddle shards
+    const uint32_t R = (uint32_t)((((uint64_t)SPB_NK + world - 1) / world + 31) / 32 * 32);
+    const uint32_t k0 = std::min<uint64_t>((uint64_t)R * rank, SPB_NK), k1 = (uint32_t)std::min<uint64_t>((uint64_t)R * (rank + 1), SPB_NK);
+    const uint32_t n = k1 - k0;
+    uint32_t h_off[2] = {0, 0};
+    SPB_CUDA(cudaMemcpyAsync(&h_off[0], c->d_koff.as<uint32_t>() + k0, 4, cudaMemcpyDeviceToHost, st));
+    SPB_CUDA(cudaMemcpyAsync(&h_off[1], c->d_koff.as<uint32_t>() + k1, 4, cudaMemcpyDeviceToHost, st));
+    SPB_CUDA(cudaStreamSynchronize(st));
+    const uint64_t nPostShard = h_off[1] - h_off[0];
+    // plain cudaMalloc allocations (IPC handles are per allocation)
+    spb::DevBuf dshard, pshard;
+    if (dshard.ensure(std::max<size_t>((size_t)n, 1) * 16) || pshard.ensure(std::max<uint64_t>(nPostShard, 1) * 8 + 64)) return 1;
+    if (n) {
+        shard_copy_kernel<<<(n + 255) / 256, 256, 0, st>>>(c->d_direct.as<ulonglong2>(), k0, n, h_off[0], dshard.as<ulonglong2>());
+        SPB_CUDA(cudaGetLastError()); c->n_launches++;
+    }
+    if (nPostShard)
+        SPB_CUDA(cudaMemcpyAsync(pshard.p, c->d_post.as<uint64_t>() + h_off[0], nPostShard * 8, cudaMemcpyDeviceToDevice, st));
+    SPB_CUDA(cudaStreamSynchronize(st));
+    // the whole table goes away: the CSR offsets, the postings and the direct table live on as this shard only
+    c->d_direct.release();
+    c->d_post.release();
+    c->d_koff.release();
+    c->d_direct = dshard;
+    c->d_post = pshard;
+    c->n_shards = world;
+    c->shard_rank = rank;
+    c->shard_R = R;
+    for (int i = 0; i < SPB_MAX_SHARDS; i++) { c->shard_direct[i] = nullptr; c->shard_post[i] = nullptr; }
+    c->shard_direct[rank] = c->d_direct.p;
+    c->shard_post[rank] = c->d_post.p;
+    return 0;
+}
+
+extern "C" int spb_index_shard_export(spb_ctx *c, void *handles128) {
+    SPB_CHECK(c && handles128, "spb_index_shard_export: NULL argument");
+    SPB_CHECK(c->have_index && c->n_shards > 1 && !c->is_lane, "spb_index_shard_export: call spb_index_shard first");
+    SPB_CUDA(cudaSetDevice(c->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h[2];
+    SPB_CUDA(cudaIpcGetMemHandle(&h[0], c->d_direct.p));
+    SPB_CUDA(cudaIpcGetMemHandle(&h[1], c->d_post.p));
+    memcpy(handles128, h, 128);
+    return 0;
+}
+
+extern "C" int spb_index_shard_attach_ipc(spb_ctx *c, int peer, const void *handles128) {
+    SPB_CHECK(c && handles128, "spb_index_shard_attach_ipc: NULL argument");
+    SPB_CHECK(c->have_index && c->n_shards > 1 && !c->is_lane, "spb_index_shard_attach_ipc: call spb_index_shard first");
+    SPB_CHECK(peer >= 0 && peer < c->n_shards && peer != c->shard_rank, "spb_index_shard_attach_ipc: peer %d out of range", peer);
+    SPB_CUDA(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h[2];
+    memcpy(h, handles128, 128);
+    void *pd = nullptr, *pp = nullptr;
+    SPB_CUDA(cudaIpcOpenMemHandle(&pd, h[0], cudaIpcMemLazyEnablePeerAccess));
+    SPB_CUDA(cudaIpcOpenMemHandle(&pp, h[1], cudaIpcMemLazyEnablePeerAccess));
+    c->ipc_mapped.push_back(pd);
+    c->ipc_mapped.push_back(pp);
+    c->shard_direct[peer] = pd;
+    c->shard_post[peer] = pp;
+    return 0;
+}
+
+extern "C" int spb_index_shard_attach_ctx(spb_ctx *c, int peer, spb_ctx *pc) {
+    SPB_CHECK(c && pc, "spb_index_shard_attach_ctx: NULL argument");
+    SPB_CHECK(c->have_index && c->n_shards > 1 && !c->is_lane, "spb_index_shard_attach_ctx: call spb_index_shard first");
+    SPB_CHECK(pc->have_index && pc->n_shards == c->n_shards && pc->shard_rank == peer && peer != c->shard_rank,
+              "spb_index_shard_attach_ctx: the peer context does not hold shard %d of %d", peer, c->n_shards);
+    if (pc->device != c->device) {
+        SPB_CUDA(cudaSetDevice(c->device));
+        int can = 0;
+        SPB_CUDA(cudaDeviceCanAccessPeer(&can, c->device, pc->device));
+        SPB_CHECK(can, "spb_index_shard_attach_ctx: device %d cannot access device %d", c->device, pc->device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(pc->device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+        SPB_CHECK(e == cudaSuccess, "spb_index_shard_attach_ctx: cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+    }
+    c->shard_direct[peer] = pc->d_direct.p;
+    c->shard_post[peer] = pc->d_post.p;
     return 0;
 }
 
@@ -340,6 +448,7 @@ extern "C" int spb_index_stats_get(spb_ctx *c, spb_index_stats *out) {
 extern "C" int spb_index_export(spb_ctx *c, uint32_t *kmer, uint32_t *id, uint16_t *pos) {
     SPB_CHECK(c && kmer && id && pos, "spb_index_export: NULL argument");
     SPB_CHECK(c->have_index, "spb_index_export: no index built");
+    SPB_CHECK(c->n_shards == 1 && c->d_koff.p, "spb_index_export: the CSR view is gone once the table is sharded (spb_index_shard)");
     SPB_CUDA(cudaSetDevice(c->device));
     if (c->n_post == 0) return 0;
     DevBuf dk, di, dp;

@@ -52,8 +52,12 @@ struct PrefArgs {
     const uint8_t *tres;
     const uint32_t *toff;
     uint32_t T;
-    const uint32_t *koff;
-    const uint64_t *post;
+    // k-mer table: 16-byte entries + posting lists, in nShards contiguous k-mer ranges of shardR k-mers (one range when not
+    // sharded); ranges of other GPUs are peer-mapped pointers (index.cu: spb_index_shard)
+    const ulonglong2 *directS[SPB_MAX_SHARDS];
+    const uint64_t *postS[SPB_MAX_SHARDS];
+    uint32_t shardR;
+    int nShards;
     const uint32_t *row3;
     const uint16_t *cnt3;
     const Matrices *mat;
@@ -71,7 +75,6 @@ struct PrefArgs {
     uint32_t *status;        // per query: ST_*
     uint32_t *need;          // per query: records needed when status == ST_CAPACITY
     // expand / lookup / bookkeeping kernels
-    const ulonglong2 *direct;  // [20^6] packed k-mer table, 16 bytes per k-mer (index.cu)
     const uint32_t *kbits;   // [20^6 / 32] occupancy bit per k-mer
     uint32_t *recs;          // [chunkCap][256] slot records: k-mer | window << 26
     uint2 *chunkTab;         // [chunkCap] (query, stream-order number of the chunk's first slot)
@@ -87,9 +90,27 @@ struct PrefArgs {
     const unsigned int *nListPtr;  // device: entries of qlist (team launch reads it, no host round trip); NULL: nList
     uint32_t nList, listOff, listStride;   // query of slot s: qlist[listOff + s * listStride]
     uint32_t hitsSolo;       // TEAM = 1: queries with more hits go to the TEAM = 8 launch
-    uint32_t *teamList;      // queries handed to the TEAM = 8 launch
+    uint32_t *teamList;      // heavy queries (classify_kernel) for the TEAM = 8 launch
     unsigned int *teamCount;
+    uint32_t *teamList2;     // queries the TEAM = 1 launch hands over at its end (truncation at max-seqs, > 256 winners)
+    unsigned int *teamCount2;
 };
+
+// table entry of a k-mer: x = 0 none | x, y with bit 63: one or two inline postings | x = len << 32 | offset of a posting list
+__device__ __forceinline__ ulonglong2 kmer_entry(const PrefArgs &A, uint32_t kmer, const uint64_t *&postBase, bool streaming) {
+    uint32_t o = 0, l = kmer;
+    if (A.nShards > 1) { o = kmer / A.shardR; l = kmer - o * A.shardR; }
+    postBase = A.postS[o];
+    return streaming ? __ldcs(A.directS[o] + l) : __ldg(A.directS[o] + l);
+}
+// number of postings of an entry and posting z of it
+__device__ __forceinline__ uint32_t entry_count(const ulonglong2 &e) {
+    return (e.x >> 63) ? 1u + (uint32_t)(e.y >> 63) : (uint32_t)(e.x >> 32);
+}
+__device__ __forceinline__ uint64_t entry_posting(const ulonglong2 &e, const uint64_t *postBase, uint32_t z) {
+    if (e.x >> 63) return (z ? e.y : e.x) & 0x7FFFFFFFFFFFFFFFull;
+    return __ldg(postBase + (uint32_t)e.x + z);
+}
 
 // Truncation key exported with a hit when the target shards of a multi-GPU run are merged (spb_prefilter_merge_shards).
 // The reference cuts a list at max-seqs in the order of its stable counting sorts (QueryMatcher.cpp:131-164,
@@ -385,22 +406,24 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
             const int x2 = s_q[w + A.pat.pos[3]] + 20 * s_q[w + A.pat.pos[4]] + 400 * s_q[w + A.pat.pos[5]];
             const uint32_t nKmers = warp_unit_kmers(A.row3, A.cnt3, x1, x2, (int)s_thr[w], (int)s_n1[w], a0, s_excl[wid], s_i1[wid],
                 [&](uint32_t kmer, uint32_t a, uint32_t b, bool valid) {
-                    uint32_t o0 = 0, len = 0;
-                    if (valid) {
-                        o0 = __ldg(A.koff + kmer);
-                        len = __ldg(A.koff + kmer + 1) - o0;
+                    uint32_t len = 0;
+                    ulonglong2 e = make_ulonglong2(0ull, 0ull);
+                    const uint64_t *pb = nullptr;
+                    if (valid && ((__ldg(A.kbits + (kmer >> 5)) >> (kmer & 31)) & 1u)) {
+                        e = kmer_entry(A, kmer, pb, false);
+                        len = entry_count(e);
                     }
                     if (pass == 0) {
                         nm += len;
                         for (uint32_t z = 0; z < len; z++) {
-                            const uint32_t h = id_hash((uint32_t)(__ldg(A.post + o0 + z) >> 16));
+                            const uint32_t h = id_hash((uint32_t)(entry_posting(e, pb, z) >> 16));
                             const uint32_t m = 1u << (h & 31);
                             const uint32_t old = atomicOr(&s_seen1[h >> 5], m);
                             if (old & m) atomicOr(&s_seen2[h >> 5], m);
                         }
                     } else {
                         for (uint32_t z = 0; z < len; z++) {
-                            const uint64_t pe = __ldg(A.post + o0 + z);   // id << 16 | pos
+                            const uint64_t pe = entry_posting(e, pb, z);   // id << 16 | pos
                             const uint32_t id = (uint32_t)(pe >> 16);
                             const uint32_t h = id_hash(id);
                             const bool twice = (s_seen2[h >> 5] >> (h & 31)) & 1u;
@@ -680,6 +703,7 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
 
 struct QMeta {               // per query, expand -> bookkeeping
     uint32_t chunk0, nChunks, K;
+    uint32_t nHits;          // classify_kernel: hits of the query = sum of its chunk counts
     int32_t minCorr;
     signed char corr[PW_MAXL];
 };
@@ -873,7 +897,6 @@ __global__ void __launch_bounds__(PX_CH, 6) lookup_kernel(PrefArgs A) {
     __shared__ uint32_t s_w[2][2][PX_CH / 32];     // [trip parity][chunk of the pair][warp]
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t nCh = min(*A.chunkCursor, A.chunkCap);
-    const uint64_t *__restrict__ post = A.post;
     uint64_t *__restrict__ arena = A.hitArena;
     const uint32_t nPairs = (nCh + 1) >> 1;
     // private stretch of the hit arena
@@ -891,6 +914,7 @@ __global__ void __launch_bounds__(PX_CH, 6) lookup_kernel(PrefArgs A) {
         const uint32_t c0 = 2 * pr;
         uint32_t kmer[2], w[2], n[2];
         ulonglong2 e[2];
+        const uint64_t *pb[2] = {nullptr, nullptr};
         bool occ[2];
 #pragma unroll
         for (int u = 0; u < 2; u++) {
@@ -906,12 +930,12 @@ __global__ void __launch_bounds__(PX_CH, 6) lookup_kernel(PrefArgs A) {
 #pragma unroll
         for (int u = 0; u < 2; u++) {
             e[u] = make_ulonglong2(0ull, 0ull);
-            if (occ[u]) e[u] = __ldcs(A.direct + kmer[u]);
+            if (occ[u]) e[u] = kmer_entry(A, kmer[u], pb[u], true);
         }
         uint32_t inc[2];
 #pragma unroll
         for (int u = 0; u < 2; u++) {
-            n[u] = (e[u].x >> 63) ? 1u + (uint32_t)(e[u].y >> 63) : (uint32_t)(e[u].x >> 32);
+            n[u] = entry_count(e[u]);
             inc[u] = (uint32_t)warp_incl_scan((int)n[u]);
             if (lane == 31) s_w[par][u][wid] = inc[u];
         }
@@ -941,7 +965,7 @@ __global__ void __launch_bounds__(PX_CH, 6) lookup_kernel(PrefArgs A) {
                     if (e[u].y >> 63) dst[1] = hit_record(e[u].y, kw, w[u]);
                 } else {
                     // list of three or more postings: four independent loads in flight per trip
-                    const uint64_t *__restrict__ pl = post + (uint32_t)e[u].x;
+                    const uint64_t *__restrict__ pl = pb[u] + (uint32_t)e[u].x;
                     for (uint32_t z = 0; z < n[u]; z += 4) {
                         uint64_t pe[4];
 #pragma unroll
@@ -954,6 +978,31 @@ __global__ void __launch_bounds__(PX_CH, 6) lookup_kernel(PrefArgs A) {
             }
         }
         cur += tt;
+    }
+}
+
+// After the gather: hits per query (sum of its chunk counts) and the split of the tile into the queries a single warp finishes
+// (stay ST_PENDING) and the heavy ones a CTA takes (listed, ST_TEAM) -- the two bookkeeping launches then run side by side on
+// two streams.  A chunk that found the hit arena full sends its query to the next round (ST_RETRY).
+__global__ void classify_kernel(PrefArgs A) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= A.nList) return;
+    const uint32_t qi = A.qlist[A.listOff + (size_t)s * A.listStride];
+    if (A.status[qi] != ST_PENDING) return;
+    QMeta &M = A.meta[qi];
+    uint32_t sum = 0;
+    bool over = false;
+    for (uint32_t ch = 0; ch < M.nChunks; ch++) {
+        const uint32_t n = A.chunkHits[M.chunk0 + ch].y;
+        over = over || (n == PX_OVER);
+        sum += (n == PX_OVER) ? 0u : n;
+    }
+    M.nHits = sum;
+    if (over) {
+        A.outStart[qi] = 0; A.outCount[qi] = 0; A.status[qi] = ST_RETRY;
+    } else if (sum > A.hitsSolo) {
+        A.teamList[atomicAdd(A.teamCount, 1u)] = qi;
+        A.status[qi] = ST_TEAM;
     }
 }
 
@@ -1115,22 +1164,9 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
         for (int i = tw * 32 + lane; i < BM2; i += TEAM * 32) S.seen2[i] = 0;
         if (tw == 0) {
             for (int i = lane; i < L; i += 32) { S.q[i] = A.q[qo + i]; S.corr[i] = M.corr[i]; }
-            // hits of the query = sum of its chunk counts; a chunk that found the hit arena full sends the query to the next round
-            const uint32_t nCh = M.nChunks, c0 = M.chunk0;
-            uint32_t sum = 0, over = 0;
-            for (uint32_t ch = (uint32_t)lane; ch < nCh; ch += 32) {
-                const uint32_t n = __ldcg(A.chunkHits + c0 + ch).y;
-                over |= (n == PX_OVER) ? 1u : 0u;
-                sum += (n == PX_OVER) ? 0u : n;
-            }
-            for (int d = 16; d > 0; d >>= 1) {
-                sum += __shfl_xor_sync(0xffffffffu, sum, d);
-                over |= __shfl_xor_sync(0xffffffffu, over, d);
-            }
+            const uint32_t nCh = M.nChunks, c0 = M.chunk0, sum = M.nHits;
             if (lane == 0) {
-                uint32_t why = ST_OK, reason = 0;
-                if (over) why = ST_RETRY;
-                else if (SOLO && sum > A.hitsSolo) why = ST_TEAM;
+                const uint32_t why = ST_OK, reason = 0;
                 S.v_K = M.K; S.v_nHits = sum; S.v_nSurv = 0; S.v_nFin = 0; S.v_slow = why; S.v_why = reason;
                 S.v_minCorr = M.minCorr; S.v_chunk0 = c0; S.v_nCh = nCh;
             }
@@ -1424,7 +1460,7 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
             if (why != ST_OK) {
                 if (lane == 0) {
                     A.outStart[qi] = 0; A.outCount[qi] = 0; A.need[qi] = reason;
-                    if (why == ST_TEAM) A.teamList[atomicAdd(A.teamCount, 1u)] = qi;
+                    if (why == ST_TEAM) A.teamList2[atomicAdd(A.teamCount2, 1u)] = qi;
                     A.status[qi] = why;
                 }
             } else {
@@ -1882,8 +1918,15 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
     A.tres = c->d_tres.as<uint8_t>();
     A.toff = c->d_toff.as<uint32_t>();
     A.T = c->T;
-    A.koff = c->d_koff.as<uint32_t>();
-    A.post = c->d_post.as<uint64_t>();
+    A.nShards = c->n_shards;
+    A.shardR = c->shard_R;
+    for (int i = 0; i < SPB_MAX_SHARDS; i++) {
+        A.directS[i] = reinterpret_cast<const ulonglong2 *>(c->shard_direct[i]);
+        A.postS[i] = reinterpret_cast<const uint64_t *>(c->shard_post[i]);
+        SPB_CHECK(i >= c->n_shards || (A.directS[i] && A.postS[i]), "spb_prefilter: shard %d of the k-mer table is not attached "
+                  "(spb_index_shard_attach_ipc / _ctx)", i);
+    }
+    A.kbits = c->d_kbits.as<uint32_t>();
     A.row3 = c->d_row3.as<uint32_t>();
     A.cnt3 = c->d_cnt3.as<uint16_t>();
     A.mat = c->d_mat.as<Matrices>();
@@ -1941,8 +1984,6 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
         if (const char *e = getenv("SPB_LOOKUP_CTAS")) lookupPerSm = std::max(1, std::min(16, atoi(e)));
         if (const char *e = getenv("SPB_EXPAND_CTAS")) expandPerSm = std::max(1, std::min(16, atoi(e)));
         const int soloBlocks = c->n_sm * soloPerSm, teamBlocks = c->n_sm * teamPerSm;
-        A.direct = c->d_direct.as<ulonglong2>();
-        A.kbits = c->d_kbits.as<uint32_t>();
         A.hitsSolo = 2048;     // r2d sweep: 1024 / 2048 / 4096 / 8192 -> 0.62 / 0.54 / 0.61 / 0.90 ms of bookkeeping
         if (const char *e = getenv("SPB_HITS_SOLO")) A.hitsSolo = (uint32_t)std::max(1, atoi(e));
         const uint32_t hitCapSolo = std::max<uint32_t>(A.hitsSolo, PW_SCAP), hitCapTeam = 32768;
@@ -1954,12 +1995,20 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
         if (const char *e = getenv("SPB_PF_CHUNKS")) chunkCap = (uint32_t)std::max(256, atoi(e));
         uint32_t hitsPerChunk = 256;
         if (const char *e = getenv("SPB_PF_HITS_PER_CHUNK")) hitsPerChunk = (uint32_t)std::max(1, atoi(e));
-        if (c->s_j.ensure(std::max((size_t)soloBlocks * PW_WARPS * sliceSolo, (size_t)teamBlocks * sliceTeam) * sizeof(uint64_t)) ||
-            c->s_k.ensure((size_t)Q * 4 + 64) || c->p_retry.ensure((size_t)Q * 4 + 64) || c->p_meta.ensure((size_t)Q * sizeof(QMeta))) return 1;
+        const size_t soloScratch = (size_t)soloBlocks * PW_WARPS * sliceSolo;      // the two bookkeeping launches run concurrently
+        if (c->s_j.ensure((soloScratch + (size_t)teamBlocks * sliceTeam) * sizeof(uint64_t)) ||
+            c->s_k.ensure((size_t)Q * 4 + 64) || c->p_team2.ensure((size_t)Q * 4 + 64) || c->p_retry.ensure((size_t)Q * 4 + 64) || c->p_meta.ensure((size_t)Q * sizeof(QMeta))) return 1;
         A.hitScratch = c->s_j.as<uint64_t>();
         A.meta = c->p_meta.as<QMeta>();
         A.teamList = c->s_k.as<uint32_t>();
-        // tile counters: [0] expand scheduler, [1] TEAM = 1 scheduler, [2] TEAM = 8 scheduler, [3] chunks allocated, [4] team list
+        A.teamList2 = c->p_team2.as<uint32_t>();
+        if (!c->aux_stream) {
+            SPB_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+            SPB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+            SPB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        }
+        // tile counters: [0] expand scheduler, [1] TEAM = 1 scheduler, [2] TEAM = 8 scheduler, [3] chunks allocated, [4] team list,
+        // [5] scheduler of the second TEAM = 8 launch, [6] its list (hand-overs of the TEAM = 1 launch)
         unsigned int *tc = reinterpret_cast<unsigned int *>(c->s_f.as<unsigned long long>() + 16);
         const uint32_t *curList = c->d_qorder.as<uint32_t>();   // longest queries first (tail of a launch)
         uint32_t curN = Q;
@@ -1993,6 +2042,7 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
                 A.nListPtr = nullptr;
                 A.chunkCursor = tc + 3;
                 A.teamCount = tc + 4;
+                A.teamCount2 = tc + 6;
                 A.qCounter = tc + 0;
                 SPB_CUDA(cudaEventRecord(ep[0], st));
                 expand_kernel<<<c->n_sm * expandPerSm, PW_WARPS * 32, 0, st>>>(A);
@@ -2001,19 +2051,41 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
                 lookup_kernel<<<c->n_sm * lookupPerSm, PX_CH, 0, st>>>(A);   // persistent: lookupPerSm CTAs per SM
                 SPB_CUDA(cudaGetLastError()); c->n_launches++;
                 SPB_CUDA(cudaEventRecord(ep[2], st));
+                classify_kernel<<<(A.nList + 255) / 256, 256, 0, st>>>(A);
+                SPB_CUDA(cudaGetLastError()); c->n_launches++;
+                SPB_CUDA(cudaEventRecord(c->ev_fork, st));
+                // heavy queries: CTA per query on the second stream, next to the warp-per-query launch
+                {
+                    PrefArgs T8 = A;
+                    T8.qCounter = tc + 2;
+                    T8.qlist = c->s_k.as<uint32_t>();
+                    T8.listOff = 0;
+                    T8.listStride = 1;
+                    T8.nListPtr = tc + 4;
+                    T8.hitCap = hitCapTeam;
+                    T8.hitScratch = c->s_j.as<uint64_t>() + soloScratch;
+                    SPB_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+                    bookkeep_kernel<PW_TEAM><<<teamBlocks, PW_TEAM * 32, 0, c->aux_stream>>>(T8);
+                    SPB_CUDA(cudaGetLastError()); c->n_launches++;
+                    SPB_CUDA(cudaEventRecord(c->ev_join, c->aux_stream));
+                }
                 A.qCounter = tc + 1;
                 A.hitCap = hitCapSolo;
                 bookkeep_kernel<1><<<soloBlocks, PW_WARPS * 32, 0, st>>>(A);
                 SPB_CUDA(cudaGetLastError()); c->n_launches++;
+                SPB_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
                 SPB_CUDA(cudaEventRecord(ep[3], st));
-                A.qCounter = tc + 2;
-                A.qlist = c->s_k.as<uint32_t>();
+                // what the warp launch handed over at its end (lists cut at max-seqs, > 256 winners): usually nothing
+                A.qCounter = tc + 5;
+                A.qlist = c->p_team2.as<uint32_t>();
                 A.listOff = 0;
                 A.listStride = 1;
-                A.nListPtr = tc + 4;
+                A.nListPtr = tc + 6;
                 A.hitCap = hitCapTeam;
+                A.hitScratch = c->s_j.as<uint64_t>() + soloScratch;
                 bookkeep_kernel<PW_TEAM><<<teamBlocks, PW_TEAM * 32, 0, st>>>(A);
                 SPB_CUDA(cudaGetLastError()); c->n_launches++;
+                A.hitScratch = c->s_j.as<uint64_t>();
                 SPB_CUDA(cudaEventRecord(ep[4], st));
                 nTilesRun++;
             }

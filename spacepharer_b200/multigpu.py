@@ -15,6 +15,11 @@ query split, M/alignment/Alignment.cpp:226-249): every rank owns one `Searcher` 
       order are the reference's selection (QueryMatcher.cpp:131-164).
   split_mode "query": every rank holds the full index and processes its own slice of the query batch; no collective
       on the data path.
+  split_mode "index": the k-mer table (direct table + posting lists) is cut into `world` contiguous k-mer ranges, rank r
+      keeps range r in its HBM, and the lookup kernel of every rank gathers the entries of the other ranges with plain
+      loads on peer-mapped pointers over NVLink (CUDA IPC handles exchanged once at load time).  Queries are partitioned
+      like in "query": no hit list is exchanged or merged, the result is the unsplit one by construction, and both the
+      table capacity and the throughput scale with the number of GPUs.
 
 torch / torch.distributed are plumbing only (process group, NCCL, device buffers of the exchange); all arithmetic is in
 libspb200's kernels.
@@ -208,6 +213,17 @@ class ShardedSearcher:
             lo, hi = int(toff[frm]), int(toff[frm + size])
             self.shard = (frm, size)
             st = s.build_index(masked[lo:hi], toff[frm:frm + size + 1] - toff[frm])
+        elif self.world > 1 and self.split_mode == "index":
+            import torch.distributed as dist
+            self.shard = (0, T)
+            st = s.build_index(masked, toff)
+            s.shard_index(self.rank, self.world)        # keep k-mer range `rank`, free the rest of the table
+            handles = [None] * self.world
+            dist.all_gather_object(handles, s.shard_export())
+            for r in range(self.world):
+                if r != self.rank:
+                    s.shard_attach_ipc(r, handles[r])
+            dist.barrier()
         else:
             self.shard = (0, T)
             st = s.build_index(masked, toff)
@@ -220,7 +236,7 @@ class ShardedSearcher:
         return Q
 
     def _my_queries(self, qres, qoff):
-        if self.world > 1 and self.split_mode == "query":
+        if self.world > 1 and self.split_mode in ("query", "index"):
             lo, hi = query_ranges(len(qoff) - 1, self.world)[self.rank]
             qoff = np.ascontiguousarray(qoff, dtype=np.uint64)
             sub = qoff[lo:hi + 1] - qoff[lo]

@@ -163,7 +163,52 @@ def _rank_main(rank, world, port, mode, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["target", "query"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_index_split_on_one_gpu(world):
+    """Index split (k-mer ranges of the table held by different contexts, gathered through mapped pointers): `world` contexts
+    on this GPU each keep one range and attach the others; every one of them returns the unsplit prefilter lists and rows.
+    (Same code path as across GPUs -- there the mapped pointers are NVLink peer memory.)"""
+    from spacepharer_b200 import api
+    tres, toff, qres, qoff = _workload()
+    ref = api.Searcher(device=0)
+    ref.build_index(tres, toff)
+    ref.set_align_targets(tres, toff)
+    off0, hits0, st0 = ref.prefilter(qres, qoff)
+    _, rows0, cig0, _, _ = ref.search(qres, qoff, int(toff[-1]))
+    ref.close()
+    ctxs = [api.Searcher(device=0) for _ in range(world)]
+    try:
+        for r, s in enumerate(ctxs):
+            s.build_index(tres, toff)
+            s.shard_index(r, world)
+        for r, s in enumerate(ctxs):
+            for p, o in enumerate(ctxs):
+                if p != r:
+                    s.shard_attach(p, o)
+        with pytest.raises(Exception):
+            ctxs[0].export_index()          # the CSR view is gone once the table is sharded
+        for r, s in enumerate(ctxs):
+            off, hits, st = s.prefilter(qres, qoff)
+            assert (off == off0).all() and (hits["id"] == hits0["id"]).all() and (hits["score"] == hits0["score"]).all()
+            assert (hits["diag"] == hits0["diag"]).all() and st["n_db_matches"] == st0["n_db_matches"]
+        # a lane of a sharded context inherits the shard map; max-seqs small enough to reach the fallback kernels as well
+        ln = ctxs[1].lane()
+        ctxs[1].set_align_targets(tres, toff)
+        _, rows, cig, _, _ = ctxs[1].search(qres, qoff, int(toff[-1]))
+        assert len(rows) == len(rows0) and (rows["target"] == rows0["target"]).all() and (rows["score"] == rows0["score"]).all()
+        o5, h5, _ = ln.prefilter(qres, qoff, max_seqs=5)
+        ln.close()
+        ref = api.Searcher(device=0)
+        ref.build_index(tres, toff)
+        o5r, h5r, _ = ref.prefilter(qres, qoff, max_seqs=5)
+        ref.close()
+        assert (o5 == o5r).all() and (h5["id"] == h5r["id"]).all() and (h5["score"] == h5r["score"]).all()
+    finally:
+        for s in ctxs:
+            s.close()
+
+
+@pytest.mark.parametrize("mode", ["target", "query", "index"])
 def test_two_gpus_equal_one(tmp_path, mode):
     import torch
     import torch.multiprocessing as mp
