@@ -51,7 +51,12 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--spacers", type=int, default=10000)
     ap.add_argument("--genomes", type=int, default=8000)
-    ap.add_argument("--split-mode", default="query", choices=["target", "query"])
+    ap.add_argument("--split-mode", default="index", choices=["index", "target", "query"],
+                    help="N > 1: index = k-mer table sharded over the GPUs, gathered through NVLink peer memory, queries partitioned "
+                         "(default); target = MMseqs2-style target split with hit-list exchange + merge; query = full index per GPU")
+    ap.add_argument("--strong-spacers", type=int, default=1000000,
+                    help="spacers of the strong-scaling leg (BASELINE config 4: the whole job split over the GPUs); 0 = skip")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity_ok check (rows of the config-2 batch vs the reference digest)")
     ap.add_argument("--cpu-sample-spacers", type=int, default=0, help="spacers in the CPU baseline sample (0 = auto)")
     ap.add_argument("--lanes", type=int, default=3,
                     help="contexts per GPU sharing one index; batches of different lanes overlap on the device (query split / 1 GPU)")
@@ -292,7 +297,7 @@ def run_ours(args):
     if args.gpus != world and rank == 0:
         print("bench.py: warning: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
 
-    weak = world > 1 and args.split_mode == "query"
+    weak = world > 1 and args.split_mode in ("query", "index")
     tres, toff, qres, qoff = workload(args, world if weak else 1)
     T, Q = len(toff) - 1, len(qoff) - 1
     db_res = int(toff[-1])
@@ -312,6 +317,18 @@ def run_ours(args):
     q_np, o_np = q_pin.numpy(), o_pin.numpy().view(np.uint64)
     stream = torch.cuda.ExternalStream(eng.searcher.stream_ptr(), device=torch.device("cuda", local))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    # three distinct batches of the same shape rotate through the lanes (value leg: lane l owns batch l mod 3; e2e leg: step
+    # i searches batch i mod 3), so no timed step repeats the previous step's inputs
+    from spacepharer_b200 import synth
+    batches = [(q_np, o_np)]
+    keep_pins = []
+    for extra_seed in (1001, 1002):
+        bq, bo, _ = synth.make_query_frames(args.spacers * (world if weak else 1), tres, toff, seed=extra_seed)
+        bqp = torch.from_numpy(np.ascontiguousarray(bq)).pin_memory()
+        bop = torch.from_numpy(np.ascontiguousarray(bo).view(np.int64)).pin_memory()
+        keep_pins += [bqp, bop]
+        batches.append((bqp.numpy(), bop.numpy().view(np.uint64)))
+    batch_q = [eng.queries_per_step(len(o) - 1) for _, o in batches]
 
     def barrier():
         torch.cuda.synchronize()
@@ -328,7 +345,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    pk_ms, pk_bytes, sw_ms, sw_cells = [], [], [], []
+    pk_ms, pk_bytes, sw_ms, sw_cells, pk_phase = [], [], [], [], []
     barrier()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
@@ -339,6 +356,7 @@ def run_ours(args):
         ev[k][1].record(stream)
         pk_ms.append(st["prefilter"]["kernel_ms"])
         pk_bytes.append(st["prefilter"]["algo_bytes"])
+        pk_phase.append(st["prefilter"])
         sw_ms.append(st["align"]["kernel_ms"])
         sw_cells.append(st["align"]["n_cells"])
     barrier()
@@ -347,6 +365,9 @@ def run_ours(args):
     launches = eng.launches() - launches0
     last = st
     single_ms = dev_ms
+    single_launches = launches
+    value_queries = eng.queries_per_step(Q) * args.steps
+    phase = {k: float(np.mean([x[k] for x in pk_phase])) for k in ("expand_ms", "lookup_ms", "bookkeep_ms")}
 
     # ---- device-resident leg over the lanes: the whole-job throughput ("value") ----
     # K steps shared by n_lanes contexts (one host thread each, every lane holds the batch resident); one CUDA event per lane
@@ -362,7 +383,7 @@ def run_ours(args):
             with torch.cuda.stream(ext[l]):
                 fl[l].zero_()
 
-        eng.run_stream([(q_np, o_np)], db_res, steps=max(args.warmup, 2) * n_lanes, resident=True, before_step=before_step)
+        eng.run_stream(batches, db_res, steps=max(args.warmup, 2) * n_lanes, resident=True, before_step=before_step)
         launches0 = eng.launches()
         e0 = [torch.cuda.Event(enable_timing=True) for _ in lanes]
         e1 = [torch.cuda.Event(enable_timing=True) for _ in lanes]
@@ -370,7 +391,8 @@ def run_ours(args):
         t_wall0 = time.perf_counter()
         for l in range(len(lanes)):
             e0[l].record(ext[l])
-        eng.run_stream([(q_np, o_np)], db_res, steps=args.steps, resident=True, before_step=before_step)
+        vsts = eng.run_stream(batches, db_res, steps=args.steps, resident=True, before_step=before_step)
+        value_queries = sum(batch_q[st["lane"] % len(batches)] for st in vsts)
         for l in range(len(lanes)):
             e1[l].record(ext[l])
         barrier()
@@ -384,12 +406,13 @@ def run_ours(args):
     # back into pinned host buffers of the library (D2H); wall clock from the first upload to the last row landed
     d2h = 0
     if n_lanes > 1:
-        eng.run_stream([(q_np, o_np)], db_res, steps=2 * n_lanes)
+        eng.run_stream(batches, db_res, steps=2 * n_lanes)
         barrier()
         t0 = time.perf_counter()
-        sts = eng.run_stream([(q_np, o_np)], db_res, steps=args.steps)
+        sts = eng.run_stream(batches, db_res, steps=args.steps)
         barrier()
         e2e_s = time.perf_counter() - t0
+        e2e_queries = sum(batch_q[i % len(batches)] for i in range(args.steps))
         d2h, n_rows_e2e = sts[-1]["d2h_bytes"], sts[-1]["rows"]
         e2e_how = ("%d lanes per GPU (contexts sharing one index, one host thread each): upload, kernels and read-back of different "
                    "batches overlap; all copies inside the timed region" % n_lanes)
@@ -409,6 +432,7 @@ def run_ours(args):
             v.close()
             return n
 
+        e2e_queries = eng.queries_per_step(Q) * args.steps
         for k in range(args.steps):
             cur = eng.search_host_begin(q_np, o_np, db_res)
             if pending is not None:
@@ -435,20 +459,109 @@ def run_ours(args):
         exh = {"kernel_ms": float(np.mean([r["kernel_ms"] for r in runs])), "cells": float(runs[-1]["n_cells"]),
                "scored": float(runs[-1]["n_scored"]), "kept": float(runs[-1]["n_kept"]), "queries": nq}
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3, exh["kernel_ms"] if exh else 0.0, single_ms], dtype=torch.float64, device="cuda")
+    # ---- strong-scaling leg (BASELINE config 4): ONE job of 1 M spacers split over the GPUs ----
+    # the whole job goes through the public API with host buffers (H2D of the frames, D2H of the sorted rows + CIGARs inside
+    # the timed region), in chunks of ~125 k frames per GPU over the lanes; total work is fixed, so the N-GPU time against the
+    # 1-GPU time is the strong-scaling curve of the split named in config.split_mode
+    strong = None
+    if args.strong_spacers > 0:
+        sq, so, _ = synth.make_query_frames(args.strong_spacers, tres, toff)
+        SQ = len(so) - 1
+        sqp = torch.from_numpy(np.ascontiguousarray(sq)).pin_memory()
+        sqn = sqp.numpy()
+        so = np.ascontiguousarray(so, dtype=np.uint64)
+        per_gpu = 125000
+        step_q = per_gpu * world
+        chunks = []
+        for c0 in range(0, SQ, step_q):
+            c1 = min(SQ, c0 + step_q)
+            chunks.append((sqn[int(so[c0]):int(so[c1])], (so[c0:c1 + 1] - so[c0]).astype(np.uint64)))
+        rows_total = [0]
+
+        def run_chunks(lst):
+            if world > 1 and args.split_mode == "target":
+                pending, stats = None, []
+                for cq, co in lst:
+                    cur = eng.search_host_begin(cq, co, db_res)
+                    stats.append(cur["stats"])
+                    if pending is not None:
+                        v = pending["view"].wait(); rows_total[0] += len(v.rows); v.close()
+                    pending = cur
+                v = pending["view"].wait(); rows_total[0] += len(v.rows); v.close()
+                return stats
+            sts_ = eng.run_stream(lst, db_res)
+            rows_total[0] += sum(x["rows"] for x in sts_)
+            return sts_
+
+        run_chunks(chunks[: max(2, 2 * n_lanes)])
+        rows_total[0] = 0
+        barrier()
+        t0 = time.perf_counter()
+        ssts = run_chunks(chunks)
+        barrier()
+        strong_s = time.perf_counter() - t0
+        stage = {k: float(sum(x["prefilter"][k] for x in ssts)) for k in ("expand_ms", "lookup_ms", "bookkeep_ms", "kernel_ms")}
+        stage["align_ms"] = float(sum(x["align"]["total_ms"] for x in ssts))
+        kmers = float(sum(x["prefilter"]["n_kmers"] for x in ssts))
+        strong = {"wall_s": strong_s, "rows": float(rows_total[0]), "kmers": kmers, "stage": stage, "chunks": len(chunks)}
+        del sqp, sqn, chunks
+
+    # ---- parity of the measured configuration against the reference binary (config 2 digest) ----
+    parity = None
+    if not args.no_parity:
+        import hashlib
+        pq, po = (qres, qoff) if world == 1 else synth.make_query_frames(args.spacers, tres, toff)[:2]
+        res = eng.search_host(np.ascontiguousarray(pq), np.ascontiguousarray(po, dtype=np.uint64), db_res)
+        rows = res["rows"]
+        lines = api.format_align_rows(rows, res["cigar"], np.diff(np.asarray(po, dtype=np.uint64)).astype(np.int64),
+                                      np.diff(np.asarray(toff, dtype=np.uint64)).astype(np.int64))
+        mine = (rows["query"].astype(np.int64).tolist(), lines)
+        allparts = [None] * world
+        if world > 1:
+            dist.all_gather_object(allparts, mine)
+        else:
+            allparts = [mine]
+        if rank == 0:
+            ent = {}
+            n_rows = 0
+            for qs, ls in allparts:
+                n_rows += len(ls)
+                for q, l in zip(qs, ls):
+                    ent.setdefault(int(q), []).append(l)
+            h = hashlib.sha256()
+            for k in range(len(po) - 1):
+                h.update(b"%d\n" % k)
+                h.update("".join(x + "\n" for x in ent.get(k, [])).encode())
+            parity = {"aln_sha256": h.hexdigest(), "aln_rows": n_rows}
+            try:
+                want = json.load(open(os.path.join(ROOT, "tests", "golden", "config2_digest.json")))
+                ok = (args.spacers == want.get("spacers", 10000) and args.genomes == 8000 and not args.no_mask and
+                      parity["aln_sha256"] == want["aln_sha256"] and n_rows == want["aln_rows"])
+                parity["reference"] = "tests/golden/config2_digest.json (SHA-256 of the reference binary's alignment DB, canonical form)"
+                parity["parity_ok"] = bool(ok)
+            except Exception as e:  # noqa: BLE001
+                parity["parity_ok"] = None
+                parity["error"] = str(e)
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, exh["kernel_ms"] if exh else 0.0, single_ms, strong["wall_s"] * 1e3 if strong else 0.0],
+                     dtype=torch.float64, device="cuda")
+    ssum = torch.tensor([strong["rows"], strong["kmers"]] + [strong["stage"][k] for k in ("expand_ms", "lookup_ms", "bookkeep_ms", "kernel_ms", "align_ms")]
+                        if strong else [0.0] * 7, dtype=torch.float64, device="cuda")
     tsum = torch.tensor([exh["cells"], exh["scored"], exh["kept"], exh["queries"]] if exh else [0.0] * 4, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-    dev_ms, e2e_ms, exh_ms, single_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+        dist.all_reduce(ssum, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms, exh_ms, single_ms, strong_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3]), float(t[4])
     q_total = eng.queries_per_step(Q)
 
     if rank == 0:
         peak, peak_src = measured_peak()
+        traffic = ncu_traffic()
         kms = float(np.mean(pk_ms))
         achieved = float(np.mean(pk_bytes)) / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
         line = {
-            "metric": METRIC, "value": q_total * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": value_queries / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak" if (weak or world == 1) else "strong", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic",
@@ -462,23 +575,50 @@ def run_ours(args):
                                  "sum of per-step CUDA-event intervals on the library stream, max over ranks",
                        "index": "resident (built once: %.1f ms device, %.2f s wall incl. H2D; tantan host pre-step %.2f s, %d residues masked)"
                                 % (ist["build_ms"], build_s, mask_s, n_masked)},
-            "e2e": {"value": q_total * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+            "e2e": {"value": e2e_queries / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(q_np.nbytes + o_np.nbytes), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps,
                     "pipeline": e2e_how},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "prefilter_team_kernel<1> + <8>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
-                         "algo_bytes_per_launch": float(np.mean(pk_bytes)), "kernel_ms": kms,
-                         "share_of_step": kms / (single_ms / args.steps),
-                         "measured": "single-lane segment (%d steps, the kernel alone on the device, CUDA events on its stream)" % args.steps},
-            "single_lane": {"value": q_total * args.steps / (single_ms * 1e-3), "ms_per_step": single_ms / args.steps},
-            "sw": {"gcups": float(np.mean(sw_cells)) / (float(np.mean(sw_ms)) * 1e-3) / 1e9 if np.mean(sw_ms) > 0 else None,
-                   "kernel_ms": float(np.mean(sw_ms)), "cells_per_step": float(np.mean(sw_cells)),
-                   "pairs": last["align"]["n_pairs"], "rows": last["align"]["n_rows"]},
+            # the prefilter = three kernel classes (expand -> lookup -> bookkeeping); `achieved` follows the contract: ALGORITHMIC
+            # bytes of the whole prefilter over the summed duration of its kernels.  The lookup kernel is the
+            # HBM-bound one: its DRAM traffic over its own duration is reported beside it (dram_*), from the committed ncu capture.
+            "roofline": dict({"bound": "hbm", "kernel": "expand_kernel + lookup_kernel + bookkeep_kernel<1|8> (prefilter)",
+                              "achieved": achieved, "peak": peak, "unit": "GB/s",
+                              "frac": achieved / peak, "traffic": traffic.get("prefilter_dram_bytes_per_launch"), "peak_source": peak_src,
+                              "algo_bytes_per_launch": float(np.mean(pk_bytes)), "kernel_ms": kms,
+                              "share_of_step": kms / (single_ms / args.steps),
+                              "kernels_ms": phase,
+                              "measured": "single-lane segment (%d steps, the kernels alone on the device, CUDA events on their stream)" % args.steps},
+                             **({"lookup": {"kernel_ms": phase["lookup_ms"],
+                                            "dram_bytes_per_launch": traffic.get("lookup_kernel_dram_bytes_per_launch"),
+                                            "dram_gbs": traffic["lookup_kernel_dram_bytes_per_launch"] / (phase["lookup_ms"] * 1e-3) / 1e9,
+                                            "dram_frac_of_peak": traffic["lookup_kernel_dram_bytes_per_launch"] / (phase["lookup_ms"] * 1e-3) / 1e9 / peak,
+                                            "note": "bytes from the committed ncu --set full capture of the same workload (profiles/), "
+                                                    "duration measured live"}}
+                                if traffic.get("lookup_kernel_dram_bytes_per_launch") and phase["lookup_ms"] > 0 else {})),
+            "single_lane": {"value": q_total * args.steps / (single_ms * 1e-3), "ms_per_step": single_ms / args.steps,
+                            "own_launches_per_step": single_launches / float(args.steps)},
+            "sw": sw_block(float(np.mean(sw_cells)), float(np.mean(sw_ms)), last["align"], clocks),
             "clocks": clocks,
             "wall_s_value_leg": wall_value,
         }
+        if strong:
+            line["strong_scaling"] = {
+                "value": SQ / (strong_ms * 1e-3), "unit": UNIT, "ms_total": strong_ms, "scaling": "strong",
+                "workload": "BASELINE config 4: %d synthetic spacers = %d frames, ONE job split over %d GPU(s) (%s), chunks of %d frames "
+                            "per GPU through the public API with pinned host buffers (H2D + D2H inside the timed region)"
+                            % (args.strong_spacers, SQ, world, ("split_mode " + args.split_mode) if world > 1 else "single GPU", per_gpu),
+                "rows": int(ssum[0]), "similar_kmers": int(ssum[1]),
+                "stage_ms_summed_over_gpus": {"expand": float(ssum[2]), "lookup": float(ssum[3]), "bookkeeping": float(ssum[4]),
+                                              "prefilter_kernels": float(ssum[5]), "align_stage": float(ssum[6])},
+                "nvlink": ({"mode": "index split: table entries of the other GPUs' k-mer ranges are gathered with peer loads inside lookup_kernel",
+                            "bytes_est": float(ssum[1]) * 0.336 * (world - 1) / world * 32.0,
+                            "how": "similar k-mers x 0.336 (share with an occupied table entry, measured on this index) x (N-1)/N remote x one "
+                                   "32-byte sector per 16-byte entry; posting lists of >= 3 targets (5 % of the entries) add their own sectors"}
+                           if (world > 1 and args.split_mode == "index") else None)}
+        if parity:
+            line["parity"] = parity
         if exh:
             line["sw_exhaustive"] = {
                 "gcups": float(tsum[0]) / (exh_ms * 1e-3) / 1e9 if exh_ms > 0 else None, "kernel_ms": exh_ms,
@@ -504,12 +644,25 @@ def run_ours(args):
 
 
 def ncu_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    """DRAM bytes per launch of the prefilter kernels from the committed ncu capture (profiles/traffic.json), or {}."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return float(json.load(open(p))["prefilter_kernel_dram_bytes_per_launch"])
+        return {k: float(v) for k, v in json.load(open(p)).items() if isinstance(v, (int, float))}
     except Exception:
-        return None
+        return {}
+
+
+def sw_block(cells, ms, aln, clocks):
+    """Smith-Waterman forward kernel: GCUPS and its integer-pipe roofline.  One packed DPX / SIMD-video instruction updates two
+    cells; the kernel issues SW_INSTR_PER_CELL_PAIR of them per row of a column pair (PRMT, VIADD, 3 x VIADDMNMX, 2 x VIMNMX + the
+    column maximum = 8), so the ceiling is SMs x 4 schedulers x 32 lanes x f_clk x 2 cells / 8 instructions."""
+    f = (clocks or {}).get("sm_mhz") or 1965.0
+    peak = 148 * 4 * 32 * f * 1e6 * 2 / 8.0 / 1e9
+    g = cells / (ms * 1e-3) / 1e9 if ms > 0 else None
+    return {"gcups": g, "kernel_ms": ms, "cells_per_step": cells, "pairs": aln["n_pairs"], "rows": aln["n_rows"],
+            "roofline": {"bound": "integer pipe (DPX s16x2)", "peak_gcups": peak, "frac": (g / peak) if g else None,
+                         "instr_per_cell_pair": 8, "sm_mhz": f,
+                         "note": "padded rows (queries shorter than the kernel's row count) are not counted as cells"}}
 
 
 _JSON_FD = None

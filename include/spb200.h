@@ -45,6 +45,8 @@ void spb_ctx_destroy(spb_ctx *ctx);
  * batches submitted to different lanes overlap on the GPU.  Create lanes after the parent's index / targets are set; do not
  * rebuild those or destroy the parent while a lane exists.  A lane cannot build an index or set targets itself. */
 int spb_ctx_create_lane(spb_ctx *parent, spb_ctx **out);
+/* number of CUDA devices visible to the process (0 without a driver / device) */
+int spb_device_count(void);
 const char *spb_last_error(void);
 const char *spb_version(void);
 /* the CUDA stream all work of this context is enqueued on (cudaStream_t as void*) */

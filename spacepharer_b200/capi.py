@@ -84,7 +84,7 @@ SYMBOLS = [
     "spb_pairs_exhaustive", "spb_align_exhaustive", "spb_spacer_frames", "spb_free_frames_result",
     "spb_ctx_create_lane", "spb_align_fetch_begin", "spb_align_fetch_wait",
     "spb_nucl_set_targets", "spb_nucl_set_queries", "spb_nucl_rescore", "spb_nucl_rescore_resident", "spb_free_nucl_result",
-    "spb_index_shard", "spb_index_shard_export", "spb_index_shard_attach_ipc", "spb_index_shard_attach_ctx",
+    "spb_device_count", "spb_index_shard", "spb_index_shard_export", "spb_index_shard_attach_ipc", "spb_index_shard_attach_ctx",
 ]
 
 _lib = None

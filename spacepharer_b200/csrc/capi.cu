@@ -54,7 +54,12 @@ void spb_ctx::pin_release(void *p) {
 extern "C" {
 
 const char *spb_last_error(void) { return spb::g_err; }
-const char *spb_version(void) { return "spb200 0.1 (sm_100a)"; }
+const char *spb_version(void) { return "spb200 0.2 (sm_100a)"; }
+int spb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 
 int spb_ctx_create(int device, spb_ctx **out) {
     SPB_CHECK(out != nullptr, "spb_ctx_create: out is NULL");

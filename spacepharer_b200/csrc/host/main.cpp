@@ -35,6 +35,8 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <memory>
+#include <atomic>
 #include <stdexcept>
 #include <exception>
 #include <functional>
@@ -82,6 +84,8 @@ struct Params {
     std::string alphSize = "nucl:5,aa:21", taxonList;
     int maxSeqLen = 65535;
     int device = 0, binSize = 0, byteLanes = 32, wordLanes = 16;
+    int gpus = 1;              // search / predictmatch: devices device .. device + gpus - 1, k-mer table sharded over them (index split)
+    int oversubscribe = 0;     // 1: with fewer devices than --gpus, several shard contexts share a device (same code path; tests)
     std::string gumbel, gumbelNucl;
     long batch = 250000;       // frames per GPU pass: formatting of batch k overlaps the kernels of batch k+1 (1 M spacers: 4.2 -> 3.7 s)
     // set-level stages (M/commons/Parameters.cpp:217,2277; src/commons/LocalParameters.h:75-77,171-176)
@@ -120,7 +124,7 @@ std::vector<FlagDef> flag_table(Params &p) {
         {"--perform-nucl-aln", 0, &p.performNuclAln}, {"--tax-fdr", 4, nullptr}, {"--remove-tmp-files", 4, nullptr},
         // spb200-specific
         {"--keep-intermediate", 0, &p.keepIntermediate},
-        {"--device", 0, &p.device}, {"--bin-size", 0, &p.binSize}, {"--byte-lanes", 0, &p.byteLanes}, {"--word-lanes", 0, &p.wordLanes},
+        {"--device", 0, &p.device}, {"--gpus", 0, &p.gpus}, {"--oversubscribe", 0, &p.oversubscribe}, {"--bin-size", 0, &p.binSize}, {"--byte-lanes", 0, &p.byteLanes}, {"--word-lanes", 0, &p.wordLanes},
         {"--gumbel", 3, &p.gumbel}, {"--gumbel-nucl", 3, &p.gumbelNucl}, {"--batch", 0, nullptr},
     };
 }
@@ -386,12 +390,17 @@ bool load_index_cache(const std::string &name, const Params &p, const Engine &E,
     return ok;
 }
 
-void build_target_index(Engine &E, const Params &p, const SeqSet &T, int kmerThr, const std::string &tName = std::string(),
-                        uint64_t srcDataSize = 0) {
-    std::vector<uint8_t> masked;
-    uint64_t nMasked = 0;
+// masked target residues: from the <targetDB>.spbidx cache when it validates, else tantan on the host (once per run, whatever the
+// number of GPUs)
+bool masked_targets(Engine &E, const Params &p, const SeqSet &T, const std::string &tName, uint64_t srcDataSize,
+                    std::vector<uint8_t> &masked, uint64_t *nMasked) {
     const bool cached = !tName.empty() && load_index_cache(tName, p, E, T, srcDataSize, masked);
-    if (!cached) mask_targets(E, p, T, masked, &nMasked);
+    if (!cached) mask_targets(E, p, T, masked, nMasked);
+    return cached;
+}
+
+void build_index_from_masked(Engine &E, const Params &p, const SeqSet &T, const std::vector<uint8_t> &masked, int kmerThr, bool cached,
+                             uint64_t nMasked, const std::string &tName) {
     const std::string pattern = p.spacedPattern.empty() ? (p.spacedMode ? "11011101" : "111111") : p.spacedPattern;
     // index-side threshold (Prefiltering.cpp:510-513): only for exact matching or when the k-mer threshold is small enough
     check(spb_index_build(E.ctx, masked.data(), T.off.data(), (uint32_t)T.keys.size(), pattern.c_str(), kmerThr), "spb_index_build");
@@ -404,6 +413,14 @@ void build_target_index(Engine &E, const Params &p, const SeqSet &T, int kmerThr
         log_line(p, "Index table: %llu targets, %llu residues (%llu masked), %llu postings, %.1f ms on the device",
                  (unsigned long long)st.n_targets, (unsigned long long)st.n_residues, (unsigned long long)nMasked,
                  (unsigned long long)st.n_postings, st.build_ms);
+}
+
+void build_target_index(Engine &E, const Params &p, const SeqSet &T, int kmerThr, const std::string &tName = std::string(),
+                        uint64_t srcDataSize = 0) {
+    std::vector<uint8_t> masked;
+    uint64_t nMasked = 0;
+    const bool cached = masked_targets(E, p, T, tName, srcDataSize, masked, &nMasked);
+    build_index_from_masked(E, p, T, masked, kmerThr, cached, nMasked, tName);
 }
 
 // Flags of the prefilter / align modules that change the reference's output and that this path does not implement keep the
@@ -440,7 +457,9 @@ void check_search_params(const Params &p) {
     if (p.kmerSize != 0 && p.kmerSize != 6) throw Fail("The k-mer size " + std::to_string(p.kmerSize) + " is not valid. (spb200 implements k = 6)");
     if (p.diagScore != 1) throw Fail("--diag-score 0 is not supported");
     if (p.exactKmer != 0) throw Fail("--exact-kmer-matching 1 is not supported");
-    if (p.split > 1) throw Fail("--split > 1: use the multi-GPU driver (target split over GPUs); a single device holds the whole index");
+    if (p.split > 1) throw Fail("--split > 1 (the reference's lossy target split) is not implemented; spread one DB over several GPUs "
+                                "with --gpus N (k-mer table sharded over the devices, unsplit result)");
+    if (p.gpus < 1 || p.gpus > 8) throw Fail("--gpus must be 1..8");
     if (p.covThr != 0 || p.addSelf != 0) throw Fail("coverage thresholds / --add-self-matches are not supported on this path");
 }
 
@@ -836,14 +855,29 @@ typedef std::function<void(int, uint32_t, const std::string &, const std::string
 template <class Sink>
 void search_dbs(const Params &p, const std::string &qName, const std::string &tName, Sink sink, bool nucl = false,
                 const NuclExtraSink *extra = nullptr) {
-    Engine E;
-    E.open(p);
+    // --gpus G: one context + one host thread per device.  Every device gets the whole target set for alignment (53 MB at
+    // GenBank-phage size) but only its k-mer range of the index table (spb_index_shard); the ranges of the other devices are
+    // read through NVLink peer memory by the lookup kernel.  Query batches are handed out to the devices one by one; rows
+    // are the unsplit rows by construction (Prefiltering.cpp:258-362,559-643 / Alignment.cpp:226-249 are the reference's split).
+    const int G = std::max(1, p.gpus);
+    const int nDev = spb_device_count();
+    if (G > 1 && p.device + G > nDev && !p.oversubscribe)
+        throw Fail("--gpus " + std::to_string(G) + " from device " + std::to_string(p.device) + ": only " + std::to_string(nDev) +
+                   " CUDA device(s) visible (--oversubscribe 1 places several shard contexts on one device)");
+    std::vector<std::unique_ptr<Engine>> eng((size_t)G);
+    for (int g = 0; g < G; g++) {
+        Params pg = p;
+        pg.device = (p.device + g < nDev || nDev == 0) ? p.device + g : p.device + g % std::max(1, nDev - p.device);
+        eng[(size_t)g].reset(new Engine());
+        eng[(size_t)g]->open(pg);
+    }
+    Engine &E0 = *eng[0];
     DBReader qdb, tdb;
     qdb.open(qName);
     tdb.open(tName);
     SeqSet Q, T;
-    load_sequences(qdb, E.seed, Q);
-    load_sequences(tdb, E.seed, T);
+    load_sequences(qdb, E0.seed, Q);
+    load_sequences(tdb, E0.seed, T);
     check_seq_len(p, Q.off, "query");
     check_seq_len(p, T.off, "target");
     NuclSet QN, TN;
@@ -852,11 +886,40 @@ void search_dbs(const Params &p, const std::string &qName, const std::string &tN
         load_nucl(qName + "_nucl_orf", qdb, Q.keys, QN);
         load_nucl(tName + "_nucl_orf", tdb, T.keys, TN);
         fill_nucl_params(p, TN.dbSize, &np);
-        check(spb_nucl_set_targets(E.ctx, TN.nt.data(), TN.off.data(), (uint32_t)T.keys.size(), TN.startCodon.data()), "spb_nucl_set_targets");
     }
     const int kmerThr = kmer_threshold(p.sensitivity, p.kmerScore, 6);
-    if (!p.exhaustive) build_target_index(E, p, T, kmerThr, tName, tdb.dataSize());
-    check(spb_align_set_targets(E.ctx, T.res.data(), T.off.data(), (uint32_t)T.keys.size(), T.keys.data()), "spb_align_set_targets");
+    std::vector<uint8_t> masked;
+    uint64_t nMasked = 0;
+    bool cached = false;
+    if (!p.exhaustive) cached = masked_targets(E0, p, T, tName, tdb.dataSize(), masked, &nMasked);
+    std::vector<std::exception_ptr> errs((size_t)G);
+    auto run_on_all = [&](const std::function<void(int)> &f) {
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; g++)
+            th.emplace_back([&, g]() { try { f(g); } catch (...) { errs[(size_t)g] = std::current_exception(); } });
+        for (std::thread &t : th) t.join();
+        for (std::exception_ptr &e : errs)
+            if (e) { std::exception_ptr x = e; e = nullptr; std::rethrow_exception(x); }
+    };
+    run_on_all([&](int g) {
+        Engine &E = *eng[(size_t)g];
+        if (nucl) check(spb_nucl_set_targets(E.ctx, TN.nt.data(), TN.off.data(), (uint32_t)T.keys.size(), TN.startCodon.data()), "spb_nucl_set_targets");
+        if (!p.exhaustive) {
+            Params pq = p;
+            if (g) pq.verbosity = 0;          // one "Index table" line
+            build_index_from_masked(E, pq, T, masked, kmerThr, cached, nMasked, tName);
+            if (G > 1) check(spb_index_shard(E.ctx, g, G), "spb_index_shard");
+        }
+        check(spb_align_set_targets(E.ctx, T.res.data(), T.off.data(), (uint32_t)T.keys.size(), T.keys.data()), "spb_align_set_targets");
+    });
+    masked.clear();
+    masked.shrink_to_fit();
+    if (G > 1 && !p.exhaustive) {
+        for (int g = 0; g < G; g++)
+            for (int h = 0; h < G; h++)
+                if (h != g) check(spb_index_shard_attach_ctx(eng[(size_t)g]->ctx, h, eng[(size_t)h]->ctx), "spb_index_shard_attach_ctx");
+        log_line(p, "Index table: k-mer ranges sharded over %d GPUs (devices %d..%d), peer loads over NVLink", G, p.device, p.device + G - 1);
+    }
     spb_prefilter_params pp;
     pp.kmer_thr = kmerThr;
     pp.max_seqs = p.maxSeqs;
@@ -866,93 +929,105 @@ void search_dbs(const Params &p, const std::string &qName, const std::string &tN
     pp.id_base = 0;
     pp.emit_trunc_keys = 0;
     spb_align_params ap;
-    fill_align_params(p, E, tdb.aminoAcidDBSize(), &ap);
+    fill_align_params(p, E0, tdb.aminoAcidDBSize(), &ap);
     const size_t nq = Q.keys.size();
-    std::thread formatter;
-    std::exception_ptr fmtError;
-    spb_align_result *prevR = nullptr;
-    spb_nucl_aln *prevNr = nullptr;
-    auto finish_previous = [&]() {
-        if (formatter.joinable()) formatter.join();
-        if (prevNr) spb_free_nucl_result(E.ctx, prevNr);
-        if (prevR) spb_free_align_result(prevR);
-        prevNr = nullptr;
-        prevR = nullptr;
-        if (fmtError) {
-            std::exception_ptr e = fmtError;
-            fmtError = nullptr;
-            std::rethrow_exception(e);
-        }
-    };
-    struct JoinGuard {       // an exception on the GPU path must not leave the formatter running on freed state
-        std::thread &t;
-        ~JoinGuard() { if (t.joinable()) t.join(); }
-    } guard{formatter};
-    for (size_t b0 = 0, b1 = 0; b0 < nq; b0 = b1) {
-        b1 = std::min(nq, b0 + (size_t)p.batch);
-        std::vector<uint64_t> off(b1 - b0 + 1);
-        for (size_t i = b0; i <= b1; i++) off[i - b0] = Q.off[i] - Q.off[b0];
-        check(spb_queries_set(E.ctx, Q.res.data() + Q.off[b0], off.data(), (uint32_t)(b1 - b0)), "spb_queries_set");
-        if (p.exhaustive) {
-            spb_exhaustive_stats es;
-            check(spb_pairs_exhaustive(E.ctx, &ap, &es), "spb_pairs_exhaustive");
-            log_line(p, "Exhaustive search: %llu pairs scored, %llu kept, %.2f GCUPS in the streaming kernel", (unsigned long long)es.n_scored,
-                     (unsigned long long)es.n_pairs, es.kernel_ms > 0 ? (double)es.n_cells / es.kernel_ms / 1e6 : 0.0);
-        } else {
-            check(spb_prefilter_resident(E.ctx, &pp), "spb_prefilter_resident");
-            check(spb_pairs_from_prefilter(E.ctx), "spb_pairs_from_prefilter");
-        }
-        check(spb_align_resident(E.ctx, &ap), "spb_align_resident");
-        spb_nucl_aln *nr = nullptr;
-        if (nucl) {
-            std::vector<uint64_t> noff(b1 - b0 + 1);
-            for (size_t i = b0; i <= b1; i++) noff[i - b0] = QN.off[i] - QN.off[b0];
-            check(spb_nucl_set_queries(E.ctx, QN.nt.data() + QN.off[b0], noff.data(), (uint32_t)(b1 - b0), QN.startCodon.data() + b0),
-                  "spb_nucl_set_queries");
-            uint64_t nRows = 0;
-            double ms = 0;
-            check(spb_nucl_rescore_resident(E.ctx, &np, &nr, &nRows, &ms), "spb_nucl_rescore_resident");
-            log_line(p, "Nucleotide re-alignment: %llu rows re-scored on the device in %.3f ms", (unsigned long long)nRows, ms);
-        }
-        // the rows leave the device on a second stream (spb_align_fetch_begin) and are turned into text by a formatter thread
-        // while this thread already drives the next batch through the GPU; results are freed here, by the thread that owns
-        // the context, once the formatter has finished with them
-        spb_align_result *r = nullptr;
-        check(spb_align_fetch_begin(E.ctx, &r), "spb_align_fetch_begin");
-        finish_previous();
-        prevR = r;
-        prevNr = nr;
-        formatter = std::thread([&, r, nr, b0]() {
-            try {
-                check(spb_align_fetch_wait(r), "spb_align_fetch_wait");
-                if (!nucl) {
-                    format_alignment_rows(p, r, Q, b0, T, [&](int th, size_t i, const std::string &buf) { sink(th, Q.keys[b0 + i], buf); });
-                } else {
-                    std::string err;
-                    format_alignment_rows(p, r, Q, b0, T, [&](int th, size_t i, const std::string &prot) {
-                        std::string nuc, comb;
-                        try {
-                            for (uint64_t k = r->offsets[i]; k < r->offsets[i + 1]; k++) {
-                                const spb_aln &a = r->rows[k];
-                                nucl_row_error(nr[k]);
-                                append_nucl_row(nuc, T.keys[a.target], nr[k], r->cigar_ops + a.cigar_off, a.cigar_len);
-                            }
-                            combine_prot_nucl_entry(prot, nuc, comb);
-                        } catch (const std::exception &e) {
-#pragma omp critical
-                            err = e.what();
-                        }
-                        if (extra) (*extra)(th, Q.keys[b0 + i], prot, nuc);
-                        sink(th, Q.keys[b0 + i], comb);
-                    });
-                    if (!err.empty()) throw Fail(err);
-                }
-            } catch (...) {
-                fmtError = std::current_exception();
+    // frames per GPU pass; with several devices every one of them should see a few batches
+    const size_t batch = G > 1 ? std::min<size_t>((size_t)p.batch, std::max<size_t>(4096, (nq + 2 * (size_t)G - 1) / (2 * (size_t)G))) : (size_t)p.batch;
+    const size_t nBatches = (nq + batch - 1) / batch;
+    std::atomic<size_t> nextBatch(0);
+    Params pf = p;                         // formatter teams share the host threads
+    pf.threads = std::max(1, p.threads / G);
+    run_on_all([&](int g) {
+        Engine &E = *eng[(size_t)g];
+        const int thBase = g * pf.threads;
+        std::thread formatter;
+        std::exception_ptr fmtError;
+        spb_align_result *prevR = nullptr;
+        spb_nucl_aln *prevNr = nullptr;
+        auto finish_previous = [&]() {
+            if (formatter.joinable()) formatter.join();
+            if (prevNr) spb_free_nucl_result(E.ctx, prevNr);
+            if (prevR) spb_free_align_result(prevR);
+            prevNr = nullptr;
+            prevR = nullptr;
+            if (fmtError) {
+                std::exception_ptr e = fmtError;
+                fmtError = nullptr;
+                std::rethrow_exception(e);
             }
-        });
-    }
-    finish_previous();
+        };
+        struct JoinGuard {       // an exception on the GPU path must not leave the formatter running on freed state
+            std::thread &t;
+            ~JoinGuard() { if (t.joinable()) t.join(); }
+        } guard{formatter};
+        for (;;) {
+            const size_t bi = nextBatch.fetch_add(1);
+            if (bi >= nBatches) break;
+            const size_t b0 = bi * batch, b1 = std::min(nq, b0 + batch);
+            std::vector<uint64_t> off(b1 - b0 + 1);
+            for (size_t i = b0; i <= b1; i++) off[i - b0] = Q.off[i] - Q.off[b0];
+            check(spb_queries_set(E.ctx, Q.res.data() + Q.off[b0], off.data(), (uint32_t)(b1 - b0)), "spb_queries_set");
+            if (p.exhaustive) {
+                spb_exhaustive_stats es;
+                check(spb_pairs_exhaustive(E.ctx, &ap, &es), "spb_pairs_exhaustive");
+                log_line(p, "Exhaustive search: %llu pairs scored, %llu kept, %.2f GCUPS in the streaming kernel", (unsigned long long)es.n_scored,
+                         (unsigned long long)es.n_pairs, es.kernel_ms > 0 ? (double)es.n_cells / es.kernel_ms / 1e6 : 0.0);
+            } else {
+                check(spb_prefilter_resident(E.ctx, &pp), "spb_prefilter_resident");
+                check(spb_pairs_from_prefilter(E.ctx), "spb_pairs_from_prefilter");
+            }
+            check(spb_align_resident(E.ctx, &ap), "spb_align_resident");
+            spb_nucl_aln *nr = nullptr;
+            if (nucl) {
+                std::vector<uint64_t> noff(b1 - b0 + 1);
+                for (size_t i = b0; i <= b1; i++) noff[i - b0] = QN.off[i] - QN.off[b0];
+                check(spb_nucl_set_queries(E.ctx, QN.nt.data() + QN.off[b0], noff.data(), (uint32_t)(b1 - b0), QN.startCodon.data() + b0),
+                      "spb_nucl_set_queries");
+                uint64_t nRows = 0;
+                double ms = 0;
+                check(spb_nucl_rescore_resident(E.ctx, &np, &nr, &nRows, &ms), "spb_nucl_rescore_resident");
+                log_line(p, "Nucleotide re-alignment: %llu rows re-scored on the device in %.3f ms", (unsigned long long)nRows, ms);
+            }
+            // the rows leave the device on a second stream (spb_align_fetch_begin) and are turned into text by a formatter thread
+            // while this thread already drives the next batch through the GPU; results are freed here, by the thread that owns
+            // the context, once the formatter has finished with them
+            spb_align_result *r = nullptr;
+            check(spb_align_fetch_begin(E.ctx, &r), "spb_align_fetch_begin");
+            finish_previous();
+            prevR = r;
+            prevNr = nr;
+            formatter = std::thread([&, r, nr, b0]() {
+                try {
+                    check(spb_align_fetch_wait(r), "spb_align_fetch_wait");
+                    if (!nucl) {
+                        format_alignment_rows(pf, r, Q, b0, T, [&](int th, size_t i, const std::string &buf) { sink(thBase + th, Q.keys[b0 + i], buf); });
+                    } else {
+                        std::string err;
+                        format_alignment_rows(pf, r, Q, b0, T, [&](int th, size_t i, const std::string &prot) {
+                            std::string nuc, comb;
+                            try {
+                                for (uint64_t k = r->offsets[i]; k < r->offsets[i + 1]; k++) {
+                                    const spb_aln &a = r->rows[k];
+                                    nucl_row_error(nr[k]);
+                                    append_nucl_row(nuc, T.keys[a.target], nr[k], r->cigar_ops + a.cigar_off, a.cigar_len);
+                                }
+                                combine_prot_nucl_entry(prot, nuc, comb);
+                            } catch (const std::exception &e) {
+#pragma omp critical
+                                err = e.what();
+                            }
+                            if (extra) (*extra)(thBase + th, Q.keys[b0 + i], prot, nuc);
+                            sink(thBase + th, Q.keys[b0 + i], comb);
+                        });
+                        if (!err.empty()) throw Fail(err);
+                    }
+                } catch (...) {
+                    fmtError = std::current_exception();
+                }
+            });
+        }
+        finish_previous();
+    });
 }
 
 // spb200 extractframes <nuclSeqDB> <outDB> [--min-length 9 --threads N]
@@ -1082,7 +1157,7 @@ int run_search(int argc, const char **argv) {
     check_search_params(p);
     check_align_params(p);
     DBWriter out;
-    out.open(p.db[2], DBTYPE_ALIGNMENT_RES, p.threads);
+    out.open(p.db[2], DBTYPE_ALIGNMENT_RES, std::max(p.threads, p.gpus));    // sink thread ids: gpu * (threads / gpus) + team thread
     search_dbs(p, p.db[0], p.db[1], [&](int th, uint32_t key, const std::string &buf) { out.write(th, key, buf.data(), buf.size()); });
     out.close();
     return 0;

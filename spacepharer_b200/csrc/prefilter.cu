@@ -97,11 +97,13 @@ struct PrefArgs {
 };
 
 // table entry of a k-mer: x = 0 none | x, y with bit 63: one or two inline postings | x = len << 32 | offset of a posting list
+template <bool SHARDED = true>
 __device__ __forceinline__ ulonglong2 kmer_entry(const PrefArgs &A, uint32_t kmer, const uint64_t *&postBase, bool streaming) {
     uint32_t o = 0, l = kmer;
-    if (A.nShards > 1) { o = kmer / A.shardR; l = kmer - o * A.shardR; }
-    postBase = A.postS[o];
-    return streaming ? __ldcs(A.directS[o] + l) : __ldg(A.directS[o] + l);
+    if (SHARDED && A.nShards > 1) { o = kmer / A.shardR; l = kmer - o * A.shardR; }
+    const ulonglong2 *d = SHARDED ? A.directS[o] : A.directS[0];
+    postBase = SHARDED ? A.postS[o] : A.postS[0];
+    return streaming ? __ldcs(d + l) : __ldg(d + l);
 }
 // number of postings of an entry and posting z of it
 __device__ __forceinline__ uint32_t entry_count(const ulonglong2 &e) {
@@ -893,6 +895,7 @@ __device__ __forceinline__ uint64_t hit_record(uint64_t pe, uint64_t kw, uint32_
     return ((pe >> 16) << 32) | kw | (uint64_t)((w - (uint32_t)(pe & 0xFFFFull)) & 0xFFFFu);
 }
 
+template <bool SHARDED>
 __global__ void __launch_bounds__(PX_CH, 6) lookup_kernel(PrefArgs A) {
     __shared__ uint32_t s_w[2][2][PX_CH / 32];     // [trip parity][chunk of the pair][warp]
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -930,7 +933,7 @@ __global__ void __launch_bounds__(PX_CH, 6) lookup_kernel(PrefArgs A) {
 #pragma unroll
         for (int u = 0; u < 2; u++) {
             e[u] = make_ulonglong2(0ull, 0ull);
-            if (occ[u]) e[u] = kmer_entry(A, kmer[u], pb[u], true);
+            if (occ[u]) e[u] = kmer_entry<SHARDED>(A, kmer[u], pb[u], true);
         }
         uint32_t inc[2];
 #pragma unroll
@@ -2048,7 +2051,8 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
                 expand_kernel<<<c->n_sm * expandPerSm, PW_WARPS * 32, 0, st>>>(A);
                 SPB_CUDA(cudaGetLastError()); c->n_launches++;
                 SPB_CUDA(cudaEventRecord(ep[1], st));
-                lookup_kernel<<<c->n_sm * lookupPerSm, PX_CH, 0, st>>>(A);   // persistent: lookupPerSm CTAs per SM
+                if (c->n_shards > 1) lookup_kernel<true><<<c->n_sm * lookupPerSm, PX_CH, 0, st>>>(A);   // persistent: lookupPerSm CTAs per SM
+                else lookup_kernel<false><<<c->n_sm * lookupPerSm, PX_CH, 0, st>>>(A);
                 SPB_CUDA(cudaGetLastError()); c->n_launches++;
                 SPB_CUDA(cudaEventRecord(ep[2], st));
                 classify_kernel<<<(A.nList + 255) / 256, 256, 0, st>>>(A);

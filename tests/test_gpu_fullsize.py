@@ -250,6 +250,15 @@ def test_config2_byte_identical_to_the_reference_binary(tmp_path):
     r = subprocess.run([BIN, "search", w + "/queries", w + "/targets", w + "/fused"] + merged + ["--batch", "10000"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert db_digest(w + "/fused") == (want["aln_sha256"], want["aln_rows"])
+    # multi-GPU in the host binary: --gpus 2 = two contexts with one k-mer range of the table each (index split, the other
+    # range read through peer-mapped pointers), query batches handed out to both.  On a one-GPU box the two contexts share
+    # the device (--oversubscribe 1: same code path, same kernels); with two GPUs the ranges sit in different HBMs.
+    import torch
+    extra = [] if torch.cuda.device_count() >= 2 else ["--oversubscribe", "1"]
+    r = subprocess.run([BIN, "search", w + "/queries", w + "/targets", w + "/fused2"] + merged + ["--gpus", "2"] + extra, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "sharded over 2 GPUs" in r.stdout
+    assert db_digest(w + "/fused2") == (want["aln_sha256"], want["aln_rows"])
 
 
 def test_config4_one_million_spacers_byte_identical_to_the_reference_binary(tmp_path):

@@ -27,14 +27,13 @@ if [[ " $* " == *" l2 "* ]]; then   # (r2c: cudaLimitMaxL2FetchGranularity 32/64
   done
 fi
 if [[ " $* " == *" sweep "* ]]; then
-  for v in 1024 2048 8192; do
+  for v in 1024 4096; do
     echo "SPB_HITS_SOLO=$v"; SPB_HITS_SOLO=$v SPB_DEBUG=1 timeout 600 python tools/perf_probe.py 2>&1 | grep "spb_prefilter:" | tail -1 | grep -o "expand.*"
   done
-  for v in 4 5 8; do
-    echo "SPB_LOOKUP_CTAS=$v"; SPB_LOOKUP_CTAS=$v SPB_DEBUG=1 timeout 600 python tools/perf_probe.py 2>&1 | grep "spb_prefilter:" | tail -1 | grep -o "expand.*"
-  done
-  for v in 6 10; do
-    echo "SPB_EXPAND_CTAS=$v"; SPB_EXPAND_CTAS=$v SPB_DEBUG=1 timeout 600 python tools/perf_probe.py 2>&1 | grep "spb_prefilter:" | tail -1 | grep -o "expand.*"
+
+  for v in "4 2" "5 1" "6 1" "3 2"; do
+    set -- $v
+    echo "SPB_SOLO_CTAS=$1 SPB_TEAM_CTAS=$2"; SPB_SOLO_CTAS=$1 SPB_TEAM_CTAS=$2 SPB_DEBUG=1 timeout 600 python tools/perf_probe.py 2>&1 | grep "spb_prefilter:" | tail -1 | grep -o "expand.*"
   done
 fi
 echo done
