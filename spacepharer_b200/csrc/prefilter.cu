@@ -98,12 +98,16 @@ struct PrefArgs {
 
 // table entry of a k-mer: x = 0 none | x, y with bit 63: one or two inline postings | x = len << 32 | offset of a posting list
 template <bool SHARDED = true>
-__device__ __forceinline__ ulonglong2 kmer_entry(const PrefArgs &A, uint32_t kmer, const uint64_t *&postBase, bool streaming) {
+__device__ __forceinline__ ulonglong2 kmer_entry(const PrefArgs &A, uint32_t kmer, bool streaming) {
     uint32_t o = 0, l = kmer;
     if (SHARDED && A.nShards > 1) { o = kmer / A.shardR; l = kmer - o * A.shardR; }
     const ulonglong2 *d = SHARDED ? A.directS[o] : A.directS[0];
-    postBase = SHARDED ? A.postS[o] : A.postS[0];
     return streaming ? __ldcs(d + l) : __ldg(d + l);
+}
+// posting lists of the shard that owns the k-mer (list offsets in the entries are relative to it)
+template <bool SHARDED = true>
+__device__ __forceinline__ const uint64_t *kmer_post_base(const PrefArgs &A, uint32_t kmer) {
+    return (SHARDED && A.nShards > 1) ? A.postS[kmer / A.shardR] : A.postS[0];
 }
 // number of postings of an entry and posting z of it
 __device__ __forceinline__ uint32_t entry_count(const ulonglong2 &e) {
@@ -412,7 +416,8 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
                     ulonglong2 e = make_ulonglong2(0ull, 0ull);
                     const uint64_t *pb = nullptr;
                     if (valid && ((__ldg(A.kbits + (kmer >> 5)) >> (kmer & 31)) & 1u)) {
-                        e = kmer_entry(A, kmer, pb, false);
+                        e = kmer_entry(A, kmer, false);
+                        pb = kmer_post_base(A, kmer);
                         len = entry_count(e);
                     }
                     if (pass == 0) {
@@ -917,7 +922,6 @@ __global__ void __launch_bounds__(PX_CH, 6) lookup_kernel(PrefArgs A) {
         const uint32_t c0 = 2 * pr;
         uint32_t kmer[2], w[2], n[2];
         ulonglong2 e[2];
-        const uint64_t *pb[2] = {nullptr, nullptr};
         bool occ[2];
 #pragma unroll
         for (int u = 0; u < 2; u++) {
@@ -933,7 +937,7 @@ __global__ void __launch_bounds__(PX_CH, 6) lookup_kernel(PrefArgs A) {
 #pragma unroll
         for (int u = 0; u < 2; u++) {
             e[u] = make_ulonglong2(0ull, 0ull);
-            if (occ[u]) e[u] = kmer_entry<SHARDED>(A, kmer[u], pb[u], true);
+            if (occ[u]) e[u] = kmer_entry<SHARDED>(A, kmer[u], true);
         }
         uint32_t inc[2];
 #pragma unroll
@@ -968,7 +972,7 @@ __global__ void __launch_bounds__(PX_CH, 6) lookup_kernel(PrefArgs A) {
                     if (e[u].y >> 63) dst[1] = hit_record(e[u].y, kw, w[u]);
                 } else {
                     // list of three or more postings: four independent loads in flight per trip
-                    const uint64_t *__restrict__ pl = pb[u] + (uint32_t)e[u].x;
+                    const uint64_t *__restrict__ pl = kmer_post_base<SHARDED>(A, kmer[u]) + (uint32_t)e[u].x;
                     for (uint32_t z = 0; z < n[u]; z += 4) {
                         uint64_t pe[4];
 #pragma unroll
@@ -1987,7 +1991,7 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
         if (const char *e = getenv("SPB_LOOKUP_CTAS")) lookupPerSm = std::max(1, std::min(16, atoi(e)));
         if (const char *e = getenv("SPB_EXPAND_CTAS")) expandPerSm = std::max(1, std::min(16, atoi(e)));
         const int soloBlocks = c->n_sm * soloPerSm, teamBlocks = c->n_sm * teamPerSm;
-        A.hitsSolo = 2048;     // r2d sweep: 1024 / 2048 / 4096 / 8192 -> 0.62 / 0.54 / 0.61 / 0.90 ms of bookkeeping
+        A.hitsSolo = 4096;     // r2h sweep (both launches side by side): 1024 / 2048 / 4096 -> 0.63 / 0.47 / 0.43 ms of bookkeeping
         if (const char *e = getenv("SPB_HITS_SOLO")) A.hitsSolo = (uint32_t)std::max(1, atoi(e));
         const uint32_t hitCapSolo = std::max<uint32_t>(A.hitsSolo, PW_SCAP), hitCapTeam = 32768;
         const size_t sliceSolo = 2 * (size_t)hitCapSolo + 2 * PW_FCAP_SOLO, sliceTeam = 2 * (size_t)hitCapTeam + 2 * PW_FCAP_TEAM;
