@@ -226,8 +226,7 @@ __global__ void __launch_bounds__(128) sw_forward_kernel(AlnArgs A) {
 // Rows >= L and columns beyond a target's end score -128 and can never raise the maximum.
 // ---------------------------------------------------------------------------------------------------------
 struct FastArgs {
-    const uint32_t *sortedKey;   // (query length << lenBits) | (tLen + 1) (0: pair not eligible), descending
-    uint32_t lenMask;            // (1 << lenBits) - 1
+    const uint32_t *sortedKey;   // tLen + 1 (0: pair not eligible), descending
     const uint32_t *sortedPair;
     uint32_t NP;
     const uint32_t *pairQ, *pairT;
@@ -269,67 +268,6 @@ __device__ __noinline__ void sw_finish_pair(const FastArgs &A, uint32_t pair, in
     A.accFlag[pair] = (uint8_t)(o.status == 1);
 }
 
-// the two packed DP columns over the targets of one thread, ROWS query rows (rows >= L score -128 and never matter: the
-// warp runs the instantiation with the fewest rows that holds its longest query)
-template <int ROWS>
-__device__ __forceinline__ void sw_fast_columns(const uint4 (*s_prof)[SWF_PROF_ROWS][SWF_THREADS], int tid, const uint32_t *wA, const uint32_t *wB,
-                                                uint32_t shA, uint32_t shB, int lenA, int lenB, uint32_t MGO, uint32_t MGE,
-                                                uint32_t &best, int &colA, int &colB, int &rowA, int &rowB) {
-    uint32_t curA = __ldg(wA), curB = __ldg(wB);
-    uint32_t H[ROWS], E[ROWS];
-#pragma unroll
-    for (int i = 0; i < ROWS; i++) { H[i] = 0; E[i] = 0; }
-    const int n = max(lenA, lenB);
-    for (int j0 = 0; j0 < n; j0 += 4) {
-        const uint32_t nxA = __ldg(wA + (j0 >> 2) + 1), nxB = __ldg(wB + (j0 >> 2) + 1);
-        uint32_t resA = __funnelshift_r(curA, nxA, shA), resB = __funnelshift_r(curB, nxB, shB);
-        curA = nxA;
-        curB = nxB;
-#pragma unroll
-        for (int jj = 0; jj < 4; jj++) {
-            const int j = j0 + jj;
-            uint32_t a = resA & 0xFFu, b = resB & 0xFFu;
-            resA >>= 8;
-            resB >>= 8;
-            if (j >= lenA || a > SPB_X) a = SWF_PAD;
-            if (j >= lenB || b > SPB_X) b = SWF_PAD;
-            const uint4 pa = s_prof[0][a][tid], pb = s_prof[1][b][tid];
-            const uint32_t paw[4] = {pa.x, pa.y, pa.z, pa.w}, pbw[4] = {pb.x, pb.y, pb.z, pb.w};
-            uint32_t Hd = 0, F = 0, colmax = 0;
-#pragma unroll
-            for (int i = 0; i < ROWS; i++) {
-                const int r = i & 3;
-                const uint32_t sel = (uint32_t)r | ((uint32_t)(r | 8) << 4) | ((uint32_t)(4 + r) << 8) | ((uint32_t)((4 + r) | 8) << 12);
-                const uint32_t sc = prmt(paw[i >> 2], pbw[i >> 2], sel);       // {s_A(i), s_B(i)} sign-extended
-                const uint32_t h1 = __viaddmax_s16x2_relu(Hd, sc, E[i]);        // max(Hd + s, E, 0)
-                const uint32_t open = __vadd2(h1, MGO);                         // h1 - go (may be negative)
-                E[i] = __viaddmax_s16x2_relu(E[i], MGE, open);                  // max(E - ge, h1 - go, 0)
-                const uint32_t h = __vmaxs2(h1, F);
-                F = __viaddmax_s16x2_relu(F, MGE, open);
-                Hd = H[i];
-                H[i] = h;
-                colmax = __vmaxs2(colmax, h);
-            }
-            const uint32_t nb = __vmaxs2(best, colmax);
-            if (nb != best) {      // a strictly better column for at least one of the two pairs
-                if ((nb & 0xFFFFu) != (best & 0xFFFFu)) {
-                    const uint32_t m = nb & 0xFFFFu;
-                    colA = j;
-#pragma unroll
-                    for (int i = ROWS - 1; i >= 0; i--) if ((H[i] & 0xFFFFu) == m) rowA = i;
-                }
-                if ((nb >> 16) != (best >> 16)) {
-                    const uint32_t m = nb >> 16;
-                    colB = j;
-#pragma unroll
-                    for (int i = ROWS - 1; i >= 0; i--) if ((H[i] >> 16) == m) rowB = i;
-                }
-                best = nb;
-            }
-        }
-    }
-}
-
 __global__ void __launch_bounds__(SWF_THREADS) sw_fast_kernel(FastArgs A) {
     __shared__ uint4 s_prof[2][SWF_PROF_ROWS][SWF_THREADS];
     const int tid = threadIdx.x;
@@ -337,19 +275,13 @@ __global__ void __launch_bounds__(SWF_THREADS) sw_fast_kernel(FastArgs A) {
     const uint32_t keyA = e0 < A.NP ? A.sortedKey[e0] : 0u;
     const uint32_t keyB = e0 + 1 < A.NP ? A.sortedKey[e0 + 1] : 0u;
     unsigned long long myCells = 0;
-    const bool work = keyA != 0u;      // keys descend: keyA == 0 implies keyB == 0
-    uint32_t pA = 0, pB = 0, qA = 0, qB = 0;
-    int lenA = 0, lenB = 0, LA = 0, LB = 0;
-    const uint32_t *wA = nullptr, *wB = nullptr;
-    uint32_t shA = 0, shB = 0;
-    if (work) {
-        pA = A.sortedPair[e0];
-        pB = keyB ? A.sortedPair[e0 + 1] : pA;
-        qA = A.pairQ[pA]; qB = A.pairQ[pB];
+    if (keyA != 0u) {      // keys descend: keyA == 0 implies keyB == 0
+        const uint32_t pA = A.sortedPair[e0];
+        const uint32_t pB = keyB ? A.sortedPair[e0 + 1] : pA;
+        const uint32_t qA = A.pairQ[pA], qB = A.pairQ[pB];
         const uint32_t tiA = A.pairT[pA], tiB = A.pairT[pB];
-        lenA = (int)((keyA & A.lenMask) - 1u);
-        lenB = keyB ? (int)((keyB & A.lenMask) - 1u) : 0;
-        LA = (int)(A.qoff[qA + 1] - A.qoff[qA]); LB = (int)(A.qoff[qB + 1] - A.qoff[qB]);
+        const int lenA = (int)(keyA - 1u), lenB = keyB ? (int)(keyB - 1u) : 0;
+        const int LA = (int)(A.qoff[qA + 1] - A.qoff[qA]), LB = (int)(A.qoff[qB + 1] - A.qoff[qB]);
 #pragma unroll
         for (int a = 0; a < SWF_PROF_ROWS; a++) {
             s_prof[0][a][tid] = __ldg(A.prof16 + (size_t)qA * SWF_PROF_ROWS + a);
@@ -357,26 +289,65 @@ __global__ void __launch_bounds__(SWF_THREADS) sw_fast_kernel(FastArgs A) {
         }
         // aligned 4-byte windows over the two targets (the residue buffer is padded by 64 bytes)
         const uint8_t *tA = A.tres + A.toff[tiA], *tB = A.tres + A.toff[tiB];
-        wA = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(tA) & ~(uintptr_t)3);
-        wB = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(tB) & ~(uintptr_t)3);
-        shA = (uint32_t)(reinterpret_cast<uintptr_t>(tA) & 3) * 8u;
-        shB = (uint32_t)(reinterpret_cast<uintptr_t>(tB) & 3) * 8u;
-    }
-    // rows the warp needs: its longest query (the pairs are sorted by query length first, so warps are nearly uniform)
-    const int rowsWarp = (int)__reduce_max_sync(0xffffffffu, (unsigned)max(LA, LB));
-    if (work) {
+        const uint32_t *wA = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(tA) & ~(uintptr_t)3);
+        const uint32_t *wB = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(tB) & ~(uintptr_t)3);
+        const uint32_t shA = (uint32_t)(reinterpret_cast<uintptr_t>(tA) & 3) * 8u, shB = (uint32_t)(reinterpret_cast<uintptr_t>(tB) & 3) * 8u;
+        uint32_t curA = __ldg(wA), curB = __ldg(wB);
         const uint32_t MGO = ((uint32_t)(-A.go) & 0xFFFFu) * 0x10001u, MGE = ((uint32_t)(-A.ge) & 0xFFFFu) * 0x10001u;
+        uint32_t H[SWF_ROWS], E[SWF_ROWS];
+#pragma unroll
+        for (int i = 0; i < SWF_ROWS; i++) { H[i] = 0; E[i] = 0; }
         uint32_t best = 0;
         int colA = -1, colB = -1, rowA = 0, rowB = 0;
-#define SWF_CASE(R) sw_fast_columns<R>(s_prof, tid, wA, wB, shA, shB, lenA, lenB, MGO, MGE, best, colA, colB, rowA, rowB)
-        if (rowsWarp <= 9) SWF_CASE(9);
-        else if (rowsWarp == 10) SWF_CASE(10);
-        else if (rowsWarp == 11) SWF_CASE(11);
-        else if (rowsWarp == 12) SWF_CASE(12);
-        else if (rowsWarp == 13) SWF_CASE(13);
-        else if (rowsWarp == 14) SWF_CASE(14);
-        else SWF_CASE(16);
-#undef SWF_CASE
+        const int n = max(lenA, lenB);
+        for (int j0 = 0; j0 < n; j0 += 4) {
+            const uint32_t nxA = __ldg(wA + (j0 >> 2) + 1), nxB = __ldg(wB + (j0 >> 2) + 1);
+            uint32_t resA = __funnelshift_r(curA, nxA, shA), resB = __funnelshift_r(curB, nxB, shB);
+            curA = nxA;
+            curB = nxB;
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const int j = j0 + jj;
+                uint32_t a = resA & 0xFFu, b = resB & 0xFFu;
+                resA >>= 8;
+                resB >>= 8;
+                if (j >= lenA || a > SPB_X) a = SWF_PAD;
+                if (j >= lenB || b > SPB_X) b = SWF_PAD;
+                const uint4 pa = s_prof[0][a][tid], pb = s_prof[1][b][tid];
+                const uint32_t paw[4] = {pa.x, pa.y, pa.z, pa.w}, pbw[4] = {pb.x, pb.y, pb.z, pb.w};
+                uint32_t Hd = 0, F = 0, colmax = 0;
+#pragma unroll
+                for (int i = 0; i < SWF_ROWS; i++) {
+                    const int r = i & 3;
+                    const uint32_t sel = (uint32_t)r | ((uint32_t)(r | 8) << 4) | ((uint32_t)(4 + r) << 8) | ((uint32_t)((4 + r) | 8) << 12);
+                    const uint32_t sc = prmt(paw[i >> 2], pbw[i >> 2], sel);       // {s_A(i), s_B(i)} sign-extended
+                    const uint32_t h1 = __viaddmax_s16x2_relu(Hd, sc, E[i]);        // max(Hd + s, E, 0)
+                    const uint32_t open = __vadd2(h1, MGO);                         // h1 - go (may be negative)
+                    E[i] = __viaddmax_s16x2_relu(E[i], MGE, open);                  // max(E - ge, h1 - go, 0)
+                    const uint32_t h = __vmaxs2(h1, F);
+                    F = __viaddmax_s16x2_relu(F, MGE, open);
+                    Hd = H[i];
+                    H[i] = h;
+                    colmax = __vmaxs2(colmax, h);
+                }
+                const uint32_t nb = __vmaxs2(best, colmax);
+                if (nb != best) {      // a strictly better column for at least one of the two pairs
+                    if ((nb & 0xFFFFu) != (best & 0xFFFFu)) {
+                        const uint32_t m = nb & 0xFFFFu;
+                        colA = j;
+#pragma unroll
+                        for (int i = SWF_ROWS - 1; i >= 0; i--) if ((H[i] & 0xFFFFu) == m) rowA = i;
+                    }
+                    if ((nb >> 16) != (best >> 16)) {
+                        const uint32_t m = nb >> 16;
+                        colB = j;
+#pragma unroll
+                        for (int i = SWF_ROWS - 1; i >= 0; i--) if ((H[i] >> 16) == m) rowB = i;
+                    }
+                    best = nb;
+                }
+            }
+        }
         sw_finish_pair(A, pA, LA, lenA, A.qbias[qA], (int)(best & 0xFFFFu), colA, rowA);
         myCells = (unsigned long long)LA * (unsigned long long)lenA;
         if (keyB) {
@@ -391,20 +362,16 @@ __global__ void __launch_bounds__(SWF_THREADS) sw_fast_kernel(FastArgs A) {
 // pair -> query map and the sort key of the register kernel (tLen + 1 for eligible queries, else 0)
 __global__ void pair_key_kernel(const uint64_t *__restrict__ pairOff, const uint32_t *__restrict__ pairT,
                                 const uint64_t *__restrict__ toff, const uint8_t *__restrict__ qfast, uint32_t Q,
-                                const uint64_t *__restrict__ qoff, int lenBits,
                                 uint32_t *__restrict__ pairQ, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
     const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= Q) return;
     const uint64_t a = pairOff[q], b = pairOff[q + 1];
     const bool f = qfast[q] != 0;
-    // query length class in the top bits (fast queries have at most SWF_ROWS = 16 residues): warps of the register kernel
-    // then hold queries of one length and run the instantiation with exactly that many rows
-    const uint32_t lq = lenBits < 27 ? (uint32_t)min((unsigned long long)(qoff[q + 1] - qoff[q]), 31ull) << lenBits : 0u;
     for (uint64_t k = a + (threadIdx.x & 31); k < b; k += 32) {
         const uint32_t t = pairT[k];
         const uint64_t tl = toff[t + 1] - toff[t];
         pairQ[k] = q;
-        keys[k] = (f && tl < 0x7FFFFFFFull) ? (lq | ((uint32_t)tl + 1u)) : 0u;
+        keys[k] = (f && tl < 0x7FFFFFFFull) ? (uint32_t)tl + 1u : 0u;
         vals[k] = (uint32_t)k;
     }
 }
@@ -1044,15 +1011,13 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
                                            matMin, c->s_a.as<signed char>(), c->s_b.as<int>(), c->s_l.as<signed char>(), c->s_m.as<uint8_t>(),
                                            fastMaxL);
     SPB_CUDA(cudaGetLastError()); c->n_launches++;
-    int keyBits = 1;
-    while (keyBits < 32 && ((uint64_t)1 << keyBits) <= c->a_maxlen + 1) keyBits++;
-    const int lenBits = keyBits;                       // target length + 1 in the low bits, query length above (if it fits)
-    if (lenBits < 27) keyBits = lenBits + 5;
     pair_key_kernel<<<(Q + 3) / 4, 128, 0, st>>>(c->d_pairoff.as<uint64_t>(), c->d_pairT.as<uint32_t>(), c->d_aoff.as<uint64_t>(),
-                                                 c->s_m.as<uint8_t>(), Q, c->d_qoff64.as<uint64_t>(), lenBits, c->d_pairQ.as<uint32_t>(),
-                                                 c->s_n.as<uint32_t>(), c->s_p.as<uint32_t>());
+                                                 c->s_m.as<uint8_t>(), Q, c->d_pairQ.as<uint32_t>(), c->s_n.as<uint32_t>(),
+                                                 c->s_p.as<uint32_t>());
     SPB_CUDA(cudaGetLastError()); c->n_launches++;
     size_t tmpBytes = 0;
+    int keyBits = 1;
+    while (keyBits < 32 && ((uint64_t)1 << keyBits) <= c->a_maxlen + 1) keyBits++;
     SPB_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmpBytes, c->s_n.as<uint32_t>(), c->s_o.as<uint32_t>(), c->s_p.as<uint32_t>(),
                                                        c->s_q.as<uint32_t>(), (int)NP, 0, keyBits, st));
     if (c->s_cub.ensure(tmpBytes)) return 1;
@@ -1073,7 +1038,6 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
     F.sortedKey = c->s_o.as<uint32_t>();
     F.sortedPair = c->s_q.as<uint32_t>();
     F.NP = (uint32_t)NP;
-    F.lenMask = lenBits < 32 ? ((1u << lenBits) - 1u) : 0xFFFFFFFFu;
     F.pairQ = c->d_pairQ.as<uint32_t>();
     F.pairT = c->d_pairT.as<uint32_t>();
     F.qoff = c->d_qoff64.as<uint64_t>();
