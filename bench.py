@@ -373,8 +373,9 @@ def run_ours(args):
     # K steps shared by n_lanes contexts (one host thread each, every lane holds the batch resident); one CUDA event per lane
     # stream before the first and after the last step, device time = latest end - earliest start; the per-step L2 flush runs
     # on the lane's stream INSIDE the timed span here
-    if n_lanes > 1:
-        lanes = eng.lanes()
+    def lanes_value_leg(engine):
+        """K steps shared by the lanes of `engine`, batches resident -> (device ms, wall s, own launches, queries searched)"""
+        lanes = engine.lanes()
         dev = torch.device("cuda", local)
         ext = [torch.cuda.ExternalStream(ln.stream_ptr(), device=dev) for ln in lanes]
         fl = [flush] + [torch.empty(256 << 20, dtype=torch.uint8, device="cuda") for _ in lanes[1:]]
@@ -383,22 +384,23 @@ def run_ours(args):
             with torch.cuda.stream(ext[l]):
                 fl[l].zero_()
 
-        eng.run_stream(batches, db_res, steps=max(args.warmup, 2) * n_lanes, resident=True, before_step=before_step)
-        launches0 = eng.launches()
+        engine.run_stream(batches, db_res, steps=max(args.warmup, 2) * len(lanes), resident=True, before_step=before_step)
+        l0 = engine.launches()
         e0 = [torch.cuda.Event(enable_timing=True) for _ in lanes]
         e1 = [torch.cuda.Event(enable_timing=True) for _ in lanes]
         barrier()
-        t_wall0 = time.perf_counter()
+        tw0 = time.perf_counter()
         for l in range(len(lanes)):
             e0[l].record(ext[l])
-        vsts = eng.run_stream(batches, db_res, steps=args.steps, resident=True, before_step=before_step)
-        value_queries = sum(batch_q[st["lane"] % len(batches)] for st in vsts)
+        vsts = engine.run_stream(batches, db_res, steps=args.steps, resident=True, before_step=before_step)
+        nq_ = sum(batch_q[st["lane"] % len(batches)] for st in vsts)
         for l in range(len(lanes)):
             e1[l].record(ext[l])
         barrier()
-        wall_value = time.perf_counter() - t_wall0
-        dev_ms = max(a.elapsed_time(b) for a in e0 for b in e1)
-        launches = eng.launches() - launches0
+        return max(a.elapsed_time(b) for a in e0 for b in e1), time.perf_counter() - tw0, engine.launches() - l0, nq_
+
+    if n_lanes > 1:
+        dev_ms, wall_value, launches, value_queries = lanes_value_leg(eng)
         eng.set_queries(q_np, o_np)
 
     # ---- end-to-end leg through the public API with HOST buffers ----
@@ -458,6 +460,15 @@ def run_ours(args):
         barrier()
         exh = {"kernel_ms": float(np.mean([r["kernel_ms"] for r in runs])), "cells": float(runs[-1]["n_cells"]),
                "scored": float(runs[-1]["n_scored"]), "kept": float(runs[-1]["n_kept"]), "queries": nq}
+
+    # ---- the same value leg with full replicas (query split) beside the sharded index, N > 1 only ----
+    replicas = None
+    if world > 1 and args.split_mode != "query" and n_lanes > 1:
+        eng_q = multigpu.ShardedSearcher(device=local, rank=rank, world=world, split_mode="query", lanes=n_lanes)
+        eng_q.load_targets(masked, tres, toff)
+        r_ms, _, _, r_q = lanes_value_leg(eng_q)
+        replicas = (r_ms, r_q)
+        eng_q.close()
 
     # ---- strong-scaling leg (BASELINE config 4): ONE job of 1 M spacers split over the GPUs ----
     # the whole job goes through the public API with host buffers (H2D of the frames, D2H of the sorted rows + CIGARs inside
@@ -543,8 +554,8 @@ def run_ours(args):
                 parity["parity_ok"] = None
                 parity["error"] = str(e)
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3, exh["kernel_ms"] if exh else 0.0, single_ms, strong["wall_s"] * 1e3 if strong else 0.0],
-                     dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s * 1e3, exh["kernel_ms"] if exh else 0.0, single_ms, strong["wall_s"] * 1e3 if strong else 0.0,
+                      replicas[0] if replicas else 0.0], dtype=torch.float64, device="cuda")
     ssum = torch.tensor([strong["rows"], strong["kmers"]] + [strong["stage"][k] for k in ("expand_ms", "lookup_ms", "bookkeep_ms", "kernel_ms", "align_ms")]
                         if strong else [0.0] * 7, dtype=torch.float64, device="cuda")
     tsum = torch.tensor([exh["cells"], exh["scored"], exh["kept"], exh["queries"]] if exh else [0.0] * 4, dtype=torch.float64, device="cuda")
@@ -617,6 +628,10 @@ def run_ours(args):
                             "how": "similar k-mers x 0.336 (share with an occupied table entry, measured on this index) x (N-1)/N remote x one "
                                    "32-byte sector per 16-byte entry; posting lists of >= 3 targets (5 % of the entries) add their own sectors"}
                            if (world > 1 and args.split_mode == "index") else None)}
+        if replicas:
+            line["query_split"] = {"value": replicas[1] / (float(t[5]) * 1e-3), "unit": UNIT, "ms_per_step": float(t[5]) / args.steps,
+                                   "note": "same value leg with the whole index replicated on every GPU and the queries partitioned (no "
+                                           "NVLink traffic on the data path): what sharding the k-mer table costs at a DB size that fits one GPU"}
         if parity:
             line["parity"] = parity
         if exh:

@@ -292,7 +292,10 @@ __global__ void __launch_bounds__(SWF_THREADS) sw_fast_kernel(FastArgs A) {
         const uint32_t *wA = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(tA) & ~(uintptr_t)3);
         const uint32_t *wB = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(tB) & ~(uintptr_t)3);
         const uint32_t shA = (uint32_t)(reinterpret_cast<uintptr_t>(tA) & 3) * 8u, shB = (uint32_t)(reinterpret_cast<uintptr_t>(tB) & 3) * 8u;
+        // target words are fetched two trips (8 columns) ahead: the pairs of a warp stream 64 different targets, mostly from DRAM
+        const int lastA = (int)((shA >> 3) + (uint32_t)lenA + 3u) / 4 + 1, lastB = (int)((shB >> 3) + (uint32_t)lenB + 3u) / 4 + 1;
         uint32_t curA = __ldg(wA), curB = __ldg(wB);
+        uint32_t nxA = __ldg(wA + 1), nxB = __ldg(wB + 1);
         const uint32_t MGO = ((uint32_t)(-A.go) & 0xFFFFu) * 0x10001u, MGE = ((uint32_t)(-A.ge) & 0xFFFFu) * 0x10001u;
         uint32_t H[SWF_ROWS], E[SWF_ROWS];
 #pragma unroll
@@ -301,10 +304,13 @@ __global__ void __launch_bounds__(SWF_THREADS) sw_fast_kernel(FastArgs A) {
         int colA = -1, colB = -1, rowA = 0, rowB = 0;
         const int n = max(lenA, lenB);
         for (int j0 = 0; j0 < n; j0 += 4) {
-            const uint32_t nxA = __ldg(wA + (j0 >> 2) + 1), nxB = __ldg(wB + (j0 >> 2) + 1);
+            // (the shorter target of the pair stops fetching at its own end: never more than 8 bytes past a target)
+            const uint32_t n2A = __ldg(wA + min((j0 >> 2) + 2, lastA)), n2B = __ldg(wB + min((j0 >> 2) + 2, lastB));
             uint32_t resA = __funnelshift_r(curA, nxA, shA), resB = __funnelshift_r(curB, nxB, shB);
             curA = nxA;
             curB = nxB;
+            nxA = n2A;
+            nxB = n2B;
 #pragma unroll
             for (int jj = 0; jj < 4; jj++) {
                 const int j = j0 + jj;

@@ -19,6 +19,10 @@ if [[ " $* " == *" ncu "* ]]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'expand_kernel|lookup_kernel|bookkeep_kernel' -s 4 -c 4 \
       -o $OUT/prof_$TAG -f python tools/perf_probe.py > $OUT/prof_$TAG.log 2>&1; echo "ncu rc=$?"
 fi
+if [[ " $* " == *" ncu2 "* ]]; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'bookkeep_kernel|sort_rows|sw_traceback|sw_reverse|align_profile|sw_fast' -s 8 -c 8 \
+      -o $OUT/prof2_$TAG -f python tools/perf_probe.py > $OUT/prof2_$TAG.log 2>&1; echo "ncu2 rc=$?"
+fi
 if [[ " $* " == *" l2 "* ]]; then   # (r2c: cudaLimitMaxL2FetchGranularity 32/64/128 leaves the DRAM bytes unchanged)
   for g in 32 64 128; do
     SPB_L2_FETCH=$g timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
