@@ -673,12 +673,27 @@ __global__ void count_widen_kernel(const uint32_t *__restrict__ cnt, uint32_t Q,
     if (i == Q) out[i] = 0;
 }
 
+// sort key of a row in the order of Matcher::compareHits (M/alignment/Matcher.h:156-167): E-value asc (double), bit score desc,
+// target length asc, target key asc
+struct RowKey { double eval; int bits; uint32_t tlen, tkey, pad; };
+
 __global__ void pack_rows_kernel(const PairOut *__restrict__ out, const uint32_t *__restrict__ acc, uint32_t nAcc,
-                                 const uint32_t *__restrict__ pairQ, const uint32_t *__restrict__ pairT, spb_aln *__restrict__ rows) {
+                                 const uint32_t *__restrict__ pairQ, const uint32_t *__restrict__ pairT, spb_aln *__restrict__ rows,
+                                 const uint64_t *__restrict__ toff, const uint32_t *__restrict__ tkeys, RowKey *__restrict__ keys) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nAcc) return;
     const uint32_t pair = acc[k];
     const PairOut o = out[pair];
+    {
+        const uint32_t t = pairT[pair];
+        RowKey rk;
+        rk.eval = o.eval;
+        rk.bits = o.bits;
+        rk.tlen = (uint32_t)min((unsigned long long)(toff[t + 1] - toff[t]), 0xFFFFFFFFull);
+        rk.tkey = tkeys[t];
+        rk.pad = 0;
+        keys[k] = rk;
+    }
     spb_aln r;
     r.query = pairQ[pair];
     r.target = pairT[pair];
@@ -711,13 +726,39 @@ __device__ __forceinline__ bool row_before(double ea, int ba, uint64_t la, uint3
     return ka < kb;
 }
 
+// Rank sort, one THREAD per row: the rank of a row is the number of rows of its query that sort before it (rows with equal
+// keys -- the same target listed twice for a query -- keep their input order).  A query has 3.7 rows on average, so a thread
+// reads a few 24-byte keys of neighbouring threads (L1) and copies its 64-byte row to its place; no per-query warp, no idle
+// lanes for the queries without rows.  (The warp-per-query kernel below is kept for lists beyond RR_MAX rows.)
+#define RR_MAX 1024
+__global__ void __launch_bounds__(256) rank_rows_kernel(const spb_aln *__restrict__ in, const RowKey *__restrict__ keys, uint32_t nAcc,
+                                                        const uint64_t *__restrict__ rowOff, spb_aln *__restrict__ out) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nAcc) return;
+    const spb_aln r = in[k];
+    const uint64_t o = rowOff[r.query];
+    const uint32_t n = (uint32_t)(rowOff[r.query + 1] - o);
+    if (n > RR_MAX) return;                 // sort_rows_kernel takes the long lists
+    const RowKey me = keys[k];
+    const uint32_t i = (uint32_t)(k - o);
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < n; j++) {
+        const RowKey x = keys[o + j];
+        const bool before = row_before(x.eval, x.bits, x.tlen, x.tkey, me.eval, me.bits, me.tlen, me.tkey);
+        const bool equal = !before && !row_before(me.eval, me.bits, me.tlen, me.tkey, x.eval, x.bits, x.tlen, x.tkey);
+        rank += (before || (equal && j < i)) ? 1u : 0u;
+    }
+    out[o + rank] = r;
+}
+
 // One warp per query, rank sort from the packed rows into the output array.  The four sort fields of a query's rows are
 // staged in shared memory once (up to SR_CAP rows, i.e. any list --max-seqs 300 can produce); longer lists read them
 // from global memory.
 #define SR_CAP 320
 #define SR_WARPS 4
 __global__ void __launch_bounds__(SR_WARPS * 32) sort_rows_kernel(const spb_aln *__restrict__ in, const uint64_t *__restrict__ rowOff, uint32_t Q,
-                                 const uint64_t *__restrict__ toff, const uint32_t *__restrict__ tkeys, spb_aln *__restrict__ out) {
+                                 const uint64_t *__restrict__ toff, const uint32_t *__restrict__ tkeys, spb_aln *__restrict__ out,
+                                 uint32_t minRows) {
     __shared__ double s_e[SR_WARPS][SR_CAP];
     __shared__ int s_b[SR_WARPS][SR_CAP];
     __shared__ uint32_t s_l[SR_WARPS][SR_CAP], s_k[SR_WARPS][SR_CAP];
@@ -726,7 +767,7 @@ __global__ void __launch_bounds__(SR_WARPS * 32) sort_rows_kernel(const spb_aln 
     if (q >= Q) return;
     const uint64_t o = rowOff[q];
     const uint32_t n = (uint32_t)(rowOff[q + 1] - o);
-    if (n == 0) return;
+    if (n == 0 || n < minRows) return;
     if (n == 1) {
         if (lane == 0) out[o] = in[o];
         return;
@@ -1193,12 +1234,18 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
         if (c->s_cub.ensure(tmpBytes)) return 1;
         SPB_CUDA(cub::DeviceScan::ExclusiveSum(c->s_cub.p, tmpBytes, cnt64, rowOff, (int)(Q + 1), st));
         if (nAcc) {
+            if (c->s_h.ensure((size_t)nAcc * sizeof(RowKey) + 64)) return 1;     // (the H/E scratch of the reverse pass is dead by now)
             pack_rows_kernel<<<(nAcc + 255) / 256, 256, 0, st>>>(c->d_pairout.as<PairOut>(), c->d_acc.as<uint32_t>(), nAcc,
-                                                                 c->d_pairQ.as<uint32_t>(), c->d_pairT.as<uint32_t>(), c->s_g.as<spb_aln>());
+                                                                 c->d_pairQ.as<uint32_t>(), c->d_pairT.as<uint32_t>(), c->s_g.as<spb_aln>(),
+                                                                 c->d_aoff.as<uint64_t>(), c->d_akeys.as<uint32_t>(), c->s_h.as<RowKey>());
             SPB_CUDA(cudaGetLastError()); c->n_launches++;
-            sort_rows_kernel<<<(Q + SR_WARPS - 1) / SR_WARPS, SR_WARPS * 32, 0, st>>>(c->s_g.as<spb_aln>(), rowOff, Q, c->d_aoff.as<uint64_t>(),
-                                                                                     c->d_akeys.as<uint32_t>(), c->d_rows.as<spb_aln>());
+            rank_rows_kernel<<<(nAcc + 255) / 256, 256, 0, st>>>(c->s_g.as<spb_aln>(), c->s_h.as<RowKey>(), nAcc, rowOff, c->d_rows.as<spb_aln>());
             SPB_CUDA(cudaGetLastError()); c->n_launches++;
+            if (c->pairs_max_per_query > RR_MAX) {      // lists longer than the per-thread rank loop takes: one warp per query
+                sort_rows_kernel<<<(Q + SR_WARPS - 1) / SR_WARPS, SR_WARPS * 32, 0, st>>>(c->s_g.as<spb_aln>(), rowOff, Q, c->d_aoff.as<uint64_t>(),
+                                                                                         c->d_akeys.as<uint32_t>(), c->d_rows.as<spb_aln>(), RR_MAX + 1);
+                SPB_CUDA(cudaGetLastError()); c->n_launches++;
+            }
         }
     }
     SPB_CUDA(cudaEventRecord(c->ev3, st));
@@ -1222,6 +1269,7 @@ extern "C" int spb_pairs_set(spb_ctx *c, const uint64_t *pair_offsets, const uin
     SPB_CHECK(NP == 0 || pair_targets, "spb_pairs_set: NULL targets");
     // work order: per query, targets by length descending so that the lanes of a warp finish together
     std::vector<uint32_t> pairT(NP);
+    uint64_t maxPer = 0;
     for (uint32_t qi = 0; qi < Q; qi++) {
         const uint64_t a = pair_offsets[qi], b = pair_offsets[qi + 1];
         SPB_CHECK(b >= a && b <= NP, "spb_pairs_set: offsets not monotone at %u", qi);
@@ -1229,6 +1277,7 @@ extern "C" int spb_pairs_set(spb_ctx *c, const uint64_t *pair_offsets, const uin
             SPB_CHECK(pair_targets[k] < c->aT, "spb_align: target id %u of query %u out of range (%u targets)", pair_targets[k], qi, c->aT);
             pairT[k] = pair_targets[k];
         }
+        maxPer = std::max<uint64_t>(maxPer, b - a);
         if (b - a > 1)
             std::stable_sort(pairT.begin() + a, pairT.begin() + b, [&](uint32_t x, uint32_t y) {
                 return (c->h_aoff[x + 1] - c->h_aoff[x]) > (c->h_aoff[y + 1] - c->h_aoff[y]);
@@ -1239,6 +1288,7 @@ extern "C" int spb_pairs_set(spb_ctx *c, const uint64_t *pair_offsets, const uin
     if (NP) SPB_CUDA(cudaMemcpyAsync(c->d_pairT.p, pairT.data(), NP * 4, cudaMemcpyHostToDevice, c->stream));
     SPB_CUDA(cudaStreamSynchronize(c->stream));
     c->n_pairs = NP;
+    c->pairs_max_per_query = maxPer;
     c->have_pairs = true;
     c->have_aln = false;
     return 0;
@@ -1259,6 +1309,7 @@ extern "C" int spb_pairs_from_prefilter(spb_ctx *c) {
         SPB_CUDA(cudaGetLastError()); c->n_launches++;
     }
     c->n_pairs = NP;
+    c->pairs_max_per_query = c->pref_max_seqs ? c->pref_max_seqs : NP;    // a hit list holds at most max-seqs targets
     c->have_pairs = true;
     c->have_aln = false;
     return 0;
@@ -1588,6 +1639,7 @@ extern "C" int spb_pairs_exhaustive(spb_ctx *c, const spb_align_params *p, spb_e
     es.n_unfiltered = (uint64_t)nSlow * T;
     es.n_pairs = NP;
     c->n_pairs = NP;
+    c->pairs_max_per_query = NP;      // unknown per query: any
     c->have_pairs = true;
     if (stats) *stats = es;
     return 0;

@@ -164,6 +164,8 @@ struct spb_ctx {
     // ---- resident alignment input / result ----
     bool have_pairs = false, have_aln = false;
     uint64_t n_pairs = 0;
+    uint64_t pairs_max_per_query = 0;   // upper bound of the pairs of one query (row-order kernels)
+    uint32_t pref_max_seqs = 0;         // max-seqs of the resident prefilter result
     spb::DevBuf d_pairoff;        // u64[Q+1]
     spb::DevBuf d_pairT;          // u32[n_pairs] (work order)
     spb::DevBuf d_pairQ;          // u32[n_pairs]

@@ -777,7 +777,7 @@ __device__ __forceinline__ uint32_t window_kmers(const uint32_t *__restrict__ ro
     return done;
 }
 
-__global__ void __launch_bounds__(PW_WARPS * 32, 8) expand_kernel(PrefArgs A) {
+__global__ void __launch_bounds__(PW_WARPS * 32, 10) expand_kernel(PrefArgs A) {
     __shared__ ExpSmem s_e[PW_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     ExpSmem &S = s_e[wid];
@@ -1987,7 +1987,7 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
             cudaFuncSetAttribute(bookkeep_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
         int teamPerSm = 4;
         if (const char *e = getenv("SPB_TEAM_CTAS")) teamPerSm = std::max(1, std::min(4, atoi(e)));
-        int lookupPerSm = 6, expandPerSm = 8;
+        int lookupPerSm = 6, expandPerSm = 10;    // r2d sweep: 6 / 8 / 10 expand CTAs per SM -> 0.319 / 0.290 / 0.274 ms
         if (const char *e = getenv("SPB_LOOKUP_CTAS")) lookupPerSm = std::max(1, std::min(16, atoi(e)));
         if (const char *e = getenv("SPB_EXPAND_CTAS")) expandPerSm = std::max(1, std::min(16, atoi(e)));
         const int soloBlocks = c->n_sm * soloPerSm, teamBlocks = c->n_sm * teamPerSm;
@@ -2246,6 +2246,7 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
     float totalMs = 0;
     SPB_CUDA(cudaEventElapsedTime(&totalMs, c->ev2, c->ev3));
     c->n_hits = nHits;
+    c->pref_max_seqs = (uint32_t)A.maxHits;
     if (getenv("SPB_DEBUG")) {
         unsigned int tcs[8];
         cudaMemcpy(tcs, reinterpret_cast<unsigned int *>(c->s_f.as<unsigned long long>() + 16), 32, cudaMemcpyDeviceToHost);
