@@ -1035,7 +1035,7 @@ __device__ __noinline__ void warp_bitonic_u64(uint64_t *a, int n_pow2) {
         __syncwarp();
         uint64_t v = (lane < n_pow2) ? a[lane] : ~0ull;
 #pragma unroll 1
-        for (int k = 2; k <= 32; k <<= 1) {
+        for (int k = 2; k <= n_pow2; k <<= 1) {      // lanes >= n_pow2 hold the maximum and sort among themselves: harmless
 #pragma unroll 1
             for (int j = k >> 1; j > 0; j >>= 1) {
                 const uint64_t o = __shfl_xor_sync(0xffffffffu, v, j);
@@ -1379,8 +1379,8 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                     for (int i = lane; i < nS; i += 32) W.surv[i] = __ldcg(bucketed + lo + i);
                 }
                 // ---- sort by (target, stream order) ----
-                {
-                    const int np2 = next_pow2(max(nS, 2));
+                if (nS > 1) {
+                    const int np2 = next_pow2(nS);
                     for (int i = nS + lane; i < np2; i += 32) W.surv[i] = ~0ull;
                     warp_bitonic_u64(W.surv, np2);
                 }
@@ -1483,7 +1483,8 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
                     if (wantT && k < (int)nc) f = (f & ~0xFFFFull) | (uint64_t)k;
                     W.surv[k] = f;
                 }
-                warp_bitonic_u64(W.surv, np2);
+                if (nc > 1) warp_bitonic_u64(W.surv, np2);
+                else __syncwarp();
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(A.cursor, (unsigned long long)nc);
                 base = __shfl_sync(0xffffffffu, base, 0);

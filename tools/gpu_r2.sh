@@ -19,6 +19,14 @@ if [[ " $* " == *" ncu "* ]]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'expand_kernel|lookup_kernel|bookkeep_kernel' -s 4 -c 4 \
       -o $OUT/prof_$TAG -f python tools/perf_probe.py > $OUT/prof_$TAG.log 2>&1; echo "ncu rc=$?"
 fi
+if [[ " $* " == *" lanesweep "* ]]; then
+  B="python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-parity --strong-spacers 0 --exhaustive-spacers 0"
+  for cfg in "SPB_LOOKUP_CTAS=6" "SPB_LOOKUP_CTAS=4" "SPB_LOOKUP_CTAS=3" "SPB_LOOKUP_CTAS=4 SPB_SOLO_CTAS=6 SPB_TEAM_CTAS=3" "SPB_EXPAND_CTAS=6 SPB_LOOKUP_CTAS=4"; do
+    for lanes in 3 4; do
+      echo "$cfg lanes=$lanes: $(env $cfg timeout 300 $B --lanes $lanes 2>/dev/null | python -c 'import json,sys; d=json.loads(sys.stdin.read()); print("value %.2fM e2e %.2fM ms %.3f" % (d["value"]/1e6, d["e2e"]["value"]/1e6, d["ms_per_step"]))')"
+    done
+  done
+fi
 if [[ " $* " == *" ncu2 "* ]]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'bookkeep_kernel|sort_rows|sw_traceback|sw_reverse|align_profile|sw_fast' -s 8 -c 8 \
       -o $OUT/prof2_$TAG -f python tools/perf_probe.py > $OUT/prof2_$TAG.log 2>&1; echo "ncu2 rc=$?"
