@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--split-mode", default="index", choices=["index", "target", "query"],
                     help="N > 1: index = k-mer table sharded over the GPUs, gathered through NVLink peer memory, queries partitioned "
                          "(default); target = MMseqs2-style target split with hit-list exchange + merge; query = full index per GPU")
+    ap.add_argument("--shard-group", type=int, default=0,
+                    help="index split: GPUs sharing one copy of the k-mer table (0 = all N); N must be a multiple of it")
     ap.add_argument("--strong-spacers", type=int, default=1000000,
                     help="spacers of the strong-scaling leg (BASELINE config 4: the whole job split over the GPUs); 0 = skip")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity_ok check (rows of the config-2 batch vs the reference digest)")
@@ -304,7 +306,8 @@ def run_ours(args):
     t0 = time.perf_counter()
     # one busy host thread per lane and rank: never more lanes than host cores per rank
     n_lanes = 1 if (world > 1 and args.split_mode == "target") else max(1, min(args.lanes, (os.cpu_count() or 1) // max(world, 1)))
-    eng = multigpu.ShardedSearcher(device=local, rank=rank, world=world, split_mode=args.split_mode, lanes=n_lanes)
+    eng = multigpu.ShardedSearcher(device=local, rank=rank, world=world, split_mode=args.split_mode, lanes=n_lanes,
+                                   shard_group=args.shard_group)
     masked, n_masked = (tres, 0) if args.no_mask else api.tantan_mask(eng.searcher.seed, tres, toff)
     mask_s = time.perf_counter() - t0
     t0 = time.perf_counter()
@@ -578,6 +581,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args, Q, T, db_res, args.spacers * (world if weak else 1)), "queries_per_step": q_total,
                        "split_mode": args.split_mode if world > 1 else "none",
+                       "shard_group": (eng.shard_group if (world > 1 and args.split_mode == "index") else None),
                        "lanes": n_lanes,
                        "l2": "256 MB memset on the lane's stream before every step (inside the timed span with lanes > 1, outside the "
                              "per-step events of the single-lane segment); index %.2f GB > L2" % (ist["bytes_device"] / 1e9),

@@ -116,10 +116,14 @@ class _DevView:
 
 
 class ShardedSearcher:
-    def __init__(self, device=0, rank=0, world=1, split_mode="query", lanes=1, **kw):
+    def __init__(self, device=0, rank=0, world=1, split_mode="query", lanes=1, shard_group=0, **kw):
         """lanes > 1: that many contexts per GPU sharing one index (api.Searcher.lane), used by run_stream for a stream of
         batches -- the kernels of one lane fill the tails and host-sync bubbles of the others."""
         self.rank, self.world, self.split_mode = rank, world, split_mode
+        # index split: GPUs that share one copy of the k-mer table (0 = all of them); world must be a multiple of it.  Groups of
+        # 2 or 4 keep the peer gathers on few NVLink partners: capacity x group at most of the throughput of full replicas
+        self.shard_group = world if not shard_group else int(shard_group)
+        assert self.shard_group >= 1 and world % self.shard_group == 0, "shard_group must divide the number of GPUs"
         self.n_lanes = max(1, int(lanes))
         self._lanes = None
         self.searcher = api.Searcher(device=device, **kw)
@@ -217,12 +221,15 @@ class ShardedSearcher:
             import torch.distributed as dist
             self.shard = (0, T)
             st = s.build_index(masked, toff)
-            s.shard_index(self.rank, self.world)        # keep k-mer range `rank`, free the rest of the table
+            G = self.shard_group
+            g0 = (self.rank // G) * G                   # first rank of my shard group
+            if G > 1:
+                s.shard_index(self.rank - g0, G)        # keep k-mer range (rank within the group), free the rest of the table
             handles = [None] * self.world
-            dist.all_gather_object(handles, s.shard_export())
-            for r in range(self.world):
+            dist.all_gather_object(handles, s.shard_export() if G > 1 else b"")
+            for r in range(g0, g0 + G):
                 if r != self.rank:
-                    s.shard_attach_ipc(r, handles[r])
+                    s.shard_attach_ipc(r - g0, handles[r])
             dist.barrier()
         else:
             self.shard = (0, T)

@@ -88,17 +88,22 @@ if os.path.exists(rep):
     out = {}
     for name, v in traffic.items():
         key = None
-        if "prefilter_team_kernel<1>" in name or "prefilter_team_kernel<(int)1>" in name:
-            key = "prefilter_team1"
-        elif "prefilter_team_kernel<8>" in name or "prefilter_team_kernel<(int)8>" in name:
-            key = "prefilter_team8"
+        if "expand_kernel" in name:
+            key = "expand_kernel"
+        elif "lookup_kernel" in name:
+            key = "lookup_kernel"
+        elif "bookkeep_kernel<1>" in name or "bookkeep_kernel<(int)1>" in name:
+            key = "bookkeep_kernel_1"
+        elif "bookkeep_kernel<8>" in name or "bookkeep_kernel<(int)8>" in name:
+            key = "bookkeep_kernel_8"
         elif "sw_fast" in name:
             key = "sw_fast_kernel"
         if key:
-            out[key + "_dram_bytes_per_launch"] = sum(v) / len(v)
-    # the roofline entry of bench.py covers both team launches (one batch = one launch of each)
-    out["prefilter_kernel_dram_bytes_per_launch"] = out.get("prefilter_team1_dram_bytes_per_launch", 0.0) + \
-        out.get("prefilter_team8_dram_bytes_per_launch", 0.0)
+            # the second bookkeep<8> launch of a tile (hand-overs of the warp launch) is usually empty: keep the largest
+            out[key + "_dram_bytes_per_launch"] = max(v)
+    # the roofline entry of bench.py covers the whole prefilter (one batch = one launch of each kernel class)
+    out["prefilter_dram_bytes_per_launch"] = sum(out.get(k + "_dram_bytes_per_launch", 0.0)
+                                                 for k in ("expand_kernel", "lookup_kernel", "bookkeep_kernel_1", "bookkeep_kernel_8"))
     out["source"] = "profiles/%s_kernels.csv (ncu --set full, cold cache)" % tag
     json.dump(out, open(os.path.join(P, "traffic.json"), "w"), indent=1)
     print("wrote kernel metrics", out)
