@@ -51,9 +51,11 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--spacers", type=int, default=10000)
     ap.add_argument("--genomes", type=int, default=8000)
-    ap.add_argument("--split-mode", default="index", choices=["index", "target", "query"],
-                    help="N > 1: index = k-mer table sharded over the GPUs, gathered through NVLink peer memory, queries partitioned "
-                         "(default); target = MMseqs2-style target split with hit-list exchange + merge; query = full index per GPU")
+    ap.add_argument("--split-mode", default="query", choices=["index", "target", "query"],
+                    help="N > 1, mode of the main legs: query = full index per GPU, queries partitioned (default: the throughput mode while "
+                         "the index fits one GPU); index = k-mer table sharded over groups of GPUs (--shard-group), gathered through NVLink "
+                         "peer memory; target = MMseqs2-style target split with hit-list exchange + merge.  The line always carries the "
+                         "index split (value, strong scaling on config 4, parity) next to the replicas.")
     ap.add_argument("--shard-group", type=int, default=0,
                     help="index split: GPUs sharing one copy of the k-mer table (0 = all N); N must be a multiple of it")
     ap.add_argument("--strong-spacers", type=int, default=1000000,
@@ -464,68 +466,84 @@ def run_ours(args):
         exh = {"kernel_ms": float(np.mean([r["kernel_ms"] for r in runs])), "cells": float(runs[-1]["n_cells"]),
                "scored": float(runs[-1]["n_scored"]), "kept": float(runs[-1]["n_kept"]), "queries": nq}
 
-    # ---- the same value leg with full replicas (query split) beside the sharded index, N > 1 only ----
-    replicas = None
-    if world > 1 and args.split_mode != "query" and n_lanes > 1:
-        eng_q = multigpu.ShardedSearcher(device=local, rank=rank, world=world, split_mode="query", lanes=n_lanes)
-        eng_q.load_targets(masked, tres, toff)
-        r_ms, _, _, r_q = lanes_value_leg(eng_q)
-        replicas = (r_ms, r_q)
-        eng_q.close()
-
     # ---- strong-scaling leg (BASELINE config 4): ONE job of 1 M spacers split over the GPUs ----
     # the whole job goes through the public API with host buffers (H2D of the frames, D2H of the sorted rows + CIGARs inside
     # the timed region), in chunks of ~125 k frames per GPU over the lanes; total work is fixed, so the N-GPU time against the
-    # 1-GPU time is the strong-scaling curve of the split named in config.split_mode
-    strong = None
+    # 1-GPU time is the strong-scaling curve of the split the engine uses
+    per_gpu = 125000
+    strong_chunks, SQ = None, 0
     if args.strong_spacers > 0:
         sq, so, _ = synth.make_query_frames(args.strong_spacers, tres, toff)
         SQ = len(so) - 1
         sqp = torch.from_numpy(np.ascontiguousarray(sq)).pin_memory()
         sqn = sqp.numpy()
         so = np.ascontiguousarray(so, dtype=np.uint64)
-        per_gpu = 125000
         step_q = per_gpu * world
-        chunks = []
+        strong_chunks = []
         for c0 in range(0, SQ, step_q):
             c1 = min(SQ, c0 + step_q)
-            chunks.append((sqn[int(so[c0]):int(so[c1])], (so[c0:c1 + 1] - so[c0]).astype(np.uint64)))
+            strong_chunks.append((sqn[int(so[c0]):int(so[c1])], (so[c0:c1 + 1] - so[c0]).astype(np.uint64)))
+
+    def strong_leg(engine, mode, lanes_n):
+        """-> [wall ms (max over ranks), rows, similar k-mers, expand, lookup, bookkeeping, prefilter kernels, align stage ms
+        (summed over ranks)] or None"""
+        if not strong_chunks:
+            return None
         rows_total = [0]
 
         def run_chunks(lst):
-            if world > 1 and args.split_mode == "target":
+            if world > 1 and mode == "target":
                 pending, stats = None, []
                 for cq, co in lst:
-                    cur = eng.search_host_begin(cq, co, db_res)
+                    cur = engine.search_host_begin(cq, co, db_res)
                     stats.append(cur["stats"])
                     if pending is not None:
                         v = pending["view"].wait(); rows_total[0] += len(v.rows); v.close()
                     pending = cur
                 v = pending["view"].wait(); rows_total[0] += len(v.rows); v.close()
                 return stats
-            sts_ = eng.run_stream(lst, db_res)
+            sts_ = engine.run_stream(lst, db_res)
             rows_total[0] += sum(x["rows"] for x in sts_)
             return sts_
 
-        run_chunks(chunks[: max(2, 2 * n_lanes)])
+        run_chunks(strong_chunks[: max(2, 2 * lanes_n)])
         rows_total[0] = 0
         barrier()
-        t0 = time.perf_counter()
-        ssts = run_chunks(chunks)
+        t0_ = time.perf_counter()
+        ssts = run_chunks(strong_chunks)
         barrier()
-        strong_s = time.perf_counter() - t0
-        stage = {k: float(sum(x["prefilter"][k] for x in ssts)) for k in ("expand_ms", "lookup_ms", "bookkeep_ms", "kernel_ms")}
-        stage["align_ms"] = float(sum(x["align"]["total_ms"] for x in ssts))
-        kmers = float(sum(x["prefilter"]["n_kmers"] for x in ssts))
-        strong = {"wall_s": strong_s, "rows": float(rows_total[0]), "kmers": kmers, "stage": stage, "chunks": len(chunks)}
-        del sqp, sqn, chunks
+        wall = time.perf_counter() - t0_
+        vals = [float(rows_total[0]), float(sum(x["prefilter"]["n_kmers"] for x in ssts))]
+        vals += [float(sum(x["prefilter"][k] for x in ssts)) for k in ("expand_ms", "lookup_ms", "bookkeep_ms", "kernel_ms")]
+        vals.append(float(sum(x["align"]["total_ms"] for x in ssts)))
+        tw = torch.tensor([wall * 1e3], dtype=torch.float64, device="cuda")
+        ts = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        return [float(tw[0])] + [float(x) for x in ts]
 
-    # ---- parity of the measured configuration against the reference binary (config 2 digest) ----
-    parity = None
-    if not args.no_parity:
+    def strong_block(v, mode, group):
+        if not v:
+            return None
+        return {"value": SQ / (v[0] * 1e-3), "unit": UNIT, "ms_total": v[0], "scaling": "strong",
+                "workload": "BASELINE config 4: %d synthetic spacers = %d frames, ONE job split over %d GPU(s) (%s), chunks of %d frames "
+                            "per GPU through the public API with pinned host buffers (H2D + D2H inside the timed region)"
+                            % (args.strong_spacers, SQ, world, ("split_mode " + mode + (", shard groups of %d" % group if mode == "index" else ""))
+                               if world > 1 else "single GPU", per_gpu),
+                "rows": int(v[1]), "similar_kmers": int(v[2]),
+                "stage_ms_summed_over_gpus": {"expand": v[3], "lookup": v[4], "bookkeeping": v[5], "prefilter_kernels": v[6], "align_stage": v[7]},
+                "nvlink": ({"mode": "index split: table entries of the other GPUs' k-mer ranges are gathered with peer loads inside lookup_kernel",
+                            "bytes_est": v[2] * 0.336 * (group - 1) / group * 32.0,
+                            "how": "similar k-mers x 0.336 (share with an occupied table entry, measured on this index) x (G-1)/G remote (G = shard "
+                                   "group) x one 32-byte sector per 16-byte entry; posting lists of >= 3 targets (5 % of the entries) add their own"}
+                           if (world > 1 and mode == "index" and group > 1) else None)}
+
+    # ---- parity of a configuration against the reference binary (config 2 digest) ----
+    def parity_check(engine):
         import hashlib
         pq, po = (qres, qoff) if world == 1 else synth.make_query_frames(args.spacers, tres, toff)[:2]
-        res = eng.search_host(np.ascontiguousarray(pq), np.ascontiguousarray(po, dtype=np.uint64), db_res)
+        res = engine.search_host(np.ascontiguousarray(pq), np.ascontiguousarray(po, dtype=np.uint64), db_res)
         rows = res["rows"]
         lines = api.format_align_rows(rows, res["cigar"], np.diff(np.asarray(po, dtype=np.uint64)).astype(np.int64),
                                       np.diff(np.asarray(toff, dtype=np.uint64)).astype(np.int64))
@@ -535,38 +553,56 @@ def run_ours(args):
             dist.all_gather_object(allparts, mine)
         else:
             allparts = [mine]
-        if rank == 0:
-            ent = {}
-            n_rows = 0
-            for qs, ls in allparts:
-                n_rows += len(ls)
-                for q, l in zip(qs, ls):
-                    ent.setdefault(int(q), []).append(l)
-            h = hashlib.sha256()
-            for k in range(len(po) - 1):
-                h.update(b"%d\n" % k)
-                h.update("".join(x + "\n" for x in ent.get(k, [])).encode())
-            parity = {"aln_sha256": h.hexdigest(), "aln_rows": n_rows}
-            try:
-                want = json.load(open(os.path.join(ROOT, "tests", "golden", "config2_digest.json")))
-                ok = (args.spacers == want.get("spacers", 10000) and args.genomes == 8000 and not args.no_mask and
-                      parity["aln_sha256"] == want["aln_sha256"] and n_rows == want["aln_rows"])
-                parity["reference"] = "tests/golden/config2_digest.json (SHA-256 of the reference binary's alignment DB, canonical form)"
-                parity["parity_ok"] = bool(ok)
-            except Exception as e:  # noqa: BLE001
-                parity["parity_ok"] = None
-                parity["error"] = str(e)
+        if rank != 0:
+            return None
+        ent = {}
+        n_rows = 0
+        for qs, ls in allparts:
+            n_rows += len(ls)
+            for q, l in zip(qs, ls):
+                ent.setdefault(int(q), []).append(l)
+        h = hashlib.sha256()
+        for k in range(len(po) - 1):
+            h.update(b"%d\n" % k)
+            h.update("".join(x + "\n" for x in ent.get(k, [])).encode())
+        out = {"aln_sha256": h.hexdigest(), "aln_rows": n_rows}
+        try:
+            want = json.load(open(os.path.join(ROOT, "tests", "golden", "config2_digest.json")))
+            ok = (args.spacers == want.get("spacers", 10000) and args.genomes == 8000 and not args.no_mask and
+                  out["aln_sha256"] == want["aln_sha256"] and n_rows == want["aln_rows"])
+            out["reference"] = "tests/golden/config2_digest.json (SHA-256 of the reference binary's alignment DB, canonical form)"
+            out["parity_ok"] = bool(ok)
+        except Exception as e:  # noqa: BLE001
+            out["parity_ok"] = None
+            out["error"] = str(e)
+        return out
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3, exh["kernel_ms"] if exh else 0.0, single_ms, strong["wall_s"] * 1e3 if strong else 0.0,
-                      replicas[0] if replicas else 0.0], dtype=torch.float64, device="cuda")
-    ssum = torch.tensor([strong["rows"], strong["kmers"]] + [strong["stage"][k] for k in ("expand_ms", "lookup_ms", "bookkeep_ms", "kernel_ms", "align_ms")]
-                        if strong else [0.0] * 7, dtype=torch.float64, device="cuda")
+    strong = strong_leg(eng, args.split_mode, n_lanes)
+    parity = None if args.no_parity else parity_check(eng)
+
+    # ---- the other way to spread the search over the GPUs, N > 1: value leg, strong-scaling leg and parity of that mode ----
+    # main mode "query" (full index per GPU): the k-mer table sharded over groups of GPUs and gathered through NVLink peer memory
+    # ("index"); main mode "index" / "target": full replicas ("query")
+    other = None
+    if world > 1 and n_lanes > 1:
+        omode = "index" if args.split_mode == "query" else "query"
+        ogroup = (args.shard_group or min(2, world)) if omode == "index" else 0
+        eng_o = multigpu.ShardedSearcher(device=local, rank=rank, world=world, split_mode=omode, lanes=n_lanes, shard_group=ogroup)
+        eng_o.load_targets(masked, tres, toff)
+        o_ms, _, _, o_q = lanes_value_leg(eng_o)
+        o_strong = strong_leg(eng_o, omode, n_lanes)
+        o_parity = None if args.no_parity else parity_check(eng_o)
+        to = torch.tensor([o_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(to, op=dist.ReduceOp.MAX)
+        other = {"mode": omode, "group": ogroup, "ms": float(to[0]), "queries": o_q, "strong": o_strong, "parity": o_parity}
+        eng_o.close()
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, exh["kernel_ms"] if exh else 0.0, single_ms], dtype=torch.float64, device="cuda")
     tsum = torch.tensor([exh["cells"], exh["scored"], exh["kept"], exh["queries"]] if exh else [0.0] * 4, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        dist.all_reduce(ssum, op=dist.ReduceOp.SUM)
-    dev_ms, e2e_ms, exh_ms, single_ms, strong_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3]), float(t[4])
+    dev_ms, e2e_ms, exh_ms, single_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     q_total = eng.queries_per_step(Q)
 
     if rank == 0:
@@ -618,26 +654,22 @@ def run_ours(args):
             "clocks": clocks,
             "wall_s_value_leg": wall_value,
         }
+        main_group = eng.shard_group if (world > 1 and args.split_mode == "index") else 0
         if strong:
-            line["strong_scaling"] = {
-                "value": SQ / (strong_ms * 1e-3), "unit": UNIT, "ms_total": strong_ms, "scaling": "strong",
-                "workload": "BASELINE config 4: %d synthetic spacers = %d frames, ONE job split over %d GPU(s) (%s), chunks of %d frames "
-                            "per GPU through the public API with pinned host buffers (H2D + D2H inside the timed region)"
-                            % (args.strong_spacers, SQ, world, ("split_mode " + args.split_mode) if world > 1 else "single GPU", per_gpu),
-                "rows": int(ssum[0]), "similar_kmers": int(ssum[1]),
-                "stage_ms_summed_over_gpus": {"expand": float(ssum[2]), "lookup": float(ssum[3]), "bookkeeping": float(ssum[4]),
-                                              "prefilter_kernels": float(ssum[5]), "align_stage": float(ssum[6])},
-                "nvlink": ({"mode": "index split: table entries of the other GPUs' k-mer ranges are gathered with peer loads inside lookup_kernel",
-                            "bytes_est": float(ssum[1]) * 0.336 * (world - 1) / world * 32.0,
-                            "how": "similar k-mers x 0.336 (share with an occupied table entry, measured on this index) x (N-1)/N remote x one "
-                                   "32-byte sector per 16-byte entry; posting lists of >= 3 targets (5 % of the entries) add their own sectors"}
-                           if (world > 1 and args.split_mode == "index") else None)}
-        if replicas:
-            line["query_split"] = {"value": replicas[1] / (float(t[5]) * 1e-3), "unit": UNIT, "ms_per_step": float(t[5]) / args.steps,
-                                   "note": "same value leg with the whole index replicated on every GPU and the queries partitioned (no "
-                                           "NVLink traffic on the data path): what sharding the k-mer table costs at a DB size that fits one GPU"}
+            line["strong_scaling"] = strong_block(strong, args.split_mode, main_group)
         if parity:
             line["parity"] = parity
+        if other:
+            blk = {"split_mode": other["mode"], "shard_group": other["group"] or None,
+                   "value": other["queries"] / (other["ms"] * 1e-3), "unit": UNIT, "ms_per_step": other["ms"] / args.steps,
+                   "strong_scaling": strong_block(other["strong"], other["mode"], other["group"]), "parity": other["parity"],
+                   "note": ("the k-mer table (direct table + posting lists) sharded over groups of %d GPUs, one k-mer range per GPU, the other "
+                            "ranges gathered by lookup_kernel with loads on NVLink peer-mapped pointers; queries partitioned.  Measured on "
+                            "8 x B200 (profiles/): groups of 2 / 4 / 8 reach 0.78 / 0.48 / 0.18 of the replica throughput -- remote 16-byte "
+                            "reads through NVSwitch do not scale with the number of peers, so the default shards over pairs" % other["group"])
+                           if other["mode"] == "index" else
+                           "the whole index replicated on every GPU, queries partitioned: no NVLink traffic on the data path"}
+            line["index_split" if other["mode"] == "index" else "query_split"] = blk
         if exh:
             line["sw_exhaustive"] = {
                 "gcups": float(tsum[0]) / (exh_ms * 1e-3) / 1e9 if exh_ms > 0 else None, "kernel_ms": exh_ms,

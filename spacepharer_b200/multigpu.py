@@ -120,9 +120,10 @@ class ShardedSearcher:
         """lanes > 1: that many contexts per GPU sharing one index (api.Searcher.lane), used by run_stream for a stream of
         batches -- the kernels of one lane fill the tails and host-sync bubbles of the others."""
         self.rank, self.world, self.split_mode = rank, world, split_mode
-        # index split: GPUs that share one copy of the k-mer table (0 = all of them); world must be a multiple of it.  Groups of
-        # 2 or 4 keep the peer gathers on few NVLink partners: capacity x group at most of the throughput of full replicas
-        self.shard_group = world if not shard_group else int(shard_group)
+        # index split: GPUs that share one copy of the k-mer table; world must be a multiple of it.  0 = pairs (all GPUs when the
+        # world is odd): measured on 8 x B200, groups of 2 / 4 / 8 reach 0.78 / 0.48 / 0.18 of the replica throughput -- remote
+        # 16-byte reads through NVSwitch do not scale with the number of peers, so larger groups are for capacity only
+        self.shard_group = (2 if world % 2 == 0 else world) if not shard_group else int(shard_group)
         assert self.shard_group >= 1 and world % self.shard_group == 0, "shard_group must divide the number of GPUs"
         self.n_lanes = max(1, int(lanes))
         self._lanes = None
