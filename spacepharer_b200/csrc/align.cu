@@ -238,6 +238,7 @@ struct FastArgs {
     PairOut *out;
     uint8_t *accFlag;
     int go, ge;
+    uint32_t keyMul;             // 16, as a run-time value: `h * keyMul + row key` stays an IMAD (FMA pipe) instead of an ALU-pipe LEA
     double evalThr, dbRes;
     spb_gumbel g;
     unsigned long long *cells;
@@ -246,6 +247,13 @@ struct FastArgs {
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t r;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
+// a * b + c on the FMA pipe (IMAD): keeps the ALU pipe, which the DPX recurrence saturates, free of the key arithmetic
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
     return r;
 }
 
@@ -300,8 +308,15 @@ __global__ void __launch_bounds__(SWF_THREADS) sw_fast_kernel(FastArgs A) {
         uint32_t H[SWF_ROWS], E[SWF_ROWS];
 #pragma unroll
         for (int i = 0; i < SWF_ROWS; i++) { H[i] = 0; E[i] = 0; }
-        uint32_t best = 0;
-        int colA = -1, colB = -1, rowA = 0, rowB = 0;
+        // End position without a branch in the column loop: every cell contributes the key `h << 4 | (15 - row)` to the column
+        // maximum (h <= 16 rows x 127 < 2^11, so a key fits the positive half of an int16; the shift cannot carry between
+        // the packed halves); the largest key of a column is its best score at the smallest row.  `thr` = best score so far
+        // << 4 | 15 per half: a column key above it is a strictly better score -- the first such column wins, as in the
+        // reference's striped kernel (StripedSmithWaterman.cpp:450-484).  The key adds run on the FMA pipe (IMAD), beside the
+        // DPX instructions of the recurrence on the ALU pipe.
+        uint32_t thr = 0x000F000Fu, keyA = 0, keyB = 0;
+        const uint32_t KM = A.keyMul;
+        int colA = -1, colB = -1;
         const int n = max(lenA, lenB);
         for (int j0 = 0; j0 < n; j0 += 4) {
             // (the shorter target of the pair stops fetching at its own end: never more than 8 bytes past a target)
@@ -321,7 +336,7 @@ __global__ void __launch_bounds__(SWF_THREADS) sw_fast_kernel(FastArgs A) {
                 if (j >= lenB || b > SPB_X) b = SWF_PAD;
                 const uint4 pa = s_prof[0][a][tid], pb = s_prof[1][b][tid];
                 const uint32_t paw[4] = {pa.x, pa.y, pa.z, pa.w}, pbw[4] = {pb.x, pb.y, pb.z, pb.w};
-                uint32_t Hd = 0, F = 0, colmax = 0;
+                uint32_t Hd = 0, F = 0, colkey = 0;
 #pragma unroll
                 for (int i = 0; i < SWF_ROWS; i++) {
                     const int r = i & 3;
@@ -334,26 +349,17 @@ __global__ void __launch_bounds__(SWF_THREADS) sw_fast_kernel(FastArgs A) {
                     F = __viaddmax_s16x2_relu(F, MGE, open);
                     Hd = H[i];
                     H[i] = h;
-                    colmax = __vmaxs2(colmax, h);
+                    colkey = __vmaxs2(colkey, mad_u32(h, KM, (uint32_t)(SWF_ROWS - 1 - i) * 0x10001u));
                 }
-                const uint32_t nb = __vmaxs2(best, colmax);
-                if (nb != best) {      // a strictly better column for at least one of the two pairs
-                    if ((nb & 0xFFFFu) != (best & 0xFFFFu)) {
-                        const uint32_t m = nb & 0xFFFFu;
-                        colA = j;
-#pragma unroll
-                        for (int i = SWF_ROWS - 1; i >= 0; i--) if ((H[i] & 0xFFFFu) == m) rowA = i;
-                    }
-                    if ((nb >> 16) != (best >> 16)) {
-                        const uint32_t m = nb >> 16;
-                        colB = j;
-#pragma unroll
-                        for (int i = SWF_ROWS - 1; i >= 0; i--) if ((H[i] >> 16) == m) rowB = i;
-                    }
-                    best = nb;
-                }
+                const uint32_t nb = __vmaxs2(thr, colkey);
+                const uint32_t chg = nb ^ thr;         // non-zero halves: a strictly better column for that pair
+                if (chg & 0xFFFFu) { keyA = colkey; colA = j; }
+                if (chg > 0xFFFFu) { keyB = colkey; colB = j; }
+                thr = nb | 0x000F000Fu;
             }
         }
+        const int rowA = SWF_ROWS - 1 - (int)(keyA & 15u), rowB = SWF_ROWS - 1 - (int)((keyB >> 16) & 15u);
+        const uint32_t best = ((keyA & 0xFFFFu) >> 4) | ((keyB >> 20) << 16);
         sw_finish_pair(A, pA, LA, lenA, A.qbias[qA], (int)(best & 0xFFFFu), colA, rowA);
         myCells = (unsigned long long)LA * (unsigned long long)lenA;
         if (keyB) {
@@ -402,31 +408,64 @@ struct TbArgs {
     unsigned char *tbScratch;
     const uint64_t *cigOff;    // [nAcc+1] offsets into cigar
     char *cigar;
+    const uint8_t *qfast;      // per query: 1 = register-kernel query (L <= 16, segLen 1), 16-row int8 profile in prof16
+    const uint4 *prof16;
 };
 
-#define TB_FAST_ROWS 32
-__global__ void sw_reverse_kernel(TbArgs A) {
+// ---------------------------------------------------------------------------------------------------------
+// Start coordinates: the reverse pass (StripedSmithWaterman.cpp:202-231).  Queries of the register kernel (qfast: L <= 16
+// and segLen == 1 under both emulated SIMD widths) run it the same way as the forward pass: the column of H / E lives in
+// registers, rows are walked in query coordinates from qEnd down to 0 (the reversed prefix), the int8 profile row of the
+// target residue is one 16-byte load, and the pass stops at the first column whose maximum equals the forward score.
+// Longer queries take the general striped-layout emulation (sw_pass) on a global H/E slice.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) sw_reverse_kernel(TbArgs A) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= A.nAcc) return;
     const uint32_t pair = A.acc[k];
     PairOut o = A.out[pair];
     const uint32_t qi = A.pairQ[pair], ti = A.pairT[pair];
-    const uint64_t qo = A.qoff[qi];
-    const uint8_t *q = A.q + qo;
-    const signed char *cb = A.qcb + qo;
     const uint8_t *t = A.tres + A.toff[ti];
-    const int rl = o.qEnd + 1;
-    const int lanes = o.word ? A.wordLanes : A.byteLanes;
-    const int seg = (rl + lanes - 1) / lanes;
     const int qEnd = o.qEnd;
-    const int16_t *M = A.mat->align;
-    auto prof = [&](int i, int a) -> int { return (int)(signed char)M[a * SPB_ALPHABET + q[qEnd - i]] + (int)cb[qEnd - i]; };
-    int score, col, row;
-    if (rl <= TB_FAST_ROWS) {
-        // spacer frames: the H/E column lives in (thread-interleaved, L1-cached) local memory instead of a global slice
-        short2 heL[TB_FAST_ROWS];
-        sw_pass(t, o.tEnd, -1, -1, rl, seg, A.go, A.ge, o.score, prof, heL, 1, score, col, row);
+    int score = 0, col = -1, row = qEnd;
+    if (A.qfast[qi] && qEnd < SWF_ROWS) {
+        const uint4 *prof = A.prof16 + (size_t)qi * SWF_PROF_ROWS;
+        int H[SWF_ROWS], E[SWF_ROWS];
+#pragma unroll
+        for (int p = 0; p < SWF_ROWS; p++) { H[p] = 0; E[p] = 0; }
+        const int go = A.go, ge = A.ge, want = o.score;
+        for (int j = o.tEnd; j >= 0; j--) {
+            uint32_t a = __ldg(t + j);
+            if (a > SPB_X) a = SPB_X;
+            const uint4 pr = __ldg(prof + a);
+            const uint32_t pw[4] = {pr.x, pr.y, pr.z, pr.w};
+            int hd = 0, F = 0, colMax = 0, colP = qEnd;
+#pragma unroll
+            for (int p = SWF_ROWS - 1; p >= 0; p--) {
+                if (p <= qEnd) {
+                    const int s = (int)(pw[p >> 2] << (24 - 8 * (p & 3))) >> 24;
+                    const int h1 = max(max(hd + s, E[p]), 0);
+                    const int open = max(h1 - go, 0);
+                    E[p] = max(max(E[p] - ge, 0), open);
+                    const int h = max(h1, F);
+                    F = max(max(F - ge, 0), open);
+                    hd = H[p];
+                    H[p] = h;
+                    if (h > colMax) { colMax = h; colP = p; }      // first (largest p = smallest reversed row) strictly better cell
+                }
+            }
+            if (colMax > score) { score = colMax; col = j; row = qEnd - colP; }
+            if (want > 0 && colMax == want) break;
+        }
     } else {
+        const uint64_t qo = A.qoff[qi];
+        const uint8_t *q = A.q + qo;
+        const signed char *cb = A.qcb + qo;
+        const int rl = qEnd + 1;
+        const int lanes = o.word ? A.wordLanes : A.byteLanes;
+        const int seg = (rl + lanes - 1) / lanes;
+        const int16_t *M = A.mat->align;
+        auto prof = [&](int i, int a) -> int { return (int)(signed char)M[a * SPB_ALPHABET + q[qEnd - i]] + (int)cb[qEnd - i]; };
         sw_pass(t, o.tEnd, -1, -1, rl, seg, A.go, A.ge, o.score, prof, A.heScratch + A.heOff[k], 1, score, col, row);
     }
     if (score != o.score || col < 0) {
@@ -438,91 +477,164 @@ __global__ void sw_reverse_kernel(TbArgs A) {
     A.out[pair] = o;
 }
 
-// banded_sw (StripedSmithWaterman.cpp:781-984), transcribed literally: band doubling, direction codes 1..5, traceback
-// from the bottom-right cell, final forced 'M'.  Scratch per pair: h_b/e_b/h_c int32[W] + direction int8[D].
-__device__ __forceinline__ int band_u(int w, int i, int j) { int x = i - w; x = x > 0 ? x : 0; return j - x + 1; }
-__device__ __forceinline__ int band_d(int w, int i, int j, int p) { int x = i - w; x = x > 0 ? x : 0; x = j - x; return x * 3 + p; }
+// ---------------------------------------------------------------------------------------------------------
+// Backtrace: the banded global-in-a-local-box DP of SmithWaterman::banded_sw (StripedSmithWaterman.cpp:781-984) over the
+// aligned box [qStart, qEnd] x [tStart, tEnd], restated in BAND coordinates.
+//
+// A row i of the band covers columns x .. x + 2 bw with x = max(i - bw, 0); slot u = j - x + 1 (1 .. 2 bw + 1) of three row
+// arrays holds H of the previous row (hb), E (eb) and H of the current row (hc); slots 0 and `edge` are the zero borders.
+// Because x advances by one per row once i > bw, the cell above (i-1, j) sits at slot u + s and the diagonal cell at slot
+// u + s - 1 with s = (i > bw) -- the whole row is a static sweep over the slots, so the arrays live in REGISTERS (fully
+// unrolled, no indexed local memory).  A cell's three direction codes (E: 2|3, F: 4|5, H: 1 or a copy of the E / F code)
+// pack into 5 bits; a band row of <= 9 cells is one 64-bit word kept in shared memory ([row][thread], conflict free).  The
+// band doubles until the forward score is reached; the walk back from the bottom-right cell reads the row words.  The reference's
+// tie rules are kept verbatim: E opens only on h - go > e - ge (:852), F likewise (:857), the diagonal wins ties against
+// the gap states and E wins against F only when strictly greater (:872-873).  `edge = min(end + 1, width - 1)` is applied
+// as a SLOT number exactly as the reference does (it zeroes a live slot when the band is clipped by the end of the target).
+// Boxes whose band outgrows 9 cells or whose rows exceed the shared-memory slice run the same sweep with the arrays in a
+// global scratch slice (band_pass_mem).
+// ---------------------------------------------------------------------------------------------------------
+#define TB_BW 4                        // widest band of the register path
+#define TB_W (2 * TB_BW + 1)           // cells per row
+#define TB_ROWS 24                     // rows of the shared-memory direction words
+#define TB_CIG 64                      // ops of the packed op list
+#define TB_THREADS 128
 
-// The band-doubling DP of banded_sw.  Returns false when the next band does not fit the given arrays (Wmax ints per row
-// array, dirCap direction bytes); on success bw is the band of the last pass and dl points at the last row's directions.
-__device__ __forceinline__ bool banded_fill(int32_t *h_b, int32_t *e_b, int32_t *h_c, int8_t *direction, int64_t Wmax, int64_t dirCap,
-                                            const uint8_t *qs, const signed char *cb, const uint8_t *db, const int16_t *M,
-                                            int qLen, int dbLen, int score, int go, int ge, int &bw, int64_t &width_d, int8_t *&dl) {
-    int64_t width = 0;
-    int mx = 0;
-    dl = direction;
-    do {
-        width = (int64_t)bw * 2 + 3;
-        width_d = (int64_t)bw * 2 + 1;
-        if (width + 1 > Wmax || width_d * qLen * 3 > dirCap) return false;
-        for (int j = 1; j < width - 1; j++) h_b[j] = 0;
-        for (int i = 0; i < qLen; i++) {
-            int beg = 0, end = dbLen - 1, u = 0, edge, f, j;
-            j = i - bw; beg = beg > j ? beg : j;
-            j = i + bw; end = end < j ? end : j;
-            edge = end + 1 < width - 1 ? end + 1 : (int)(width - 1);
-            f = h_b[0] = e_b[0] = h_b[edge] = e_b[edge] = h_c[0] = 0;
-            dl = direction + width_d * i * 3;
-            const int qa = qs[i];
-            const int cbi = cb[i];
-            for (j = beg; j <= end; j++) {
-                u = band_u(bw, i, j);
-                const int e = band_u(bw, i - 1, j), b = band_u(bw, i, j - 1), d = band_u(bw, i - 1, j - 1);
-                const int de = band_d(bw, i, j, 0), df = band_d(bw, i, j, 1), dh = band_d(bw, i, j, 2);
-                int t1 = i == 0 ? -go : h_b[e] - go;
-                int t2 = i == 0 ? -ge : e_b[e] - ge;
-                e_b[u] = t1 > t2 ? t1 : t2;
-                dl[de] = t1 > t2 ? 3 : 2;
-                t1 = h_c[b] - go;
-                t2 = f - ge;
-                f = t1 > t2 ? t1 : t2;
-                dl[df] = t1 > t2 ? 5 : 4;
-                const int e1 = e_b[u] > 0 ? e_b[u] : 0;
-                const int f1 = f > 0 ? f : 0;
-                t1 = e1 > f1 ? e1 : f1;
-                t2 = h_b[d] + (int)(signed char)M[qa * SPB_ALPHABET + db[j]] + cbi;
-                h_c[u] = t1 > t2 ? t1 : t2;
-                if (h_c[u] > mx) mx = h_c[u];
-                if (t1 <= t2) dl[dh] = 1;
-                else dl[dh] = e1 > f1 ? dl[de] : dl[df];
-            }
-            for (j = 1; j <= u; j++) h_b[j] = h_c[j];
-        }
-        bw *= 2;
-    } while (mx < score);
-    bw /= 2;
-    return true;
+struct BandCell { int e, f, h, code; };
+// one cell: hAbove / eAbove = H, E of (i-1, j); hLeft = H of (i, j-1); hDiag = H of (i-1, j-1); f = running F of the row
+__device__ __forceinline__ BandCell band_cell(bool firstRow, int hAbove, int eAbove, int hLeft, int hDiag, int f, int sub, int go, int ge) {
+    BandCell c;
+    int t1 = firstRow ? -go : hAbove - go;
+    int t2 = firstRow ? -ge : eAbove - ge;
+    c.e = t1 > t2 ? t1 : t2;
+    const int de = t1 > t2 ? 3 : 2;
+    t1 = hLeft - go;
+    t2 = f - ge;
+    c.f = t1 > t2 ? t1 : t2;
+    const int df = t1 > t2 ? 5 : 4;
+    const int e1 = max(c.e, 0), f1 = max(c.f, 0);
+    t1 = max(e1, f1);
+    t2 = hDiag + sub;
+    c.h = t1 > t2 ? t1 : t2;
+    const int dh = (t1 <= t2) ? 1 : (e1 > f1 ? de : df);
+    c.code = dh | ((de & 1) << 3) | ((df & 1) << 4);
+    return c;
+}
+// direction code of (row word, cell, state): 0 when the cell was never written
+__device__ __forceinline__ int band_code(unsigned long long w, int cell, int st) {
+    const int bits = (int)(w >> (5 * cell)) & 31;
+    if ((bits & 7) == 0) return 0;
+    return st == 2 ? (bits & 7) : (st == 0 ? 2 + ((bits >> 3) & 1) : 4 + ((bits >> 4) & 1));
 }
 
-// Walk back from the bottom-right cell (StripedSmithWaterman.cpp:882-960); ops are produced last-to-first into cig[0..n).
-// Returns false on a direction code outside 1..5 or when cigCap is reached ("Trace back error").
-__device__ __forceinline__ bool banded_walk(const int8_t *dl, int64_t width_d, int bw, int qLen, int dbLen, char *cig, uint32_t cigCap,
-                                            uint32_t &n) {
+// one pass over the box with band bw <= BWMAX; the row arrays (slots 0 .. 2 TB_BW + 2) persist between passes like the
+// reference's heap arrays.  Returns the largest H.
+template <int BWMAX>
+__device__ __forceinline__ int band_pass_reg(int (&hb)[TB_W + 2], int (&eb)[TB_W + 2], int (&hc)[TB_W + 2], unsigned long long *dirs,
+                                             const uint8_t *qs, const signed char *cb, const uint8_t *db, const signed char *s_mat,
+                                             int qLen, int dbLen, int bw, int go, int ge) {
+    constexpr int W = 2 * BWMAX + 1;
+    const int width = 2 * bw + 3;
+#pragma unroll
+    for (int u = 1; u <= W; u++) if (u < width - 1) hb[u] = 0;
+    int mx = 0;
+    for (int i = 0; i < qLen; i++) {
+        const int x = max(i - bw, 0), end = min(dbLen - 1, i + bw);
+        const int edge = min(end + 1, width - 1), uEnd = end - x + 1;
+        const bool s = i > bw, first = (i == 0);
+        hb[0] = eb[0] = hc[0] = 0;
+#pragma unroll
+        for (int u = 1; u <= W + 1; u++) if (u == edge) { hb[u] = 0; eb[u] = 0; }
+        const signed char *mrow = s_mat + (int)qs[i] * 32;
+        const int cbi = cb[i];
+        int f = 0;
+        unsigned long long word = 0;
+#pragma unroll
+        for (int u = 1; u <= W; u++) {
+            if (u <= uEnd) {
+                const int sub = (int)mrow[db[u + x - 1]] + cbi;
+                const BandCell c = band_cell(first, s ? hb[u + 1] : hb[u], s ? eb[u + 1] : eb[u], hc[u - 1], s ? hb[u] : hb[u - 1], f, sub, go, ge);
+                eb[u] = c.e;
+                f = c.f;
+                hc[u] = c.h;
+                mx = max(mx, c.h);
+                word |= (unsigned long long)c.code << (5 * (u - 1));
+            }
+        }
+#pragma unroll
+        for (int u = 1; u <= W; u++) if (u <= uEnd) hb[u] = hc[u];
+        dirs[(size_t)i * TB_THREADS] = word;
+    }
+    return mx;
+}
+
+// the same sweep with the row arrays and one direction byte per cell in memory (any band width)
+__device__ __noinline__ int band_pass_mem(int *hb, int *eb, int *hc, uint8_t *dirs, const uint8_t *qs, const signed char *cb, const uint8_t *db,
+                                          const signed char *s_mat, int qLen, int dbLen, int bw, int go, int ge) {
+    const int width = 2 * bw + 3, cells = 2 * bw + 1;
+    for (int u = 1; u < width - 1; u++) hb[u] = 0;
+    int mx = 0;
+    for (int i = 0; i < qLen; i++) {
+        const int x = max(i - bw, 0), end = min(dbLen - 1, i + bw);
+        const int edge = min(end + 1, width - 1), uEnd = end - x + 1;
+        const int s = i > bw ? 1 : 0;
+        hb[0] = eb[0] = hb[edge] = eb[edge] = hc[0] = 0;
+        const signed char *mrow = s_mat + (int)qs[i] * 32;
+        const int cbi = cb[i];
+        int f = 0;
+        uint8_t *drow = dirs + (size_t)i * cells;
+        for (int u = 1; u <= uEnd; u++) {
+            const int sub = (int)mrow[db[u + x - 1]] + cbi;
+            const BandCell c = band_cell(i == 0, hb[u + s], eb[u + s], hc[u - 1], hb[u + s - 1], f, sub, go, ge);
+            eb[u] = c.e;
+            f = c.f;
+            hc[u] = c.h;
+            mx = max(mx, c.h);
+            drow[u - 1] = (uint8_t)c.code;
+        }
+        for (int u = uEnd; u < cells; u++) drow[u] = 0;
+        for (int u = 1; u <= uEnd; u++) hb[u] = hc[u];
+    }
+    return mx;
+}
+
+// Walk back from the bottom-right cell (StripedSmithWaterman.cpp:882-960).  code(i, cell, st) returns the direction code or 0.
+// Ops are produced last-to-first: emit(op) with op 0 = M, 1 = I, 2 = D.  Returns false on a missing code or when the op list
+// is full ("Trace back error").
+template <class Code, class Emit>
+__device__ __forceinline__ bool band_walk(int qLen, int dbLen, int bw, uint32_t cap, Code code, Emit emit, uint32_t &n) {
+    const int cells = 2 * bw + 1;
     int i = qLen - 1, j = dbLen - 1, st = 2;
     n = 0;
     while (i > 0 || j > 0) {
-        const int t1 = band_d(bw, i, j, st);
-        char op = 0;
-        switch (dl[t1]) {
-            case 1: --i; --j; st = 2; dl -= width_d * 3; op = 'M'; break;
-            case 2: --i; st = 0; dl -= width_d * 3; op = 'I'; break;
-            case 3: --i; st = 2; dl -= width_d * 3; op = 'I'; break;
-            case 4: --j; st = 1; op = 'D'; break;
-            case 5: --j; st = 2; op = 'D'; break;
+        // the reference addresses its direction bytes as one flat array: a cell left / right of the row's band is the last /
+        // first cell of the neighbouring row
+        int r = i, cell = j - max(i - bw, 0);
+        if (cell < 0) { r--; cell += cells; }
+        else if (cell >= cells) { r++; cell -= cells; }
+        if (r < 0 || r >= qLen || cell < 0 || cell >= cells) return false;
+        int op;
+        switch (code(r, cell, st)) {
+            case 1: --i; --j; st = 2; op = 0; break;
+            case 2: --i; st = 0; op = 1; break;
+            case 3: --i; st = 2; op = 1; break;
+            case 4: --j; st = 1; op = 2; break;
+            case 5: --j; st = 2; op = 2; break;
             default: return false;
         }
-        if (n + 1 >= cigCap) return false;
-        cig[n++] = op;
+        if (n + 1 >= cap) return false;
+        emit(op);
+        n++;
     }
     return true;
 }
 
-#define TB_FAST_BW 4                                   // widest band of the local-memory path
-#define TB_FAST_W (2 * TB_FAST_BW + 5)                 // ints per row array
-#define TB_FAST_QLEN 21
-#define TB_FAST_DIR ((2 * TB_FAST_BW + 1) * TB_FAST_QLEN * 3)
-#define TB_FAST_CIG 64
-__global__ void sw_traceback_kernel(TbArgs A) {
+__global__ void __launch_bounds__(TB_THREADS) sw_traceback_kernel(TbArgs A) {
+    __shared__ unsigned long long s_dirs[TB_ROWS * TB_THREADS];
+    __shared__ signed char s_mat[SPB_ALPHABET * 32];
+    for (int x = threadIdx.x; x < SPB_ALPHABET * 32; x += blockDim.x)
+        s_mat[x] = (x & 31) < SPB_ALPHABET ? (signed char)A.mat->align[(x >> 5) * SPB_ALPHABET + (x & 31)] : (signed char)0;
+    __syncthreads();
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= A.nAcc) return;
     const uint32_t pair = A.acc[k];
@@ -533,7 +645,6 @@ __global__ void sw_traceback_kernel(TbArgs A) {
     const uint8_t *qs = A.q + qo + o.qStart;
     const signed char *cb = A.qcb + qo + o.qStart;
     const uint8_t *db = A.tres + A.toff[ti] + o.tStart;
-    const int16_t *M = A.mat->align;
     const int dbLen = o.tEnd - o.tStart + 1, qLen = o.qEnd - o.qStart + 1;
     const int score = o.score, go = A.go, ge = A.ge;
     const int bw0 = abs(dbLen - qLen) + 1;
@@ -541,71 +652,85 @@ __global__ void sw_traceback_kernel(TbArgs A) {
     const uint32_t cigCap = (uint32_t)(A.cigOff[k + 1] - A.cigOff[k]);
     uint32_t n = 0;
     bool bad = false, done = false;
-    // Spacer-sized alignments: the band arrays, the direction bytes and the ops stay in thread-local memory (interleaved
-    // across the warp, L1-cached) -- same arithmetic, same order.  Anything that outgrows them (band doubled past
-    // TB_FAST_BW, long aligned span) replays the whole loop on the global scratch slice below.
-    if (bw0 <= TB_FAST_BW && qLen <= TB_FAST_QLEN && qLen + dbLen + 2 <= TB_FAST_CIG) {
-        int32_t hL[3 * TB_FAST_W];
-        int8_t dirL[TB_FAST_DIR];
-        char cigL[TB_FAST_CIG];
-        for (int x = 0; x < 3 * TB_FAST_W; x++) hL[x] = 0;
-        int bw = bw0;
-        int64_t width_d = 0;
-        int8_t *dl = dirL;
-        if (banded_fill(hL, hL + TB_FAST_W, hL + 2 * TB_FAST_W, dirL, TB_FAST_W, TB_FAST_DIR, qs, cb, db, M, qLen, dbLen, score, go, ge,
-                        bw, width_d, dl)) {
+    // ops as 2-bit codes, last-to-first, in two registers
+    unsigned long long opsLo = 0, opsHi = 0;
+    auto emit = [&](int op) {
+        if (n < 32) opsLo |= (unsigned long long)op << (2 * n);
+        else opsHi |= (unsigned long long)op << (2 * (n - 32));
+    };
+    auto op_at = [&](uint32_t x) -> int { return (int)((x < 32 ? opsLo >> (2 * x) : opsHi >> (2 * (x - 32))) & 3ull); };
+    if (bw0 <= TB_BW && qLen <= TB_ROWS && qLen + dbLen + 2 <= TB_CIG) {
+        int hb[TB_W + 2], eb[TB_W + 2], hc[TB_W + 2];
+#pragma unroll
+        for (int u = 0; u < TB_W + 2; u++) { hb[u] = 0; eb[u] = 0; hc[u] = 0; }
+        unsigned long long *dirs = s_dirs + threadIdx.x;
+        int bw = bw0, mx = 0;
+        bool fits = true;
+        for (;;) {
+            if (bw == 1) mx = band_pass_reg<1>(hb, eb, hc, dirs, qs, cb, db, s_mat, qLen, dbLen, bw, go, ge);
+            else if (bw == 2) mx = band_pass_reg<2>(hb, eb, hc, dirs, qs, cb, db, s_mat, qLen, dbLen, bw, go, ge);
+            else mx = band_pass_reg<TB_BW>(hb, eb, hc, dirs, qs, cb, db, s_mat, qLen, dbLen, bw, go, ge);
+            if (mx >= score) break;
+            bw *= 2;
+            if (bw > TB_BW) { fits = false; break; }     // replayed from the start on the scratch slice below
+        }
+        if (fits) {
             done = true;
-            bad = !banded_walk(dl, width_d, bw, qLen, dbLen, cigL, min(cigCap, (uint32_t)TB_FAST_CIG), n);
-            if (!bad) {
-                cigL[n++] = 'M';
-                // reversed copy to the output + identities (Matcher.cpp:61-187)
-                int ids = 0, qi2 = 0, ti2 = 0;
-                for (uint32_t x = 0; x < n; x++) {
-                    const char op = cigL[n - 1 - x];
-                    cig[x] = op;
-                    if (op == 'M') { ids += (qs[qi2] == db[ti2]); qi2++; ti2++; }
-                    else if (op == 'I') qi2++;
-                    else ti2++;
-                }
-                o.cigLen = n;
-                o.nIdent = ids;
-                o.alnLen = (int)n;
-            }
+            bad = !band_walk(qLen, dbLen, bw, min(cigCap, (uint32_t)TB_CIG),
+                             [&](int r, int cell, int st) { return band_code(dirs[(size_t)r * TB_THREADS], cell, st); }, emit, n);
         }
     }
     if (!done) {
-        // scratch layout: [h_b | e_b | h_c] int32 each Wmax, then direction bytes
+        // scratch slice: [hb | eb | hc] int32 each Wmax, then one direction byte per cell; ops go to the output slice directly
         const uint64_t bytes = A.tbOff[k + 1] - A.tbOff[k];
         unsigned char *base = A.tbScratch + A.tbOff[k];
         int bwMax = bw0;
         while (bwMax < max(qLen, dbLen)) bwMax *= 2;
         const int64_t Wmax = (int64_t)bwMax * 2 + 3 + 2;
-        int32_t *h_b = reinterpret_cast<int32_t *>(base);
-        int32_t *e_b = h_b + Wmax;
-        int32_t *h_c = e_b + Wmax;
-        int8_t *direction = reinterpret_cast<int8_t *>(h_c + Wmax);
+        int *hb = reinterpret_cast<int *>(base), *eb = hb + Wmax, *hc = eb + Wmax;
+        uint8_t *dirs = reinterpret_cast<uint8_t *>(hc + Wmax);
         const int64_t dirCap = (int64_t)bytes - 3 * Wmax * 4;
-        for (int64_t x = 0; x < 3 * Wmax; x++) h_b[x] = 0;
+        for (int64_t x = 0; x < 3 * Wmax; x++) hb[x] = 0;
         int bw = bw0;
-        int64_t width_d = 0;
-        int8_t *dl = direction;
-        bad = !banded_fill(h_b, e_b, h_c, direction, Wmax, dirCap, qs, cb, db, M, qLen, dbLen, score, go, ge, bw, width_d, dl);
-        if (!bad) bad = !banded_walk(dl, width_d, bw, qLen, dbLen, cig, cigCap, n);
-        if (!bad) {
-            cig[n++] = 'M';
-            for (uint32_t a = 0, b = n - 1; a < b; a++, b--) { char tmp = cig[a]; cig[a] = cig[b]; cig[b] = tmp; }
-            int ids = 0, qi2 = 0, ti2 = 0;
-            for (uint32_t x = 0; x < n; x++) {
-                if (cig[x] == 'M') { ids += (qs[qi2] == db[ti2]); qi2++; ti2++; }
-                else if (cig[x] == 'I') qi2++;
-                else ti2++;
-            }
-            o.cigLen = n;
-            o.nIdent = ids;
-            o.alnLen = (int)n;
+        for (;;) {
+            if ((int64_t)bw * 2 + 3 + 1 > Wmax || ((int64_t)bw * 2 + 1) * qLen > dirCap) { bad = true; break; }
+            if (band_pass_mem(hb, eb, hc, dirs, qs, cb, db, s_mat, qLen, dbLen, bw, go, ge) >= score) break;
+            bw *= 2;
         }
+        if (!bad) {
+            const int cells = 2 * bw + 1;
+            bad = !band_walk(qLen, dbLen, bw, cigCap,
+                             [&](int r, int cell, int st) {
+                                 const int bits = dirs[(size_t)r * cells + cell];
+                                 return (bits & 7) == 0 ? 0 : (st == 2 ? (bits & 7) : (st == 0 ? 2 + ((bits >> 3) & 1) : 4 + ((bits >> 4) & 1)));
+                             },
+                             [&](int op) { cig[n] = "MID"[op]; }, n);
+            if (!bad) {
+                cig[n++] = 'M';
+                for (uint32_t a = 0, b = n - 1; a < b; a++, b--) { const char tmp = cig[a]; cig[a] = cig[b]; cig[b] = tmp; }
+            } else {
+                for (uint32_t x = 0; x < cigCap; x++) cig[x] = 0;    // a failed walk leaves no partial ops behind
+            }
+        }
+    } else if (!bad) {
+        // the walk produced the path end-to-start; the start cell is the final forced 'M' of the reference
+        cig[0] = 'M';
+        for (uint32_t x = 1; x <= n; x++) cig[x] = "MID"[op_at(n - x)];
+        n++;
     }
-    if (bad) {
+    if (!bad) {
+        // identities (Matcher.cpp:61-187)
+        int ids = 0, qi2 = 0, ti2 = 0;
+        for (uint32_t x = 0; x < n; x++) {
+            const char op = cig[x];
+            if (op == 'M') { ids += (qs[qi2] == db[ti2]); qi2++; ti2++; }
+            else if (op == 'I') qi2++;
+            else ti2++;
+        }
+        o.cigLen = n;
+        o.nIdent = ids;
+        o.alnLen = (int)n;
+    } else {
         // reference: "Trace back error" -> no CIGAR; alnLength from coordinates, no identities (Matcher.cpp:141-152)
         o.cigLen = 0;
         o.nIdent = 0;
@@ -1096,6 +1221,7 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
     F.accFlag = c->s_e.as<uint8_t>();
     F.go = p->gap_open;
     F.ge = p->gap_extend;
+    F.keyMul = 16u;
     F.evalThr = p->eval_thr;
     F.dbRes = (double)p->db_res_count;
     F.g = p->gumbel;
@@ -1186,7 +1312,9 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
         B.go = A.go; B.ge = A.ge; B.byteLanes = A.byteLanes; B.wordLanes = A.wordLanes;
         B.heScratch = c->s_h.as<short2>();
         B.heOff = heOff;
-        sw_reverse_kernel<<<(nAcc + 63) / 64, 64, 0, st>>>(B);
+        B.qfast = c->s_m.as<uint8_t>();
+        B.prof16 = c->s_l.as<uint4>();
+        sw_reverse_kernel<<<(nAcc + 127) / 128, 128, 0, st>>>(B);
         SPB_CUDA(cudaGetLastError()); c->n_launches++;
         if (c->s_i.ensure(((size_t)nAcc + 1) * 16) || c->s_j.ensure(((size_t)nAcc + 1) * 16)) return 1;
         uint64_t *tbSz = c->s_i.as<uint64_t>(), *tbOff = tbSz + (nAcc + 1);
@@ -1211,7 +1339,7 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
         B.tbScratch = c->s_k.as<unsigned char>();
         B.cigOff = cigOff;
         B.cigar = c->d_cig.as<char>();
-        sw_traceback_kernel<<<(nAcc + 63) / 64, 64, 0, st>>>(B);
+        sw_traceback_kernel<<<(nAcc + TB_THREADS - 1) / TB_THREADS, TB_THREADS, 0, st>>>(B);
         SPB_CUDA(cudaGetLastError()); c->n_launches++;
         c->n_cigar = cigTotal;
     }

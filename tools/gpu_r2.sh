@@ -27,6 +27,10 @@ if [[ " $* " == *" lanesweep "* ]]; then
     done
   done
 fi
+if [[ " $* " == *" ncu3 "* ]]; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'bookkeep_kernel|expand_kernel' -s 6 -c 4 \
+      -o $OUT/prof3_$TAG -f python tools/perf_probe.py > $OUT/prof3_$TAG.log 2>&1; echo "ncu3 rc=$?"
+fi
 if [[ " $* " == *" ncu2 "* ]]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'bookkeep_kernel|sort_rows|sw_traceback|sw_reverse|align_profile|sw_fast' -s 8 -c 8 \
       -o $OUT/prof2_$TAG -f python tools/perf_probe.py > $OUT/prof2_$TAG.log 2>&1; echo "ncu2 rc=$?"
