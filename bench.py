@@ -60,6 +60,8 @@ def parse_args():
                     help="index split: GPUs sharing one copy of the k-mer table (0 = all N); N must be a multiple of it")
     ap.add_argument("--strong-spacers", type=int, default=1000000,
                     help="spacers of the strong-scaling leg (BASELINE config 4: the whole job split over the GPUs); 0 = skip")
+    ap.add_argument("--no-disk-to-disk", action="store_true",
+                    help="skip the product-level leg (the C++ host binary `spb200 search` on the config-4 DBs, from disk to disk)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity_ok check (rows of the config-2 batch vs the reference digest)")
     ap.add_argument("--cpu-sample-spacers", type=int, default=0, help="spacers in the CPU baseline sample (0 = auto)")
     ap.add_argument("--lanes", type=int, default=3,
@@ -579,6 +581,7 @@ def run_ours(args):
 
     strong = strong_leg(eng, args.split_mode, n_lanes)
     parity = None if args.no_parity else parity_check(eng)
+    d2d = disk_to_disk(args, tres, toff, sq, so) if (world == 1 and args.strong_spacers > 0 and not args.no_disk_to_disk) else None
 
     # ---- the other way to spread the search over the GPUs, N > 1: value leg, strong-scaling leg and parity of that mode ----
     # main mode "query" (full index per GPU): the k-mer table sharded over groups of GPUs and gathered through NVLink peer memory
@@ -659,6 +662,8 @@ def run_ours(args):
             line["strong_scaling"] = strong_block(strong, args.split_mode, main_group)
         if parity:
             line["parity"] = parity
+        if d2d:
+            line["disk_to_disk"] = d2d
         if other:
             blk = {"split_mode": other["mode"], "shard_group": other["group"] or None,
                    "value": other["queries"] / (other["ms"] * 1e-3), "unit": UNIT, "ms_per_step": other["ms"] / args.steps,
@@ -673,6 +678,10 @@ def run_ours(args):
         if exh:
             line["sw_exhaustive"] = {
                 "gcups": float(tsum[0]) / (exh_ms * 1e-3) / 1e9 if exh_ms > 0 else None, "kernel_ms": exh_ms,
+                "roofline": {"bound": "integer pipe (DPX s16x2)", "alu_instr_per_cell_pair": 7,
+                             "peak_gcups": world * 148 * 4 * 16 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6 * 2 / 7.0 / 1e9,
+                             "frac": (float(tsum[0]) / (exh_ms * 1e-3) / 1e9) / (world * 148 * 4 * 16 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6 * 2 / 7.0 / 1e9)
+                             if exh_ms > 0 else None},
                 "cells": float(tsum[0]), "pairs_scored": int(tsum[1]), "pairs_kept": int(tsum[2]),
                 "workload": "config 5 (--exhaustive-search, no k-mer stage): %d frames (%d spacers per GPU) x all %d ORFs, "
                             "sw_exhaustive_kernel; cells = sum qLen*tLen, time = max over ranks of the kernel's CUDA-event time, mean of 2 runs"
@@ -694,6 +703,55 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def disk_to_disk(args, tres, toff, sq, so):
+    """Product level: the C++ host binary on BASELINE config 4 from on-disk MMseqs2 DBs to the on-disk alignment DB -- DB read,
+    tantan, index build, prefilter + align on the GPU, text formatting of every row, DB write (`spb200 search`, the fused
+    prefilter + align modules with the workflow's argv).  Two runs (the first one also pays the cold page cache and driver); the
+    phases are the binary's own wall clock (SPB_TIMING)."""
+    import shutil
+    import subprocess as sp
+    import tempfile
+    from spacepharer_b200 import dbio
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_host_cli import ALN_FLAGS, BIN, PREF_FLAGS
+    if not os.path.exists(BIN):
+        return {"error": "spacepharer_b200/lib/spb200 not built"}
+    w = tempfile.mkdtemp(prefix="spb_d2d_")
+    try:
+        dbio.write_sequence_db_arrays(os.path.join(w, "targets"), tres, toff)
+        dbio.write_sequence_db_arrays(os.path.join(w, "queries"), sq, so)
+        threads = str(min(16, os.cpu_count() or 1))
+        seen, merged = set(), []
+        for lst in (PREF_FLAGS, ALN_FLAGS):
+            for i in range(0, len(lst), 2):
+                if lst[i] not in seen:
+                    seen.add(lst[i])
+                    merged += [lst[i], threads if lst[i] == "--threads" else lst[i + 1]]
+        runs = []
+        for it in range(2):
+            t0 = time.perf_counter()
+            r = sp.run([BIN, "search", w + "/queries", w + "/targets", w + "/aln"] + merged + ["--batch", "250000"], capture_output=True,
+                       text=True, env=dict(os.environ, SPB_TIMING="1"))
+            dt = time.perf_counter() - t0
+            if r.returncode != 0:
+                return {"error": (r.stderr or r.stdout)[-300:]}
+            ph = {}
+            for l in r.stderr.split("\n"):
+                if "[spb200 timing]" in l:
+                    name, val = l.split("]", 1)[1].rsplit(None, 2)[0].strip(), float(l.split()[-2])
+                    ph[name] = val
+            runs.append({"wall_s": dt, "phases_s": ph})
+        best = min(runs, key=lambda x: x["wall_s"])
+        n_rows = sum(1 for _ in open(w + "/aln.index"))
+        return {"value": (len(so) - 1) / best["wall_s"], "unit": UNIT, "wall_s": best["wall_s"], "runs": runs, "host_threads": int(threads),
+                "entries_written": n_rows, "aln_db_bytes": os.path.getsize(w + "/aln"),
+                "workload": "BASELINE config 4 through the host binary: `spb200 search queries targets aln` (workflow argv, --batch 250000), "
+                            "%d spacers = %d frames vs %d ORFs, on-disk DBs in, on-disk alignment DB out; wall clock of the whole process"
+                            % (args.strong_spacers, len(so) - 1, len(toff) - 1)}
+    finally:
+        shutil.rmtree(w, ignore_errors=True)
+
+
 def ncu_traffic():
     """DRAM bytes per launch of the prefilter kernels from the committed ncu capture (profiles/traffic.json), or {}."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
@@ -705,14 +763,17 @@ def ncu_traffic():
 
 def sw_block(cells, ms, aln, clocks):
     """Smith-Waterman forward kernel: GCUPS and its integer-pipe roofline.  One packed DPX / SIMD-video instruction updates two
-    cells; the kernel issues SW_INSTR_PER_CELL_PAIR of them per row of a column pair (PRMT, VIADD, 3 x VIADDMNMX, 2 x VIMNMX + the
-    column maximum = 8), so the ceiling is SMs x 4 schedulers x 32 lanes x f_clk x 2 cells / 8 instructions."""
+    cells; per row of a column pair the kernel issues 7.5 of them on the ALU pipe (PRMT, VIADD.16x2, 3 x VIADDMNMX.S16x2, VIMNMX for H
+    and half a VIMNMX3 for the column-maximum key; the key's IMAD runs on the FMA pipe beside them).  The ALU pipe takes one warp
+    instruction every two cycles per scheduler (16 lanes / clock), so the ceiling is SMs x 4 schedulers x 16 lanes x f_clk x 2 cells /
+    7.5 instructions.  (sw_exhaustive_kernel, 7 ALU instructions per cell pair, measures 4850 GCUPS = 0.91 of the same formula with 7,
+    and ncu reports its ALU pipe 89-90 % busy: profiles/r1j_exhaustive_kernels.csv.)"""
     f = (clocks or {}).get("sm_mhz") or 1965.0
-    peak = 148 * 4 * 32 * f * 1e6 * 2 / 8.0 / 1e9
+    peak = 148 * 4 * 16 * f * 1e6 * 2 / 7.5 / 1e9
     g = cells / (ms * 1e-3) / 1e9 if ms > 0 else None
     return {"gcups": g, "kernel_ms": ms, "cells_per_step": cells, "pairs": aln["n_pairs"], "rows": aln["n_rows"],
             "roofline": {"bound": "integer pipe (DPX s16x2)", "peak_gcups": peak, "frac": (g / peak) if g else None,
-                         "instr_per_cell_pair": 8, "sm_mhz": f,
+                         "alu_instr_per_cell_pair": 7.5, "alu_lanes_per_clock_per_sm": 64, "sm_mhz": f,
                          "note": "padded rows (queries shorter than the kernel's row count) are not counted as cells"}}
 
 

@@ -529,6 +529,7 @@ __device__ __forceinline__ int band_code(unsigned long long w, int cell, int st)
 
 // one pass over the box with band bw <= BWMAX; the row arrays (slots 0 .. 2 TB_BW + 2) persist between passes like the
 // reference's heap arrays.  Returns the largest H.
+// qs / cb / db: the thread's column of the staged sequences (element i at [i * TB_THREADS])
 template <int BWMAX>
 __device__ __forceinline__ int band_pass_reg(int (&hb)[TB_W + 2], int (&eb)[TB_W + 2], int (&hc)[TB_W + 2], unsigned long long *dirs,
                                              const uint8_t *qs, const signed char *cb, const uint8_t *db, const signed char *s_mat,
@@ -545,14 +546,14 @@ __device__ __forceinline__ int band_pass_reg(int (&hb)[TB_W + 2], int (&eb)[TB_W
         hb[0] = eb[0] = hc[0] = 0;
 #pragma unroll
         for (int u = 1; u <= W + 1; u++) if (u == edge) { hb[u] = 0; eb[u] = 0; }
-        const signed char *mrow = s_mat + (int)qs[i] * 32;
-        const int cbi = cb[i];
+        const signed char *mrow = s_mat + (int)qs[i * TB_THREADS] * 32;
+        const int cbi = cb[i * TB_THREADS];
         int f = 0;
         unsigned long long word = 0;
 #pragma unroll
         for (int u = 1; u <= W; u++) {
             if (u <= uEnd) {
-                const int sub = (int)mrow[db[u + x - 1]] + cbi;
+                const int sub = (int)mrow[db[(u + x - 1) * TB_THREADS]] + cbi;
                 const BandCell c = band_cell(first, s ? hb[u + 1] : hb[u], s ? eb[u + 1] : eb[u], hc[u - 1], s ? hb[u] : hb[u - 1], f, sub, go, ge);
                 eb[u] = c.e;
                 f = c.f;
@@ -631,6 +632,8 @@ __device__ __forceinline__ bool band_walk(int qLen, int dbLen, int bw, uint32_t 
 
 __global__ void __launch_bounds__(TB_THREADS) sw_traceback_kernel(TbArgs A) {
     __shared__ unsigned long long s_dirs[TB_ROWS * TB_THREADS];
+    __shared__ uint8_t s_qs[TB_ROWS * TB_THREADS], s_ts[TB_CIG * TB_THREADS];     // the box's query rows / target columns, [i][thread]
+    __shared__ signed char s_cb[TB_ROWS * TB_THREADS];
     __shared__ signed char s_mat[SPB_ALPHABET * 32];
     for (int x = threadIdx.x; x < SPB_ALPHABET * 32; x += blockDim.x)
         s_mat[x] = (x & 31) < SPB_ALPHABET ? (signed char)A.mat->align[(x >> 5) * SPB_ALPHABET + (x & 31)] : (signed char)0;
@@ -664,12 +667,17 @@ __global__ void __launch_bounds__(TB_THREADS) sw_traceback_kernel(TbArgs A) {
 #pragma unroll
         for (int u = 0; u < TB_W + 2; u++) { hb[u] = 0; eb[u] = 0; hc[u] = 0; }
         unsigned long long *dirs = s_dirs + threadIdx.x;
+        // the box's sequences go to shared memory first: independent loads, and every read of the sweeps below is an LDS
+        uint8_t *sq = s_qs + threadIdx.x, *st = s_ts + threadIdx.x;
+        signed char *sc = s_cb + threadIdx.x;
+        for (int i = 0; i < qLen; i++) { sq[i * TB_THREADS] = qs[i]; sc[i * TB_THREADS] = cb[i]; }
+        for (int j = 0; j < dbLen; j++) st[j * TB_THREADS] = db[j];
         int bw = bw0, mx = 0;
         bool fits = true;
         for (;;) {
-            if (bw == 1) mx = band_pass_reg<1>(hb, eb, hc, dirs, qs, cb, db, s_mat, qLen, dbLen, bw, go, ge);
-            else if (bw == 2) mx = band_pass_reg<2>(hb, eb, hc, dirs, qs, cb, db, s_mat, qLen, dbLen, bw, go, ge);
-            else mx = band_pass_reg<TB_BW>(hb, eb, hc, dirs, qs, cb, db, s_mat, qLen, dbLen, bw, go, ge);
+            if (bw == 1) mx = band_pass_reg<1>(hb, eb, hc, dirs, sq, sc, st, s_mat, qLen, dbLen, bw, go, ge);
+            else if (bw == 2) mx = band_pass_reg<2>(hb, eb, hc, dirs, sq, sc, st, s_mat, qLen, dbLen, bw, go, ge);
+            else mx = band_pass_reg<TB_BW>(hb, eb, hc, dirs, sq, sc, st, s_mat, qLen, dbLen, bw, go, ge);
             if (mx >= score) break;
             bw *= 2;
             if (bw > TB_BW) { fits = false; break; }     // replayed from the start on the scratch slice below

@@ -4,7 +4,14 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <fcntl.h>
 #include <sys/stat.h>
+#include <unistd.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#include <parallel/algorithm>
+#endif
 
 #include <algorithm>
 #include <stdexcept>
@@ -49,28 +56,72 @@ void DBReader::open(const std::string &name) {
         if (n == 0) throw std::runtime_error("Could not open data file " + name + "!");
     }
     dataSize_ = data_.size();
+    // index: the whole text is read once and parsed by all host threads (slices cut at line ends); a 1 M-spacer query DB has
+    // 3.8 M lines, and stdio + strtoull per line used to cost more than the GPU search itself
     const std::string idx = name + ".index";
-    FILE *f = fopen(idx.c_str(), "r");
-    if (!f) throw std::runtime_error("Could not open index file " + idx + "!");
-    char line[256];
-    while (fgets(line, sizeof(line), f)) {
-        char *p = line, *e = nullptr;
-        unsigned long long k = strtoull(p, &e, 10);
-        if (e == p) continue;
-        p = e;
-        unsigned long long o = strtoull(p, &e, 10);
-        if (e == p) throw std::runtime_error("Malformed index line in " + idx);
-        p = e;
-        unsigned long long l = strtoull(p, &e, 10);
-        if (e == p) throw std::runtime_error("Malformed index line in " + idx);
-        if (o + l > dataSize_) throw std::runtime_error("Index entry beyond the end of the data file in " + idx);
-        entries_.push_back(DBEntry{(uint32_t)k, (uint64_t)o, (uint64_t)l});
+    std::vector<char> text;
+    {
+        FILE *f = fopen(idx.c_str(), "r");
+        if (!f) throw std::runtime_error("Could not open index file " + idx + "!");
+        fclose(f);
+        append_file(idx, text);
     }
-    fclose(f);
-    std::stable_sort(entries_.begin(), entries_.end(), [](const DBEntry &a, const DBEntry &b) { return a.key < b.key; });
+    const size_t tn = text.size();
+    int nth = 1;
+#ifdef _OPENMP
+    nth = std::max(1, omp_get_max_threads());
+#endif
+    if (tn < (1u << 20)) nth = 1;
+    std::vector<std::vector<DBEntry>> part((size_t)nth);
+    std::vector<int> bad((size_t)nth, 0);
+#pragma omp parallel for num_threads(nth) schedule(static, 1)
+    for (int t = 0; t < nth; t++) {
+        size_t a = tn * (size_t)t / (size_t)nth, b = tn * (size_t)(t + 1) / (size_t)nth;
+        if (t > 0) { while (a < tn && text[a - 1] != '\n') a++; }
+        if (t + 1 < nth) { while (b < tn && text[b - 1] != '\n') b++; }
+        std::vector<DBEntry> &out = part[(size_t)t];
+        out.reserve((b - a) / 12 + 16);
+        const char *p = text.data() + a, *const end = text.data() + b;
+        while (p < end) {
+            const char *le = (const char *)memchr(p, '\n', (size_t)(end - p));
+            if (!le) le = end;
+            unsigned long long v[3] = {0, 0, 0};
+            int nf = 0;
+            const char *q = p;
+            while (nf < 3) {
+                while (q < le && (*q == ' ' || *q == '\t' || *q == '\r')) q++;
+                if (q >= le || *q < '0' || *q > '9') break;
+                unsigned long long x = 0;
+                while (q < le && *q >= '0' && *q <= '9') x = x * 10 + (unsigned long long)(*q++ - '0');
+                v[nf++] = x;
+            }
+            if (nf == 3) {
+                if (v[1] + v[2] > dataSize_) bad[(size_t)t] = 2;
+                out.push_back(DBEntry{(uint32_t)v[0], (uint64_t)v[1], (uint64_t)v[2]});
+            } else if (nf != 0) {
+                bad[(size_t)t] = 1;
+            }
+            p = le + 1;
+        }
+    }
+    for (int t = 0; t < nth; t++) {
+        if (bad[(size_t)t] == 1) throw std::runtime_error("Malformed index line in " + idx);
+        if (bad[(size_t)t] == 2) throw std::runtime_error("Index entry beyond the end of the data file in " + idx);
+    }
+    size_t total = 0;
+    for (const auto &v : part) total += v.size();
+    entries_.reserve(total);
+    for (const auto &v : part) entries_.insert(entries_.end(), v.begin(), v.end());
+    // DBs written by the reference's (and our) writers are already in key order with ascending offsets: both sorts are skipped then
+    bool keySorted = true, offSorted = true;
+    for (size_t i = 1; i < entries_.size() && keySorted; i++) keySorted = entries_[i - 1].key <= entries_[i].key;
+    if (!keySorted)
+        std::stable_sort(entries_.begin(), entries_.end(), [](const DBEntry &a, const DBEntry &b) { return a.key < b.key; });
     linear_.resize(entries_.size());
     for (size_t i = 0; i < entries_.size(); i++) linear_[i] = (uint32_t)i;
-    std::stable_sort(linear_.begin(), linear_.end(), [&](uint32_t a, uint32_t b) { return entries_[a].offset < entries_[b].offset; });
+    for (size_t i = 1; i < entries_.size() && offSorted; i++) offSorted = entries_[i - 1].offset < entries_[i].offset;
+    if (!offSorted)
+        std::stable_sort(linear_.begin(), linear_.end(), [&](uint32_t a, uint32_t b) { return entries_[a].offset < entries_[b].offset; });
     linearRank_.resize(entries_.size());
     for (size_t i = 0; i < linear_.size(); i++) linearRank_[linear_[i]] = (uint32_t)i;
     dbtype_ = 0;
@@ -95,14 +146,20 @@ size_t DBReader::linearIdOfKey(uint32_t key) const {
     return i == SIZE_MAX ? SIZE_MAX : (size_t)linearRank_[i];
 }
 
+DBWriter::~DBWriter() { if (fd_ >= 0) ::close(fd_); }
+
 void DBWriter::open(const std::string &name, int dbtype, int threads) {
     name_ = name;
     dbtype_ = dbtype;
     parts_.assign((size_t)(threads > 0 ? threads : 1), Part());
+    fileEnd_ = 0;
+    if (fd_ >= 0) ::close(fd_);
+    fd_ = -1;
     // a stale .dbtype would make the workflow believe the step is finished
     remove((name + ".dbtype").c_str());
 }
 
+// entries of a part are offsets into its unflushed buffer until flush() re-bases them
 void DBWriter::write(int thread, uint32_t key, const char *payload, size_t len) {
     Part &p = parts_[(size_t)thread];
     DBEntry e;
@@ -136,36 +193,103 @@ static inline char *put_u64(char *p, unsigned long long v) {
     return p;
 }
 
-void DBWriter::close() {
-    FILE *f = fopen(name_.c_str(), "wb");
-    if (!f) throw std::runtime_error("Could not open " + name_ + " for writing!");
-    std::vector<DBEntry> all;
-    uint64_t base = 0;
-    bool ok = true;
-    for (Part &p : parts_) {
-        if (!p.data.empty() && fwrite(p.data.data(), 1, p.data.size(), f) != p.data.size()) ok = false;
-        for (DBEntry e : p.idx) {
-            e.offset += base;
-            all.push_back(e);
-        }
-        base += p.data.size();
+// Data written so far by parts [first, first + count) goes to the file now (called between batches, e.g. from the formatter
+// thread of a GPU while the next batch is on the device): every part gets the next free stretch of the file, the parts are
+// written with one pwrite stream each, and their buffers are emptied.  The entries keep their final offsets in the index.
+void DBWriter::flush(int first, int count) {
+    std::lock_guard<std::mutex> lock(mu_);
+    if (fd_ < 0) {
+        fd_ = ::open(name_.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (fd_ < 0) throw std::runtime_error("Could not open " + name_ + " for writing!");
     }
-    if (fclose(f) != 0) ok = false;
+    const int last = std::min<int>((int)parts_.size(), first + count);
+    std::vector<uint64_t> base((size_t)std::max(0, last - first) + 1, fileEnd_);
+    for (int i = first; i < last; i++) base[(size_t)(i - first) + 1] = base[(size_t)(i - first)] + parts_[(size_t)i].data.size();
+    bool ok = true;
+#pragma omp parallel for schedule(dynamic, 1) reduction(&& : ok)
+    for (int i = first; i < last; i++) {
+        Part &pt = parts_[(size_t)i];
+        const std::vector<char> &d = pt.data;
+        const uint64_t at = base[(size_t)(i - first)];
+        size_t done = 0;
+        while (done < d.size()) {
+            const ssize_t w = pwrite(fd_, d.data() + done, std::min<size_t>(d.size() - done, (size_t)1 << 28), (off_t)(at + done));
+            if (w <= 0) { ok = false; break; }
+            done += (size_t)w;
+        }
+        for (size_t k = pt.flushed; k < pt.idx.size(); k++) pt.idx[k].offset += at;
+        pt.flushed = pt.idx.size();
+        pt.data.clear();
+    }
+    fileEnd_ = base.back();
     if (!ok) {
+        ::close(fd_);
+        fd_ = -1;
         remove(name_.c_str());
         throw std::runtime_error("Could not write to " + name_);
     }
-    std::stable_sort(all.begin(), all.end(), [](const DBEntry &a, const DBEntry &b) { return a.key < b.key; });
-    // index lines "key\toffset\tlength\n", formatted into one buffer (no stdio call per entry)
-    std::string ix;
-    ix.resize(all.size() * 64 + 64);
-    char *w = &ix[0];
-    for (const DBEntry &e : all) {
-        w = put_u64(w, e.key); *w++ = '\t';
-        w = put_u64(w, (unsigned long long)e.offset); *w++ = '\t';
-        w = put_u64(w, (unsigned long long)e.length); *w++ = '\n';
+}
+
+void DBWriter::close() {
+    flush(0, (int)parts_.size());
+    const size_t np = parts_.size();
+    size_t nEntries = 0;
+    for (size_t i = 0; i < np; i++) nEntries += parts_[i].idx.size();
+    {
+        std::lock_guard<std::mutex> lock(mu_);
+        const bool ok = (::close(fd_) == 0);
+        fd_ = -1;
+        if (!ok) {
+            remove(name_.c_str());
+            throw std::runtime_error("Could not write to " + name_);
+        }
     }
-    write_all(name_ + ".index", "wb", ix.data(), (size_t)(w - ix.data()));
+    std::vector<DBEntry> all;
+    all.reserve(nEntries);
+    for (size_t i = 0; i < np; i++) all.insert(all.end(), parts_[i].idx.begin(), parts_[i].idx.end());
+    bool sorted = true;
+    for (size_t i = 1; i < all.size() && sorted; i++) sorted = all[i - 1].key <= all[i].key;
+    if (!sorted) {
+#ifdef _OPENMP
+        __gnu_parallel::stable_sort(all.begin(), all.end(), [](const DBEntry &a, const DBEntry &b) { return a.key < b.key; });
+#else
+        std::stable_sort(all.begin(), all.end(), [](const DBEntry &a, const DBEntry &b) { return a.key < b.key; });
+#endif
+    }
+    // index lines "key\toffset\tlength\n": slices formatted by all threads, written back to back
+    int nth = 1;
+#ifdef _OPENMP
+    nth = std::max(1, omp_get_max_threads());
+#endif
+    if (all.size() < 65536) nth = 1;
+    std::vector<std::string> ixs((size_t)nth);
+#pragma omp parallel for num_threads(nth) schedule(static, 1)
+    for (int t = 0; t < nth; t++) {
+        const size_t a = all.size() * (size_t)t / (size_t)nth, b = all.size() * (size_t)(t + 1) / (size_t)nth;
+        std::string &ix = ixs[(size_t)t];
+        ix.resize((b - a) * 64 + 64);
+        char *w = &ix[0];
+        for (size_t i = a; i < b; i++) {
+            const DBEntry &e = all[i];
+            w = put_u64(w, e.key); *w++ = '\t';
+            w = put_u64(w, (unsigned long long)e.offset); *w++ = '\t';
+            w = put_u64(w, (unsigned long long)e.length); *w++ = '\n';
+        }
+        ix.resize((size_t)(w - ix.data()));
+    }
+    {
+        const std::string path = name_ + ".index";
+        FILE *f = fopen(path.c_str(), "wb");
+        if (!f) throw std::runtime_error("Could not open " + path + " for writing!");
+        bool wok = true;
+        for (const std::string &ix : ixs)
+            if (!ix.empty() && fwrite(ix.data(), 1, ix.size(), f) != ix.size()) wok = false;
+        if (fclose(f) != 0) wok = false;
+        if (!wok) {
+            remove(path.c_str());
+            throw std::runtime_error("Could not write to " + path);
+        }
+    }
     const unsigned char b[4] = {(unsigned char)(dbtype_ & 0xFF), (unsigned char)((dbtype_ >> 8) & 0xFF), (unsigned char)((dbtype_ >> 16) & 0xFF),
                                 (unsigned char)((dbtype_ >> 24) & 0xFF)};
     const std::string tmp = name_ + ".dbtype.tmp";

@@ -10,6 +10,7 @@
 
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -57,13 +58,21 @@ public:
     // (the workflow scripts test for it: blastp.sh:31,39)
     void open(const std::string &name, int dbtype, int threads);
     void write(int thread, uint32_t key, const char *payload, size_t len);   // payload without the NUL
+    // writes what parts [first, first + count) hold to the data file now and empties their buffers; no write() to those parts
+    // may run concurrently.  Lets a long search put its output on disk batch by batch, overlapped with the GPU work.
+    void flush(int first, int count);
     void close();
+    ~DBWriter();
 
 private:
     struct Part {
-        std::vector<char> data;
+        std::vector<char> data;        // entries not yet in the file
         std::vector<DBEntry> idx;
+        size_t flushed = 0;            // idx[0 .. flushed) carry file offsets, the rest offsets into data
     };
+    std::mutex mu_;
+    int fd_ = -1;
+    uint64_t fileEnd_ = 0;
     std::string name_;
     int dbtype_ = 0;
     std::vector<Part> parts_;

@@ -37,6 +37,7 @@
 #include <algorithm>
 #include <memory>
 #include <atomic>
+#include <chrono>
 #include <stdexcept>
 #include <exception>
 #include <functional>
@@ -50,6 +51,7 @@
 
 #include "../../../include/spb200.h"
 #include "db_io.h"
+#include "fastfmt.h"
 #include "setscore.h"
 #include "submat.h"
 
@@ -85,6 +87,7 @@ struct Params {
     int maxSeqLen = 65535;
     int device = 0, binSize = 0, byteLanes = 32, wordLanes = 16;
     int gpus = 1;              // search / predictmatch: devices device .. device + gpus - 1, k-mer table sharded over them (index split)
+    int lanes = 2;             // search / predictmatch: contexts per device that share its index and overlap their batches (one host thread each)
     int oversubscribe = 0;     // 1: with fewer devices than --gpus, several shard contexts share a device (same code path; tests)
     std::string gumbel, gumbelNucl;
     long batch = 250000;       // frames per GPU pass: formatting of batch k overlaps the kernels of batch k+1 (1 M spacers: 4.2 -> 3.7 s)
@@ -124,7 +127,7 @@ std::vector<FlagDef> flag_table(Params &p) {
         {"--perform-nucl-aln", 0, &p.performNuclAln}, {"--tax-fdr", 4, nullptr}, {"--remove-tmp-files", 4, nullptr},
         // spb200-specific
         {"--keep-intermediate", 0, &p.keepIntermediate},
-        {"--device", 0, &p.device}, {"--gpus", 0, &p.gpus}, {"--oversubscribe", 0, &p.oversubscribe}, {"--bin-size", 0, &p.binSize}, {"--byte-lanes", 0, &p.byteLanes}, {"--word-lanes", 0, &p.wordLanes},
+        {"--device", 0, &p.device}, {"--gpus", 0, &p.gpus}, {"--lanes", 0, &p.lanes}, {"--oversubscribe", 0, &p.oversubscribe}, {"--bin-size", 0, &p.binSize}, {"--byte-lanes", 0, &p.byteLanes}, {"--word-lanes", 0, &p.wordLanes},
         {"--gumbel", 3, &p.gumbel}, {"--gumbel-nucl", 3, &p.gumbelNucl}, {"--batch", 0, nullptr},
     };
 }
@@ -280,7 +283,7 @@ size_t seqid_to_buffer(float seqId, char *b) {
     *b++ = '.';
     if (seqId < 0.10) *b++ = '0';
     if (seqId < 0.01) *b++ = '0';
-    b += sprintf(b, "%d", (int)(seqId * 1000));
+    b = put_int(b, (int)(seqId * 1000));
     return (size_t)(b - s);
 }
 
@@ -289,28 +292,41 @@ void compress_cigar(const char *ops, uint32_t n, std::string &out) {
     char state = 'M';
     unsigned count = 0;
     char tmp[16];
+    auto run = [&]() {
+        char *w = put_uint(tmp, count);
+        *w++ = state;
+        out.append(tmp, (size_t)(w - tmp));
+    };
     for (uint32_t i = 0; i < n; i++) {
         if (ops[i] != state) {
-            out.append(tmp, (size_t)sprintf(tmp, "%u%c", count, state));
+            run();
             state = ops[i];
             count = 1;
         } else {
             count++;
         }
     }
-    out.append(tmp, (size_t)sprintf(tmp, "%u%c", count, state));
+    run();
 }
 
 struct Engine {
     spb_ctx *ctx = nullptr;
     SubMat seed, ungapped, align;
     ~Engine() { if (ctx) spb_ctx_destroy(ctx); }
-    void open(const Params &p) {
+    // host part (matrices) and device part (context) separately: a search reads and masks its DBs while the CUDA context
+    // of every device comes up in the background
+    void load_matrices(const Params &p) {
         seed.load(p.seedSubMat, 8.0, -0.2);        // Prefiltering.cpp:64
         ungapped.load(p.subMat, 2.0, -0.2);        // Prefiltering.cpp:65
         align.load(p.subMat, 2.0, p.scoreBias);    // Alignment.cpp:159
+    }
+    void create_context(const Params &p) {
         check(spb_ctx_create(p.device, &ctx), "spb_ctx_create");
         check(spb_set_matrices(ctx, seed.sub, seed.pback, ungapped.sub, align.sub, align.pback), "spb_set_matrices");
+    }
+    void open(const Params &p) {
+        load_matrices(p);
+        create_context(p);
     }
 };
 
@@ -332,6 +348,22 @@ void log_line(const Params &p, const char *fmt, ...) {
 // in ~20 ms (index.cu) -- faster than reading 1.7 GB back -- so the cache holds what is expensive on the HOST side: the
 // tantan-masked residues (SEQINDEXDATA of the reference's index) plus the parameters they depend on.  Layout of
 // <targetDB>.spbidx: IdxHeader, keys u32[T], offsets u64[T+1], masked residues u8[N].
+// phase wall clock of the host binary on stderr (SPB_TIMING=1; development aid)
+struct PhaseClock;
+extern PhaseClock g_clock;
+struct PhaseClock {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    bool on = getenv("SPB_TIMING") != nullptr;
+    void mark(const char *what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[spb200 timing] %-28s %8.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
+PhaseClock g_clock;
+
 struct IdxHeader {
     char magic[8];            // "SPBIDX1"
     uint32_t version, mask, maskLower, pad;
@@ -460,6 +492,7 @@ void check_search_params(const Params &p) {
     if (p.split > 1) throw Fail("--split > 1 (the reference's lossy target split) is not implemented; spread one DB over several GPUs "
                                 "with --gpus N (k-mer table sharded over the devices, unsplit result)");
     if (p.gpus < 1 || p.gpus > 8) throw Fail("--gpus must be 1..8");
+    if (p.lanes < 1 || p.lanes > 8) throw Fail("--lanes must be 1..8");
     if (p.covThr != 0 || p.addSelf != 0) throw Fail("coverage thresholds / --add-self-matches are not supported on this path");
 }
 
@@ -519,7 +552,10 @@ int run_prefilter(int argc, const char **argv) {
                 buf.clear();
                 for (uint64_t h = r->offsets[i]; h < r->offsets[i + 1]; h++) {
                     const spb_hit &x = r->hits[h];   // id -> DB key (Prefiltering.cpp:827-829)
-                    buf.append(tmp, (size_t)sprintf(tmp, "%u\t%d\t%d\n", T.keys[x.id], x.score, x.diag));
+                    char *w = put_uint(tmp, T.keys[x.id]); *w++ = '\t';
+                    w = put_int(w, x.score); *w++ = '\t';
+                    w = put_int(w, x.diag); *w++ = '\n';
+                    buf.append(tmp, (size_t)(w - tmp));
                 }
                 out.write(th, Q.keys[b0 + (size_t)i], buf.data(), buf.size());
             }
@@ -579,10 +615,17 @@ void format_alignment_rows(const Params &p, const spb_align_result *r, const Seq
             for (uint64_t k = r->offsets[i]; k < r->offsets[i + 1]; k++) {
                 const spb_aln &a = r->rows[k];
                 char *w = tmp;
-                w += sprintf(w, "%u\t%d\t", T.keys[a.target], a.bits);
+                w = put_uint(w, T.keys[a.target]); *w++ = '\t';
+                w = put_int(w, a.bits); *w++ = '\t';
                 w += seqid_to_buffer(a.seq_id, w);
-                w += sprintf(w, "\t%.3E\t%d\t%d\t%d\t%d\t%d\t%d\t", a.eval, a.q_start, a.q_end, qLen, a.t_start, a.t_end,
-                             (int)(T.off[a.target + 1] - T.off[a.target]));
+                *w++ = '\t';
+                w = put_e3(w, a.eval); *w++ = '\t';
+                w = put_int(w, a.q_start); *w++ = '\t';
+                w = put_int(w, a.q_end); *w++ = '\t';
+                w = put_int(w, qLen); *w++ = '\t';
+                w = put_int(w, a.t_start); *w++ = '\t';
+                w = put_int(w, a.t_end); *w++ = '\t';
+                w = put_int(w, (int)(T.off[a.target + 1] - T.off[a.target])); *w++ = '\t';
                 buf.append(tmp, (size_t)(w - tmp));
                 cig.clear();
                 if (a.cigar_len) compress_cigar(r->cigar_ops + a.cigar_off, a.cigar_len, cig);
@@ -852,32 +895,58 @@ int run_combineprotnuclaln(int argc, const char **argv) {
 // re-scored on the resident <db>_nucl_orf entries (spb_nucl_rescore_resident) and combined like combineprotnuclaln; the sink
 // then receives the combined rows, and extra(thread, key, protein rows, nucleotide rows), if given, the two intermediates
 typedef std::function<void(int, uint32_t, const std::string &, const std::string &)> NuclExtraSink;
+// batchDone(first sink thread, threads): called by a GPU's formatter thread after the rows of a batch went through the sink
+typedef std::function<void(int, int)> BatchDone;
 template <class Sink>
 void search_dbs(const Params &p, const std::string &qName, const std::string &tName, Sink sink, bool nucl = false,
-                const NuclExtraSink *extra = nullptr) {
+                const NuclExtraSink *extra = nullptr, const BatchDone *batchDone = nullptr) {
     // --gpus G: one context + one host thread per device.  Every device gets the whole target set for alignment (53 MB at
     // GenBank-phage size) but only its k-mer range of the index table (spb_index_shard); the ranges of the other devices are
     // read through NVLink peer memory by the lookup kernel.  Query batches are handed out to the devices one by one; rows
     // are the unsplit rows by construction (Prefiltering.cpp:258-362,559-643 / Alignment.cpp:226-249 are the reference's split).
     const int G = std::max(1, p.gpus);
-    const int nDev = spb_device_count();
-    if (G > 1 && p.device + G > nDev && !p.oversubscribe)
-        throw Fail("--gpus " + std::to_string(G) + " from device " + std::to_string(p.device) + ": only " + std::to_string(nDev) +
-                   " CUDA device(s) visible (--oversubscribe 1 places several shard contexts on one device)");
     std::vector<std::unique_ptr<Engine>> eng((size_t)G);
     for (int g = 0; g < G; g++) {
-        Params pg = p;
-        pg.device = (p.device + g < nDev || nDev == 0) ? p.device + g : p.device + g % std::max(1, nDev - p.device);
         eng[(size_t)g].reset(new Engine());
-        eng[(size_t)g]->open(pg);
+        eng[(size_t)g]->load_matrices(p);
     }
+    // The CUDA driver and the context of every device come up in the background (0.6 - 1 s) while this thread reads, encodes and
+    // masks the DBs -- none of that needs the device.
+    std::exception_ptr ctxErr;
+    std::thread ctxThread([&]() {
+        try {
+            const int nDev = spb_device_count();
+            if (G > 1 && p.device + G > nDev && !p.oversubscribe)
+                throw Fail("--gpus " + std::to_string(G) + " from device " + std::to_string(p.device) + ": only " + std::to_string(nDev) +
+                           " CUDA device(s) visible (--oversubscribe 1 places several shard contexts on one device)");
+            std::vector<std::thread> th;
+            std::vector<std::exception_ptr> err((size_t)G);
+            for (int g = 0; g < G; g++) {
+                Params pg = p;
+                pg.device = (p.device + g < nDev || nDev == 0) ? p.device + g : p.device + g % std::max(1, nDev - p.device);
+                th.emplace_back([&, g, pg]() { try { eng[(size_t)g]->create_context(pg); } catch (...) { err[(size_t)g] = std::current_exception(); } });
+            }
+            for (std::thread &x : th) x.join();
+            for (std::exception_ptr &e : err) if (e) std::rethrow_exception(e);
+        } catch (...) {
+            ctxErr = std::current_exception();
+        }
+    });
+    struct JoinGuardCtx {       // an exception while the DBs are read must not leave the context thread running
+        std::thread &t;
+        ~JoinGuardCtx() { if (t.joinable()) t.join(); }
+    } joinCtx{ctxThread};
     Engine &E0 = *eng[0];
+    PhaseClock &pc = g_clock;
+    pc.mark("start-up");
     DBReader qdb, tdb;
     qdb.open(qName);
     tdb.open(tName);
+    pc.mark("open DBs");
     SeqSet Q, T;
     load_sequences(qdb, E0.seed, Q);
     load_sequences(tdb, E0.seed, T);
+    pc.mark("encode sequences");
     check_seq_len(p, Q.off, "query");
     check_seq_len(p, T.off, "target");
     NuclSet QN, TN;
@@ -892,6 +961,10 @@ void search_dbs(const Params &p, const std::string &qName, const std::string &tN
     uint64_t nMasked = 0;
     bool cached = false;
     if (!p.exhaustive) cached = masked_targets(E0, p, T, tName, tdb.dataSize(), masked, &nMasked);
+    pc.mark("tantan");
+    ctxThread.join();
+    if (ctxErr) std::rethrow_exception(ctxErr);
+    pc.mark("(contexts ready)");
     std::vector<std::exception_ptr> errs((size_t)G);
     auto run_on_all = [&](const std::function<void(int)> &f) {
         std::vector<std::thread> th;
@@ -914,11 +987,29 @@ void search_dbs(const Params &p, const std::string &qName, const std::string &tN
     });
     masked.clear();
     masked.shrink_to_fit();
+    pc.mark("index + targets");
     if (G > 1 && !p.exhaustive) {
         for (int g = 0; g < G; g++)
             for (int h = 0; h < G; h++)
                 if (h != g) check(spb_index_shard_attach_ctx(eng[(size_t)g]->ctx, h, eng[(size_t)h]->ctx), "spb_index_shard_attach_ctx");
         log_line(p, "Index table: k-mer ranges sharded over %d GPUs (devices %d..%d), peer loads over NVLink", G, p.device, p.device + G - 1);
+    }
+    // Lanes: further contexts on every device that borrow its index / targets (spb_ctx_create_lane) and are driven by their own
+    // host thread, so that upload, host-side sizing, kernels and read-back of different batches overlap on the device.
+    const int L = std::max(1, p.lanes), W = G * L;
+    struct Lanes {
+        std::vector<spb_ctx *> ctx;
+        ~Lanes() { for (spb_ctx *c : ctx) if (c) spb_ctx_destroy(c); }
+    } lanes;
+    std::vector<spb_ctx *> worker((size_t)W, nullptr);      // worker w = g * L + lane
+    for (int g = 0; g < G; g++) {
+        worker[(size_t)g * L] = eng[(size_t)g]->ctx;
+        for (int l = 1; l < L; l++) {
+            spb_ctx *c = nullptr;
+            check(spb_ctx_create_lane(eng[(size_t)g]->ctx, &c), "spb_ctx_create_lane");
+            lanes.ctx.push_back(c);
+            worker[(size_t)g * L + l] = c;
+        }
     }
     spb_prefilter_params pp;
     pp.kmer_thr = kmerThr;
@@ -931,15 +1022,24 @@ void search_dbs(const Params &p, const std::string &qName, const std::string &tN
     spb_align_params ap;
     fill_align_params(p, E0, tdb.aminoAcidDBSize(), &ap);
     const size_t nq = Q.keys.size();
-    // frames per GPU pass; with several devices every one of them should see a few batches
-    const size_t batch = G > 1 ? std::min<size_t>((size_t)p.batch, std::max<size_t>(4096, (nq + 2 * (size_t)G - 1) / (2 * (size_t)G))) : (size_t)p.batch;
+    // frames per GPU pass; with several workers every one of them should see a few batches
+    const size_t batch = W > 1 ? std::min<size_t>((size_t)p.batch, std::max<size_t>(4096, (nq + 2 * (size_t)W - 1) / (2 * (size_t)W))) : (size_t)p.batch;
     const size_t nBatches = (nq + batch - 1) / batch;
     std::atomic<size_t> nextBatch(0);
     Params pf = p;                         // formatter teams share the host threads
-    pf.threads = std::max(1, p.threads / G);
-    run_on_all([&](int g) {
-        Engine &E = *eng[(size_t)g];
-        const int thBase = g * pf.threads;
+    pf.threads = std::max(1, p.threads / W);
+    std::vector<std::exception_ptr> werrs((size_t)W);
+    auto run_on_workers = [&](const std::function<void(int)> &f) {
+        std::vector<std::thread> th;
+        for (int w = 0; w < W; w++)
+            th.emplace_back([&, w]() { try { f(w); } catch (...) { werrs[(size_t)w] = std::current_exception(); } });
+        for (std::thread &t : th) t.join();
+        for (std::exception_ptr &e : werrs)
+            if (e) { std::exception_ptr x = e; e = nullptr; std::rethrow_exception(x); }
+    };
+    run_on_workers([&](int w) {
+        struct { spb_ctx *ctx; } E{worker[(size_t)w]};
+        const int thBase = w * pf.threads;
         std::thread formatter;
         std::exception_ptr fmtError;
         spb_align_result *prevR = nullptr;
@@ -1001,6 +1101,7 @@ void search_dbs(const Params &p, const std::string &qName, const std::string &tN
                     check(spb_align_fetch_wait(r), "spb_align_fetch_wait");
                     if (!nucl) {
                         format_alignment_rows(pf, r, Q, b0, T, [&](int th, size_t i, const std::string &buf) { sink(thBase + th, Q.keys[b0 + i], buf); });
+                        if (batchDone) (*batchDone)(thBase, pf.threads);
                     } else {
                         std::string err;
                         format_alignment_rows(pf, r, Q, b0, T, [&](int th, size_t i, const std::string &prot) {
@@ -1020,6 +1121,7 @@ void search_dbs(const Params &p, const std::string &qName, const std::string &tN
                             sink(thBase + th, Q.keys[b0 + i], comb);
                         });
                         if (!err.empty()) throw Fail(err);
+                        if (batchDone) (*batchDone)(thBase, pf.threads);
                     }
                 } catch (...) {
                     fmtError = std::current_exception();
@@ -1028,6 +1130,7 @@ void search_dbs(const Params &p, const std::string &qName, const std::string &tN
         }
         finish_previous();
     });
+    pc.mark("batches (GPU + formatting)");
 }
 
 // spb200 extractframes <nuclSeqDB> <outDB> [--min-length 9 --threads N]
@@ -1157,9 +1260,14 @@ int run_search(int argc, const char **argv) {
     check_search_params(p);
     check_align_params(p);
     DBWriter out;
-    out.open(p.db[2], DBTYPE_ALIGNMENT_RES, std::max(p.threads, p.gpus));    // sink thread ids: gpu * (threads / gpus) + team thread
-    search_dbs(p, p.db[0], p.db[1], [&](int th, uint32_t key, const std::string &buf) { out.write(th, key, buf.data(), buf.size()); });
+    out.open(p.db[2], DBTYPE_ALIGNMENT_RES, std::max(p.threads, p.gpus * p.lanes));    // sink thread ids: worker * (threads / workers) + team thread
+    // the rows of a batch go to disk as soon as they are formatted, while the next batch is on the device
+    const BatchDone flush = [&](int first, int count) { out.flush(first, count); };
+    search_dbs(p, p.db[0], p.db[1], [&](int th, uint32_t key, const std::string &buf) { out.write(th, key, buf.data(), buf.size()); }, false,
+               nullptr, &flush);
+    g_clock.mark("(join)");
     out.close();
+    g_clock.mark("write DB");
     return 0;
 }
 
@@ -1359,31 +1467,36 @@ int run_showparams(int argc, const char **argv) {
 }  // namespace
 
 int main(int argc, const char **argv) {
+    pow10_ld(0);      // the table of put_e3 is built before any formatter thread exists
     if (argc < 2) {
         fprintf(stderr, "spb200 (%s): prefilter | align | search | createindex | extractframes | besthitperset | mergeresultsbyset | combinescore | filtermatchbyfdr | predictmatch | proteinaln2nucl | combineprotnuclaln | dumpmatrix | dbcopy | showparams\n", spb_version());
         return 1;
     }
     const std::string cmd = argv[1];
+    int rc = 1;
     try {
-        if (cmd == "prefilter") return run_prefilter(argc, argv);
-        if (cmd == "align") return run_align(argc, argv);
-        if (cmd == "search") return run_search(argc, argv);
-        if (cmd == "createindex") return run_createindex(argc, argv);
-        if (cmd == "extractframes") return run_extractframes(argc, argv);
-        if (cmd == "besthitperset") return run_besthitperset(argc, argv);
-        if (cmd == "mergeresultsbyset") return run_mergeresultsbyset(argc, argv);
-        if (cmd == "combinescore") return run_combinescore(argc, argv);
-        if (cmd == "filtermatchbyfdr") return run_filtermatchbyfdr(argc, argv);
-        if (cmd == "predictmatch") return run_predictmatch(argc, argv);
-        if (cmd == "proteinaln2nucl") return run_proteinaln2nucl(argc, argv);
-        if (cmd == "combineprotnuclaln") return run_combineprotnuclaln(argc, argv);
-        if (cmd == "dumpmatrix") return run_dumpmatrix(argc, argv);
-        if (cmd == "dbcopy") return run_dbcopy(argc, argv);
-        if (cmd == "showparams") return run_showparams(argc, argv);
-        fprintf(stderr, "Invalid Command: %s\n", cmd.c_str());
-        return 1;
+        if (cmd == "prefilter") rc = run_prefilter(argc, argv);
+        else if (cmd == "align") rc = run_align(argc, argv);
+        else if (cmd == "search") rc = run_search(argc, argv);
+        else if (cmd == "createindex") rc = run_createindex(argc, argv);
+        else if (cmd == "extractframes") rc = run_extractframes(argc, argv);
+        else if (cmd == "besthitperset") rc = run_besthitperset(argc, argv);
+        else if (cmd == "mergeresultsbyset") rc = run_mergeresultsbyset(argc, argv);
+        else if (cmd == "combinescore") rc = run_combinescore(argc, argv);
+        else if (cmd == "filtermatchbyfdr") rc = run_filtermatchbyfdr(argc, argv);
+        else if (cmd == "predictmatch") rc = run_predictmatch(argc, argv);
+        else if (cmd == "proteinaln2nucl") rc = run_proteinaln2nucl(argc, argv);
+        else if (cmd == "combineprotnuclaln") rc = run_combineprotnuclaln(argc, argv);
+        else if (cmd == "dumpmatrix") rc = run_dumpmatrix(argc, argv);
+        else if (cmd == "dbcopy") rc = run_dbcopy(argc, argv);
+        else if (cmd == "showparams") rc = run_showparams(argc, argv);
+        else {
+            fprintf(stderr, "Invalid Command: %s\n", cmd.c_str());
+            return 1;
+        }
     } catch (const std::exception &e) {
         fprintf(stderr, "%s\n", e.what());
         return 1;
     }
+    return rc;
 }

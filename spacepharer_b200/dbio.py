@@ -84,6 +84,28 @@ def write_sequence_db(name, keys, seqs):
 DBTYPE_GENERIC_DB = 12
 
 
+def write_sequence_db_arrays(name, res, off):
+    """Sequence DB (keys 0..n-1, entries `residues\\n\\0`) straight from the encoded arrays (residues uint8, offsets [n+1]):
+    vectorised, for the million-entry DBs of the benchmarks (write_sequence_db takes 10 s per million entries)."""
+    lut = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWYX", dtype=np.uint8)
+    off = np.asarray(off, dtype=np.int64)
+    n = len(off) - 1
+    lens = np.diff(off)
+    out = np.empty(int(off[-1]) + 2 * n, dtype=np.uint8)
+    seq_of = np.repeat(np.arange(n, dtype=np.int64), lens)
+    out[np.arange(int(off[-1]), dtype=np.int64) + 2 * seq_of] = lut[np.asarray(res)[: int(off[-1])]]
+    ends = off[1:] + 2 * np.arange(n, dtype=np.int64)
+    out[ends] = 10
+    out[ends + 1] = 0
+    with open(name, "wb") as f:
+        f.write(out.tobytes())
+    starts = off[:-1] + 2 * np.arange(n, dtype=np.int64)
+    import pandas as pd
+    pd.DataFrame({"k": np.arange(n, dtype=np.int64), "o": starts, "l": lens + 2}).to_csv(name + ".index", sep="\t", header=False, index=False)
+    with open(name + ".dbtype", "wb") as f:
+        f.write(struct.pack("<i", DBTYPE_AMINO_ACIDS))
+
+
 def write_set_db(name, res, off, set_of):
     """A set database like `createsetdb` leaves it for the search and the set-level stages (data/createsetdb.sh:115-160):
     the amino-acid sequence DB <name> (key = sequence index) plus <name>_member_to_set (sequence -> set key),

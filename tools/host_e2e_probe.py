@@ -14,9 +14,11 @@ for lst in (PREF_FLAGS, ALN_FLAGS):
     for i in range(0, len(lst), 2):
         if lst[i] not in seen:
             seen.add(lst[i]); merged += [lst[i], threads if lst[i] == "--threads" else lst[i + 1]]
-for extra in ([], ["--batch", "250000"]):
+for extra in (["--batch", "250000", "--lanes", "1"], ["--batch", "250000", "--lanes", "2"], ["--batch", "250000", "--lanes", "1"], ["--batch", "250000", "--lanes", "2"]):
     t0 = time.time()
-    r = subprocess.run([BIN, "search", w + "/queries", w + "/targets", w + "/aln"] + merged + extra, capture_output=True, text=True)
+    r = subprocess.run([BIN, "search", w + "/queries", w + "/targets", w + "/aln"] + merged + extra, capture_output=True, text=True,
+                       env=dict(os.environ, SPB_TIMING="1"))
     dt = time.time() - t0
     print("spb200 search %s: %.2f s wall (%d threads), rc %d, %.0f frames/s from disk to disk" % (" ".join(extra) or "(one 1 M-frame batch per GPU pass)", dt, int(threads), r.returncode, nq / dt))
     print("  " + "\n  ".join(l for l in r.stdout.split("\n") if l.strip())[:1200])
+    print("  " + "\n  ".join(l for l in r.stderr.split("\n") if "timing" in l))
