@@ -581,7 +581,6 @@ def run_ours(args):
 
     strong = strong_leg(eng, args.split_mode, n_lanes)
     parity = None if args.no_parity else parity_check(eng)
-    d2d = disk_to_disk(args, tres, toff, sq, so) if (world == 1 and args.strong_spacers > 0 and not args.no_disk_to_disk) else None
 
     # ---- the other way to spread the search over the GPUs, N > 1: value leg, strong-scaling leg and parity of that mode ----
     # main mode "query" (full index per GPU): the k-mer table sharded over groups of GPUs and gathered through NVLink peer memory
@@ -607,6 +606,11 @@ def run_ours(args):
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
     dev_ms, e2e_ms, exh_ms, single_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     q_total = eng.queries_per_step(Q)
+    eng_group = eng.shard_group
+    # the engine's contexts are released before the host binary runs as its own process on the same device
+    eng.close()
+    torch.cuda.empty_cache()
+    d2d = disk_to_disk(args, tres, toff, sq, so) if (world == 1 and args.strong_spacers > 0 and not args.no_disk_to_disk) else None
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -620,7 +624,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args, Q, T, db_res, args.spacers * (world if weak else 1)), "queries_per_step": q_total,
                        "split_mode": args.split_mode if world > 1 else "none",
-                       "shard_group": (eng.shard_group if (world > 1 and args.split_mode == "index") else None),
+                       "shard_group": (eng_group if (world > 1 and args.split_mode == "index") else None),
                        "lanes": n_lanes,
                        "l2": "256 MB memset on the lane's stream before every step (inside the timed span with lanes > 1, outside the "
                              "per-step events of the single-lane segment); index %.2f GB > L2" % (ist["bytes_device"] / 1e9),
@@ -657,7 +661,7 @@ def run_ours(args):
             "clocks": clocks,
             "wall_s_value_leg": wall_value,
         }
-        main_group = eng.shard_group if (world > 1 and args.split_mode == "index") else 0
+        main_group = eng_group if (world > 1 and args.split_mode == "index") else 0
         if strong:
             line["strong_scaling"] = strong_block(strong, args.split_mode, main_group)
         if parity:
@@ -698,7 +702,6 @@ def run_ours(args):
             line["cpu_baseline"] = {k: r[k] for k in r if k in ("value", "unit", "cores", "kind", "sample", "prefilter_ms", "align_ms",
                                                                 "index_build_s")}
         emit(line)
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 

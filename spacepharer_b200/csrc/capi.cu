@@ -133,7 +133,7 @@ void spb_ctx_destroy(spb_ctx *c) {
                            &c->d_pairoff, &c->d_pairT, &c->d_pairQ, &c->d_pairout, &c->d_acc, &c->d_cig, &c->d_rows, &c->d_rowoff, &c->d_st_rows, &c->d_st_cig, &c->d_st_off, &c->d_tnt, &c->d_tntoff, &c->d_tntsc, &c->d_qnt, &c->d_qntoff, &c->d_qntsc, &c->d_nrows,
                            &c->s_a, &c->s_b, &c->s_c, &c->s_d, &c->s_e, &c->s_f, &c->s_g, &c->s_h, &c->s_i, &c->s_j,
                            &c->s_k, &c->s_l, &c->s_m, &c->s_n, &c->s_o, &c->s_p, &c->s_q, &c->s_cub,
-                           &c->p_recs, &c->p_ctab, &c->p_ccnt, &c->p_harena, &c->p_meta, &c->p_retry, &c->p_team2};
+                           &c->p_recs, &c->p_ctab, &c->p_ccnt, &c->p_harena, &c->p_meta, &c->p_heavy, &c->p_retry, &c->p_team2};
     for (spb::DevBuf *b : bufs) b->release();
     for (void *m : c->ipc_mapped) cudaIpcCloseMemHandle(m);
     c->ipc_mapped.clear();

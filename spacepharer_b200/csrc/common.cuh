@@ -201,6 +201,7 @@ struct spb_ctx {
     spb::DevBuf p_ccnt;           // uint2[chunkCap] (first hit record, hits) per chunk
     spb::DevBuf p_harena;         // u64[] hit records, chunk after chunk
     spb::DevBuf p_meta;           // QMeta[Q]
+    spb::DevBuf p_heavy;          // HeavyQ[]: window tables of the queries whose slot records are filled chunk by chunk
     spb::DevBuf p_retry;          // u32[Q] queries of the next round
     spb::DevBuf p_team2;          // u32[Q] queries the warp-per-query bookkeeping hands to the CTA launch
     cudaStream_t aux_stream = nullptr;   // the CTA-per-query bookkeeping runs beside the warp-per-query one

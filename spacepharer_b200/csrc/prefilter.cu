@@ -82,6 +82,12 @@ struct PrefArgs {
     uint64_t *hitArena;      // [hitArenaCap] hit records, chunk after chunk: id << 32 | k << 16 | 16-bit diagonal
     uint32_t hitArenaCap;
     struct QMeta *meta;      // [Q]
+    struct HeavyQ *heavyTab; // window tables of the heavy queries of the tile
+    unsigned int *heavyCount;
+    uint32_t *heavyItems;    // work items of expand_heavy_kernel: heavy query << 8 | chunk group
+    unsigned int *heavyItemCount;
+    uint32_t heavyItemCap;
+    uint32_t heavyK, heavyCap;   // queries with more similar k-mers than heavyK are filled by expand_heavy_kernel
     unsigned int *chunkCursor;   // chunks allocated in this tile
     uint32_t chunkCap;
     uint64_t *hitScratch;    // [teams in the grid][2 * hitCap + 2 * FCAP] survivor list | grouped by target bucket | per-target winners
@@ -712,10 +718,23 @@ struct QMeta {               // per query, expand -> bookkeeping
     uint32_t chunk0, nChunks, K;
     uint32_t nHits;          // classify_kernel: hits of the query = sum of its chunk counts
     int32_t minCorr;
+    uint32_t heavy;          // 1 + index of the query's window table (HeavyQ) when its slot records are filled chunk by chunk, else 0
     signed char corr[PW_MAXL];
 };
 
+// Window table of a query with very many similar k-mers (K is heavy-tailed: median 340, mean 1076, max 38 161 per frame): its
+// slot records are not written by the warp that counted them -- that one warp would still be filling long after every
+// other query of the tile is done -- but chunk by chunk by expand_heavy_kernel, one warp per 256-slot chunk.
+struct HeavyQ {
+    uint32_t kstart[PW_MAXL];            // slots before window w (kstart[nWin] = K)
+    uint16_t x1[PW_MAXL], x2[PW_MAXL];
+    short thr[PW_MAXL], best1[PW_MAXL], cut1[PW_MAXL];
+    uint32_t nWin, chunk0, K;
+};
+#define PX_HEAVY_GROUP 8u     // chunks per work item of expand_heavy_kernel
+
 struct ExpSmem {
+    uint32_t kst[PW_MAXL + 1];            // slots before every window
     float cb[PW_MAXL];
     uint16_t x1[PW_MAXL], x2[PW_MAXL];   // first / second 3-mer of every window
     short thr[PW_MAXL];
@@ -729,13 +748,26 @@ __device__ __noinline__ int warp_incl_scan_ool(int v) { return warp_incl_scan(v)
 // One window of a query: the rectangles of its similar-k-mer list, 32 outer score values per round (lane = score value,
 // descending = ascending outer rank).  EXPAND = false: returns the number of k-mers.  EXPAND = true: writes the slot records
 // from `dst` on (dst[k] for the k-th k-mer of the window) and returns the same count.
+// The records of a round are filled FLAT: the lanes that own a rectangle leave its descriptor (first slot, first outer rank,
+// inner count, reciprocal) in the warp's shared-memory table, then lane l takes slots l, l + 32, ... of the whole round and
+// walks the table forward to the rectangle its slot lies in -- every lane is busy whatever the rectangle sizes (they average
+// 50 slots, a quarter of them fewer than 12), and the two slots of a trip keep four independent row loads in flight.
+struct ExpRound {
+    uint4 desc[32];          // (first slot, first outer rank, inner count, magic reciprocal) per rectangle of the round
+    uint32_t end[32];        // one past its last slot
+};
+
 template <bool EXPAND>
 __device__ __forceinline__ uint32_t window_kmers(const uint32_t *__restrict__ row3, const uint16_t *__restrict__ cnt3, int x1, int x2,
-                                                 int thr, int best1, int cut1, uint32_t w, uint32_t *dst) {
+                                                 int thr, int best1, int cut1, uint32_t w, uint32_t *dst, ExpRound *R,
+                                                 uint32_t lo = 0u, uint32_t hi = 0xFFFFFFFFu) {     // only slots [lo, hi) of the window are written
     const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
     const int vlo = max(cut1, -SPB_SCORE_OFF);
     const uint16_t *c1 = cnt3 + (size_t)x1 * SPB_CNT3_W;
     const uint16_t *c2 = cnt3 + (size_t)x2 * SPB_CNT3_W;
+    const uint32_t *row1 = row3 + (size_t)x1 * SPB_N3;
+    const uint32_t *row2 = row3 + (size_t)x2 * SPB_N3;
     uint32_t done = 0;
     for (int v0 = best1; v0 >= vlo; v0 -= 32) {
         const int v = v0 - lane;
@@ -751,26 +783,34 @@ __device__ __forceinline__ uint32_t window_kmers(const uint32_t *__restrict__ ro
         const uint32_t cnt = rows * c;
         const uint32_t inc = (uint32_t)warp_incl_scan_ool((int)cnt);
         const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
-        if (EXPAND) {
-            // magic reciprocal of the inner count: p / c == umulhi(p, M) for p < 2^16, 1 < c < 2^16 (M = floor(2^32 / c) + 1)
-            const uint32_t M = (c > 1) ? (0xFFFFFFFFu / c + 1u) : 0u;
-            const uint32_t kst = done + inc - cnt;
-            unsigned m = __ballot_sync(0xffffffffu, cnt != 0);
-            while (m) {
-                const int j = __ffs(m) - 1;
-                m &= m - 1;
-                const uint32_t ra0 = __shfl_sync(0xffffffffu, a0, j), rc = __shfl_sync(0xffffffffu, c, j);
-                const uint32_t rn = __shfl_sync(0xffffffffu, cnt, j), rM = __shfl_sync(0xffffffffu, M, j);
-                const uint32_t rk = __shfl_sync(0xffffffffu, kst, j);
-                const uint32_t *row1 = row3 + (size_t)x1 * SPB_N3 + ra0;
-                const uint32_t *row2 = row3 + (size_t)x2 * SPB_N3;
-                for (uint32_t p = (uint32_t)lane; p < rn; p += 32) {
-                    const uint32_t ar = (rc > 1) ? __umulhi(p, rM) : p;
-                    const uint32_t b = p - ar * rc;
-                    const uint32_t i1 = __ldg(row1 + ar) & 0xFFFFu, i2 = __ldg(row2 + b) & 0xFFFFu;
-                    dst[rk + p] = (i1 + 8000u * i2) | (w << 26);
-                }
+        if (EXPAND && tot && done < hi && done + tot > lo) {
+            const unsigned m = __ballot_sync(0xffffffffu, cnt != 0);
+            if (cnt) {
+                const int r = __popc(m & lt);
+                // magic reciprocal of the inner count: p / c == umulhi(p, M) for p < 2^16, 1 < c < 2^16 (M = floor(2^32 / c) + 1)
+                R->desc[r] = make_uint4(done + inc - cnt, a0, c, (c > 1) ? (0xFFFFFFFFu / c + 1u) : 0u);
+                R->end[r] = done + inc;
             }
+            __syncwarp();
+            const uint32_t end = min(done + tot, hi);
+            int r0 = 0, r1 = 0;
+            for (uint32_t s0 = max(done, lo) + (uint32_t)lane; s0 < end; s0 += 64) {
+                const uint32_t s1 = s0 + 32;
+                const bool two = s1 < end;
+                while (s0 >= R->end[r0]) r0++;
+                r1 = max(r1, r0);
+                if (two) { while (s1 >= R->end[r1]) r1++; }
+                const uint4 d0 = R->desc[r0], d1 = R->desc[r1];
+                const uint32_t p0 = s0 - d0.x, p1 = s1 - d1.x;
+                const uint32_t ar0 = (d0.z > 1) ? __umulhi(p0, d0.w) : p0, ar1 = (d1.z > 1) ? __umulhi(p1, d1.w) : p1;
+                const uint32_t b0 = p0 - ar0 * d0.z, b1 = p1 - ar1 * d1.z;
+                uint32_t i1a = __ldg(row1 + d0.y + ar0), i2a = __ldg(row2 + b0), i1b = 0, i2b = 0;
+                if (two) { i1b = __ldg(row1 + d1.y + ar1); i2b = __ldg(row2 + b1); }
+                dst[s0] = ((i1a & 0xFFFFu) + 8000u * (i2a & 0xFFFFu)) | (w << 26);
+                if (two) dst[s1] = ((i1b & 0xFFFFu) + 8000u * (i2b & 0xFFFFu)) | (w << 26);
+                r0 = r1;
+            }
+            __syncwarp();      // the next round rewrites the table
         }
         done += tot;
     }
@@ -779,6 +819,7 @@ __device__ __forceinline__ uint32_t window_kmers(const uint32_t *__restrict__ ro
 
 __global__ void __launch_bounds__(PW_WARPS * 32, 10) expand_kernel(PrefArgs A) {
     __shared__ ExpSmem s_e[PW_WARPS];
+    __shared__ ExpRound s_r[PW_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     ExpSmem &S = s_e[wid];
     for (;;) {
@@ -856,9 +897,13 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 10) expand_kernel(PrefArgs A) {
         __syncwarp();
         // similar k-mers of the query: count, allocate chunks, write
         uint32_t K = 0;
-        for (int w = 0; w < P - 1; w++)
+        for (int w = 0; w < P - 1; w++) {
+            if (lane == 0) S.kst[w] = K;
             if (S.best1[w] != -32768)
-                K += window_kmers<false>(A.row3, A.cnt3, S.x1[w], S.x2[w], S.thr[w], S.best1[w], S.cut1[w], (uint32_t)w, nullptr);
+                K += window_kmers<false>(A.row3, A.cnt3, S.x1[w], S.x2[w], S.thr[w], S.best1[w], S.cut1[w], (uint32_t)w, nullptr, nullptr);
+        }
+        if (lane == 0) S.kst[P - 1] = K;
+        __syncwarp();
         if (K > 65535u) {
             if (lane == 0) { A.outStart[qi] = 0; A.outCount[qi] = 0; A.status[qi] = ST_CAPACITY; A.need[qi] = 4; }
             continue;
@@ -877,13 +922,60 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 10) expand_kernel(PrefArgs A) {
             continue;
         }
         uint32_t *dst = A.recs + (size_t)base * PX_CH;
-        uint32_t kk = 0;
-        for (int w = 0; w < P - 1; w++)
-            if (S.best1[w] != -32768)
-                kk += window_kmers<true>(A.row3, A.cnt3, S.x1[w], S.x2[w], S.thr[w], S.best1[w], S.cut1[w], (uint32_t)w, dst + kk);
+        uint32_t heavy = 0;
+        if (K > A.heavyK) {
+            if (lane == 0) heavy = atomicAdd(A.heavyCount, 1u) + 1u;
+            heavy = __shfl_sync(0xffffffffu, heavy, 0);
+            if (heavy > A.heavyCap) heavy = 0;        // table full: filled here after all
+        }
+        if (heavy) {
+            HeavyQ &H = A.heavyTab[heavy - 1];
+            for (int w = lane; w < P; w += 32) {
+                H.kstart[w] = S.kst[w];
+                if (w < P - 1) { H.x1[w] = S.x1[w]; H.x2[w] = S.x2[w]; H.thr[w] = S.thr[w]; H.best1[w] = S.best1[w]; H.cut1[w] = S.cut1[w]; }
+            }
+            const uint32_t nG = (nCh + PX_HEAVY_GROUP - 1) / PX_HEAVY_GROUP;
+            uint32_t ib = 0;
+            if (lane == 0) {
+                H.nWin = (uint32_t)(P - 1); H.chunk0 = base; H.K = K;
+                ib = atomicAdd(A.heavyItemCount, nG);
+            }
+            ib = __shfl_sync(0xffffffffu, ib, 0);
+            for (uint32_t g = (uint32_t)lane; g < nG; g += 32) A.heavyItems[ib + g] = ((heavy - 1) << 8) | g;
+        } else {
+            for (int w = 0; w < P - 1; w++)
+                if (S.best1[w] != -32768)
+                    window_kmers<true>(A.row3, A.cnt3, S.x1[w], S.x2[w], S.thr[w], S.best1[w], S.cut1[w], (uint32_t)w, dst + S.kst[w], &s_r[wid]);
+        }
         for (uint32_t k = K + (uint32_t)lane; k < nCh * PX_CH; k += 32) dst[k] = PX_INVALID;
         for (uint32_t i = (uint32_t)lane; i < nCh; i += 32) A.chunkTab[base + i] = make_uint2(qi, i * PX_CH);
-        if (lane == 0) { M.chunk0 = base; M.nChunks = nCh; M.K = K; M.minCorr = minCorr; A.status[qi] = ST_PENDING; }
+        if (lane == 0) { M.chunk0 = base; M.nChunks = nCh; M.K = K; M.minCorr = minCorr; M.heavy = heavy; A.status[qi] = ST_PENDING; }
+    }
+}
+
+// Slot records of the heavy queries: one warp per group of 8 chunks (2048 slots; the work items were listed by expand_kernel).
+// The warp finds the windows that overlap its stretch in the query's window table and fills only its own slots of them --
+// every work item is at most 32 trips, so the queries with tens of thousands of similar k-mers no longer form the tail of the
+// stage.
+__global__ void __launch_bounds__(PW_WARPS * 32, 10) expand_heavy_kernel(PrefArgs A) {
+    __shared__ ExpRound s_r[PW_WARPS];
+    const int wid = threadIdx.x >> 5;
+    const uint32_t nItems = min(*A.heavyItemCount, A.heavyItemCap);
+    const uint32_t nWarps = gridDim.x * PW_WARPS;
+    for (uint32_t it = blockIdx.x * PW_WARPS + (uint32_t)wid; it < nItems; it += nWarps) {
+        const uint32_t item = A.heavyItems[it];
+        const HeavyQ &H = A.heavyTab[item >> 8];
+        const uint32_t K = H.K;
+        const uint32_t lo = (item & 0xFFu) * PX_HEAVY_GROUP * PX_CH, hi = min(lo + PX_HEAVY_GROUP * PX_CH, K);
+        uint32_t *dst = A.recs + (size_t)H.chunk0 * PX_CH;
+        const int nW = (int)H.nWin;
+        for (int w = 0; w < nW; w++) {
+            const uint32_t ks = H.kstart[w], ke = H.kstart[w + 1];
+            if (ke <= lo || ke == ks) continue;
+            if (ks >= hi) break;
+            window_kmers<true>(A.row3, A.cnt3, H.x1[w], H.x2[w], H.thr[w], H.best1[w], H.cut1[w], (uint32_t)w, dst + ks, &s_r[wid],
+                               lo > ks ? lo - ks : 0u, hi - ks);
+        }
     }
 }
 
@@ -1133,11 +1225,17 @@ __global__ void __launch_bounds__((TEAM == 1 ? PW_WARPS : TEAM) * 32, TEAM == 1 
     long long phase[6] = {0, 0, 0, 0, 0, 0}, phT = clock64();
 #endif
     // f(record, valid) is called warp-wide for the hit records of the chunks this warp owns (TEAM = 8: chunks round-robin)
+    // (the lookup kernel writes the hits of chunks 2p and 2p + 1 back to back: the warp-per-query launch walks such a pair as one
+    // stretch -- a chunk holds ~145 hits, so two chunks fill three 128-hit trips instead of four)
     auto for_hits = [&](auto f) {
         const uint32_t nCh = S.v_nCh, c0 = S.v_chunk0;
         for (uint32_t ch = (uint32_t)tw; ch < nCh; ch += TEAM) {
             const uint2 cb = __ldcg(A.chunkHits + c0 + ch);
-            const uint32_t n = cb.y;
+            uint32_t n = cb.y;
+            if (SOLO && ((c0 + ch) & 1u) == 0u && ch + 1 < nCh) {
+                n += __ldcg(A.chunkHits + c0 + ch + 1).y;
+                ch++;
+            }
             const uint64_t *src = A.hitArena + (size_t)cb.x;
             for (uint32_t i0 = 0; i0 < n; i0 += 128) {
                 uint64_t r[4];
@@ -1808,10 +1906,11 @@ __global__ void similar_kmers_test_kernel(const uint32_t *row3, const uint16_t *
     const int best1 = (int)(row3[(size_t)x1 * SPB_N3] >> 16) - SPB_SCORE_OFF;
     const int best2 = (int)(row3[(size_t)x2 * SPB_N3] >> 16) - SPB_SCORE_OFF;
     const int cut1 = thr - best2;
+    __shared__ ExpRound s_r;
     uint32_t K = 0;
     if (cut1 <= SPB_CNT3_W - SPB_SCORE_OFF - 1) {
-        K = window_kmers<false>(row3, cnt3, x1, x2, thr, best1, cut1, 0u, nullptr);
-        if (K <= cap) window_kmers<true>(row3, cnt3, x1, x2, thr, best1, cut1, 0u, out);
+        K = window_kmers<false>(row3, cnt3, x1, x2, thr, best1, cut1, 0u, nullptr, nullptr);
+        if (K <= cap) window_kmers<true>(row3, cnt3, x1, x2, thr, best1, cut1, 0u, out, &s_r);
     }
     if (threadIdx.x == 0) *n = K;
 }
@@ -2008,6 +2107,14 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
             c->s_k.ensure((size_t)Q * 4 + 64) || c->p_team2.ensure((size_t)Q * 4 + 64) || c->p_retry.ensure((size_t)Q * 4 + 64) || c->p_meta.ensure((size_t)Q * sizeof(QMeta))) return 1;
         A.hitScratch = c->s_j.as<uint64_t>();
         A.meta = c->p_meta.as<QMeta>();
+        // queries with more similar k-mers than this are filled chunk by chunk (expand_heavy_kernel); 65535 switches that off
+        A.heavyK = 2048;
+        if (const char *e = getenv("SPB_EXPAND_HEAVY")) A.heavyK = (uint32_t)std::max(1, std::min(65535, atoi(e)));
+        A.heavyCap = std::min<uint32_t>(std::min(Q, tileQ), 16384u);
+        A.heavyItemCap = A.heavyCap * 32u;     // K <= 65535: at most 256 chunks = 32 groups per query
+        if (c->p_heavy.ensure((size_t)A.heavyCap * sizeof(HeavyQ) + (size_t)A.heavyItemCap * 4)) return 1;
+        A.heavyTab = c->p_heavy.as<HeavyQ>();
+        A.heavyItems = reinterpret_cast<uint32_t *>(c->p_heavy.as<unsigned char>() + (size_t)A.heavyCap * sizeof(HeavyQ));
         A.teamList = c->s_k.as<uint32_t>();
         A.teamList2 = c->p_team2.as<uint32_t>();
         if (!c->aux_stream) {
@@ -2042,19 +2149,25 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
                     c->ev_phase.push_back(ev);
                 }
                 cudaEvent_t *ep = c->ev_phase.data() + (size_t)nTilesRun * 5;
-                SPB_CUDA(cudaMemsetAsync(tc, 0, 32, st));
+                SPB_CUDA(cudaMemsetAsync(tc, 0, 48, st));
                 A.qlist = curList;
                 A.listOff = t;
                 A.listStride = nTiles;
                 A.nList = (curN - t + nTiles - 1) / nTiles;
                 A.nListPtr = nullptr;
                 A.chunkCursor = tc + 3;
+                A.heavyCount = tc + 7;
+                A.heavyItemCount = tc + 8;
                 A.teamCount = tc + 4;
                 A.teamCount2 = tc + 6;
                 A.qCounter = tc + 0;
                 SPB_CUDA(cudaEventRecord(ep[0], st));
                 expand_kernel<<<c->n_sm * expandPerSm, PW_WARPS * 32, 0, st>>>(A);
                 SPB_CUDA(cudaGetLastError()); c->n_launches++;
+                if (A.heavyK < 65535u) {
+                    expand_heavy_kernel<<<c->n_sm * expandPerSm, PW_WARPS * 32, 0, st>>>(A);
+                    SPB_CUDA(cudaGetLastError()); c->n_launches++;
+                }
                 SPB_CUDA(cudaEventRecord(ep[1], st));
                 if (c->n_shards > 1) lookup_kernel<true><<<c->n_sm * lookupPerSm, PX_CH, 0, st>>>(A);   // persistent: lookupPerSm CTAs per SM
                 else lookup_kernel<false><<<c->n_sm * lookupPerSm, PX_CH, 0, st>>>(A);
