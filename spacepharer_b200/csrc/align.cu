@@ -654,7 +654,8 @@ __global__ void __launch_bounds__(TB_THREADS) sw_traceback_kernel(TbArgs A) {
     char *cig = A.cigar + A.cigOff[k];
     const uint32_t cigCap = (uint32_t)(A.cigOff[k + 1] - A.cigOff[k]);
     uint32_t n = 0;
-    bool bad = false, done = false;
+    int ids = 0;
+    bool bad = false, done = false, idsDone = false;
     // ops as 2-bit codes, last-to-first, in two registers
     unsigned long long opsLo = 0, opsHi = 0;
     auto emit = [&](int op) {
@@ -721,19 +722,31 @@ __global__ void __launch_bounds__(TB_THREADS) sw_traceback_kernel(TbArgs A) {
             }
         }
     } else if (!bad) {
-        // the walk produced the path end-to-start; the start cell is the final forced 'M' of the reference
+        // the walk produced the path end-to-start; the start cell is the final forced 'M' of the reference.  Ops and identities
+        // (Matcher.cpp:61-187) in one pass over the packed list, residues from the staged box: nothing is read back from global memory
+        const uint8_t *sq = s_qs + threadIdx.x, *st = s_ts + threadIdx.x;
         cig[0] = 'M';
-        for (uint32_t x = 1; x <= n; x++) cig[x] = "MID"[op_at(n - x)];
+        ids = (sq[0] == st[0]);
+        int qi2 = 1, ti2 = 1;
+        for (uint32_t x = 1; x <= n; x++) {
+            const int op = op_at(n - x);
+            cig[x] = "MID"[op];
+            if (op == 0) { ids += (sq[qi2 * TB_THREADS] == st[ti2 * TB_THREADS]); qi2++; ti2++; }
+            else if (op == 1) qi2++;
+            else ti2++;
+        }
         n++;
+        idsDone = true;
     }
     if (!bad) {
-        // identities (Matcher.cpp:61-187)
-        int ids = 0, qi2 = 0, ti2 = 0;
-        for (uint32_t x = 0; x < n; x++) {
-            const char op = cig[x];
-            if (op == 'M') { ids += (qs[qi2] == db[ti2]); qi2++; ti2++; }
-            else if (op == 'I') qi2++;
-            else ti2++;
+        if (!idsDone) {
+            int qi2 = 0, ti2 = 0;
+            for (uint32_t x = 0; x < n; x++) {
+                const char op = cig[x];
+                if (op == 'M') { ids += (qs[qi2] == db[ti2]); qi2++; ti2++; }
+                else if (op == 'I') qi2++;
+                else ti2++;
+            }
         }
         o.cigLen = n;
         o.nIdent = ids;

@@ -107,8 +107,13 @@ template <bool SHARDED = true>
 __device__ __forceinline__ ulonglong2 kmer_entry(const PrefArgs &A, uint32_t kmer, bool streaming) {
     uint32_t o = 0, l = kmer;
     if (SHARDED && A.nShards > 1) { o = kmer / A.shardR; l = kmer - o * A.shardR; }
-    const ulonglong2 *d = SHARDED ? A.directS[o] : A.directS[0];
-    return streaming ? __ldcs(d + l) : __ldg(d + l);
+    const ulonglong2 *d = (SHARDED ? A.directS[o] : A.directS[0]) + l;
+    if (!streaming) return __ldg(d);
+    // a random 16-byte read: with the default policy L2 fetches the whole 128-byte line (117 B of DRAM traffic per entry,
+    // tools/gather_probe.cu); the 64-byte fetch hint halves that.  The access rate, which bounds the gather, is the same.
+    ulonglong2 r;
+    asm volatile("ld.global.nc.L2::64B.v2.u64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(d));
+    return r;
 }
 // posting lists of the shard that owns the k-mer (list offsets in the entries are relative to it)
 template <bool SHARDED = true>

@@ -88,7 +88,9 @@ if os.path.exists(rep):
     out = {}
     for name, v in traffic.items():
         key = None
-        if "expand_kernel" in name:
+        if "expand_heavy" in name:
+            key = "expand_heavy_kernel"
+        elif "expand_kernel" in name:
             key = "expand_kernel"
         elif "lookup_kernel" in name:
             key = "lookup_kernel"
@@ -103,7 +105,7 @@ if os.path.exists(rep):
             out[key + "_dram_bytes_per_launch"] = max(v)
     # the roofline entry of bench.py covers the whole prefilter (one batch = one launch of each kernel class)
     out["prefilter_dram_bytes_per_launch"] = sum(out.get(k + "_dram_bytes_per_launch", 0.0)
-                                                 for k in ("expand_kernel", "lookup_kernel", "bookkeep_kernel_1", "bookkeep_kernel_8"))
+                                                 for k in ("expand_kernel", "expand_heavy_kernel", "lookup_kernel", "bookkeep_kernel_1", "bookkeep_kernel_8"))
     out["source"] = "profiles/%s_kernels.csv (ncu --set full, cold cache)" % tag
     json.dump(out, open(os.path.join(P, "traffic.json"), "w"), indent=1)
     print("wrote kernel metrics", out)

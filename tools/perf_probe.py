@@ -22,3 +22,10 @@ for it in range(3):
           "GCUPS %.2f" % (ast["n_cells"] / ast["kernel_ms"] / 1e6))
 Q = len(qoff) - 1
 print("queries/s (kernels only): %.0f" % (Q / ((pst["kernel_ms"] + ast["kernel_ms"]) / 1e3)))
+
+if os.environ.get("SPB_PROBE_BANDS"):
+    ql = rows["q_end"].astype(np.int64) - rows["q_start"] + 1
+    tl = rows["t_end"].astype(np.int64) - rows["t_start"] + 1
+    bw = np.abs(tl - ql) + 1
+    print("traceback boxes: band classes", {int(b): int((bw == b).sum()) for b in np.unique(bw)[:12]}, "max band", int(bw.max()), "boxes wider than 4:", int((bw > 4).sum()),
+          "max qLen", int(ql.max()), "max tLen", int(tl.max()), "cells of the widest", int((ql * (2 * bw + 1))[np.argmax(bw)]))
