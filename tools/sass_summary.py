@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
-KERNELS = [("build/prefilter.o", "expand_kernel"), ("build/prefilter.o", "lookup_kernel"), ("build/prefilter.o", "bookkeep_kernel"),
+KERNELS = [("build/prefilter.o", "expand_kernel"), ("build/prefilter.o", "expand_heavy_kernel"), ("build/prefilter.o", "lookup_kernel"), ("build/prefilter.o", "bookkeep_kernel"),
            ("build/align.o", "sw_fast_kernel"), ("build/align.o", "sw_exhaustive_kernel"), ("build/align.o", "sw_traceback_kernel"),
            ("build/align.o", "sw_reverse_kernel")]
 INTEREST = ("VIADDMNMX", "VIMNMX", "VIADD", "PRMT", "LDG", "LDS", "STG", "STS", "ATOMS", "ATOMG", "RED", "SHFL", "REDUX", "VOTE", "POPC",
