@@ -60,6 +60,7 @@ def parse_args():
                     help="index split: GPUs sharing one copy of the k-mer table (0 = all N); N must be a multiple of it")
     ap.add_argument("--strong-spacers", type=int, default=1000000,
                     help="spacers of the strong-scaling leg (BASELINE config 4: the whole job split over the GPUs); 0 = skip")
+    ap.add_argument("--no-control", action="store_true", help="skip the control-setDB pass of the strong-scaling leg")
     ap.add_argument("--no-disk-to-disk", action="store_true",
                     help="skip the product-level leg (the C++ host binary `spb200 search` on the config-4 DBs, from disk to disk)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity_ok check (rows of the config-2 batch vs the reference digest)")
@@ -587,6 +588,18 @@ def run_ours(args):
 
     strong = strong_leg(eng, args.split_mode, n_lanes)
     parity = None if args.no_parity else parity_check(eng)
+    # predictmatch searches the spacers twice: against the target setDB and against the reversed-ORF control setDB
+    # (data/predictmatch.sh:78,96).  The same 1 M-spacer job against the control set, on a second engine (its own index, same split)
+    strong_ctrl = None
+    if strong and not args.no_control:
+        ctres = synth.reverse_targets(tres, toff)
+        cmasked = ctres if args.no_mask else api.tantan_mask(eng.searcher.seed, ctres, toff)[0]
+        eng_c = multigpu.ShardedSearcher(device=local, rank=rank, world=world, split_mode=args.split_mode, lanes=n_lanes,
+                                         shard_group=args.shard_group)
+        eng_c.load_targets(cmasked, ctres, toff)
+        strong_ctrl = strong_leg(eng_c, args.split_mode, n_lanes)
+        eng_c.close()
+        del ctres, cmasked
 
     # ---- the other way to spread the search over the GPUs, N > 1: value leg, strong-scaling leg and parity of that mode ----
     # main mode "query" (full index per GPU): the k-mer table sharded over groups of GPUs and gathered through NVLink peer memory
@@ -667,6 +680,12 @@ def run_ours(args):
         main_group = eng_group if (world > 1 and args.split_mode == "index") else 0
         if strong:
             line["strong_scaling"] = strong_block(strong, args.split_mode, main_group)
+            if strong_ctrl:
+                line["strong_scaling"]["control"] = {"ms_total": strong_ctrl[0], "rows": int(strong_ctrl[1]), "value": SQ / (strong_ctrl[0] * 1e-3),
+                                                     "workload": "the same spacers against the reversed-ORF control setDB (second search of predictmatch)"}
+                both = strong[0] + strong_ctrl[0]
+                line["strong_scaling"]["target_plus_control"] = {"ms_total": both, "value": SQ / (both * 1e-3), "unit": UNIT,
+                                                                 "note": "both searches of predictmatch for the 1 M spacers; spacers/s = %.0f" % (args.strong_spacers / (both * 1e-3))}
         if parity:
             line["parity"] = parity
         if d2d:
