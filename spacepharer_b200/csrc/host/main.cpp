@@ -1441,13 +1441,52 @@ int run_dbcopy(int argc, const char **argv) {
     DBWriter out;
     out.open(argv[3], in.dbtype(), threads);
     const size_t n = in.size();
+    const size_t flushEvery = argc > 5 ? (size_t)atoll(argv[5]) : 0;      // streaming writer: flush all parts every N entries
     for (size_t i = 0; i < n; i++) {
         const DBEntry &e = in.byKey(i);
         out.write((int)(i * (size_t)threads / (n ? n : 1)), e.key, in.data(e), e.length ? e.length - 1 : 0);
+        if (flushEvery && (i + 1) % flushEvery == 0) out.flush(0, threads);
     }
     out.close();
     printf("%zu entries, %llu residues\n", n, (unsigned long long)in.aminoAcidDBSize());
     return 0;
+}
+
+// spb200 fmtcheck <n> <seed>: put_e3 / put_int against printf on n random and adversarial values (host self-test, no GPU)
+int run_fmtcheck(int argc, const char **argv) {
+    const long n = argc > 2 ? atol(argv[2]) : 1000000;
+    unsigned long long x = argc > 3 ? strtoull(argv[3], nullptr, 10) : 1;
+    auto next = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    long bad = 0;
+    char a[64], b[64];
+    for (long i = 0; i < n; i++) {
+        double v;
+        const int mode = (int)(i & 3);
+        if (mode == 0) {                      // any finite positive double
+            unsigned long long bits = next() & 0x7FEFFFFFFFFFFFFFull;
+            memcpy(&v, &bits, 8);
+        } else if (mode == 1) {               // E-value range
+            v = (1.0 + (double)(next() % 9000000) / 1e6) * pow(10.0, (double)((long)(next() % 60) - 45));
+        } else {                              // on and next to the rounding boundaries of four digits
+            const int d = 1000 + (int)(next() % 9000), e = (int)(next() % 60) - 40;
+            v = (d + (mode == 2 ? 0.5 : 0.0)) * pow(10.0, e - 3);
+            if (next() & 1) v = nextafter(v, (next() & 1) ? 0.0 : 1e300);
+        }
+        *put_e3(a, v) = 0;
+        snprintf(b, sizeof(b), "%.3E", v);
+        if (strcmp(a, b)) { if (bad < 5) fprintf(stderr, "%.17g: %s vs %s\n", v, a, b); bad++; }
+        const long long iv = (long long)next();
+        *put_int(a, iv) = 0;
+        snprintf(b, sizeof(b), "%lld", iv);
+        if (strcmp(a, b)) { if (bad < 5) fprintf(stderr, "%lld: %s vs %s\n", iv, a, b); bad++; }
+    }
+    for (double v : {0.0, 1e-320, 5e-324, 1e308, 9.9995, 9.99949999999, 0.00099995, 1.0, 200.0}) {
+        *put_e3(a, v) = 0;
+        snprintf(b, sizeof(b), "%.3E", v);
+        if (strcmp(a, b)) bad++;
+    }
+    printf("%ld values, %ld mismatches\n", n, bad);
+    return bad ? 1 : 0;
 }
 
 int run_showparams(int argc, const char **argv) {
@@ -1490,6 +1529,7 @@ int main(int argc, const char **argv) {
         else if (cmd == "dumpmatrix") rc = run_dumpmatrix(argc, argv);
         else if (cmd == "dbcopy") rc = run_dbcopy(argc, argv);
         else if (cmd == "showparams") rc = run_showparams(argc, argv);
+        else if (cmd == "fmtcheck") rc = run_fmtcheck(argc, argv);
         else {
             fprintf(stderr, "Invalid Command: %s\n", cmd.c_str());
             return 1;

@@ -75,6 +75,37 @@ def test_db_round_trip(tmp_path, db, threads):
     assert keys == sorted(keys)
 
 
+@pytest.mark.parametrize("threads,every", [(1, 7), (4, 3), (3, 100)])
+def test_db_streaming_writer(tmp_path, threads, every):
+    """DBWriter::flush between batches (what `spb200 search` does while the next batch is on the device): the entries written
+    so far go to the file, the index still carries their final offsets"""
+    src = os.path.join(GOLDEN, "config1", "prot_result")
+    dst = str(tmp_path / "copy")
+    run("dbcopy", src, dst, str(threads), str(every))
+    assert dbio.read_entries(src) == dbio.read_entries(dst)
+    assert dbio.read_dbtype(src) == dbio.read_dbtype(dst)
+    keys = [int(l.split()[0]) for l in open(dst + ".index")]
+    assert keys == sorted(keys)
+
+
+def test_large_index_is_parsed_in_parallel(tmp_path):
+    """an index text above 1 MB is cut into slices at line ends and parsed by all threads; the entries and their order do not change"""
+    n = 90000
+    name = str(tmp_path / "big")
+    dbio.write_db(name, ((k, b"%d" % (k * 7)) for k in range(n)), dbio.DBTYPE_GENERIC_DB)
+    assert os.path.getsize(name + ".index") > (1 << 20)
+    run("dbcopy", name, name + "_copy", "5", "1000")
+    src, dst = dbio.read_entries(name), dbio.read_entries(name + "_copy")
+    assert len(dst) == n and src == dst
+
+
+def test_row_formatter_matches_printf():
+    """fastfmt.h: `%.3E` and integers of the result rows without stdio, byte for byte what printf prints (random doubles, the
+    E-value range, values on and next to the four-digit rounding boundaries, denormals)"""
+    out = run("fmtcheck", "400000", "11").stdout
+    assert "400000 values, 0 mismatches" in out
+
+
 def test_workflow_argv_is_accepted():
     out = run("showparams", "prefilter", "q", "t", "p", *PREF_FLAGS).stdout
     assert "kmer_thr=112" in out and "max_seqs=300" in out and "pattern=11011101" in out and "seed_sub_mat=VTML80.out" in out
