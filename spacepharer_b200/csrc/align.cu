@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(TB_THREADS) sw_traceback_kernel(TbArgs A) {
     const uint32_t cigCap = (uint32_t)(A.cigOff[k + 1] - A.cigOff[k]);
     uint32_t n = 0;
     int ids = 0;
-    bool bad = false, done = false, idsDone = false;
+    bool bad = false, done = false, idsDone = false, allM = false;
     // ops as 2-bit codes, last-to-first, in two registers
     unsigned long long opsLo = 0, opsHi = 0;
     auto emit = [&](int op) {
@@ -673,9 +673,25 @@ __global__ void __launch_bounds__(TB_THREADS) sw_traceback_kernel(TbArgs A) {
         signed char *sc = s_cb + threadIdx.x;
         for (int i = 0; i < qLen; i++) { sq[i * TB_THREADS] = qs[i]; sc[i * TB_THREADS] = cb[i]; }
         for (int j = 0; j < dbLen; j++) st[j * TB_THREADS] = db[j];
+        // Ungapped boxes need no DP.  If the box is square and its main diagonal sums to the forward score, the reference's DP can
+        // only return all matches: every H on the diagonal is a local alignment score that the rest of the diagonal extends,
+        // so none can exceed the prefix sum without beating the optimum; the diagonal then wins every tie against the gap states
+        // (:872), the first band reaches the score (no doubling, :877) and the walk never leaves it.  (qLen >= 4 keeps the
+        // clipped-band slot rule of :837 out of the picture.)  Nine boxes in ten of a spacer search end here.
+        if (qLen == dbLen && qLen >= 4) {
+            int sum = 0;
+            for (int i = 0; i < qLen; i++) sum += (int)s_mat[(int)sq[i * TB_THREADS] * 32 + st[i * TB_THREADS]] + sc[i * TB_THREADS];
+            if (sum == score) {
+                for (int i = 0; i < qLen; i++) { cig[i] = 'M'; ids += (sq[i * TB_THREADS] == st[i * TB_THREADS]); }
+                n = (uint32_t)qLen;
+                done = true;
+                idsDone = true;
+                allM = true;
+            }
+        }
         int bw = bw0, mx = 0;
         bool fits = true;
-        for (;;) {
+        for (; !allM;) {
             if (bw == 1) mx = band_pass_reg<1>(hb, eb, hc, dirs, sq, sc, st, s_mat, qLen, dbLen, bw, go, ge);
             else if (bw == 2) mx = band_pass_reg<2>(hb, eb, hc, dirs, sq, sc, st, s_mat, qLen, dbLen, bw, go, ge);
             else mx = band_pass_reg<TB_BW>(hb, eb, hc, dirs, sq, sc, st, s_mat, qLen, dbLen, bw, go, ge);
@@ -683,7 +699,7 @@ __global__ void __launch_bounds__(TB_THREADS) sw_traceback_kernel(TbArgs A) {
             bw *= 2;
             if (bw > TB_BW) { fits = false; break; }     // replayed from the start on the scratch slice below
         }
-        if (fits) {
+        if (fits && !allM) {
             done = true;
             bad = !band_walk(qLen, dbLen, bw, min(cigCap, (uint32_t)TB_CIG),
                              [&](int r, int cell, int st) { return band_code(dirs[(size_t)r * TB_THREADS], cell, st); }, emit, n);
@@ -721,7 +737,7 @@ __global__ void __launch_bounds__(TB_THREADS) sw_traceback_kernel(TbArgs A) {
                 for (uint32_t x = 0; x < cigCap; x++) cig[x] = 0;    // a failed walk leaves no partial ops behind
             }
         }
-    } else if (!bad) {
+    } else if (!bad && !allM) {
         // the walk produced the path end-to-start; the start cell is the final forced 'M' of the reference.  Ops and identities
         // (Matcher.cpp:61-187) in one pass over the packed list, residues from the staged box: nothing is read back from global memory
         const uint8_t *sq = s_qs + threadIdx.x, *st = s_ts + threadIdx.x;
