@@ -1232,15 +1232,20 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
     if (c->s_cub.ensure(tmpBytes)) return 1;
     SPB_CUDA(cub::DeviceRadixSort::SortPairsDescending(c->s_cub.p, tmpBytes, c->s_n.as<uint32_t>(), c->s_o.as<uint32_t>(), c->s_p.as<uint32_t>(),
                                                        c->s_q.as<uint32_t>(), (int)NP, 0, keyBits, st));
+    // every query of the batch runs the register kernel (what a spacer batch looks like): no work items of the shared-memory
+    // kernel to count, no H/E slices for the reverse pass -- and no host round trip to learn that
+    const bool allFast = c->q_minlen >= 1 && c->q_maxlen <= (uint32_t)fastMaxL;
     uint32_t *itemCnt = c->s_c.as<uint32_t>(), *itemBase = itemCnt + (Q + 1);
-    item_count_kernel<<<(Q + 1 + 255) / 256, 256, 0, st>>>(c->d_pairoff.as<uint64_t>(), c->s_m.as<uint8_t>(), Q, itemCnt);
-    SPB_CUDA(cudaGetLastError()); c->n_launches++;
-    SPB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, itemCnt, itemBase, (int)(Q + 1), st));
-    if (c->s_cub.ensure(tmpBytes)) return 1;
-    SPB_CUDA(cub::DeviceScan::ExclusiveSum(c->s_cub.p, tmpBytes, itemCnt, itemBase, (int)(Q + 1), st));
     uint32_t nItems = 0;
-    SPB_CUDA(cudaMemcpyAsync(&nItems, itemBase + Q, 4, cudaMemcpyDeviceToHost, st));
-    SPB_CUDA(cudaStreamSynchronize(st));
+    if (!allFast) {
+        item_count_kernel<<<(Q + 1 + 255) / 256, 256, 0, st>>>(c->d_pairoff.as<uint64_t>(), c->s_m.as<uint8_t>(), Q, itemCnt);
+        SPB_CUDA(cudaGetLastError()); c->n_launches++;
+        SPB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, itemCnt, itemBase, (int)(Q + 1), st));
+        if (c->s_cub.ensure(tmpBytes)) return 1;
+        SPB_CUDA(cub::DeviceScan::ExclusiveSum(c->s_cub.p, tmpBytes, itemCnt, itemBase, (int)(Q + 1), st));
+        SPB_CUDA(cudaMemcpyAsync(&nItems, itemBase + Q, 4, cudaMemcpyDeviceToHost, st));
+        SPB_CUDA(cudaStreamSynchronize(st));
+    }
 
     FastArgs F;
     memset(&F, 0, sizeof(F));
@@ -1329,14 +1334,16 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
         // scratch: s_g he offsets u64[nAcc+1] (+ sizes), s_h he scratch, s_i tb offsets, s_j cig offsets, s_k tb scratch
         if (c->s_g.ensure(((size_t)nAcc + 1) * 16)) return 1;
         uint64_t *heSz = c->s_g.as<uint64_t>(), *heOff = heSz + (nAcc + 1);
-        he_size_kernel<<<(nAcc + 1 + 255) / 256, 256, 0, st>>>(A.out, c->d_acc.as<uint32_t>(), nAcc, heSz);
-        SPB_CUDA(cudaGetLastError()); c->n_launches++;
-        SPB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, heSz, heOff, (int)(nAcc + 1), st));
-        if (c->s_cub.ensure(tmpBytes)) return 1;
-        SPB_CUDA(cub::DeviceScan::ExclusiveSum(c->s_cub.p, tmpBytes, heSz, heOff, (int)(nAcc + 1), st));
         uint64_t heTotal = 0;
-        SPB_CUDA(cudaMemcpyAsync(&heTotal, heOff + nAcc, 8, cudaMemcpyDeviceToHost, st));
-        SPB_CUDA(cudaStreamSynchronize(st));
+        if (!allFast) {      // H/E slices of the reverse pass: only queries outside the register kernel use them
+            he_size_kernel<<<(nAcc + 1 + 255) / 256, 256, 0, st>>>(A.out, c->d_acc.as<uint32_t>(), nAcc, heSz);
+            SPB_CUDA(cudaGetLastError()); c->n_launches++;
+            SPB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, heSz, heOff, (int)(nAcc + 1), st));
+            if (c->s_cub.ensure(tmpBytes)) return 1;
+            SPB_CUDA(cub::DeviceScan::ExclusiveSum(c->s_cub.p, tmpBytes, heSz, heOff, (int)(nAcc + 1), st));
+            SPB_CUDA(cudaMemcpyAsync(&heTotal, heOff + nAcc, 8, cudaMemcpyDeviceToHost, st));
+            SPB_CUDA(cudaStreamSynchronize(st));
+        }
         if (c->s_h.ensure(heTotal * sizeof(short2) + 16)) return 1;
         TbArgs B;
         memset(&B, 0, sizeof(B));

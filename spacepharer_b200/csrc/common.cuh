@@ -143,7 +143,7 @@ struct spb_ctx {
     bool have_queries = false;
     uint32_t Q = 0;
     uint64_t q_res = 0;
-    uint32_t q_maxlen = 0;
+    uint32_t q_maxlen = 0, q_minlen = 0;
     spb::DevBuf d_q;              // u8[q_res]
     spb::DevBuf d_qoff;           // u32[Q+1]
     spb::DevBuf d_qoff64;         // u64[Q+1]

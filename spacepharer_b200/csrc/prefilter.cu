@@ -1990,6 +1990,7 @@ int spb::queries_install(spb_ctx *c, const uint8_t *q_residues, bool on_device, 
     c->Q = Q;
     c->q_res = NQ;
     c->q_maxlen = maxL;
+    c->q_minlen = Q ? *std::min_element(c->h_qlen.begin(), c->h_qlen.end()) : 0u;
     c->have_queries = true;
     c->have_pref = false;
     c->have_pairs = false;
