@@ -166,6 +166,36 @@ def test_prefilter_random_vs_oracle(searcher, bin_size, maxseqs):
         assert st["n_slow_path"] <= 0.1 * (len(qoff) - 1)
 
 
+@pytest.mark.parametrize("env", [
+    {"SPB_PF_CHUNKS": "300", "SPB_PF_HITS_PER_CHUNK": "24"},                 # slot / hit arenas overflow: retry rounds with doubled arenas
+    {"SPB_EXPAND_HEAVY": "64"},                                               # almost every query is filled by expand_heavy_kernel
+    {"SPB_EXPAND_HEAVY": "65535"},                                            # ... none is
+    {"SPB_HITS_SOLO": "32", "SPB_PF_TILEQ": "256"},                           # everything handed to the CTA-per-query launch, many tiles
+    {"SPB_PF_TILEQ": "300", "SPB_PF_CHUNKS": "700", "SPB_EXPAND_HEAVY": "300"},
+])
+def test_prefilter_is_independent_of_arena_sizes_and_hand_over_points(searcher, env):
+    """arena capacities, tile size and the hand-over thresholds between the kernels are tuning knobs: every setting gives the
+    list of the default configuration (which the other tests pin on the oracle and the reference)"""
+    import os
+    from spacepharer_b200 import synth
+    tres, toff, _ = synth.make_targets(n_genomes=60, seed=5)
+    qres, qoff, _ = synth.make_query_frames(2500, tres, toff, seed=9)
+    searcher.build_index(tres, toff)
+    off0, hits0, _ = searcher.prefilter(qres, qoff)
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        off, hits, _ = searcher.prefilter(qres, qoff)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    assert (off == off0).all()
+    assert (hits["id"] == hits0["id"]).all() and (hits["score"] == hits0["score"]).all() and (hits["diag"] == hits0["diag"]).all()
+
+
 def test_prefilter_edge_cases(searcher):
     """empty batch, queries shorter than the k-mer span, one window only, X-only query"""
     T, _ = Cm.load_fasta_set("small")
