@@ -480,7 +480,11 @@ def run_ours(args):
     # the whole job goes through the public API with host buffers (H2D of the frames, D2H of the sorted rows + CIGARs inside
     # the timed region), in chunks of ~125 k frames per GPU over the lanes; total work is fixed, so the N-GPU time against the
     # 1-GPU time is the strong-scaling curve of the split the engine uses
+    # chunk size: at most 125 k frames, and small enough that every lane of every GPU sees two chunks (a job of 3.79 M frames
+    # on 8 GPUs x 3 lanes in 125 k chunks would leave two lanes idle for the last third of the run)
     per_gpu = 125000
+    if args.strong_spacers > 0:
+        per_gpu = int(min(125000, max(32768, -(-(len(so) - 1) // (world * 2 * n_lanes)))))
     strong_chunks, SQ = None, 0
     if args.strong_spacers > 0:
         SQ = len(so) - 1
