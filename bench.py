@@ -60,6 +60,8 @@ def parse_args():
                     help="index split: GPUs sharing one copy of the k-mer table (0 = all N); N must be a multiple of it")
     ap.add_argument("--strong-spacers", type=int, default=1000000,
                     help="spacers of the strong-scaling leg (BASELINE config 4: the whole job split over the GPUs); 0 = skip")
+    ap.add_argument("--long-steps", type=int, default=200,
+                    help="steps of the additional long value leg (`steady_state`), 0 = skip")
     ap.add_argument("--no-control", action="store_true", help="skip the control-setDB pass of the strong-scaling leg")
     ap.add_argument("--no-disk-to-disk", action="store_true",
                     help="skip the product-level leg (the C++ host binary `spb200 search` on the config-4 DBs, from disk to disk)")
@@ -388,8 +390,9 @@ def run_ours(args):
     # K steps shared by n_lanes contexts (one host thread each, every lane holds the batch resident); one CUDA event per lane
     # stream before the first and after the last step, device time = latest end - earliest start; the per-step L2 flush runs
     # on the lane's stream INSIDE the timed span here
-    def lanes_value_leg(engine):
+    def lanes_value_leg(engine, steps=None):
         """K steps shared by the lanes of `engine`, batches resident -> (device ms, wall s, own launches, queries searched)"""
+        steps = steps or args.steps
         lanes = engine.lanes()
         dev = torch.device("cuda", local)
         ext = [torch.cuda.ExternalStream(ln.stream_ptr(), device=dev) for ln in lanes]
@@ -407,15 +410,19 @@ def run_ours(args):
         tw0 = time.perf_counter()
         for l in range(len(lanes)):
             e0[l].record(ext[l])
-        vsts = engine.run_stream(batches, db_res, steps=args.steps, resident=True, before_step=before_step)
+        vsts = engine.run_stream(batches, db_res, steps=steps, resident=True, before_step=before_step)
         nq_ = sum(batch_q[st["lane"] % len(batches)] for st in vsts)
         for l in range(len(lanes)):
             e1[l].record(ext[l])
         barrier()
         return max(a.elapsed_time(b) for a in e0 for b in e1), time.perf_counter() - tw0, engine.launches() - l0, nq_
 
+    long_leg = None
     if n_lanes > 1:
         dev_ms, wall_value, launches, value_queries = lanes_value_leg(eng)
+        if args.long_steps > args.steps:      # the same leg over a longer timed region (K steps are 30-40 ms of device time)
+            lm, lw, _, lq = lanes_value_leg(eng, args.long_steps)
+            long_leg = [lm, lq]
         eng.set_queries(q_np, o_np)
 
     # ---- end-to-end leg through the public API with HOST buffers ----
@@ -622,12 +629,13 @@ def run_ours(args):
         other = {"mode": omode, "group": ogroup, "ms": float(to[0]), "queries": o_q, "strong": o_strong, "parity": o_parity}
         eng_o.close()
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3, exh["kernel_ms"] if exh else 0.0, single_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s * 1e3, exh["kernel_ms"] if exh else 0.0, single_ms, long_leg[0] if long_leg else 0.0],
+                     dtype=torch.float64, device="cuda")
     tsum = torch.tensor([exh["cells"], exh["scored"], exh["kept"], exh["queries"]] if exh else [0.0] * 4, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-    dev_ms, e2e_ms, exh_ms, single_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+    dev_ms, e2e_ms, exh_ms, single_ms, long_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3]), float(t[4])
     q_total = eng.queries_per_step(Q)
     eng_group = eng.shard_group
     eng.close()
@@ -682,6 +690,10 @@ def run_ours(args):
             "wall_s_value_leg": wall_value,
         }
         main_group = eng_group if (world > 1 and args.split_mode == "index") else 0
+        if long_leg and long_ms > 0:
+            line["steady_state"] = {"value": long_leg[1] / (long_ms * 1e-3), "unit": UNIT, "steps": args.long_steps,
+                                    "ms_per_step": long_ms / args.long_steps,
+                                    "note": "the value leg again over %d steps (%.0f ms of device time instead of %.0f)" % (args.long_steps, long_ms, dev_ms)}
         if strong:
             line["strong_scaling"] = strong_block(strong, args.split_mode, main_group)
             if strong_ctrl:
