@@ -27,21 +27,17 @@ static inline char *put_int(char *p, long long v) {
 }
 
 // 10^n as long double for n in [-350, 350]; exact for 0 <= n <= 27, otherwise within an ulp (2^-64 relative)
-static inline long double pow10_ld(int n) {
-    static long double tab[701];
-    static bool init = false;
-    if (!init) {
-#pragma omp critical(spb_pow10_init)
-        {
-            if (!init) {
-                tab[350] = 1.0L;
-                for (int i = 1; i <= 350; i++) tab[350 + i] = tab[350 + i - 1] * 10.0L;
-                for (int i = 1; i <= 350; i++) tab[350 - i] = 1.0L / tab[350 + i];
-                init = true;
-            }
-        }
+struct Pow10Table {
+    long double v[701];
+    Pow10Table() {
+        v[350] = 1.0L;
+        for (int i = 1; i <= 350; i++) v[350 + i] = v[350 + i - 1] * 10.0L;
+        for (int i = 1; i <= 350; i++) v[350 - i] = 1.0L / v[350 + i];
     }
-    return tab[350 + n];
+};
+static inline long double pow10_ld(int n) {
+    static const Pow10Table tab;      // (initialisation of a function-local static is thread-safe)
+    return tab.v[350 + n];
 }
 
 // printf("%.3E", x) for every double; returns the end of the output
