@@ -99,6 +99,24 @@ def test_large_index_is_parsed_in_parallel(tmp_path):
     assert len(dst) == n and src == dst
 
 
+def test_vectorised_sequence_db_writer(tmp_path):
+    """dbio.write_sequence_db_arrays (the million-entry DBs of bench.py's disk_to_disk leg) writes the bytes of the entry-by-entry
+    writer, and the host binary reads them back"""
+    import numpy as np
+    from spacepharer_b200 import synth
+    tres, toff, _ = synth.make_targets(n_genomes=20, seed=11)
+    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+    dbio.write_sequence_db_arrays(a, tres, toff)
+    lut = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWYX", dtype=np.uint8)
+    txt = lut[tres]
+    n = len(toff) - 1
+    dbio.write_sequence_db(b, range(n), (txt[int(toff[i]):int(toff[i + 1])].tobytes() for i in range(n)))
+    for ext in ("", ".index", ".dbtype"):
+        assert open(a + ext, "rb").read() == open(b + ext, "rb").read()
+    out = run("dbcopy", a, str(tmp_path / "c")).stdout
+    assert "%d entries, %d residues" % (n, int(toff[-1])) in out
+
+
 def test_row_formatter_matches_printf():
     """fastfmt.h: `%.3E` and integers of the result rows without stdio, byte for byte what printf prints (random doubles, the
     E-value range, values on and next to the four-digit rounding boundaries, denormals)"""
