@@ -60,6 +60,7 @@ class AlignParams(C.Structure):
         ("compBias", C.c_int),
         ("byteLanes", C.c_int), ("wordLanes", C.c_int),
         ("g", Gumbel),
+        ("covThr", C.c_float), ("covMode", C.c_int), ("seqIdThr", C.c_float), ("alnLenThr", C.c_int), ("seqIdMode", C.c_int),
     ]
 
 
@@ -158,6 +159,8 @@ def lib():
     L.spo_extract_frames.restype = C.c_int
     L.spo_format_row.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(Aln), C.c_int, C.c_int]
     L.spo_format_row.restype = C.c_int
+    L.spo_format_row_nobt.argtypes = L.spo_format_row.argtypes
+    L.spo_format_row_nobt.restype = C.c_int
     L.spo_nucl_default_params.argtypes = [C.POINTER(NuclParams), C.c_uint64]
     L.spo_nucl_default_params.restype = None
     L.spo_nucl_rescore.argtypes = [C.POINTER(NuclParams), C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int,
@@ -284,9 +287,10 @@ class Prefilter:
 
 
 def align_params(db_res_count, gap_open=16, gap_extend=2, eval_thr=200.0, comp_bias=1, gumbel=None,
-                 byte_lanes=32, word_lanes=16):
+                 byte_lanes=32, word_lanes=16, cov=0.0, cov_mode=0, min_seq_id=0.0, min_aln_len=0, seq_id_mode=0):
     g = Gumbel(**(gumbel or GUMBEL_VTML40_16_2))
-    return AlignParams(gap_open, gap_extend, eval_thr, db_res_count, comp_bias, byte_lanes, word_lanes, g)
+    return AlignParams(gap_open, gap_extend, eval_thr, db_res_count, comp_bias, byte_lanes, word_lanes, g,
+                       cov, cov_mode, min_seq_id, min_aln_len, seq_id_mode)
 
 
 def align_pair(m40, p, q, t):
@@ -306,9 +310,9 @@ def sw_forward(m40, p, q, t):
     return s.value, qe.value, te.value, w.value
 
 
-def format_row(tkey, a, qlen, tlen):
+def format_row(tkey, a, qlen, tlen, backtrace=True):
     buf = C.create_string_buffer(2048)
-    n = lib().spo_format_row(buf, tkey, C.byref(a), qlen, tlen)
+    n = (lib().spo_format_row if backtrace else lib().spo_format_row_nobt)(buf, tkey, C.byref(a), qlen, tlen)
     return buf.raw[:n].decode()
 
 
@@ -322,13 +326,13 @@ def bitscore(score, gumbel=None):
     return lib().spo_bitscore(C.byref(g), float(score))
 
 
-def align_query(m40, p, q, targets, keys):
+def align_query(m40, p, q, targets, keys, backtrace=True):
     """Align q against each (target residues, key); returns rows sorted like Matcher::compareHits."""
     res = []
     for t, key in zip(targets, keys):
         a = align_pair(m40, p, q, t)
         if a.ok == 1:
-            res.append((a.eval, -a.bits, len(t), key, format_row(key, a, len(q), len(t))))
+            res.append((a.eval, -a.bits, len(t), key, format_row(key, a, len(q), len(t), backtrace)))
     res.sort(key=lambda r: r[:4])
     return [r[4] for r in res]
 

@@ -1099,10 +1099,42 @@ static void rle_cigar(const char *bt, char *out, size_t outCap) { /* Matcher::co
     snprintf(out + o, outCap - o, "%zu%c", counter, state);
 }
 
+/* Util::canBeCovered, M/commons/Util.cpp:533-550 (float arithmetic, as there); case labels by value (Parameters.h:246-251:
+ * BIDIRECTIONAL 0, TARGET 1, QUERY 2, LENGTH_QUERY 3, LENGTH_TARGET 4, LENGTH_SHORTER 5) */
+static int spo_can_be_covered(float covThr, int covMode, float qLen, float tLen) {
+    switch (covMode) {
+    case 0: return (qLen / tLen >= covThr) && (tLen / qLen >= covThr);
+    case 2: return (tLen / qLen) >= covThr;
+    case 1: return (qLen / tLen) >= covThr;
+    case 3: return ((tLen / qLen) >= covThr) && (tLen / qLen) <= 1.0;
+    case 4: return ((qLen / tLen) >= covThr) && (qLen / tLen) <= 1.0;
+    case 5: return ((tLen < qLen ? tLen : qLen) / (tLen > qLen ? tLen : qLen)) >= covThr;
+    default: return 1;
+    }
+}
+
+/* Util::hasCoverage, M/commons/Util.cpp:552-567 */
+static int spo_has_coverage(float covThr, int covMode, float qCov, float tCov) {
+    switch (covMode) {
+    case 0: return (qCov >= covThr) && (tCov >= covThr);
+    case 2: return qCov >= covThr;
+    case 1: return tCov >= covThr;
+    default: return 1;
+    }
+}
+
+/* SmithWaterman::computeCov, StripedSmithWaterman.cpp:1055-1057 */
+static float spo_compute_cov(unsigned start, unsigned end, unsigned len) {
+    unsigned hi = start > end ? start : end, lo = start < end ? start : end;
+    return ((len < hi ? len : hi) - lo + 1) / (float)len;
+}
+
 void spo_align_pair(const spo_matrix *m, const spo_align_params *p, const unsigned char *q, int L,
                     const unsigned char *t, int tLen, spo_aln *out) {
     memset(out, 0, sizeof(*out));
     out->qStart = out->tStart = -1;
+    /* the pair is skipped when its lengths cannot reach the coverage (Alignment.cpp:378-381) */
+    if (!spo_can_be_covered(p->covThr, p->covMode, (float)L, (float)tLen)) return;
     signed char *cb = (signed char *)malloc((size_t)L);
     int *sc = (int *)malloc(sizeof(int) * (size_t)L * SPO_ALPH);
     int bias = build_profile(m, p->compBias, q, L, cb, sc);
@@ -1130,6 +1162,11 @@ void spo_align_pair(const spo_matrix *m, const spo_align_params *p, const unsign
     out->qStart = b.read - r.read;
     int dl = out->tEnd - out->tStart + 1, ql = out->qEnd - out->qStart + 1;
     int bw = abs(dl - ql) + 1;
+    /* coverage of the final coordinates (:226-232): below the threshold ssw_align returns without a backtrace and
+     * checkCriteria rejects the pair on the same test */
+    const float qCov = spo_compute_cov((unsigned)out->qStart, (unsigned)out->qEnd, (unsigned)L);
+    const float tCov = spo_compute_cov((unsigned)out->tStart, (unsigned)out->tEnd, (unsigned)tLen);
+    if (!spo_has_coverage(p->covThr, p->covMode, qCov, tCov)) { free(cb); free(sc); return; }
     char *bt = banded_trace(t + out->tStart, q + out->qStart, cb + out->qStart, dl, ql, b.score, go, ge, bw, m);
     int ids = 0;
     if (bt) {
@@ -1148,8 +1185,11 @@ void spo_align_pair(const spo_matrix *m, const spo_align_params *p, const unsign
         out->alnLen = (a > d ? a : d) + 1;
     }
     out->nIdent = ids;
-    out->seqId = (float)ids / (float)out->alnLen; /* Util::computeSeqId, --seq-id-mode 0 */
-    out->ok = (out->eval <= p->evalThr) ? 1 : 0;  /* Alignment::checkCriteria, Alignment.cpp:555-574 */
+    /* Util::computeSeqId, M/commons/Util.cpp:588-598 */
+    const int idDen = p->seqIdMode == 1 ? (L < tLen ? L : tLen) : p->seqIdMode == 2 ? (L > tLen ? L : tLen) : out->alnLen;
+    out->seqId = (float)ids / (float)idDen;
+    /* Alignment::checkCriteria, Alignment.cpp:555-574 (coverage was tested above) */
+    out->ok = (out->eval <= p->evalThr && out->seqId >= p->seqIdThr && out->alnLen >= p->alnLenThr) ? 1 : 0;
     free(cb); free(sc);
 }
 
@@ -1190,6 +1230,15 @@ int spo_format_row(char *buf, uint32_t tKey, const spo_aln *a, int qLen, int tLe
     }
     return sprintf(buf, "%u\t%d\t%s\t%.3E\t%d\t%d\t%d\t%d\t%d\t%d\t%s\n", tKey, a->bits, sid, a->eval,
                    a->qStart, a->qEnd, qLen, a->tStart, a->tEnd, tLen, a->cigar);
+}
+
+/* the same row without the backtrace column: `--alignment-mode 3` without `-a` (addBacktrace == false, Matcher.cpp:355-367) */
+int spo_format_row_nobt(char *buf, uint32_t tKey, const spo_aln *a, int qLen, int tLen) {
+    int n = spo_format_row(buf, tKey, a, qLen, tLen);
+    while (n > 0 && buf[n - 1] != '\t') n--;
+    buf[n - 1] = '\n';
+    buf[n] = 0;
+    return n;
 }
 
 /* =========================================================================================================

@@ -1,0 +1,108 @@
+#!/usr/bin/env python
+"""Golden fixtures for the acceptance criteria of `align` from the REFERENCE binary (oracle/_ref/spacepharer); development time only.
+
+  tests/golden/criteria/<set>_<tag>.txt.gz   alignment DBs of the `small` (all-pairs subset, 9-15 aa queries) and `long` (all pairs,
+                                             17-150 aa queries, gapped tracebacks) sets under -c / --cov-mode 0..5, --min-seq-id,
+                                             --seq-id-mode, --min-aln-len (Alignment.cpp:353-404 canBeCovered + checkCriteria,
+                                             StripedSmithWaterman.cpp:195-240 coverage exits, Util.cpp:533-567), and the
+                                             10-column rows of `--alignment-mode 3` without `-a` (Matcher.cpp:355-366)
+  tests/golden/criteria/cases.json           the flag set of every fixture
+Usage: python tools/gen_golden_criteria.py
+"""
+import gzip
+import json
+import os
+import shutil
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from gen_golden import dump_db, run  # noqa: E402
+from oracle import refbin  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+# tag -> (set, evalue, cov, cov_mode, min_seq_id, min_aln_len, backtrace, seq_id_mode); cov modes: Parameters.h:246-251
+# (0 query and target, 1 target, 2 query, 3 / 4 / 5 length ratios)
+CASES = {
+    "small_c0.05_m0": ("small", "200", 0.05, 0, 0.0, 0, 1, 0),
+    "small_c0.05_m1": ("small", "200", 0.05, 1, 0.0, 0, 1, 0),
+    "small_c0.5_m2": ("small", "200", 0.5, 2, 0.0, 0, 1, 0),
+    "small_c0.8_m2": ("small", "200", 0.8, 2, 0.0, 0, 1, 0),
+    "small_c0.1_m3": ("small", "200", 0.1, 3, 0.0, 0, 1, 0),
+    "small_c0.05_m4": ("small", "200", 0.05, 4, 0.0, 0, 1, 0),
+    "small_c0.05_m5": ("small", "200", 0.05, 5, 0.0, 0, 1, 0),
+    "small_id0.8": ("small", "200", 0.0, 0, 0.8, 0, 1, 0),
+    "small_len9": ("small", "200", 0.0, 0, 0.0, 9, 1, 0),
+    "small_noback": ("small", "200", 0.0, 0, 0.0, 0, 0, 0),
+    "long_c0.5_m0": ("long", "1.000E-01", 0.5, 0, 0.0, 0, 1, 0),
+    "long_c0.3_m1": ("long", "1.000E-01", 0.3, 1, 0.0, 0, 1, 0),
+    "long_c0.7_m2": ("long", "1.000E-01", 0.7, 2, 0.0, 0, 1, 0),
+    "long_c0.5_m3": ("long", "1.000E-01", 0.5, 3, 0.0, 0, 1, 0),
+    "long_c0.5_m4": ("long", "1.000E-01", 0.5, 4, 0.0, 0, 1, 0),
+    "long_c0.5_m5": ("long", "1.000E-01", 0.5, 5, 0.0, 0, 1, 0),
+    "long_id0.6": ("long", "1.000E-01", 0.0, 0, 0.6, 0, 1, 0),
+    "long_id0.3_mode1": ("long", "1.000E-01", 0.0, 0, 0.3, 0, 1, 1),
+    "long_id0.3_mode2": ("long", "1.000E-01", 0.0, 0, 0.3, 0, 1, 2),
+    "long_len40": ("long", "1.000E-01", 0.0, 0, 0.0, 40, 1, 0),
+    "long_c0.6_m2_id0.5_len25": ("long", "1.000E-01", 0.6, 2, 0.5, 25, 1, 0),
+    "long_c0.6_m2_id0.5_len25_noback": ("long", "1.000E-01", 0.6, 2, 0.5, 25, 0, 0),
+}
+
+
+def aln_flags(evalue, cov, cov_mode, seq_id, aln_len, backtrace, id_mode):
+    f = refbin.ALN_FLAGS.format(evalue=evalue, go=16, ge=2, threads=4)
+    f = f.replace(" -c 0 --cov-mode 0 ", " -c %g --cov-mode %d " % (cov, cov_mode))
+    f = f.replace("--min-seq-id 0 --min-aln-len 0", "--min-seq-id %g --min-aln-len %d" % (seq_id, aln_len))
+    f = f.replace("--seq-id-mode 0", "--seq-id-mode %d" % id_mode)
+    if not backtrace:
+        f = f.replace("-a 1 --alignment-mode 2", "-a 0 --alignment-mode 3")
+    return f
+
+
+def main():
+    assert refbin.available(), "build the reference first: make -C oracle ref"
+    B = refbin.REF_BIN
+    out = os.path.join(GOLD, "criteria")
+    os.makedirs(out, exist_ok=True)
+    work = tempfile.mkdtemp(prefix="spgoldc_")
+    n_seq = {}
+    for name in ("small", "long"):
+        w = os.path.join(work, name)
+        os.makedirs(w)
+        for n in ("t", "q"):
+            with gzip.open(os.path.join(GOLD, name, n + ".fasta.gz"), "rb") as f, open(os.path.join(w, n + ".fasta"), "wb") as g:
+                g.write(f.read())
+            run("%s createdb %s/%s.fasta %s/%sdb --dbtype 1 --shuffle 0" % (B, w, n, w, n))
+        nT = sum(1 for _ in open(os.path.join(w, "tdb.index")))
+        nQ = sum(1 for _ in open(os.path.join(w, "qdb.index")))
+        n_seq[name] = (nT, nQ)
+        # the all-pairs prefilter DBs of tools/gen_golden.py: every third target for the first 40 queries (small), all pairs (long)
+        with open(os.path.join(w, "allpairs"), "wb") as f, open(os.path.join(w, "allpairs.index"), "w") as fi:
+            pos = 0
+            for q in range(nQ):
+                if name == "small":
+                    body = b"".join(b"%d\t0\t0\n" % t for t in range(0, nT, 3)) if q < 40 else b""
+                else:
+                    body = b"".join(b"%d\t0\t0\n" % t for t in range(nT))
+                f.write(body + b"\0")
+                fi.write("%d\t%d\t%d\n" % (q, pos, len(body) + 1))
+                pos += len(body) + 1
+        with open(os.path.join(w, "allpairs.dbtype"), "wb") as f:
+            f.write((7).to_bytes(4, "little"))        # DBTYPE_PREFILTER_RES
+    for tag, (name, ev, cov, mode, sid, alen, back, idm) in CASES.items():
+        w = os.path.join(work, name)
+        run("%s align %s/qdb %s/tdb %s/allpairs %s/aln_%s %s" % (B, w, w, w, w, tag, aln_flags(ev, cov, mode, sid, alen, back, idm)))
+        dump_db(os.path.join(w, "aln_" + tag), os.path.join(out, tag + ".txt.gz"))
+    with open(os.path.join(out, "cases.json"), "w") as f:
+        json.dump({t: dict(set=c[0], evalue=float(c[1]), cov=c[2], cov_mode=c[3], min_seq_id=c[4], min_aln_len=c[5], backtrace=c[6],
+                        seq_id_mode=c[7])
+                   for t, c in CASES.items()}, f, indent=1)
+    shutil.rmtree(work)
+    print("criteria fixtures written")
+
+
+if __name__ == "__main__":
+    main()
