@@ -132,6 +132,15 @@ typedef struct spb_align_params {
     int32_t comp_bias;
     int32_t byte_lanes, word_lanes; /* SIMD layout of the emulated reference build: 32/16 (AVX2), 16/8 (SSE) */
     spb_gumbel gumbel;
+    /* Acceptance criteria beyond the E-value (all 0 in the predictmatch search): a pair is reported when its lengths can reach
+     * the coverage (Util::canBeCovered, M/commons/Util.cpp:533-550, tested before the alignment in Alignment.cpp:378) and its
+     * alignment passes Alignment::checkCriteria (Alignment.cpp:555-574; Util::hasCoverage Util.cpp:552-567). */
+    float cov_thr;                  /* -c */
+    int32_t cov_mode;               /* --cov-mode: 0 query and target, 1 target, 2 query, 3 / 4 / 5 length ratios (Parameters.h:246-251) */
+    float seq_id_thr;               /* --min-seq-id */
+    int32_t aln_len_thr;            /* --min-aln-len */
+    int32_t seq_id_mode;            /* --seq-id-mode: identities / 0 alignment length, 1 shorter, 2 longer sequence (Util.cpp:588-598) */
+    int32_t reserved;               /* 0 */
 } spb_align_params;
 
 typedef struct spb_aln {     /* Matcher::result_t, M/alignment/Matcher.h:24-119 */

@@ -159,6 +159,8 @@ def lib():
     L.spo_extract_frames.restype = C.c_int
     L.spo_format_row.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(Aln), C.c_int, C.c_int]
     L.spo_format_row.restype = C.c_int
+    L.spo_can_be_covered.argtypes = [C.c_float, C.c_int, C.c_float, C.c_float]
+    L.spo_can_be_covered.restype = C.c_int
     L.spo_format_row_nobt.argtypes = L.spo_format_row.argtypes
     L.spo_format_row_nobt.restype = C.c_int
     L.spo_nucl_default_params.argtypes = [C.POINTER(NuclParams), C.c_uint64]
@@ -308,6 +310,18 @@ def sw_forward(m40, p, q, t):
     lib().spo_sw_forward(C.byref(m40), C.byref(p), _u8(q), len(q), _u8(t), len(t),
                          C.byref(s), C.byref(qe), C.byref(te), C.byref(w))
     return s.value, qe.value, te.value, w.value
+
+
+def can_be_covered(cov, cov_mode, qlen, tlen):
+    return bool(lib().spo_can_be_covered(cov, cov_mode, float(qlen), float(tlen)))
+
+
+def prefilter_coverage_filter(rows, cov, cov_mode, qlen, tlens):
+    """Prefiltering.cpp:834-842: with -c > 0 and --cov-mode 0 / 2 / 5 the hits whose lengths cannot reach the coverage are not
+    written (after the max-seqs cut); rows = [(target id, score, diagonal)], tlens = target lengths by id"""
+    if not (cov > 0.0 and cov_mode in (0, 2, 5)):
+        return list(rows)
+    return [r for r in rows if can_be_covered(cov, cov_mode, qlen, tlens[r[0]])]
 
 
 def format_row(tkey, a, qlen, tlen, backtrace=True):

@@ -1101,7 +1101,7 @@ static void rle_cigar(const char *bt, char *out, size_t outCap) { /* Matcher::co
 
 /* Util::canBeCovered, M/commons/Util.cpp:533-550 (float arithmetic, as there); case labels by value (Parameters.h:246-251:
  * BIDIRECTIONAL 0, TARGET 1, QUERY 2, LENGTH_QUERY 3, LENGTH_TARGET 4, LENGTH_SHORTER 5) */
-static int spo_can_be_covered(float covThr, int covMode, float qLen, float tLen) {
+int spo_can_be_covered(float covThr, int covMode, float qLen, float tLen) {
     switch (covMode) {
     case 0: return (qLen / tLen >= covThr) && (tLen / qLen >= covThr);
     case 2: return (tLen / qLen) >= covThr;

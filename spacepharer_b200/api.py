@@ -322,24 +322,28 @@ class Searcher:
         pair_targets = np.ascontiguousarray(pair_targets, dtype=np.uint32)
         capi.check(self.lib.spb_pairs_set(self.h, _u64(pair_off), pair_targets.ctypes.data_as(C.POINTER(C.c_uint32))))
 
-    def _align_params(self, db_res_count, evalue, gap_open, gap_extend, comp_bias, gumbel, byte_lanes, word_lanes):
+    def _align_params(self, db_res_count, evalue, gap_open, gap_extend, comp_bias, gumbel, byte_lanes, word_lanes,
+                      cov=0.0, cov_mode=0, min_seq_id=0.0, min_aln_len=0, seq_id_mode=0):
+        """cov / cov_mode / min_seq_id / min_aln_len / seq_id_mode: `-c`, `--cov-mode`, `--min-seq-id`, `--min-aln-len`,
+        `--seq-id-mode` of the align module (Alignment.cpp:378,396,555-574); all 0 in the predictmatch search"""
         g = capi.Gumbel(*(gumbel or gumbel_for(self.sub_mat_name, gap_open, gap_extend)))
-        return capi.AlignParams(gap_open, gap_extend, evalue, db_res_count, comp_bias, byte_lanes, word_lanes, g)
+        return capi.AlignParams(gap_open, gap_extend, evalue, db_res_count, comp_bias, byte_lanes, word_lanes, g,
+                                cov, cov_mode, min_seq_id, min_aln_len, seq_id_mode, 0)
 
     def align_resident(self, db_res_count, evalue=200.0, gap_open=16, gap_extend=2, comp_bias=1, gumbel=None,
-                       byte_lanes=32, word_lanes=16):
-        p = self._align_params(db_res_count, evalue, gap_open, gap_extend, comp_bias, gumbel, byte_lanes, word_lanes)
+                       byte_lanes=32, word_lanes=16, **criteria):
+        p = self._align_params(db_res_count, evalue, gap_open, gap_extend, comp_bias, gumbel, byte_lanes, word_lanes, **criteria)
         capi.check(self.lib.spb_align_resident(self.h, C.byref(p)))
         R = capi.AlignResult()
         capi.check(self.lib.spb_align_stats(self.h, C.byref(R)))
         return self._aln_stats(R)
 
     def pairs_exhaustive(self, db_res_count, evalue=200.0, gap_open=16, gap_extend=2, comp_bias=1, gumbel=None,
-                         byte_lanes=32, word_lanes=16):
+                         byte_lanes=32, word_lanes=16, **criteria):
         """Exhaustive search (BASELINE config 5): score the resident queries against EVERY alignment target with the
         streaming register kernel; the pairs reaching the E-value threshold become the resident pair list.
         -> stats dict (n_scored, n_cells, n_kept, n_unfiltered, n_pairs, kernel_ms, total_ms, gcups)"""
-        p = self._align_params(db_res_count, evalue, gap_open, gap_extend, comp_bias, gumbel, byte_lanes, word_lanes)
+        p = self._align_params(db_res_count, evalue, gap_open, gap_extend, comp_bias, gumbel, byte_lanes, word_lanes, **criteria)
         E = capi.ExhaustiveStats()
         capi.check(self.lib.spb_pairs_exhaustive(self.h, C.byref(p), C.byref(E)))
         st = {n: getattr(E, n) for n, _ in capi.ExhaustiveStats._fields_}
@@ -387,7 +391,8 @@ class Searcher:
         """Fused predictmatch search step: prefilter -> align with the hit lists kept in HBM.
         kw: kmer_thr, max_seqs, min_ungapped_score, bin_size, comp_bias, evalue, gap_open, gap_extend, gumbel"""
         pk = {k: kw[k] for k in ("kmer_thr", "max_seqs", "min_ungapped_score", "bin_size", "comp_bias", "id_base") if k in kw}
-        ak = {k: kw[k] for k in ("evalue", "gap_open", "gap_extend", "comp_bias", "gumbel", "byte_lanes", "word_lanes") if k in kw}
+        ak = {k: kw[k] for k in ("evalue", "gap_open", "gap_extend", "comp_bias", "gumbel", "byte_lanes", "word_lanes", "cov", "cov_mode",
+                                 "min_seq_id", "min_aln_len", "seq_id_mode") if k in kw}
         self.set_queries(qres, qoff)
         pst = self.prefilter_resident(**pk)
         pref = self.prefilter_fetch() if fetch_prefilter else None
@@ -430,14 +435,14 @@ class Searcher:
         capi.check(self.lib.spb_align_set_targets(self.h, _u8(tres), _u64(toff), self.aT, kp))
 
     def align(self, qres, qoff, pair_off, pair_targets, db_res_count, evalue=200.0, gap_open=16, gap_extend=2,
-              comp_bias=1, gumbel=None, byte_lanes=32, word_lanes=16):
-        """-> (offsets uint64[Q+1], rows structured array, cigar bytes, stats)"""
+              comp_bias=1, gumbel=None, byte_lanes=32, word_lanes=16, **criteria):
+        """-> (offsets uint64[Q+1], rows structured array, cigar bytes, stats); criteria: see _align_params"""
         qres = np.ascontiguousarray(qres, dtype=np.uint8)
         qoff = np.ascontiguousarray(qoff, dtype=np.uint64)
         pair_off = np.ascontiguousarray(pair_off, dtype=np.uint64)
         pair_targets = np.ascontiguousarray(pair_targets, dtype=np.uint32)
         Q = len(qoff) - 1
-        p = self._align_params(db_res_count, evalue, gap_open, gap_extend, comp_bias, gumbel, byte_lanes, word_lanes)
+        p = self._align_params(db_res_count, evalue, gap_open, gap_extend, comp_bias, gumbel, byte_lanes, word_lanes, **criteria)
         r = C.POINTER(capi.AlignResult)()
         capi.check(self.lib.spb_align(self.h, _u8(qres), _u64(qoff), Q, _u64(pair_off),
                                       pair_targets.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(p), C.byref(r)))
@@ -604,14 +609,16 @@ def format_seq_id(x):
     return s + str(int(np.float32(x * np.float32(1000))))
 
 
-def format_align_rows(rows, cigar, q_lens, t_lens, keys=None):
-    """Matcher::resultToBuffer (M/alignment/Matcher.cpp:323-370)"""
+def format_align_rows(rows, cigar, q_lens, t_lens, keys=None, backtrace=True):
+    """Matcher::resultToBuffer (M/alignment/Matcher.cpp:323-370); backtrace=False: the ten columns of `--alignment-mode 3`
+    without `-a`"""
     out = []
     for r in rows:
         t = int(r["target"])
         ops = cigar[int(r["cigar_off"]): int(r["cigar_off"]) + int(r["cigar_len"])].decode()
-        out.append("%d\t%d\t%s\t%.3E\t%d\t%d\t%d\t%d\t%d\t%d\t%s" % (
+        row = "%d\t%d\t%s\t%.3E\t%d\t%d\t%d\t%d\t%d\t%d" % (
             int(keys[t]) if keys is not None else t, int(r["bits"]), format_seq_id(r["seq_id"]), float(r["eval"]),
             int(r["q_start"]), int(r["q_end"]), int(q_lens[int(r["query"])]), int(r["t_start"]), int(r["t_end"]),
-            int(t_lens[t]), compress_cigar(ops) if ops else ""))
+            int(t_lens[t]))
+        out.append(row + "\t" + (compress_cigar(ops) if ops else "") if backtrace else row)
     return out

@@ -39,7 +39,9 @@ class PrefilterResult(C.Structure):
 class AlignParams(C.Structure):
     _fields_ = [("gap_open", C.c_int32), ("gap_extend", C.c_int32), ("eval_thr", C.c_double),
                 ("db_res_count", C.c_uint64), ("comp_bias", C.c_int32), ("byte_lanes", C.c_int32),
-                ("word_lanes", C.c_int32), ("gumbel", Gumbel)]
+                ("word_lanes", C.c_int32), ("gumbel", Gumbel),
+                ("cov_thr", C.c_float), ("cov_mode", C.c_int32), ("seq_id_thr", C.c_float), ("aln_len_thr", C.c_int32),
+                ("seq_id_mode", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Aln(C.Structure):

@@ -839,19 +839,76 @@ __global__ void count_widen_kernel(const uint32_t *__restrict__ cnt, uint32_t Q,
 // target length asc, target key asc
 struct RowKey { double eval; int bits; uint32_t tlen, tkey, pad; };
 
-__global__ void pack_rows_kernel(const PairOut *__restrict__ out, const uint32_t *__restrict__ acc, uint32_t nAcc,
-                                 const uint32_t *__restrict__ pairQ, const uint32_t *__restrict__ pairT, spb_aln *__restrict__ rows,
-                                 const uint64_t *__restrict__ toff, const uint32_t *__restrict__ tkeys, RowKey *__restrict__ keys) {
+// Util::computeSeqId (M/commons/Util.cpp:588-598): identities over the alignment length (--seq-id-mode 0), the shorter (1) or the
+// longer (2) sequence
+__device__ __forceinline__ float seq_id_of(int mode, int nIdent, int qLen, int tLen, int alnLen) {
+    const int den = mode == 1 ? min(qLen, tLen) : mode == 2 ? max(qLen, tLen) : alnLen;
+    return (float)nIdent / (float)den;
+}
+
+// Acceptance criteria beyond the E-value (all zero in the predictmatch search).  The reference skips a pair whose lengths cannot
+// reach the coverage before aligning it (Util::canBeCovered, M/commons/Util.cpp:533-550; Alignment.cpp:378-381) and drops an
+// alignment that fails Alignment::checkCriteria (Alignment.cpp:555-574; Util::hasCoverage Util.cpp:552-567; the coverage exit of
+// ssw_align, StripedSmithWaterman.cpp:226-232, rejects the same pairs).  --max-accept / --max-rejected are unlimited on this path,
+// so the outcome of a pair does not depend on its neighbours and both tests run on the finished alignment, one thread per pair.
+struct Criteria { float covThr; int covMode; float seqIdThr; int alnLenThr; int seqIdMode; };
+
+__device__ __forceinline__ bool can_be_covered(float covThr, int covMode, float qLen, float tLen) {
+    switch (covMode) {      // Parameters.h:246-251
+    case 0: return (qLen / tLen >= covThr) && (tLen / qLen >= covThr);
+    case 1: return (qLen / tLen) >= covThr;
+    case 2: return (tLen / qLen) >= covThr;
+    case 3: return ((tLen / qLen) >= covThr) && (tLen / qLen) <= 1.0f;
+    case 4: return ((qLen / tLen) >= covThr) && (qLen / tLen) <= 1.0f;
+    case 5: return (fminf(tLen, qLen) / fmaxf(tLen, qLen)) >= covThr;
+    default: return true;
+    }
+}
+
+__device__ __forceinline__ bool has_coverage(float covThr, int covMode, float qCov, float tCov) {
+    switch (covMode) {
+    case 0: return (qCov >= covThr) && (tCov >= covThr);
+    case 1: return tCov >= covThr;
+    case 2: return qCov >= covThr;
+    default: return true;
+    }
+}
+
+__global__ void criteria_kernel(const PairOut *__restrict__ out, const uint32_t *__restrict__ acc, uint32_t nAcc,
+                                const uint32_t *__restrict__ pairQ, const uint32_t *__restrict__ pairT,
+                                const uint64_t *__restrict__ qoff, const uint64_t *__restrict__ toff, Criteria cr,
+                                uint8_t *__restrict__ keep) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nAcc) return;
     const uint32_t pair = acc[k];
     const PairOut o = out[pair];
+    const uint32_t q = pairQ[pair], t = pairT[pair];
+    const unsigned qLen = (unsigned)(qoff[q + 1] - qoff[q]), tLen = (unsigned)(toff[t + 1] - toff[t]);
+    bool ok = can_be_covered(cr.covThr, cr.covMode, (float)qLen, (float)tLen);
+    // SmithWaterman::computeCov (StripedSmithWaterman.cpp:1055-1057) on the final coordinates
+    const float qCov = (float)(unsigned)(o.qEnd - o.qStart + 1) / (float)qLen;
+    const float tCov = (float)(unsigned)(o.tEnd - o.tStart + 1) / (float)tLen;
+    ok = ok && has_coverage(cr.covThr, cr.covMode, qCov, tCov);
+    ok = ok && seq_id_of(cr.seqIdMode, o.nIdent, (int)qLen, (int)tLen, o.alnLen) >= cr.seqIdThr;
+    ok = ok && o.alnLen >= cr.alnLenThr;
+    keep[k] = ok ? 1 : 0;
+}
+
+__global__ void pack_rows_kernel(const PairOut *__restrict__ out, const uint32_t *__restrict__ acc, uint32_t nAcc,
+                                 const uint32_t *__restrict__ pairQ, const uint32_t *__restrict__ pairT, spb_aln *__restrict__ rows,
+                                 const uint64_t *__restrict__ toff, const uint32_t *__restrict__ tkeys, RowKey *__restrict__ keys,
+                                 const uint64_t *__restrict__ qoff, int seqIdMode) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nAcc) return;
+    const uint32_t pair = acc[k];
+    const PairOut o = out[pair];
+    uint32_t tlen;
     {
         const uint32_t t = pairT[pair];
         RowKey rk;
         rk.eval = o.eval;
         rk.bits = o.bits;
-        rk.tlen = (uint32_t)min((unsigned long long)(toff[t + 1] - toff[t]), 0xFFFFFFFFull);
+        rk.tlen = tlen = (uint32_t)min((unsigned long long)(toff[t + 1] - toff[t]), 0xFFFFFFFFull);
         rk.tkey = tkeys[t];
         rk.pad = 0;
         keys[k] = rk;
@@ -865,7 +922,8 @@ __global__ void pack_rows_kernel(const PairOut *__restrict__ out, const uint32_t
     r.q_start = o.qStart; r.q_end = o.qEnd; r.t_start = o.tStart; r.t_end = o.tEnd;
     r.n_ident = o.nIdent;
     r.aln_len = o.alnLen;
-    r.seq_id = (float)o.nIdent / (float)o.alnLen;   // Util::computeSeqId, --seq-id-mode 0
+    r.seq_id = seqIdMode == 0 ? (float)o.nIdent / (float)o.alnLen
+                              : seq_id_of(seqIdMode, o.nIdent, (int)(qoff[r.query + 1] - qoff[r.query]), (int)tlen, o.alnLen);
     r.cigar_off = o.cigOff;
     r.cigar_len = o.cigLen;
     r.reserved = 0;
@@ -1180,6 +1238,8 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
     SPB_CHECK(c->have_queries && c->have_pairs, "spb_align: no resident queries / pairs");
     SPB_CHECK(p->gap_open >= 0 && p->gap_open <= 255 && p->gap_extend >= 0 && p->gap_extend <= 255, "spb_align: gap costs out of range");
     SPB_CHECK(p->byte_lanes > 0 && p->word_lanes > 0, "spb_align: lanes must be positive");
+    SPB_CHECK(p->cov_mode >= 0 && p->cov_mode <= 5 && p->seq_id_mode >= 0 && p->seq_id_mode <= 2,
+              "spb_align: cov_mode must be 0..5 and seq_id_mode 0..2");
     cudaStream_t st = c->stream;
     const uint32_t Q = c->Q;
     const uint64_t NP = c->n_pairs;
@@ -1387,17 +1447,38 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
         SPB_CUDA(cudaGetLastError()); c->n_launches++;
         c->n_cigar = cigTotal;
     }
+    // ---- -c / --cov-mode / --min-seq-id / --min-aln-len: the accepted list shrinks to the pairs that pass (their CIGAR slices
+    // stay where they are; the slices of dropped pairs become slack of the CIGAR buffer).  Not on the predictmatch path.
+    uint32_t nRows = nAcc;
+    const uint32_t *accRows = c->d_acc.as<uint32_t>();
+    if (nAcc && (p->cov_thr != 0.0f || p->cov_mode != 0 || p->seq_id_thr != 0.0f || p->aln_len_thr != 0)) {
+        Criteria cr;
+        cr.covThr = p->cov_thr; cr.covMode = p->cov_mode; cr.seqIdThr = p->seq_id_thr; cr.alnLenThr = p->aln_len_thr;
+        cr.seqIdMode = p->seq_id_mode;
+        uint8_t *keep = c->s_e.as<uint8_t>();            // (the E-value flags are dead: d_acc was selected from them)
+        uint32_t *kept = c->s_q.as<uint32_t>();          // (the sorted pair list of the forward kernel is dead too)
+        criteria_kernel<<<(nAcc + 255) / 256, 256, 0, st>>>(c->d_pairout.as<PairOut>(), accRows, nAcc, c->d_pairQ.as<uint32_t>(),
+                                                            c->d_pairT.as<uint32_t>(), c->d_qoff64.as<uint64_t>(), c->d_aoff.as<uint64_t>(),
+                                                            cr, keep);
+        SPB_CUDA(cudaGetLastError()); c->n_launches++;
+        SPB_CUDA(cub::DeviceSelect::Flagged(nullptr, tmpBytes, accRows, keep, kept, d_nAcc, (int)nAcc, st));
+        if (c->s_cub.ensure(tmpBytes)) return 1;
+        SPB_CUDA(cub::DeviceSelect::Flagged(c->s_cub.p, tmpBytes, accRows, keep, kept, d_nAcc, (int)nAcc, st));
+        SPB_CUDA(cudaMemcpyAsync(&nRows, d_nAcc, 4, cudaMemcpyDeviceToHost, st));
+        SPB_CUDA(cudaStreamSynchronize(st));
+        accRows = kept;
+    }
     // ---- result rows: per query in the order of Matcher::compareHits (part of the stage: `align` writes sorted entries)
     {
         // scratch: s_g packed rows, s_i row counts u32[Q+1] + u64[Q+1] widened
-        if (c->s_g.ensure(std::max<size_t>(nAcc, 1) * sizeof(spb_aln)) || c->d_rows.ensure(std::max<size_t>(nAcc, 1) * sizeof(spb_aln)) ||
+        if (c->s_g.ensure(std::max<size_t>(nRows, 1) * sizeof(spb_aln)) || c->d_rows.ensure(std::max<size_t>(nRows, 1) * sizeof(spb_aln)) ||
             c->s_i.ensure(((size_t)Q + 1) * 12 + 64) || c->d_rowoff.ensure(((size_t)Q + 1) * 8 + 64)) return 1;
         uint32_t *cnt32 = c->s_i.as<uint32_t>();
         uint64_t *cnt64 = reinterpret_cast<uint64_t *>(c->s_i.as<unsigned char>() + (((size_t)Q + 1) * 4 + 15) / 16 * 16);
         uint64_t *rowOff = c->d_rowoff.as<uint64_t>();
         SPB_CUDA(cudaMemsetAsync(cnt32, 0, ((size_t)Q + 1) * 4, st));
-        if (nAcc) {
-            row_count_kernel<<<(nAcc + 255) / 256, 256, 0, st>>>(c->d_acc.as<uint32_t>(), nAcc, c->d_pairQ.as<uint32_t>(), cnt32);
+        if (nRows) {
+            row_count_kernel<<<(nRows + 255) / 256, 256, 0, st>>>(accRows, nRows, c->d_pairQ.as<uint32_t>(), cnt32);
             SPB_CUDA(cudaGetLastError()); c->n_launches++;
         }
         count_widen_kernel<<<(Q + 1 + 255) / 256, 256, 0, st>>>(cnt32, Q, cnt64);
@@ -1405,13 +1486,14 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
         SPB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, cnt64, rowOff, (int)(Q + 1), st));
         if (c->s_cub.ensure(tmpBytes)) return 1;
         SPB_CUDA(cub::DeviceScan::ExclusiveSum(c->s_cub.p, tmpBytes, cnt64, rowOff, (int)(Q + 1), st));
-        if (nAcc) {
-            if (c->s_h.ensure((size_t)nAcc * sizeof(RowKey) + 64)) return 1;     // (the H/E scratch of the reverse pass is dead by now)
-            pack_rows_kernel<<<(nAcc + 255) / 256, 256, 0, st>>>(c->d_pairout.as<PairOut>(), c->d_acc.as<uint32_t>(), nAcc,
+        if (nRows) {
+            if (c->s_h.ensure((size_t)nRows * sizeof(RowKey) + 64)) return 1;     // (the H/E scratch of the reverse pass is dead by now)
+            pack_rows_kernel<<<(nRows + 255) / 256, 256, 0, st>>>(c->d_pairout.as<PairOut>(), accRows, nRows,
                                                                  c->d_pairQ.as<uint32_t>(), c->d_pairT.as<uint32_t>(), c->s_g.as<spb_aln>(),
-                                                                 c->d_aoff.as<uint64_t>(), c->d_akeys.as<uint32_t>(), c->s_h.as<RowKey>());
+                                                                 c->d_aoff.as<uint64_t>(), c->d_akeys.as<uint32_t>(), c->s_h.as<RowKey>(),
+                                                                 c->d_qoff64.as<uint64_t>(), p->seq_id_mode);
             SPB_CUDA(cudaGetLastError()); c->n_launches++;
-            rank_rows_kernel<<<(nAcc + 255) / 256, 256, 0, st>>>(c->s_g.as<spb_aln>(), c->s_h.as<RowKey>(), nAcc, rowOff, c->d_rows.as<spb_aln>());
+            rank_rows_kernel<<<(nRows + 255) / 256, 256, 0, st>>>(c->s_g.as<spb_aln>(), c->s_h.as<RowKey>(), nRows, rowOff, c->d_rows.as<spb_aln>());
             SPB_CUDA(cudaGetLastError()); c->n_launches++;
             if (c->pairs_max_per_query > RR_MAX) {      // lists longer than the per-thread rank loop takes: one warp per query
                 sort_rows_kernel<<<(Q + SR_WARPS - 1) / SR_WARPS, SR_WARPS * 32, 0, st>>>(c->s_g.as<spb_aln>(), rowOff, Q, c->d_aoff.as<uint64_t>(),
@@ -1424,8 +1506,8 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
     SPB_CUDA(cudaStreamSynchronize(st));
     SPB_CUDA(cudaEventElapsedTime(&ms, c->ev2, c->ev3));
     c->aln_stats.total_ms = ms;
-    c->aln_stats.n_rows = nAcc;
-    c->n_acc = nAcc;
+    c->aln_stats.n_rows = nRows;
+    c->n_acc = nRows;
     c->have_aln = true;
     return 0;
 }

@@ -493,7 +493,22 @@ void check_search_params(const Params &p) {
                                 "with --gpus N (k-mer table sharded over the devices, unsplit result)");
     if (p.gpus < 1 || p.gpus > 8) throw Fail("--gpus must be 1..8");
     if (p.lanes < 1 || p.lanes > 8) throw Fail("--lanes must be 1..8");
-    if (p.covThr != 0 || p.addSelf != 0) throw Fail("coverage thresholds / --add-self-matches are not supported on this path");
+    if (p.addSelf != 0) throw Fail("--add-self-matches is not supported on this path");
+    if (p.covThr < 0 || p.covThr > 1) throw Fail("Error in argument -c");
+    if (p.covMode < 0 || p.covMode > 5) throw Fail("Error in argument --cov-mode");
+}
+
+// Util::canBeCovered (M/commons/Util.cpp:533-550), float arithmetic as there; modes by value (Parameters.h:246-251)
+bool can_be_covered(float covThr, int covMode, float qLen, float tLen) {
+    switch (covMode) {
+    case 0: return (qLen / tLen >= covThr) && (tLen / qLen >= covThr);
+    case 1: return (qLen / tLen) >= covThr;
+    case 2: return (tLen / qLen) >= covThr;
+    case 3: return ((tLen / qLen) >= covThr) && (tLen / qLen) <= 1.0;
+    case 4: return ((qLen / tLen) >= covThr) && (qLen / tLen) <= 1.0;
+    case 5: return (std::min(tLen, qLen) / std::max(tLen, qLen)) >= covThr;
+    default: return true;
+    }
 }
 
 int run_prefilter(int argc, const char **argv) {
@@ -530,6 +545,7 @@ int run_prefilter(int argc, const char **argv) {
     const size_t nq = Q.keys.size();
     double kernelMs = 0;
     uint64_t nHits = 0;
+    const bool covFilter = p.covThr > 0.0 && (p.covMode == 0 || p.covMode == 2 || p.covMode == 5);
     for (size_t b0 = 0, b1 = 0; b0 < nq; b0 = b1) {
         b1 = std::min(nq, b0 + (size_t)p.batch);
         std::vector<uint64_t> off(b1 - b0 + 1);
@@ -550,8 +566,12 @@ int run_prefilter(int argc, const char **argv) {
 #pragma omp for schedule(static)
             for (long i = 0; i < (long)(b1 - b0); i++) {
                 buf.clear();
+                const float qLen = (float)(Q.off[b0 + (size_t)i + 1] - Q.off[b0 + (size_t)i]);
                 for (uint64_t h = r->offsets[i]; h < r->offsets[i + 1]; h++) {
                     const spb_hit &x = r->hits[h];   // id -> DB key (Prefiltering.cpp:827-829)
+                    // -c with --cov-mode 0 / 2 / 5: hits whose lengths cannot reach the coverage are not written (after the
+                    // max-seqs cut, Prefiltering.cpp:834-842)
+                    if (covFilter && !can_be_covered((float)p.covThr, p.covMode, qLen, (float)(T.off[x.id + 1] - T.off[x.id]))) continue;
                     char *w = put_uint(tmp, T.keys[x.id]); *w++ = '\t';
                     w = put_int(w, x.score); *w++ = '\t';
                     w = put_int(w, x.diag); *w++ = '\n';
@@ -580,6 +600,11 @@ void fill_align_params(const Params &p, const Engine &E, uint64_t dbRes, spb_ali
     ap->comp_bias = p.compBias;
     ap->byte_lanes = p.byteLanes;
     ap->word_lanes = p.wordLanes;
+    ap->cov_thr = (float)p.covThr;          // Parameters holds -c and --min-seq-id as float
+    ap->cov_mode = p.covMode;
+    ap->seq_id_thr = (float)p.seqIdThr;
+    ap->aln_len_thr = p.alnLenThr;
+    ap->seq_id_mode = p.seqIdMode;
     if (!gumbel_for(E.align.name, go, ge, p.gumbel, &ap->gumbel))
         throw Fail("no Gumbel parameters for " + E.align.name + " gap open " + std::to_string(go) + " extend " + std::to_string(ge) +
                    ": pass the twelve ALP values of the reference run with --gumbel lambda,K,a_I,b_I,alpha_I,beta_I,a_J,b_J,alpha_J,beta_J,sigma,tau");
@@ -588,12 +613,17 @@ void fill_align_params(const Params &p, const Engine &E, uint64_t dbRes, spb_ali
 void check_align_params(const Params &p) {
     check_unimplemented_flags(p);
     if (p.altAli != 0 || p.realign != 0) throw Fail("--alt-ali / --realign are not supported on this path");
-    if (p.seqIdThr != 0 || p.covThr != 0 || p.alnLenThr != 0) throw Fail("--min-seq-id / -c / --min-aln-len thresholds are not supported on this path");
-    if (p.seqIdMode != 0) throw Fail("--seq-id-mode != 0 is not supported");
+    if (p.seqIdThr < 0 || p.seqIdThr > 1) throw Fail("Error in argument --min-seq-id");
+    if (p.covThr < 0 || p.covThr > 1) throw Fail("Error in argument -c");
+    if (p.covMode < 0 || p.covMode > 5) throw Fail("Error in argument --cov-mode");
+    if (p.seqIdMode < 0 || p.seqIdMode > 2) throw Fail("Error in argument --seq-id-mode");
+    if (p.alnLenThr < 0) throw Fail("Error in argument --min-aln-len");
     if (p.maxRejected != INT_MAX || p.maxAccept != INT_MAX) throw Fail("--max-rejected / --max-accept are not supported");
-    // -a forces SCORE_COV_SEQID (Alignment.cpp:35-37); the other modes print fewer columns and are not implemented
-    // (--alignment-mode 3 without -a writes the ten columns without the backtrace in the reference, Matcher::resultToBuffer)
-    if (p.addBacktrace != 1) throw Fail("only the -a 1 (backtrace) output of the predictmatch search is implemented");
+    // -a forces SCORE_COV_SEQID (Alignment.cpp:35-37).  --alignment-mode 3 without -a computes the same alignments and writes
+    // the ten columns without the backtrace (Matcher::resultToBuffer, Matcher.cpp:355-367); the score-only / coverage-only modes
+    // (estimated sequence identity, no start positions) are not implemented
+    if (p.addBacktrace != 1 && p.alignmentMode != 3)
+        throw Fail("only the rows of --alignment-mode 3 (score, coverage, sequence identity) or -a 1 (the predictmatch search) are implemented");
 }
 
 // rows of one batch as text, one entry per query (Matcher::resultToBuffer, M/alignment/Matcher.cpp:323-370); sink(thread,
@@ -625,7 +655,13 @@ void format_alignment_rows(const Params &p, const spb_align_result *r, const Seq
                 w = put_int(w, qLen); *w++ = '\t';
                 w = put_int(w, a.t_start); *w++ = '\t';
                 w = put_int(w, a.t_end); *w++ = '\t';
-                w = put_int(w, (int)(T.off[a.target + 1] - T.off[a.target])); *w++ = '\t';
+                w = put_int(w, (int)(T.off[a.target + 1] - T.off[a.target]));
+                if (!p.addBacktrace) {      // ten columns (Matcher.cpp:355-367)
+                    *w++ = '\n';
+                    buf.append(tmp, (size_t)(w - tmp));
+                    continue;
+                }
+                *w++ = '\t';
                 buf.append(tmp, (size_t)(w - tmp));
                 cig.clear();
                 if (a.cigar_len) compress_cigar(r->cigar_ops + a.cigar_off, a.cigar_len, cig);
@@ -1496,10 +1532,11 @@ int run_showparams(int argc, const char **argv) {
     parse_args(argc, argv, 3, mod == "align" ? 4 : 3, p);
     if (mod == "align") check_align_params(p); else check_search_params(p);
     printf("sub_mat=%s seed_sub_mat=%s kmer_thr=%d max_seqs=%d min_ungapped=%d mask=%d comp_bias=%d pattern=%s "
-           "evalue=%g gap_open=%s gap_extend=%s threads=%d\n",
+           "evalue=%g gap_open=%s gap_extend=%s threads=%d cov=%g cov_mode=%d min_seq_id=%g min_aln_len=%d seq_id_mode=%d backtrace=%d\n",
            multiparam_aa(p.subMat).c_str(), multiparam_aa(p.seedSubMat).c_str(), kmer_threshold(p.sensitivity, p.kmerScore, 6), p.maxSeqs,
            p.minUngapped, p.mask, p.compBias, p.spacedPattern.empty() ? (p.spacedMode ? "11011101" : "111111") : p.spacedPattern.c_str(),
-           p.evalue, multiparam_aa(p.gapOpen).c_str(), multiparam_aa(p.gapExtend).c_str(), p.threads);
+           p.evalue, multiparam_aa(p.gapOpen).c_str(), multiparam_aa(p.gapExtend).c_str(), p.threads, (double)(float)p.covThr, p.covMode,
+           (double)(float)p.seqIdThr, p.alnLenThr, p.seqIdMode, p.addBacktrace);
     return 0;
 }
 

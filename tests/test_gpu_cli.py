@@ -131,3 +131,62 @@ def test_createindex_cache_is_used_and_validated(tmp_path):
     r = run("prefilter", os.path.join(C1, "qsetdb"), db, pref + "2", *PREF_FLAGS)
     assert "ignored" in r.stdout and "masked residues from" not in r.stdout
     assert dbio.read_entries(pref + "2") == dbio.read_entries(os.path.join(C1, "pref_0"))
+
+
+def _long_set_dbs(tmp_path):
+    """the `long` fixture set as on-disk DBs (keys = order of the FASTA, createdb --shuffle 0) + its all-pairs prefilter DB"""
+    from conftest import read_fasta_gz
+    w = str(tmp_path)
+    n = {}
+    for name in ("t", "q"):
+        seqs = [s.encode() for s in read_fasta_gz(os.path.join(GOLDEN, "long", name + ".fasta.gz"))]
+        dbio.write_sequence_db(os.path.join(w, name + "db"), range(len(seqs)), seqs)
+        n[name] = len(seqs)
+    body = b"".join(b"%d\t0\t0\n" % t for t in range(n["t"]))
+    dbio.write_db(os.path.join(w, "allpairs"), ((q, body) for q in range(n["q"])), dbio.DBTYPE_PREFILTER_RES)
+    return w
+
+
+def _with(flags, **over):
+    out = list(flags)
+    for k, v in over.items():
+        out[out.index(k) + 1] = str(v)
+    return out
+
+
+@pytest.mark.parametrize("tag", ["long_c0.5_m0", "long_c0.3_m1", "long_c0.7_m2", "long_c0.5_m4", "long_id0.3_mode1", "long_len40",
+                                 "long_c0.6_m2_id0.5_len25", "long_c0.6_m2_id0.5_len25_noback"])
+def test_align_acceptance_criteria_flags(tmp_path, tag):
+    """`spb200 align` with -c / --cov-mode / --min-seq-id / --seq-id-mode / --min-aln-len / -a 0 --alignment-mode 3 writes the
+    reference binary's alignment DB (tests/golden/criteria)"""
+    import json
+    c = json.load(open(os.path.join(GOLDEN, "criteria", "cases.json")))[tag]
+    w = _long_set_dbs(tmp_path)
+    over = {"-e": c["evalue"], "-c": c["cov"], "--cov-mode": c["cov_mode"], "--min-seq-id": c["min_seq_id"],
+            "--min-aln-len": c["min_aln_len"], "--seq-id-mode": c["seq_id_mode"]}
+    if not c["backtrace"]:
+        over.update({"-a": 0, "--alignment-mode": 3})
+    run("align", w + "/qdb", w + "/tdb", w + "/allpairs", w + "/aln", *_with(ALN_FLAGS, **over))
+    got = {k: v for k, v in entries_as_rows(w + "/aln").items() if v}
+    assert got == read_dump(os.path.join(GOLDEN, "criteria", tag + ".txt.gz"))
+
+
+@pytest.mark.parametrize("mode", [0, 1, 5])
+def test_prefilter_coverage_flag(tmp_path, mode):
+    """`spb200 prefilter -c 0.5`: hits that cannot reach the coverage are left out of the written lists in the modes 0 / 2 / 5
+    (Prefiltering.cpp:834-842); the fused search with the same flags equals prefilter + align"""
+    w = _long_set_dbs(tmp_path)
+    flags = _with(PREF_FLAGS, **{"-c": 0.5, "--cov-mode": mode})
+    run("prefilter", w + "/qdb", w + "/tdb", w + "/pref", *flags)
+    got = {k: v for k, v in entries_as_rows(w + "/pref").items() if v}
+    assert got == read_dump(os.path.join(GOLDEN, "criteria", "pref_long_c0.5_m%d.txt.gz" % mode))
+    aflags = _with(ALN_FLAGS, **{"-c": 0.5, "--cov-mode": mode})
+    run("align", w + "/qdb", w + "/tdb", w + "/pref", w + "/aln", *aflags)
+    seen, merged = set(), []
+    for lst in (flags, aflags):
+        for i in range(0, len(lst), 2):
+            if lst[i] not in seen:
+                seen.add(lst[i])
+                merged += [lst[i], lst[i + 1]]
+    run("search", w + "/qdb", w + "/tdb", w + "/fused", *merged)
+    assert entries_as_rows(w + "/fused") == entries_as_rows(w + "/aln")

@@ -296,6 +296,29 @@ def test_align_family_golden(searcher):
     assert not bad, bad[:4]
 
 
+@pytest.mark.parametrize("tag", sorted(Cm.criteria_cases()))
+def test_align_acceptance_criteria_golden(searcher, tag):
+    """-c / --cov-mode 0..5, --min-seq-id, --seq-id-mode, --min-aln-len and the rows without backtrace against the reference
+    binary's alignment DBs (tests/golden/criteria; Alignment.cpp:378,396,555-574)"""
+    from spacepharer_b200 import api
+    T, Q, pref, ref, kw = Cm.criteria_case(tag)
+    pairs = [[int(r.split("\t")[0]) for r in pref.get(i, [])] for i in range(len(Q))]
+    backtrace = kw.pop("backtrace")
+    kw["evalue"] = kw.pop("eval_thr")
+    tres, toff = O.concat(T)
+    searcher.set_align_targets(tres, toff, None)
+    qres, qoff = O.concat(Q)
+    poff = np.zeros(len(Q) + 1, dtype=np.uint64)
+    np.cumsum([len(p) for p in pairs], out=poff[1:])
+    pt = np.concatenate([np.asarray(p, dtype=np.uint32) for p in pairs])
+    off, rows, cig, st = searcher.align(qres, qoff, poff, pt, Cm.db_res_count(T), **kw)
+    qlens, tlens = [len(q) for q in Q], [len(t) for t in T]
+    got = [api.format_align_rows(rows[int(off[i]):int(off[i + 1])], cig, qlens, tlens, None, backtrace) for i in range(len(Q))]
+    bad = [(i, got[i][:2], ref.get(i, [])[:2]) for i in range(len(Q)) if got[i] != ref.get(i, [])]
+    assert not bad, bad[:4]
+    assert st["n_rows"] == sum(len(v) for v in ref.values()) == int(off[-1])
+
+
 def test_align_long_striped_golden(searcher):
     """queries of 17..150 aa: stripe-dependent E update, byte->word overflow, gapped tracebacks"""
     T, Q = Cm.load_fasta_set("long")

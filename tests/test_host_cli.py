@@ -131,6 +131,16 @@ def test_workflow_argv_is_accepted():
     assert "evalue=200" in out and "gap_open=16" in out and "gap_extend=2" in out and "sub_mat=VTML40.out" in out
 
 
+def test_acceptance_criteria_flags_are_parsed():
+    """-c / --cov-mode / --min-seq-id / --seq-id-mode / --min-aln-len and --alignment-mode 3 without -a reach the align
+    parameters (Parameters.h:394-402 holds -c and --min-seq-id as float)"""
+    out = run("showparams", "align", "q", "t", "p", "a", *ALN_FLAGS, "-c", "0.8", "--cov-mode", "2", "--min-seq-id", "0.3",
+              "--seq-id-mode", "1", "--min-aln-len", "12", "-a", "0", "--alignment-mode", "3").stdout
+    assert "cov=0.8 cov_mode=2 min_seq_id=0.3 min_aln_len=12 seq_id_mode=1 backtrace=0" in out
+    out = run("showparams", "prefilter", "q", "t", "p", *PREF_FLAGS, "-c", "0.5", "--cov-mode", "5").stdout
+    assert "cov=0.5 cov_mode=5" in out
+
+
 def test_errors_like_the_reference():
     r = run("prefilter", "q", "t", "p", "--no-such-flag", "1", ok=False)
     assert r.returncode == 1 and "Unrecognized parameter" in r.stderr
@@ -142,14 +152,15 @@ def test_errors_like_the_reference():
 
 @pytest.mark.parametrize("module,flags", [
     ("prefilter", ["--mask-lower-case", "1"]), ("prefilter", ["--alph-size", "nucl:5,aa:13"]), ("prefilter", ["--alph-size", "13"]),
-    ("prefilter", ["--taxon-list", "10239"]), ("align", ["--alignment-mode", "3", "-a", "0"]), ("align", ["--mask-lower-case", "1"])])
+    ("prefilter", ["--taxon-list", "10239"]), ("align", ["--alignment-mode", "1", "-a", "0"]), ("align", ["--mask-lower-case", "1"]),
+    ("align", ["--max-accept", "5"]), ("align", ["--cov-mode", "6"]), ("prefilter", ["--add-self-matches", "1"])])
 def test_flags_that_would_change_the_result_are_refused(module, flags):
     """A drop-in must not exit 0 with a DB that differs from the reference's: flags of the two modules that this path does not
     implement keep the reference default and any other value fails loudly."""
     base = PREF_FLAGS if module == "prefilter" else ALN_FLAGS
     dbs = ["q", "t", "p"] if module == "prefilter" else ["q", "t", "p", "a"]
     r = run("showparams", module, *dbs, *base, *flags, ok=False)
-    assert r.returncode == 1 and ("not supported" in r.stderr or "only the" in r.stderr), r.stderr
+    assert r.returncode == 1 and ("not supported" in r.stderr or "only the" in r.stderr or "Error in argument" in r.stderr), r.stderr
     # the workflow's own values of the same flags pass
     run("showparams", module, *dbs, *base)
 

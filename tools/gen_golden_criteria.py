@@ -6,7 +6,8 @@
                                              --seq-id-mode, --min-aln-len (Alignment.cpp:353-404 canBeCovered + checkCriteria,
                                              StripedSmithWaterman.cpp:195-240 coverage exits, Util.cpp:533-567), and the
                                              10-column rows of `--alignment-mode 3` without `-a` (Matcher.cpp:355-366)
-  tests/golden/criteria/cases.json           the flag set of every fixture
+  tests/golden/criteria/pref_long_c0.5_m*    prefilter lists of the `long` set under -c 0.5 --cov-mode 0 / 1 / 2 / 5 (Prefiltering.cpp:834-842)
+  tests/golden/criteria/cases.json           the flag set of every alignment fixture
 Usage: python tools/gen_golden_criteria.py
 """
 import gzip
@@ -96,6 +97,14 @@ def main():
         w = os.path.join(work, name)
         run("%s align %s/qdb %s/tdb %s/allpairs %s/aln_%s %s" % (B, w, w, w, w, tag, aln_flags(ev, cov, mode, sid, alen, back, idm)))
         dump_db(os.path.join(w, "aln_" + tag), os.path.join(out, tag + ".txt.gz"))
+    # prefilter lists under -c: hits whose lengths cannot reach the coverage are dropped after the max-seqs cut in the modes
+    # 0 / 2 / 5 (Prefiltering.cpp:834-842); mode 1 leaves the list alone
+    w = os.path.join(work, "long")
+    for mode in (0, 1, 2, 5):
+        tag = "pref_long_c0.5_m%d" % mode
+        flags = refbin.PREF_FLAGS.format(maxseqs=300, mask=1, threads=4, sens="5.7").replace(" -c 0 --cov-mode 0 ", " -c 0.5 --cov-mode %d " % mode)
+        run("%s prefilter %s/qdb %s/tdb %s/%s %s" % (B, w, w, w, tag, flags))
+        dump_db(os.path.join(w, tag), os.path.join(out, tag + ".txt.gz"))
     with open(os.path.join(out, "cases.json"), "w") as f:
         json.dump({t: dict(set=c[0], evalue=float(c[1]), cov=c[2], cov_mode=c[3], min_seq_id=c[4], min_aln_len=c[5], backtrace=c[6],
                         seq_id_mode=c[7])
