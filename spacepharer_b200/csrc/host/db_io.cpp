@@ -1,6 +1,7 @@
 // db_io.cpp -- see db_io.h
 #include "db_io.h"
 
+#include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -17,6 +18,37 @@
 #include <stdexcept>
 
 namespace spbhost {
+
+// ---- zstd through the system library (no headers in the image: the four entry points are declared here) ----
+namespace {
+struct Zstd {
+    size_t (*decompress)(void *dst, size_t dstCapacity, const void *src, size_t srcSize) = nullptr;
+    size_t (*compress)(void *dst, size_t dstCapacity, const void *src, size_t srcSize, int level) = nullptr;
+    size_t (*compressBound)(size_t srcSize) = nullptr;
+    unsigned (*isError)(size_t code) = nullptr;
+    const char *(*getErrorName)(size_t code) = nullptr;
+};
+
+const Zstd &zstd() {
+    static const Zstd z = [] {
+        Zstd r;
+        void *h = dlopen("libzstd.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libzstd.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) throw std::runtime_error("Compressed databases (--compressed 1) need libzstd.so.1, which could not be loaded");
+        r.decompress = (decltype(r.decompress))dlsym(h, "ZSTD_decompress");
+        r.compress = (decltype(r.compress))dlsym(h, "ZSTD_compress");
+        r.compressBound = (decltype(r.compressBound))dlsym(h, "ZSTD_compressBound");
+        r.isError = (decltype(r.isError))dlsym(h, "ZSTD_isError");
+        r.getErrorName = (decltype(r.getErrorName))dlsym(h, "ZSTD_getErrorName");
+        if (!r.decompress || !r.compress || !r.compressBound || !r.isError || !r.getErrorName)
+            throw std::runtime_error("libzstd.so.1 lacks the simple API (ZSTD_compress / ZSTD_decompress)");
+        return r;
+    }();
+    return z;
+}
+
+bool g_compressedDefault = false;
+}  // namespace
 
 static bool file_exists(const std::string &p) {
     struct stat st;
@@ -56,6 +88,17 @@ void DBReader::open(const std::string &name) {
         if (n == 0) throw std::runtime_error("Could not open data file " + name + "!");
     }
     dataSize_ = data_.size();
+    dbtype_ = 0;
+    {
+        const std::string tp = name + ".dbtype";
+        FILE *t = fopen(tp.c_str(), "rb");
+        if (t) {
+            unsigned char b[4] = {0, 0, 0, 0};
+            if (fread(b, 1, 4, t) == 4) dbtype_ = (int)(b[0] | (b[1] << 8) | (b[2] << 16) | ((unsigned)b[3] << 24));
+            fclose(t);
+        }
+    }
+    const bool isCompressed = compressed();      // index lengths are uncompressed lengths then
     // index: the whole text is read once and parsed by all host threads (slices cut at line ends); a 1 M-spacer query DB has
     // 3.8 M lines, and stdio + strtoull per line used to cost more than the GPU search itself
     const std::string idx = name + ".index";
@@ -96,7 +139,7 @@ void DBReader::open(const std::string &name) {
                 v[nf++] = x;
             }
             if (nf == 3) {
-                if (v[1] + v[2] > dataSize_) bad[(size_t)t] = 2;
+                if (isCompressed ? v[1] + 5 > dataSize_ : v[1] + v[2] > dataSize_) bad[(size_t)t] = 2;
                 out.push_back(DBEntry{(uint32_t)v[0], (uint64_t)v[1], (uint64_t)v[2]});
             } else if (nf != 0) {
                 bad[(size_t)t] = 1;
@@ -124,15 +167,46 @@ void DBReader::open(const std::string &name) {
         std::stable_sort(linear_.begin(), linear_.end(), [&](uint32_t a, uint32_t b) { return entries_[a].offset < entries_[b].offset; });
     linearRank_.resize(entries_.size());
     for (size_t i = 0; i < linear_.size(); i++) linearRank_[linear_[i]] = (uint32_t)i;
-    dbtype_ = 0;
-    const std::string tp = name + ".dbtype";
-    FILE *t = fopen(tp.c_str(), "rb");
-    if (t) {
-        unsigned char b[4] = {0, 0, 0, 0};
-        if (fread(b, 1, 4, t) == 4) dbtype_ = (int)(b[0] | (b[1] << 8) | (b[2] << 16) | ((unsigned)b[3] << 24));
-        fclose(t);
+    if (isCompressed) inflate(name);
+}
+
+// DBReader::getDataCompressed (DBReader.cpp:512-539) for every entry at once: the DB is rebuilt in memory in the uncompressed
+// layout, entries in their old (offset) order, so that ids, lengths and getAminoAcidDBSize (the sum of the index lengths,
+// DBReader.cpp:774-831) are what the reference sees through its per-entry decompression.
+void DBReader::inflate(const std::string &name) {
+    const Zstd &z = zstd();
+    const size_t n = entries_.size();
+    std::vector<uint64_t> at(n + 1, 0);
+    for (size_t id = 0; id < n; id++) {
+        const DBEntry &e = entries_[linear_[id]];
+        if (e.length == 0) throw std::runtime_error("Malformed index line in " + name + ".index");
+        at[id + 1] = at[id] + e.length;
     }
-    if (dbtype_ & (1 << 31)) throw std::runtime_error("Compressed databases (--compressed 1) are not supported: " + name);
+    std::vector<char> out((size_t)at[n]);
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(max : bad)
+    for (long id = 0; id < (long)n; id++) {
+        DBEntry &e = entries_[linear_[(size_t)id]];
+        const char *src = data_.data() + e.offset;
+        unsigned int cSize;
+        memcpy(&cSize, src, 4);
+        const uint64_t want = e.length - 1;
+        char *dst = out.data() + at[(size_t)id];
+        if (e.offset + 4 + (uint64_t)cSize + 1 > data_.size()) { bad = std::max(bad, 2); continue; }
+        if (src[4 + cSize] == 0) {                 // one zstd frame
+            const size_t got = z.decompress(dst, (size_t)want, src + 4, cSize);
+            if (z.isError(got) || got != want) { bad = std::max(bad, 1); continue; }
+        } else {                                   // stored (terminator 0xFF)
+            if (cSize != want) { bad = std::max(bad, 1); continue; }
+            memcpy(dst, src + 4, cSize);
+        }
+        dst[want] = '\0';
+    }
+    if (bad == 2) throw std::runtime_error("Index entry beyond the end of the data file in " + name + ".index");
+    if (bad) throw std::runtime_error("Could not decompress an entry of " + name + " (ZSTD_decompress)");
+    for (size_t id = 0; id < n; id++) entries_[linear_[id]].offset = at[id];
+    data_.swap(out);
+    dataSize_ = data_.size();
 }
 
 size_t DBReader::findKey(uint32_t key) const {
@@ -148,9 +222,16 @@ size_t DBReader::linearIdOfKey(uint32_t key) const {
 
 DBWriter::~DBWriter() { if (fd_ >= 0) ::close(fd_); }
 
+void DBWriter::setCompressedDefault(bool on) { g_compressedDefault = on; }
+
 void DBWriter::open(const std::string &name, int dbtype, int threads) {
     name_ = name;
-    dbtype_ = dbtype;
+    dbtype_ = dbtype & 0x7FFFFFFF;
+    compressed_ = g_compressedDefault;
+    if (compressed_) {
+        zstd();                                   // fails here, before anything is written, when the library is missing
+        dbtype_ |= (int)(1u << 31);
+    }
     parts_.assign((size_t)(threads > 0 ? threads : 1), Part());
     fileEnd_ = 0;
     if (fd_ >= 0) ::close(fd_);
@@ -166,8 +247,28 @@ void DBWriter::write(int thread, uint32_t key, const char *payload, size_t len) 
     e.key = key;
     e.offset = p.data.size();
     e.length = len + 1;
-    p.data.insert(p.data.end(), payload, payload + len);
-    p.data.push_back('\0');
+    if (!compressed_) {
+        p.data.insert(p.data.end(), payload, payload + len);
+        p.data.push_back('\0');
+    } else if (len < 60) {
+        // DBWriter::writeAdd / writeEnd (DBWriter.cpp:279-369): short payloads are stored, terminator 0xFF
+        const unsigned int sz = (unsigned int)len;
+        const char *b = reinterpret_cast<const char *>(&sz);
+        p.data.insert(p.data.end(), b, b + 4);
+        p.data.insert(p.data.end(), payload, payload + len);
+        p.data.push_back((char)0xFF);
+    } else {
+        // one zstd frame at the reference's level 3, terminator 0x00; the index keeps the uncompressed length
+        const Zstd &z = zstd();
+        const size_t at = p.data.size(), cap = z.compressBound(len);
+        p.data.resize(at + 4 + cap + 1);
+        const size_t got = z.compress(p.data.data() + at + 4, cap, payload, len, 3);
+        if (z.isError(got)) throw std::runtime_error(std::string("ZSTD_compress: ") + z.getErrorName(got));
+        const unsigned int sz = (unsigned int)got;
+        memcpy(p.data.data() + at, &sz, 4);
+        p.data[at + 4 + got] = '\0';
+        p.data.resize(at + 4 + got + 1);
+    }
     p.idx.push_back(e);
 }
 

@@ -6,6 +6,13 @@
 //   <name>.index   text lines  key \t offset \t length   (length includes the NUL; any line order)
 //   <name>.dbtype  4-byte little-endian int (0 amino acids, 5 alignment results, 7 prefilter results)
 // A multi-threaded reference writer may leave <name>.0 .. <name>.N-1 whose offsets live in the concatenated space.
+//
+// Compressed DBs (`--compressed 1`, bit 31 of the dbtype; DBReader.cpp:191,512-539, DBWriter.cpp:254-397): an entry is
+//   u32 size | size bytes | terminator   with terminator 0x00 = one zstd frame, 0xFF = stored as is (payloads below 60 bytes);
+// its index length stays the uncompressed length + 1.  The reader inflates such a DB once, in parallel, into the uncompressed
+// layout (same entry order), so everything behind it is unchanged; the writer deflates entry by entry in the calling thread.
+// zstd comes from the system's libzstd.so.1 (dlopen; the image has the library but no headers) -- without it compressed DBs
+// fail loudly.
 #pragma once
 
 #include <stdint.h>
@@ -29,7 +36,8 @@ public:
     // throws std::runtime_error with the reference's wording on missing files
     void open(const std::string &name);
     size_t size() const { return entries_.size(); }
-    int dbtype() const { return dbtype_; }
+    int dbtype() const { return dbtype_ & 0x7FFFFFFF; }
+    bool compressed() const { return (dbtype_ & (1u << 31)) != 0; }
     // entries sorted by key (DBReader::NOSORT id order after sortIndex) ...
     const DBEntry &byKey(size_t i) const { return entries_[i]; }
     // ... and the LINEAR_ACCESS order (by data offset, DBReader.cpp:339-368): ids of the prefilter index
@@ -44,6 +52,7 @@ public:
     uint64_t dataSize() const { return dataSize_; }
 
 private:
+    void inflate(const std::string &name);
     std::vector<DBEntry> entries_;
     std::vector<uint32_t> linear_, linearRank_;
     std::vector<char> data_;
@@ -57,6 +66,8 @@ public:
     // per-thread data files merged by DBWriter::mergeResults; the index is written sorted by key, <name>.dbtype last
     // (the workflow scripts test for it: blastp.sh:31,39)
     void open(const std::string &name, int dbtype, int threads);
+    // --compressed: mode of every DBWriter opened afterwards (the flag of the module that is running)
+    static void setCompressedDefault(bool on);
     void write(int thread, uint32_t key, const char *payload, size_t len);   // payload without the NUL
     // writes what parts [first, first + count) hold to the data file now and empties their buffers; no write() to those parts
     // may run concurrently.  Lets a long search put its output on disk batch by batch, overlapped with the GPU work.
@@ -75,6 +86,7 @@ private:
     uint64_t fileEnd_ = 0;
     std::string name_;
     int dbtype_ = 0;
+    bool compressed_ = false;
     std::vector<Part> parts_;
 };
 

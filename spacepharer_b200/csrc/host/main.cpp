@@ -162,7 +162,8 @@ void parse_args(int argc, const char **argv, int first, size_t nDb, Params &p) {
         }
     }
     if (p.db.size() != nDb) throw Fail("expected " + std::to_string(nDb) + " database arguments, got " + std::to_string(p.db.size()));
-    if (p.compressed != 0) throw Fail("--compressed 1 is not supported");
+    if (p.compressed != 0 && p.compressed != 1) throw Fail("Error in argument --compressed");
+    DBWriter::setCompressedDefault(p.compressed == 1);   // every DB this module writes (DBWriter.cpp:32-41: WRITER_COMPRESSED_MODE)
     if (p.threads < 1) p.threads = 1;
 }
 
@@ -1470,10 +1471,11 @@ int run_dumpmatrix(int argc, const char **argv) {
 }
 
 int run_dbcopy(int argc, const char **argv) {
-    if (argc < 4) throw Fail("usage: spb200 dbcopy <inDB> <outDB> [threads]");
+    if (argc < 4) throw Fail("usage: spb200 dbcopy <inDB> <outDB> [threads] [flushEvery] [compressed]");
     DBReader in;
     in.open(argv[2]);
     const int threads = argc > 4 ? atoi(argv[4]) : 1;
+    DBWriter::setCompressedDefault(argc > 6 && atoi(argv[6]) == 1);
     DBWriter out;
     out.open(argv[3], in.dbtype(), threads);
     const size_t n = in.size();

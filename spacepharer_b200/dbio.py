@@ -3,7 +3,8 @@
 Format (M/commons/DBReader.h:57-99, DBWriter.cpp:216-440): `<name>` holds NUL-terminated entries,
 `<name>.index` text lines `key\\toffset\\tlength` (length includes the NUL), `<name>.dbtype` a 4-byte
 little-endian int (0 amino acids, 5 alignment results, 7 prefilter results).  Multi-threaded writers
-may leave `<name>.0 .. <name>.N-1` whose offsets live in the concatenated space.  The native reader /
+may leave `<name>.0 .. <name>.N-1` whose offsets live in the concatenated space.  DBs written with `--compressed 1`
+(bit 31 of the dbtype) are inflated while reading.  The native reader /
 writer used by the spb200 binary is spacepharer_b200/csrc/host/db_io.cpp.
 """
 import glob
@@ -31,7 +32,38 @@ def read_db(name):
     rows = [tuple(int(x) for x in line.split()[:3]) for line in open(name + ".index") if line.strip()]
     rows.sort()
     a = np.array(rows, dtype=np.int64).reshape(-1, 3)
+    if os.path.exists(name + ".dbtype") and read_dbtype(name) < 0:      # bit 31: --compressed 1
+        a, data = _inflate(a, data)
     return a[:, 0].astype(np.uint32), a[:, 1].copy(), a[:, 2].copy(), data
+
+
+def _inflate(rows, data):
+    """Compressed DB (DBReader.cpp:512-539, DBWriter.cpp:254-397): an entry is `u32 size | size bytes | terminator`, terminator 0
+    = one zstd frame, 0xFF = stored; the index length is the uncompressed length + 1.  -> rows and data in the uncompressed
+    layout (entries in offset order).  zstd through the system's libzstd.so.1, like the host binary."""
+    import ctypes as C
+    z = C.CDLL("libzstd.so.1")
+    z.ZSTD_decompress.restype = C.c_size_t
+    z.ZSTD_decompress.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+    z.ZSTD_isError.argtypes = [C.c_size_t]
+    out, pos = [], 0
+    rows = rows.copy()
+    for i in np.argsort(rows[:, 1], kind="stable"):
+        o, want = int(rows[i, 1]), int(rows[i, 2]) - 1
+        size = struct.unpack_from("<I", data, o)[0]
+        body = data[o + 4:o + 4 + size]
+        if data[o + 4 + size] == 0:
+            buf = C.create_string_buffer(max(want, 1))
+            got = z.ZSTD_decompress(buf, want, body, size)
+            if z.ZSTD_isError(got) or got != want:
+                raise ValueError("could not decompress the entry at offset %d" % o)
+            body = buf.raw[:want]
+        elif size != want:
+            raise ValueError("stored entry at offset %d: %d bytes, index says %d" % (o, size, want))
+        out.append(body + b"\0")
+        rows[i, 1] = pos
+        pos += want + 1
+    return rows, b"".join(out)
 
 
 def read_dbtype(name):

@@ -190,3 +190,27 @@ def test_prefilter_coverage_flag(tmp_path, mode):
                 merged += [lst[i], lst[i + 1]]
     run("search", w + "/qdb", w + "/tdb", w + "/fused", *merged)
     assert entries_as_rows(w + "/fused") == entries_as_rows(w + "/aln")
+
+
+def test_compressed_dbs_in_and_out(tmp_path):
+    """--compressed 1: the modules read the reference's compressed query / target / prefilter DBs (tests/golden/compressed) and
+    write compressed result DBs whose entries are the reference's (DBReader.cpp:512-539, DBWriter.cpp:254-397)"""
+    CZ = os.path.join(GOLDEN, "compressed")
+    pref, aln, fused = str(tmp_path / "pref"), str(tmp_path / "aln"), str(tmp_path / "fused")
+    pflags, aflags = _with(PREF_FLAGS, **{"--compressed": 1}), _with(ALN_FLAGS, **{"--compressed": 1})
+    run("prefilter", os.path.join(CZ, "qsetdb"), os.path.join(CZ, "targets"), pref, *pflags)
+    assert dbio.read_dbtype(pref) == dbio.DBTYPE_PREFILTER_RES - (1 << 31)
+    assert dbio.read_entries(pref) == dbio.read_entries(os.path.join(C1, "pref_0"))
+    run("align", os.path.join(CZ, "qsetdb"), os.path.join(CZ, "targets"), os.path.join(CZ, "pref_0"), aln, *aflags)
+    assert dbio.read_dbtype(aln) == dbio.DBTYPE_ALIGNMENT_RES - (1 << 31)
+    assert dbio.read_entries(aln) == dbio.read_entries(os.path.join(C1, "prot_result"))
+    # compressed input, plain output
+    seen, merged = set(), []
+    for lst in (PREF_FLAGS, ALN_FLAGS):
+        for i in range(0, len(lst), 2):
+            if lst[i] not in seen:
+                seen.add(lst[i])
+                merged += [lst[i], lst[i + 1]]
+    run("search", os.path.join(CZ, "qsetdb"), os.path.join(CZ, "targets"), fused, *merged)
+    assert dbio.read_dbtype(fused) == dbio.DBTYPE_ALIGNMENT_RES
+    assert dbio.read_entries(fused) == dbio.read_entries(os.path.join(C1, "prot_result"))

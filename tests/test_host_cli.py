@@ -88,6 +88,51 @@ def test_db_streaming_writer(tmp_path, threads, every):
     assert keys == sorted(keys)
 
 
+@pytest.mark.parametrize("db", ["targets", "qsetdb", "pref_0", "prot_result"])
+def test_compressed_db_is_read(tmp_path, db):
+    """--compressed 1 DBs written by the reference (tests/golden/compressed: zstd frames, short entries stored; bit 31 of the
+    dbtype) are inflated by the host reader and by the Python mirror into exactly the uncompressed DB"""
+    src, plain = os.path.join(GOLDEN, "compressed", db), os.path.join(GOLDEN, "config1", db)
+    assert dbio.read_dbtype(src) & 0x7FFFFFFF == dbio.read_dbtype(plain) and dbio.read_dbtype(src) < 0
+    assert dbio.read_entries(src) == dbio.read_entries(plain)
+    dst = str(tmp_path / "copy")
+    out = run("dbcopy", src, dst, "2").stdout
+    assert dbio.read_dbtype(dst) == dbio.read_dbtype(plain)
+    assert dbio.read_entries(dst) == dbio.read_entries(plain)
+    if db in ("targets", "qsetdb"):       # getAminoAcidDBSize counts uncompressed residues (sum of the index lengths)
+        assert "%d residues" % dbio.amino_acid_db_size(plain) in out
+
+
+@pytest.mark.parametrize("db,threads,every", [("targets", 3, 0), ("prot_result", 2, 40), ("qsetdb", 1, 0)])
+def test_compressed_db_is_written(tmp_path, db, threads, every):
+    """the writer's compressed mode (DBWriter.cpp:254-397): entry = u32 size | bytes | terminator (0 zstd frame, 0xFF stored
+    below 60 bytes), index lengths stay uncompressed, dbtype bit 31; read back by both readers, also after streaming flushes"""
+    import struct
+    plain = os.path.join(GOLDEN, "config1", db)
+    dst = str(tmp_path / "c")
+    run("dbcopy", plain, dst, str(threads), str(every), "1")
+    assert dbio.read_dbtype(dst) == dbio.read_dbtype(plain) - (1 << 31)
+    want = dbio.read_entries(plain)
+    assert dbio.read_entries(dst) == want
+    raw = open(dst, "rb").read()
+    n_stored = n_frames = 0
+    for line in open(dst + ".index"):
+        k, o, l = (int(x) for x in line.split())
+        assert l == len(want[k]) + 1
+        size = struct.unpack_from("<I", raw, o)[0]
+        term = raw[o + 4 + size]
+        assert term in (0, 0xFF) and (term == 0xFF) == (len(want[k]) < 60)
+        if term == 0:
+            assert raw[o + 4:o + 8] == b"\x28\xb5\x2f\xfd"       # zstd frame magic
+            n_frames += 1
+        else:
+            assert size == len(want[k])
+            n_stored += 1
+    assert n_stored + n_frames == len(want) and (n_frames > 0 or db != "targets")
+    run("dbcopy", dst, str(tmp_path / "back"), "2")
+    assert dbio.read_entries(str(tmp_path / "back")) == want
+
+
 def test_large_index_is_parsed_in_parallel(tmp_path):
     """an index text above 1 MB is cut into slices at line ends and parsed by all threads; the entries and their order do not change"""
     n = 90000
@@ -163,6 +208,7 @@ def test_flags_that_would_change_the_result_are_refused(module, flags):
     assert r.returncode == 1 and ("not supported" in r.stderr or "only the" in r.stderr or "Error in argument" in r.stderr), r.stderr
     # the workflow's own values of the same flags pass
     run("showparams", module, *dbs, *base)
+    run("showparams", module, *dbs, *base, "--compressed", "1")
 
 
 def test_no_cpu_fallback(tmp_path):
