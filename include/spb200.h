@@ -95,6 +95,8 @@ typedef struct spb_prefilter_params {
     uint32_t id_base;        /* added to local target ids for tie-order purposes (target shards) */
     int32_t emit_trunc_keys; /* 1: keep the max-seqs truncation key of every hit on the device (target shards, see
                                 spb_prefilter_device_trunc_keys); requires max_seqs <= 4096 */
+    int32_t exact_kmer;      /* --exact-kmer-matching 1: every window looks up only its own k-mer (takeOnlyBestKmer,
+                                Prefiltering.cpp:177, QueryMatcher.cpp:221-231); served by the one-CTA-per-query kernel */
 } spb_prefilter_params;
 
 typedef struct spb_hit {     /* hit_t, M/prefiltering/QueryMatcher.h:35-52 */

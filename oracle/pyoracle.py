@@ -40,6 +40,7 @@ class PrefilterParams(C.Structure):
         ("binSize", C.c_int),
         ("compBias", C.c_int),
         ("pattern", C.c_char * 33),
+        ("exactKmer", C.c_int),
     ]
 
 
@@ -236,11 +237,11 @@ def concat(seqs):
 
 class Prefilter:
     def __init__(self, tres, toff, m80, m40u, kmer_thr=112, max_seqs=300, min_diag=15, bin_size=2,
-                 comp_bias=1, pattern="11011101"):
+                 comp_bias=1, pattern="11011101", exact_kmer=0):
         self.tres = np.ascontiguousarray(tres, dtype=np.uint8)
         self.toff = np.ascontiguousarray(toff, dtype=np.uint64)
         self.m80, self.m40u = m80, m40u
-        self.p = PrefilterParams(kmer_thr, max_seqs, min_diag, bin_size, comp_bias, pattern.encode())
+        self.p = PrefilterParams(kmer_thr, max_seqs, min_diag, bin_size, comp_bias, pattern.encode(), exact_kmer)
         self.T = len(self.toff) - 1
         self.h = lib().spo_prefilter_create(_u8(self.tres), self.toff.ctypes.data_as(C.POINTER(C.c_uint64)),
                                             self.T, C.byref(m80), C.byref(m40u), C.byref(self.p))

@@ -561,8 +561,14 @@ int spo_prefilter_query(spo_prefilter *pf, const unsigned char *q, int L, spo_hi
         int thr = pf->p.kmerThr - bias;
         if (thr < 0) thr = 0;
         thr = (short)thr;
-        int nk = spo_similar_kmers(pf, k6, thr, klist, kcap);
-        while (nk == kcap && kcap < 262144 * 32) { /* KmerGenerator::MAX_KMER_RESULT_SIZE */
+        int nk;
+        if (pf->p.exactKmer) { /* takeOnlyBestKmer: the window's own k-mer, whatever the threshold (QueryMatcher.cpp:221-227) */
+            uint32_t k = 0, mul = 1;
+            for (int i = 0; i < SPO_KMER; i++) { k += k6[i] * mul; mul *= 20; }
+            klist[0] = k;
+            nk = 1;
+        } else nk = spo_similar_kmers(pf, k6, thr, klist, kcap);
+        while (!pf->p.exactKmer && nk == kcap && kcap < 262144 * 32) { /* KmerGenerator::MAX_KMER_RESULT_SIZE */
             kcap *= 2;
             klist = (uint32_t *)realloc(klist, sizeof(uint32_t) * (size_t)kcap);
             nk = spo_similar_kmers(pf, k6, thr, klist, kcap);

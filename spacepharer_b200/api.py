@@ -255,8 +255,8 @@ class Searcher:
                     total_ms=float(R.total_ms))
 
     def prefilter_resident(self, kmer_thr=112, max_seqs=300, min_ungapped_score=15, bin_size=2, comp_bias=1, id_base=0,
-                           emit_trunc_keys=0):
-        p = capi.PrefilterParams(kmer_thr, max_seqs, min_ungapped_score, bin_size, comp_bias, id_base, emit_trunc_keys)
+                           emit_trunc_keys=0, exact_kmer=0):
+        p = capi.PrefilterParams(kmer_thr, max_seqs, min_ungapped_score, bin_size, comp_bias, id_base, emit_trunc_keys, exact_kmer)
         capi.check(self.lib.spb_prefilter_resident(self.h, C.byref(p)))
         R = capi.PrefilterResult()
         capi.check(self.lib.spb_prefilter_stats(self.h, C.byref(R)))
@@ -390,7 +390,7 @@ class Searcher:
     def search(self, qres, qoff, db_res_count, fetch_prefilter=False, **kw):
         """Fused predictmatch search step: prefilter -> align with the hit lists kept in HBM.
         kw: kmer_thr, max_seqs, min_ungapped_score, bin_size, comp_bias, evalue, gap_open, gap_extend, gumbel"""
-        pk = {k: kw[k] for k in ("kmer_thr", "max_seqs", "min_ungapped_score", "bin_size", "comp_bias", "id_base") if k in kw}
+        pk = {k: kw[k] for k in ("kmer_thr", "max_seqs", "min_ungapped_score", "bin_size", "comp_bias", "id_base", "exact_kmer") if k in kw}
         ak = {k: kw[k] for k in ("evalue", "gap_open", "gap_extend", "comp_bias", "gumbel", "byte_lanes", "word_lanes", "cov", "cov_mode",
                                  "min_seq_id", "min_aln_len", "seq_id_mode") if k in kw}
         self.set_queries(qres, qoff)
@@ -403,12 +403,12 @@ class Searcher:
 
     # ---- prefilter ---------------------------------------------------------------------------
     def prefilter(self, qres, qoff, kmer_thr=112, max_seqs=300, min_ungapped_score=15, bin_size=2, comp_bias=1,
-                  id_base=0):
+                  id_base=0, exact_kmer=0):
         """-> (offsets uint64[Q+1], hits structured array (id, score, diag), stats dict)"""
         qres = np.ascontiguousarray(qres, dtype=np.uint8)
         qoff = np.ascontiguousarray(qoff, dtype=np.uint64)
         Q = len(qoff) - 1
-        p = capi.PrefilterParams(kmer_thr, max_seqs, min_ungapped_score, bin_size, comp_bias, id_base, 0)
+        p = capi.PrefilterParams(kmer_thr, max_seqs, min_ungapped_score, bin_size, comp_bias, id_base, 0, exact_kmer)
         r = C.POINTER(capi.PrefilterResult)()
         capi.check(self.lib.spb_prefilter(self.h, _u8(qres), _u64(qoff), Q, C.byref(p), C.byref(r)))
         try:

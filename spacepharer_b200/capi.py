@@ -21,7 +21,7 @@ class IndexStats(C.Structure):
 class PrefilterParams(C.Structure):
     _fields_ = [("kmer_thr", C.c_int32), ("max_seqs", C.c_int32), ("min_diag_score", C.c_int32),
                 ("bin_size", C.c_int32), ("comp_bias", C.c_int32), ("id_base", C.c_uint32),
-                ("emit_trunc_keys", C.c_int32)]
+                ("emit_trunc_keys", C.c_int32), ("exact_kmer", C.c_int32)]
 
 
 class Hit(C.Structure):

@@ -489,7 +489,7 @@ void check_search_params(const Params &p) {
     check_unimplemented_flags(p);
     if (p.kmerSize != 0 && p.kmerSize != 6) throw Fail("The k-mer size " + std::to_string(p.kmerSize) + " is not valid. (spb200 implements k = 6)");
     if (p.diagScore != 1) throw Fail("--diag-score 0 is not supported");
-    if (p.exactKmer != 0) throw Fail("--exact-kmer-matching 1 is not supported");
+    if (p.exactKmer != 0 && p.exactKmer != 1) throw Fail("Error in argument --exact-kmer-matching");
     if (p.split > 1) throw Fail("--split > 1 (the reference's lossy target split) is not implemented; spread one DB over several GPUs "
                                 "with --gpus N (k-mer table sharded over the devices, unsplit result)");
     if (p.gpus < 1 || p.gpus > 8) throw Fail("--gpus must be 1..8");
@@ -540,6 +540,7 @@ int run_prefilter(int argc, const char **argv) {
     pp.comp_bias = p.compBias;
     pp.id_base = 0;
     pp.emit_trunc_keys = 0;
+    pp.exact_kmer = p.exactKmer;
 
     DBWriter out;
     out.open(p.db[2], DBTYPE_PREFILTER_RES, p.threads);
@@ -1056,6 +1057,7 @@ void search_dbs(const Params &p, const std::string &qName, const std::string &tN
     pp.comp_bias = p.compBias;
     pp.id_base = 0;
     pp.emit_trunc_keys = 0;
+    pp.exact_kmer = p.exactKmer;
     spb_align_params ap;
     fill_align_params(p, E0, tdb.aminoAcidDBSize(), &ap);
     const size_t nq = Q.keys.size();

@@ -63,6 +63,7 @@ struct PrefArgs {
     const Matrices *mat;
     Pattern6 pat;
     int kmerThr, maxHits, minDiag, compBias, minSubUngapped;
+    int exactKmer;           // --exact-kmer-matching: a window looks up only its own k-mer (prefilter_kernel only)
     uint32_t binMask, idBase;
     Rec *gScratch;           // [gridDim.x][cap] (global-memory variant)
     uint32_t cap;            // record capacity per CTA
@@ -363,7 +364,10 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
         const short bias = (short)((b < 0.0f) ? __dsub_rn((double)b, 0.5) : __dadd_rn((double)b, 0.5));
         const short thr = (short)max(A.kmerThr - (int)bias, 0);
         int n1 = 0;
-        if (!hasX && w < P - 1) {   // quirk A: the last window is never counted
+        if (A.exactKmer) {
+            // takeOnlyBestKmer (Prefiltering.cpp:177, QueryMatcher.cpp:221-227): one "outer neighbour", the 3-mer itself
+            n1 = (!hasX && w < P - 1) ? 1 : 0;
+        } else if (!hasX && w < P - 1) {   // quirk A: the last window is never counted
             const int x1 = s_q[w + A.pat.pos[0]] + 20 * s_q[w + A.pat.pos[1]] + 400 * s_q[w + A.pat.pos[2]];
             const int x2 = s_q[w + A.pat.pos[3]] + 20 * s_q[w + A.pat.pos[4]] + 400 * s_q[w + A.pat.pos[5]];
             const int best2 = (int)(__ldg(A.row3 + (size_t)x2 * SPB_N3) >> 16) - SPB_SCORE_OFF;
@@ -386,6 +390,7 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
     const int capScore = 255 - ungBias;
     // similar k-mers before (w, a): number of inner neighbours of every outer neighbour a' < a (KmerGenerator.cpp:186-216)
     auto inner_count = [&](int w, int x1, int x2, int a) -> uint32_t {
+        if (A.exactKmer) return 1u;
         const int s1 = (int)(__ldg(A.row3 + (size_t)x1 * SPB_N3 + a) >> 16) - SPB_SCORE_OFF;
         const int cut2 = (int)s_thr[w] - s1;
         if (cut2 > SPB_CNT3_W - SPB_SCORE_OFF - 1) return 0u;
@@ -421,8 +426,7 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
             const int a0 = (u - s_ubase[w]) << 5;
             const int x1 = s_q[w + A.pat.pos[0]] + 20 * s_q[w + A.pat.pos[1]] + 400 * s_q[w + A.pat.pos[2]];
             const int x2 = s_q[w + A.pat.pos[3]] + 20 * s_q[w + A.pat.pos[4]] + 400 * s_q[w + A.pat.pos[5]];
-            const uint32_t nKmers = warp_unit_kmers(A.row3, A.cnt3, x1, x2, (int)s_thr[w], (int)s_n1[w], a0, s_excl[wid], s_i1[wid],
-                [&](uint32_t kmer, uint32_t a, uint32_t b, bool valid) {
+            auto on_kmer = [&](uint32_t kmer, uint32_t a, uint32_t b, bool valid) {
                     uint32_t len = 0;
                     ulonglong2 e = make_ulonglong2(0ull, 0ull);
                     const uint64_t *pb = nullptr;
@@ -457,7 +461,10 @@ __global__ void __launch_bounds__(PF_THREADS) prefilter_kernel(PrefArgs A) {
                             }
                         }
                     }
-                });
+                };
+            uint32_t nKmers = 1;
+            if (A.exactKmer) on_kmer((uint32_t)x1 + 8000u * (uint32_t)x2, 0u, 0u, lane == 0);
+            else nKmers = warp_unit_kmers(A.row3, A.cnt3, x1, x2, (int)s_thr[w], (int)s_n1[w], a0, s_excl[wid], s_i1[wid], on_kmer);
             if (pass == 0 && lane == 0) nk += nKmers;
         }
         __syncthreads();
@@ -2053,6 +2060,7 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
     for (int i = 0; i < SPB_ALPHABET * SPB_ALPHABET; i++) A.minSubUngapped = std::min(A.minSubUngapped, (int)c->hm.ungapped[i]);
     A.binMask = (uint32_t)p->bin_size - 1;
     A.idBase = p->id_base;
+    A.exactKmer = p->exact_kmer ? 1 : 0;
 
     // scratch: s_a start u64[Q], s_b count u32[Q], s_c status u32[Q], s_d need u32[Q], s_e slow list u32[Q], s_f counters, s_g arena
     if (c->s_a.ensure((size_t)Q * 8) || c->s_b.ensure((size_t)Q * 4) || c->s_c.ensure((size_t)Q * 4) || c->s_d.ensure((size_t)Q * 4) ||
@@ -2133,6 +2141,14 @@ extern "C" int spb_prefilter_resident(spb_ctx *c, const spb_prefilter_params *p)
         unsigned int *tc = reinterpret_cast<unsigned int *>(c->s_f.as<unsigned long long>() + 16);
         const uint32_t *curList = c->d_qorder.as<uint32_t>();   // longest queries first (tail of a launch)
         uint32_t curN = Q;
+        if (A.exactKmer) {
+            // --exact-kmer-matching: one k-mer per window -- nothing to expand; every query goes straight to the CTA-per-query
+            // kernel of stage 2, which enumerates the window's own k-mer instead of its similar k-mers
+            curN = 0;
+            SPB_CUDA(cudaMemcpyAsync(c->s_e.p, curList, (size_t)Q * 4, cudaMemcpyDeviceToDevice, st));
+            memset(h_ctr, 0, sizeof(h_ctr));
+            h_ctr[0] = Q;
+        }
         unsigned int nTilesRun = 0;
         bool arenaOverflow = false;
         for (int round = 0; curN; round++) {

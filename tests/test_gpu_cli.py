@@ -214,3 +214,11 @@ def test_compressed_dbs_in_and_out(tmp_path):
     run("search", os.path.join(CZ, "qsetdb"), os.path.join(CZ, "targets"), fused, *merged)
     assert dbio.read_dbtype(fused) == dbio.DBTYPE_ALIGNMENT_RES
     assert dbio.read_entries(fused) == dbio.read_entries(os.path.join(C1, "prot_result"))
+
+
+def test_exact_kmer_matching_flag(tmp_path):
+    """`spb200 prefilter --exact-kmer-matching 1` writes the reference binary's lists (tests/golden/criteria/pref_long_exact)"""
+    w = _long_set_dbs(tmp_path)
+    run("prefilter", w + "/qdb", w + "/tdb", w + "/pref", *_with(PREF_FLAGS, **{"--exact-kmer-matching": 1}))
+    got = {k: v for k, v in entries_as_rows(w + "/pref").items() if v}
+    assert got == read_dump(os.path.join(GOLDEN, "criteria", "pref_long_exact.txt.gz"))

@@ -128,6 +128,22 @@ def test_prefilter_saturated_families_golden(searcher, maxseqs):
     assert not bad, bad[:5]
 
 
+@pytest.mark.parametrize("name", ["small", "long"])
+def test_prefilter_exact_kmer_matching_golden(searcher, name):
+    """--exact-kmer-matching 1 against the reference binary's lists: one k-mer per window, served by the CTA-per-query kernel"""
+    T, Q = Cm.load_fasta_set(name)
+    tres, toff = _product_mask(searcher, T)
+    rows, st = _gpu_prefilter_rows(searcher, tres, toff, Q, exact_kmer=1)
+    ref = Cm.dump("criteria", "pref_%s_exact.txt.gz" % name)
+    bad = [(i, rows[i][:3], ref.get(i, [])[:3]) for i in range(len(Q)) if rows[i] != ref.get(i, [])]
+    assert not bad, bad[:4]
+    assert st["n_slow_path"] == len(Q)
+    # the default mode on the same context afterwards is untouched
+    rows, _ = _gpu_prefilter_rows(searcher, tres, toff, Q)
+    ref = Cm.dump(name, "pref_mask1.txt.gz")
+    assert all(rows[i] == ref.get(i, []) for i in range(len(Q)))
+
+
 def test_prefilter_long_golden(searcher):
     T, Q = Cm.load_fasta_set("long")
     tres, toff = _product_mask(searcher, T)

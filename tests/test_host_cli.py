@@ -182,7 +182,7 @@ def test_acceptance_criteria_flags_are_parsed():
     out = run("showparams", "align", "q", "t", "p", "a", *ALN_FLAGS, "-c", "0.8", "--cov-mode", "2", "--min-seq-id", "0.3",
               "--seq-id-mode", "1", "--min-aln-len", "12", "-a", "0", "--alignment-mode", "3").stdout
     assert "cov=0.8 cov_mode=2 min_seq_id=0.3 min_aln_len=12 seq_id_mode=1 backtrace=0" in out
-    out = run("showparams", "prefilter", "q", "t", "p", *PREF_FLAGS, "-c", "0.5", "--cov-mode", "5").stdout
+    out = run("showparams", "prefilter", "q", "t", "p", *PREF_FLAGS, "-c", "0.5", "--cov-mode", "5", "--exact-kmer-matching", "1").stdout
     assert "cov=0.5 cov_mode=5" in out
 
 

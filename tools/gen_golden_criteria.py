@@ -7,6 +7,7 @@
                                              StripedSmithWaterman.cpp:195-240 coverage exits, Util.cpp:533-567), and the
                                              10-column rows of `--alignment-mode 3` without `-a` (Matcher.cpp:355-366)
   tests/golden/criteria/pref_long_c0.5_m*    prefilter lists of the `long` set under -c 0.5 --cov-mode 0 / 1 / 2 / 5 (Prefiltering.cpp:834-842)
+  tests/golden/criteria/pref_{small,long}_exact  prefilter lists under --exact-kmer-matching 1
   tests/golden/criteria/cases.json           the flag set of every alignment fixture
 Usage: python tools/gen_golden_criteria.py
 """
@@ -103,6 +104,13 @@ def main():
     for mode in (0, 1, 2, 5):
         tag = "pref_long_c0.5_m%d" % mode
         flags = refbin.PREF_FLAGS.format(maxseqs=300, mask=1, threads=4, sens="5.7").replace(" -c 0 --cov-mode 0 ", " -c 0.5 --cov-mode %d " % mode)
+        run("%s prefilter %s/qdb %s/tdb %s/%s %s" % (B, w, w, w, tag, flags))
+        dump_db(os.path.join(w, tag), os.path.join(out, tag + ".txt.gz"))
+    # --exact-kmer-matching 1: every window looks up its own k-mer only (Prefiltering.cpp:177, QueryMatcher.cpp:221-231)
+    for name in ("small", "long"):
+        w = os.path.join(work, name)
+        tag = "pref_%s_exact" % name
+        flags = refbin.PREF_FLAGS.format(maxseqs=300, mask=1, threads=4, sens="5.7").replace("--exact-kmer-matching 0", "--exact-kmer-matching 1")
         run("%s prefilter %s/qdb %s/tdb %s/%s %s" % (B, w, w, w, tag, flags))
         dump_db(os.path.join(w, tag), os.path.join(out, tag + ".txt.gz"))
     with open(os.path.join(out, "cases.json"), "w") as f:
