@@ -311,7 +311,8 @@ static void build_index(spo_prefilter *pf) {
                 mul *= 20;
             }
             if (hasX) continue;
-            if (pf->p.kmerThr > 0 && self < pf->p.kmerThr) continue;
+            /* an exact-matching search indexes every k-mer: localKmerThr = 0 (Prefiltering.cpp:509-512) */
+            if (!pf->p.exactKmer && pf->p.kmerThr > 0 && self < pf->p.kmerThr) continue;
             tmp[c].k = k; tmp[c].id = t; tmp[c].pos = (uint16_t)w; c++;
         }
         if (c > 1) qsort(tmp, c, sizeof(post_tmp), cmp_kp);

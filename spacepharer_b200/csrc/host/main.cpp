@@ -436,7 +436,8 @@ void build_index_from_masked(Engine &E, const Params &p, const SeqSet &T, const 
                              uint64_t nMasked, const std::string &tName) {
     const std::string pattern = p.spacedPattern.empty() ? (p.spacedMode ? "11011101" : "111111") : p.spacedPattern;
     // index-side threshold (Prefiltering.cpp:510-513): only for exact matching or when the k-mer threshold is small enough
-    check(spb_index_build(E.ctx, masked.data(), T.off.data(), (uint32_t)T.keys.size(), pattern.c_str(), kmerThr), "spb_index_build");
+    // (an exact-matching search indexes every k-mer: localKmerThr = 0)
+    check(spb_index_build(E.ctx, masked.data(), T.off.data(), (uint32_t)T.keys.size(), pattern.c_str(), p.exactKmer ? 0 : kmerThr), "spb_index_build");
     spb_index_stats st;
     check(spb_index_stats_get(E.ctx, &st), "spb_index_stats_get");
     if (cached)

@@ -133,13 +133,14 @@ def test_createindex_cache_is_used_and_validated(tmp_path):
     assert dbio.read_entries(pref + "2") == dbio.read_entries(os.path.join(C1, "pref_0"))
 
 
-def _long_set_dbs(tmp_path):
+def _long_set_dbs(tmp_path, fixture="long"):
     """the `long` fixture set as on-disk DBs (keys = order of the FASTA, createdb --shuffle 0) + its all-pairs prefilter DB"""
     from conftest import read_fasta_gz
     w = str(tmp_path)
+    os.makedirs(w, exist_ok=True)
     n = {}
     for name in ("t", "q"):
-        seqs = [s.encode() for s in read_fasta_gz(os.path.join(GOLDEN, "long", name + ".fasta.gz"))]
+        seqs = [s.encode() for s in read_fasta_gz(os.path.join(GOLDEN, fixture, name + ".fasta.gz"))]
         dbio.write_sequence_db(os.path.join(w, name + "db"), range(len(seqs)), seqs)
         n[name] = len(seqs)
     body = b"".join(b"%d\t0\t0\n" % t for t in range(n["t"]))
@@ -222,3 +223,8 @@ def test_exact_kmer_matching_flag(tmp_path):
     run("prefilter", w + "/qdb", w + "/tdb", w + "/pref", *_with(PREF_FLAGS, **{"--exact-kmer-matching": 1}))
     got = {k: v for k, v in entries_as_rows(w + "/pref").items() if v}
     assert got == read_dump(os.path.join(GOLDEN, "criteria", "pref_long_exact.txt.gz"))
+    # -s 1.0: the index of an exact-matching search is not pruned by the k-mer threshold (Prefiltering.cpp:509-512)
+    w = _long_set_dbs(tmp_path / "small", "small")
+    run("prefilter", w + "/qdb", w + "/tdb", w + "/pref", *_with(PREF_FLAGS, **{"--exact-kmer-matching": 1, "-s": "1.0"}))
+    got = {k: v for k, v in entries_as_rows(w + "/pref").items() if v}
+    assert got == read_dump(os.path.join(GOLDEN, "criteria", "pref_small_exact_s1.0.txt.gz"))

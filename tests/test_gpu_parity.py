@@ -138,6 +138,16 @@ def test_prefilter_exact_kmer_matching_golden(searcher, name):
     bad = [(i, rows[i][:3], ref.get(i, [])[:3]) for i in range(len(Q)) if rows[i] != ref.get(i, [])]
     assert not bad, bad[:4]
     assert st["n_slow_path"] == len(Q)
+    if name == "small":
+        # -s 1.0: the threshold (154) neither selects k-mers nor prunes the index of an exact-matching search
+        # (localKmerThr = 0, Prefiltering.cpp:509-512) -- same lists
+        from spacepharer_b200 import api
+        assert Cm.dump("criteria", "pref_small_exact_s1.0.txt.gz") == ref
+        searcher.build_index(tres, toff, kmer_thr=0)
+        qres, qoff = O.concat(Q)
+        off, hits, _ = searcher.prefilter(qres, qoff, kmer_thr=154, exact_kmer=1)
+        got = [api.format_prefilter_rows(hits[int(off[i]):int(off[i + 1])], None) for i in range(len(Q))]
+        assert all(got[i] == ref.get(i, []) for i in range(len(Q)))
     # the default mode on the same context afterwards is untouched
     rows, _ = _gpu_prefilter_rows(searcher, tres, toff, Q)
     ref = Cm.dump(name, "pref_mask1.txt.gz")

@@ -113,6 +113,12 @@ def main():
         flags = refbin.PREF_FLAGS.format(maxseqs=300, mask=1, threads=4, sens="5.7").replace("--exact-kmer-matching 0", "--exact-kmer-matching 1")
         run("%s prefilter %s/qdb %s/tdb %s/%s %s" % (B, w, w, w, tag, flags))
         dump_db(os.path.join(w, tag), os.path.join(out, tag + ".txt.gz"))
+    # ... at -s 1.0 (k-mer threshold 154): the index of an exact-matching search is built WITHOUT the self-score pruning of its
+    # k-mers (localKmerThr = 0, Prefiltering.cpp:509-512), so the lists hold hits the pruned index of pref_s1.0 cannot give
+    w = os.path.join(work, "small")
+    flags = refbin.PREF_FLAGS.format(maxseqs=300, mask=1, threads=4, sens="1.0").replace("--exact-kmer-matching 0", "--exact-kmer-matching 1")
+    run("%s prefilter %s/qdb %s/tdb %s/pref_small_exact_s1.0 %s" % (B, w, w, w, flags))
+    dump_db(os.path.join(w, "pref_small_exact_s1.0"), os.path.join(out, "pref_small_exact_s1.0.txt.gz"))
     with open(os.path.join(out, "cases.json"), "w") as f:
         json.dump({t: dict(set=c[0], evalue=float(c[1]), cov=c[2], cov_mode=c[3], min_seq_id=c[4], min_aln_len=c[5], backtrace=c[6],
                         seq_id_mode=c[7])
