@@ -246,10 +246,11 @@ struct SeqSet {
     std::vector<uint8_t> res;
     std::vector<uint64_t> off;
     std::vector<uint32_t> keys;   // DB key of every sequence (position = id)
+    std::vector<uint8_t> lower;   // 1 where the DB holds a lower-case letter (only filled for --mask-lower-case 1)
 };
 
 // ids in LINEAR_ACCESS order (what Prefiltering / IndexBuilder use for both DBs, Prefiltering.cpp:163-164,187-188)
-void load_sequences(const DBReader &db, const SubMat &m, SeqSet &s) {
+void load_sequences(const DBReader &db, const SubMat &m, SeqSet &s, bool wantLower = false) {
     const size_t n = db.size();
     s.off.assign(n + 1, 0);
     s.keys.resize(n);
@@ -263,10 +264,16 @@ void load_sequences(const DBReader &db, const SubMat &m, SeqSet &s) {
     }
     s.off[n] = total;
     s.res.resize(total + 1);
+    if (wantLower) s.lower.assign(total + 1, 0);
 #pragma omp parallel for schedule(dynamic, 256)
     for (long i = 0; i < (long)n; i++) {
         const DBEntry &e = db.linear((size_t)i);
-        m.encode(db.data(e), (size_t)(s.off[i + 1] - s.off[i]), s.res.data() + s.off[i]);
+        const size_t len = (size_t)(s.off[i + 1] - s.off[i]);
+        m.encode(db.data(e), len, s.res.data() + s.off[i]);
+        if (wantLower) {
+            const char *c = db.data(e);
+            for (size_t k = 0; k < len; k++) s.lower[s.off[i] + k] = islower((unsigned char)c[k]) ? 1 : 0;
+        }
     }
 }
 
@@ -382,7 +389,9 @@ uint64_t seqset_checksum(const SeqSet &T) {
     uint64_t h = 1469598103934665603ULL;
     h = fnv1a(T.keys.data(), T.keys.size() * 4, h);
     h = fnv1a(T.off.data(), T.off.size() * 8, h);
-    return fnv1a(T.res.data(), (size_t)T.off.back(), h);
+    h = fnv1a(T.res.data(), (size_t)T.off.back(), h);
+    if (!T.lower.empty()) h = fnv1a(T.lower.data(), (size_t)T.off.back(), h);   // --mask-lower-case 1: the case is part of the input
+    return h;
 }
 
 void fill_idx_header(const Params &p, const Engine &E, const SeqSet &T, uint64_t srcDataSize, IdxHeader *h) {
@@ -403,6 +412,16 @@ void mask_targets(Engine &E, const Params &p, const SeqSet &T, std::vector<uint8
     *nMasked = 0;
     if (p.mask)   // IndexBuilder.cpp:137-149
         check(spb_tantan_mask(E.seed.prob, E.seed.pback, masked.data(), T.off.data(), (uint32_t)T.keys.size(), p.threads, nMasked), "spb_tantan_mask");
+    if (p.maskLower) {   // IndexBuilder.cpp:151-160: after tantan, every lower-case letter of the DB becomes X in the index
+        if (T.lower.size() != T.res.size()) throw Fail("--mask-lower-case 1: the target sequences were read without their case");
+        const uint8_t x = E.seed.aa2num[(unsigned char)'X'];
+        const size_t n = (size_t)T.off.back();
+        uint64_t cnt = 0;
+#pragma omp parallel for reduction(+ : cnt) schedule(static)
+        for (long i = 0; i < (long)n; i++)
+            if (T.lower[(size_t)i]) { masked[(size_t)i] = x; cnt++; }     // (counted like the reference: also where tantan masked already)
+        *nMasked += cnt;
+    }
 }
 
 // true if <name>.spbidx exists and belongs to exactly this target set and these masking parameters
@@ -463,7 +482,7 @@ void build_target_index(Engine &E, const Params &p, const SeqSet &T, int kmerThr
 // --split-mode (needs --split > 1), --realign-score-bias / --realign-max-seqs (need --realign 1), --zdrop (nucleotide
 // alignment only), --alignment-output-mode 0, --pca / --pcb (profiles), --db-load-mode, --split-memory-limit (memory management).
 void check_unimplemented_flags(const Params &p) {
-    if (p.maskLower != 0) throw Fail("--mask-lower-case 1 is not supported (lower-case masking is not applied to the index)");
+    if (p.maskLower != 0 && p.maskLower != 1) throw Fail("Error in argument --mask-lower-case");
     {
         // "--alph-size nucl:5,aa:21" or a single number for both
         std::string aa = p.alphSize;
@@ -526,7 +545,7 @@ int run_prefilter(int argc, const char **argv) {
     log_line(p, "Target database size: %zu type: Aminoacid", tdb.size());
     SeqSet Q, T;
     load_sequences(qdb, E.seed, Q);
-    load_sequences(tdb, E.seed, T);
+    load_sequences(tdb, E.seed, T, p.maskLower == 1);
     check_seq_len(p, Q.off, "query");
     check_seq_len(p, T.off, "target");
     const int kmerThr = kmer_threshold(p.sensitivity, p.kmerScore, 6);
@@ -984,7 +1003,7 @@ void search_dbs(const Params &p, const std::string &qName, const std::string &tN
     pc.mark("open DBs");
     SeqSet Q, T;
     load_sequences(qdb, E0.seed, Q);
-    load_sequences(tdb, E0.seed, T);
+    load_sequences(tdb, E0.seed, T, p.maskLower == 1);
     pc.mark("encode sequences");
     check_seq_len(p, Q.off, "query");
     check_seq_len(p, T.off, "target");
@@ -1276,7 +1295,7 @@ int run_createindex(int argc, const char **argv) {
     DBReader tdb;
     tdb.open(p.db[0]);
     SeqSet T;
-    load_sequences(tdb, E.seed, T);
+    load_sequences(tdb, E.seed, T, p.maskLower == 1);
     std::vector<uint8_t> masked;
     uint64_t nMasked = 0;
     mask_targets(E, p, T, masked, &nMasked);

@@ -228,3 +228,21 @@ def test_exact_kmer_matching_flag(tmp_path):
     run("prefilter", w + "/qdb", w + "/tdb", w + "/pref", *_with(PREF_FLAGS, **{"--exact-kmer-matching": 1, "-s": "1.0"}))
     got = {k: v for k, v in entries_as_rows(w + "/pref").items() if v}
     assert got == read_dump(os.path.join(GOLDEN, "criteria", "pref_small_exact_s1.0.txt.gz"))
+
+
+@pytest.mark.parametrize("mask", [0, 1])
+def test_mask_lower_case_flag(tmp_path, mask):
+    """`spb200 prefilter --mask-lower-case 1` on a target DB with lower-case stretches writes the reference binary's lists; the
+    index cache written with the flag is picked up"""
+    from conftest import read_fasta_gz
+    w = _long_set_dbs(tmp_path, "small")
+    seqs = [x.encode() for x in read_fasta_gz(os.path.join(GOLDEN, "criteria", "t_lower.fasta.gz"))]
+    dbio.write_sequence_db(w + "/tlow", range(len(seqs)), seqs)
+    flags = _with(PREF_FLAGS, **{"--mask-lower-case": 1, "--mask": mask})
+    ref = read_dump(os.path.join(GOLDEN, "criteria", "pref_small_lower_mask%d.txt.gz" % mask))
+    run("prefilter", w + "/qdb", w + "/tlow", w + "/pref", *flags)
+    assert {k: v for k, v in entries_as_rows(w + "/pref").items() if v} == ref
+    run("createindex", w + "/tlow", w + "/tmp", "--mask", str(mask), "--mask-lower-case", "1", "--threads", "2")
+    r = run("prefilter", w + "/qdb", w + "/tlow", w + "/pref2", *flags)
+    assert "masked residues from" in r.stdout
+    assert {k: v for k, v in entries_as_rows(w + "/pref2").items() if v} == ref

@@ -196,8 +196,8 @@ def test_errors_like_the_reference():
 
 
 @pytest.mark.parametrize("module,flags", [
-    ("prefilter", ["--mask-lower-case", "1"]), ("prefilter", ["--alph-size", "nucl:5,aa:13"]), ("prefilter", ["--alph-size", "13"]),
-    ("prefilter", ["--taxon-list", "10239"]), ("align", ["--alignment-mode", "1", "-a", "0"]), ("align", ["--mask-lower-case", "1"]),
+    ("prefilter", ["--mask-lower-case", "2"]), ("prefilter", ["--alph-size", "nucl:5,aa:13"]), ("prefilter", ["--alph-size", "13"]),
+    ("prefilter", ["--taxon-list", "10239"]), ("align", ["--alignment-mode", "1", "-a", "0"]), ("align", ["--mask-lower-case", "2"]),
     ("align", ["--max-accept", "5"]), ("align", ["--cov-mode", "6"]), ("prefilter", ["--add-self-matches", "1"])])
 def test_flags_that_would_change_the_result_are_refused(module, flags):
     """A drop-in must not exit 0 with a DB that differs from the reference's: flags of the two modules that this path does not
@@ -247,3 +247,28 @@ def test_createindex_writes_the_masked_residue_cache(tmp_path):
     order = np.argsort(dbio.read_db(db)[1], kind="stable")
     want = np.concatenate([O.tantan_mask(m80, O.encode(seqs[i], m80))[0] for i in order])
     assert (masked == want).all() and int((want == 20).sum()) >= 866
+
+
+@pytest.mark.parametrize("mask", [0, 1])
+def test_createindex_masks_lower_case_letters(tmp_path, mask):
+    """--mask-lower-case 1 (IndexBuilder.cpp:151-160): the residues the index is built from carry X wherever the DB holds a lower-case
+    letter, on top of tantan; the cache of the same DB without the flag is not accepted for it"""
+    import struct
+    from conftest import read_fasta_gz
+    seqs = [x.encode() for x in read_fasta_gz(os.path.join(GOLDEN, "criteria", "t_lower.fasta.gz"))]
+    db = str(tmp_path / "tdb")
+    dbio.write_sequence_db(db, range(len(seqs)), seqs)
+    r = run("createindex", db, str(tmp_path / "tmp"), "--threads", "2", "--mask", str(mask), "--mask-lower-case", "1")
+    raw = open(db + ".spbidx", "rb").read()
+    version, m, mask_lower, _ = struct.unpack_from("<4I", raw, 8)
+    T, N, _, checksum = struct.unpack_from("<4Q", raw, 24)
+    assert (m, mask_lower) == (mask, 1) and T == len(seqs)
+    masked = np.frombuffer(raw, dtype=np.uint8, count=N, offset=56 + 64 + 4 * T + 8 * (T + 1))
+    Tn, low = Cm.lower_case_targets()
+    want = np.concatenate(Cm.mask_lower_case(Cm.mask_targets(Tn) if mask else Tn, low))
+    assert (masked == want).all()
+    assert "%d masked" % (int(sum(l.sum() for l in low)) + (int(sum((a != b).sum() for a, b in zip(Cm.mask_targets(Tn), Tn))) if mask else 0)) in r.stdout
+    # without the flag: other header, other checksum input
+    run("createindex", db, str(tmp_path / "tmp"), "--threads", "2", "--mask", str(mask))
+    raw2 = open(db + ".spbidx", "rb").read()
+    assert struct.unpack_from("<4I", raw2, 8)[2] == 0 and struct.unpack_from("<4Q", raw2, 24)[3] != checksum

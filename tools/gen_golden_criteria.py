@@ -8,6 +8,8 @@
                                              10-column rows of `--alignment-mode 3` without `-a` (Matcher.cpp:355-366)
   tests/golden/criteria/pref_long_c0.5_m*    prefilter lists of the `long` set under -c 0.5 --cov-mode 0 / 1 / 2 / 5 (Prefiltering.cpp:834-842)
   tests/golden/criteria/pref_{small,long}_exact  prefilter lists under --exact-kmer-matching 1
+  tests/golden/criteria/t_lower.fasta.gz, pref_small_lower_mask{0,1}  targets of `small` with lower-case stretches and the lists under
+                                             --mask-lower-case 1 (IndexBuilder.cpp:151-160)
   tests/golden/criteria/cases.json           the flag set of every alignment fixture
 Usage: python tools/gen_golden_criteria.py
 """
@@ -119,6 +121,30 @@ def main():
     flags = refbin.PREF_FLAGS.format(maxseqs=300, mask=1, threads=4, sens="1.0").replace("--exact-kmer-matching 0", "--exact-kmer-matching 1")
     run("%s prefilter %s/qdb %s/tdb %s/pref_small_exact_s1.0 %s" % (B, w, w, w, flags))
     dump_db(os.path.join(w, "pref_small_exact_s1.0"), os.path.join(out, "pref_small_exact_s1.0.txt.gz"))
+    # --mask-lower-case 1: lower-case letters of the target DB become X in the index, after tantan (IndexBuilder.cpp:151-160).
+    # Targets = the `small` set with seeded lower-case stretches (createdb keeps the case).
+    import numpy as np
+    rng = np.random.default_rng(41)
+    w = os.path.join(work, "small")
+    with open(os.path.join(w, "t.fasta")) as f:
+        recs = f.read().split(">")[1:]
+    with open(os.path.join(w, "t_lower.fasta"), "w") as f:
+        for r in recs:
+            head, seq = r.split("\n", 1)
+            seq = list(seq.replace("\n", ""))
+            for _ in range(int(rng.integers(0, 4))):
+                a = int(rng.integers(0, len(seq)))
+                b = min(len(seq), a + int(rng.integers(1, 25)))
+                seq[a:b] = [c.lower() for c in seq[a:b]]
+            f.write(">%s\n%s\n" % (head, "".join(seq)))
+    with open(os.path.join(w, "t_lower.fasta"), "rb") as f, gzip.open(os.path.join(out, "t_lower.fasta.gz"), "wb", 9) as g:
+        g.write(f.read())
+    run("%s createdb %s/t_lower.fasta %s/tdb_lower --dbtype 1 --shuffle 0" % (B, w, w))
+    for mask in (0, 1):
+        tag = "pref_small_lower_mask%d" % mask
+        flags = refbin.PREF_FLAGS.format(maxseqs=300, mask=mask, threads=4, sens="5.7").replace("--mask-lower-case 0", "--mask-lower-case 1")
+        run("%s prefilter %s/qdb %s/tdb_lower %s/%s %s" % (B, w, w, w, tag, flags))
+        dump_db(os.path.join(w, tag), os.path.join(out, tag + ".txt.gz"))
     with open(os.path.join(out, "cases.json"), "w") as f:
         json.dump({t: dict(set=c[0], evalue=float(c[1]), cov=c[2], cov_mode=c[3], min_seq_id=c[4], min_aln_len=c[5], backtrace=c[6],
                         seq_id_mode=c[7])
