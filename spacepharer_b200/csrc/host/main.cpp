@@ -482,6 +482,10 @@ void build_target_index(Engine &E, const Params &p, const SeqSet &T, int kmerThr
 // --split-mode (needs --split > 1), --realign-score-bias / --realign-max-seqs (need --realign 1), --zdrop (nucleotide
 // alignment only), --alignment-output-mode 0, --pca / --pcb (profiles), --db-load-mode, --split-memory-limit (memory management).
 void check_unimplemented_flags(const Params &p) {
+    // a DB searched against itself: the reference lists the identity hit first and scores it with scoreIdentical
+    // (Prefiltering.cpp:539-552,808-820; Alignment.cpp:62,384-394).  SpacePHARER never does that (spacers vs phages); refused.
+    if (p.db.size() >= 2 && p.db[0] == p.db[1])
+        throw Fail("query and target database are the same: the self-match handling of the reference is not supported on this path");
     if (p.maskLower != 0 && p.maskLower != 1) throw Fail("Error in argument --mask-lower-case");
     {
         // "--alph-size nucl:5,aa:21" or a single number for both

@@ -211,6 +211,13 @@ def test_flags_that_would_change_the_result_are_refused(module, flags):
     run("showparams", module, *dbs, *base, "--compressed", "1")
 
 
+def test_same_query_and_target_db_is_refused():
+    """the reference treats a DB searched against itself specially (identity hit first, scoreIdentical); not on this path"""
+    for module, dbs in (("prefilter", ["db", "db", "p"]), ("align", ["db", "db", "p", "a"])):
+        r = run("showparams", module, *dbs, *(PREF_FLAGS if module == "prefilter" else ALN_FLAGS), ok=False)
+        assert r.returncode == 1 and "not supported" in r.stderr
+
+
 def test_no_cpu_fallback(tmp_path):
     import torch
     if torch.cuda.is_available():
