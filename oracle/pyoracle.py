@@ -325,6 +325,54 @@ def prefilter_coverage_filter(rows, cov, cov_mode, qlen, tlens):
     return [r for r in rows if can_be_covered(cov, cov_mode, qlen, tlens[r[0]])]
 
 
+def decompose_by_amino_acid(entry_lengths, world):
+    """DBReader::decomposeDomainByAminoAcid (M/commons/DBReader.cpp:1171-1213) for all ranks: entry_lengths = index lengths
+    (residues + 2) in id order -> [(start, count)] per split; greedy cut once a split holds >= ceil(dataSize / world) bytes"""
+    n = len(entry_lengths)
+    if world == 1:
+        return [(0, n)]
+    if n <= world:
+        return [(r if r < n else 0, 1 if r < n else 0) for r in range(world)]
+    data = int(sum(entry_lengths))
+    chunk = -(-data // world)
+    per = [0] * world
+    rank = acc = 0
+    for l in entry_lengths:
+        if acc >= chunk:
+            acc = 0
+            rank += 1
+        acc += int(l)
+        per[rank] += 1
+    out, start = [], 0
+    for c in per:
+        out.append((start, c))
+        start += c
+    return out
+
+
+def target_split_prefilter(T, Q, m80, m40u, split, max_seqs=300, threads=4, **kw):
+    """MMseqs2's own target split (--split N --split-mode 0): every split is searched with max-seqs / N + 4 sqrt(max-seqs / N)
+    (Prefiltering.cpp:343-346), the lists of a query are concatenated and sorted by (|score| desc, key asc) without a cut
+    (mergeTargetSplits, Prefiltering.cpp:364-481; hit_t::compareHitsByScoreAndId).  T = masked targets, keys = positions.
+    -> per query [(id, score, diag)]"""
+    import math
+    max_res = min(len(T), max_seqs)
+    if split > 1:
+        max_res = max(1, max_res // split + int(4 * math.sqrt(max_res / split)))
+    qres, qoff = concat(Q)
+    rows = [[] for _ in Q]
+    for start, count in decompose_by_amino_acid([len(t) + 2 for t in T], split):
+        if count == 0:
+            continue
+        tres, toff = concat(T[start:start + count])
+        pf = Prefilter(tres, toff, m80, m40u, max_seqs=max_res, **kw)
+        off, hits = pf.batch(qres, qoff, threads=threads)
+        pf.close()
+        for qi in range(len(Q)):
+            rows[qi] += [(int(h["id"]) + start, int(h["score"]), int(h["diag"])) for h in hits[int(off[qi]):int(off[qi + 1])]]
+    return [sorted(r, key=lambda h: (-abs(h[1]), h[0])) for r in rows]
+
+
 def format_row(tkey, a, qlen, tlen, backtrace=True):
     buf = C.create_string_buffer(2048)
     n = (lib().spo_format_row if backtrace else lib().spo_format_row_nobt)(buf, tkey, C.byref(a), qlen, tlen)

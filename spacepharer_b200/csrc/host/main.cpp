@@ -86,6 +86,7 @@ struct Params {
     std::string alphSize = "nucl:5,aa:21", taxonList;
     int maxSeqLen = 65535;
     int device = 0, binSize = 0, byteLanes = 32, wordLanes = 16;
+    bool targetSplitOk = false; // set by the prefilter module: --split N --split-mode 0 (the reference's own target split) is served
     int gpus = 1;              // search / predictmatch: devices device .. device + gpus - 1, k-mer table sharded over them (index split)
     int lanes = 2;             // search / predictmatch: contexts per device that share its index and overlap their batches (one host thread each)
     int oversubscribe = 0;     // 1: with fewer devices than --gpus, several shard contexts share a device (same code path; tests)
@@ -514,8 +515,12 @@ void check_search_params(const Params &p) {
     if (p.kmerSize != 0 && p.kmerSize != 6) throw Fail("The k-mer size " + std::to_string(p.kmerSize) + " is not valid. (spb200 implements k = 6)");
     if (p.diagScore != 1) throw Fail("--diag-score 0 is not supported");
     if (p.exactKmer != 0 && p.exactKmer != 1) throw Fail("Error in argument --exact-kmer-matching");
-    if (p.split > 1) throw Fail("--split > 1 (the reference's lossy target split) is not implemented; spread one DB over several GPUs "
-                                "with --gpus N (k-mer table sharded over the devices, unsplit result)");
+    // --split N with --split-mode 1 (query split) or 2 (auto: query split whenever the memory suffices, Prefiltering.cpp:258-290) gives
+    // the unsplit result and needs nothing here; --split-mode 0 is the reference's lossy target split (prefilter module only)
+    if (p.split < 0 || p.splitMode < 0 || p.splitMode > 2) throw Fail("Error in argument --split / --split-mode");
+    if (p.split > 1 && p.splitMode == 0 && !p.targetSplitOk)
+        throw Fail("--split > 1 with --split-mode 0 (the reference's lossy target split) is only served by the prefilter module; spread one "
+                   "DB over several GPUs with --gpus N (k-mer table sharded over the devices, unsplit result)");
     if (p.gpus < 1 || p.gpus > 8) throw Fail("--gpus must be 1..8");
     if (p.lanes < 1 || p.lanes > 8) throw Fail("--lanes must be 1..8");
     if (p.addSelf != 0) throw Fail("--add-self-matches is not supported on this path");
@@ -536,9 +541,128 @@ bool can_be_covered(float covThr, int covMode, float qLen, float tLen) {
     }
 }
 
+// DBReader::decomposeDomainByAminoAcid (M/commons/DBReader.cpp:1171-1213) for every rank: entries in id order, entry length =
+// residues + 2 as in the index; a split is closed once it holds ceil(dataSize / world) bytes
+std::vector<std::pair<size_t, size_t>> decompose_by_amino_acid(const SeqSet &T, size_t world) {
+    const size_t n = T.keys.size();
+    std::vector<std::pair<size_t, size_t>> out(world, std::make_pair((size_t)0, (size_t)0));
+    if (world == 1) { out[0] = std::make_pair((size_t)0, n); return out; }
+    if (n <= world) {
+        for (size_t r = 0; r < world; r++) out[r] = std::make_pair(r < n ? r : (size_t)0, r < n ? (size_t)1 : (size_t)0);
+        return out;
+    }
+    const uint64_t dataSize = T.off.back() + 2 * (uint64_t)n;
+    const uint64_t chunk = (uint64_t)ceil((double)dataSize / (double)world);
+    size_t rank = 0;
+    uint64_t acc = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (acc >= chunk) { acc = 0; rank++; }
+        acc += T.off[i + 1] - T.off[i] + 2;
+        out[rank].second++;
+    }
+    size_t start = 0;
+    for (size_t r = 0; r < world; r++) { out[r].first = start; start += out[r].second; }
+    return out;
+}
+
+struct PrefHit { uint32_t key; int32_t score, diag; };
+
+// `prefilter --split N --split-mode 0`: MMseqs2's own target split (Prefiltering.cpp:258-362 set-up, :712-733 one index per split,
+// :364-481 mergeTargetSplits).  It is LOSSY by design: every split keeps max-seqs / N + 4 sqrt(max-seqs / N) hits per query and the
+// merge only concatenates and sorts, so the DB differs from the unsplit one -- a drop-in called with these flags has to write
+// what the reference writes.  The splits run one after the other on the context (index rebuilt per split, ~ms on the device).
+int run_prefilter_target_split(Engine &E, const Params &p, const SeqSet &Q, const SeqSet &T, int kmerThr, const std::string &tName,
+                               uint64_t srcDataSize) {
+    std::vector<uint8_t> masked;
+    uint64_t nMasked = 0;
+    masked_targets(E, p, T, tName, srcDataSize, masked, &nMasked);
+    const size_t nq = Q.keys.size(), split = (size_t)p.split;
+    size_t maxRes = std::min<size_t>(T.keys.size(), (size_t)p.maxSeqs);
+    maxRes = std::max<size_t>(1, maxRes / split + (size_t)(4 * sqrt((double)maxRes / (double)split)));      // Prefiltering.cpp:343-346
+    log_line(p, "Target split mode. Searching through %zu splits, %zu hits per query and split", split, maxRes);
+    const std::string pattern = p.spacedPattern.empty() ? (p.spacedMode ? "11011101" : "111111") : p.spacedPattern;
+    const bool covFilter = p.covThr > 0.0 && (p.covMode == 0 || p.covMode == 2 || p.covMode == 5);
+    std::vector<std::vector<PrefHit>> rows(nq);
+    uint64_t nHits = 0;
+    double kernelMs = 0;
+    const auto ranges = decompose_by_amino_acid(T, split);
+    for (size_t sIdx = 0; sIdx < split; sIdx++) {
+        const size_t from = ranges[sIdx].first, cnt = ranges[sIdx].second;
+        if (cnt == 0) continue;
+        std::vector<uint64_t> toff(cnt + 1);
+        for (size_t i = 0; i <= cnt; i++) toff[i] = T.off[from + i] - T.off[from];
+        check(spb_index_build(E.ctx, masked.data() + T.off[from], toff.data(), (uint32_t)cnt, pattern.c_str(), p.exactKmer ? 0 : kmerThr),
+              "spb_index_build");
+        spb_prefilter_params pp;
+        pp.kmer_thr = kmerThr;
+        pp.max_seqs = (int32_t)maxRes;
+        pp.min_diag_score = p.minUngapped;
+        pp.bin_size = p.binSize ? p.binSize : bin_size_for(cnt);      // QueryMatcher sees the split's dbSize
+        pp.comp_bias = p.compBias;
+        pp.id_base = 0;                                               // ids are local to the split (Prefiltering.cpp:827)
+        pp.emit_trunc_keys = 0;
+        pp.exact_kmer = p.exactKmer;
+        for (size_t b0 = 0, b1 = 0; b0 < nq; b0 = b1) {
+            b1 = std::min(nq, b0 + (size_t)p.batch);
+            std::vector<uint64_t> off(b1 - b0 + 1);
+            for (size_t i = b0; i <= b1; i++) off[i - b0] = Q.off[i] - Q.off[b0];
+            spb_prefilter_result *r = nullptr;
+            check(spb_prefilter(E.ctx, Q.res.data() + Q.off[b0], off.data(), (uint32_t)(b1 - b0), &pp, &r), "spb_prefilter");
+            kernelMs += r->kernel_ms;
+#pragma omp parallel for num_threads(p.threads) schedule(static)
+            for (long i = 0; i < (long)(b1 - b0); i++) {
+                const float qLen = (float)(Q.off[b0 + (size_t)i + 1] - Q.off[b0 + (size_t)i]);
+                std::vector<PrefHit> &dst = rows[b0 + (size_t)i];
+                for (uint64_t h = r->offsets[i]; h < r->offsets[i + 1]; h++) {
+                    const spb_hit &x = r->hits[h];
+                    const size_t tid = from + x.id;
+                    if (covFilter && !can_be_covered((float)p.covThr, p.covMode, qLen, (float)(T.off[tid + 1] - T.off[tid]))) continue;
+                    dst.push_back(PrefHit{T.keys[tid], x.score, x.diag});
+                }
+            }
+            spb_free_prefilter_result(r);
+        }
+        log_line(p, "Process prefiltering step %zu of %zu: targets %zu .. %zu", sIdx + 1, split, from, from + cnt);
+    }
+    // mergeTargetSplits: the lists of a query concatenated, sorted by hit_t::compareHitsByScoreAndId; never compressed
+    DBWriter::setCompressedDefault(false);
+    DBWriter out;
+    out.open(p.db[2], DBTYPE_PREFILTER_RES, p.threads);
+#pragma omp parallel num_threads(p.threads)
+    {
+        int th = 0;
+#ifdef _OPENMP
+        th = omp_get_thread_num();
+#endif
+        std::string buf;
+        char tmp[64];
+#pragma omp for schedule(static) reduction(+ : nHits)
+        for (long i = 0; i < (long)nq; i++) {
+            std::vector<PrefHit> &v = rows[(size_t)i];
+            std::sort(v.begin(), v.end(), [](const PrefHit &a, const PrefHit &b) {
+                if (abs(a.score) != abs(b.score)) return abs(a.score) > abs(b.score);
+                return a.key < b.key;
+            });
+            buf.clear();
+            for (const PrefHit &x : v) {
+                char *w = put_uint(tmp, x.key); *w++ = '\t';
+                w = put_int(w, x.score); *w++ = '\t';
+                w = put_int(w, x.diag); *w++ = '\n';
+                buf.append(tmp, (size_t)(w - tmp));
+            }
+            nHits += v.size();
+            out.write(th, Q.keys[(size_t)i], buf.data(), buf.size());
+        }
+    }
+    out.close();
+    log_line(p, "%llu prefilter hits for %zu queries over %zu target splits; match kernels %.3f ms", (unsigned long long)nHits, nq, split, kernelMs);
+    return 0;
+}
+
 int run_prefilter(int argc, const char **argv) {
     Params p;
     parse_args(argc, argv, 2, 3, p);
+    p.targetSplitOk = true;
     check_search_params(p);
     Engine E;
     E.open(p);
@@ -554,6 +678,7 @@ int run_prefilter(int argc, const char **argv) {
     check_seq_len(p, T.off, "target");
     const int kmerThr = kmer_threshold(p.sensitivity, p.kmerScore, 6);
     log_line(p, "k-mer similarity threshold: %d", kmerThr);
+    if (p.split > 1 && p.splitMode == 0) return run_prefilter_target_split(E, p, Q, T, kmerThr, p.db[1], tdb.dataSize());
     build_target_index(E, p, T, kmerThr, p.db[1], tdb.dataSize());
 
     spb_prefilter_params pp;
@@ -1558,6 +1683,7 @@ int run_showparams(int argc, const char **argv) {
     const std::string mod = argv[2];
     Params p;
     parse_args(argc, argv, 3, mod == "align" ? 4 : 3, p);
+    p.targetSplitOk = (mod == "prefilter");
     if (mod == "align") check_align_params(p); else check_search_params(p);
     printf("sub_mat=%s seed_sub_mat=%s kmer_thr=%d max_seqs=%d min_ungapped=%d mask=%d comp_bias=%d pattern=%s "
            "evalue=%g gap_open=%s gap_extend=%s threads=%d cov=%g cov_mode=%d min_seq_id=%g min_aln_len=%d seq_id_mode=%d backtrace=%d\n",

@@ -246,3 +246,20 @@ def test_mask_lower_case_flag(tmp_path, mask):
     r = run("prefilter", w + "/qdb", w + "/tlow", w + "/pref2", *flags)
     assert "masked residues from" in r.stdout
     assert {k: v for k, v in entries_as_rows(w + "/pref2").items() if v} == ref
+
+
+@pytest.mark.parametrize("name,split,maxseqs", [("family", 3, 20), ("small", 2, 100)])
+def test_reference_target_split_flag(tmp_path, name, split, maxseqs):
+    """`spb200 prefilter --split N --split-mode 0` writes what the reference's own (lossy) target split writes: targets cut by
+    decomposeDomainByAminoAcid, max-seqs / N + 4 sqrt(max-seqs / N) hits per split, lists concatenated and sorted
+    (Prefiltering.cpp:343-346,364-481); --split-mode 1 stays the unsplit list"""
+    w = _long_set_dbs(tmp_path, name)
+    flags = _with(PREF_FLAGS, **{"--split": split, "--split-mode": 0, "--max-seqs": maxseqs})
+    r = run("prefilter", w + "/qdb", w + "/tdb", w + "/pref", *flags)
+    assert "Target split mode" in r.stdout
+    got = {k: v for k, v in entries_as_rows(w + "/pref").items() if v}
+    assert got == read_dump(os.path.join(GOLDEN, "criteria", "pref_%s_split%d_max%d.txt.gz" % (name, split, maxseqs)))
+    if name == "family":
+        run("prefilter", w + "/qdb", w + "/tdb", w + "/pref1", *_with(PREF_FLAGS, **{"--split": split, "--split-mode": 1, "--max-seqs": 10}))
+        got = {k: v for k, v in entries_as_rows(w + "/pref1").items() if v}
+        assert got == read_dump(os.path.join(GOLDEN, "family", "pref_max10.txt.gz"))

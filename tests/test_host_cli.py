@@ -186,6 +186,18 @@ def test_acceptance_criteria_flags_are_parsed():
     assert "cov=0.5 cov_mode=5" in out
 
 
+def test_split_flags():
+    """--split N: query split / auto (modes 1, 2) give the unsplit result and are accepted; mode 0, the reference's own lossy target
+    split, is served by the prefilter module"""
+    for mode in ("0", "1", "2"):
+        run("showparams", "prefilter", "q", "t", "p", *PREF_FLAGS, "--split", "3", "--split-mode", mode)
+    r = run("showparams", "prefilter", "q", "t", "p", *PREF_FLAGS, "--split-mode", "3", ok=False)
+    assert r.returncode == 1 and "Error in argument" in r.stderr
+    # the fused search refuses it before touching a device or a DB
+    r = run("search", "q", "t", "out", "--split", "2", "--split-mode", "0", ok=False)
+    assert r.returncode == 1 and "only served by the prefilter module" in r.stderr
+
+
 def test_errors_like_the_reference():
     r = run("prefilter", "q", "t", "p", "--no-such-flag", "1", ok=False)
     assert r.returncode == 1 and "Unrecognized parameter" in r.stderr

@@ -10,6 +10,7 @@
   tests/golden/criteria/pref_{small,long}_exact  prefilter lists under --exact-kmer-matching 1
   tests/golden/criteria/t_lower.fasta.gz, pref_small_lower_mask{0,1}  targets of `small` with lower-case stretches and the lists under
                                              --mask-lower-case 1 (IndexBuilder.cpp:151-160)
+  tests/golden/criteria/pref_family_split3_max20, pref_small_split2_max100  lists of the reference's own target split (--split N --split-mode 0)
   tests/golden/criteria/cases.json           the flag set of every alignment fixture
 Usage: python tools/gen_golden_criteria.py
 """
@@ -144,6 +145,21 @@ def main():
         tag = "pref_small_lower_mask%d" % mask
         flags = refbin.PREF_FLAGS.format(maxseqs=300, mask=mask, threads=4, sens="5.7").replace("--mask-lower-case 0", "--mask-lower-case 1")
         run("%s prefilter %s/qdb %s/tdb_lower %s/%s %s" % (B, w, w, w, tag, flags))
+        dump_db(os.path.join(w, tag), os.path.join(out, tag + ".txt.gz"))
+    # --split N --split-mode 0: MMseqs2's own (lossy) target split -- targets cut by decomposeDomainByAminoAcid, every split searched
+    # with max-seqs / N + 4 sqrt(max-seqs / N), lists concatenated and sorted (Prefiltering.cpp:343-346,364-481,712-733)
+    w = os.path.join(work, "family")
+    os.makedirs(w)
+    for n in ("t", "q"):
+        with gzip.open(os.path.join(GOLD, "family", n + ".fasta.gz"), "rb") as f, open(os.path.join(w, n + ".fasta"), "wb") as g:
+            g.write(f.read())
+        run("%s createdb %s/%s.fasta %s/%sdb --dbtype 1 --shuffle 0" % (B, w, n, w, n))
+    for name, split, maxseqs in (("family", 3, 20), ("small", 2, 100)):
+        w = os.path.join(work, name)
+        tag = "pref_%s_split%d_max%d" % (name, split, maxseqs)
+        flags = refbin.PREF_FLAGS.format(maxseqs=maxseqs, mask=1, threads=4, sens="5.7").replace("--split 0 --split-mode 2",
+                                                                                               "--split %d --split-mode 0" % split)
+        run("%s prefilter %s/qdb %s/tdb %s/%s %s" % (B, w, w, w, tag, flags))
         dump_db(os.path.join(w, tag), os.path.join(out, tag + ".txt.gz"))
     with open(os.path.join(out, "cases.json"), "w") as f:
         json.dump({t: dict(set=c[0], evalue=float(c[1]), cov=c[2], cov_mode=c[3], min_seq_id=c[4], min_aln_len=c[5], backtrace=c[6],
