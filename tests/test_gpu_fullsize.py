@@ -259,6 +259,18 @@ def test_config2_byte_identical_to_the_reference_binary(tmp_path):
     assert r.returncode == 0, r.stderr
     assert "sharded over 2 GPUs" in r.stdout
     assert db_digest(w + "/fused2") == (want["aln_sha256"], want["aln_rows"])
+    # the flag surface beyond the predictmatch defaults at the same size (tools/gen_golden_config2_flags.py): acceptance criteria,
+    # rows without backtrace, --seq-id-mode, exact k-mer matching, the reference's own target split
+    flags = json.load(open(os.path.join(GOLDEN, "config2_flags_digest.json")))
+    assert (flags["n_queries"], flags["n_targets"]) == (nq, nt)
+    for name, c in sorted(flags["cases"].items()):
+        argv = list(ALN_FLAGS if c["module"] == "align" else PREF_FLAGS)
+        for k, v in c["flags"].items():
+            argv[argv.index(k) + 1] = v
+        dbs = [w + "/queries", w + "/targets"] + ([w + "/pref"] if c["module"] == "align" else []) + [w + "/" + name]
+        r = subprocess.run([BIN, c["module"]] + dbs + argv, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert db_digest(w + "/" + name) == (c["sha256"], c["rows"]), name
 
 
 def test_config4_one_million_spacers_byte_identical_to_the_reference_binary(tmp_path):
