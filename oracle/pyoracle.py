@@ -62,6 +62,7 @@ class AlignParams(C.Structure):
         ("byteLanes", C.c_int), ("wordLanes", C.c_int),
         ("g", Gumbel),
         ("covThr", C.c_float), ("covMode", C.c_int), ("seqIdThr", C.c_float), ("alnLenThr", C.c_int), ("seqIdMode", C.c_int),
+        ("swMode", C.c_int),
     ]
 
 
@@ -290,10 +291,25 @@ class Prefilter:
 
 
 def align_params(db_res_count, gap_open=16, gap_extend=2, eval_thr=200.0, comp_bias=1, gumbel=None,
-                 byte_lanes=32, word_lanes=16, cov=0.0, cov_mode=0, min_seq_id=0.0, min_aln_len=0, seq_id_mode=0):
+                 byte_lanes=32, word_lanes=16, cov=0.0, cov_mode=0, min_seq_id=0.0, min_aln_len=0, seq_id_mode=0, sw_mode=0):
     g = Gumbel(**(gumbel or GUMBEL_VTML40_16_2))
     return AlignParams(gap_open, gap_extend, eval_thr, db_res_count, comp_bias, byte_lanes, word_lanes, g,
-                       cov, cov_mode, min_seq_id, min_aln_len, seq_id_mode)
+                       cov, cov_mode, min_seq_id, min_aln_len, seq_id_mode, sw_mode)
+
+
+def sw_mode_for(alignment_mode, backtrace, cov=0.0, min_seq_id=0.0):
+    """Alignment::Alignment + initSWMode (Alignment.cpp:29-37,174-196): -a forces the full mode; --alignment-mode 0 picks by the
+    thresholds.  -> sw_mode of align_params (0 full, 1 score + coverage, 2 score only)"""
+    if backtrace or alignment_mode == 3:
+        return 0
+    if alignment_mode == 2:
+        return 1
+    if alignment_mode == 0:
+        if cov > 0.0 and min_seq_id == 0.0:
+            return 1
+        if cov > 0.0 and min_seq_id > 0.0:
+            return 0
+    return 2
 
 
 def align_pair(m40, p, q, t):

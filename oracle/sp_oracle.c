@@ -1153,6 +1153,21 @@ void spo_align_pair(const spo_matrix *m, const spo_align_params *p, const unsign
     if (b.ref == -1) { free(cb); free(sc); return; } /* no residue could be aligned */
     out->eval = spo_evalue(&p->g, (double)b.score, (double)L, (double)p->dbResCount);
     out->bits = (int)(spo_bitscore(&p->g, (double)b.score) + 0.5);
+    if (p->swMode == 2) {
+        /* SCORE_ONLY: ssw_align returns after the forward pass (:195-197); no start positions (-1), coverage stays 0
+         * (Matcher.cpp:140-147), identity estimated from the score per column over the END positions (:164-169, :205-209) */
+        unsigned qa = (unsigned)(b.read > 1 ? b.read : 1), ta = (unsigned)(b.ref > 1 ? b.ref : 1);
+        float est = (float)(((unsigned short)b.score / (float)(qa > ta ? qa : ta)) * 0.1656 + 0.1141);
+        if (est > 1.0f) est = 1.0f;
+        if (est < 0.0f) est = 0.0f;
+        out->seqId = est;
+        int a = abs(b.read - (-1)), d = abs(b.ref - (-1));   /* computeAlnLength(qStart = -1, qEnd, dbStart = -1, dbEnd) */
+        out->alnLen = (a > d ? a : d) + 1;
+        out->ok = (out->eval <= p->evalThr && out->seqId >= p->seqIdThr && spo_has_coverage(p->covThr, p->covMode, 0.0f, 0.0f) &&
+                   out->alnLen >= p->alnLenThr) ? 1 : 0;
+        free(cb); free(sc);
+        return;
+    }
     if (out->eval > p->evalThr) { free(cb); free(sc); return; } /* ssw_align early return, :191-200 */
     /* reverse pass on q[qEnd..0] against t[tEnd..0] (:202-231) */
     int rl = b.read + 1;
@@ -1174,6 +1189,20 @@ void spo_align_pair(const spo_matrix *m, const spo_align_params *p, const unsign
     const float qCov = spo_compute_cov((unsigned)out->qStart, (unsigned)out->qEnd, (unsigned)L);
     const float tCov = spo_compute_cov((unsigned)out->tStart, (unsigned)out->tEnd, (unsigned)tLen);
     if (!spo_has_coverage(p->covThr, p->covMode, qCov, tCov)) { free(cb); free(sc); return; }
+    if (p->swMode == 1) {
+        /* SCORE_COV: start and end positions, no backtrace (:233-235); identity estimated over the aligned spans */
+        unsigned qa = (unsigned)(out->qEnd - out->qStart > 1 ? out->qEnd - out->qStart : 1);
+        unsigned ta = (unsigned)(out->tEnd - out->tStart > 1 ? out->tEnd - out->tStart : 1);
+        float est = (float)(((unsigned short)b.score / (float)(qa > ta ? qa : ta)) * 0.1656 + 0.1141);
+        if (est > 1.0f) est = 1.0f;
+        if (est < 0.0f) est = 0.0f;
+        out->seqId = est;
+        int a = abs(out->qEnd - out->qStart), d = abs(out->tEnd - out->tStart);
+        out->alnLen = (a > d ? a : d) + 1;
+        out->ok = (out->eval <= p->evalThr && out->seqId >= p->seqIdThr && out->alnLen >= p->alnLenThr) ? 1 : 0;
+        free(cb); free(sc);
+        return;
+    }
     char *bt = banded_trace(t + out->tStart, q + out->qStart, cb + out->qStart, dl, ql, b.score, go, ge, bw, m);
     int ids = 0;
     if (bt) {

@@ -57,13 +57,30 @@ CASES = {
 }
 
 
-def aln_flags(evalue, cov, cov_mode, seq_id, aln_len, backtrace, id_mode):
+# alignment modes without -a (Alignment::initSWMode, Alignment.cpp:174-196): 1 score only (no start positions, identity estimated
+# from the score), 2 score + coverage (start positions, estimated identity), 0 picks by the thresholds; same tuple + alignment mode
+MODE_CASES = {
+    "small_mode0": ("small", "200", 0.0, 0, 0.0, 0, 0, 0, 0),
+    "small_mode1": ("small", "200", 0.0, 0, 0.0, 0, 0, 0, 1),
+    "small_mode2": ("small", "200", 0.0, 0, 0.0, 0, 0, 0, 2),
+    "small_mode0_c0.3_m2": ("small", "200", 0.3, 2, 0.0, 0, 0, 0, 0),
+    "small_mode0_c0.3_m2_id0.5": ("small", "200", 0.3, 2, 0.5, 0, 0, 0, 0),
+    "small_mode1_id0.25_len12": ("small", "200", 0.0, 0, 0.25, 12, 0, 0, 1),
+    "small_mode1_c0.3_m2": ("small", "200", 0.3, 2, 0.0, 0, 0, 0, 1),
+    "long_mode1": ("long", "1.000E-01", 0.0, 0, 0.0, 0, 0, 0, 1),
+    "long_mode2": ("long", "1.000E-01", 0.0, 0, 0.0, 0, 0, 0, 2),
+    "long_mode2_c0.5_m0_id0.3": ("long", "1.000E-01", 0.5, 0, 0.3, 0, 0, 0, 2),
+    "long_mode0_c0.6_m2": ("long", "1.000E-01", 0.6, 2, 0.0, 0, 0, 0, 0),
+}
+
+
+def aln_flags(evalue, cov, cov_mode, seq_id, aln_len, backtrace, id_mode, aln_mode=None):
     f = refbin.ALN_FLAGS.format(evalue=evalue, go=16, ge=2, threads=4)
     f = f.replace(" -c 0 --cov-mode 0 ", " -c %g --cov-mode %d " % (cov, cov_mode))
     f = f.replace("--min-seq-id 0 --min-aln-len 0", "--min-seq-id %g --min-aln-len %d" % (seq_id, aln_len))
     f = f.replace("--seq-id-mode 0", "--seq-id-mode %d" % id_mode)
     if not backtrace:
-        f = f.replace("-a 1 --alignment-mode 2", "-a 0 --alignment-mode 3")
+        f = f.replace("-a 1 --alignment-mode 2", "-a 0 --alignment-mode %d" % (3 if aln_mode is None else aln_mode))
     return f
 
 
@@ -97,9 +114,11 @@ def main():
                 pos += len(body) + 1
         with open(os.path.join(w, "allpairs.dbtype"), "wb") as f:
             f.write((7).to_bytes(4, "little"))        # DBTYPE_PREFILTER_RES
-    for tag, (name, ev, cov, mode, sid, alen, back, idm) in CASES.items():
+    for tag, c in list(CASES.items()) + list(MODE_CASES.items()):
+        name, ev, cov, mode, sid, alen, back, idm = c[:8]
         w = os.path.join(work, name)
-        run("%s align %s/qdb %s/tdb %s/allpairs %s/aln_%s %s" % (B, w, w, w, w, tag, aln_flags(ev, cov, mode, sid, alen, back, idm)))
+        run("%s align %s/qdb %s/tdb %s/allpairs %s/aln_%s %s" % (B, w, w, w, w, tag, aln_flags(ev, cov, mode, sid, alen, back, idm,
+                                                                                            c[8] if len(c) > 8 else None)))
         dump_db(os.path.join(w, "aln_" + tag), os.path.join(out, tag + ".txt.gz"))
     # prefilter lists under -c: hits whose lengths cannot reach the coverage are dropped after the max-seqs cut in the modes
     # 0 / 2 / 5 (Prefiltering.cpp:834-842); mode 1 leaves the list alone
@@ -163,8 +182,8 @@ def main():
         dump_db(os.path.join(w, tag), os.path.join(out, tag + ".txt.gz"))
     with open(os.path.join(out, "cases.json"), "w") as f:
         json.dump({t: dict(set=c[0], evalue=float(c[1]), cov=c[2], cov_mode=c[3], min_seq_id=c[4], min_aln_len=c[5], backtrace=c[6],
-                        seq_id_mode=c[7])
-                   for t, c in CASES.items()}, f, indent=1)
+                        seq_id_mode=c[7], alignment_mode=(c[8] if len(c) > 8 else 3))
+                   for t, c in list(CASES.items()) + list(MODE_CASES.items())}, f, indent=1)
     shutil.rmtree(work)
     print("criteria fixtures written")
 
