@@ -142,7 +142,9 @@ typedef struct spb_align_params {
     float seq_id_thr;               /* --min-seq-id */
     int32_t aln_len_thr;            /* --min-aln-len */
     int32_t seq_id_mode;            /* --seq-id-mode: identities / 0 alignment length, 1 shorter, 2 longer sequence (Util.cpp:588-598) */
-    int32_t reserved;               /* 0 */
+    int32_t sw_mode;                /* 0: score, coverage, sequence identity, backtrace (-a 1 or --alignment-mode 3: what predictmatch runs);
+                                       1: score + coverage (--alignment-mode 2 without -a: no backtrace, identity estimated from the score);
+                                       2: score only (--alignment-mode 1: no start positions either) -- Alignment::initSWMode, Alignment.cpp:174-196 */
 } spb_align_params;
 
 typedef struct spb_aln {     /* Matcher::result_t, M/alignment/Matcher.h:24-119 */

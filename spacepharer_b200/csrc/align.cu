@@ -851,7 +851,34 @@ __device__ __forceinline__ float seq_id_of(int mode, int nIdent, int qLen, int t
 // alignment that fails Alignment::checkCriteria (Alignment.cpp:555-574; Util::hasCoverage Util.cpp:552-567; the coverage exit of
 // ssw_align, StripedSmithWaterman.cpp:226-232, rejects the same pairs).  --max-accept / --max-rejected are unlimited on this path,
 // so the outcome of a pair does not depend on its neighbours and both tests run on the finished alignment, one thread per pair.
-struct Criteria { float covThr; int covMode; float seqIdThr; int alnLenThr; int seqIdMode; };
+struct Criteria { float covThr; int covMode; float seqIdThr; int alnLenThr; int seqIdMode; int swMode; };
+
+// Alignment modes without a backtrace (Alignment::initSWMode, Alignment.cpp:174-196; Matcher::getSWResult, Matcher.cpp:140-169).
+// swMode 1 = SCORE_COV: start and end positions, the alignment length is the longer span, the sequence identity is ESTIMATED from
+// the raw score per column (Matcher::estimateSeqIdByScorePerCol, Matcher.cpp:205-209: float quotient, double constants).
+// swMode 2 = SCORE_ONLY: forward pass only -- start positions -1, coverage 0, the estimate runs over the end positions.
+__device__ __forceinline__ float est_seq_id(int score, unsigned qa, unsigned ta) {
+    const float perCol = (float)(score & 0xFFFF) / (float)max(qa, ta);
+    const float e = __double2float_rn(__dadd_rn(__dmul_rn((double)perCol, 0.1656), 0.1141));
+    return fmaxf(0.0f, fminf(e, 1.0f));
+}
+struct ModeRow { int qStart, tStart, alnLen; float seqId, qCov, tCov; };
+__device__ __forceinline__ ModeRow mode_row(const PairOut &o, int swMode, unsigned qLen, unsigned tLen) {
+    ModeRow m;
+    if (swMode == 2) {
+        m.qStart = -1; m.tStart = -1;
+        m.alnLen = max(abs(o.qEnd + 1), abs(o.tEnd + 1)) + 1;          // Matcher::computeAlnLength with both starts at -1
+        m.seqId = est_seq_id(o.score, (unsigned)max(o.qEnd, 1), (unsigned)max(o.tEnd, 1));
+        m.qCov = 0.0f; m.tCov = 0.0f;
+    } else {
+        m.qStart = o.qStart; m.tStart = o.tStart;
+        m.alnLen = max(abs(o.qEnd - o.qStart), abs(o.tEnd - o.tStart)) + 1;
+        m.seqId = est_seq_id(o.score, (unsigned)max(o.qEnd - o.qStart, 1), (unsigned)max(o.tEnd - o.tStart, 1));
+        m.qCov = (float)(unsigned)(o.qEnd - o.qStart + 1) / (float)qLen;
+        m.tCov = (float)(unsigned)(o.tEnd - o.tStart + 1) / (float)tLen;
+    }
+    return m;
+}
 
 __device__ __forceinline__ bool can_be_covered(float covThr, int covMode, float qLen, float tLen) {
     switch (covMode) {      // Parameters.h:246-251
@@ -885,6 +912,12 @@ __global__ void criteria_kernel(const PairOut *__restrict__ out, const uint32_t 
     const uint32_t q = pairQ[pair], t = pairT[pair];
     const unsigned qLen = (unsigned)(qoff[q + 1] - qoff[q]), tLen = (unsigned)(toff[t + 1] - toff[t]);
     bool ok = can_be_covered(cr.covThr, cr.covMode, (float)qLen, (float)tLen);
+    if (cr.swMode != 0) {
+        const ModeRow m = mode_row(o, cr.swMode, qLen, tLen);
+        ok = ok && has_coverage(cr.covThr, cr.covMode, m.qCov, m.tCov) && m.seqId >= cr.seqIdThr && m.alnLen >= cr.alnLenThr;
+        keep[k] = ok ? 1 : 0;
+        return;
+    }
     // SmithWaterman::computeCov (StripedSmithWaterman.cpp:1055-1057) on the final coordinates
     const float qCov = (float)(unsigned)(o.qEnd - o.qStart + 1) / (float)qLen;
     const float tCov = (float)(unsigned)(o.tEnd - o.tStart + 1) / (float)tLen;
@@ -897,7 +930,7 @@ __global__ void criteria_kernel(const PairOut *__restrict__ out, const uint32_t 
 __global__ void pack_rows_kernel(const PairOut *__restrict__ out, const uint32_t *__restrict__ acc, uint32_t nAcc,
                                  const uint32_t *__restrict__ pairQ, const uint32_t *__restrict__ pairT, spb_aln *__restrict__ rows,
                                  const uint64_t *__restrict__ toff, const uint32_t *__restrict__ tkeys, RowKey *__restrict__ keys,
-                                 const uint64_t *__restrict__ qoff, int seqIdMode) {
+                                 const uint64_t *__restrict__ qoff, int seqIdMode, int swMode) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nAcc) return;
     const uint32_t pair = acc[k];
@@ -927,6 +960,15 @@ __global__ void pack_rows_kernel(const PairOut *__restrict__ out, const uint32_t
     r.cigar_off = o.cigOff;
     r.cigar_len = o.cigLen;
     r.reserved = 0;
+    if (swMode != 0) {       // no backtrace was computed: estimated identity, span as length, no CIGAR (traceback fields are stale)
+        const ModeRow m = mode_row(o, swMode, (unsigned)(qoff[r.query + 1] - qoff[r.query]), tlen);
+        r.q_start = m.qStart; r.t_start = m.tStart;
+        r.n_ident = 0;
+        r.aln_len = m.alnLen;
+        r.seq_id = m.seqId;
+        r.cigar_off = 0;
+        r.cigar_len = 0;
+    }
     rows[k] = r;
 }
 
@@ -1238,8 +1280,9 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
     SPB_CHECK(c->have_queries && c->have_pairs, "spb_align: no resident queries / pairs");
     SPB_CHECK(p->gap_open >= 0 && p->gap_open <= 255 && p->gap_extend >= 0 && p->gap_extend <= 255, "spb_align: gap costs out of range");
     SPB_CHECK(p->byte_lanes > 0 && p->word_lanes > 0, "spb_align: lanes must be positive");
-    SPB_CHECK(p->cov_mode >= 0 && p->cov_mode <= 5 && p->seq_id_mode >= 0 && p->seq_id_mode <= 2,
-              "spb_align: cov_mode must be 0..5 and seq_id_mode 0..2");
+    SPB_CHECK(p->cov_mode >= 0 && p->cov_mode <= 5 && p->seq_id_mode >= 0 && p->seq_id_mode <= 2 && p->sw_mode >= 0 && p->sw_mode <= 2,
+              "spb_align: cov_mode must be 0..5, seq_id_mode 0..2 and sw_mode 0..2");
+    const int swMode = p->sw_mode;
     cudaStream_t st = c->stream;
     const uint32_t Q = c->Q;
     const uint64_t NP = c->n_pairs;
@@ -1390,7 +1433,7 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
     c->aln_stats.kernel_ms = ms;
     c->aln_stats.n_cells = h_ctr[0];
     const uint32_t nAcc = (uint32_t)(h_ctr[1] & 0xFFFFFFFFull);
-    if (nAcc) {
+    if (nAcc && swMode != 2) {      // (score only: neither the reverse pass nor the traceback)
         // scratch: s_g he offsets u64[nAcc+1] (+ sizes), s_h he scratch, s_i tb offsets, s_j cig offsets, s_k tb scratch
         if (c->s_g.ensure(((size_t)nAcc + 1) * 16)) return 1;
         uint64_t *heSz = c->s_g.as<uint64_t>(), *heOff = heSz + (nAcc + 1);
@@ -1436,16 +1479,18 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
         SPB_CUDA(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, st));
         SPB_CUDA(cudaStreamSynchronize(st));
         SPB_CHECK(h_err == 0, "spb_align: forward and reverse Smith-Waterman scores differ (accepted pair #%d)", h_err - 1);
-        if (c->s_k.ensure(tbTotal + 64) || c->d_cig.ensure(cigTotal + 64)) return 1;
-        // slices are sized by an upper bound of the alignment length: the slack between them is copied out with the result
-        SPB_CUDA(cudaMemsetAsync(c->d_cig.p, 0, cigTotal, st));
-        B.tbOff = tbOff;
-        B.tbScratch = c->s_k.as<unsigned char>();
-        B.cigOff = cigOff;
-        B.cigar = c->d_cig.as<char>();
-        sw_traceback_kernel<<<(nAcc + TB_THREADS - 1) / TB_THREADS, TB_THREADS, 0, st>>>(B);
-        SPB_CUDA(cudaGetLastError()); c->n_launches++;
-        c->n_cigar = cigTotal;
+        if (swMode == 0) {          // (score + coverage stops at the start positions)
+            if (c->s_k.ensure(tbTotal + 64) || c->d_cig.ensure(cigTotal + 64)) return 1;
+            // slices are sized by an upper bound of the alignment length: the slack between them is copied out with the result
+            SPB_CUDA(cudaMemsetAsync(c->d_cig.p, 0, cigTotal, st));
+            B.tbOff = tbOff;
+            B.tbScratch = c->s_k.as<unsigned char>();
+            B.cigOff = cigOff;
+            B.cigar = c->d_cig.as<char>();
+            sw_traceback_kernel<<<(nAcc + TB_THREADS - 1) / TB_THREADS, TB_THREADS, 0, st>>>(B);
+            SPB_CUDA(cudaGetLastError()); c->n_launches++;
+            c->n_cigar = cigTotal;
+        }
     }
     // ---- -c / --cov-mode / --min-seq-id / --min-aln-len: the accepted list shrinks to the pairs that pass (their CIGAR slices
     // stay where they are; the slices of dropped pairs become slack of the CIGAR buffer).  Not on the predictmatch path.
@@ -1455,6 +1500,7 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
         Criteria cr;
         cr.covThr = p->cov_thr; cr.covMode = p->cov_mode; cr.seqIdThr = p->seq_id_thr; cr.alnLenThr = p->aln_len_thr;
         cr.seqIdMode = p->seq_id_mode;
+        cr.swMode = swMode;
         uint8_t *keep = c->s_e.as<uint8_t>();            // (the E-value flags are dead: d_acc was selected from them)
         uint32_t *kept = c->s_q.as<uint32_t>();          // (the sorted pair list of the forward kernel is dead too)
         criteria_kernel<<<(nAcc + 255) / 256, 256, 0, st>>>(c->d_pairout.as<PairOut>(), accRows, nAcc, c->d_pairQ.as<uint32_t>(),
@@ -1491,7 +1537,7 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
             pack_rows_kernel<<<(nRows + 255) / 256, 256, 0, st>>>(c->d_pairout.as<PairOut>(), accRows, nRows,
                                                                  c->d_pairQ.as<uint32_t>(), c->d_pairT.as<uint32_t>(), c->s_g.as<spb_aln>(),
                                                                  c->d_aoff.as<uint64_t>(), c->d_akeys.as<uint32_t>(), c->s_h.as<RowKey>(),
-                                                                 c->d_qoff64.as<uint64_t>(), p->seq_id_mode);
+                                                                 c->d_qoff64.as<uint64_t>(), p->seq_id_mode, swMode);
             SPB_CUDA(cudaGetLastError()); c->n_launches++;
             rank_rows_kernel<<<(nRows + 255) / 256, 256, 0, st>>>(c->s_g.as<spb_aln>(), c->s_h.as<RowKey>(), nRows, rowOff, c->d_rows.as<spb_aln>());
             SPB_CUDA(cudaGetLastError()); c->n_launches++;

@@ -741,6 +741,13 @@ int run_prefilter(int argc, const char **argv) {
 // ---------------------------------------------------------------------------------------------------------
 // align
 // ---------------------------------------------------------------------------------------------------------
+int sw_mode_of(const Params &p) {
+    if (p.addBacktrace || p.alignmentMode == 3) return 0;
+    if (p.alignmentMode == 2) return 1;
+    if (p.alignmentMode == 0 && (float)p.covThr > 0.0f) return ((float)p.seqIdThr == 0.0f) ? 1 : 0;
+    return 2;
+}
+
 void fill_align_params(const Params &p, const Engine &E, uint64_t dbRes, spb_align_params *ap) {
     const int go = atoi(multiparam_aa(p.gapOpen).c_str()), ge = atoi(multiparam_aa(p.gapExtend).c_str());
     memset(ap, 0, sizeof(*ap));
@@ -756,6 +763,9 @@ void fill_align_params(const Params &p, const Engine &E, uint64_t dbRes, spb_ali
     ap->seq_id_thr = (float)p.seqIdThr;
     ap->aln_len_thr = p.alnLenThr;
     ap->seq_id_mode = p.seqIdMode;
+    // Alignment::Alignment + initSWMode (Alignment.cpp:29-37,174-196): -a forces score + coverage + identity with backtrace;
+    // --alignment-mode 0 picks by the thresholds, 1 = score only, 2 = score + coverage, 3 = the full mode without the backtrace column
+    ap->sw_mode = sw_mode_of(p);
     if (!gumbel_for(E.align.name, go, ge, p.gumbel, &ap->gumbel))
         throw Fail("no Gumbel parameters for " + E.align.name + " gap open " + std::to_string(go) + " extend " + std::to_string(ge) +
                    ": pass the twelve ALP values of the reference run with --gumbel lambda,K,a_I,b_I,alpha_I,beta_I,a_J,b_J,alpha_J,beta_J,sigma,tau");
@@ -770,11 +780,11 @@ void check_align_params(const Params &p) {
     if (p.seqIdMode < 0 || p.seqIdMode > 2) throw Fail("Error in argument --seq-id-mode");
     if (p.alnLenThr < 0) throw Fail("Error in argument --min-aln-len");
     if (p.maxRejected != INT_MAX || p.maxAccept != INT_MAX) throw Fail("--max-rejected / --max-accept are not supported");
-    // -a forces SCORE_COV_SEQID (Alignment.cpp:35-37).  --alignment-mode 3 without -a computes the same alignments and writes
-    // the ten columns without the backtrace (Matcher::resultToBuffer, Matcher.cpp:355-367); the score-only / coverage-only modes
-    // (estimated sequence identity, no start positions) are not implemented
-    if (p.addBacktrace != 1 && p.alignmentMode != 3)
-        throw Fail("only the rows of --alignment-mode 3 (score, coverage, sequence identity) or -a 1 (the predictmatch search) are implemented");
+    // -a forces SCORE_COV_SEQID (Alignment.cpp:35-37); without it the rows have ten columns (Matcher::resultToBuffer,
+    // Matcher.cpp:355-367) and --alignment-mode selects how much is computed (fill_align_params)
+    if (p.addBacktrace != 0 && p.addBacktrace != 1) throw Fail("Error in argument -a");
+    if (p.alignmentMode < 0 || p.alignmentMode > 3)
+        throw Fail("--alignment-mode " + std::to_string(p.alignmentMode) + " (ungapped) is not supported on this path");
 }
 
 // rows of one batch as text, one entry per query (Matcher::resultToBuffer, M/alignment/Matcher.cpp:323-370); sink(thread,
@@ -1686,11 +1696,11 @@ int run_showparams(int argc, const char **argv) {
     p.targetSplitOk = (mod == "prefilter");
     if (mod == "align") check_align_params(p); else check_search_params(p);
     printf("sub_mat=%s seed_sub_mat=%s kmer_thr=%d max_seqs=%d min_ungapped=%d mask=%d comp_bias=%d pattern=%s "
-           "evalue=%g gap_open=%s gap_extend=%s threads=%d cov=%g cov_mode=%d min_seq_id=%g min_aln_len=%d seq_id_mode=%d backtrace=%d\n",
+           "evalue=%g gap_open=%s gap_extend=%s threads=%d cov=%g cov_mode=%d min_seq_id=%g min_aln_len=%d seq_id_mode=%d backtrace=%d sw_mode=%d\n",
            multiparam_aa(p.subMat).c_str(), multiparam_aa(p.seedSubMat).c_str(), kmer_threshold(p.sensitivity, p.kmerScore, 6), p.maxSeqs,
            p.minUngapped, p.mask, p.compBias, p.spacedPattern.empty() ? (p.spacedMode ? "11011101" : "111111") : p.spacedPattern.c_str(),
            p.evalue, multiparam_aa(p.gapOpen).c_str(), multiparam_aa(p.gapExtend).c_str(), p.threads, (double)(float)p.covThr, p.covMode,
-           (double)(float)p.seqIdThr, p.alnLenThr, p.seqIdMode, p.addBacktrace);
+           (double)(float)p.seqIdThr, p.alnLenThr, p.seqIdMode, p.addBacktrace, sw_mode_of(p));
     return 0;
 }
 

@@ -156,7 +156,8 @@ def _with(flags, **over):
 
 
 @pytest.mark.parametrize("tag", ["long_c0.5_m0", "long_c0.3_m1", "long_c0.7_m2", "long_c0.5_m4", "long_id0.3_mode1", "long_len40",
-                                 "long_c0.6_m2_id0.5_len25", "long_c0.6_m2_id0.5_len25_noback"])
+                                 "long_c0.6_m2_id0.5_len25", "long_c0.6_m2_id0.5_len25_noback", "long_mode1", "long_mode2",
+                                 "long_mode2_c0.5_m0_id0.3", "long_mode0_c0.6_m2"])
 def test_align_acceptance_criteria_flags(tmp_path, tag):
     """`spb200 align` with -c / --cov-mode / --min-seq-id / --seq-id-mode / --min-aln-len / -a 0 --alignment-mode 3 writes the
     reference binary's alignment DB (tests/golden/criteria)"""
@@ -165,8 +166,8 @@ def test_align_acceptance_criteria_flags(tmp_path, tag):
     w = _long_set_dbs(tmp_path)
     over = {"-e": c["evalue"], "-c": c["cov"], "--cov-mode": c["cov_mode"], "--min-seq-id": c["min_seq_id"],
             "--min-aln-len": c["min_aln_len"], "--seq-id-mode": c["seq_id_mode"]}
-    if not c["backtrace"]:
-        over.update({"-a": 0, "--alignment-mode": 3})
+    if not c["backtrace"]:      # ten columns; --alignment-mode 1 score only, 2 score + coverage, 0 picks by the thresholds, 3 full
+        over.update({"-a": 0, "--alignment-mode": c["alignment_mode"]})
     run("align", w + "/qdb", w + "/tdb", w + "/allpairs", w + "/aln", *_with(ALN_FLAGS, **over))
     got = {k: v for k, v in entries_as_rows(w + "/aln").items() if v}
     assert got == read_dump(os.path.join(GOLDEN, "criteria", tag + ".txt.gz"))

@@ -182,6 +182,13 @@ def test_acceptance_criteria_flags_are_parsed():
     out = run("showparams", "align", "q", "t", "p", "a", *ALN_FLAGS, "-c", "0.8", "--cov-mode", "2", "--min-seq-id", "0.3",
               "--seq-id-mode", "1", "--min-aln-len", "12", "-a", "0", "--alignment-mode", "3").stdout
     assert "cov=0.8 cov_mode=2 min_seq_id=0.3 min_aln_len=12 seq_id_mode=1 backtrace=0" in out
+    # Alignment::initSWMode (Alignment.cpp:174-196): -a forces the full mode (0); without it 1 = score only (2), 2 = score + coverage (1),
+    # 0 picks by the thresholds
+    for extra, want in ((["-a", "1", "--alignment-mode", "1"], 0), (["-a", "0", "--alignment-mode", "3"], 0),
+                        (["-a", "0", "--alignment-mode", "2"], 1), (["-a", "0", "--alignment-mode", "1"], 2),
+                        (["-a", "0", "--alignment-mode", "0"], 2), (["-a", "0", "--alignment-mode", "0", "-c", "0.5"], 1),
+                        (["-a", "0", "--alignment-mode", "0", "-c", "0.5", "--min-seq-id", "0.3"], 0)):
+        assert ("sw_mode=%d" % want) in run("showparams", "align", "q", "t", "p", "a", *ALN_FLAGS, *extra).stdout, extra
     out = run("showparams", "prefilter", "q", "t", "p", *PREF_FLAGS, "-c", "0.5", "--cov-mode", "5", "--exact-kmer-matching", "1").stdout
     assert "cov=0.5 cov_mode=5" in out
 
@@ -209,7 +216,7 @@ def test_errors_like_the_reference():
 
 @pytest.mark.parametrize("module,flags", [
     ("prefilter", ["--mask-lower-case", "2"]), ("prefilter", ["--alph-size", "nucl:5,aa:13"]), ("prefilter", ["--alph-size", "13"]),
-    ("prefilter", ["--taxon-list", "10239"]), ("align", ["--alignment-mode", "1", "-a", "0"]), ("align", ["--mask-lower-case", "2"]),
+    ("prefilter", ["--taxon-list", "10239"]), ("align", ["--alignment-mode", "4", "-a", "0"]), ("align", ["--mask-lower-case", "2"]),
     ("align", ["--max-accept", "5"]), ("align", ["--cov-mode", "6"]), ("prefilter", ["--add-self-matches", "1"])])
 def test_flags_that_would_change_the_result_are_refused(module, flags):
     """A drop-in must not exit 0 with a DB that differs from the reference's: flags of the two modules that this path does not
