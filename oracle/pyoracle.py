@@ -405,11 +405,21 @@ def bitscore(score, gumbel=None):
     return lib().spo_bitscore(C.byref(g), float(score))
 
 
-def align_query(m40, p, q, targets, keys, backtrace=True):
-    """Align q against each (target residues, key); returns rows sorted like Matcher::compareHits."""
+def align_query(m40, p, q, targets, keys, backtrace=True, max_accept=2**31 - 1, max_rejected=2**31 - 1):
+    """Align q against each (target residues, key) in list order; returns rows sorted like Matcher::compareHits.
+    --max-accept / --max-rejected (Alignment.cpp:353-404): the list is walked until max_accept pairs passed or max_rejected
+    pairs IN A ROW failed (E-value, coverage, identity, length, or lengths that cannot reach the coverage)."""
     res = []
+    passed = rejected = 0
     for t, key in zip(targets, keys):
+        if not (passed < max_accept and rejected < max_rejected):
+            break
         a = align_pair(m40, p, q, t)
+        if a.ok == 1:
+            passed += 1
+            rejected = 0
+        else:
+            rejected += 1
         if a.ok == 1:
             res.append((a.eval, -a.bits, len(t), key, format_row(key, a, len(q), len(t), backtrace)))
     res.sort(key=lambda r: r[:4])

@@ -11,6 +11,7 @@
   tests/golden/criteria/t_lower.fasta.gz, pref_small_lower_mask{0,1}  targets of `small` with lower-case stretches and the lists under
                                              --mask-lower-case 1 (IndexBuilder.cpp:151-160)
   tests/golden/criteria/pref_family_split3_max20, pref_small_split2_max100  lists of the reference's own target split (--split N --split-mode 0)
+  tests/golden/criteria/family_acc* / family_rej*, limits.json  --max-accept / --max-rejected on the `family` set (Alignment.cpp:353-404)
   tests/golden/criteria/cases.json           the flag set of every alignment fixture
 Usage: python tools/gen_golden_criteria.py
 """
@@ -180,6 +181,35 @@ def main():
                                                                                                "--split %d --split-mode 0" % split)
         run("%s prefilter %s/qdb %s/tdb %s/%s %s" % (B, w, w, w, tag, flags))
         dump_db(os.path.join(w, tag), os.path.join(out, tag + ".txt.gz"))
+    # --max-accept / --max-rejected (Alignment.cpp:353-404): the prefilter list is walked in order until that many pairs passed /
+    # that many pairs in a row failed.  `family` set, its --max-seqs 300 prefilter lists (tests/golden/family/pref_max300).
+    w = os.path.join(work, "family")
+    ent = {}
+    with gzip.open(os.path.join(GOLD, "family", "pref_max300.txt.gz"), "rt") as f:
+        for line in f:
+            k, row = line.rstrip("\n").split("\t", 1)
+            ent.setdefault(int(k), []).append(row)
+    nQ = sum(1 for _ in open(os.path.join(w, "qdb.index")))
+    with open(os.path.join(w, "pref300"), "wb") as f, open(os.path.join(w, "pref300.index"), "w") as fi:
+        pos = 0
+        for q in range(nQ):
+            body = "".join(r + "\n" for r in ent.get(q, [])).encode()
+            f.write(body + b"\0")
+            fi.write("%d\t%d\t%d\n" % (q, pos, len(body) + 1))
+            pos += len(body) + 1
+    with open(os.path.join(w, "pref300.dbtype"), "wb") as f:
+        f.write((7).to_bytes(4, "little"))
+    limits = {}
+    for tag, acc, rej, sid, ev in (("family_acc2", 2, 2147483647, 0.0, "200"), ("family_rej1_id0.93", 2147483647, 1, 0.93, "200"),
+                                   ("family_rej3_id0.95", 2147483647, 3, 0.95, "200"), ("family_acc3_rej2_id0.9", 3, 2, 0.9, "200"),
+                                   ("family_rej2_e1e-20", 2147483647, 2, 0.0, "1.000E-20")):
+        f = aln_flags(ev, 0.0, 0, sid, 0, 1, 0).replace("--max-rejected 2147483647 --max-accept 2147483647",
+                                                       "--max-rejected %d --max-accept %d" % (rej, acc))
+        run("%s align %s/qdb %s/tdb %s/pref300 %s/aln_%s %s" % (B, w, w, w, w, tag, f))
+        dump_db(os.path.join(w, "aln_" + tag), os.path.join(out, tag + ".txt.gz"))
+        limits[tag] = dict(max_accept=acc, max_rejected=rej, min_seq_id=sid, evalue=float(ev))
+    with open(os.path.join(out, "limits.json"), "w") as f:
+        json.dump(limits, f, indent=1)
     with open(os.path.join(out, "cases.json"), "w") as f:
         json.dump({t: dict(set=c[0], evalue=float(c[1]), cov=c[2], cov_mode=c[3], min_seq_id=c[4], min_aln_len=c[5], backtrace=c[6],
                         seq_id_mode=c[7], alignment_mode=(c[8] if len(c) > 8 else 3))
