@@ -145,6 +145,8 @@ typedef struct spb_align_params {
     int32_t sw_mode;                /* 0: score, coverage, sequence identity, backtrace (-a 1 or --alignment-mode 3: what predictmatch runs);
                                        1: score + coverage (--alignment-mode 2 without -a: no backtrace, identity estimated from the score);
                                        2: score only (--alignment-mode 1: no start positions either) -- Alignment::initSWMode, Alignment.cpp:174-196 */
+    int32_t max_accept;             /* --max-accept / --max-rejected (Alignment.cpp:353-404): the pair list of a query is walked in the caller's */
+    int32_t max_rejected;           /* order until max_accept pairs passed or max_rejected pairs in a row failed; <= 0 or INT32_MAX: no limit */
 } spb_align_params;
 
 typedef struct spb_aln {     /* Matcher::result_t, M/alignment/Matcher.h:24-119 */

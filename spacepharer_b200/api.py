@@ -335,14 +335,15 @@ class Searcher:
         capi.check(self.lib.spb_pairs_set(self.h, _u64(pair_off), pair_targets.ctypes.data_as(C.POINTER(C.c_uint32))))
 
     def _align_params(self, db_res_count, evalue, gap_open, gap_extend, comp_bias, gumbel, byte_lanes, word_lanes,
-                      cov=0.0, cov_mode=0, min_seq_id=0.0, min_aln_len=0, seq_id_mode=0, sw_mode=0):
+                      cov=0.0, cov_mode=0, min_seq_id=0.0, min_aln_len=0, seq_id_mode=0, sw_mode=0, max_accept=0, max_rejected=0):
         """cov / cov_mode / min_seq_id / min_aln_len / seq_id_mode: `-c`, `--cov-mode`, `--min-seq-id`, `--min-aln-len`,
         `--seq-id-mode` of the align module (Alignment.cpp:378,396,555-574); all 0 in the predictmatch search.
         sw_mode: 0 full alignment with backtrace (`-a 1` / `--alignment-mode 3`), 1 score + coverage (`--alignment-mode 2`), 2 score
-        only (`--alignment-mode 1`) -- see sw_mode_for"""
+        only (`--alignment-mode 1`) -- see sw_mode_for.  max_accept / max_rejected: `--max-accept` / `--max-rejected`, the ordered walk
+        of each query's pair list (Alignment.cpp:353-404); 0 = no limit"""
         g = capi.Gumbel(*(gumbel or gumbel_for(self.sub_mat_name, gap_open, gap_extend)))
         return capi.AlignParams(gap_open, gap_extend, evalue, db_res_count, comp_bias, byte_lanes, word_lanes, g,
-                                cov, cov_mode, min_seq_id, min_aln_len, seq_id_mode, sw_mode)
+                                cov, cov_mode, min_seq_id, min_aln_len, seq_id_mode, sw_mode, max_accept, max_rejected)
 
     def align_resident(self, db_res_count, evalue=200.0, gap_open=16, gap_extend=2, comp_bias=1, gumbel=None,
                        byte_lanes=32, word_lanes=16, **criteria):
@@ -406,7 +407,7 @@ class Searcher:
         kw: kmer_thr, max_seqs, min_ungapped_score, bin_size, comp_bias, evalue, gap_open, gap_extend, gumbel"""
         pk = {k: kw[k] for k in ("kmer_thr", "max_seqs", "min_ungapped_score", "bin_size", "comp_bias", "id_base", "exact_kmer") if k in kw}
         ak = {k: kw[k] for k in ("evalue", "gap_open", "gap_extend", "comp_bias", "gumbel", "byte_lanes", "word_lanes", "cov", "cov_mode",
-                                 "min_seq_id", "min_aln_len", "seq_id_mode", "sw_mode") if k in kw}
+                                 "min_seq_id", "min_aln_len", "seq_id_mode", "sw_mode", "max_accept", "max_rejected") if k in kw}
         self.set_queries(qres, qoff)
         pst = self.prefilter_resident(**pk)
         pref = self.prefilter_fetch() if fetch_prefilter else None

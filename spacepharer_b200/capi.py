@@ -41,7 +41,7 @@ class AlignParams(C.Structure):
                 ("db_res_count", C.c_uint64), ("comp_bias", C.c_int32), ("byte_lanes", C.c_int32),
                 ("word_lanes", C.c_int32), ("gumbel", Gumbel),
                 ("cov_thr", C.c_float), ("cov_mode", C.c_int32), ("seq_id_thr", C.c_float), ("aln_len_thr", C.c_int32),
-                ("seq_id_mode", C.c_int32), ("sw_mode", C.c_int32)]
+                ("seq_id_mode", C.c_int32), ("sw_mode", C.c_int32), ("max_accept", C.c_int32), ("max_rejected", C.c_int32)]
 
 
 class Aln(C.Structure):

@@ -927,6 +927,38 @@ __global__ void criteria_kernel(const PairOut *__restrict__ out, const uint32_t 
     keep[k] = ok ? 1 : 0;
 }
 
+// --max-accept / --max-rejected (Alignment.cpp:353-404): the reference walks the prefilter list of a query in order and stops once
+// max_accept pairs passed, or max_rejected pairs IN A ROW failed (lengths that cannot reach the coverage, E-value, checkCriteria).
+// Pairs behind the stop are never aligned there; here every pair has its verdict already (final[pair] = 1: passes), so one thread
+// per query replays the walk over the verdicts and clears the pairs behind the stop.  order[] maps list position -> pair (NULL: the
+// work order is the list order).
+__global__ void set_flags_kernel(const uint32_t *__restrict__ acc, uint32_t n, uint8_t *__restrict__ final_) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) final_[acc[k]] = 1;
+}
+__global__ void list_order_kernel(const uint64_t *__restrict__ pairOff, const uint32_t *__restrict__ pairQ, const uint32_t *__restrict__ rank,
+                                  uint32_t NP, uint32_t *__restrict__ order) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < NP) order[pairOff[pairQ[k]] + rank[k]] = k;
+}
+__global__ void accept_limit_kernel(const uint64_t *__restrict__ pairOff, uint32_t Q, const uint32_t *__restrict__ order,
+                                    uint32_t maxAccept, uint32_t maxRejected, uint8_t *__restrict__ final_) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    const uint64_t a = pairOff[q], b = pairOff[q + 1];
+    uint32_t passed = 0, rejected = 0;
+    uint64_t r = a;
+    for (; r < b && passed < maxAccept && rejected < maxRejected; r++) {
+        const uint32_t pair = order ? order[r] : (uint32_t)r;
+        if (final_[pair]) { passed++; rejected = 0; } else rejected++;
+    }
+    for (; r < b; r++) final_[order ? order[r] : (uint32_t)r] = 0;
+}
+__global__ void gather_flags_kernel(const uint32_t *__restrict__ acc, uint32_t n, const uint8_t *__restrict__ final_, uint8_t *__restrict__ keep) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) keep[k] = final_[acc[k]];
+}
+
 __global__ void pack_rows_kernel(const PairOut *__restrict__ out, const uint32_t *__restrict__ acc, uint32_t nAcc,
                                  const uint32_t *__restrict__ pairQ, const uint32_t *__restrict__ pairT, spb_aln *__restrict__ rows,
                                  const uint64_t *__restrict__ toff, const uint32_t *__restrict__ tkeys, RowKey *__restrict__ keys,
@@ -1514,6 +1546,40 @@ static int align_pipeline(spb_ctx *c, const spb_align_params *p) {
         SPB_CUDA(cudaStreamSynchronize(st));
         accRows = kept;
     }
+    // ---- --max-accept / --max-rejected: replay the reference's walk over each query's list on the verdicts (see accept_limit_kernel)
+    const bool limAcc = p->max_accept > 0 && p->max_accept != INT32_MAX, limRej = p->max_rejected > 0 && p->max_rejected != INT32_MAX;
+    if (limAcc || limRej) {
+        SPB_CHECK(c->pair_rank_mode != 2, "spb_align: --max-accept / --max-rejected need a pair list with an order (not the exhaustive search)");
+        uint8_t *final_ = c->s_e.as<uint8_t>();          // u8[NP] (E-value flags / criteria flags: both consumed by now)
+        uint8_t *keep2 = c->s_n.as<uint8_t>();           // (sort keys of the forward kernel: dead)
+        uint32_t *kept2 = c->s_o.as<uint32_t>();
+        uint32_t *order = nullptr;
+        SPB_CUDA(cudaMemsetAsync(final_, 0, NP, st));
+        if (nRows) {
+            set_flags_kernel<<<(nRows + 255) / 256, 256, 0, st>>>(accRows, nRows, final_);
+            SPB_CUDA(cudaGetLastError()); c->n_launches++;
+        }
+        if (c->pair_rank_mode == 1) {
+            order = c->s_p.as<uint32_t>();               // (unsorted sort values: dead)
+            list_order_kernel<<<(unsigned)((NP + 255) / 256), 256, 0, st>>>(c->d_pairoff.as<uint64_t>(), c->d_pairQ.as<uint32_t>(),
+                                                                          c->d_pairRank.as<uint32_t>(), (uint32_t)NP, order);
+            SPB_CUDA(cudaGetLastError()); c->n_launches++;
+        }
+        accept_limit_kernel<<<(Q + 127) / 128, 128, 0, st>>>(c->d_pairoff.as<uint64_t>(), Q, order,
+                                                             limAcc ? (uint32_t)p->max_accept : 0xFFFFFFFFu,
+                                                             limRej ? (uint32_t)p->max_rejected : 0xFFFFFFFFu, final_);
+        SPB_CUDA(cudaGetLastError()); c->n_launches++;
+        if (nRows) {
+            gather_flags_kernel<<<(nRows + 255) / 256, 256, 0, st>>>(accRows, nRows, final_, keep2);
+            SPB_CUDA(cudaGetLastError()); c->n_launches++;
+            SPB_CUDA(cub::DeviceSelect::Flagged(nullptr, tmpBytes, accRows, keep2, kept2, d_nAcc, (int)nRows, st));
+            if (c->s_cub.ensure(tmpBytes)) return 1;
+            SPB_CUDA(cub::DeviceSelect::Flagged(c->s_cub.p, tmpBytes, accRows, keep2, kept2, d_nAcc, (int)nRows, st));
+            SPB_CUDA(cudaMemcpyAsync(&nRows, d_nAcc, 4, cudaMemcpyDeviceToHost, st));
+            SPB_CUDA(cudaStreamSynchronize(st));
+            accRows = kept2;
+        }
+    }
     // ---- result rows: per query in the order of Matcher::compareHits (part of the stage: `align` writes sorted entries)
     {
         // scratch: s_g packed rows, s_i row counts u32[Q+1] + u64[Q+1] widened
@@ -1568,26 +1634,31 @@ extern "C" int spb_pairs_set(spb_ctx *c, const uint64_t *pair_offsets, const uin
     SPB_CHECK(NP < 0x7FFFFFF0ull, "spb_pairs_set: more than 2^31 pairs in one call; split the batch");
     SPB_CHECK(NP == 0 || pair_targets, "spb_pairs_set: NULL targets");
     // work order: per query, targets by length descending so that the lanes of a warp finish together
-    std::vector<uint32_t> pairT(NP);
+    // (the position in the caller's list travels with the pair: --max-accept / --max-rejected walk the list in its order)
+    std::vector<uint32_t> pairT(NP), rank(NP);
     uint64_t maxPer = 0;
     for (uint32_t qi = 0; qi < Q; qi++) {
         const uint64_t a = pair_offsets[qi], b = pair_offsets[qi + 1];
         SPB_CHECK(b >= a && b <= NP, "spb_pairs_set: offsets not monotone at %u", qi);
         for (uint64_t k = a; k < b; k++) {
             SPB_CHECK(pair_targets[k] < c->aT, "spb_align: target id %u of query %u out of range (%u targets)", pair_targets[k], qi, c->aT);
-            pairT[k] = pair_targets[k];
+            rank[k] = (uint32_t)(k - a);
         }
         maxPer = std::max<uint64_t>(maxPer, b - a);
         if (b - a > 1)
-            std::stable_sort(pairT.begin() + a, pairT.begin() + b, [&](uint32_t x, uint32_t y) {
+            std::stable_sort(rank.begin() + a, rank.begin() + b, [&](uint32_t i, uint32_t j) {
+                const uint32_t x = pair_targets[a + i], y = pair_targets[a + j];
                 return (c->h_aoff[x + 1] - c->h_aoff[x]) > (c->h_aoff[y + 1] - c->h_aoff[y]);
             });
+        for (uint64_t k = a; k < b; k++) pairT[k] = pair_targets[a + rank[k]];
     }
-    if (c->d_pairoff.ensure(((size_t)Q + 1) * 8) || c->d_pairT.ensure(NP * 4 + 16)) return 1;
+    if (c->d_pairoff.ensure(((size_t)Q + 1) * 8) || c->d_pairT.ensure(NP * 4 + 16) || c->d_pairRank.ensure(NP * 4 + 16)) return 1;
     SPB_CUDA(cudaMemcpyAsync(c->d_pairoff.p, pair_offsets, ((size_t)Q + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     if (NP) SPB_CUDA(cudaMemcpyAsync(c->d_pairT.p, pairT.data(), NP * 4, cudaMemcpyHostToDevice, c->stream));
+    if (NP) SPB_CUDA(cudaMemcpyAsync(c->d_pairRank.p, rank.data(), NP * 4, cudaMemcpyHostToDevice, c->stream));
     SPB_CUDA(cudaStreamSynchronize(c->stream));
     c->n_pairs = NP;
+    c->pair_rank_mode = 1;
     c->pairs_max_per_query = maxPer;
     c->have_pairs = true;
     c->have_aln = false;
@@ -1609,6 +1680,7 @@ extern "C" int spb_pairs_from_prefilter(spb_ctx *c) {
         SPB_CUDA(cudaGetLastError()); c->n_launches++;
     }
     c->n_pairs = NP;
+    c->pair_rank_mode = 0;
     c->pairs_max_per_query = c->pref_max_seqs ? c->pref_max_seqs : NP;    // a hit list holds at most max-seqs targets
     c->have_pairs = true;
     c->have_aln = false;
@@ -1939,6 +2011,7 @@ extern "C" int spb_pairs_exhaustive(spb_ctx *c, const spb_align_params *p, spb_e
     es.n_unfiltered = (uint64_t)nSlow * T;
     es.n_pairs = NP;
     c->n_pairs = NP;
+    c->pair_rank_mode = 2;
     c->pairs_max_per_query = NP;      // unknown per query: any
     c->have_pairs = true;
     if (stats) *stats = es;

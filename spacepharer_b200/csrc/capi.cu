@@ -130,7 +130,7 @@ void spb_ctx_destroy(spb_ctx *c) {
     cudaStreamSynchronize(c->stream);
     spb::DevBuf *bufs[] = {&c->d_mat, &c->d_tres, &c->d_toff, &c->d_koff, &c->d_post, &c->d_direct, &c->d_kbits, &c->d_row3, &c->d_cnt3,
                            &c->d_ares, &c->d_aoff, &c->d_akeys, &c->d_q, &c->d_qoff, &c->d_qoff64, &c->d_qorder, &c->d_hits, &c->d_hits_alt, &c->d_hitoff, &c->d_hit_tkeys, &c->s_tk,
-                           &c->d_pairoff, &c->d_pairT, &c->d_pairQ, &c->d_pairout, &c->d_acc, &c->d_cig, &c->d_rows, &c->d_rowoff, &c->d_st_rows, &c->d_st_cig, &c->d_st_off, &c->d_tnt, &c->d_tntoff, &c->d_tntsc, &c->d_qnt, &c->d_qntoff, &c->d_qntsc, &c->d_nrows,
+                           &c->d_pairoff, &c->d_pairT, &c->d_pairRank, &c->d_pairQ, &c->d_pairout, &c->d_acc, &c->d_cig, &c->d_rows, &c->d_rowoff, &c->d_st_rows, &c->d_st_cig, &c->d_st_off, &c->d_tnt, &c->d_tntoff, &c->d_tntsc, &c->d_qnt, &c->d_qntoff, &c->d_qntsc, &c->d_nrows,
                            &c->s_a, &c->s_b, &c->s_c, &c->s_d, &c->s_e, &c->s_f, &c->s_g, &c->s_h, &c->s_i, &c->s_j,
                            &c->s_k, &c->s_l, &c->s_m, &c->s_n, &c->s_o, &c->s_p, &c->s_q, &c->s_cub,
                            &c->p_recs, &c->p_ctab, &c->p_ccnt, &c->p_harena, &c->p_meta, &c->p_heavy, &c->p_retry, &c->p_team2};

@@ -168,6 +168,8 @@ struct spb_ctx {
     uint32_t pref_max_seqs = 0;         // max-seqs of the resident prefilter result
     spb::DevBuf d_pairoff;        // u64[Q+1]
     spb::DevBuf d_pairT;          // u32[n_pairs] (work order)
+    spb::DevBuf d_pairRank;       // u32[n_pairs]: position of the pair in the caller's list of its query (pair_rank_mode == 1)
+    int pair_rank_mode = 0;       // 0: work order = list order (pairs from the resident prefilter), 1: d_pairRank, 2: unknown (exhaustive)
     spb::DevBuf d_pairQ;          // u32[n_pairs]
     spb::DevBuf d_pairout;        // PairOut[n_pairs]
     spb::DevBuf d_acc;            // u32[n_acc] accepted pair indices

@@ -766,6 +766,8 @@ void fill_align_params(const Params &p, const Engine &E, uint64_t dbRes, spb_ali
     // Alignment::Alignment + initSWMode (Alignment.cpp:29-37,174-196): -a forces score + coverage + identity with backtrace;
     // --alignment-mode 0 picks by the thresholds, 1 = score only, 2 = score + coverage, 3 = the full mode without the backtrace column
     ap->sw_mode = sw_mode_of(p);
+    ap->max_accept = p.maxAccept;        // INT_MAX = no limit
+    ap->max_rejected = p.maxRejected;
     if (!gumbel_for(E.align.name, go, ge, p.gumbel, &ap->gumbel))
         throw Fail("no Gumbel parameters for " + E.align.name + " gap open " + std::to_string(go) + " extend " + std::to_string(ge) +
                    ": pass the twelve ALP values of the reference run with --gumbel lambda,K,a_I,b_I,alpha_I,beta_I,a_J,b_J,alpha_J,beta_J,sigma,tau");
@@ -779,7 +781,9 @@ void check_align_params(const Params &p) {
     if (p.covMode < 0 || p.covMode > 5) throw Fail("Error in argument --cov-mode");
     if (p.seqIdMode < 0 || p.seqIdMode > 2) throw Fail("Error in argument --seq-id-mode");
     if (p.alnLenThr < 0) throw Fail("Error in argument --min-aln-len");
-    if (p.maxRejected != INT_MAX || p.maxAccept != INT_MAX) throw Fail("--max-rejected / --max-accept are not supported");
+    if (p.maxRejected < 1 || p.maxAccept < 1) throw Fail("Error in argument --max-rejected / --max-accept (must be >= 1)");
+    if (p.exhaustive && (p.maxRejected != INT_MAX || p.maxAccept != INT_MAX))
+        throw Fail("--max-rejected / --max-accept walk a prefilter list in its order: not supported with --exhaustive-search 1");
     // -a forces SCORE_COV_SEQID (Alignment.cpp:35-37); without it the rows have ten columns (Matcher::resultToBuffer,
     // Matcher.cpp:355-367) and --alignment-mode selects how much is computed (fill_align_params)
     if (p.addBacktrace != 0 && p.addBacktrace != 1) throw Fail("Error in argument -a");

@@ -264,3 +264,28 @@ def test_reference_target_split_flag(tmp_path, name, split, maxseqs):
         run("prefilter", w + "/qdb", w + "/tdb", w + "/pref1", *_with(PREF_FLAGS, **{"--split": split, "--split-mode": 1, "--max-seqs": 10}))
         got = {k: v for k, v in entries_as_rows(w + "/pref1").items() if v}
         assert got == read_dump(os.path.join(GOLDEN, "family", "pref_max10.txt.gz"))
+
+
+@pytest.mark.parametrize("tag", ["family_acc2", "family_rej3_id0.95", "family_acc3_rej2_id0.9"])
+def test_max_accept_max_rejected_flags(tmp_path, tag):
+    """`spb200 align --max-accept / --max-rejected` on the family set writes the reference binary's alignment DB; the fused search
+    (lists straight from the resident prefilter) too"""
+    import json
+    c = json.load(open(os.path.join(GOLDEN, "criteria", "limits.json")))[tag]
+    w = _long_set_dbs(tmp_path, "family")
+    pref = read_dump(os.path.join(GOLDEN, "family", "pref_max300.txt.gz"))
+    nq = len(dbio.read_entries(w + "/qdb"))
+    dbio.write_db(w + "/pref300", ((q, "".join(r + "\n" for r in pref.get(q, [])).encode()) for q in range(nq)), dbio.DBTYPE_PREFILTER_RES)
+    over = {"-e": c["evalue"], "--min-seq-id": c["min_seq_id"], "--max-accept": c["max_accept"], "--max-rejected": c["max_rejected"]}
+    aflags = _with(ALN_FLAGS, **over)
+    run("align", w + "/qdb", w + "/tdb", w + "/pref300", w + "/aln", *aflags)
+    ref = read_dump(os.path.join(GOLDEN, "criteria", tag + ".txt.gz"))
+    assert {k: v for k, v in entries_as_rows(w + "/aln").items() if v} == ref
+    seen, merged = set(), []
+    for lst in (PREF_FLAGS, aflags):
+        for i in range(0, len(lst), 2):
+            if lst[i] not in seen:
+                seen.add(lst[i])
+                merged += [lst[i], lst[i + 1]]
+    run("search", w + "/qdb", w + "/tdb", w + "/fused", *merged)
+    assert {k: v for k, v in entries_as_rows(w + "/fused").items() if v} == ref

@@ -345,6 +345,31 @@ def test_align_acceptance_criteria_golden(searcher, tag):
     assert st["n_rows"] == sum(len(v) for v in ref.values()) == int(off[-1])
 
 
+@pytest.mark.parametrize("tag", sorted(Cm.limit_cases()))
+def test_align_max_accept_max_rejected_golden(searcher, tag):
+    """--max-accept / --max-rejected (Alignment.cpp:353-404) against the reference binary: the verdicts of all pairs are replayed in
+    the order of the caller's list (the work order of the kernels is by target length)"""
+    c = Cm.limit_cases()[tag]
+    T, Q = Cm.load_fasta_set("family")
+    pref = Cm.dump("family", "pref_max300.txt.gz")
+    pairs = [[int(r.split("\t")[0]) for r in pref.get(i, [])] for i in range(len(Q))]
+    rows, _, _ = _gpu_align_rows(searcher, T, Q, pairs, Cm.db_res_count(T), evalue=c["evalue"], min_seq_id=c["min_seq_id"],
+                                 max_accept=c["max_accept"], max_rejected=c["max_rejected"])
+    ref = Cm.dump("criteria", tag + ".txt.gz")
+    bad = [(i, rows[i][:2], ref.get(i, [])[:2]) for i in range(len(Q)) if rows[i] != ref.get(i, [])]
+    assert not bad, bad[:4]
+    # the same through the fused search: the resident hit lists are walked in their own order
+    if tag == "family_acc3_rej2_id0.9":
+        from spacepharer_b200 import api
+        tres, toff = _product_mask(searcher, T)
+        searcher.build_index(tres, toff)
+        qres, qoff = O.concat(Q)
+        off, r2, cig, _, _ = searcher.search(qres, qoff, Cm.db_res_count(T), evalue=c["evalue"], min_seq_id=c["min_seq_id"],
+                                             max_accept=c["max_accept"], max_rejected=c["max_rejected"])
+        got = [api.format_align_rows(r2[int(off[i]):int(off[i + 1])], cig, [len(q) for q in Q], [len(t) for t in T]) for i in range(len(Q))]
+        assert all(got[i] == ref.get(i, []) for i in range(len(Q)))
+
+
 def test_align_long_striped_golden(searcher):
     """queries of 17..150 aa: stripe-dependent E update, byte->word overflow, gapped tracebacks"""
     T, Q = Cm.load_fasta_set("long")
