@@ -298,3 +298,37 @@ def test_createindex_masks_lower_case_letters(tmp_path, mask):
     run("createindex", db, str(tmp_path / "tmp"), "--threads", "2", "--mask", str(mask))
     raw2 = open(db + ".spbidx", "rb").read()
     assert struct.unpack_from("<4I", raw2, 8)[2] == 0 and struct.unpack_from("<4Q", raw2, 24)[3] != checksum
+
+
+def test_tantan_four_sequences_per_vector_equals_the_scalar_path():
+    """spb_tantan_mask on AVX2 hosts runs four targets in the lanes of a vector (same operation order per lane, no FMA): the masks
+    are bit-identical to the one-sequence path -- ragged lengths (0 .. 400, incl. groups where one lane ends far earlier), repeat-rich
+    sequences with thousands of masked residues, X residues, and a tail that does not fill a group"""
+    from spacepharer_b200 import api, submat, matrices
+    seed = submat.SubMat(matrices.matrix_text("VTML80.out"), 8.0, -0.2)
+    rng = np.random.default_rng(5)
+    seqs = []
+    for i in range(4003):
+        L = int(rng.integers(0, 400)) if i % 7 else int(rng.integers(0, 60))
+        if i % 3 == 0:
+            s = np.resize(rng.integers(0, 20, size=int(rng.integers(1, 8))), L).astype(np.uint8)
+            if L:
+                s[rng.integers(0, L, size=L // 10)] = rng.integers(0, 21, size=L // 10)
+        else:
+            s = rng.integers(0, 21, size=L).astype(np.uint8)
+        seqs.append(s)
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    np.cumsum([len(s) for s in seqs], out=off[1:])
+    res = np.concatenate(seqs)
+    got, n = api.tantan_mask(seed, res, off, threads=3)
+    os.environ["SPB_TANTAN_SCALAR"] = "1"
+    try:
+        want, n2 = api.tantan_mask(seed, res, off, threads=3)
+    finally:
+        del os.environ["SPB_TANTAN_SCALAR"]
+    assert n == n2 > 10000 and (got == want).all()
+    # ... and to the oracle's restatement on a sample
+    m80, _, _ = Cm.mats()
+    for i in range(0, 4003, 97):
+        a, b = int(off[i]), int(off[i + 1])
+        assert (O.tantan_mask(m80, res[a:b])[0] == got[a:b]).all()
