@@ -55,7 +55,7 @@ static bool file_exists(const std::string &p) {
     return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode);
 }
 
-static void append_file(const std::string &p, std::vector<char> &out) {
+static void append_file(const std::string &p, RawBuf &out) {
     FILE *f = fopen(p.c_str(), "rb");
     if (!f) throw std::runtime_error("Could not open data file " + p + "!");
     long n = -1;
@@ -102,7 +102,7 @@ void DBReader::open(const std::string &name) {
     // index: the whole text is read once and parsed by all host threads (slices cut at line ends); a 1 M-spacer query DB has
     // 3.8 M lines, and stdio + strtoull per line used to cost more than the GPU search itself
     const std::string idx = name + ".index";
-    std::vector<char> text;
+    RawBuf text;
     {
         FILE *f = fopen(idx.c_str(), "r");
         if (!f) throw std::runtime_error("Could not open index file " + idx + "!");
@@ -115,16 +115,35 @@ void DBReader::open(const std::string &name) {
     nth = std::max(1, omp_get_max_threads());
 #endif
     if (tn < (1u << 20)) nth = 1;
-    std::vector<std::vector<DBEntry>> part((size_t)nth);
+    // two passes over slices cut at line ends: count the lines, then parse straight into the final table (sized once, not
+    // zeroed: every thread touches its own stretch first -- the page faults of a 3.8 M-entry table were most of the parse time)
+    std::vector<size_t> cut((size_t)nth + 1, 0), lines((size_t)nth + 1, 0);
+    for (int t = 0; t <= nth; t++) {
+        size_t a = tn * (size_t)t / (size_t)nth;
+        if (t > 0 && t < nth) { while (a < tn && text[a - 1] != '\n') a++; }
+        cut[(size_t)t] = (t == nth) ? tn : a;
+    }
+#pragma omp parallel for num_threads(nth) schedule(static, 1)
+    for (int t = 0; t < nth; t++) {
+        size_t n = 0;
+        const char *p = text.data() + cut[(size_t)t], *const end = text.data() + cut[(size_t)t + 1];
+        while (p < end) {
+            const char *le = (const char *)memchr(p, '\n', (size_t)(end - p));
+            n++;
+            if (!le) break;
+            p = le + 1;
+        }
+        lines[(size_t)t + 1] = n;
+    }
+    for (int t = 0; t < nth; t++) lines[(size_t)t + 1] += lines[(size_t)t];
+    entries_.resize(lines[(size_t)nth]);
+    std::vector<size_t> used((size_t)nth, 0);
     std::vector<int> bad((size_t)nth, 0);
 #pragma omp parallel for num_threads(nth) schedule(static, 1)
     for (int t = 0; t < nth; t++) {
-        size_t a = tn * (size_t)t / (size_t)nth, b = tn * (size_t)(t + 1) / (size_t)nth;
-        if (t > 0) { while (a < tn && text[a - 1] != '\n') a++; }
-        if (t + 1 < nth) { while (b < tn && text[b - 1] != '\n') b++; }
-        std::vector<DBEntry> &out = part[(size_t)t];
-        out.reserve((b - a) / 12 + 16);
-        const char *p = text.data() + a, *const end = text.data() + b;
+        DBEntry *out = entries_.data() + lines[(size_t)t];
+        size_t n = 0;
+        const char *p = text.data() + cut[(size_t)t], *const end = text.data() + cut[(size_t)t + 1];
         while (p < end) {
             const char *le = (const char *)memchr(p, '\n', (size_t)(end - p));
             if (!le) le = end;
@@ -140,33 +159,45 @@ void DBReader::open(const std::string &name) {
             }
             if (nf == 3) {
                 if (isCompressed ? v[1] + 5 > dataSize_ : v[1] + v[2] > dataSize_) bad[(size_t)t] = 2;
-                out.push_back(DBEntry{(uint32_t)v[0], (uint64_t)v[1], (uint64_t)v[2]});
+                out[n++] = DBEntry((uint32_t)v[0], (uint64_t)v[1], (uint64_t)v[2]);
             } else if (nf != 0) {
                 bad[(size_t)t] = 1;
             }
             p = le + 1;
         }
+        used[(size_t)t] = n;
     }
     for (int t = 0; t < nth; t++) {
         if (bad[(size_t)t] == 1) throw std::runtime_error("Malformed index line in " + idx);
         if (bad[(size_t)t] == 2) throw std::runtime_error("Index entry beyond the end of the data file in " + idx);
     }
-    size_t total = 0;
-    for (const auto &v : part) total += v.size();
-    entries_.reserve(total);
-    for (const auto &v : part) entries_.insert(entries_.end(), v.begin(), v.end());
+    {   // blank lines leave holes behind a slice: close them (none in a DB any writer produced)
+        size_t w = 0;
+        for (int t = 0; t < nth; t++) {
+            const size_t from = lines[(size_t)t], n = used[(size_t)t];
+            if (w != from && n) memmove((void *)(entries_.data() + w), (const void *)(entries_.data() + from), n * sizeof(DBEntry));
+            w += n;
+        }
+        entries_.resize(w);
+    }
     // DBs written by the reference's (and our) writers are already in key order with ascending offsets: both sorts are skipped then
-    bool keySorted = true, offSorted = true;
-    for (size_t i = 1; i < entries_.size() && keySorted; i++) keySorted = entries_[i - 1].key <= entries_[i].key;
-    if (!keySorted)
+    const long ne = (long)entries_.size();
+    int keyBad = 0, offBad = 0;
+#pragma omp parallel for num_threads(nth) schedule(static) reduction(| : keyBad)
+    for (long i = 1; i < ne; i++) keyBad |= entries_[(size_t)i - 1].key > entries_[(size_t)i].key ? 1 : 0;
+    if (keyBad)
         std::stable_sort(entries_.begin(), entries_.end(), [](const DBEntry &a, const DBEntry &b) { return a.key < b.key; });
     linear_.resize(entries_.size());
-    for (size_t i = 0; i < entries_.size(); i++) linear_[i] = (uint32_t)i;
-    for (size_t i = 1; i < entries_.size() && offSorted; i++) offSorted = entries_[i - 1].offset < entries_[i].offset;
-    if (!offSorted)
+#pragma omp parallel for num_threads(nth) schedule(static) reduction(| : offBad)
+    for (long i = 0; i < ne; i++) {
+        linear_[(size_t)i] = (uint32_t)i;
+        if (i > 0) offBad |= entries_[(size_t)i - 1].offset >= entries_[(size_t)i].offset ? 1 : 0;
+    }
+    if (offBad)
         std::stable_sort(linear_.begin(), linear_.end(), [&](uint32_t a, uint32_t b) { return entries_[a].offset < entries_[b].offset; });
     linearRank_.resize(entries_.size());
-    for (size_t i = 0; i < linear_.size(); i++) linearRank_[linear_[i]] = (uint32_t)i;
+#pragma omp parallel for num_threads(nth) schedule(static)
+    for (long i = 0; i < ne; i++) linearRank_[linear_[(size_t)i]] = (uint32_t)i;
     if (isCompressed) inflate(name);
 }
 
@@ -182,7 +213,7 @@ void DBReader::inflate(const std::string &name) {
         if (e.length == 0) throw std::runtime_error("Malformed index line in " + name + ".index");
         at[id + 1] = at[id] + e.length;
     }
-    std::vector<char> out((size_t)at[n]);
+    RawBuf out((size_t)at[n]);
     int bad = 0;
 #pragma omp parallel for schedule(dynamic, 256) reduction(max : bad)
     for (long id = 0; id < (long)n; id++) {

@@ -17,18 +17,34 @@
 
 #include <stdint.h>
 
+#include <memory>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace spbhost {
 
 enum { DBTYPE_AMINO_ACIDS = 0, DBTYPE_ALIGNMENT_RES = 5, DBTYPE_PREFILTER_RES = 7 };
 
+// char buffer whose resize() does not zero the new bytes (they are overwritten by a file read or by the inflater right away; the
+// zero fill of a few hundred MB was a measurable part of opening a DB)
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { typedef NoInitAlloc<U> other; };
+    NoInitAlloc() {}
+    template <class U> NoInitAlloc(const NoInitAlloc<U> &) {}
+    template <class U> void construct(U *p) { ::new ((void *)p) U; }
+    template <class U, class... A> void construct(U *p, A &&... a) { ::new ((void *)p) U(std::forward<A>(a)...); }
+};
+typedef std::vector<char, NoInitAlloc<char>> RawBuf;
+
 struct DBEntry {
     uint32_t key;
     uint64_t offset;
     uint64_t length;   // incl. the terminating NUL
+    DBEntry() {}       // (not zeroed: the reader sizes its table once and fills it from all threads -- first touch in parallel)
+    DBEntry(uint32_t k, uint64_t o, uint64_t l) : key(k), offset(o), length(l) {}
 };
 
 class DBReader {
@@ -55,7 +71,7 @@ private:
     void inflate(const std::string &name);
     std::vector<DBEntry> entries_;
     std::vector<uint32_t> linear_, linearRank_;
-    std::vector<char> data_;
+    RawBuf data_;
     uint64_t dataSize_ = 0;
     int dbtype_ = 0;
 };
