@@ -405,7 +405,7 @@ def bitscore(score, gumbel=None):
     return lib().spo_bitscore(C.byref(g), float(score))
 
 
-def align_query(m40, p, q, targets, keys, backtrace=True, max_accept=2**31 - 1, max_rejected=2**31 - 1):
+def align_query(m40, p, q, targets, keys, backtrace=True, max_accept=2**31 - 1, max_rejected=2**31 - 1, alt_ali=0):
     """Align q against each (target residues, key) in list order; returns rows sorted like Matcher::compareHits.
     --max-accept / --max-rejected (Alignment.cpp:353-404): the list is walked until max_accept pairs passed or max_rejected
     pairs IN A ROW failed (E-value, coverage, identity, length, or lengths that cannot reach the coverage)."""
@@ -421,8 +421,20 @@ def align_query(m40, p, q, targets, keys, backtrace=True, max_accept=2**31 - 1, 
         else:
             rejected += 1
         if a.ok == 1:
-            res.append((a.eval, -a.bits, len(t), key, format_row(key, a, len(q), len(t), backtrace)))
-    res.sort(key=lambda r: r[:4])
+            res.append((a.eval, -a.bits, len(t), key, format_row(key, a, len(q), len(t), backtrace), a.tStart, a.tEnd, t))
+    # --alt-ali N (Alignment::computeAlternativeAlignment, Alignment.cpp:576-611): for every result of the first pass the aligned
+    # target stretch [dbStart, dbEnd) is masked with X and the pair aligned again, up to N times while the criteria hold; every
+    # further alignment masks its own stretch too
+    for r in list(res) if alt_ali > 0 else []:
+        key, t = r[3], np.array(r[7], dtype=np.uint8, copy=True)
+        t[r[5]:r[6]] = 20
+        for _ in range(alt_ali):
+            a = align_pair(m40, p, q, t)
+            if a.ok != 1:
+                break
+            res.append((a.eval, -a.bits, len(t), key, format_row(key, a, len(q), len(t), backtrace), a.tStart, a.tEnd, t))
+            t[a.tStart:a.tEnd] = 20
+    res.sort(key=lambda r: r[:4])       # (stable; the reference's std::sort leaves the order of fully tied rows to its implementation)
     return [r[4] for r in res]
 
 

@@ -86,6 +86,7 @@ struct Params {
     std::string alphSize = "nucl:5,aa:21", taxonList;
     int maxSeqLen = 65535;
     int device = 0, binSize = 0, byteLanes = 32, wordLanes = 16;
+    bool altAliOk = false;      // set by the align module: --alt-ali N is served there (host rounds over masked target copies)
     bool targetSplitOk = false; // set by the prefilter module: --split N --split-mode 0 (the reference's own target split) is served
     int gpus = 1;              // search / predictmatch: devices device .. device + gpus - 1, k-mer table sharded over them (index split)
     int lanes = 2;             // search / predictmatch: contexts per device that share its index and overlap their batches (one host thread each)
@@ -775,7 +776,11 @@ void fill_align_params(const Params &p, const Engine &E, uint64_t dbRes, spb_ali
 
 void check_align_params(const Params &p) {
     check_unimplemented_flags(p);
-    if (p.altAli != 0 || p.realign != 0) throw Fail("--alt-ali / --realign are not supported on this path");
+    if (p.realign != 0) throw Fail("--realign is not supported on this path");
+    if (p.altAli < 0) throw Fail("Error in argument --alt-ali");
+    if (p.altAli > 0 && !p.altAliOk) throw Fail("--alt-ali is only served by the align module (not supported in the fused search)");
+    if (p.altAli > 0 && sw_mode_of(p) == 2)
+        throw Fail("--alt-ali needs start positions: not supported with the score-only alignment mode");
     if (p.seqIdThr < 0 || p.seqIdThr > 1) throw Fail("Error in argument --min-seq-id");
     if (p.covThr < 0 || p.covThr > 1) throw Fail("Error in argument -c");
     if (p.covMode < 0 || p.covMode > 5) throw Fail("Error in argument --cov-mode");
@@ -842,9 +847,160 @@ void write_alignment_rows(const Params &p, const spb_align_result *r, const SeqS
     format_alignment_rows(p, r, Q, b0, T, [&](int th, size_t i, const std::string &buf) { out.write(th, Q.keys[b0 + i], buf.data(), buf.size()); });
 }
 
+// one result row as text (Matcher::resultToBuffer) -- the row formatter of format_alignment_rows for a single row
+void format_one_row(const Params &p, const spb_aln &a, uint32_t tKey, int qLen, int tLen, const char *cigarOps, std::string &out) {
+    char tmp[256];
+    char *w = tmp;
+    w = put_uint(w, tKey); *w++ = '\t';
+    w = put_int(w, a.bits); *w++ = '\t';
+    w += seqid_to_buffer(a.seq_id, w);
+    *w++ = '\t';
+    w = put_e3(w, a.eval); *w++ = '\t';
+    w = put_int(w, a.q_start); *w++ = '\t';
+    w = put_int(w, a.q_end); *w++ = '\t';
+    w = put_int(w, qLen); *w++ = '\t';
+    w = put_int(w, a.t_start); *w++ = '\t';
+    w = put_int(w, a.t_end); *w++ = '\t';
+    w = put_int(w, tLen);
+    if (!p.addBacktrace) {
+        *w++ = '\n';
+        out.append(tmp, (size_t)(w - tmp));
+        return;
+    }
+    *w++ = '\t';
+    out.append(tmp, (size_t)(w - tmp));
+    std::string cig;
+    if (a.cigar_len) compress_cigar(cigarOps + a.cigar_off, a.cigar_len, cig);
+    out += cig;
+    out.push_back('\n');
+}
+
+// `align --alt-ali N` (Alignment::computeAlternativeAlignment, Alignment.cpp:576-611): for every result of the first pass the aligned
+// target stretch [dbStart, dbEnd) is masked with X and the pair is aligned again, up to N times while the criteria hold; every
+// further alignment masks its own stretch too.  Here the masked targets of one round form a temporary target set (one copy per
+// live result) and go through the same spb_align call, N rounds per batch; nothing changes on the device.  The rows of a query
+// are then ordered like the reference orders them: first-pass results in the order of the prefilter list, behind them the
+// alternative alignments of result 0, 1, ... in the order they were found, and std::sort with Matcher::compareHits over that
+// sequence (rows that tie in E-value, score, length and key keep the order the library's introsort gives them -- the reference
+// binary is built with the same libstdc++).
+struct AltRow { double eval; int bits; uint32_t tlen, tkey; std::string text; };
+
+void align_batch_with_alternatives(Engine &E, const Params &p, const spb_align_params &ap, const SeqSet &PQ, size_t b0, size_t b1,
+                                   const std::vector<uint64_t> &pairOff, const std::vector<uint32_t> &pairT, const SeqSet &T,
+                                   const spb_align_result *first, DBWriter &out, uint64_t *nAltRows) {
+    const size_t nq = b1 - b0;
+    // live results: one masked copy of the target each
+    struct Live { uint32_t q; uint32_t t; std::vector<uint8_t> res; size_t slot; };   // slot: index into rowsOf[q]
+    std::vector<std::vector<AltRow>> firstRows(nq);            // first pass, list order
+    std::vector<std::vector<std::vector<AltRow>>> altRows(nq); // per first-pass result: its alternatives in order
+    std::vector<Live> live;
+    for (size_t i = 0; i < nq; i++) {
+        const uint64_t a = pairOff[b0 + i] - pairOff[b0], b = pairOff[b0 + i + 1] - pairOff[b0];
+        const int qLen = (int)(PQ.off[b0 + i + 1] - PQ.off[b0 + i]);
+        // the device returns the rows sorted; the reference starts from the list order: position of every row's target in the list
+        std::vector<char> used((size_t)(b - a), 0);
+        std::vector<std::pair<uint64_t, uint64_t>> byPos;     // (list position, row index)
+        for (uint64_t k = first->offsets[i]; k < first->offsets[i + 1]; k++) {
+            uint64_t pos = b - a;
+            for (uint64_t j = 0; j < b - a; j++)
+                if (!used[(size_t)j] && pairT[pairOff[b0] + a + j] == first->rows[k].target) { pos = j; break; }
+            if (pos == b - a) throw Fail("align --alt-ali: a result row names a target that is not in the prefilter list");
+            used[(size_t)pos] = 1;
+            byPos.push_back(std::make_pair(pos, k));
+        }
+        std::sort(byPos.begin(), byPos.end());
+        altRows[i].resize(byPos.size());
+        for (size_t s0 = 0; s0 < byPos.size(); s0++) {
+            const spb_aln &r = first->rows[byPos[s0].second];
+            const uint32_t t = r.target;
+            const int tLen = (int)(T.off[t + 1] - T.off[t]);
+            AltRow row{r.eval, r.bits, (uint32_t)tLen, T.keys[t], std::string()};
+            format_one_row(p, r, T.keys[t], qLen, tLen, first->cigar_ops, row.text);
+            firstRows[i].push_back(std::move(row));
+            Live l;
+            l.q = (uint32_t)i; l.t = t; l.slot = s0;
+            l.res.assign(T.res.begin() + (long)T.off[t], T.res.begin() + (long)T.off[t + 1]);
+            for (int x = std::max(r.t_start, 0); x < r.t_end && x < tLen; x++) l.res[(size_t)x] = 20;      // [dbStart, dbEnd): X
+            live.push_back(std::move(l));
+        }
+    }
+    spb_align_params ap2 = ap;
+    ap2.max_accept = 0;          // the limits of the list walk do not apply to the alternatives
+    ap2.max_rejected = 0;
+    for (int round = 0; round < p.altAli && !live.empty(); round++) {
+        // temporary target set = the masked copies, in the order of `live` (grouped by query, ascending)
+        std::vector<uint8_t> tres;
+        std::vector<uint64_t> toff(1, 0);
+        std::vector<uint32_t> tkeys;
+        std::vector<uint64_t> po(nq + 1, 0);
+        std::vector<uint32_t> pt;
+        for (size_t k = 0; k < live.size(); k++) {
+            tres.insert(tres.end(), live[k].res.begin(), live[k].res.end());
+            toff.push_back(tres.size());
+            tkeys.push_back(T.keys[live[k].t]);
+            po[live[k].q + 1]++;
+            pt.push_back((uint32_t)k);
+        }
+        tres.push_back(0);
+        for (size_t i = 0; i < nq; i++) po[i + 1] += po[i];
+        std::vector<uint64_t> qo(nq + 1);
+        for (size_t i = 0; i <= nq; i++) qo[i] = PQ.off[b0 + i] - PQ.off[b0];
+        check(spb_align_set_targets(E.ctx, tres.data(), toff.data(), (uint32_t)live.size(), tkeys.data()), "spb_align_set_targets");
+        spb_align_result *r = nullptr;
+        check(spb_align(E.ctx, PQ.res.data() + PQ.off[b0], qo.data(), (uint32_t)nq, po.data(), pt.data(), &ap2, &r), "spb_align");
+        std::vector<char> passed(live.size(), 0);
+        for (size_t i = 0; i < nq; i++) {
+            const int qLen = (int)(PQ.off[b0 + i + 1] - PQ.off[b0 + i]);
+            for (uint64_t k = r->offsets[i]; k < r->offsets[i + 1]; k++) {
+                const spb_aln &a = r->rows[k];
+                Live &l = live[a.target];
+                const int tLen = (int)l.res.size();
+                AltRow row{a.eval, a.bits, (uint32_t)tLen, T.keys[l.t], std::string()};
+                format_one_row(p, a, T.keys[l.t], qLen, tLen, r->cigar_ops, row.text);
+                altRows[i][l.slot].push_back(std::move(row));
+                for (int x = std::max(a.t_start, 0); x < a.t_end && x < tLen; x++) l.res[(size_t)x] = 20;
+                passed[a.target] = 1;
+                (*nAltRows)++;
+            }
+        }
+        spb_free_align_result(r);
+        std::vector<Live> next;
+        for (size_t k = 0; k < live.size(); k++)
+            if (passed[k]) next.push_back(std::move(live[k]));
+        live.swap(next);
+    }
+    // the original targets back for the next batch
+    check(spb_align_set_targets(E.ctx, T.res.data(), T.off.data(), (uint32_t)T.keys.size(), T.keys.data()), "spb_align_set_targets");
+#pragma omp parallel num_threads(p.threads)
+    {
+        int th = 0;
+#ifdef _OPENMP
+        th = omp_get_thread_num();
+#endif
+#pragma omp for schedule(static)
+        for (long i = 0; i < (long)nq; i++) {
+            std::vector<AltRow> all;
+            for (AltRow &r : firstRows[(size_t)i]) all.push_back(std::move(r));
+            for (std::vector<AltRow> &v : altRows[(size_t)i])
+                for (AltRow &r : v) all.push_back(std::move(r));
+            if (all.size() > 1)
+                std::sort(all.begin(), all.end(), [](const AltRow &x, const AltRow &y) {      // Matcher::compareHits
+                    if (x.eval != y.eval) return x.eval < y.eval;
+                    if (x.bits != y.bits) return x.bits > y.bits;
+                    if (x.tlen != y.tlen) return x.tlen < y.tlen;
+                    return x.tkey < y.tkey;
+                });
+            std::string buf;
+            for (const AltRow &r : all) buf += r.text;
+            out.write(th, PQ.keys[b0 + (size_t)i], buf.data(), buf.size());
+        }
+    }
+}
+
 int run_align(int argc, const char **argv) {
     Params p;
     parse_args(argc, argv, 2, 4, p);
+    p.altAliOk = true;
     check_align_params(p);
     Engine E;
     E.open(p);
@@ -891,7 +1047,7 @@ int run_align(int argc, const char **argv) {
     PQ.res.push_back(0);
     DBWriter out;
     out.open(p.db[3], DBTYPE_ALIGNMENT_RES, p.threads);
-    uint64_t nRows = 0, nCells = 0;
+    uint64_t nRows = 0, nCells = 0, nAlt = 0;
     double kernelMs = 0;
     for (size_t b0 = 0, b1 = 0; b0 < np; b0 = b1) {
         b1 = std::min(np, b0 + (size_t)p.batch);
@@ -904,12 +1060,14 @@ int run_align(int argc, const char **argv) {
         nRows += r->n_rows;
         nCells += r->n_cells;
         kernelMs += r->kernel_ms;
-        write_alignment_rows(p, r, PQ, b0, T, out);
+        if (p.altAli > 0) align_batch_with_alternatives(E, p, ap, PQ, b0, b1, pairOff, pairT, T, r, out, &nAlt);
+        else write_alignment_rows(p, r, PQ, b0, T, out);
         spb_free_align_result(r);
     }
     out.close();
     log_line(p, "%llu alignments accepted of %zu pairs; %.2f GCUPS in the forward kernels", (unsigned long long)nRows, pairT.size(),
              kernelMs > 0 ? (double)nCells / kernelMs / 1e6 : 0.0);
+    if (p.altAli > 0) log_line(p, "%llu alternative alignments (--alt-ali %d)", (unsigned long long)nAlt, p.altAli);
     return 0;
 }
 
@@ -1698,6 +1856,7 @@ int run_showparams(int argc, const char **argv) {
     Params p;
     parse_args(argc, argv, 3, mod == "align" ? 4 : 3, p);
     p.targetSplitOk = (mod == "prefilter");
+    p.altAliOk = (mod == "align");
     if (mod == "align") check_align_params(p); else check_search_params(p);
     printf("sub_mat=%s seed_sub_mat=%s kmer_thr=%d max_seqs=%d min_ungapped=%d mask=%d comp_bias=%d pattern=%s "
            "evalue=%g gap_open=%s gap_extend=%s threads=%d cov=%g cov_mode=%d min_seq_id=%g min_aln_len=%d seq_id_mode=%d backtrace=%d sw_mode=%d\n",

@@ -289,3 +289,25 @@ def test_max_accept_max_rejected_flags(tmp_path, tag):
                 merged += [lst[i], lst[i + 1]]
     run("search", w + "/qdb", w + "/tdb", w + "/fused", *merged)
     assert {k: v for k, v in entries_as_rows(w + "/fused").items() if v} == ref
+
+
+@pytest.mark.parametrize("tag", ["small_alt2", "long_alt3", "long_alt2_c0.5_m2"])
+def test_alternative_alignments_flag(tmp_path, tag):
+    """`spb200 align --alt-ali N` writes the reference binary's alignment DB byte for byte -- including the order of rows that tie in
+    every sort field, which is whatever std::sort makes of the reference's initial order (first-pass results in list order, then
+    the alternatives of result 0, 1, ...)"""
+    import json
+    c = json.load(open(os.path.join(GOLDEN, "criteria", "alt_ali.json")))[tag]
+    w = _long_set_dbs(tmp_path, c["set"])
+    if c["set"] == "small":       # the all-pairs subset of tools/gen_golden.py: every third target for the first 40 queries
+        nt, nq = len(dbio.read_entries(w + "/tdb")), len(dbio.read_entries(w + "/qdb"))
+        body = b"".join(b"%d\t0\t0\n" % t for t in range(0, nt, 3))
+        dbio.write_db(w + "/allpairs", ((q, body if q < 40 else b"") for q in range(nq)), dbio.DBTYPE_PREFILTER_RES)
+    over = {"-e": c["evalue"], "-c": c["cov"], "--cov-mode": c["cov_mode"], "--alt-ali": c["alt_ali"]}
+    r = run("align", w + "/qdb", w + "/tdb", w + "/allpairs", w + "/aln", *_with(ALN_FLAGS, **over), "--batch", "25")
+    assert "alternative alignments" in r.stdout
+    got = {k: v for k, v in entries_as_rows(w + "/aln").items() if v}
+    assert got == read_dump(os.path.join(GOLDEN, "criteria", tag + ".txt.gz"))
+    # the fused search does not take the flag
+    r = subprocess.run([BIN, "search", w + "/qdb", w + "/tdb", w + "/x", "--alt-ali", "1", "-a", "1"], capture_output=True, text=True)
+    assert r.returncode == 1 and "only served by the align module" in r.stderr

@@ -12,6 +12,7 @@
                                              --mask-lower-case 1 (IndexBuilder.cpp:151-160)
   tests/golden/criteria/pref_family_split3_max20, pref_small_split2_max100  lists of the reference's own target split (--split N --split-mode 0)
   tests/golden/criteria/family_acc* / family_rej*, limits.json  --max-accept / --max-rejected on the `family` set (Alignment.cpp:353-404)
+  tests/golden/criteria/*_alt*, alt_ali.json  alternative alignments (--alt-ali N, Alignment.cpp:576-611)
   tests/golden/criteria/cases.json           the flag set of every alignment fixture
 Usage: python tools/gen_golden_criteria.py
 """
@@ -208,6 +209,17 @@ def main():
         run("%s align %s/qdb %s/tdb %s/pref300 %s/aln_%s %s" % (B, w, w, w, w, tag, f))
         dump_db(os.path.join(w, "aln_" + tag), os.path.join(out, tag + ".txt.gz"))
         limits[tag] = dict(max_accept=acc, max_rejected=rej, min_seq_id=sid, evalue=float(ev))
+    # --alt-ali N (Alignment::computeAlternativeAlignment, Alignment.cpp:576-611)
+    alts = {}
+    for tag, name, n, ev, cov, mode in (("small_alt2", "small", 2, "200", 0.0, 0), ("long_alt3", "long", 3, "1.000E-01", 0.0, 0),
+                                        ("long_alt2_c0.5_m2", "long", 2, "1.000E-01", 0.5, 2)):
+        w = os.path.join(work, name)
+        f = aln_flags(ev, cov, mode, 0.0, 0, 1, 0).replace("--alt-ali 0", "--alt-ali %d" % n)
+        run("%s align %s/qdb %s/tdb %s/allpairs %s/aln_%s %s" % (B, w, w, w, w, tag, f))
+        dump_db(os.path.join(w, "aln_" + tag), os.path.join(out, tag + ".txt.gz"))
+        alts[tag] = dict(set=name, alt_ali=n, evalue=float(ev), cov=cov, cov_mode=mode)
+    with open(os.path.join(out, "alt_ali.json"), "w") as f:
+        json.dump(alts, f, indent=1)
     with open(os.path.join(out, "limits.json"), "w") as f:
         json.dump(limits, f, indent=1)
     with open(os.path.join(out, "cases.json"), "w") as f:
