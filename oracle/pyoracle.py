@@ -438,6 +438,49 @@ def align_query(m40, p, q, targets, keys, backtrace=True, max_accept=2**31 - 1, 
     return [r[4] for r in res]
 
 
+def has_coverage(cov, cov_mode, q_cov, t_cov):
+    """Util::hasCoverage (M/commons/Util.cpp:552-567) on float32 coverages"""
+    cov, q_cov, t_cov = np.float32(cov), np.float32(q_cov), np.float32(t_cov)
+    if cov_mode == 0:
+        return bool(q_cov >= cov and t_cov >= cov)
+    if cov_mode == 1:
+        return bool(t_cov >= cov)
+    if cov_mode == 2:
+        return bool(q_cov >= cov)
+    return True
+
+
+def align_query_realign(m40, m40_realign, db_res_count, q, targets, keys, eval_thr=200.0, cov=0.0, cov_mode=0, min_seq_id=0.0,
+                        min_aln_len=0, realign_max_seqs=2**31 - 1, gap_open=16, gap_extend=2):
+    """--realign 1 (Alignment.cpp:47-56,415-447): first pass SCORE ONLY with the alignment matrix (coverage threshold off, the length
+    pre-check of canBeCovered on), results sorted like Matcher::compareHits; second pass, in that order and for at most
+    realign_max_seqs results: the full alignment with the REALIGN matrix (score bias + --realign-score-bias) without E-value limit,
+    kept when its coverage reaches -c; the row carries the boundaries, identity and backtrace of the second pass and the score and
+    E-value of the first."""
+    p1 = align_params(db_res_count, gap_open, gap_extend, eval_thr, min_seq_id=min_seq_id, min_aln_len=min_aln_len, sw_mode=2)
+    p2 = align_params(db_res_count, gap_open, gap_extend, 3.4028234663852886e38)
+    first = []
+    for t, key in zip(targets, keys):
+        if not can_be_covered(cov, cov_mode, len(q), len(t)):
+            continue
+        a = align_pair(m40, p1, q, t)
+        if a.ok == 1:
+            first.append((a.eval, -a.bits, len(t), key, t, a.bits))
+    first.sort(key=lambda r: r[:4])
+    res = []
+    for ev, _, tlen, key, t, bits in first:
+        if len(res) >= realign_max_seqs:
+            break
+        a = align_pair(m40_realign, p2, q, t)
+        q_cov = np.float32(a.qEnd - a.qStart + 1) / np.float32(len(q))
+        t_cov = np.float32(a.tEnd - a.tStart + 1) / np.float32(tlen)
+        if has_coverage(cov, cov_mode, q_cov, t_cov):
+            a.bits, a.eval = bits, ev
+            res.append((ev, -bits, tlen, key, format_row(key, a, len(q), tlen)))
+    res.sort(key=lambda r: r[:4])
+    return [r[4] for r in res]
+
+
 ALN_ROW = np.dtype([("ok", "<i4"), ("score", "<i4"), ("bits", "<i4"), ("_pad", "<i4"), ("eval", "<f8"),
                     ("q_start", "<i4"), ("q_end", "<i4"), ("t_start", "<i4"), ("t_end", "<i4"),
                     ("n_ident", "<i4"), ("aln_len", "<i4")])

@@ -26,6 +26,7 @@
 // Host-only helpers used by the CPU tests: dumpmatrix, dbcopy, showparams.
 // Errors follow the reference: message on stderr, exit code 1 (Debug(Debug::ERROR) ... EXIT(EXIT_FAILURE)).
 #include <ctype.h>
+#include <float.h>
 #include <limits.h>
 #include <math.h>
 #include <stdarg.h>
@@ -78,7 +79,8 @@ struct Params {
     int addBacktrace = 0, alignmentMode = 0, altAli = 0, realign = 0, seqIdMode = 0, alnLenThr = 0;
     int maxRejected = INT_MAX, maxAccept = INT_MAX;
     std::string gapOpen = "nucl:5,aa:11", gapExtend = "nucl:2,aa:1";
-    double scoreBias = 0.0;
+    double scoreBias = 0.0, realignScoreBias = -0.2;
+    int realignMaxSeqs = INT_MAX;
     int threads = 1, verbosity = 3, compressed = 0;
     // spb200-specific
     // flags whose non-default values would change the reference's result but are not implemented: parsed so that they can be
@@ -86,6 +88,7 @@ struct Params {
     std::string alphSize = "nucl:5,aa:21", taxonList;
     int maxSeqLen = 65535;
     int device = 0, binSize = 0, byteLanes = 32, wordLanes = 16;
+    bool realignOk = false;     // set by the align module: --realign 1 is served there (two passes over the same spb_align call)
     bool altAliOk = false;      // set by the align module: --alt-ali N is served there (host rounds over masked target copies)
     bool targetSplitOk = false; // set by the prefilter module: --split N --split-mode 0 (the reference's own target split) is served
     int gpus = 1;              // search / predictmatch: devices device .. device + gpus - 1, k-mer table sharded over them (index split)
@@ -122,7 +125,7 @@ std::vector<FlagDef> flag_table(Params &p) {
         // accepted and without influence on this path (profile / nucleotide / memory-management flags of the same modules)
         {"--alph-size", 3, &p.alphSize}, {"--max-seq-len", 0, &p.maxSeqLen}, {"--split-memory-limit", 4, nullptr},
         {"--db-load-mode", 4, nullptr}, {"--pca", 4, nullptr}, {"--pcb", 4, nullptr}, {"--alignment-output-mode", 4, nullptr},
-        {"--wrapped-scoring", 4, nullptr}, {"--realign-score-bias", 4, nullptr}, {"--realign-max-seqs", 4, nullptr},
+        {"--wrapped-scoring", 4, nullptr}, {"--realign-score-bias", 2, &p.realignScoreBias}, {"--realign-max-seqs", 0, &p.realignMaxSeqs},
         {"--zdrop", 4, nullptr}, {"--local-tmp", 4, nullptr}, {"--taxon-list", 3, &p.taxonList}, {"--exhaustive-search-filter", 4, nullptr},
         {"--exhaustive-search", 0, &p.exhaustive},
         {"--simple-best-hit", 0, &p.simpleBestHit}, {"--fdr", 1, &p.fdr}, {"--report-fdr", 0, &p.reportFdr},
@@ -776,7 +779,11 @@ void fill_align_params(const Params &p, const Engine &E, uint64_t dbRes, spb_ali
 
 void check_align_params(const Params &p) {
     check_unimplemented_flags(p);
-    if (p.realign != 0) throw Fail("--realign is not supported on this path");
+    if (p.realign != 0 && p.realign != 1) throw Fail("Error in argument --realign");
+    if (p.realign && !p.realignOk) throw Fail("--realign is only served by the align module (not supported in the fused search)");
+    if (p.realign && (p.altAli > 0 || p.maxRejected != INT_MAX || p.maxAccept != INT_MAX))
+        throw Fail("--realign together with --alt-ali / --max-accept / --max-rejected is not supported");
+    if (p.realign && p.realignMaxSeqs < 1) throw Fail("Error in argument --realign-max-seqs");
     if (p.altAli < 0) throw Fail("Error in argument --alt-ali");
     if (p.altAli > 0 && !p.altAliOk) throw Fail("--alt-ali is only served by the align module (not supported in the fused search)");
     if (p.altAli > 0 && sw_mode_of(p) == 2)
@@ -997,10 +1004,94 @@ void align_batch_with_alternatives(Engine &E, const Params &p, const spb_align_p
     }
 }
 
+// `align --realign 1` (Alignment.cpp:47-56,415-447): the first pass only scores (SCORE_ONLY, coverage threshold off, the length
+// pre-check of canBeCovered on) and is sorted like Matcher::compareHits; the second pass aligns the survivors in that order with the
+// REALIGN matrix (score bias + --realign-score-bias; its own composition-bias profile), without E-value limit, keeps those whose
+// coverage reaches -c (at most --realign-max-seqs of them) and reports their boundaries, identity and backtrace with the score and
+// E-value of the first pass.  Both passes are the same spb_align call; the matrices are swapped in between.
+void align_batch_realign(Engine &E, const Params &p, const spb_align_params &ap, const SubMat &realignMat, const SeqSet &PQ, size_t b0,
+                         size_t b1, const std::vector<uint64_t> &pairOff, const std::vector<uint32_t> &pairT, const SeqSet &T,
+                         DBWriter &out, uint64_t *nRows, uint64_t *nCells, double *kernelMs) {
+    const size_t nq = b1 - b0;
+    std::vector<uint64_t> qo(nq + 1), po(nq + 1, 0);
+    std::vector<uint32_t> pt;
+    for (size_t i = 0; i <= nq; i++) qo[i] = PQ.off[b0 + i] - PQ.off[b0];
+    for (size_t i = 0; i < nq; i++) {      // Util::canBeCovered with the real -c before the first pass (Alignment.cpp:378)
+        const float qLen = (float)(qo[i + 1] - qo[i]);
+        for (uint64_t k = pairOff[b0 + i]; k < pairOff[b0 + i + 1]; k++) {
+            const uint32_t t = pairT[k];
+            if (can_be_covered((float)p.covThr, p.covMode, qLen, (float)(T.off[t + 1] - T.off[t]))) pt.push_back(t);
+        }
+        po[i + 1] = pt.size();
+    }
+    spb_align_params ap1 = ap;
+    ap1.sw_mode = 2;
+    ap1.cov_thr = 0.0f;
+    ap1.cov_mode = 0;
+    spb_align_result *r1 = nullptr;
+    check(spb_align(E.ctx, PQ.res.data() + PQ.off[b0], qo.data(), (uint32_t)nq, po.data(), pt.data(), &ap1, &r1), "spb_align");
+    *nCells += r1->n_cells;
+    *kernelMs += r1->kernel_ms;
+    // second pass: the rows of the first, in their order
+    std::vector<uint64_t> po2(nq + 1, 0);
+    std::vector<uint32_t> pt2((size_t)r1->n_rows);
+    for (size_t i = 0; i < nq; i++) {
+        for (uint64_t k = r1->offsets[i]; k < r1->offsets[i + 1]; k++) pt2[(size_t)k] = r1->rows[k].target;
+        po2[i + 1] = r1->offsets[i + 1];
+    }
+    spb_align_params ap2 = ap;
+    ap2.sw_mode = 0;
+    ap2.eval_thr = (double)FLT_MAX;
+    ap2.seq_id_thr = 0.0f;
+    ap2.aln_len_thr = 0;
+    ap2.max_accept = p.realignMaxSeqs;      // (INT_MAX: no limit) at most that many results pass, walked in the first pass's order
+    ap2.max_rejected = 0;
+    const bool swap = p.realignScoreBias != 0.0;
+    if (swap) check(spb_set_matrices(E.ctx, E.seed.sub, E.seed.pback, E.ungapped.sub, realignMat.sub, realignMat.pback), "spb_set_matrices");
+    spb_align_result *r2 = nullptr;
+    check(spb_align(E.ctx, PQ.res.data() + PQ.off[b0], qo.data(), (uint32_t)nq, po2.data(), pt2.data(), &ap2, &r2), "spb_align");
+    if (swap) check(spb_set_matrices(E.ctx, E.seed.sub, E.seed.pback, E.ungapped.sub, E.align.sub, E.align.pback), "spb_set_matrices");
+    *nCells += r2->n_cells;
+    *kernelMs += r2->kernel_ms;
+    uint64_t rows = 0;
+#pragma omp parallel num_threads(p.threads) reduction(+ : rows)
+    {
+        int th = 0;
+#ifdef _OPENMP
+        th = omp_get_thread_num();
+#endif
+        std::string buf;
+#pragma omp for schedule(static)
+        for (long i = 0; i < (long)nq; i++) {
+            buf.clear();
+            const int qLen = (int)(qo[(size_t)i + 1] - qo[(size_t)i]);
+            std::vector<char> used((size_t)(r2->offsets[i + 1] - r2->offsets[i]), 0);
+            for (uint64_t k = r1->offsets[i]; k < r1->offsets[i + 1]; k++) {      // first-pass order = the order of the result
+                const spb_aln &f = r1->rows[k];
+                for (uint64_t j = r2->offsets[i]; j < r2->offsets[i + 1]; j++) {
+                    if (used[(size_t)(j - r2->offsets[i])] || r2->rows[j].target != f.target) continue;
+                    used[(size_t)(j - r2->offsets[i])] = 1;
+                    spb_aln a = r2->rows[j];
+                    a.bits = f.bits;             // res.score / res.eval of the first pass (Alignment.cpp:433-434)
+                    a.eval = f.eval;
+                    format_one_row(p, a, T.keys[a.target], qLen, (int)(T.off[a.target + 1] - T.off[a.target]), r2->cigar_ops, buf);
+                    rows++;
+                    break;
+                }
+            }
+            out.write(th, PQ.keys[b0 + (size_t)i], buf.data(), buf.size());
+        }
+    }
+    *nRows += rows;
+    spb_free_align_result(r1);
+    spb_free_align_result(r2);
+}
+
 int run_align(int argc, const char **argv) {
     Params p;
     parse_args(argc, argv, 2, 4, p);
     p.altAliOk = true;
+    p.realignOk = true;
     check_align_params(p);
     Engine E;
     E.open(p);
@@ -1049,11 +1140,21 @@ int run_align(int argc, const char **argv) {
     out.open(p.db[3], DBTYPE_ALIGNMENT_RES, p.threads);
     uint64_t nRows = 0, nCells = 0, nAlt = 0;
     double kernelMs = 0;
+    SubMat realignMat;
+    if (p.realign) {
+        // -a is switched on for a realignment (Alignment.cpp:52-55); the matrix of the second pass (Alignment.cpp:164-170)
+        p.addBacktrace = 1;
+        realignMat.load(p.subMat, 2.0, p.scoreBias + p.realignScoreBias);
+    }
     for (size_t b0 = 0, b1 = 0; b0 < np; b0 = b1) {
         b1 = std::min(np, b0 + (size_t)p.batch);
         while (b1 > b0 + 1 && pairOff[b1] - pairOff[b0] > 0x7FFFFFF0ull) b1 = b0 + (b1 - b0) / 2;
         std::vector<uint64_t> qo(b1 - b0 + 1), po(b1 - b0 + 1);
         for (size_t i = b0; i <= b1; i++) { qo[i - b0] = PQ.off[i] - PQ.off[b0]; po[i - b0] = pairOff[i] - pairOff[b0]; }
+        if (p.realign) {
+            align_batch_realign(E, p, ap, realignMat, PQ, b0, b1, pairOff, pairT, T, out, &nRows, &nCells, &kernelMs);
+            continue;
+        }
         spb_align_result *r = nullptr;
         check(spb_align(E.ctx, PQ.res.data() + PQ.off[b0], qo.data(), (uint32_t)(b1 - b0), po.data(), pairT.data() + pairOff[b0], &ap, &r),
               "spb_align");
@@ -1857,6 +1958,7 @@ int run_showparams(int argc, const char **argv) {
     parse_args(argc, argv, 3, mod == "align" ? 4 : 3, p);
     p.targetSplitOk = (mod == "prefilter");
     p.altAliOk = (mod == "align");
+    p.realignOk = (mod == "align");
     if (mod == "align") check_align_params(p); else check_search_params(p);
     printf("sub_mat=%s seed_sub_mat=%s kmer_thr=%d max_seqs=%d min_ungapped=%d mask=%d comp_bias=%d pattern=%s "
            "evalue=%g gap_open=%s gap_extend=%s threads=%d cov=%g cov_mode=%d min_seq_id=%g min_aln_len=%d seq_id_mode=%d backtrace=%d sw_mode=%d\n",

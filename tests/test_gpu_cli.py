@@ -311,3 +311,21 @@ def test_alternative_alignments_flag(tmp_path, tag):
     # the fused search does not take the flag
     r = subprocess.run([BIN, "search", w + "/qdb", w + "/tdb", w + "/x", "--alt-ali", "1", "-a", "1"], capture_output=True, text=True)
     assert r.returncode == 1 and "only served by the align module" in r.stderr
+
+
+@pytest.mark.parametrize("tag", ["small_realign_b0.6", "long_realign_b1.0", "long_realign_b1.0_c0.5_m2_max3", "long_realign_b0.2"])
+def test_realign_flag(tmp_path, tag):
+    """`spb200 align --realign 1` (two passes over the same spb_align call, matrices swapped in between) writes the reference binary's
+    alignment DB"""
+    import json
+    c = json.load(open(os.path.join(GOLDEN, "criteria", "realign.json")))[tag]
+    w = _long_set_dbs(tmp_path, c["set"])
+    if c["set"] == "small":
+        nt, nq = len(dbio.read_entries(w + "/tdb")), len(dbio.read_entries(w + "/qdb"))
+        body = b"".join(b"%d\t0\t0\n" % t for t in range(0, nt, 3))
+        dbio.write_db(w + "/allpairs", ((q, body if q < 40 else b"") for q in range(nq)), dbio.DBTYPE_PREFILTER_RES)
+    over = {"-e": c["evalue"], "-c": c["cov"], "--cov-mode": c["cov_mode"], "--realign": 1, "--realign-score-bias": c["realign_score_bias"],
+            "--realign-max-seqs": c["realign_max_seqs"]}
+    run("align", w + "/qdb", w + "/tdb", w + "/allpairs", w + "/aln", *_with(ALN_FLAGS, **over), "--batch", "30")
+    got = {k: v for k, v in entries_as_rows(w + "/aln").items() if v}
+    assert got == read_dump(os.path.join(GOLDEN, "criteria", tag + ".txt.gz"))

@@ -208,8 +208,11 @@ def test_split_flags():
 def test_errors_like_the_reference():
     r = run("prefilter", "q", "t", "p", "--no-such-flag", "1", ok=False)
     assert r.returncode == 1 and "Unrecognized parameter" in r.stderr
-    r = run("showparams", "align", "q", "t", "p", "a", "--realign", "1", "-a", "1", ok=False)
+    run("showparams", "align", "q", "t", "p", "a", "--realign", "1", "-a", "1", "--realign-score-bias", "-0.5", "--realign-max-seqs", "4")
+    r = run("showparams", "align", "q", "t", "p", "a", "--realign", "1", "--alt-ali", "2", "-a", "1", ok=False)
     assert r.returncode == 1 and "not supported" in r.stderr
+    r = run("search", "q", "t", "o", "--realign", "1", "-a", "1", ok=False)
+    assert r.returncode == 1 and "only served by the align module" in r.stderr
     run("showparams", "align", "q", "t", "p", "a", "--alt-ali", "3", "-a", "1")
     r = run("showparams", "align", "q", "t", "p", "a", "--alt-ali", "3", "--alignment-mode", "1", ok=False)
     assert r.returncode == 1 and "start positions" in r.stderr

@@ -13,6 +13,7 @@
   tests/golden/criteria/pref_family_split3_max20, pref_small_split2_max100  lists of the reference's own target split (--split N --split-mode 0)
   tests/golden/criteria/family_acc* / family_rej*, limits.json  --max-accept / --max-rejected on the `family` set (Alignment.cpp:353-404)
   tests/golden/criteria/*_alt*, alt_ali.json  alternative alignments (--alt-ali N, Alignment.cpp:576-611)
+  tests/golden/criteria/*_realign_*, realign.json  --realign 1 with --realign-score-bias / --realign-max-seqs (Alignment.cpp:415-447)
   tests/golden/criteria/cases.json           the flag set of every alignment fixture
 Usage: python tools/gen_golden_criteria.py
 """
@@ -220,6 +221,21 @@ def main():
         alts[tag] = dict(set=name, alt_ali=n, evalue=float(ev), cov=cov, cov_mode=mode)
     with open(os.path.join(out, "alt_ali.json"), "w") as f:
         json.dump(alts, f, indent=1)
+    # --realign 1 (Alignment.cpp:47-56,415-447): score-only first pass, second pass with the realign matrix
+    realign = {}
+    for tag, name, bias, ev, cov, mode, mx in (("small_realign_b0.6", "small", -0.6, "200", 0.0, 0, 2147483647),
+                                               ("long_realign_b1.0", "long", -1.0, "1.000E-01", 0.0, 0, 2147483647),
+                                               ("long_realign_b1.0_c0.5_m2_max3", "long", -1.0, "1.000E-01", 0.5, 2, 3),
+                                               ("long_realign_b0.2", "long", -0.2, "1.000E-01", 0.3, 0, 2147483647)):
+        w = os.path.join(work, name)
+        f = aln_flags(ev, cov, mode, 0.0, 0, 1, 0).replace("--realign 0 --realign-score-bias -0.2 --realign-max-seqs 2147483647",
+                                                          "--realign 1 --realign-score-bias %g --realign-max-seqs %d" % (bias, mx))
+        assert "--realign 1" in f
+        run("%s align %s/qdb %s/tdb %s/allpairs %s/aln_%s %s" % (B, w, w, w, w, tag, f))
+        dump_db(os.path.join(w, "aln_" + tag), os.path.join(out, tag + ".txt.gz"))
+        realign[tag] = dict(set=name, realign_score_bias=bias, evalue=float(ev), cov=cov, cov_mode=mode, realign_max_seqs=mx)
+    with open(os.path.join(out, "realign.json"), "w") as f:
+        json.dump(realign, f, indent=1)
     with open(os.path.join(out, "limits.json"), "w") as f:
         json.dump(limits, f, indent=1)
     with open(os.path.join(out, "cases.json"), "w") as f:
